@@ -1,0 +1,856 @@
+// abi.cu -- the C ABI declared in include/swpc3d_b200.h: device state, uploads, kernel launches and
+// the halo exchange (NCCL send/recv or single-process emulation).  No torch types, no CPU fallback:
+// every entry point fails loudly when CUDA is not usable.
+#include "../../include/swpc3d_b200.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+using namespace swpc;
+
+static thread_local std::string g_err;
+extern "C" const char *swpc3d_last_error(void) { return g_err.c_str(); }
+extern "C" const char *swpc3d_version(void) { return "swpc3d_b200 0.1 (reference: OpenSWPC 25.05.2 swpc_3d)"; }
+
+static int fail(const std::string &m) {
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char b_[512];                                                                                \
+            snprintf(b_, sizeof(b_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return fail(b_);                                                                             \
+        }                                                                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use has no NCCL dependency
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(std::string("cannot dlopen libnccl.so.2: ") + dlerror());
+#define SYM(f, s)                                                         \
+    *(void **)(&g_nccl.f) = dlsym(g_nccl.lib, s);                         \
+    if (!g_nccl.f) return fail(std::string("libnccl: missing symbol ") + s);
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    return 0;
+}
+#define NK(call)                                                                                       \
+    do {                                                                                               \
+        ncclResult_t r_ = (call);                                                                      \
+        if (r_ != ncclSuccess) {                                                                       \
+            char b_[512];                                                                              \
+            snprintf(b_, sizeof(b_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+            return fail(b_);                                                                           \
+        }                                                                                              \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+struct swpc3d_handle {
+    swpc3d_grid g{};
+    int dev = 0;
+    int nxp = 0, nyp = 0, NZP = 0, NXM = 0, NYM = 0;
+    int nzm_h = 0;                         // host k extent (nz + 6 + kpad)
+    long long ncell = 0;
+    int fb = 8;                            // field bytes
+    int nm = 0;
+    void *F[9] = {};                       // Vx Vy Vz Sxx Syy Szz Syz Sxz Sxy
+    float *R = nullptr;
+    float *med[5] = {};                    // rho lam mu taup taus
+    int4 *band = nullptr;
+    int *kbeg_a = nullptr, *kob = nullptr;
+    std::vector<int> h_kbeg_a;
+    long long *aoff = nullptr;
+    float *aux = nullptr;
+    long long naux = 0;
+    float4 *g4[6] = {};                    // gxc gxe gyc gye gzc gze
+    float *cg[6] = {};                     // cerjan gx_c gx_b gy_c gy_b gz_c gz_b
+    bool absorber_ready = false, medium_ready = false;
+    // coefficients
+    double r40[6][2] = {};                 // x40 x41 y40 y41 z40 z41, in F precision but stored as double
+    double r20[3] = {};
+    float c1[MAXNM] = {}, c2[MAXNM] = {}, d1[MAXNM] = {}, d2 = 0.f;
+    // sources
+    int nsrc = 0, stf = 3, bf_mode = 0;
+    float tbeg = 0.f;
+    int *src_ijk = nullptr;
+    double *src_mo = nullptr, *src_mij = nullptr;
+    float *src_prm = nullptr, *src_stime = nullptr;
+    std::vector<float> h_prm;
+    double dt_dxyz = 0;
+    // stations
+    int nst = 0, ntdec_w = 0, ntw = 0;
+    int *st_ijk = nullptr;
+    float *wav = nullptr;
+    float M0 = 1.f, UC = 1e-15f;
+    unsigned int *vmax_d = nullptr;
+    // halo
+    void *sbuf[4] = {}, *rbuf[4] = {};     // 0: +x (ip) 1: -x (im) 2: +y (jp) 3: -y (jm)
+    int nbr[4] = {-1, -1, -1, -1};
+    ncclComm_t comm = nullptr;
+    int comm_rank = -1, comm_size = 0;
+    // streams
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // tuning
+    int tk = 128, ti = 2, jlen = 32;
+    int variant = 1;
+    long long launches = 0;
+};
+
+static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
+
+template <typename F>
+static KParams<F> make_params(const swpc3d_handle *h) {
+    KParams<F> p{};
+    const swpc3d_grid &g = h->g;
+    p.nz = g.nz; p.nxp = h->nxp; p.nyp = h->nyp;
+    p.NZP = h->NZP; p.NXM = h->NXM; p.NYM = h->NYM;
+    p.SI = h->NZP; p.SJ = (long long)h->NZP * h->NXM;
+    p.ncell = h->ncell;
+    p.li0_k = g.ibeg_k - g.ibeg; p.li1_k = g.iend_k - g.ibeg;
+    p.lj0_k = g.jbeg_k - g.jbeg; p.lj1_k = g.jend_k - g.jbeg;
+    p.k1_k = g.kend_k;
+    p.abc = g.abc_type;
+    p.Vx = (F *)h->F[0]; p.Vy = (F *)h->F[1]; p.Vz = (F *)h->F[2];
+    p.Sxx = (F *)h->F[3]; p.Syy = (F *)h->F[4]; p.Szz = (F *)h->F[5];
+    p.Syz = (F *)h->F[6]; p.Sxz = (F *)h->F[7]; p.Sxy = (F *)h->F[8];
+    p.R = h->R;
+    p.rho = h->med[0]; p.lam = h->med[1]; p.mu = h->med[2]; p.taup = h->med[3]; p.taus = h->med[4];
+    p.band = h->band; p.kbeg_a = h->kbeg_a; p.kob = h->kob;
+    p.aoff = h->aoff; p.aux = h->aux; p.naux = h->naux;
+    p.gxc = h->g4[0]; p.gxe = h->g4[1]; p.gyc = h->g4[2]; p.gye = h->g4[3]; p.gzc = h->g4[4]; p.gze = h->g4[5];
+    p.cgx_c = h->cg[0]; p.cgx_b = h->cg[1]; p.cgy_c = h->cg[2]; p.cgy_b = h->cg[3]; p.cgz_c = h->cg[4]; p.cgz_b = h->cg[5];
+    for (int o = 0; o < 2; o++) {
+        p.r40x[o] = (F)h->r40[0][o]; p.r41x[o] = (F)h->r40[1][o];
+        p.r40y[o] = (F)h->r40[2][o]; p.r41y[o] = (F)h->r40[3][o];
+        p.r40z[o] = (F)h->r40[4][o]; p.r41z[o] = (F)h->r40[5][o];
+    }
+    p.r20x = (F)h->r20[0]; p.r20y = (F)h->r20[1]; p.r20z = (F)h->r20[2];
+    for (int m = 0; m < MAXNM; m++) { p.c1[m] = h->c1[m]; p.c2[m] = h->c2[m]; p.d1[m] = h->d1[m]; }
+    p.d2 = h->d2;
+    p.dt = g.dt;
+    return p;
+}
+
+// kernel__setup coefficients (m_kernel.f90:43-67) in the kind F, and r20 (m_absorb_p.f90:70-72)
+template <typename F>
+static void setup_coefs(swpc3d_handle *h, const float *ts) {
+    const swpc3d_grid &g = h->g;
+    const F d[3] = {(F)g.dx, (F)g.dy, (F)g.dz};
+    for (int a = 0; a < 3; a++) {
+        const F rc40 = (F)17.0 / (F)16.0 / d[a], rc41 = (F)1.0 / (F)48.0 / d[a];
+        const F rd40 = -(F)1.0 / (F)16.0 / d[a], rd41 = -(F)1.0 / (F)48.0 / d[a];
+        h->r40[2 * a][0] = (double)(F)(rc40 + (-1) * rd40);
+        h->r40[2 * a][1] = (double)(F)(rc40 + (1) * rd40);
+        h->r40[2 * a + 1][0] = (double)(F)(rc41 + (-1) * rd41);
+        h->r40[2 * a + 1][1] = (double)(F)(rc41 + (1) * rd41);
+        h->r20[a] = (double)(F)((F)1.0f / d[a]);
+    }
+    const float dt = g.dt;
+    const int nm = g.nm;
+    h->d2 = 0.0f;
+    if (nm > 0) {
+        float sum = 0.0f;
+        for (int m = 0; m < nm; m++) {
+            h->c1[m] = (2 * ts[m] - dt) / (2 * ts[m] + dt);
+            h->c2[m] = (2) / (2 * ts[m] + dt) / nm;
+            h->d1[m] = 2 * ts[m] / (2 * ts[m] - dt);
+            sum += dt / (2 * ts[m] - dt);
+        }
+        h->d2 = sum / nm;
+    }
+    h->dt_dxyz = (double)((F)dt / ((F)g.dx * (F)g.dy * (F)g.dz));   // m_source.f90:306
+}
+
+extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handle **out) {
+    if (!g || !out) return fail("swpc3d_create: null argument");
+    *out = nullptr;
+    if (g->field_bytes != 8 && g->field_bytes != 4) return fail("field_bytes must be 8 (MP=DP) or 4 (MP=SP)");
+    if (g->nm < 0 || g->nm > MAXNM) return fail("nm must be 0..3");
+    if (g->abc_type != SWPC3D_ABC_PML && g->abc_type != SWPC3D_ABC_CERJAN) return fail("abc_type must be 1 (pml) or 2 (cerjan)");
+    if (g->nm > 0 && !ts) return fail("ts[nm] required when nm > 0");
+    if (g->iend < g->ibeg || g->jend < g->jbeg || g->nz < 1) return fail("empty subdomain");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("no CUDA device available (the swpc3d_b200 path has no CPU fallback): ") + cudaGetErrorString(e));
+    swpc3d_handle *h = new swpc3d_handle();
+    h->g = *g;
+    h->dev = g->device >= 0 ? g->device : (g->myid % ndev);   // m_global.f90:208-214
+    CK(cudaSetDevice(h->dev));
+    h->nxp = g->iend - g->ibeg + 1;
+    h->nyp = g->jend - g->jbeg + 1;
+    h->NXM = h->nxp + 2 * HALO + g->ipad;
+    h->NYM = h->nyp + 2 * HALO + g->jpad;
+    h->nzm_h = g->nz + 6 + g->kpad;
+    h->NZP = ((g->nz + g->kpad + KOFF + 3) + 31) / 32 * 32;
+    h->ncell = (long long)h->NZP * h->NXM * h->NYM;
+    h->fb = g->field_bytes;
+    h->nm = g->nm;
+    if (h->fb == 8) setup_coefs<double>(h, ts);
+    else setup_coefs<float>(h, ts);
+    CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+    for (int a = 0; a < 9; a++) {
+        CK(cudaMalloc(&h->F[a], (size_t)h->ncell * h->fb));
+        CK(cudaMemsetAsync(h->F[a], 0, (size_t)h->ncell * h->fb, h->st));
+    }
+    if (h->nm > 0) {
+        CK(cudaMalloc(&h->R, (size_t)h->ncell * 6 * h->nm * sizeof(float)));
+        CK(cudaMemsetAsync(h->R, 0, (size_t)h->ncell * 6 * h->nm * sizeof(float), h->st));
+    }
+    for (int a = 0; a < 5; a++) {
+        CK(cudaMalloc(&h->med[a], (size_t)h->ncell * sizeof(float)));
+        CK(cudaMemsetAsync(h->med[a], 0, (size_t)h->ncell * sizeof(float), h->st));
+    }
+    const size_t n2 = (size_t)h->NXM * h->NYM;
+    CK(cudaMalloc(&h->band, n2 * sizeof(int4)));
+    CK(cudaMalloc(&h->kbeg_a, n2 * sizeof(int)));
+    CK(cudaMalloc(&h->kob, n2 * sizeof(int)));
+    CK(cudaMemsetAsync(h->band, 0, n2 * sizeof(int4), h->st));
+    CK(cudaMemsetAsync(h->kob, 0, n2 * sizeof(int), h->st));
+    // kbeg_a: m_global.f90:334-343
+    h->h_kbeg_a.resize(n2);
+    for (int mj = 0; mj < h->NYM; mj++)
+        for (int mi = 0; mi < h->NXM; mi++) {
+            const int i = g->ibeg - HALO + mi, j = g->jbeg - HALO + mj;
+            const bool wall = (i <= g->na || g->nx - g->na + 1 <= i || j <= g->na || g->ny - g->na + 1 <= j);
+            h->h_kbeg_a[(size_t)mi + (size_t)h->NXM * mj] = wall ? 1 : g->nz - g->na + 1;
+        }
+    CK(cudaMemcpyAsync(h->kbeg_a, h->h_kbeg_a.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMalloc(&h->vmax_d, 3 * sizeof(unsigned int)));
+    // halo buffers: 5 planes per face, m_global.f90:251-258
+    const size_t isz = (size_t)5 * h->nyp * g->nz * h->fb, jsz = (size_t)5 * h->nxp * g->nz * h->fb;
+    for (int f = 0; f < 4; f++) {
+        const size_t sz = f < 2 ? isz : jsz;
+        CK(cudaMalloc(&h->sbuf[f], sz));
+        CK(cudaMalloc(&h->rbuf[f], sz));
+        CK(cudaMemsetAsync(h->sbuf[f], 0, sz, h->st));
+        CK(cudaMemsetAsync(h->rbuf[f], 0, sz, h->st));
+    }
+    // neighbour table: itbl, m_global.f90:624-642
+    const int idx = g->myid % g->nproc_x, idy = g->myid / g->nproc_x;
+    h->nbr[0] = (idx + 1 < g->nproc_x) ? g->myid + 1 : -1;
+    h->nbr[1] = (idx - 1 >= 0) ? g->myid - 1 : -1;
+    h->nbr[2] = (idy + 1 < g->nproc_y) ? g->myid + g->nproc_x : -1;
+    h->nbr[3] = (idy - 1 >= 0) ? g->myid - g->nproc_x : -1;
+    CK(cudaStreamSynchronize(h->st));
+    *out = h;
+    return 0;
+}
+
+extern "C" int swpc3d_destroy(swpc3d_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->dev);
+    cudaDeviceSynchronize();
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int a = 0; a < 9; a++) cudaFree(h->F[a]);
+    cudaFree(h->R);
+    for (int a = 0; a < 5; a++) cudaFree(h->med[a]);
+    cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->aoff); cudaFree(h->aux);
+    for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
+    cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
+    cudaFree(h->st_ijk); cudaFree(h->wav); cudaFree(h->vmax_d);
+    for (int f = 0; f < 4; f++) { cudaFree(h->sbuf[f]); cudaFree(h->rbuf[f]); }
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+    return 0;
+}
+
+// host (reference layout, k from -2) <-> device (padded) copy of one 3-D array
+static int copy3d(swpc3d_handle *h, void *dev, const void *host_c, void *host_m, size_t elem, bool to_device) {
+    // host row = one column: nzm_h elements starting at k = -2  <->  device index KOFF-1-2 = KOFF-3
+    const size_t rows = (size_t)h->NXM * h->NYM;
+    char *d = (char *)dev + (size_t)(KOFF - 3) * elem;
+    if (to_device)
+        CK(cudaMemcpy2DAsync(d, (size_t)h->NZP * elem, host_c, (size_t)h->nzm_h * elem, (size_t)h->nzm_h * elem, rows,
+                             cudaMemcpyHostToDevice, h->st));
+    else
+        CK(cudaMemcpy2DAsync(host_m, (size_t)h->nzm_h * elem, d, (size_t)h->NZP * elem, (size_t)h->nzm_h * elem, rows,
+                             cudaMemcpyDeviceToHost, h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_upload_medium(swpc3d_handle *h, const float *rho, const float *lam, const float *mu, const float *taup,
+                                    const float *taus, const int32_t *kfs, const int32_t *kob, const int32_t *kfs_top,
+                                    const int32_t *kfs_bot, const int32_t *kob_top, const int32_t *kob_bot,
+                                    const int32_t *kbeg_a) {
+    if (!h) return fail("null handle");
+    if (!rho || !lam || !mu || !taup || !taus || !kob || !kfs_top || !kfs_bot || !kob_top || !kob_bot)
+        return fail("swpc3d_upload_medium: null array");
+    (void)kfs;
+    CK(cudaSetDevice(h->dev));
+    const float *src[5] = {rho, lam, mu, taup, taus};
+    for (int a = 0; a < 5; a++)
+        if (copy3d(h, h->med[a], src[a], nullptr, sizeof(float), true)) return 1;
+    const size_t n2 = (size_t)h->NXM * h->NYM;
+    std::vector<int4> band(n2);
+    for (size_t n = 0; n < n2; n++) band[n] = make_int4(kfs_top[n], kfs_bot[n], kob_top[n], kob_bot[n]);
+    // the reference defines the bands on owned (i,j) only (m_medium.f90:376-386); make the rest inert
+    for (int mj = 0; mj < h->NYM; mj++)
+        for (int mi = 0; mi < h->NXM; mi++)
+            if (mi < HALO || mi >= HALO + h->nxp || mj < HALO || mj >= HALO + h->nyp) band[(size_t)mi + (size_t)h->NXM * mj] = make_int4(1, 1, 1, 1);
+    CK(cudaMemcpyAsync(h->band, band.data(), n2 * sizeof(int4), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemcpyAsync(h->kob, kob, n2 * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    if (kbeg_a) {
+        for (int lj = 0; lj < h->nyp; lj++)
+            for (int li = 0; li < h->nxp; li++) {
+                const size_t n = (size_t)(li + HALO) + (size_t)h->NXM * (lj + HALO);
+                if (kbeg_a[n] != h->h_kbeg_a[n]) return fail("swpc3d_upload_medium: kbeg_a differs from m_global.f90:334-343");
+            }
+    }
+    CK(cudaStreamSynchronize(h->st));
+    h->medium_ready = true;
+    return 0;
+}
+
+extern "C" int swpc3d_upload_fields(swpc3d_handle *h, const void *Vx, const void *Vy, const void *Vz, const void *Sxx,
+                                    const void *Syy, const void *Szz, const void *Syz, const void *Sxz, const void *Sxy) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    const void *src[9] = {Vx, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy};
+    for (int a = 0; a < 9; a++)
+        if (src[a] && copy3d(h, h->F[a], src[a], nullptr, (size_t)h->fb, true)) return 1;
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_download_fields(swpc3d_handle *h, void *Vx, void *Vy, void *Vz, void *Sxx, void *Syy, void *Szz,
+                                      void *Syz, void *Sxz, void *Sxy) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    void *dst[9] = {Vx, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy};
+    for (int a = 0; a < 9; a++)
+        if (dst[a] && copy3d(h, h->F[a], nullptr, dst[a], (size_t)h->fb, false)) return 1;
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_zero_state(swpc3d_handle *h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    for (int a = 0; a < 9; a++) CK(cudaMemsetAsync(h->F[a], 0, (size_t)h->ncell * h->fb, h->st));
+    if (h->R) CK(cudaMemsetAsync(h->R, 0, (size_t)h->ncell * 6 * h->nm * sizeof(float), h->st));
+    if (h->aux) CK(cudaMemsetAsync(h->aux, 0, (size_t)h->naux * 18 * sizeof(float), h->st));
+    if (h->wav) CK(cudaMemsetAsync(h->wav, 0, (size_t)h->ntw * 3 * h->nst * sizeof(float), h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_setup_pml(swpc3d_handle *h, const float *gxc, const float *gxe, const float *gyc, const float *gye,
+                                const float *gzc, const float *gze) {
+    if (!h) return fail("null handle");
+    if (h->g.abc_type != SWPC3D_ABC_PML) return fail("swpc3d_setup_pml: abc_type is not pml");
+    if (!gxc || !gxe || !gyc || !gye || !gzc || !gze) return fail("swpc3d_setup_pml: null profile");
+    CK(cudaSetDevice(h->dev));
+    const float *src[6] = {gxc, gxe, gyc, gye, gzc, gze};
+    const int len[6] = {h->nxp, h->nxp, h->nyp, h->nyp, h->g.nz, h->g.nz};
+    for (int a = 0; a < 6; a++) {
+        if (!h->g4[a]) CK(cudaMalloc(&h->g4[a], (size_t)len[a] * sizeof(float4)));
+        CK(cudaMemcpyAsync(h->g4[a], src[a], (size_t)len[a] * sizeof(float4), cudaMemcpyHostToDevice, h->st));
+    }
+    // shell-only ADE storage: column (i,j) holds k = kbeg_a(i,j)..nz, columns start on 32-element boundaries
+    std::vector<long long> aoff((size_t)h->nxp * h->nyp);
+    long long off = 0;
+    for (int lj = 0; lj < h->nyp; lj++)
+        for (int li = 0; li < h->nxp; li++) {
+            const int kb = h->h_kbeg_a[(size_t)(li + HALO) + (size_t)h->NXM * (lj + HALO)];
+            const int len_k = h->g.nz - kb + 1;
+            // keep the column's lane phase: element k sits at off + (k - kb) with off = 32*q + ((kb-1) & 31)
+            const int phase = (kb - 1) & 31;
+            aoff[(size_t)li + (size_t)h->nxp * lj] = off + phase;
+            off += ((phase + len_k) + 31) / 32 * 32;
+        }
+    h->naux = off;
+    if (h->aoff) cudaFree(h->aoff);
+    if (h->aux) cudaFree(h->aux);
+    CK(cudaMalloc(&h->aoff, aoff.size() * sizeof(long long)));
+    CK(cudaMemcpyAsync(h->aoff, aoff.data(), aoff.size() * sizeof(long long), cudaMemcpyHostToDevice, h->st));
+    CK(cudaMalloc(&h->aux, (size_t)std::max<long long>(h->naux, 1) * 18 * sizeof(float)));
+    CK(cudaMemsetAsync(h->aux, 0, (size_t)std::max<long long>(h->naux, 1) * 18 * sizeof(float), h->st));
+    CK(cudaStreamSynchronize(h->st));
+    h->absorber_ready = true;
+    return 0;
+}
+
+extern "C" int swpc3d_setup_cerjan(swpc3d_handle *h, const float *gx_c, const float *gx_b, const float *gy_c, const float *gy_b,
+                                   const float *gz_c, const float *gz_b) {
+    if (!h) return fail("null handle");
+    if (h->g.abc_type != SWPC3D_ABC_CERJAN) return fail("swpc3d_setup_cerjan: abc_type is not cerjan");
+    if (!gx_c || !gx_b || !gy_c || !gy_b || !gz_c || !gz_b) return fail("swpc3d_setup_cerjan: null vector");
+    CK(cudaSetDevice(h->dev));
+    const float *src[6] = {gx_c, gx_b, gy_c, gy_b, gz_c, gz_b};
+    for (int a = 0; a < 6; a++) {
+        const bool isz = a >= 4;
+        const int len_d = a < 2 ? h->NXM : (a < 4 ? h->NYM : h->NZP);
+        std::vector<float> tmp((size_t)len_d, 1.0f);
+        if (isz) {   // host vector covers k = -2 .. nz+3+kpad  ->  device index k + KOFF - 1
+            for (int q = 0; q < h->nzm_h; q++) tmp[(size_t)(q - 2 + KOFF - 1)] = src[a][q];
+        } else {
+            for (int q = 0; q < len_d; q++) tmp[(size_t)q] = src[a][q];
+        }
+        if (!h->cg[a]) CK(cudaMalloc(&h->cg[a], (size_t)len_d * sizeof(float)));
+        CK(cudaMemcpy(h->cg[a], tmp.data(), (size_t)len_d * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    h->absorber_ready = true;
+    return 0;
+}
+
+static int stf_code(const char *s) {
+    if (!s) return 3;
+    if (!strcmp(s, "boxcar")) return 0;
+    if (!strcmp(s, "triangle")) return 1;
+    if (!strcmp(s, "herrmann")) return 2;
+    if (!strcmp(s, "kupper")) return 3;
+    if (!strcmp(s, "cosine")) return 4;
+    if (!strcmp(s, "texp")) return 5;
+    return 3;   // default branch of momentrate, m_fdtool.f90:494
+}
+
+extern "C" int swpc3d_set_sources(swpc3d_handle *h, int32_t nsrc, const int32_t *isrc, const int32_t *jsrc, const int32_t *ksrc,
+                                  const double *mo, const double *mxx, const double *myy, const double *mzz, const double *myz,
+                                  const double *mxz, const double *mxy, const float *srcprm, const char *stftype, int32_t bf_mode,
+                                  float tbeg) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
+    h->src_ijk = nullptr; h->src_mo = nullptr; h->src_mij = nullptr; h->src_prm = nullptr; h->src_stime = nullptr;
+    h->nsrc = nsrc; h->bf_mode = bf_mode; h->stf = stf_code(stftype); h->tbeg = tbeg;
+    if (nsrc <= 0) return 0;
+    std::vector<int> ijk(3 * (size_t)nsrc);
+    std::vector<double> vmo((size_t)nsrc), mij(6 * (size_t)nsrc);
+    for (int i = 0; i < nsrc; i++) {
+        const int mi = isrc[i] - h->g.ibeg + HALO, mj = jsrc[i] - h->g.jbeg + HALO;
+        // the reference keeps sources in the sleeve [ibeg-2, iend+3] (m_source.f90:209-211); the 4-node shear
+        // stencil then touches mi-1 >= 0
+        if (mi < 1 || mi >= h->NXM || mj < 1 || mj >= h->NYM || ksrc[i] < 1 - 2 + 1 || ksrc[i] > h->g.nz + 3)
+            return fail("swpc3d_set_sources: source outside of the subdomain sleeve");
+        ijk[3 * i] = mi; ijk[3 * i + 1] = mj; ijk[3 * i + 2] = ksrc[i];
+        vmo[i] = mo ? mo[i] : 0.0;
+        mij[6 * i] = mxx ? mxx[i] : 0; mij[6 * i + 1] = myy ? myy[i] : 0; mij[6 * i + 2] = mzz ? mzz[i] : 0;
+        mij[6 * i + 3] = myz ? myz[i] : 0; mij[6 * i + 4] = mxz ? mxz[i] : 0; mij[6 * i + 5] = mxy ? mxy[i] : 0;
+    }
+    h->h_prm.assign(srcprm, srcprm + 2 * (size_t)nsrc);
+    CK(cudaMalloc(&h->src_ijk, ijk.size() * sizeof(int)));
+    CK(cudaMalloc(&h->src_mo, vmo.size() * sizeof(double)));
+    CK(cudaMalloc(&h->src_mij, mij.size() * sizeof(double)));
+    CK(cudaMalloc(&h->src_prm, h->h_prm.size() * sizeof(float)));
+    CK(cudaMalloc(&h->src_stime, (size_t)nsrc * sizeof(float)));
+    CK(cudaMemcpy(h->src_ijk, ijk.data(), ijk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->src_mo, vmo.data(), vmo.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->src_mij, mij.data(), mij.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->src_prm, h->h_prm.data(), h->h_prm.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t *ist, const int32_t *jst, const int32_t *kst,
+                                   int32_t ntdec_w, int32_t ntw, float M0, float UC) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    cudaFree(h->st_ijk); cudaFree(h->wav);
+    h->st_ijk = nullptr; h->wav = nullptr;
+    h->nst = nst; h->ntdec_w = ntdec_w; h->ntw = ntw; h->M0 = M0; h->UC = UC;
+    if (nst <= 0 || ntw <= 0) return 0;
+    std::vector<int> ijk(3 * (size_t)nst);
+    for (int i = 0; i < nst; i++) {
+        const int mi = ist[i] - h->g.ibeg + HALO, mj = jst[i] - h->g.jbeg + HALO;
+        if (mi < HALO || mi >= HALO + h->nxp || mj < HALO || mj >= HALO + h->nyp || kst[i] < 1 || kst[i] > h->g.nz)
+            return fail("swpc3d_set_stations: station outside of the owned box (m_wav.f90:203)");
+        ijk[3 * i] = mi; ijk[3 * i + 1] = mj; ijk[3 * i + 2] = kst[i];
+    }
+    CK(cudaMalloc(&h->st_ijk, ijk.size() * sizeof(int)));
+    CK(cudaMemcpy(h->st_ijk, ijk.data(), ijk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->wav, (size_t)ntw * 3 * nst * sizeof(float)));
+    CK(cudaMemset(h->wav, 0, (size_t)ntw * 3 * nst * sizeof(float)));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sweeps
+template <typename F, bool STRESS>
+static int launch_sweep(swpc3d_handle *h) {
+    const KParams<F> p = make_params<F>(h);
+    dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
+    const int jlen = std::max(1, h->jlen);
+    dim3 grd((unsigned)((h->g.nz + h->tk - 1) / h->tk), (unsigned)((h->nxp + h->ti - 1) / h->ti), (unsigned)((h->nyp + jlen - 1) / jlen));
+    switch (h->nm) {
+    case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
+    case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
+    case 2: sweep_direct<F, 2, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
+    default: sweep_direct<F, 3, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int ready(swpc3d_handle *h) {
+    if (!h) return fail("null handle");
+    if (!h->medium_ready) return fail("swpc3d: medium not uploaded (swpc3d_upload_medium)");
+    if (!h->absorber_ready) return fail("swpc3d: absorber not set up (swpc3d_setup_pml / swpc3d_setup_cerjan)");
+    CK(cudaSetDevice(h->dev));
+    return 0;
+}
+
+extern "C" int swpc3d_update_stress(swpc3d_handle *h) {
+    if (ready(h)) return 1;
+    return h->fb == 8 ? launch_sweep<double, true>(h) : launch_sweep<float, true>(h);
+}
+extern "C" int swpc3d_update_vel(swpc3d_handle *h) {
+    if (ready(h)) return 1;
+    return h->fb == 8 ? launch_sweep<double, false>(h) : launch_sweep<float, false>(h);
+}
+
+// host evaluation of the moment-rate functions (same formulas as kernels.cuh / m_fdtool.f90:339-497) so that small
+// source sets get a libm-evaluated value
+static float momentrate_host(float t, int stf, float ts, float tr) {
+    const double PI = 3.14159265358979323846;
+    switch (stf) {
+    case 0: return (ts <= t && t <= ts + tr) ? 1.0f / tr : 0.0f;
+    case 1:
+        if (ts <= t && t <= ts + tr / 2) return 4 * (t - ts) / (tr * tr);
+        if (ts + tr / 2 < t && t <= ts + tr) return -4 * (t - ts - tr) / (tr * tr);
+        return 0.0f;
+    case 2: {
+        const float t1 = ts + tr / 4, t2 = ts + 3 * tr / 4, tr3 = tr * tr * tr;
+        if (ts <= t && t < t1) return 16 * ((t - ts) * (t - ts)) / tr3;
+        if (t1 <= t && t < t2) return -2 * (8 * (t * t + tr * ts + ts * ts - t * tr - 2 * t * ts) + tr * tr) / tr3;
+        if (t2 <= t && t <= ts + tr) return 16 * ((ts + tr - t) * (ts + tr - t)) / tr3;
+        return 0.0f;
+    }
+    case 4: return (ts <= t && t <= ts + tr) ? (float)((1 - cos(2 * PI * (double)(t - ts) / (double)tr)) / (double)tr) : 0.0f;
+    case 5:
+        if (ts <= t) {
+            const float tt = t - ts;
+            return (float)((2 * PI) * (2 * PI) * (double)tt / (double)(tr * tr) * exp(-2 * PI * (double)tt / (double)tr));
+        }
+        return 0.0f;
+    default:
+        if (ts <= t && t <= ts + tr) {
+            const double s = sin(PI * (double)(t - ts) / (double)tr);
+            return (float)(3 * PI * (s * s * s) / (double)(4 * tr));
+        }
+        return 0.0f;
+    }
+}
+
+template <typename F>
+static int launch_source(swpc3d_handle *h, int it, bool body) {
+    SrcParams s{};
+    s.nsrc = h->nsrc; s.ijk = h->src_ijk; s.mo = h->src_mo; s.mij = h->src_mij; s.prm = h->src_prm;
+    s.stf = h->stf; s.dt_dxyz = h->dt_dxyz;
+    const float dt = h->g.dt;
+    s.t = body ? h->tbeg + it * dt : h->tbeg + ((float)it - 0.5f) * dt;   // m_source.f90:873 / :800
+    s.stime = nullptr;
+    if (h->nsrc <= 256) {
+        float st[256];
+        for (int i = 0; i < h->nsrc; i++) st[i] = momentrate_host(s.t, h->stf, h->h_prm[2 * i], h->h_prm[2 * i + 1]);
+        CK(cudaMemcpyAsync(h->src_stime, st, (size_t)h->nsrc * sizeof(float), cudaMemcpyHostToDevice, h->st));
+        s.stime = h->src_stime;
+    }
+    const KParams<F> p = make_params<F>(h);
+    const int nb = (h->nsrc + 127) / 128;
+    if (body) bodyforce_kernel<F><<<nb, 128, 0, h->st>>>(p, s);
+    else stressglut_kernel<F><<<nb, 128, 0, h->st>>>(p, s);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swpc3d_stressglut(swpc3d_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (h->bf_mode || h->nsrc <= 0) return 0;
+    return h->fb == 8 ? launch_source<double>(h, it, false) : launch_source<float>(h, it, false);
+}
+extern "C" int swpc3d_bodyforce(swpc3d_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (!h->bf_mode || h->nsrc <= 0) return 0;
+    return h->fb == 8 ? launch_source<double>(h, it, true) : launch_source<float>(h, it, true);
+}
+
+extern "C" int swpc3d_wav_store(swpc3d_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (h->nst <= 0 || h->ntdec_w <= 0 || (it - 1) % h->ntdec_w != 0) return 0;
+    const int itw = (it - 1) / h->ntdec_w + 1;
+    if (itw > h->ntw) return 0;
+    const int nb = (h->nst + 127) / 128;
+    if (h->fb == 8) wav_store_kernel<double><<<nb, 128, 0, h->st>>>(make_params<double>(h), h->nst, h->st_ijk, h->wav, h->ntw, itw, h->M0, h->UC);
+    else wav_store_kernel<float><<<nb, 128, 0, h->st>>>(make_params<float>(h), h->nst, h->st_ijk, h->wav, h->ntw, itw, h->M0, h->UC);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swpc3d_vmax(swpc3d_handle *h, float out[3]) {
+    if (ready(h)) return 1;
+    const swpc3d_grid &g = h->g;
+    const int margin = 5;
+    const int i0 = std::max(g.na + margin + 1, g.ibeg_k), i1 = std::min(g.nx - g.na - margin, g.iend_k);
+    const int j0 = std::max(g.na + margin + 1, g.jbeg_k), j1 = std::min(g.ny - g.na - margin, g.jend_k);
+    out[0] = out[1] = out[2] = 0.0f;
+    if (i1 < i0 || j1 < j0) return 0;
+    CK(cudaMemsetAsync(h->vmax_d, 0, 3 * sizeof(unsigned int), h->st));
+    const long long n = (long long)(i1 - i0 + 1) * (j1 - j0 + 1);
+    const int nb = (int)std::min<long long>((n + 255) / 256, 1184);
+    if (h->fb == 8) vmax_kernel<double><<<nb, 256, 0, h->st>>>(make_params<double>(h), i0 - g.ibeg, i1 - g.ibeg, j0 - g.jbeg, j1 - g.jbeg, h->vmax_d);
+    else vmax_kernel<float><<<nb, 256, 0, h->st>>>(make_params<float>(h), i0 - g.ibeg, i1 - g.ibeg, j0 - g.jbeg, j1 - g.jbeg, h->vmax_d);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_get_wav(swpc3d_handle *h, float *wav_vel) {
+    if (!h) return fail("null handle");
+    if (h->nst <= 0 || h->ntw <= 0) return 0;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaMemcpyAsync(wav_vel, h->wav, (size_t)h->ntw * 3 * h->nst * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_sync(swpc3d_handle *h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo exchange.  Plane lists of m_global.f90:416-443/461-486 (velocity) and :527-553/573-599 (stress);
+// mi/mj are memory-box indices: ibeg <-> HALO, iend <-> HALO+nxp-1.
+struct FaceLists { PlaneList send[4], recv[4]; };
+
+static FaceLists face_lists(const swpc3d_handle *h, int which) {
+    FaceLists L{};
+    const int ib = HALO, ie = HALO + h->nxp - 1, jb = HALO, je = HALO + h->nyp - 1;
+    void *const *F = h->F;
+    enum { Vx = 0, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy };
+    auto set = [](PlaneList &pl, std::initializer_list<std::pair<void *, int>> v) {
+        pl.n = 0;
+        for (auto &e : v) { pl.field[pl.n] = e.first; pl.m[pl.n] = e.second; pl.n++; }
+    };
+    if (which == 1) {   // velocity
+        set(L.send[0], {{F[Vx], ie - 1}, {F[Vx], ie}, {F[Vy], ie}, {F[Vz], ie}});
+        set(L.send[1], {{F[Vx], ib}, {F[Vy], ib}, {F[Vy], ib + 1}, {F[Vz], ib}, {F[Vz], ib + 1}});
+        set(L.send[2], {{F[Vx], je}, {F[Vy], je - 1}, {F[Vy], je}, {F[Vz], je}});
+        set(L.send[3], {{F[Vx], jb}, {F[Vx], jb + 1}, {F[Vy], jb}, {F[Vz], jb}, {F[Vz], jb + 1}});
+        set(L.recv[1], {{F[Vx], ib - 2}, {F[Vx], ib - 1}, {F[Vy], ib - 1}, {F[Vz], ib - 1}});                      // from -x
+        set(L.recv[0], {{F[Vx], ie + 1}, {F[Vy], ie + 1}, {F[Vy], ie + 2}, {F[Vz], ie + 1}, {F[Vz], ie + 2}});     // from +x
+        set(L.recv[3], {{F[Vx], jb - 1}, {F[Vy], jb - 2}, {F[Vy], jb - 1}, {F[Vz], jb - 1}});                      // from -y
+        set(L.recv[2], {{F[Vx], je + 1}, {F[Vx], je + 2}, {F[Vy], je + 1}, {F[Vz], je + 1}, {F[Vz], je + 2}});     // from +y
+    } else {            // stress
+        set(L.send[0], {{F[Sxx], ie}, {F[Sxy], ie - 1}, {F[Sxy], ie}, {F[Sxz], ie - 1}, {F[Sxz], ie}});
+        set(L.send[1], {{F[Sxx], ib}, {F[Sxx], ib + 1}, {F[Sxy], ib}, {F[Sxz], ib}});
+        set(L.send[2], {{F[Syy], je}, {F[Sxy], je - 1}, {F[Sxy], je}, {F[Syz], je - 1}, {F[Syz], je}});
+        set(L.send[3], {{F[Syy], jb}, {F[Syy], jb + 1}, {F[Sxy], jb}, {F[Syz], jb}});
+        set(L.recv[1], {{F[Sxx], ib - 1}, {F[Sxy], ib - 2}, {F[Sxy], ib - 1}, {F[Sxz], ib - 2}, {F[Sxz], ib - 1}});
+        set(L.recv[0], {{F[Sxx], ie + 1}, {F[Sxx], ie + 2}, {F[Sxy], ie + 1}, {F[Sxz], ie + 1}});
+        set(L.recv[3], {{F[Syy], jb - 1}, {F[Sxy], jb - 2}, {F[Sxy], jb - 1}, {F[Syz], jb - 2}, {F[Syz], jb - 1}});
+        set(L.recv[2], {{F[Syy], je + 1}, {F[Syy], je + 2}, {F[Sxy], je + 1}, {F[Syz], je + 1}});
+    }
+    return L;
+}
+
+template <typename F>
+static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack) {
+    const int nz = h->g.nz;
+    for (int f = 0; f < 4; f++) {
+        if (h->nbr[f] < 0) continue;
+        const bool xface = f < 2;
+        const int nline = xface ? h->nyp : h->nxp;
+        const PlaneList &pl = pack ? L.send[f] : L.recv[f];
+        dim3 blk(128, 1, 1), grd((unsigned)((nz + 127) / 128), (unsigned)nline, (unsigned)pl.n);
+        F *buf = (F *)(pack ? h->sbuf[f] : h->rbuf[f]);
+        if (xface) {
+            if (pack) halo_kernel<F, true, true><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+            else halo_kernel<F, true, false><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+        } else {
+            if (pack) halo_kernel<F, false, true><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+            else halo_kernel<F, false, false><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+        }
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+static size_t face_count(const swpc3d_handle *h, const PlaneList &pl, int f) {
+    return (size_t)pl.n * (size_t)(f < 2 ? h->nyp : h->nxp) * (size_t)h->g.nz;
+}
+
+static int comm_exchange(swpc3d_handle *h, int which) {
+    if (ready(h)) return 1;
+    bool any = false;
+    for (int f = 0; f < 4; f++) any |= (h->nbr[f] >= 0);
+    if (!any) return 0;   // all neighbours MPI_PROC_NULL: outer halos keep their zeros
+    if (!h->comm) return fail("swpc3d_comm_*: this rank has neighbours but swpc3d_comm_init was not called");
+    const FaceLists L = face_lists(h, which);
+    if (h->fb == 8 ? launch_halo<double>(h, L, true) : launch_halo<float>(h, L, true)) return 1;
+    const ncclDataType_t ty = h->fb == 8 ? ncclDouble : ncclFloat;
+    NK(g_nccl.GroupStart());
+    for (int f = 0; f < 4; f++) {
+        if (h->nbr[f] < 0) continue;
+        NK(g_nccl.Send(h->sbuf[f], face_count(h, L.send[f], f), ty, h->nbr[f], h->comm, h->st));
+        NK(g_nccl.Recv(h->rbuf[f], face_count(h, L.recv[f], f), ty, h->nbr[f], h->comm, h->st));
+    }
+    NK(g_nccl.GroupEnd());
+    return h->fb == 8 ? launch_halo<double>(h, L, false) : launch_halo<float>(h, L, false);
+}
+
+extern "C" int swpc3d_comm_stress(swpc3d_handle *h) { return comm_exchange(h, 0); }
+extern "C" int swpc3d_comm_vel(swpc3d_handle *h) { return comm_exchange(h, 1); }
+
+extern "C" int swpc3d_nccl_unique_id(char id[128]) {
+    if (nccl_load()) return 1;
+    ncclUniqueId u;
+    NK(g_nccl.GetUniqueId(&u));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id, &u, 128);
+    return 0;
+}
+
+extern "C" int swpc3d_comm_init(swpc3d_handle *h, const char id[128], int32_t nranks, int32_t rank) {
+    if (!h) return fail("null handle");
+    if (nccl_load()) return 1;
+    if (nranks != h->g.nproc_x * h->g.nproc_y) return fail("swpc3d_comm_init: nranks != nproc_x*nproc_y (assert, m_global.f90:232)");
+    if (rank != h->g.myid) return fail("swpc3d_comm_init: rank != myid");
+    CK(cudaSetDevice(h->dev));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    NK(g_nccl.CommInitRank(&h->comm, nranks, u, rank));
+    h->comm_rank = rank;
+    h->comm_size = nranks;
+    return 0;
+}
+
+// single-process emulation: all handles on GPUs of this process, ordered by myid
+extern "C" int swpc3d_comm_local(swpc3d_handle **hs, int32_t n, int32_t which) {
+    if (!hs || n <= 0) return fail("swpc3d_comm_local: no handles");
+    for (int q = 0; q < n; q++) {
+        if (ready(hs[q])) return 1;
+        if (hs[q]->g.myid != q) return fail("swpc3d_comm_local: handles must be ordered by myid");
+        const FaceLists L = face_lists(hs[q], which);
+        if (hs[q]->fb == 8 ? launch_halo<double>(hs[q], L, true) : launch_halo<float>(hs[q], L, true)) return 1;
+    }
+    for (int q = 0; q < n; q++) { CK(cudaSetDevice(hs[q]->dev)); CK(cudaStreamSynchronize(hs[q]->st)); }
+    const int opp[4] = {1, 0, 3, 2};
+    for (int q = 0; q < n; q++) {
+        swpc3d_handle *h = hs[q];
+        const FaceLists L = face_lists(h, which);
+        for (int f = 0; f < 4; f++) {
+            if (h->nbr[f] < 0) continue;
+            if (h->nbr[f] >= n) return fail("swpc3d_comm_local: neighbour not in the handle list");
+            swpc3d_handle *o = hs[h->nbr[f]];
+            CK(cudaMemcpy(o->rbuf[opp[f]], h->sbuf[f], face_count(h, L.send[f], f) * (size_t)h->fb, cudaMemcpyDefault));
+        }
+    }
+    for (int q = 0; q < n; q++) {
+        const FaceLists L = face_lists(hs[q], which);
+        CK(cudaSetDevice(hs[q]->dev));
+        if (hs[q]->fb == 8 ? launch_halo<double>(hs[q], L, false) : launch_halo<float>(hs[q], L, false)) return 1;
+    }
+    for (int q = 0; q < n; q++) { CK(cudaSetDevice(hs[q]->dev)); CK(cudaStreamSynchronize(hs[q]->st)); }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int swpc3d_step(swpc3d_handle *h, int32_t it) {
+    // main.f90:119-139
+    if (swpc3d_wav_store(h, it)) return 1;
+    if (swpc3d_update_stress(h)) return 1;
+    if (swpc3d_stressglut(h, it)) return 1;
+    if (swpc3d_comm_stress(h)) return 1;
+    if (swpc3d_update_vel(h)) return 1;
+    if (swpc3d_bodyforce(h, it)) return 1;
+    if (swpc3d_comm_vel(h)) return 1;
+    return 0;
+}
+
+extern "C" int swpc3d_run(swpc3d_handle *h, int32_t it0, int32_t it1) {
+    for (int it = it0; it <= it1; it++)
+        if (swpc3d_step(h, it)) return 1;
+    return 0;
+}
+
+extern "C" int swpc3d_timer_start(swpc3d_handle *h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    CK(cudaEventRecord(h->ev0, h->st));
+    return 0;
+}
+extern "C" int swpc3d_timer_stop(swpc3d_handle *h, float *ms) {
+    if (!h || !ms) return fail("null argument");
+    CK(cudaSetDevice(h->dev));
+    CK(cudaEventRecord(h->ev1, h->st));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+
+extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t value) {
+    if (!h || !key) return fail("null argument");
+    if (!strcmp(key, "tk")) { if (value < 32 || value > 1024 || value % 32) return fail("tk must be a multiple of 32 in 32..1024"); h->tk = value; }
+    else if (!strcmp(key, "ti")) { if (value < 1 || value > 32) return fail("ti must be 1..32"); h->ti = value; }
+    else if (!strcmp(key, "jlen")) { if (value < 1) return fail("jlen must be >= 1"); h->jlen = value; }
+    else if (!strcmp(key, "variant")) h->variant = value;
+    else return fail(std::string("unknown option ") + key);
+    if (h->tk * h->ti > 256) return fail("tk*ti must be <= 256 (launch bounds)");
+    return 0;
+}
+
+extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value) {
+    if (!h || !key || !value) return fail("null argument");
+    if (!strcmp(key, "launches")) *value = (double)h->launches;
+    else if (!strcmp(key, "NZP")) *value = h->NZP;
+    else if (!strcmp(key, "NXM")) *value = h->NXM;
+    else if (!strcmp(key, "NYM")) *value = h->NYM;
+    else if (!strcmp(key, "naux")) *value = (double)h->naux;
+    else if (!strcmp(key, "device")) *value = h->dev;
+    else if (!strcmp(key, "device_bytes")) {
+        double b = (double)h->ncell * (9.0 * h->fb + 5 * 4 + 6.0 * h->nm * 4) + (double)h->naux * 18 * 4;
+        *value = b;
+    } else return fail(std::string("unknown info key ") + key);
+    return 0;
+}

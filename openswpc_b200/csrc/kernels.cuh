@@ -1,0 +1,490 @@
+// kernels.cuh -- sm_100a device code of the swpc_3d time step (hand-written, no tensor cores: the
+// path is an HBM-bound staggered-grid stencil).
+//
+// Arithmetic contract (parity with the reference): every temporary keeps the kind
+// it is declared with in the Fortran source -- F (= real(MP): double by default, float for MP=SP)
+// for field differences, float for medium / memory-variable / PML terms -- and every expression is
+// written in the reference's evaluation order.  Built with -fmad=false the results are bit-identical
+// to a plain-IEEE evaluation of those expressions (see tests/test_gpu_parity.py).
+//
+// Layout in HBM (all arrays): (k,i,j) with k fastest, as m_kernel.f90:380, but with device padding:
+//   idx(k,i,j) = (k + KOFF - 1) + NZP * ((i - ibeg + 3) + NXM * (j - jbeg + 3))
+// KOFF = 32 puts k = 1 of every column on a 128-byte boundary for float and double arrays; NZP is a
+// multiple of 32; the +-3 i/j margins are the reference's halo/sleeve cells (m_global.f90:295-298).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace swpc {
+
+constexpr int KOFF = 32;   // leading k padding (elements)
+constexpr int HALO = 3;    // i/j margin cells each side (m_global.f90:295-298)
+constexpr int MAXNM = 3;   // NM of the reference build (m_global.f90:31)
+
+struct Band { int fs_top, fs_bot, ob_top, ob_bot; };   // kfs_top, kfs_bot, kob_top, kob_bot of one column
+
+template <typename F>
+struct KParams {
+    // ---- geometry (local = index inside the owned box, 0-based)
+    int nz, nxp, nyp;
+    int NZP, NXM, NYM;
+    long long SI, SJ;                 // element strides of i and j
+    long long ncell;                  // NZP*NXM*NYM
+    int li0_k, li1_k, lj0_k, lj1_k;   // interior kernel box, local, inclusive (empty if li0_k > li1_k)
+    int k1_k;                         // kend_k (kbeg_k is always 1)
+    int abc;                          // 1 = PML, 2 = Cerjan
+    // ---- fields
+    F *Vx, *Vy, *Vz, *Sxx, *Syy, *Szz, *Syz, *Sxz, *Sxy;
+    float *R;                         // 6*NM arrays of ncell floats: R[(c*NM+m)*ncell + idx], c: xx yy zz yz xz xy
+    const float *rho, *lam, *mu, *taup, *taus;
+    const int4 *band;                 // per (mi,mj) over the memory box: NXM*NYM
+    const int *kbeg_a;                // per (mi,mj)
+    const int *kob;                   // per (mi,mj)
+    // ---- PML
+    const long long *aoff;            // per owned column (li + nxp*lj): start of the column in the aux arrays
+    float *aux;                       // 18 arrays of naux floats
+    long long naux;
+    const float4 *gxc, *gxe, *gyc, *gye, *gzc, *gze;   // g(1:4) per owned i / j / k
+    // ---- Cerjan (indexed by memory-box index mi / mj, and k + KOFF - 1)
+    const float *cgx_c, *cgx_b, *cgy_c, *cgy_b, *cgz_c, *cgz_b;
+    // ---- coefficients
+    F r40x[2], r41x[2], r40y[2], r41y[2], r40z[2], r41z[2];   // [0]: 4th order (isign=-1), [1]: 2nd order (isign=+1)
+    F r20x, r20y, r20z;
+    float c1[MAXNM], c2[MAXNM], d1[MAXNM], d2;
+    float dt;
+};
+
+// aux array order (m_absorb_p.f90:47-52)
+enum Aux { axVx = 0, ayVx, azVx, axVy, ayVy, azVy, axVz, ayVz, azVz,
+           axSxx, aySxy, azSxz, axSxy, aySyy, azSyz, axSxz, aySyz, azSzz };
+
+constexpr float FLT_EPS_ = 1.1920929e-07f;   // epsilon(1.0)
+
+template <typename T> __device__ __forceinline__ T ldro(const T *p) { return __ldg(p); }
+
+// m_kernel.f90:103-104: isign = sign(1, max((k-kfs_top)(kfs_bot-k), (k-kob_top)(kob_bot-k)))
+__device__ __forceinline__ int fd_order_sel(int k, const int4 b) {
+    int a = (k - b.x) * (b.y - k);
+    int c = (k - b.z) * (b.w - k);
+    return (max(a, c) >= 0) ? 1 : 0;
+}
+
+// m_kernel.f90:293-309
+__device__ __forceinline__ float mu_harm(float a, float b, float c, float d) {
+    return 4 * a * b * c * d / (a * b * c + a * b * d + a * c * d + b * c * d + FLT_EPS_);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stress update of one interior cell: kernel__update_stress, m_kernel.f90:179-242 (normal) and
+// :266-337 (shear) in ONE pass so that V and mu are read once; Cerjan multiply (m_absorb_c.f90:113-168)
+// fused as a post-multiply of the freshly updated value.
+template <typename F, int NM>
+__device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n, int k, int mi, int mj, const int4 bnd) {
+    const long long si = p.SI, sj = p.SJ;
+    const int o = fd_order_sel(k, bnd);
+    const F re40x = p.r40x[o], re41x = p.r41x[o], re40y = p.r40y[o], re41y = p.r41y[o], re40z = p.r40z[o], re41z = p.r41z[o];
+    const F *__restrict__ Vx = p.Vx, *__restrict__ Vy = p.Vy, *__restrict__ Vz = p.Vz;
+    const float dt = p.dt;
+
+    const F vx0 = ldro(Vx + n), vy0 = ldro(Vy + n), vz0 = ldro(Vz + n);
+    const F vx_im1 = ldro(Vx + n - si), vx_ip1 = ldro(Vx + n + si), vx_im2 = ldro(Vx + n - 2 * si);
+    const F vy_jm1 = ldro(Vy + n - sj), vy_jp1 = ldro(Vy + n + sj), vy_jm2 = ldro(Vy + n - 2 * sj);
+    const F vz_km1 = ldro(Vz + n - 1), vz_kp1 = ldro(Vz + n + 1), vz_km2 = ldro(Vz + n - 2);
+
+    const F dxVx = (vx0 - vx_im1) * re40x - (vx_ip1 - vx_im2) * re41x;
+    const F dyVy = (vy0 - vy_jm1) * re40y - (vy_jp1 - vy_jm2) * re41y;
+    const F dzVz = (vz0 - vz_km1) * re40z - (vz_kp1 - vz_km2) * re41z;
+
+    const F dxVy_dyVx = (ldro(Vy + n + si) - vy0) * re40x - (ldro(Vy + n + 2 * si) - ldro(Vy + n - si)) * re41x +
+                        (ldro(Vx + n + sj) - vx0) * re40y - (ldro(Vx + n + 2 * sj) - ldro(Vx + n - sj)) * re41y;
+    const F dxVz_dzVx = (ldro(Vz + n + si) - vz0) * re40x - (ldro(Vz + n + 2 * si) - ldro(Vz + n - si)) * re41x +
+                        (ldro(Vx + n + 1) - vx0) * re40z - (ldro(Vx + n + 2) - ldro(Vx + n - 1)) * re41z;
+    const F dyVz_dzVy = (ldro(Vz + n + sj) - vz0) * re40y - (ldro(Vz + n + 2 * sj) - ldro(Vz + n - sj)) * re41y +
+                        (ldro(Vy + n + 1) - vy0) * re40z - (ldro(Vy + n + 2) - ldro(Vy + n - 1)) * re41z;
+
+    const float mu0 = ldro(p.mu + n), mu_k = ldro(p.mu + n + 1), mu_i = ldro(p.mu + n + si), mu_j = ldro(p.mu + n + sj);
+    const float mu2 = 2 * mu0;
+    const float lam2mu = ldro(p.lam + n) + mu2;
+    const float taup1 = ldro(p.taup + n), taus1 = ldro(p.taus + n);
+
+    const float d3v3 = (float)(dxVx + dyVy + dzVz);
+    const float dyVy_dzVz = (float)(dyVy + dzVz);
+    const float dxVx_dzVz = (float)(dxVx + dzVz);
+    const float dxVx_dyVy = (float)(dxVx + dyVy);
+
+    const float muxz = mu_harm(mu0, mu_k, mu_i, ldro(p.mu + n + 1 + si));
+    const float muxy = mu_harm(mu0, mu_i, mu_j, ldro(p.mu + n + si + sj));
+    const float muyz = mu_harm(mu0, mu_k, mu_j, ldro(p.mu + n + 1 + sj));
+
+    float Rxx_n = 0.0f, Ryy_n = 0.0f, Rzz_n = 0.0f, Ryz_n = 0.0f, Rxz_n = 0.0f, Rxy_n = 0.0f;
+    if (NM > 0) {
+        float *__restrict__ R = p.R + n;
+        const long long nc = p.ncell;
+#pragma unroll
+        for (int m = 0; m < NM; m++) {
+            const float c1 = p.c1[m], c2 = p.c2[m], d1 = p.d1[m];
+            float *rxx = R + (0 * NM + m) * nc, *ryy = R + (1 * NM + m) * nc, *rzz = R + (2 * NM + m) * nc;
+            float *ryz = R + (3 * NM + m) * nc, *rxz = R + (4 * NM + m) * nc, *rxy = R + (5 * NM + m) * nc;
+            const float nxx = c1 * (*rxx) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dyVy_dzVz) * dt;
+            const float nyy = c1 * (*ryy) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dzVz) * dt;
+            const float nzz = c1 * (*rzz) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dyVy) * dt;
+            // shear R: the product with the F-kind strain rate is an F expression rounded on store (m_kernel.f90:320-322)
+            const float nyz = (float)(c1 * (*ryz) - c2 * muyz * taus1 * dyVz_dzVy * dt);
+            const float nxz = (float)(c1 * (*rxz) - c2 * muxz * taus1 * dxVz_dzVx * dt);
+            const float nxy = (float)(c1 * (*rxy) - c2 * muxy * taus1 * dxVy_dyVx * dt);
+            *rxx = nxx; *ryy = nyy; *rzz = nzz; *ryz = nyz; *rxz = nxz; *rxy = nxy;
+            Rxx_n = Rxx_n + d1 * nxx; Ryy_n = Ryy_n + d1 * nyy; Rzz_n = Rzz_n + d1 * nzz;
+            Ryz_n = Ryz_n + d1 * nyz; Rxz_n = Rxz_n + d1 * nxz; Rxy_n = Rxy_n + d1 * nxy;
+        }
+    }
+    const float taup_plus1 = 1 + taup1 * (1 + p.d2);
+    const float taus_plus1 = 1 + taus1 * (1 + p.d2);
+
+    F sxx = p.Sxx[n] + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dyVy_dzVz + Rxx_n) * dt;
+    F syy = p.Syy[n] + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dzVz + Ryy_n) * dt;
+    F szz = p.Szz[n] + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dyVy + Rzz_n) * dt;
+    F syz = p.Syz[n] + (muyz * taus_plus1 * dyVz_dzVy + Ryz_n) * dt;
+    F sxz = p.Sxz[n] + (muxz * taus_plus1 * dxVz_dzVx + Rxz_n) * dt;
+    F sxy = p.Sxy[n] + (muxy * taus_plus1 * dxVy_dyVx + Rxy_n) * dt;
+
+    if (p.abc == 2) {   // Cerjan sponge, m_absorb_c.f90:129-133, :155-157
+        const int kk = k + KOFF - 1;
+        const float gxc = p.cgx_c[mi], gxb = p.cgx_b[mi], gyc = p.cgy_c[mj], gyb = p.cgy_b[mj], gzc = p.cgz_c[kk], gzb = p.cgz_b[kk];
+        const float gcc = gxc * gyc * gzc;
+        sxx = sxx * gcc; syy = syy * gcc; szz = szz * gcc;
+        syz = syz * gxc * gyb * gzb;
+        sxz = sxz * gxb * gyc * gzb;
+        sxy = sxy * gxb * gyb * gzc;
+    }
+    p.Sxx[n] = sxx; p.Syy[n] = syy; p.Szz[n] = szz; p.Syz[n] = syz; p.Sxz[n] = sxz; p.Sxy[n] = sxy;
+}
+
+// stress update of one PML cell: absorb_p__update_stress, m_absorb_p.f90:453-519 (both k-loops fused)
+template <typename F>
+__device__ __forceinline__ void stress_pml(const KParams<F> &p, long long n, int k, int li, int lj, long long a) {
+    const long long si = p.SI, sj = p.SJ, na = p.naux;
+    const F *__restrict__ Vx = p.Vx, *__restrict__ Vy = p.Vy, *__restrict__ Vz = p.Vz;
+    const float dt = p.dt;
+    const F r20x = p.r20x, r20y = p.r20y, r20z = p.r20z;
+    const float4 gxc = ldro(p.gxc + li), gxe = ldro(p.gxe + li), gyc = ldro(p.gyc + lj), gye = ldro(p.gye + lj);
+    const float4 gzc = ldro(p.gzc + (k - 1)), gze = ldro(p.gze + (k - 1));
+    float *__restrict__ A = p.aux + a;
+
+    const F vx0 = ldro(Vx + n), vy0 = ldro(Vy + n), vz0 = ldro(Vz + n);
+    const F dxVx = (vx0 - ldro(Vx + n - si)) * r20x;
+    const F dyVy = (vy0 - ldro(Vy + n - sj)) * r20y;
+    const F dzVz = (vz0 - ldro(Vz + n - 1)) * r20z;
+    const float mu0 = ldro(p.mu + n), mu_k = ldro(p.mu + n + 1), mu_i = ldro(p.mu + n + si), mu_j = ldro(p.mu + n + sj);
+    const float lam2mu_R = (ldro(p.lam + n) + 2 * mu0);
+    const float lam_R = lam2mu_R - 2 * mu0;
+
+    const float a_xVx = A[axVx * na], a_yVy = A[ayVy * na], a_zVz = A[azVz * na];
+    const float dxVx_ade = gxc.x * (float)(dxVx) + gxc.y * a_xVx;
+    const float dyVy_ade = gyc.x * (float)(dyVy) + gyc.y * a_yVy;
+    const float dzVz_ade = gzc.x * (float)(dzVz) + gzc.y * a_zVz;
+
+    p.Sxx[n] = p.Sxx[n] + (lam2mu_R * dxVx_ade + lam_R * (dyVy_ade + dzVz_ade)) * dt;
+    p.Syy[n] = p.Syy[n] + (lam2mu_R * dyVy_ade + lam_R * (dxVx_ade + dzVz_ade)) * dt;
+    p.Szz[n] = p.Szz[n] + (lam2mu_R * dzVz_ade + lam_R * (dxVx_ade + dyVy_ade)) * dt;
+
+    A[axVx * na] = gxc.z * a_xVx + gxc.w * (float)(dxVx) * dt;
+    A[ayVy * na] = gyc.z * a_yVy + gyc.w * (float)(dyVy) * dt;
+    A[azVz * na] = gzc.z * a_zVz + gzc.w * (float)(dzVz) * dt;
+
+    const F dxVy = (ldro(Vy + n + si) - vy0) * r20x;
+    const F dxVz = (ldro(Vz + n + si) - vz0) * r20x;
+    const F dyVx = (ldro(Vx + n + sj) - vx0) * r20y;
+    const F dyVz = (ldro(Vz + n + sj) - vz0) * r20y;
+    const F dzVx = (ldro(Vx + n + 1) - vx0) * r20z;
+    const F dzVy = (ldro(Vy + n + 1) - vy0) * r20z;
+
+    const float muxz = mu_harm(mu0, mu_k, mu_i, ldro(p.mu + n + 1 + si));
+    const float muxy = mu_harm(mu0, mu_i, mu_j, ldro(p.mu + n + si + sj));
+    const float muyz = mu_harm(mu0, mu_k, mu_j, ldro(p.mu + n + 1 + sj));
+
+    const float a_yVx = A[ayVx * na], a_zVx = A[azVx * na], a_xVy = A[axVy * na];
+    const float a_zVy = A[azVy * na], a_xVz = A[axVz * na], a_yVz = A[ayVz * na];
+
+    p.Syz[n] = p.Syz[n] + muyz * (gye.x * dyVz + gze.x * dzVy + gye.y * a_yVz + gze.y * a_zVy) * dt;
+    p.Sxz[n] = p.Sxz[n] + muxz * (gxe.x * dxVz + gze.x * dzVx + gxe.y * a_xVz + gze.y * a_zVx) * dt;
+    p.Sxy[n] = p.Sxy[n] + muxy * (gxe.x * dxVy + gye.x * dyVx + gxe.y * a_xVy + gye.y * a_yVx) * dt;
+
+    A[ayVx * na] = gye.z * a_yVx + gye.w * (float)(dyVx) * dt;
+    A[azVx * na] = gze.z * a_zVx + gze.w * (float)(dzVx) * dt;
+    A[axVy * na] = gxe.z * a_xVy + gxe.w * (float)(dxVy) * dt;
+    A[azVy * na] = gze.z * a_zVy + gze.w * (float)(dzVy) * dt;
+    A[axVz * na] = gxe.z * a_xVz + gxe.w * (float)(dxVz) * dt;
+    A[ayVz * na] = gye.z * a_yVz + gye.w * (float)(dyVz) * dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// velocity update of one interior cell: kernel__update_vel m_kernel.f90:99-129 (+ Cerjan m_absorb_c.f90:185-187)
+template <typename F>
+__device__ __forceinline__ void vel_interior(const KParams<F> &p, long long n, int k, int mi, int mj, const int4 bnd) {
+    const long long si = p.SI, sj = p.SJ;
+    const int o = fd_order_sel(k, bnd);
+    const F re40x = p.r40x[o], re41x = p.r41x[o], re40y = p.r40y[o], re41y = p.r41y[o], re40z = p.r40z[o], re41z = p.r41z[o];
+    const F *__restrict__ Sxx = p.Sxx, *__restrict__ Syy = p.Syy, *__restrict__ Szz = p.Szz;
+    const F *__restrict__ Syz = p.Syz, *__restrict__ Sxz = p.Sxz, *__restrict__ Sxy = p.Sxy;
+    const float dt = p.dt;
+    const F sxy0 = ldro(Sxy + n), sxz0 = ldro(Sxz + n), syz0 = ldro(Syz + n);
+
+    const F d3Sx3 = (ldro(Sxx + n + si) - ldro(Sxx + n)) * re40x - (ldro(Sxx + n + 2 * si) - ldro(Sxx + n - si)) * re41x +
+                    (sxy0 - ldro(Sxy + n - sj)) * re40y - (ldro(Sxy + n + sj) - ldro(Sxy + n - 2 * sj)) * re41y +
+                    (sxz0 - ldro(Sxz + n - 1)) * re40z - (ldro(Sxz + n + 1) - ldro(Sxz + n - 2)) * re41z;
+    const F d3Sy3 = (sxy0 - ldro(Sxy + n - si)) * re40x - (ldro(Sxy + n + si) - ldro(Sxy + n - 2 * si)) * re41x +
+                    (ldro(Syy + n + sj) - ldro(Syy + n)) * re40y - (ldro(Syy + n + 2 * sj) - ldro(Syy + n - sj)) * re41y +
+                    (syz0 - ldro(Syz + n - 1)) * re40z - (ldro(Syz + n + 1) - ldro(Syz + n - 2)) * re41z;
+    const F d3Sz3 = (sxz0 - ldro(Sxz + n - si)) * re40x - (ldro(Sxz + n + si) - ldro(Sxz + n - 2 * si)) * re41x +
+                    (syz0 - ldro(Syz + n - sj)) * re40y - (ldro(Syz + n + sj) - ldro(Syz + n - 2 * sj)) * re41y +
+                    (ldro(Szz + n + 1) - ldro(Szz + n)) * re40z - (ldro(Szz + n + 2) - ldro(Szz + n - 1)) * re41z;
+
+    const float rho0 = ldro(p.rho + n);
+    F vx = p.Vx[n] + 2.0f / (rho0 + ldro(p.rho + n + si)) * d3Sx3 * dt;
+    F vy = p.Vy[n] + 2.0f / (rho0 + ldro(p.rho + n + sj)) * d3Sy3 * dt;
+    F vz = p.Vz[n] + 2.0f / (rho0 + ldro(p.rho + n + 1)) * d3Sz3 * dt;
+    if (p.abc == 2) {
+        const int kk = k + KOFF - 1;
+        const float gxc = p.cgx_c[mi], gxb = p.cgx_b[mi], gyc = p.cgy_c[mj], gyb = p.cgy_b[mj], gzc = p.cgz_c[kk], gzb = p.cgz_b[kk];
+        vx = vx * gxb * gyc * gzc;
+        vy = vy * gxc * gyb * gzc;
+        vz = vz * gxc * gyc * gzb;
+    }
+    p.Vx[n] = vx; p.Vy[n] = vy; p.Vz[n] = vz;
+}
+
+// velocity update of one PML cell: absorb_p__update_vel m_absorb_p.f90:261-308
+template <typename F>
+__device__ __forceinline__ void vel_pml(const KParams<F> &p, long long n, int k, int li, int lj, long long a) {
+    const long long si = p.SI, sj = p.SJ, na = p.naux;
+    const F *__restrict__ Sxx = p.Sxx, *__restrict__ Syy = p.Syy, *__restrict__ Szz = p.Szz;
+    const F *__restrict__ Syz = p.Syz, *__restrict__ Sxz = p.Sxz, *__restrict__ Sxy = p.Sxy;
+    const float dt = p.dt;
+    const F r20x = p.r20x, r20y = p.r20y, r20z = p.r20z;
+    const float4 gxc = ldro(p.gxc + li), gxe = ldro(p.gxe + li), gyc = ldro(p.gyc + lj), gye = ldro(p.gye + lj);
+    const float4 gzc = ldro(p.gzc + (k - 1)), gze = ldro(p.gze + (k - 1));
+    float *__restrict__ A = p.aux + a;
+    const F sxy0 = ldro(Sxy + n), sxz0 = ldro(Sxz + n), syz0 = ldro(Syz + n);
+
+    const F dxSxx = (ldro(Sxx + n + si) - ldro(Sxx + n)) * r20x;
+    const F dySyy = (ldro(Syy + n + sj) - ldro(Syy + n)) * r20y;
+    const F dzSzz = (ldro(Szz + n + 1) - ldro(Szz + n)) * r20z;
+    const F dySyz = (syz0 - ldro(Syz + n - sj)) * r20y;
+    const F dzSyz = (syz0 - ldro(Syz + n - 1)) * r20z;
+    const F dxSxz = (sxz0 - ldro(Sxz + n - si)) * r20x;
+    const F dzSxz = (sxz0 - ldro(Sxz + n - 1)) * r20z;
+    const F dxSxy = (sxy0 - ldro(Sxy + n - si)) * r20x;
+    const F dySxy = (sxy0 - ldro(Sxy + n - sj)) * r20y;
+
+    const float rho0 = ldro(p.rho + n);
+    const float bx = 2.0f / (rho0 + ldro(p.rho + n + si));
+    const float by = 2.0f / (rho0 + ldro(p.rho + n + sj));
+    const float bz = 2.0f / (rho0 + ldro(p.rho + n + 1));
+
+    const float a_xSxx = A[axSxx * na], a_ySxy = A[aySxy * na], a_zSxz = A[azSxz * na];
+    const float a_xSxy = A[axSxy * na], a_ySyy = A[aySyy * na], a_zSyz = A[azSyz * na];
+    const float a_xSxz = A[axSxz * na], a_ySyz = A[aySyz * na], a_zSzz = A[azSzz * na];
+
+    p.Vx[n] = p.Vx[n] + bx * (float)(gxe.x * dxSxx + gyc.x * dySxy + gzc.x * dzSxz + gxe.y * a_xSxx + gyc.y * a_ySxy + gzc.y * a_zSxz) * dt;
+    p.Vy[n] = p.Vy[n] + by * (float)(gxc.x * dxSxy + gye.x * dySyy + gzc.x * dzSyz + gxc.y * a_xSxy + gye.y * a_ySyy + gzc.y * a_zSyz) * dt;
+    p.Vz[n] = p.Vz[n] + bz * (float)(gxc.x * dxSxz + gyc.x * dySyz + gze.x * dzSzz + gxc.y * a_xSxz + gyc.y * a_ySyz + gze.y * a_zSzz) * dt;
+
+    A[axSxx * na] = gxe.z * a_xSxx + gxe.w * (float)(dxSxx) * dt;
+    A[aySxy * na] = gyc.z * a_ySxy + gyc.w * (float)(dySxy) * dt;
+    A[azSxz * na] = gzc.z * a_zSxz + gzc.w * (float)(dzSxz) * dt;
+    A[axSxy * na] = gxc.z * a_xSxy + gxc.w * (float)(dxSxy) * dt;
+    A[aySyy * na] = gye.z * a_ySyy + gye.w * (float)(dySyy) * dt;
+    A[azSyz * na] = gzc.z * a_zSyz + gzc.w * (float)(dzSyz) * dt;
+    A[axSxz * na] = gxc.z * a_xSxz + gxc.w * (float)(dxSxz) * dt;
+    A[aySyz * na] = gyc.z * a_ySyz + gyc.w * (float)(dySyz) * dt;
+    A[azSzz * na] = gze.z * a_zSzz + gze.w * (float)(dzSzz) * dt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sweep kernels, version 1 ("direct"): thread = one (k,i) column position, block = TK x TI tile of the
+// (k,i) plane, marching over jlen planes along j (the slowest axis).  Neighbour values come through
+// L1/L2 (read-only path); every streamed array (S, R, medium, aux) is touched exactly once.
+// Interior cells and absorber cells partition the owned box (m_global.f90:334-376) and read only the
+// other field family, so one pass per family is order-independent.
+template <typename F, int NM, bool STRESS>
+__global__ void __launch_bounds__(256) sweep_direct(const __grid_constant__ KParams<F> p, int jlen, int lj_begin, int lj_end) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int li = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k > p.nz || li >= p.nxp) return;
+    const int mi = li + HALO;
+    const int ljs = lj_begin + blockIdx.z * jlen;
+    const int lje = min(ljs + jlen, lj_end);
+    const bool pml_mode = (p.abc == 1);
+    const bool i_interior = (li >= p.li0_k && li <= p.li1_k);
+    for (int lj = ljs; lj < lje; lj++) {
+        const int mj = lj + HALO;
+        const long long col = (long long)mi + (long long)p.NXM * mj;
+        const long long n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+        bool is_pml = false;
+        if (pml_mode) is_pml = (k >= p.kbeg_a[col]);
+        if (is_pml) {
+            const long long a = p.aoff[li + (long long)p.nxp * lj] + (k - p.kbeg_a[col]);
+            if (STRESS) stress_pml<F>(p, n, k, li, lj, a);
+            else vel_pml<F>(p, n, k, li, lj, a);
+        } else if (i_interior && lj >= p.lj0_k && lj <= p.lj1_k && k <= p.k1_k) {
+            const int4 bnd = p.band[col];
+            if (STRESS) stress_interior<F, NM>(p, n, k, mi, mj, bnd);
+            else vel_interior<F>(p, n, k, mi, mj, bnd);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// source time functions, m_fdtool.f90:339-497 (PI is real(DP) there)
+__device__ __forceinline__ float momentrate_dev(float t, int stf, float ts, float tr) {
+    const double PI = 3.14159265358979323846;
+    switch (stf) {
+    case 0:   // boxcar
+        return (ts <= t && t <= ts + tr) ? 1.0f / tr : 0.0f;
+    case 1:   // triangle
+        if (ts <= t && t <= ts + tr / 2) return 4 * (t - ts) / (tr * tr);
+        if (ts + tr / 2 < t && t <= ts + tr) return -4 * (t - ts - tr) / (tr * tr);
+        return 0.0f;
+    case 2: {   // herrmann
+        const float t1 = ts + tr / 4, t2 = ts + 3 * tr / 4, tr3 = tr * tr * tr;
+        if (ts <= t && t < t1) return 16 * ((t - ts) * (t - ts)) / tr3;
+        if (t1 <= t && t < t2) return -2 * (8 * (t * t + tr * ts + ts * ts - t * tr - 2 * t * ts) + tr * tr) / tr3;
+        if (t2 <= t && t <= ts + tr) return 16 * ((ts + tr - t) * (ts + tr - t)) / tr3;
+        return 0.0f;
+    }
+    case 4:   // cosine
+        return (ts <= t && t <= ts + tr) ? (float)((1 - cos(2 * PI * (double)(t - ts) / (double)tr)) / (double)tr) : 0.0f;
+    case 5:   // texp
+        if (ts <= t) {
+            const float tt = t - ts;
+            return (float)((2 * PI) * (2 * PI) * (double)tt / (double)(tr * tr) * exp(-2 * PI * (double)tt / (double)tr));
+        }
+        return 0.0f;
+    default: {   // kupper (also the reference's default branch)
+        if (ts <= t && t <= ts + tr) {
+            const double s = sin(PI * (double)(t - ts) / (double)tr);
+            return (float)(3 * PI * (s * s * s) / (double)(4 * tr));
+        }
+        return 0.0f;
+    }
+    }
+}
+
+struct SrcParams {
+    int nsrc;
+    const int *ijk;         // 3*nsrc: LOCAL memory-box indices (mi, mj) and k
+    const double *mo;       // nsrc
+    const double *mij;      // 6*nsrc: mxx myy mzz myz mxz mxy  (body force: fx fy fz in the first three)
+    const float *prm;       // 2*nsrc
+    const float *stime;     // optional host-evaluated moment rate for this step (nsrc), else nullptr
+    int stf;
+    float t;                // evaluation time
+    double dt_dxyz;
+};
+
+// source__stressglut m_source.f90:798-841: 15 atomic adds per source (sources may share cells)
+template <typename F>
+__global__ void stressglut_kernel(const __grid_constant__ KParams<F> p, const SrcParams s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.nsrc) return;
+    const float stime = s.stime ? s.stime[i] : momentrate_dev(s.t, s.stf, s.prm[2 * i], s.prm[2 * i + 1]);
+    const F sdrop = (F)((F)s.mo[i] * stime * (F)s.dt_dxyz);
+    const long long si = p.SI, sj = p.SJ;
+    const long long n = (long long)(s.ijk[3 * i + 2] + KOFF - 1) + (long long)p.NZP * ((long long)s.ijk[3 * i] + (long long)p.NXM * s.ijk[3 * i + 1]);
+    const F mxx = (F)s.mij[6 * i], myy = (F)s.mij[6 * i + 1], mzz = (F)s.mij[6 * i + 2];
+    const F myz = (F)s.mij[6 * i + 3], mxz = (F)s.mij[6 * i + 4], mxy = (F)s.mij[6 * i + 5];
+    atomicAdd(p.Sxx + n, -(mxx * sdrop));
+    atomicAdd(p.Syy + n, -(myy * sdrop));
+    atomicAdd(p.Szz + n, -(mzz * sdrop));
+    const F qxy = mxy * sdrop / 4, qxz = mxz * sdrop / 4, qyz = myz * sdrop / 4;
+    atomicAdd(p.Sxy + n, -qxy); atomicAdd(p.Sxy + n - sj, -qxy); atomicAdd(p.Sxy + n - si, -qxy); atomicAdd(p.Sxy + n - si - sj, -qxy);
+    atomicAdd(p.Sxz + n, -qxz); atomicAdd(p.Sxz + n - 1, -qxz); atomicAdd(p.Sxz + n - si, -qxz); atomicAdd(p.Sxz + n - 1 - si, -qxz);
+    atomicAdd(p.Syz + n, -qyz); atomicAdd(p.Syz + n - 1, -qyz); atomicAdd(p.Syz + n - sj, -qyz); atomicAdd(p.Syz + n - 1 - sj, -qyz);
+}
+
+// source__bodyforce m_source.f90:870-892
+template <typename F>
+__global__ void bodyforce_kernel(const __grid_constant__ KParams<F> p, const SrcParams s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.nsrc) return;
+    const float stime = s.stime ? s.stime[i] : momentrate_dev(s.t, s.stf, s.prm[2 * i], s.prm[2 * i + 1]);
+    const long long si = p.SI, sj = p.SJ;
+    const long long n = (long long)(s.ijk[3 * i + 2] + KOFF - 1) + (long long)p.NZP * ((long long)s.ijk[3 * i] + (long long)p.NXM * s.ijk[3 * i + 1]);
+    const F fx = (F)s.mij[6 * i], fy = (F)s.mij[6 * i + 1], fz = (F)s.mij[6 * i + 2];
+    const F dtd = (F)s.dt_dxyz;
+    const float *rho = p.rho;
+    atomicAdd(p.Vx + n, (F)((2.0f / (rho[n] + rho[n + si])) * fx * stime * dtd / 2));
+    atomicAdd(p.Vx + n - si, (F)((2.0f / (rho[n] + rho[n - si])) * fx * stime * dtd / 2));
+    atomicAdd(p.Vy + n, (F)((2.0f / (rho[n] + rho[n + sj])) * fy * stime * dtd / 2));
+    atomicAdd(p.Vy + n - sj, (F)((2.0f / (rho[n] + rho[n - sj])) * fy * stime * dtd / 2));
+    atomicAdd(p.Vz + n, (F)((2.0f / (rho[n] + rho[n + 1])) * fz * stime * dtd / 2));
+    atomicAdd(p.Vz + n - 1, (F)((2.0f / (rho[n] + rho[n - 1])) * fz * stime * dtd / 2));
+}
+
+// wav__store (velocity) m_wav.f90:527-532
+template <typename F>
+__global__ void wav_store_kernel(const __grid_constant__ KParams<F> p, int nst, const int *ijk, float *wav, int ntw, int itw, float M0, float UC) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nst) return;
+    const long long si = p.SI, sj = p.SJ;
+    const long long n = (long long)(ijk[3 * s + 2] + KOFF - 1) + (long long)p.NZP * ((long long)ijk[3 * s] + (long long)p.NXM * ijk[3 * s + 1]);
+    float *w = wav + (long long)ntw * 3 * s + (itw - 1);
+    w[0] = (float)(p.Vx[n] + p.Vx[n - si]) / 2.0f * M0 * UC * 1e9f;
+    w[ntw] = (float)(p.Vy[n] + p.Vy[n - sj]) / 2.0f * M0 * UC * 1e9f;
+    w[2 * ntw] = -(float)(p.Vz[n] + p.Vz[n - 1]) / 2.0f * M0 * UC * 1e9f;
+}
+
+// kernel__vmax m_kernel.f90:360-372: max |V| at k = kob(i,j)+1 over the given local (i,j) window
+template <typename F>
+__global__ void vmax_kernel(const __grid_constant__ KParams<F> p, int li0, int li1, int lj0, int lj1, unsigned int *out3) {
+    const int ni = li1 - li0 + 1, nj = lj1 - lj0 + 1;
+    float xm = 0.0f, ym = 0.0f, zm = 0.0f;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < (long long)ni * nj; t += (long long)gridDim.x * blockDim.x) {
+        const int li = li0 + (int)(t % ni), lj = lj0 + (int)(t / ni);
+        const long long col = (long long)(li + HALO) + (long long)p.NXM * (lj + HALO);
+        const long long n = (long long)(p.kob[col] + 1 + KOFF - 1) + (long long)p.NZP * col;
+        xm = fmaxf(xm, (float)fabs((double)p.Vx[n]));
+        ym = fmaxf(ym, (float)fabs((double)p.Vy[n]));
+        zm = fmaxf(zm, (float)fabs((double)p.Vz[n]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
+        ym = fmaxf(ym, __shfl_xor_sync(0xffffffffu, ym, o));
+        zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+    }
+    if ((threadIdx.x & 31) == 0) {   // non-negative floats order like their bit patterns
+        atomicMax(out3 + 0, __float_as_uint(xm));
+        atomicMax(out3 + 1, __float_as_uint(ym));
+        atomicMax(out3 + 2, __float_as_uint(zm));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo planes, m_global.f90:391-607.  A "plane list" names up to 5 (field, plane index) pairs; the
+// message layout is the reference's: plane-major, then (j-jbeg)*nz + (k-1) for x faces /
+// (i-ibeg)*nz + (k-1) for y faces, k = 1..nz only, no corners.
+struct PlaneList {
+    int n;
+    void *field[5];
+    int m[5];        // memory-box index (mi for x faces, mj for y faces) of the plane
+};
+
+template <typename F, bool XFACE, bool PACK>
+__global__ void halo_kernel(int nz, int nline, int NZP, int NXM, const PlaneList pl, F *buf) {
+    // one thread per (k, line) ; line = owned j (x face) or owned i (y face)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;   // 0-based
+    const int line = blockIdx.y;
+    const int s = blockIdx.z;
+    if (k >= nz || s >= pl.n) return;
+    F *f = (F *)pl.field[s];
+    long long col;
+    if (XFACE) col = (long long)pl.m[s] + (long long)NXM * (line + HALO);
+    else col = (long long)(line + HALO) + (long long)NXM * pl.m[s];
+    const long long n = (long long)(k + KOFF) + (long long)NZP * col;
+    const long long b = (long long)s * nline * nz + (long long)line * nz + k;
+    if (PACK) buf[b] = f[n];
+    else f[n] = buf[b];
+}
+
+}   // namespace swpc

@@ -227,6 +227,7 @@ int ora_get_map(const ora_sim *s, int rank, const char *name, int *out);
 /* gather the owned cells of every rank into a global (k=1..nz, i=1..nx, j=1..ny) array */
 int ora_gather_field(const ora_sim *s, const char *name, double *out);
 int ora_get_sources(const ora_sim *s, int rank, int *ijk /*3*nsrc*/, double *mo /*nsrc*/);
+int ora_get_source_details(const ora_sim *s, int rank, double *mij /*6*nsrc*/, float *srcprm /*2*nsrc*/);
 int ora_get_stations(const ora_sim *s, int rank, int *ijk /*3*nst*/, char *names /*9*nst*/);
 int ora_get_wav(const ora_sim *s, int rank, float *out /*(ntw,3,nst)*/);
 /* PML profile g?c/g?e: name gxc gxe gyc gye gzc gze -> (4,n) floats */

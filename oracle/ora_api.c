@@ -207,6 +207,23 @@ int ora_get_sources(const ora_sim *s, int rank, int *ijk, double *mo) {
     return r->nsrc;
 }
 
+/* mij (6,nsrc): mxx myy mzz myz mxz mxy (bf_mode: fx fy fz 0 0 0); srcprm (2,nsrc) */
+int ora_get_source_details(const ora_sim *s, int rank, double *mij, float *srcprm) {
+    const ora_rank *r = &s->r[rank];
+    for (int i = 0; i < r->nsrc; i++) {
+        if (s->cfg.bf_mode) {
+            mij[6 * i] = (double)r->fx[i]; mij[6 * i + 1] = (double)r->fy[i]; mij[6 * i + 2] = (double)r->fz[i];
+            mij[6 * i + 3] = mij[6 * i + 4] = mij[6 * i + 5] = 0.0;
+        } else {
+            mij[6 * i] = (double)r->mxx[i]; mij[6 * i + 1] = (double)r->myy[i]; mij[6 * i + 2] = (double)r->mzz[i];
+            mij[6 * i + 3] = (double)r->myz[i]; mij[6 * i + 4] = (double)r->mxz[i]; mij[6 * i + 5] = (double)r->mxy[i];
+        }
+        srcprm[2 * i] = r->srcprm[2 * i];
+        srcprm[2 * i + 1] = r->srcprm[2 * i + 1];
+    }
+    return r->nsrc;
+}
+
 int ora_get_stations(const ora_sim *s, int rank, int *ijk, char *names) {
     const ora_rank *r = &s->r[rank];
     for (int i = 0; i < r->nst; i++) {
