@@ -109,6 +109,9 @@ int swpc3d_sync(swpc3d_handle *h);
 
 /* kernel__vmax (m_kernel.f90:350-374): this rank's max |V| at k = kob(i,j)+1, unscaled */
 int swpc3d_vmax(swpc3d_handle *h, float out[3]);
+/* kernel__vmax + mpi_reduce(MAX) of report__progress (m_report.f90:138-140): NCCL max over all ranks when a
+ * communicator is attached, else identical to swpc3d_vmax */
+int swpc3d_vmax_global(swpc3d_handle *h, float out[3]);
 /* `!$acc update self(wav_vel)` (m_wav.f90:672): (ntw,3,nst) floats */
 int swpc3d_get_wav(swpc3d_handle *h, float *wav_vel);
 

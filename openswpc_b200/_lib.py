@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 ROOT = PKG.parent
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared", "-diag-suppress", "177"]
+              "-Xcompiler", "-ffp-contract=off", "-shared", "-diag-suppress", "177"]
 
 
 def build(fmad: bool = False, force: bool = False, verbose: bool = False) -> Path:
@@ -51,7 +51,7 @@ SYMBOLS = [
     "swpc3d_download_fields", "swpc3d_zero_state", "swpc3d_setup_pml", "swpc3d_setup_cerjan", "swpc3d_set_sources",
     "swpc3d_set_stations", "swpc3d_update_stress", "swpc3d_stressglut", "swpc3d_comm_stress", "swpc3d_update_vel",
     "swpc3d_bodyforce", "swpc3d_comm_vel", "swpc3d_wav_store", "swpc3d_step", "swpc3d_run", "swpc3d_sync", "swpc3d_vmax",
-    "swpc3d_get_wav", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
+    "swpc3d_get_wav", "swpc3d_vmax_global", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
 ]
 
 _lib = None
@@ -62,6 +62,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("SWPC3D_LIB"):   # development: pick an experimental build of the same ABI
+        LIB_PATH = Path(os.environ["SWPC3D_LIB"])
     if not LIB_PATH.exists():
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the swpc3d_b200 path has no CPU fallback)")
@@ -86,6 +89,7 @@ def load() -> C.CDLL:
     lib.swpc3d_run.argtypes = [vp, i32, i32]
     lib.swpc3d_vmax.argtypes = [vp, fp]
     lib.swpc3d_get_wav.argtypes = [vp, fp]
+    lib.swpc3d_vmax_global.argtypes = [vp, fp]
     lib.swpc3d_nccl_unique_id.argtypes = [C.c_char_p]
     lib.swpc3d_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     lib.swpc3d_comm_local.argtypes = [C.POINTER(vp), i32, i32]

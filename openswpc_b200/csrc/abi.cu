@@ -44,6 +44,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -65,6 +66,7 @@ static int nccl_load() {
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -129,7 +131,7 @@ struct swpc3d_handle {
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tuning
-    int tk = 128, ti = 2, jlen = 32;
+    int tk = 32, ti = 8, jlen = 16, pf = 1;
     int variant = 1;
     long long launches = 0;
 };
@@ -510,14 +512,15 @@ extern "C" int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t 
 template <typename F, bool STRESS>
 static int launch_sweep(swpc3d_handle *h) {
     const KParams<F> p = make_params<F>(h);
+    if (h->tk * h->ti > 256) return fail("tk*ti must be <= 256 (launch bounds)");
     dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
     const int jlen = std::max(1, h->jlen);
     dim3 grd((unsigned)((h->g.nz + h->tk - 1) / h->tk), (unsigned)((h->nxp + h->ti - 1) / h->ti), (unsigned)((h->nyp + jlen - 1) / jlen));
     switch (h->nm) {
-    case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
-    case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
-    case 2: sweep_direct<F, 2, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
-    default: sweep_direct<F, 3, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp); break;
+    case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
+    case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
+    case 2: sweep_direct<F, 2, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
+    default: sweep_direct<F, 3, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -636,6 +639,17 @@ extern "C" int swpc3d_vmax(swpc3d_handle *h, float out[3]) {
     else vmax_kernel<float><<<nb, 256, 0, h->st>>>(make_params<float>(h), i0 - g.ibeg, i1 - g.ibeg, j0 - g.jbeg, j1 - g.jbeg, h->vmax_d);
     h->launches++;
     CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_vmax_global(swpc3d_handle *h, float out[3]) {
+    if (swpc3d_vmax(h, out)) return 1;
+    if (!h->comm) return 0;
+    // non-negative floats: the max of the values is the max of their bit patterns, reduce as float
+    CK(cudaMemcpyAsync(h->vmax_d, out, 3 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    NK(g_nccl.AllReduce(h->vmax_d, h->vmax_d, 3, ncclFloat, ncclMax, h->comm, h->st));
     CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return 0;
@@ -834,9 +848,9 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     if (!strcmp(key, "tk")) { if (value < 32 || value > 1024 || value % 32) return fail("tk must be a multiple of 32 in 32..1024"); h->tk = value; }
     else if (!strcmp(key, "ti")) { if (value < 1 || value > 32) return fail("ti must be 1..32"); h->ti = value; }
     else if (!strcmp(key, "jlen")) { if (value < 1) return fail("jlen must be >= 1"); h->jlen = value; }
+    else if (!strcmp(key, "pf")) { if (value < 0 || value > 8) return fail("pf must be 0..8"); h->pf = value; }
     else if (!strcmp(key, "variant")) h->variant = value;
     else return fail(std::string("unknown option ") + key);
-    if (h->tk * h->ti > 256) return fail("tk*ti must be <= 256 (launch bounds)");
     return 0;
 }
 

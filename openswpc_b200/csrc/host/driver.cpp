@@ -1,0 +1,1123 @@
+// driver.cpp -- host-side mirror of swpc_3d's setup chain and driver loop (include/swpc3d_host.h).
+//
+// Setup-only CPU code: it produces, for ONE rank, exactly the arrays the reference's setup modules hand to
+// the time loop (the loop itself runs only on the GPU through swpc3d_b200.h).  Every routine cites the
+// reference lines whose result it must reproduce (paths under /root/reference, OpenSWPC 25.05.2); kinds follow
+// the Fortran declarations (default real = float, PI = real(DP), src/shared/m_std.f90:14).
+#include "../../../include/swpc3d_host.h"
+
+#include <sys/stat.h>
+#include <time.h>
+
+#include <algorithm>
+#include <cctype>
+#include <chrono>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_herr;
+int hfail(const std::string &m) {
+    g_herr = m;
+    return 1;
+}
+
+constexpr double PI_D = 3.14159265358979323846;
+constexpr double R_EARTH = 6371.0;
+constexpr float EPS_SP = 1.1920929e-07f;   // epsilon(1.0)
+constexpr int NBD = 9;
+
+// ------------------------------------------------------------------------------------------------------------
+// input.inf reader: src/shared/m_readini.f90:29-100 (+ typed wrappers :103-170), m_system.f90:75-102
+class IniFile {
+  public:
+    bool strict = false;
+    static IniFile from_text(const std::string &text) {
+        IniFile f;
+        std::istringstream is(text);
+        std::string l;
+        while (std::getline(is, l)) {
+            if (!l.empty() && l.back() == '\r') l.pop_back();
+            f.lines_.push_back(l);
+        }
+        return f;
+    }
+    static bool from_file(const std::string &path, IniFile &out) {
+        std::ifstream is(path);
+        if (!is) return false;
+        std::stringstream ss;
+        ss << is.rdbuf();
+        out = from_text(ss.str());
+        return true;
+    }
+    // first non-comment line that STARTS with the key and continues with '=' wins (:78-92)
+    std::string get(const std::string &key, const std::string &def) const {
+        for (const std::string &raw : lines_) {
+            size_t p = raw.find_first_not_of(" \t");
+            if (p == std::string::npos) continue;
+            if (raw[p] == '#' || raw[p] == '!') continue;
+            if (raw.compare(p, key.size(), key) != 0) continue;
+            size_t q = raw.find_first_not_of(" \t", p + key.size());
+            if (q == std::string::npos || raw[q] != '=') continue;
+            return expand_env(list_directed(raw.substr(q + 1)));
+        }
+        if (strict) {
+            std::fprintf(stderr, "[swpc3d_b200 readini] key %s is not found. Program terminate ...\n", key.c_str());
+            std::exit(1);
+        }
+        return expand_env(def);
+    }
+    double get_d(const std::string &k, double def) const {
+        char b[64];
+        std::snprintf(b, sizeof b, "%.17g", def);
+        return std::strtod(real_token(get(k, b)).c_str(), nullptr);
+    }
+    float get_s(const std::string &k, float def) const {
+        char b[64];
+        std::snprintf(b, sizeof b, "%.9g", (double)def);
+        return std::strtof(real_token(get(k, b)).c_str(), nullptr);
+    }
+    int get_i(const std::string &k, int def) const { return (int)std::strtol(get(k, std::to_string(def)).c_str(), nullptr, 10); }
+    bool get_l(const std::string &k, bool def) const {
+        std::string v = get(k, def ? "T" : "F");
+        size_t p = v.find_first_not_of(' ');
+        if (p == std::string::npos) return false;
+        if (v[p] == '.') p++;
+        return p < v.size() && (v[p] == 'T' || v[p] == 't');
+    }
+
+  private:
+    std::vector<std::string> lines_;
+    // one item of a Fortran list-directed character read (:89)
+    static std::string list_directed(const std::string &s) {
+        size_t p = s.find_first_not_of(" \t");
+        if (p == std::string::npos) return "";
+        std::string out;
+        if (s[p] == '\'' || s[p] == '"') {
+            const char q = s[p++];
+            while (p < s.size()) {
+                if (s[p] == q) {
+                    if (p + 1 < s.size() && s[p + 1] == q) { out += q; p += 2; continue; }
+                    break;
+                }
+                out += s[p++];
+            }
+        } else {
+            while (p < s.size() && s[p] != ' ' && s[p] != '\t' && s[p] != ',' && s[p] != '/') out += s[p++];
+        }
+        return out;
+    }
+    static std::string expand_env(const std::string &s) {
+        std::string out;
+        size_t p = 0;
+        while (p < s.size()) {
+            if (s[p] == '$' && p + 1 < s.size() && s[p + 1] == '{') {
+                size_t e = s.find('}', p);
+                if (e == std::string::npos) break;
+                const char *v = std::getenv(s.substr(p + 2, e - p - 2).c_str());
+                if (v) out += v;
+                p = e + 1;
+            } else out += s[p++];
+        }
+        if (p < s.size()) out += s.substr(p);
+        while (!out.empty() && out.back() == ' ') out.pop_back();
+        return out;
+    }
+    static std::string real_token(const std::string &s) {
+        std::string t;
+        for (char ch : s) {
+            if (ch == ' ' || ch == '\t' || ch == ',' || ch == '/') { if (t.empty()) continue; break; }
+            t += (ch == 'd' || ch == 'D' || ch == 'q' || ch == 'Q') ? 'e' : ch;
+        }
+        return t;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// src/shared/m_fdtool.f90 / m_std.f90 helpers
+inline int x2i(float x, float xbeg, float dx) { return (int)std::ceil((x - xbeg) / dx); }               // :600-609
+inline float i2x(int i, float xbeg, float dx) { float h = (float)i - 0.5f; return xbeg + h * dx; }       // :639-648
+inline float deg2rad_s(float deg) { return (float)(PI_D / (double)180.0f * (double)deg); }               // m_std.f90:132-139
+inline float rad2deg_s(float rad) { return (float)((double)180.0f / PI_D * (double)rad); }               // m_std.f90:152-159
+
+void decomp1d(int n, int nproc, int proc, int &np, int &beg, int &end) {   // m_global.f90:234-247, :275-288
+    const int m = n % nproc, q = (n - m) / nproc;
+    if (proc <= nproc - m - 1) { np = q; beg = proc * (n - m) / nproc + 1; end = (proc + 1) * (n - m) / nproc; }
+    else { np = q + 1; beg = proc * (q + 1) - (nproc - m) + 1; end = (proc + 1) * (q + 1) - (nproc - m); }
+}
+
+void relax_times(int nm, float *ts, float fmin, float fmax) {   // visco_set_relaxtime :691-727
+    const float wa = (float)(2 * PI_D * (double)fmin), wb = (float)(2 * PI_D * (double)fmax);
+    if (nm == 0) return;
+    if (nm == 1) { ts[0] = 1.0f / std::sqrt(wa * wb); return; }
+    for (int im = 1; im <= nm; im++) {
+        const double e = (double)(im - 1) / (double)(nm - 1);
+        const float w = (float)((double)wa * std::pow((double)(wb / wa), e));
+        ts[im - 1] = 1.0f / w;
+    }
+}
+
+float constq_zeta(int nm, float fmin, float fmax, const float *ts) {   // visco_constq_zeta :756-812
+    if (nm == 0) return 0.0f;
+    const float wa = (float)(2 * PI_D * (double)fmin), wb = (float)(2 * PI_D * (double)fmax);
+    float i0s = 0.0f, i1s = 0.0f, i2s = 0.0f;
+    std::vector<float> i0(nm), i1(nm);
+    for (int m = 0; m < nm; m++) {
+        const float t = ts[m];
+        i0[m] = (std::log(1.0f + (wb * wb) * (t * t)) - std::log(1.0f + (wa * wa) * (t * t))) / (2 * t);
+        i1[m] = ((std::atan(wb * t) - wb * t / (1 + (wb * wb) * (t * t))) - (std::atan(wa * t) - wa * t / (1 + (wa * wa) * (t * t)))) / (2 * t);
+    }
+    for (int m = 0; m < nm; m++) i0s += i0[m];
+    for (int m = 0; m < nm; m++) i1s += i1[m];
+    for (int m = 0; m < nm - 1; m++)
+        for (int q = m + 1; q < nm; q++) {
+            const float w1 = std::atan(wb * ts[m]) / ts[m] - std::atan(wb * ts[q]) / ts[q];
+            const float w2 = std::atan(wa * ts[m]) / ts[m] - std::atan(wa * ts[q]) / ts[q];
+            const float v = ts[m] * ts[q] / (ts[q] * ts[q] - ts[m] * ts[m]) * (w1 - w2);
+            i2s = i2s + v;
+        }
+    return i0s / (i1s + 2 * i2s);
+}
+
+float stable_dt(float dx, float dy, float dz, float vmax) {   // fdm_stable_dt :81-96
+    const float hh = 1.0f / std::sqrt(1 / (dx * dx) + 1 / (dy * dy) + 1 / (dz * dz));
+    const float cc = 6.0f / 7.0f;
+    return cc * hh / vmax;
+}
+float moment_magnitude(float m0) { return m0 < EPS_SP ? -12345.0f : (std::log10(m0) - 9.1f) * 2.0f / 3.0f; }   // :281-293
+float seismic_moment(float mw) { return std::pow(10.0f, 1.5f * mw + 9.05f); }                                     // :296-304
+
+void sdr2moment(float strike, float dip, float rake, float m[6]) {   // :307-336 ; m = mxx myy mzz myz mxz mxy
+    const float sd = std::sin(deg2rad_s(dip)), cd = std::cos(deg2rad_s(dip));
+    const float s2d = std::sin(deg2rad_s(2 * dip)), c2d = std::cos(deg2rad_s(2 * dip));
+    const float sl = std::sin(deg2rad_s(rake)), cl = std::cos(deg2rad_s(rake));
+    const float sf = std::sin(deg2rad_s(strike)), cf = std::cos(deg2rad_s(strike));
+    const float s2f = std::sin(deg2rad_s(2 * strike)), c2f = std::cos(deg2rad_s(2 * strike));
+    m[0] = -(sd * cl * s2f + s2d * sl * sf * sf);
+    m[5] = (sd * cl * c2f + s2d * sl * s2f / 2);
+    m[4] = -(cd * cl * cf + c2d * sl * sf);
+    m[1] = (sd * cl * s2f - s2d * sl * cf * cf);
+    m[3] = -(cd * cl * sf - c2d * sl * cf);
+    m[2] = (s2d * sl);
+}
+
+float seawater_vel(float z, bool munk) {   // m_seawater.f90:34-47
+    const double eps = munk ? 0.00737 : 0.0, zc = 1300.0;
+    const double zb = 2 * ((double)z * (double)1000.0f - zc) / zc;
+    return (float)(1.5 * (1.0 + eps * (zb - 1.0 + std::exp(-zb))));
+}
+
+// ADE-CFS PML profile, m_absorb_p.f90:533-573
+void damping_profile(float x, float H, float xb, float xe, int na, float fcut, float dt, float g[4]) {
+    const float cp = 6.0f, b0 = 7.0f;
+    const float R0 = std::pow(10.0f, -(std::log10((float)na) - 1) / std::log10(2.0f) - 3.0f);
+    const float d0 = -((1.0f / (2.0f * H)) * 2.0f * cp * std::log(R0));
+    const float a0 = (float)(PI_D * (double)fcut);
+    float xx = 0.0f;
+    if (x <= xb + H) xx = (xb + H) - x;
+    else if (x >= xe - H) xx = x - (xe - H);
+    const float q = std::fabs(xx / H);
+    const float d = d0 * q, a = a0 * (1.0f - q), b = 1.0f + (b0 - 1.0f) * (q * q);
+    const float den = 1.0f + (dt / 2.0f) * (a + d / b);
+    g[0] = ((1.0f + (dt / 2.0f) * a) / b) / den;
+    g[1] = (-1.0f / b) / den;
+    g[2] = (1.0f - (dt / 2.0f) * (a + d / b)) / den;
+    g[3] = (d / b) / den;
+}
+
+// Gauss-Krueger projection, src/shared/m_gk.f90 (all double)
+struct GaussKrueger {
+    double al[6], be[6], AA[6], de[7];
+    static constexpr double a = 6378137.0, F = 298.257222101, m0 = 0.9999;
+    double n;
+    GaussKrueger() {
+        n = 1.0 / (2.0 * F - 1.0);
+        al[1] = (1 / 2. + (-2 / 3. + (5 / 16. + (41 / 180. - 127 / 288. * n) * n) * n) * n) * n;
+        al[2] = (13 / 48. + (-3 / 5. + (557 / 1440. + 281 / 630. * n) * n) * n) * (n * n);
+        al[3] = (61 / 240. + (-103 / 140. + 15061 / 26880. * n) * n) * (n * n * n);
+        al[4] = (49561 / 161280. - 179 / 168. * n) * (n * n * n * n);
+        al[5] = 34729 / 80640. * (n * n * n * n * n);
+        be[1] = (1 / 2. + (-2 / 3. + (37 / 96. + (-1 / 360. - 81 / 512. * n) * n) * n) * n) * n;
+        be[2] = ((1 / 48. + (1 / 15. + (-437 / 1440. + 46 / 105. * n) * n) * n) * n) * n;
+        be[3] = (((17 / 480. + (-37 / 840. - 209 / 4480. * n) * n) * n) * n) * n;
+        be[4] = ((((4397 / 161280. - 11 / 504. * n) * n) * n) * n) * n;
+        be[5] = ((((4583 / 161280. * n) * n) * n) * n) * n;
+        de[1] = (2 / 1. + (-2 / 3. + (-2 / 1. + (116 / 45. + (26 / 45. + (-2854 / 675.) * n) * n) * n) * n) * n) * n;
+        de[2] = ((7 / 3. + (-8 / 5. + (-227 / 45. + (2704 / 315. + (2323 / 945.) * n) * n) * n) * n) * n) * n;
+        de[3] = (((56 / 15. + (-136 / 35. + (-1262 / 105. + (73814 / 2835.) * n) * n) * n) * n) * n) * n;
+        de[4] = ((((4279 / 630. + (-332 / 35. + (-399572 / 14175.) * n) * n) * n) * n) * n) * n;
+        de[5] = (((((4174 / 315. + (-144838 / 6237.) * n) * n) * n) * n) * n) * n;
+        de[6] = ((((((601676 / 22275.) * n) * n) * n) * n) * n) * n;
+        const double n2 = n * n, n4 = n2 * n2;
+        AA[0] = 1 + (1 / 4. + 1 / 64. * n2) * n2;
+        AA[1] = -3 / 2. * (1. - 1 / 8. * n2 - 1 / 64. * n4) * n;
+        AA[2] = 15 / 16. * (1. - 1 / 4. * n2) * n2;
+        AA[3] = -35 / 48. * (1. - 5 / 16. * n2) * (n2 * n);
+        AA[4] = 315 / 512. * n4;
+        AA[5] = -693 / 1280. * (n4 * n);
+    }
+    static double atanh0(double x) { return std::log((1. + x) / (1. - x)) / 2.0; }
+    double S_phi0(double p0) const {
+        double s = AA[0] * p0;
+        for (int j = 1; j <= 5; j++) s = s + AA[j] * std::sin(2 * j * p0);
+        return s * (m0 * a / (1 + n));
+    }
+    void ll2xy(double lon, double lat, double lon0, double lat0, double &x, double &y) const {   // :40-92
+        const double d2r = PI_D / 180.0;
+        const double lam = d2r * lon, lam0 = d2r * lon0, phi = d2r * lat, phi0 = d2r * lat0;
+        const double e2n = 2.0 * std::sqrt(n) / (1.0 + n);
+        const double lc = std::cos(lam - lam0), ls = std::sin(lam - lam0);
+        const double tchi = std::sinh(atanh0(std::sin(phi)) - e2n * std::atanh(e2n * std::sin(phi)));
+        const double cchi = std::sqrt(1 + tchi * tchi);
+        const double xi = std::atan(tchi / lc), eta = atanh0(ls / cchi);
+        const double Abar = m0 * a / (1 + n) * AA[0];
+        double xx = xi, yy = eta;
+        for (int j = 1; j <= 5; j++) {
+            xx = xx + al[j] * std::sin(2 * j * xi) * std::cosh(2 * j * eta);
+            yy = yy + al[j] * std::cos(2 * j * xi) * std::sinh(2 * j * eta);
+        }
+        x = (Abar * xx - S_phi0(phi0)) / 1000;
+        y = (Abar * yy) / 1000;
+    }
+    void xy2ll(double x, double y, double lon0, double lat0, double &lon, double &lat) const {   // :115-158
+        const double d2r = PI_D / 180.0, r2d = 180.0 / PI_D;
+        const double lam0 = d2r * lon0, phi0 = d2r * lat0;
+        const double Abar = m0 * a / (1 + n) * AA[0];
+        const double xi = (x * 1000 + S_phi0(phi0)) / Abar, eta = y * 1000 / Abar;
+        double xi2 = xi, eta2 = eta;
+        for (int j = 1; j <= 5; j++) {
+            xi2 = xi2 - be[j] * std::sin(2 * j * xi) * std::cosh(2 * j * eta);
+            eta2 = eta2 - be[j] * std::cos(2 * j * xi) * std::sinh(2 * j * eta);
+        }
+        const double chi = std::asin(std::sin(xi2) / std::cosh(eta2));
+        const double lam = lam0 + std::atan(std::sinh(eta2) / std::cos(xi2));
+        double phi = chi;
+        for (int j = 1; j <= 6; j++) phi = phi + de[j] * std::sin(2 * j * chi);
+        lon = r2d * lam;
+        lat = r2d * phi;
+    }
+};
+const GaussKrueger &gk() { static GaussKrueger g; return g; }
+
+void geomap_g2c(float lon, float lat, float lon0, float lat0, float phi, float &x, float &y) {   // m_geomap.f90:18-41
+    const float pr = deg2rad_s(phi);
+    double xd, yd;
+    gk().ll2xy(lon, lat, lon0, lat0, xd, yd);
+    const float xx = (float)xd, yy = (float)yd;
+    x = std::cos(pr) * xx + std::sin(pr) * yy;
+    y = -std::sin(pr) * xx + std::cos(pr) * yy;
+}
+void geomap_c2g(float x, float y, float lon0, float lat0, float phi, float &lon, float &lat) {   // m_geomap.f90:44-65
+    const float pr = deg2rad_s(phi);
+    const float xx = std::cos(pr) * x - std::sin(pr) * y, yy = std::sin(pr) * x + std::cos(pr) * y;
+    double lo, la;
+    gk().xy2ll(xx, yy, lon0, lat0, lo, la);
+    lon = (float)lo;
+    lat = (float)la;
+}
+
+std::vector<float> parse_reals(const std::string &line) {
+    std::vector<float> v;
+    size_t p = 0;
+    while (p < line.size()) {
+        while (p < line.size() && (line[p] == ' ' || line[p] == '\t' || line[p] == ',' || line[p] == '\r' || line[p] == '\n')) p++;
+        if (p >= line.size()) break;
+        std::string t;
+        while (p < line.size() && line[p] != ' ' && line[p] != '\t' && line[p] != ',' && line[p] != '\r' && line[p] != '\n') {
+            char ch = line[p++];
+            t += (ch == 'd' || ch == 'D') ? 'e' : ch;
+        }
+        char *e = nullptr;
+        const float x = std::strtof(t.c_str(), &e);
+        if (e == t.c_str()) break;
+        v.push_back(x);
+    }
+    return v;
+}
+bool blank_or_comment(const std::string &l) {
+    size_t p = l.find_first_not_of(" \t\r\n");
+    return p == std::string::npos || l[p] == '#';
+}
+std::string join_path(const std::string &base, const std::string &fn) {
+    if (fn.empty() || fn[0] == '/' || base.empty()) return fn;
+    return base + "/" + fn;
+}
+
+}   // namespace
+
+// ============================================================================================================
+struct swpc3d_host {
+    // ---- global parameters (m_global.f90:124-216)
+    bool benchmark_mode = false;
+    std::string title, odir, abc_type, vmodel_type, stftype, stf_format, sdep_fit, wav_format, st_format, fn_stf, fn_stloc, base;
+    int nproc_x = 1, nproc_y = 2, nx = 256, ny = 256, nz = 256, nt = 1000, ipad = 0, jpad = 0, kpad = 0, na = 20, nm = 3;
+    double dx = 0.5, dy = 0.5, dz = 0.5;
+    float dt = 0.01f, xbeg = 0, ybeg = 0, zbeg = 0, tbeg = 0, xend = 0, yend = 0, zend = 0, clon = 0, clat = 0, phi = 0;
+    float fq_min = 0.05f, fq_max = 5.0f, fq_ref = 1.0f, vcut = 0.0f;
+    bool pw_mode = false, green_mode = false, bf_mode = false, earth_flattening = false;
+    int ntdec_w = 10, ntdec_r = 10, ntw = 0;
+    bool sw_wav_v = false;
+    float vmin = 0, vmax = 0, vmin_local = 0, vmax_local = 0, fmax = 0, fcut = 0, M0 = 0, UC = 1e-15f, zeta = 0, d2 = 0;
+    float ts[8] = {}, c1[8] = {}, c2[8] = {}, d1[8] = {};
+    float evlo = 0, evla = 0, evdp = 0, m0ij[6] = {}, f0[3] = {}, otim = 0, sx0 = 0, sy0 = 0;
+    int exedate = 0, tz_minutes = 0;
+    int field_bytes = 8;
+    // ---- this rank (m_global.f90:219-388)
+    int myid = 0, idx = 0, idy = 0, nxp = 0, nyp = 0, ibeg = 0, iend = 0, jbeg = 0, jend = 0;
+    int ibeg_m = 0, iend_m = 0, jbeg_m = 0, jend_m = 0, kbeg_m = 0, kend_m = 0, nzm = 0, nxm = 0, nym = 0;
+    int ibeg_k = 0, iend_k = 0, jbeg_k = 0, jend_k = 0, kbeg_k = 0, kend_k = 0;
+    std::vector<float> xc, yc, zc;
+    std::vector<float> rho, lam, mu, taup, taus, bddep;
+    std::vector<int> kfs, kob, kfs_top, kfs_bot, kob_top, kob_bot, kbeg_a;
+    std::vector<float> gxc, gxe, gyc, gye, gzc, gze;       // PML (4,n)
+    std::vector<float> cgx_c, cgx_b, cgy_c, cgy_b, cgz_c, cgz_b;   // Cerjan
+    // sources / stations
+    std::vector<int> src_ijk, st_ijk;
+    std::vector<double> mo, mij;
+    std::vector<float> srcprm, xst, yst, zst, stlo, stla;
+    std::vector<std::string> stnm;
+    // device
+    swpc3d_handle *dev = nullptr;
+    std::vector<float> wav;
+    double loop_seconds = 0;
+
+    size_t i3(int k, int i, int j) const { return (size_t)(k - kbeg_m) + (size_t)nzm * ((size_t)(i - ibeg_m) + (size_t)nxm * (size_t)(j - jbeg_m)); }
+    size_t i2(int i, int j) const { return (size_t)(i - ibeg_m) + (size_t)nxm * (size_t)(j - jbeg_m); }
+
+    int setup(const IniFile &ini, int nm_, int myid_, int npx, int npy, int nt_o);
+    int setup_global(const IniFile &ini, int npx, int npy, int nt_o);
+    int setup_geometry();
+    int setup_medium(const IniFile &ini);
+    void setup_kernel();
+    int setup_source(const IniFile &ini);
+    int setup_absorb();
+    int setup_wav(const IniFile &ini);
+};
+
+int swpc3d_host::setup_global(const IniFile &ini, int npx, int npy, int nt_o) {
+    benchmark_mode = ini.get_l("benchmark_mode", false);
+    title = ini.get("title", "swpc3d");
+    nproc_x = ini.get_i("nproc_x", 1);
+    nproc_y = ini.get_i("nproc_y", 2);
+    nx = ini.get_i("nx", 256); ny = ini.get_i("ny", 256); nz = ini.get_i("nz", 256);
+    nt = ini.get_i("nt", 1000);
+    ipad = ini.get_i("ipad", 0); jpad = ini.get_i("jpad", 0); kpad = ini.get_i("kpad", 0);
+    odir = ini.get("odir", "./out");
+    if (benchmark_mode) {   // m_global.f90:144-158
+        dx = dy = dz = 0.5f;
+        dt = 0.04f; na = 20;
+        xbeg = -((float)nx / 2.0f * (float)dx);
+        ybeg = -((float)ny / 2.0f * (float)dy);
+        zbeg = -30 * (float)dz;
+        tbeg = 0.0f; clon = 139.7604f; clat = 35.7182f; phi = 0.0f;
+        abc_type = "pml";
+    } else {
+        dx = ini.get_d("dx", 0.5); dy = ini.get_d("dy", 0.5); dz = ini.get_d("dz", 0.5);
+        dt = ini.get_s("dt", 0.01f);
+        na = ini.get_i("na", 20);
+        xbeg = ini.get_s("xbeg", -(float)(nx / 2) * (float)dx);
+        ybeg = ini.get_s("ybeg", -(float)(ny / 2) * (float)dy);
+        zbeg = ini.get_s("zbeg", -30 * (float)dz);
+        tbeg = ini.get_s("tbeg", 0.0f);
+        clon = ini.get_s("clon", 139.7604f); clat = ini.get_s("clat", 35.7182f); phi = ini.get_s("phi", 0.0f);
+        abc_type = ini.get("abc_type", "pml");
+    }
+    if (npx > 0) nproc_x = npx;
+    if (npy > 0) nproc_y = npy;
+    if (nt_o > 0) nt = nt_o;
+    xend = xbeg + nx * (float)dx; yend = ybeg + ny * (float)dy; zend = zbeg + nz * (float)dz;
+    if (myid < 0 || myid >= nproc_x * nproc_y) return hfail("myid outside of nproc_x*nproc_y (assert, m_global.f90:232)");
+    if (abc_type != "pml" && abc_type != "cerjan") return hfail("abc_type must be 'pml' or 'cerjan' (assert, m_absorb.f90:37)");
+    UC = 1e-15f;
+    const time_t now = time(nullptr);
+    struct tm lt;
+    localtime_r(&now, &lt);
+    exedate = (int)now;
+    tz_minutes = (int)(lt.tm_gmtoff / 60);
+    return 0;
+}
+
+int swpc3d_host::setup_geometry() {
+    idx = myid % nproc_x; idy = myid / nproc_x;
+    decomp1d(nx, nproc_x, idx, nxp, ibeg, iend);
+    decomp1d(ny, nproc_y, idy, nyp, jbeg, jend);
+    ibeg_m = ibeg - 3; iend_m = iend + 3 + ipad; jbeg_m = jbeg - 3; jend_m = jend + 3 + jpad; kbeg_m = -2; kend_m = nz + 3 + kpad;
+    nzm = kend_m - kbeg_m + 1; nxm = iend_m - ibeg_m + 1; nym = jend_m - jbeg_m + 1;
+    if ((ibeg_m <= na && iend_m < na + 1) || (iend_m >= nx - na + 1 && ibeg_m > nx - na) || (jbeg_m <= na && jend_m < na + 1) ||
+        (jend_m >= ny - na + 1 && jbeg_m > ny - na))
+        return hfail("subdomain narrower than the absorber: the reference's absorber homogenisation (m_medium.f90:124-176) would read out of bounds");
+    xc.resize(nxm); yc.resize(nym); zc.resize(nzm);
+    for (int i = ibeg_m; i <= iend_m; i++) xc[i - ibeg_m] = i2x(i, xbeg, (float)dx);
+    for (int j = jbeg_m; j <= jend_m; j++) yc[j - jbeg_m] = i2x(j, ybeg, (float)dy);
+    for (int k = kbeg_m; k <= kend_m; k++) zc[k - kbeg_m] = i2x(k, zbeg, (float)dz);
+    kbeg_a.assign((size_t)nxm * nym, 0);
+    for (int j = jbeg_m; j <= jend_m; j++)
+        for (int i = ibeg_m; i <= iend_m; i++)
+            kbeg_a[i2(i, j)] = (i <= na || nx - na + 1 <= i || j <= na || ny - na + 1 <= j) ? 1 : nz - na + 1;
+    ibeg_k = ibeg; iend_k = iend; jbeg_k = jbeg; jend_k = jend; kbeg_k = 1; kend_k = nz;
+    if (abc_type == "pml") {   // m_global.f90:355-376
+        if (iend <= na) ibeg_k = iend + 1; else if (ibeg <= na) ibeg_k = na + 1;
+        if (ibeg >= nx - na + 1) iend_k = ibeg - 1; else if (iend >= nx - na + 1) iend_k = nx - na;
+        if (jend <= na) jbeg_k = jend + 1; else if (jbeg <= na) jbeg_k = na + 1;
+        if (jbeg >= ny - na + 1) jend_k = jbeg - 1; else if (jend >= ny - na + 1) jend_k = ny - na;
+        kend_k = nz - na;
+    }
+    return 0;
+}
+
+int swpc3d_host::setup_medium(const IniFile &ini) {
+    const size_t nc = (size_t)nzm * nxm * nym, n2 = (size_t)nxm * nym;
+    rho.assign(nc, 0.f); lam.assign(nc, 0.f); mu.assign(nc, 0.f); taup.assign(nc, 0.f); taus.assign(nc, 0.f);
+    bddep.assign(n2 * (NBD + 1), -9999.0f);
+    // every supported model is laterally uniform at build time: fill one column profile, then broadcast
+    std::vector<float> p_rho(nzm), p_lam(nzm), p_mu(nzm), p_qp(nzm), p_qs(nzm);
+    float bd0 = 0.0f;
+    if (benchmark_mode) {   // m_medium.f90:55-74
+        fq_min = 0.05f; fq_max = 5.0f; fq_ref = 1.0f;
+        for (int q = 0; q < nzm; q++) {
+            if (zc[q] < 0.0f) { p_rho[q] = 0.001f; p_mu[q] = 0.0f; p_lam[q] = 0.0f; }
+            else { p_rho[q] = 2.7f; p_mu[q] = 2.7f * 3.5f * 3.5f; p_lam[q] = 2.7f * 3.5f * 3.5f; }
+            p_qp[q] = 1e10f; p_qs[q] = 1e10f;
+        }
+    } else {
+        fq_min = ini.get_s("fq_min", 0.05f); fq_max = ini.get_s("fq_max", 5.00f); fq_ref = ini.get_s("fq_ref", 1.00f);
+        vmodel_type = ini.get("vmodel_type", "uni");
+        vcut = ini.get_s("vcut", 0.0f);
+        const bool munk = ini.get_l("munk_profile", false), ef = ini.get_l("earth_flattening", false);
+        std::vector<float> zs(nzm), Cv(nzm);
+        for (int q = 0; q < nzm; q++) {
+            if (ef) { zs[q] = (float)(R_EARTH - R_EARTH * std::exp(-(double)zc[q] / R_EARTH)); Cv[q] = (float)std::exp((double)zc[q] / R_EARTH); }
+            else { zs[q] = zc[q]; Cv[q] = 1.0f; }
+        }
+        if (vmodel_type == "uni") {   // m_vmodel_uni.f90:50-136
+            const float vp0 = ini.get_s("vp0", 5.0f);
+            const float vs0 = ini.get_s("vs0", vp0 / std::sqrt(3.0f));
+            const float rho0 = ini.get_s("rho0", 2.7f), qp0 = ini.get_s("qp0", 1000000.0f), qs0 = ini.get_s("qs0", 1000000.0f);
+            bd0 = ini.get_s("topo0", 0.0f);
+            for (int q = 0; q < nzm; q++) {
+                float vp1, vs1, r1;
+                if (zs[q] > bd0) { vp1 = Cv[q] * vp0; vs1 = Cv[q] * vs0; r1 = rho0; p_qp[q] = qp0; p_qs[q] = qs0; }
+                else if (zc[q] > 0.0f) { vp1 = Cv[q] * seawater_vel(zs[q], munk); vs1 = 0.0f; r1 = 1.0f; p_qp[q] = 1000000.0f; p_qs[q] = 1000000.0f; }
+                else { vp1 = 0.0f; vs1 = 0.0f; r1 = 0.001f; p_qp[q] = 10.0f; p_qs[q] = 10.0f; }
+                p_rho[q] = r1;
+                p_mu[q] = r1 * vs1 * vs1;
+                p_lam[q] = r1 * (vp1 * vp1 - 2 * vs1 * vs1);
+            }
+        } else if (vmodel_type == "lhm") {   // m_vmodel_lhm.f90:55-160
+            const std::string fn = join_path(base, ini.get("fn_lhm", ""));
+            std::ifstream is(fn);
+            if (!is) return hfail("vmodel_lhm: cannot open " + fn + " (assert, m_vmodel_lhm.f90:72-76)");
+            std::vector<float> depth, r0, vp0, vs0, qp0, qs0;
+            std::string line;
+            while (std::getline(is, line)) {
+                if (blank_or_comment(line)) continue;
+                const std::vector<float> v = parse_reals(line);
+                if (v.size() < 6) continue;
+                depth.push_back(v[0]); r0.push_back(v[1]); vp0.push_back(v[2]); vs0.push_back(v[3]); qp0.push_back(v[4]); qs0.push_back(v[5]);
+            }
+            const int nl = (int)depth.size();
+            if (nl == 0) return hfail("vmodel_lhm: no layer in " + fn);
+            for (int l = nl - 2; l >= 0; l--)   // velocity cut-off :100-109
+                if ((vp0[l] < vcut || vs0[l] < vcut) && (vp0[l] > 0 && vs0[l] > 0)) {
+                    vp0[l] = vp0[l + 1]; vs0[l] = vs0[l + 1]; r0[l] = r0[l + 1]; qp0[l] = qp0[l + 1]; qs0[l] = qs0[l + 1];
+                }
+            bd0 = depth[0];
+            for (int q = 0; q < nzm; q++) {
+                if (zs[q] < depth[0]) {
+                    if (zs[q] < 0.0f) { p_rho[q] = 0.001f; p_mu[q] = 0.0f; p_lam[q] = 0.0f; p_qp[q] = 10.0f; p_qs[q] = 10.0f; }
+                    else {
+                        const float vp1 = Cv[q] * seawater_vel(zc[q], munk);
+                        p_rho[q] = 1.0f; p_mu[q] = 0.0f; p_lam[q] = 1.0f * vp1 * vp1; p_qp[q] = 1000000.0f; p_qs[q] = 1000000.0f;
+                    }
+                    continue;
+                }
+                float r1 = 0, vp1 = 0, vs1 = 0, a = 0, b = 0;
+                for (int l = 0; l < nl; l++)
+                    if (zs[q] >= depth[l]) { r1 = r0[l]; vp1 = Cv[q] * vp0[l]; vs1 = Cv[q] * vs0[l]; a = qp0[l]; b = qs0[l]; }
+                p_rho[q] = r1; p_mu[q] = r1 * vs1 * vs1; p_lam[q] = r1 * (vp1 * vp1 - 2 * vs1 * vs1); p_qp[q] = a; p_qs[q] = b;
+            }
+        } else {
+            return hfail("vmodel_type '" + vmodel_type + "' is outside the hot-path scope of this build (uni, lhm, benchmark_mode)");
+        }
+    }
+    for (size_t n = 0; n < n2; n++) bddep[n] = bd0;
+
+    // absorber homogenisation (m_medium.f90:124-190) copies columns outward; with laterally uniform input it is the
+    // identity in x and y, and in z it repeats the value at k = nz-na below it
+    for (int q = nz - na + 1 - kbeg_m; q < nzm; q++) {
+        const int s = nz - na - kbeg_m;
+        p_rho[q] = p_rho[s]; p_lam[q] = p_lam[s]; p_mu[q] = p_mu[s]; p_qp[q] = p_qp[s]; p_qs[q] = p_qs[s];
+    }
+    // tau-method (:193-207) and relaxed moduli (:231-271), still per depth
+    relax_times(nm, ts, fq_min, fq_max);
+    zeta = constq_zeta(nm, fq_min, fq_max, ts);
+    if (benchmark_mode) zeta = 0.0f;
+    std::vector<float> p_tp(nzm), p_tsx(nzm);
+    for (int q = 0; q < nzm; q++) { p_tp[q] = nm * zeta / p_qp[q]; p_tsx[q] = nm * zeta / p_qs[q]; }
+    if (nm > 0) {
+        const float omega = (float)(2 * PI_D * (double)fq_ref);
+        std::complex<float> cc(0.0f, 0.0f);
+        for (int m = 0; m < nm; m++) {
+            const std::complex<double> w = std::complex<double>(0.0, 1.0) * (double)omega * (double)ts[m];
+            const std::complex<double> qd = w / (1.0 - w);
+            cc = cc + std::complex<float>((float)qd.real(), (float)qd.imag());
+        }
+        cc = std::complex<float>(cc.real() / (float)nm, cc.imag() / (float)nm);
+        for (int q = 0; q < nzm; q++) {
+            const float rb2 = p_mu[q], ra2 = p_lam[q] + 2 * p_mu[q];
+            const std::complex<float> zs_ = 1.0f - cc * p_tsx[q], zp_ = 1.0f - cc * p_tp[q];
+            const float chi_mu = 1.0f / (1.0f / std::sqrt(zs_)).real();
+            const float chi_lam = 1.0f / (1.0f / std::sqrt(zp_)).real();
+            p_mu[q] = rb2 / (chi_mu * chi_mu);
+            p_lam[q] = ra2 / (chi_lam * chi_lam) - 2 * p_mu[q];
+        }
+    }
+    for (int j = 0; j < nym; j++)
+        for (int i = 0; i < nxm; i++) {
+            const size_t o = (size_t)nzm * ((size_t)i + (size_t)nxm * j);
+            std::copy(p_rho.begin(), p_rho.end(), rho.begin() + o);
+            std::copy(p_lam.begin(), p_lam.end(), lam.begin() + o);
+            std::copy(p_mu.begin(), p_mu.end(), mu.begin() + o);
+            std::copy(p_tp.begin(), p_tp.end(), taup.begin() + o);
+            std::copy(p_tsx.begin(), p_tsx.end(), taus.begin() + o);
+        }
+
+    // surface_detection m_medium.f90:339-394 -- evaluated per column exactly as the reference does (Q1: only
+    // i in [ibeg-1, iend+2], j likewise are scanned; the outermost margin keeps kbeg-1 = 0)
+    kfs.assign(n2, 0); kob.assign(n2, 0); kfs_top.assign(n2, 0); kfs_bot.assign(n2, 0); kob_top.assign(n2, 0); kob_bot.assign(n2, 0);
+    for (int j = jbeg - 1; j <= jend + 2; j++)
+        for (int i = ibeg - 1; i <= iend + 2; i++)
+            for (int k = 1; k <= nz - 1; k++) {
+                const size_t a = i3(k, i, j), b = i3(k + 1, i, j);
+                if (std::fabs(mu[a]) < EPS_SP && std::fabs(mu[b]) > EPS_SP) kob[i2(i, j)] = k;
+                if (std::fabs(lam[a]) < EPS_SP && std::fabs(lam[b]) > EPS_SP) kfs[i2(i, j)] = k;
+            }
+    for (int j = jbeg; j <= jend; j++)
+        for (int i = ibeg; i <= iend; i++) {
+            int f0_ = 1 << 30, f1 = -(1 << 30), o0 = 1 << 30, o1 = -(1 << 30);
+            for (int jj = j - 2; jj <= j + 3; jj++)
+                for (int ii = i - 2; ii <= i + 3; ii++) {
+                    f0_ = std::min(f0_, kfs[i2(ii, jj)]); f1 = std::max(f1, kfs[i2(ii, jj)]);
+                    o0 = std::min(o0, kob[i2(ii, jj)]); o1 = std::max(o1, kob[i2(ii, jj)]);
+                }
+            kfs_top[i2(i, j)] = std::max(f0_ - 2, 1); kfs_bot[i2(i, j)] = std::min(f1 + 2, nz);
+            kob_top[i2(i, j)] = std::max(o0 - 2, 1); kob_bot[i2(i, j)] = std::min(o1 + 2, nz);
+        }
+    // velocity_minmax :396-427 (local part)
+    float vmx = -1.0f, vmn = 1e30f;
+    for (int j = jbeg; j <= jend; j++)
+        for (int i = ibeg; i <= iend; i++)
+            for (int k = kfs[i2(i, j)] + 1; k <= nz; k++) {
+                const size_t n = i3(k, i, j);
+                const float vp = std::sqrt((lam[n] + 2 * mu[n]) / rho[n]), vs = std::sqrt(mu[n] / rho[n]);
+                vmx = std::max(vmx, vp);
+                if (vs < EPS_SP) continue;
+                vmn = std::min(vmn, vs);
+            }
+    vmin_local = vmin = vmn;
+    vmax_local = vmax = vmx;
+    if (ini.get_l("stabilize_pml", false)) return hfail("stabilize_pml = .true. is outside the hot-path scope of this build");
+    return 0;
+}
+
+void swpc3d_host::setup_kernel() {   // m_kernel.f90:58-67 (the device computes its own copy; kept for reporting)
+    d2 = 0.0f;
+    if (nm > 0) {
+        float sum = 0.0f;
+        for (int m = 0; m < nm; m++) {
+            c1[m] = (2 * ts[m] - dt) / (2 * ts[m] + dt);
+            c2[m] = (2) / (2 * ts[m] + dt) / nm;
+            d1[m] = 2 * ts[m] / (2 * ts[m] - dt);
+            sum += dt / (2 * ts[m] - dt);
+        }
+        d2 = sum / nm;
+    }
+}
+
+int swpc3d_host::setup_source(const IniFile &ini) {   // m_source.f90:41-314
+    pw_mode = ini.get_l("pw_mode", false);
+    green_mode = ini.get_l("green_mode", false);
+    bf_mode = ini.get_l("bf_mode", false);
+    if ((pw_mode || green_mode) && !benchmark_mode) return hfail("pw_mode / green_mode are outside the hot-path scope of this build");
+    fn_stf = ini.get("fn_stf", "");
+    stftype = ini.get("stftype", "kupper");
+    if (stftype == "scosine") stftype = "cosine";
+    stf_format = ini.get("stf_format", "xym0ij");
+    sdep_fit = ini.get("sdep_fit", "asis");
+    earth_flattening = ini.get_l("earth_flattening", false);
+
+    struct Src { float x, y, z, t0, tr, mo, m[6]; };
+    std::vector<Src> g;
+    if (benchmark_mode) {   // :115-166
+        stftype = "kupper"; bf_mode = false; pw_mode = false;
+        Src s{};
+        s.x = 0.0f; s.y = 0.0f; s.z = 5.0f; s.mo = 1e15f; s.t0 = 0.1f; s.tr = 2.0f;
+        s.m[0] = s.m[1] = s.m[2] = 1 / std::sqrt(3.0f);
+        g.push_back(s);
+        evlo = clon; evla = clat; evdp = s.z;
+        std::copy(s.m, s.m + 6, m0ij);
+    } else {
+        const std::string fn = join_path(base, fn_stf);
+        std::ifstream is(fn);
+        if (!is) return hfail("source__setup: cannot open " + fn);
+        const bool ll = stf_format.compare(0, 2, "ll") == 0, xy = stf_format.compare(0, 2, "xy") == 0;
+        const std::string kind = stf_format.size() >= 6 ? stf_format.substr(2, 4) : "";
+        std::string line;
+        while (std::getline(is, line)) {
+            if (blank_or_comment(line)) continue;
+            const std::vector<float> v = parse_reals(line);
+            Src s{};
+            if (bf_mode) {   // source__grid_bodyforce :741-768
+                if (v.size() < 8 || !(ll || xy)) return hfail("source file: bad body-force record / invalid source type");
+                if (xy) { s.x = v[0]; s.y = v[1]; } else geomap_g2c(v[0], v[1], clon, clat, phi, s.x, s.y);
+                s.z = v[2]; s.t0 = v[3]; s.tr = v[4]; s.m[0] = v[5]; s.m[1] = v[6]; s.m[2] = v[7];
+                if (g.empty()) { geomap_c2g(s.x, s.y, clon, clat, phi, evlo, evla); evdp = s.z; f0[0] = s.m[0]; f0[1] = s.m[1]; f0[2] = s.m[2]; otim = s.t0; }
+                g.push_back(s);
+                continue;
+            }
+            if (!(ll || xy) || !(kind == "m0ij" || kind == "m0dc" || kind == "mwij" || kind == "mwdc"))
+                return hfail("stf_format '" + stf_format + "' is outside the hot-path scope of this build (xy|ll + m0|mw + ij|dc)");
+            const size_t need = kind[2] == 'i' ? 12 : 9;
+            if (v.size() < need) return hfail("source file: bad moment record (assert(ierr == 0), m_source.f90:517)");
+            if (xy) { s.x = v[0]; s.y = v[1]; } else geomap_g2c(v[0], v[1], clon, clat, phi, s.x, s.y);
+            s.z = v[2]; s.t0 = v[3]; s.tr = v[4];
+            s.mo = kind[1] == '0' ? v[5] : seismic_moment(v[5]);
+            if (kind[2] == 'i') std::copy(v.begin() + 6, v.begin() + 12, s.m);
+            else sdr2moment(v[6] - phi, v[7], v[8], s.m);
+            if (g.empty()) {   // :675-687
+                geomap_c2g(s.x, s.y, clon, clat, phi, evlo, evla);
+                sx0 = s.x; sy0 = s.y; evdp = s.z; std::copy(s.m, s.m + 6, m0ij); otim = s.t0;
+            }
+            g.push_back(s);
+        }
+    }
+    if (earth_flattening)
+        for (Src &s : g) s.z = -(float)(R_EARTH * std::log((R_EARTH - (double)s.z) / R_EARTH));
+    fcut = 0.0f;
+    for (const Src &s : g) fcut = std::max(fcut, 1 / s.tr);
+    fmax = 2 * fcut;
+    if (bf_mode) {
+        float sum = 0.0f;
+        for (const Src &s : g) sum += s.m[0] * s.m[0] + s.m[1] * s.m[1] + s.m[2] * s.m[2];
+        M0 = std::sqrt(sum);
+        UC = UC * 1000;
+    } else {
+        float sum = 0.0f;
+        for (const Src &s : g) sum += s.mo;
+        M0 = sum;
+    }
+    src_ijk.clear(); mo.clear(); mij.clear(); srcprm.clear();
+    const size_t n2 = (size_t)nxm * nym;
+    for (const Src &s : g) {
+        int is = x2i(s.x, xbeg, (float)dx), js = x2i(s.y, ybeg, (float)dy), ks = x2i(s.z, zbeg, (float)dz);
+        if (!(ibeg - 2 <= is && is <= iend + 3 && jbeg - 2 <= js && js <= jend + 3 && 1 - 2 <= ks && ks <= nz + 3)) continue;   // :209-211
+        float sz = s.z;
+        if (sdep_fit.size() == 3 && sdep_fit[0] == 'b' && sdep_fit[1] == 'd' && std::isdigit((unsigned char)sdep_fit[2])) {   // :263-271
+            sz = bddep[(size_t)(sdep_fit[2] - '0') * n2 + i2(is, js)];
+            ks = x2i(sz, zbeg, (float)dz);
+        }
+        if (!(xbeg <= s.x && s.x <= xend && ybeg <= s.y && s.y <= yend && zbeg <= sz && sz <= zend))
+            return hfail("source__setup: source outside of the model space (assert, m_source.f90:277-281)");
+        src_ijk.push_back(is); src_ijk.push_back(js); src_ijk.push_back(ks);
+        srcprm.push_back(s.t0); srcprm.push_back(s.tr);
+        if (bf_mode) {
+            mo.push_back(0.0);
+            for (int q = 0; q < 3; q++) mij.push_back(field_bytes == 8 ? (double)s.m[q] / (double)M0 : (double)(s.m[q] / M0));
+            for (int q = 3; q < 6; q++) mij.push_back(0.0);
+        } else {
+            mo.push_back(field_bytes == 8 ? (double)s.mo / (double)M0 : (double)(s.mo / M0));   // :302, real(MP)/real(SP)
+            for (int q = 0; q < 6; q++) mij.push_back((double)s.m[q]);
+        }
+    }
+    return 0;
+}
+
+int swpc3d_host::setup_absorb() {
+    const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
+    if (abc_type == "pml") {   // m_absorb_p.f90:75-93
+        const float hx = na * fdx, hy = na * fdy, hz = na * fdz;
+        gxc.assign(4 * (size_t)nxp, 0.f); gxe.assign(4 * (size_t)nxp, 0.f);
+        gyc.assign(4 * (size_t)nyp, 0.f); gye.assign(4 * (size_t)nyp, 0.f);
+        gzc.assign(4 * (size_t)nz, 0.f); gze.assign(4 * (size_t)nz, 0.f);
+        for (int i = ibeg; i <= iend; i++) {
+            damping_profile(xc[i - ibeg_m], hx, xbeg, xend, na, fcut, dt, &gxc[4 * (i - ibeg)]);
+            damping_profile(xc[i - ibeg_m] + fdx / 2.0f, hx, xbeg, xend, na, fcut, dt, &gxe[4 * (i - ibeg)]);
+        }
+        for (int j = jbeg; j <= jend; j++) {
+            damping_profile(yc[j - jbeg_m], hy, ybeg, yend, na, fcut, dt, &gyc[4 * (j - jbeg)]);
+            damping_profile(yc[j - jbeg_m] + fdy / 2.0f, hy, ybeg, yend, na, fcut, dt, &gye[4 * (j - jbeg)]);
+        }
+        for (int k = 1; k <= nz; k++) {
+            damping_profile(zc[k - kbeg_m], hz, zbeg, zend, na, fcut, dt, &gzc[4 * (k - 1)]);
+            damping_profile(zc[k - kbeg_m] + fdz / 2.0f, hz, zbeg, zend, na, fcut, dt, &gze[4 * (k - 1)]);
+        }
+    } else {   // m_absorb_c.f90:38-101
+        const float alpha = 0.09f, Lx = na * fdx, Ly = na * fdy, Lz = na * fdz;
+        auto sq = [](float v) { return v * v; };
+        cgx_c.assign(nxm, 1.0f); cgx_b.assign(nxm, 1.0f); cgy_c.assign(nym, 1.0f); cgy_b.assign(nym, 1.0f); cgz_c.assign(nzm, 1.0f); cgz_b.assign(nzm, 1.0f);
+        auto fill = [&](int lo, int hi, int lo_m, int n, float d, float L, std::vector<float> &gc, std::vector<float> &gb, bool top_open) {
+            for (int q = lo; q <= hi; q++) {
+                if (q <= na) {
+                    if (top_open) continue;
+                    gc[q - lo_m] = std::exp(-(alpha * sq(1.0f - (i2x(q, 0.0f, d)) / L)));
+                    gb[q - lo_m] = std::exp(-(alpha * sq(1.0f - ((i2x(q, 0.0f, d) + d / 2)) / L)));
+                } else if (q >= n - na + 1) {
+                    gc[q - lo_m] = std::exp(-(alpha * sq(1.0f - (i2x(q, n * d, -d) + d / 2) / L)));
+                    gb[q - lo_m] = std::exp(-(alpha * sq(1.0f - ((i2x(q, n * d, -d))) / L)));
+                }
+            }
+        };
+        fill(ibeg, iend, ibeg_m, nx, fdx, Lx, cgx_c, cgx_b, false);
+        fill(jbeg, jend, jbeg_m, ny, fdy, Ly, cgy_c, cgy_b, false);
+        fill(1, nz, kbeg_m, nz, fdz, Lz, cgz_c, cgz_b, true);   // the top band stays 1 (:86-93)
+    }
+    return 0;
+}
+
+int swpc3d_host::setup_wav(const IniFile &ini) {   // m_wav.f90:54-271
+    ntdec_w = ini.get_i("ntdec_w", 10);
+    sw_wav_v = ini.get_l("sw_wav_v", false);
+    const bool other = ini.get_l("sw_wav_u", false) || ini.get_l("sw_wav_stress", false) || ini.get_l("sw_wav_strain", false);
+    wav_format = ini.get("wav_format", "sac");
+    st_format = ini.get("st_format", "xy");
+    fn_stloc = ini.get("fn_stloc", "");
+    ntdec_r = ini.get_i("ntdec_r", 10);   // m_report.f90:47
+    if (!(sw_wav_v || other)) return 0;
+    ntw = (int)std::floor((float)(nt - 1) / (float)ntdec_w + 1.0f);
+    std::ifstream is(join_path(base, fn_stloc));
+    if (!is) return 0;   // 'no station location file found' :157-161
+    const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
+    const size_t n2 = (size_t)nxm * nym;
+    std::string line;
+    while (std::getline(is, line)) {
+        if (blank_or_comment(line)) continue;
+        std::istringstream ls(line);
+        float a, b, z;
+        std::string name, zsw;
+        if (!(ls >> a >> b >> z >> name >> zsw)) continue;
+        name = name.substr(0, 8);
+        zsw = zsw.substr(0, 3);
+        float x, y, lo, la;
+        if (st_format == "xy") { x = a; y = b; geomap_c2g(x, y, clon, clat, phi, lo, la); }
+        else if (st_format == "ll") { lo = a; la = b; geomap_g2c(lo, la, clon, clat, phi, x, y); }
+        else return hfail("unknown st_format: " + st_format);
+        const int is_ = x2i(x, xbeg, fdx), js = x2i(y, ybeg, fdy);
+        int ks = x2i(z, zbeg, fdz);
+        if (!(i2x(1, xbeg, fdx) < x && x < i2x(nx, xbeg, fdx) && i2x(1, ybeg, fdy) < y && y < i2x(ny, ybeg, fdy) && 1 < ks && ks < nz)) continue;
+        if (!(ibeg <= is_ && is_ <= iend && jbeg <= js && js <= jend)) continue;   // owner rank only (:203)
+        if (zsw == "dep") ks = x2i(z, zbeg, fdz);
+        else if (zsw == "fsb") ks = kfs[i2(is_, js)] + 1;
+        else if (zsw == "obb") ks = kob[i2(is_, js)] + 1;
+        else if (zsw == "oba") ks = kob[i2(is_, js)] - 1;
+        else if (zsw.size() == 3 && zsw[0] == 'b' && zsw[1] == 'd' && std::isdigit((unsigned char)zsw[2]))
+            ks = x2i(bddep[(size_t)(zsw[2] - '0') * n2 + i2(is_, js)], zbeg, fdz);
+        else ks = x2i(z, zbeg, fdz);
+        if (ks > nz) ks = nz - 1;
+        if (ks < 1) ks = 1 + 1;
+        st_ijk.push_back(is_); st_ijk.push_back(js); st_ijk.push_back(ks);
+        xst.push_back(x); yst.push_back(y); zst.push_back(z); stlo.push_back(lo); stla.push_back(la); stnm.push_back(name);
+    }
+    return 0;
+}
+
+int swpc3d_host::setup(const IniFile &ini, int nm_, int myid_, int npx, int npy, int nt_o) {
+    if (nm_ < 0 || nm_ > 3) return hfail("nm must be 0..3");
+    nm = nm_;
+    myid = myid_;
+    if (setup_global(ini, npx, npy, nt_o)) return 1;   // main.f90:64 order
+    if (setup_geometry()) return 1;
+    if (setup_medium(ini)) return 1;
+    setup_kernel();
+    if (setup_source(ini)) return 1;
+    if (setup_absorb()) return 1;
+    if (setup_wav(ini)) return 1;
+    return 0;
+}
+
+// ============================================================================================================
+// C interface
+extern "C" {
+
+static int host_create(IniFile &ini, const char *base_dir, int nm, int myid, int npx, int npy, int nt, int fb, swpc3d_host **out) {
+    if (!out) return hfail("null out");
+    *out = nullptr;
+    if (fb != 8 && fb != 4) return hfail("field_bytes must be 8 or 4");
+    ini.strict = ini.get_l("strict_mode", false);   // main.f90:60-61
+    swpc3d_host *h = new swpc3d_host();
+    h->base = base_dir ? base_dir : "";
+    h->field_bytes = fb;
+    if (h->setup(ini, nm, myid, npx, npy, nt)) { delete h; return 1; }
+    *out = h;
+    return 0;
+}
+
+int swpc3d_host_create(const char *inf_path, const char *base_dir, int32_t nm, int32_t myid, int32_t npx, int32_t npy, int32_t nt,
+                       int32_t fb, swpc3d_host **out) {
+    IniFile ini;
+    if (!inf_path || !IniFile::from_file(inf_path, ini)) return hfail(std::string("cannot open parameter file ") + (inf_path ? inf_path : "(null)"));
+    return host_create(ini, base_dir, nm, myid, npx, npy, nt, fb, out);
+}
+int swpc3d_host_create_from_text(const char *text, const char *base_dir, int32_t nm, int32_t myid, int32_t npx, int32_t npy, int32_t nt,
+                                 int32_t fb, swpc3d_host **out) {
+    IniFile ini = IniFile::from_text(text ? text : "");
+    return host_create(ini, base_dir, nm, myid, npx, npy, nt, fb, out);
+}
+int swpc3d_host_destroy(swpc3d_host *h) {
+    if (!h) return 0;
+    if (h->dev) swpc3d_destroy(h->dev);
+    delete h;
+    return 0;
+}
+
+const char *swpc3d_host_last_error(void) { return g_herr.c_str(); }
+
+int swpc3d_host_get_int(swpc3d_host *h, const char *name, int32_t *v) {
+    if (!h || !name || !v) return hfail("null argument");
+    const std::string n = name;
+#define GI(x) if (n == #x) { *v = (int32_t)h->x; return 0; }
+    GI(nx) GI(ny) GI(nz) GI(nt) GI(na) GI(nm) GI(nproc_x) GI(nproc_y) GI(myid) GI(ibeg) GI(iend) GI(jbeg) GI(jend) GI(nxp) GI(nyp)
+    GI(ibeg_k) GI(iend_k) GI(jbeg_k) GI(jend_k) GI(kbeg_k) GI(kend_k) GI(ntw) GI(ntdec_w) GI(ntdec_r) GI(bf_mode) GI(nzm) GI(nxm) GI(nym)
+    GI(exedate) GI(tz_minutes) GI(field_bytes)
+#undef GI
+    if (n == "nsrc") { *v = (int32_t)(h->src_ijk.size() / 3); return 0; }
+    if (n == "nst") { *v = (int32_t)(h->st_ijk.size() / 3); return 0; }
+    return hfail("unknown int " + n);
+}
+int swpc3d_host_get_double(swpc3d_host *h, const char *name, double *v) {
+    if (!h || !name || !v) return hfail("null argument");
+    const std::string n = name;
+#define GD(x) if (n == #x) { *v = (double)h->x; return 0; }
+    GD(dx) GD(dy) GD(dz) GD(dt) GD(xbeg) GD(ybeg) GD(zbeg) GD(tbeg) GD(vmin) GD(vmax) GD(vmin_local) GD(vmax_local) GD(fmax) GD(fcut)
+    GD(M0) GD(UC) GD(zeta) GD(d2) GD(loop_seconds) GD(evlo) GD(evla) GD(evdp) GD(clon) GD(clat) GD(phi)
+#undef GD
+    if (n == "c") { *v = (double)(h->dt / stable_dt((float)h->dx, (float)h->dy, (float)h->dz, h->vmax)); return 0; }   // m_fdtool.f90:99-113
+    if (n == "r") {   // m_fdtool.f90:116-134
+        const float dh = std::max(std::max((float)h->dx, (float)h->dy), (float)h->dz);
+        *v = (double)((h->vmin / h->fmax) / dh);
+        return 0;
+    }
+    return hfail("unknown double " + n);
+}
+int swpc3d_host_get_string(swpc3d_host *h, const char *name, char *buf, int32_t cap) {
+    if (!h || !name || !buf || cap <= 0) return hfail("null argument");
+    const std::string n = name;
+    const std::string *s = nullptr;
+    if (n == "title") s = &h->title; else if (n == "odir") s = &h->odir; else if (n == "abc_type") s = &h->abc_type;
+    else if (n == "stftype") s = &h->stftype; else if (n == "vmodel_type") s = &h->vmodel_type; else if (n == "stf_format") s = &h->stf_format;
+    else if (n == "wav_format") s = &h->wav_format;
+    if (!s) return hfail("unknown string " + n);
+    std::snprintf(buf, (size_t)cap, "%s", s->c_str());
+    return 0;
+}
+int swpc3d_host_set_minmax(swpc3d_host *h, float vmin, float vmax) {
+    if (!h) return hfail("null handle");
+    h->vmin = vmin; h->vmax = vmax;
+    return 0;
+}
+int swpc3d_host_set_exedate(swpc3d_host *h, int32_t exedate, int32_t tz) {
+    if (!h) return hfail("null handle");
+    h->exedate = exedate; h->tz_minutes = tz;
+    return 0;
+}
+
+extern "C++" {
+template <typename T>
+static int put(const std::vector<T> &v, void *out, int64_t cap, int64_t *n) {
+    if (n) *n = (int64_t)v.size();
+    if (out) std::memcpy(out, v.data(), sizeof(T) * (size_t)std::min<int64_t>(cap, (int64_t)v.size()));
+    return 0;
+}
+}
+int swpc3d_host_get_array(swpc3d_host *h, const char *name, void *out, int64_t cap, int64_t *n) {
+    if (!h || !name) return hfail("null argument");
+    const std::string s = name;
+#define GA(x) if (s == #x) return put(h->x, out, cap, n);
+    GA(rho) GA(lam) GA(mu) GA(taup) GA(taus) GA(kfs) GA(kob) GA(kfs_top) GA(kfs_bot) GA(kob_top) GA(kob_bot) GA(kbeg_a)
+    GA(gxc) GA(gxe) GA(gyc) GA(gye) GA(gzc) GA(gze) GA(src_ijk) GA(st_ijk) GA(mo) GA(mij) GA(srcprm) GA(xc) GA(yc) GA(zc)
+    GA(stlo) GA(stla) GA(wav)
+#undef GA
+    if (s == "gx_c") return put(h->cgx_c, out, cap, n);
+    if (s == "gx_b") return put(h->cgx_b, out, cap, n);
+    if (s == "gy_c") return put(h->cgy_c, out, cap, n);
+    if (s == "gy_b") return put(h->cgy_b, out, cap, n);
+    if (s == "gz_c") return put(h->cgz_c, out, cap, n);
+    if (s == "gz_b") return put(h->cgz_b, out, cap, n);
+    auto small = [&](const float *p) { std::vector<float> v(p, p + h->nm); return put(v, out, cap, n); };
+    if (s == "ts") return small(h->ts);
+    if (s == "c1") return small(h->c1);
+    if (s == "c2") return small(h->c2);
+    if (s == "d1") return small(h->d1);
+    return hfail("unknown array " + s);
+}
+int swpc3d_host_station_name(swpc3d_host *h, int32_t i, char *buf9) {
+    if (!h || !buf9 || i < 0 || (size_t)i >= h->stnm.size()) return hfail("bad station index");
+    std::memset(buf9, 0, 9);
+    std::strncpy(buf9, h->stnm[(size_t)i].c_str(), 8);
+    return 0;
+}
+
+// `!$acc enter data copyin(...)` main.f90:80-113
+int swpc3d_host_attach_device(swpc3d_host *h, int32_t device) {
+    if (!h) return hfail("null handle");
+    if (h->dev) { swpc3d_destroy(h->dev); h->dev = nullptr; }
+    swpc3d_grid g{};
+    g.nx = h->nx; g.ny = h->ny; g.nz = h->nz; g.nproc_x = h->nproc_x; g.nproc_y = h->nproc_y; g.myid = h->myid;
+    g.ibeg = h->ibeg; g.iend = h->iend; g.jbeg = h->jbeg; g.jend = h->jend; g.ipad = h->ipad; g.jpad = h->jpad; g.kpad = h->kpad;
+    g.ibeg_k = h->ibeg_k; g.iend_k = h->iend_k; g.jbeg_k = h->jbeg_k; g.jend_k = h->jend_k; g.kbeg_k = h->kbeg_k; g.kend_k = h->kend_k;
+    g.na = h->na; g.nm = h->nm; g.abc_type = h->abc_type == "pml" ? SWPC3D_ABC_PML : SWPC3D_ABC_CERJAN;
+    g.field_bytes = h->field_bytes; g.device = device; g.dx = h->dx; g.dy = h->dy; g.dz = h->dz; g.dt = h->dt;
+#define DV(call) if (call) return hfail(std::string("device: ") + swpc3d_last_error());
+    DV(swpc3d_create(&g, h->ts, &h->dev));
+    DV(swpc3d_upload_medium(h->dev, h->rho.data(), h->lam.data(), h->mu.data(), h->taup.data(), h->taus.data(), h->kfs.data(), h->kob.data(),
+                            h->kfs_top.data(), h->kfs_bot.data(), h->kob_top.data(), h->kob_bot.data(), h->kbeg_a.data()));
+    if (g.abc_type == SWPC3D_ABC_PML) { DV(swpc3d_setup_pml(h->dev, h->gxc.data(), h->gxe.data(), h->gyc.data(), h->gye.data(), h->gzc.data(), h->gze.data())); }
+    else { DV(swpc3d_setup_cerjan(h->dev, h->cgx_c.data(), h->cgx_b.data(), h->cgy_c.data(), h->cgy_b.data(), h->cgz_c.data(), h->cgz_b.data())); }
+    const int nsrc = (int)(h->src_ijk.size() / 3);
+    if (nsrc > 0) {
+        std::vector<int> a(nsrc), b(nsrc), c(nsrc);
+        std::vector<double> m[6];
+        for (int q = 0; q < 6; q++) m[q].resize(nsrc);
+        for (int i = 0; i < nsrc; i++) {
+            a[i] = h->src_ijk[3 * i]; b[i] = h->src_ijk[3 * i + 1]; c[i] = h->src_ijk[3 * i + 2];
+            for (int q = 0; q < 6; q++) m[q][i] = h->mij[6 * (size_t)i + q];
+        }
+        DV(swpc3d_set_sources(h->dev, nsrc, a.data(), b.data(), c.data(), h->mo.data(), m[0].data(), m[1].data(), m[2].data(), m[3].data(),
+                              m[4].data(), m[5].data(), h->srcprm.data(), h->stftype.c_str(), h->bf_mode ? 1 : 0, h->tbeg));
+    }
+    const int nst = (int)(h->st_ijk.size() / 3);
+    if (nst > 0 && h->sw_wav_v) {
+        std::vector<int> a(nst), b(nst), c(nst);
+        for (int i = 0; i < nst; i++) { a[i] = h->st_ijk[3 * i]; b[i] = h->st_ijk[3 * i + 1]; c[i] = h->st_ijk[3 * i + 2]; }
+        DV(swpc3d_set_stations(h->dev, nst, a.data(), b.data(), c.data(), h->ntdec_w, h->ntw, h->M0, h->UC));
+    }
+#undef DV
+    return 0;
+}
+swpc3d_handle *swpc3d_host_handle(swpc3d_host *h) { return h ? h->dev : nullptr; }
+
+int swpc3d_host_banner(swpc3d_host *h) {   // m_report.f90:64-92
+    if (!h) return hfail("null handle");
+    double c, r;
+    swpc3d_host_get_double(h, "c", &c);
+    swpc3d_host_get_double(h, "r", &r);
+    std::fprintf(stderr, "\n ------------------------------------------------------------------------------\n");
+    std::fprintf(stderr, "  SWPC_3D (swpc3d_b200, B200-native time loop)%s\n", h->benchmark_mode ? " (benchmark mode) " : (h->bf_mode ? " (body force mode) " : ""));
+    std::fprintf(stderr, " ------------------------------------------------------------------------------\n\n");
+    std::fprintf(stderr, "  Grid Size               : %8d x %6d x %6d\n", h->nx, h->ny, h->nz);
+    std::fprintf(stderr, "  MPI Partitioning        : %8d x %4d\n", h->nproc_x, h->nproc_y);
+    std::fprintf(stderr, "  Stability  Condition c  : %15.3f  (c<1)\n", c);
+    std::fprintf(stderr, "  Wavelength Condition r  : %15.3f  (r>5-10)\n", r);
+    std::fprintf(stderr, "  Minimum velocity        : %15.3f  [km/s]\n", (double)h->vmin);
+    std::fprintf(stderr, "  Maximum velocity        : %15.3f  [km/s]\n", (double)h->vmax);
+    std::fprintf(stderr, "  Maximum frequency       : %15.3f  [Hz]\n\n", (double)h->fmax);
+    std::fprintf(stderr, " ------------------------------------------------------------------------------\n\n");
+    if (c > 1.0) return hfail("stability condition is violated (assert(c <= 1.0), m_report.f90:100-103)");
+    return 0;
+}
+
+int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, float *vm, int32_t nvm, int32_t *nrec) {
+    if (!h || !h->dev) return hfail("swpc3d_host_run: no device attached");
+    int rec = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int it = it0; it <= it1; it++) {
+        if (h->ntdec_r > 0 && it % h->ntdec_r == 0) {   // report__progress m_report.f90:120-185
+            float v[3];
+            if (swpc3d_vmax_global(h->dev, v)) return hfail(std::string("device: ") + swpc3d_last_error());
+            const float mx = std::max(v[0], std::max(v[1], v[2]));
+            if (mx * h->UC > 1e5f) return hfail("numerical divergence detected (m_report.f90:144-151)");
+            for (int q = 0; q < 3; q++) v[q] = v[q] * h->UC * h->M0;
+            if (vm && rec < nvm) { vm[3 * rec] = v[0]; vm[3 * rec + 1] = v[1]; vm[3 * rec + 2] = v[2]; }
+            rec++;
+            if (verbose && h->myid == 0) {
+                const double tt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                double etas = (double)(h->nt - it) / (double)std::max(1, it - it0 + 1) * tt;
+                const int eh = (int)(etas / 3600); etas -= eh * 3600.0;
+                const int em = (int)(etas / 60); etas -= em * 60.0;
+                std::fprintf(stderr, "  it=%07d,%6.3f s/loop, eta %03d:%02d:%02d, (%9.2E %9.2E %9.2E )\n", it, tt / std::max(1, it - it0 + 1), eh, em,
+                             (int)etas, (double)v[0], (double)v[1], (double)v[2]);
+            }
+        }
+        if (swpc3d_step(h->dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
+    }
+    if (swpc3d_sync(h->dev)) return hfail(std::string("device: ") + swpc3d_last_error());
+    h->loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (nrec) *nrec = rec;
+    return 0;
+}
+
+// SAC writer: m_sac.f90:314-449 (header), m_wav.f90:346-393 (values), :782-792 (file names)
+static void put_chars(char *dst, const std::string &s, int n) {
+    for (int q = 0; q < n; q++) dst[q] = q < (int)s.size() ? s[q] : ' ';
+}
+static void mkdirs(const std::string &p) {
+    for (size_t q = 1; q <= p.size(); q++)
+        if (q == p.size() || p[q] == '/') mkdir(p.substr(0, q).c_str(), 0777);
+}
+int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles) {
+    if (!h) return hfail("null handle");
+    if (nfiles) *nfiles = 0;
+    const int nst = (int)(h->st_ijk.size() / 3);
+    if (!h->sw_wav_v || nst == 0 || h->ntw <= 0) return 0;
+    if (!h->dev) return hfail("swpc3d_host_write_sac: no device attached");
+    h->wav.assign((size_t)h->ntw * 3 * nst, 0.0f);
+    if (swpc3d_get_wav(h->dev, h->wav.data())) return hfail(std::string("device: ") + swpc3d_last_error());   // `update self(wav_vel)` m_wav.f90:672
+    const std::string dir = std::string(odir ? odir : h->odir.c_str()) + "/wav";
+    mkdirs(dir);
+    const char *cmpnm[3] = {"Vx", "Vy", "Vz"};
+    const time_t tt = (time_t)h->exedate + (time_t)h->tz_minutes * 60;   // daytim__localtime m_daytim.f90:262-264
+    struct tm g;
+    gmtime_r(&tt, &g);
+    int count = 0;
+    for (int s = 0; s < nst; s++)
+        for (int c = 0; c < 3; c++) {
+            float f[70];
+            int32_t iv[35], lv[5];
+            char a[192];
+            std::fill(f, f + 70, -12345.0f);
+            std::fill(iv, iv + 35, -12345);
+            std::fill(lv, lv + 5, 0);
+            for (int q = 0; q < 24; q++) put_chars(a + 8 * q, "-12345", 8);
+            put_chars(a + 8, "-12345", 16);
+            const double delta = (double)(h->ntdec_w * h->dt);
+            f[0] = (float)((int)(delta * 1e7)) / 1e7f;
+            f[5] = h->tbeg; f[7] = h->otim;
+            f[31] = h->stla[s]; f[32] = h->stlo[s]; f[34] = h->zst[s] * 1000;
+            f[35] = h->evla; f[36] = h->evlo; f[38] = h->evdp; f[39] = moment_magnitude(h->M0);
+            if (h->bf_mode) { f[40] = h->f0[0]; f[41] = h->f0[1]; f[42] = h->f0[2]; }
+            else for (int q = 0; q < 6; q++) f[40 + q] = h->m0ij[q];
+            f[46] = h->clon; f[47] = h->clat; f[48] = h->phi;
+            const float ddx = h->sx0 - h->xst[s], ddy = h->sy0 - h->yst[s];
+            f[50] = std::sqrt(ddx * ddx + ddy * ddy);
+            f[51] = rad2deg_s(std::atan2(h->yst[s] - h->sy0, h->xst[s] - h->sx0));
+            f[52] = rad2deg_s(std::atan2(h->sy0 - h->yst[s], h->sx0 - h->xst[s]));
+            f[57] = c == 0 ? 0.0f + h->phi : (c == 1 ? 90.0f + h->phi : 0.0f);
+            f[58] = 90.0f;
+            iv[0] = g.tm_year + 1900; iv[1] = g.tm_yday + 1; iv[2] = g.tm_hour; iv[3] = g.tm_min; iv[4] = g.tm_sec; iv[5] = 0;
+            iv[6] = 6; iv[9] = h->ntw; iv[15] = 1; iv[16] = 7;
+            lv[0] = 1; lv[2] = 1;
+            put_chars(a, h->stnm[s], 8);
+            std::string t = h->title;
+            t.erase(0, t.find_first_not_of(' ') == std::string::npos ? t.size() : t.find_first_not_of(' '));
+            put_chars(a + 8, t.substr(0, 16), 16);
+            put_chars(a + 160, cmpnm[c], 8);
+            const std::string fn = dir + "/" + h->title + ".3d." + h->stnm[s] + "." + cmpnm[c] + ".sac";
+            FILE *fp = std::fopen(fn.c_str(), "wb");
+            if (!fp) return hfail("cannot write " + fn);
+            std::fwrite(f, 4, 70, fp); std::fwrite(iv, 4, 35, fp); std::fwrite(lv, 4, 5, fp); std::fwrite(a, 1, 192, fp);
+            std::fwrite(h->wav.data() + (size_t)h->ntw * 3 * s + (size_t)h->ntw * c, 4, (size_t)h->ntw, fp);
+            std::fclose(fp);
+            count++;
+        }
+    if (nfiles) *nfiles = count;
+    return 0;
+}
+
+}   // extern "C"

@@ -62,6 +62,24 @@ enum Aux { axVx = 0, ayVx, azVx, axVy, ayVy, azVy, axVz, ayVz, azVz,
 constexpr float FLT_EPS_ = 1.1920929e-07f;   // epsilon(1.0)
 
 template <typename T> __device__ __forceinline__ T ldro(const T *p) { return __ldg(p); }
+// streamed (touched once per sweep) data: evict-first so that L1/L2 keep the stencil neighbours
+#ifndef SWPC_STREAM_HINT
+#define SWPC_STREAM_HINT 1
+#endif
+template <typename T> __device__ __forceinline__ T lds_(const T *p) {
+#if SWPC_STREAM_HINT
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename T> __device__ __forceinline__ void sts_(T *p, T v) {
+#if SWPC_STREAM_HINT
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // m_kernel.f90:103-104: isign = sign(1, max((k-kfs_top)(kfs_bot-k), (k-kob_top)(kob_bot-k)))
 __device__ __forceinline__ int fd_order_sel(int k, const int4 b) {
@@ -126,14 +144,15 @@ __device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n
             const float c1 = p.c1[m], c2 = p.c2[m], d1 = p.d1[m];
             float *rxx = R + (0 * NM + m) * nc, *ryy = R + (1 * NM + m) * nc, *rzz = R + (2 * NM + m) * nc;
             float *ryz = R + (3 * NM + m) * nc, *rxz = R + (4 * NM + m) * nc, *rxy = R + (5 * NM + m) * nc;
-            const float nxx = c1 * (*rxx) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dyVy_dzVz) * dt;
-            const float nyy = c1 * (*ryy) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dzVz) * dt;
-            const float nzz = c1 * (*rzz) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dyVy) * dt;
+            const float oxx = lds_(rxx), oyy = lds_(ryy), ozz = lds_(rzz), oyz = lds_(ryz), oxz = lds_(rxz), oxy = lds_(rxy);
+            const float nxx = c1 * (oxx) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dyVy_dzVz) * dt;
+            const float nyy = c1 * (oyy) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dzVz) * dt;
+            const float nzz = c1 * (ozz) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dyVy) * dt;
             // shear R: the product with the F-kind strain rate is an F expression rounded on store (m_kernel.f90:320-322)
-            const float nyz = (float)(c1 * (*ryz) - c2 * muyz * taus1 * dyVz_dzVy * dt);
-            const float nxz = (float)(c1 * (*rxz) - c2 * muxz * taus1 * dxVz_dzVx * dt);
-            const float nxy = (float)(c1 * (*rxy) - c2 * muxy * taus1 * dxVy_dyVx * dt);
-            *rxx = nxx; *ryy = nyy; *rzz = nzz; *ryz = nyz; *rxz = nxz; *rxy = nxy;
+            const float nyz = (float)(c1 * (oyz) - c2 * muyz * taus1 * dyVz_dzVy * dt);
+            const float nxz = (float)(c1 * (oxz) - c2 * muxz * taus1 * dxVz_dzVx * dt);
+            const float nxy = (float)(c1 * (oxy) - c2 * muxy * taus1 * dxVy_dyVx * dt);
+            sts_(rxx, nxx); sts_(ryy, nyy); sts_(rzz, nzz); sts_(ryz, nyz); sts_(rxz, nxz); sts_(rxy, nxy);
             Rxx_n = Rxx_n + d1 * nxx; Ryy_n = Ryy_n + d1 * nyy; Rzz_n = Rzz_n + d1 * nzz;
             Ryz_n = Ryz_n + d1 * nyz; Rxz_n = Rxz_n + d1 * nxz; Rxy_n = Rxy_n + d1 * nxy;
         }
@@ -141,12 +160,12 @@ __device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n
     const float taup_plus1 = 1 + taup1 * (1 + p.d2);
     const float taus_plus1 = 1 + taus1 * (1 + p.d2);
 
-    F sxx = p.Sxx[n] + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dyVy_dzVz + Rxx_n) * dt;
-    F syy = p.Syy[n] + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dzVz + Ryy_n) * dt;
-    F szz = p.Szz[n] + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dyVy + Rzz_n) * dt;
-    F syz = p.Syz[n] + (muyz * taus_plus1 * dyVz_dzVy + Ryz_n) * dt;
-    F sxz = p.Sxz[n] + (muxz * taus_plus1 * dxVz_dzVx + Rxz_n) * dt;
-    F sxy = p.Sxy[n] + (muxy * taus_plus1 * dxVy_dyVx + Rxy_n) * dt;
+    F sxx = lds_(p.Sxx + n) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dyVy_dzVz + Rxx_n) * dt;
+    F syy = lds_(p.Syy + n) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dzVz + Ryy_n) * dt;
+    F szz = lds_(p.Szz + n) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dyVy + Rzz_n) * dt;
+    F syz = lds_(p.Syz + n) + (muyz * taus_plus1 * dyVz_dzVy + Ryz_n) * dt;
+    F sxz = lds_(p.Sxz + n) + (muxz * taus_plus1 * dxVz_dzVx + Rxz_n) * dt;
+    F sxy = lds_(p.Sxy + n) + (muxy * taus_plus1 * dxVy_dyVx + Rxy_n) * dt;
 
     if (p.abc == 2) {   // Cerjan sponge, m_absorb_c.f90:129-133, :155-157
         const int kk = k + KOFF - 1;
@@ -157,7 +176,7 @@ __device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n
         sxz = sxz * gxb * gyc * gzb;
         sxy = sxy * gxb * gyb * gzc;
     }
-    p.Sxx[n] = sxx; p.Syy[n] = syy; p.Szz[n] = szz; p.Syz[n] = syz; p.Sxz[n] = sxz; p.Sxy[n] = sxy;
+    sts_(p.Sxx + n, sxx); sts_(p.Syy + n, syy); sts_(p.Szz + n, szz); sts_(p.Syz + n, syz); sts_(p.Sxz + n, sxz); sts_(p.Sxy + n, sxy);
 }
 
 // stress update of one PML cell: absorb_p__update_stress, m_absorb_p.f90:453-519 (both k-loops fused)
@@ -307,8 +326,41 @@ __device__ __forceinline__ void vel_pml(const KParams<F> &p, long long n, int k,
 // L1/L2 (read-only path); every streamed array (S, R, medium, aux) is touched exactly once.
 // Interior cells and absorber cells partition the owned box (m_global.f90:334-376) and read only the
 // other field family, so one pass per family is order-independent.
+#ifndef SWPC_MINB
+#define SWPC_MINB 3
+#endif
+
+__device__ __forceinline__ void pf_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// L2 prefetch of everything the cell at linear index n (pf planes ahead along j) will stream from HBM: turns the
+// DRAM latency of the next plane into an L2 hit without holding registers.
 template <typename F, int NM, bool STRESS>
-__global__ void __launch_bounds__(256) sweep_direct(const __grid_constant__ KParams<F> p, int jlen, int lj_begin, int lj_end) {
+__device__ __forceinline__ void prefetch_cell(const KParams<F> &p, long long n, bool pml_target, long long a) {
+    if (STRESS) {
+        pf_l2(p.Sxx + n); pf_l2(p.Syy + n); pf_l2(p.Szz + n); pf_l2(p.Syz + n); pf_l2(p.Sxz + n); pf_l2(p.Sxy + n);
+        pf_l2(p.lam + n); pf_l2(p.mu + n + p.SJ);
+        pf_l2(p.Vx + n + 2 * p.SJ); pf_l2(p.Vy + n + p.SJ); pf_l2(p.Vz + n + 2 * p.SJ);
+        if (pml_target) {
+#pragma unroll
+            for (int q = 0; q < 9; q++) pf_l2(p.aux + a + q * p.naux);
+        } else {
+            pf_l2(p.taup + n); pf_l2(p.taus + n);
+#pragma unroll
+            for (int q = 0; q < 6 * NM; q++) pf_l2(p.R + n + q * p.ncell);
+        }
+    } else {
+        pf_l2(p.Vx + n); pf_l2(p.Vy + n); pf_l2(p.Vz + n); pf_l2(p.rho + n + p.SJ);
+        pf_l2(p.Sxx + n); pf_l2(p.Szz + n); pf_l2(p.Sxz + n);
+        pf_l2(p.Syy + n + 2 * p.SJ); pf_l2(p.Sxy + n + p.SJ); pf_l2(p.Syz + n + p.SJ);
+        if (pml_target) {
+#pragma unroll
+            for (int q = 9; q < 18; q++) pf_l2(p.aux + a + q * p.naux);
+        }
+    }
+}
+
+template <typename F, int NM, bool STRESS>
+__global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_constant__ KParams<F> p, int jlen, int lj_begin, int lj_end, int pf) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int li = blockIdx.y * blockDim.y + threadIdx.y;
     if (k > p.nz || li >= p.nxp) return;
@@ -321,6 +373,17 @@ __global__ void __launch_bounds__(256) sweep_direct(const __grid_constant__ KPar
         const int mj = lj + HALO;
         const long long col = (long long)mi + (long long)p.NXM * mj;
         const long long n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+        if (pf > 0 && lj + pf < p.nyp) {
+            const long long colp = col + (long long)p.NXM * pf;
+            bool pt = false;
+            long long ap = 0;
+            if (pml_mode) {
+                const int kb = p.kbeg_a[colp];
+                pt = (k >= kb);
+                if (pt) ap = p.aoff[li + (long long)p.nxp * (lj + pf)] + (k - kb);
+            }
+            prefetch_cell<F, NM, STRESS>(p, n + p.SJ * pf, pt, ap);
+        }
         bool is_pml = false;
         if (pml_mode) is_pml = (k >= p.kbeg_a[col]);
         if (is_pml) {

@@ -80,7 +80,7 @@ def main():
     ap.add_argument("--dtype", default="f64")
     ap.add_argument("--abc", default="pml")
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--configs", default="128,2,32", help="semicolon separated tk,ti,jlen triples")
+    ap.add_argument("--configs", default="128,2,32", help="semicolon separated tk,ti,jlen[,pf] tuples")
     a = ap.parse_args()
     dtype = np.float64 if a.dtype == "f64" else np.float32
     dev, geom = make_rank(a.nx, a.ny, a.nz, a.nm, dtype, abc=a.abc, na=a.na)
@@ -89,13 +89,11 @@ def main():
     pml_frac = 1 - ((a.nx - 2 * a.na) * (a.ny - 2 * a.na) * (a.nz - a.na)) / ncell if a.abc == "pml" else 0.0
     bpc = bytes_per_cell(a.nm, W, pml_frac)
     for cfg in a.configs.split(";"):
-        tk, ti, jlen = map(int, cfg.split(","))
-        dev.set_option("tk", 32)
-        dev.set_option("ti", 1)
-        dev.set_option("ti", ti) if tk * ti <= 256 else None
+        tk, ti, jlen, pf = (list(map(int, cfg.split(","))) + [0])[:4]
         dev.set_option("tk", tk)
         dev.set_option("ti", ti)
         dev.set_option("jlen", jlen)
+        dev.set_option("pf", pf)
         for it in range(1, 4):
             dev.step(it)
         dev.sync()
@@ -111,7 +109,7 @@ def main():
         for it in range(4, 4 + a.steps):
             dev.step(it)
         ms_t = dev.timer_stop() / a.steps
-        print(json.dumps({"grid": [a.nx, a.ny, a.nz], "nm": a.nm, "dtype": a.dtype, "abc": a.abc, "tk": tk, "ti": ti, "jlen": jlen,
+        print(json.dumps({"grid": [a.nx, a.ny, a.nz], "nm": a.nm, "dtype": a.dtype, "abc": a.abc, "tk": tk, "ti": ti, "jlen": jlen, "pf": pf,
                           "ms_stress": round(ms_s, 3), "ms_vel": round(ms_v, 3), "ms_step": round(ms_t, 3),
                           "gcells_s": round(ncell / ms_t / 1e6, 3), "bytes_per_cell": round(bpc, 1),
                           "GBs": round(ncell * bpc / ms_t / 1e6, 1), "vmax": [float(x) for x in dev.vmax()]}), flush=True)

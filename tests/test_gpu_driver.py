@@ -1,0 +1,53 @@
+"""End-to-end on the GPU through the product's own driver (input.inf -> host setup -> device -> SAC files), against
+the oracle run of the same input: progress-line amplitudes, station traces and SAC files byte for byte."""
+import numpy as np
+import pytest
+
+from helpers import rel_l2, write_case
+from openswpc_b200.swpc3d import Swpc3d
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", [dict(), dict(abc_type="cerjan", vmodel="uni"), dict(benchmark=True, nx=64, ny=64, nz=80, na=20)])
+def test_driver_sac_matches_oracle(tmp_path, case):
+    nt = 60
+    inf = write_case(tmp_path, nt=nt, ntdec_r=10, sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"], **case)
+    o = Oracle(inf, base_dir=tmp_path, nm=3)
+    o.lib.ora_set_exedate(o.h, 1_700_000_000, 540)
+    vm_ref = o.run(1, nt)
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    run.set_exedate(1_700_000_000, 540)
+    run.attach_device(0)
+    vm = run.run(1, nt)
+    np.testing.assert_array_equal(vm, vm_ref)                      # report__progress triplets
+    n_ref = o.write_sac(tmp_path / "ref")
+    n = run.write_sac(tmp_path / "gpu")
+    assert n == n_ref == 3 * run["nst"]
+    assert n > 0 or case.get("benchmark")
+    for f in sorted((tmp_path / "ref" / "wav").glob("*.sac")):
+        g = tmp_path / "gpu" / "wav" / f.name
+        assert g.exists(), f.name
+        assert g.read_bytes() == f.read_bytes(), f.name
+    if run["nst"]:
+        w = run.wav()
+        assert rel_l2(w, o.wav(0)) <= 1e-5                         # the north-star bar; in fact identical
+        np.testing.assert_array_equal(w, o.wav(0))
+
+
+def test_sac_header_fields(tmp_path):
+    inf = write_case(tmp_path, nt=20, title="hdrtest")
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    run.set_exedate(86400 * 365, 0)
+    run.attach_device(0)
+    run.run(1, 20)
+    run.write_sac(tmp_path / "o")
+    raw = (tmp_path / "o" / "wav" / "hdrtest.3d.st01.Vz.sac").read_bytes()
+    f = np.frombuffer(raw[:280], dtype=np.float32)
+    i = np.frombuffer(raw[280:420], dtype=np.int32)
+    assert len(raw) == 632 + 4 * run["ntw"]
+    assert f[0] == np.float32(int(np.float64(np.float32(2 * np.float32(0.02))) * 1e7)) / np.float32(1e7)   # delta, m_sac.f90:339
+    assert i[9] == run["ntw"] and i[6] == 6 and i[15] == 1 and i[16] == 7
+    assert i[0] == 1971 and i[1] == 1
+    assert raw[440:448] == b"st01    " and raw[448:464] == b"hdrtest         " and raw[600:608] == b"Vz      "
