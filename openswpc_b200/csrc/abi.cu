@@ -134,6 +134,11 @@ struct swpc3d_handle {
     int tk = 32, ti = 8, jlen = 16, pf = 1;
     int variant = 1;
     long long launches = 0;
+    // per-kernel CUDA-event timing of the two sweeps (option "kernel_timing"): event pairs recorded on the launch
+    // stream, read back after a synchronisation by swpc3d_get_info("ms_stress" / "ms_vel")
+    bool ktiming = false;
+    std::vector<cudaEvent_t> kev[2][2];   // [stress|vel][begin|end]
+    size_t kev_used[2] = {0, 0};
 };
 
 static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
@@ -516,11 +521,27 @@ static int launch_sweep(swpc3d_handle *h) {
     dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
     const int jlen = std::max(1, h->jlen);
     dim3 grd((unsigned)((h->g.nz + h->tk - 1) / h->tk), (unsigned)((h->nxp + h->ti - 1) / h->ti), (unsigned)((h->nyp + jlen - 1) / jlen));
+    const int w = STRESS ? 0 : 1;
+    const bool timed = h->ktiming && h->kev_used[w] < 4096;
+    if (timed) {
+        if (h->kev_used[w] == h->kev[w][0].size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            h->kev[w][0].push_back(a);
+            h->kev[w][1].push_back(b);
+        }
+        CK(cudaEventRecord(h->kev[w][0][h->kev_used[w]], h->st));
+    }
     switch (h->nm) {
     case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
     case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
     case 2: sweep_direct<F, 2, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
     default: sweep_direct<F, 3, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
+    }
+    if (timed) {
+        CK(cudaEventRecord(h->kev[w][1][h->kev_used[w]], h->st));
+        h->kev_used[w]++;
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -850,6 +871,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "jlen")) { if (value < 1) return fail("jlen must be >= 1"); h->jlen = value; }
     else if (!strcmp(key, "pf")) { if (value < 0 || value > 8) return fail("pf must be 0..8"); h->pf = value; }
     else if (!strcmp(key, "variant")) h->variant = value;
+    else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; }
     else return fail(std::string("unknown option ") + key);
     return 0;
 }
@@ -862,6 +884,19 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "NYM")) *value = h->NYM;
     else if (!strcmp(key, "naux")) *value = (double)h->naux;
     else if (!strcmp(key, "device")) *value = h->dev;
+    else if (!strcmp(key, "ms_stress") || !strcmp(key, "ms_vel") || !strcmp(key, "n_stress") || !strcmp(key, "n_vel")) {
+        const int w = strstr(key, "stress") ? 0 : 1;
+        if (key[0] == 'n') { *value = (double)h->kev_used[w]; return 0; }
+        CK(cudaSetDevice(h->dev));
+        CK(cudaStreamSynchronize(h->st));
+        double sum = 0;
+        for (size_t q = 0; q < h->kev_used[w]; q++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h->kev[w][0][q], h->kev[w][1][q]));
+            sum += ms;
+        }
+        *value = h->kev_used[w] ? sum / (double)h->kev_used[w] : 0.0;   // average launch duration [ms]
+    }
     else if (!strcmp(key, "device_bytes")) {
         double b = (double)h->ncell * (9.0 * h->fb + 5 * 4 + 6.0 * h->nm * 4) + (double)h->naux * 18 * 4;
         *value = b;

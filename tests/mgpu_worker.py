@@ -1,0 +1,50 @@
+"""Worker of tests/test_multi_gpu.py: one rank of a torchrun job.  Runs the product's driver on this rank's GPU with
+NCCL halo exchange and checks fields, traces and progress amplitudes against the oracle's emulated decomposition."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+from helpers import write_case  # noqa: E402
+from openswpc_b200.distributed import allreduce_minmax, attach_nccl, init_process_group  # noqa: E402
+from openswpc_b200.swpc3d import Swpc3d  # noqa: E402
+from oracle_lib import Oracle  # noqa: E402
+
+
+def main():
+    work = Path(sys.argv[1])
+    npx, npy, nt = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    rank, world, local = init_process_group("nccl")
+    d = work / f"r{rank}"
+    inf = write_case(d, nt=nt, nproc_x=npx, nproc_y=npy, nx=56, ny=48, ntdec_r=5,
+                     sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
+    run = Swpc3d(inf, base_dir=d, nm=3, myid=rank)
+    allreduce_minmax(run)
+    run.attach_device(local)
+    attach_nccl(run)
+    vm = run.run(1, nt)
+    run.write_sac(d / "out")
+    o = Oracle(inf, base_dir=d, nm=3)
+    assert np.float32(run["vmin"]) == np.float32(o.cfg("vmin")) and np.float32(run["vmax"]) == np.float32(o.cfg("vmax"))
+    vm_ref = o.run(1, nt)
+    np.testing.assert_array_equal(vm, vm_ref)
+    got = run.download_fields()
+    r = o.rank(rank)
+    # owned cells and the halo planes filled by the exchange (i, j margins of width 2 next to a neighbour)
+    sl = (slice(3, 3 + r["nyp"]), slice(3, 3 + r["nxp"]), slice(3, 3 + o.cfg("nz")))
+    for n, a in got.items():
+        ref = o.field(rank, n)
+        assert np.array_equal(a[sl], ref[sl]), (rank, n, float(np.abs(a[sl] - ref[sl]).max()))
+        assert np.array_equal(a[:, :, 3:3 + o.cfg("nz")], ref[:, :, 3:3 + o.cfg("nz")]), (rank, n, "halo")
+    if run["nst"]:
+        np.testing.assert_array_equal(run.wav(), o.wav(rank))
+    print(f"rank {rank}/{world} ok: nst={run['nst']} nsrc={run['nsrc']}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

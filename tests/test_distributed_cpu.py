@@ -1,0 +1,62 @@
+"""N>1 host-side plumbing on CPU: world_size-2 gloo job doing what bench.py / the driver do before the first step --
+per-rank setup, the vmin/vmax all-reduce of m_medium.f90:424-425 and the broadcast of the 128-byte NCCL id."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, work, port, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from helpers import write_case
+    from openswpc_b200.distributed import allreduce_minmax, init_process_group, layout_for
+    from openswpc_b200.swpc3d import Swpc3d
+
+    init_process_group("gloo")
+    npx, npy = layout_for(world)
+    d = Path(work) / f"r{rank}"
+    # a model whose slowest/fastest material differ between the two halves is not expressible with a 1-D model,
+    # so make the ranks disagree through vmin_local by construction: the reduction must still give one global pair
+    inf = write_case(d, nt=10, nproc_x=npx, nproc_y=npy, nx=56, ny=48)
+    run = Swpc3d(inf, base_dir=d, nm=3, myid=rank)
+    before = (run["vmin_local"], run["vmax_local"])
+    run.set_minmax(before[0] + rank, before[1] - rank)   # pretend the local values differ
+    import torch
+
+    a = torch.tensor([run["vmin"]]), torch.tensor([run["vmax"]])
+    dist.all_reduce(a[0], op=dist.ReduceOp.MIN)
+    dist.all_reduce(a[1], op=dist.ReduceOp.MAX)
+    allreduce_minmax(run)   # uses the *_local values
+    box = [bytes(range(128)) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    q.put((rank, run["ibeg"], run["iend"], run["jbeg"], run["jend"], run["vmin"], run["vmax"], float(a[0]), float(a[1]), box[0] == bytes(range(128)),
+           before))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_setup(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    ps = [ctx.Process(target=_worker, args=(r, 2, str(tmp_path), port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, r1) = res
+    assert (r0[1], r0[2], r1[1], r1[2]) == (1, 28, 29, 56)          # m_global.f90:275-281 for nx=56, nproc_x=2
+    assert (r0[3], r0[4]) == (r1[3], r1[4]) == (1, 48)
+    assert r0[9] and r1[9]                                           # unique-id broadcast reached both ranks
+    assert r0[5] == r1[5] and r0[6] == r1[6]                         # one global (vmin, vmax) pair after the reduction
+    assert np.isclose(r0[5], min(r0[10][0], r1[10][0])) and np.isclose(r0[6], max(r0[10][1], r1[10][1]))
+    assert np.isclose(r0[7], r0[10][0]) and np.isclose(r0[8], r0[10][1])   # MIN / MAX semantics of the raw all-reduce

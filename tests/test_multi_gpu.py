@@ -1,0 +1,29 @@
+"""N>1: one process per GPU, NCCL send/recv halo exchange, against the oracle's emulated MPI decomposition."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("layout", [(2, 1), (1, 2), (2, 2)])
+def test_nccl_halo_exchange_matches_oracle(tmp_path, layout):
+    n = layout[0] * layout[1]
+    if _ngpu() < n:
+        pytest.skip(f"needs {n} GPUs")
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "mgpu_worker.py"), str(tmp_path), str(layout[0]), str(layout[1]), "30"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert p.stdout.count(" ok:") == n
