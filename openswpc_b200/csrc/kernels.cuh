@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_cons
         const int mj = lj + HALO;
         const long long col = (long long)mi + (long long)p.NXM * mj;
         const long long n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
-        if (pf > 0 && lj + pf < p.nyp) {
+        if (pf > 0 && lj + pf < lje) {
             const long long colp = col + (long long)p.NXM * pf;
             bool pt = false;
             long long ap = 0;

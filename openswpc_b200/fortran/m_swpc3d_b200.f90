@@ -1,0 +1,204 @@
+!! m_swpc3d_b200.f90 -- ISO_C_BINDING face of libswpc3d_b200.so (include/swpc3d_b200.h) for OpenSWPC's swpc_3d.
+!!
+!! SOURCE ONLY: the build image has no Fortran compiler, so this module is not compiled or tested there.  It shows the
+!! binding a maintainer adds to src/swpc_3d/ so that the hot subroutines become one-line calls (INTEGRATION.md):
+!!
+!!   kernel__update_stress + absorb__update_stress -> swpc3d_update_stress     (m_kernel.f90:142, m_absorb.f90:60)
+!!   source__stressglut(it)                        -> swpc3d_stressglut        (m_source.f90:776)
+!!   global__comm_stress                           -> swpc3d_comm_stress       (m_global.f90:500)
+!!   kernel__update_vel + absorb__update_vel       -> swpc3d_update_vel        (m_kernel.f90:75, m_absorb.f90:43)
+!!   source__bodyforce(it)                         -> swpc3d_bodyforce         (m_source.f90:850)
+!!   global__comm_vel                              -> swpc3d_comm_vel          (m_global.f90:391)
+!!   wav__store(it) (velocity traces)              -> swpc3d_wav_store         (m_wav.f90:515-539)
+!!   kernel__vmax                                  -> swpc3d_vmax              (m_kernel.f90:350)
+!!   `!$acc enter data copyin(...)`                -> swpc3d_create / upload_medium / setup_pml|cerjan / set_sources /
+!!                                                    set_stations            (main.f90:80-113)
+module m_swpc3d_b200
+
+    use iso_c_binding
+    implicit none
+    private
+
+    integer(c_int32_t), parameter, public :: SWPC3D_ABC_PML = 1, SWPC3D_ABC_CERJAN = 2
+
+    !! mirrors `swpc3d_grid` field by field
+    type, bind(c), public :: swpc3d_grid
+        integer(c_int32_t) :: nx, ny, nz
+        integer(c_int32_t) :: nproc_x, nproc_y, myid
+        integer(c_int32_t) :: ibeg, iend, jbeg, jend
+        integer(c_int32_t) :: ipad, jpad, kpad
+        integer(c_int32_t) :: ibeg_k, iend_k, jbeg_k, jend_k, kbeg_k, kend_k
+        integer(c_int32_t) :: na, nm, abc_type, field_bytes, device, reserved
+        real(c_double)     :: dx, dy, dz
+        real(c_float)      :: dt, reserved_f
+    end type swpc3d_grid
+
+    public :: swpc3d_create, swpc3d_destroy, swpc3d_upload_medium, swpc3d_upload_fields, swpc3d_download_fields
+    public :: swpc3d_setup_pml, swpc3d_setup_cerjan, swpc3d_set_sources, swpc3d_set_stations
+    public :: swpc3d_update_stress, swpc3d_stressglut, swpc3d_comm_stress
+    public :: swpc3d_update_vel, swpc3d_bodyforce, swpc3d_comm_vel
+    public :: swpc3d_wav_store, swpc3d_step, swpc3d_sync, swpc3d_vmax, swpc3d_vmax_global, swpc3d_get_wav
+    public :: swpc3d_nccl_unique_id, swpc3d_comm_init, swpc3d_last_error
+    public :: swpc3d_check
+
+    interface
+
+        function swpc3d_last_error() bind(c, name='swpc3d_last_error') result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+
+        integer(c_int) function swpc3d_create(g, ts, h) bind(c, name='swpc3d_create')
+            import :: c_int, c_float, c_ptr, swpc3d_grid
+            type(swpc3d_grid), intent(in) :: g
+            real(c_float), intent(in) :: ts(*)          !! ts(1:nm), m_global.f90:41
+            type(c_ptr), intent(out) :: h
+        end function
+
+        integer(c_int) function swpc3d_destroy(h) bind(c, name='swpc3d_destroy')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+
+        !! arrays are passed exactly as allocated in m_medium.f90:441-452 (kbeg_m:kend_m, ibeg_m:iend_m, jbeg_m:jend_m)
+        integer(c_int) function swpc3d_upload_medium(h, rho, lam, mu, taup, taus, kfs, kob, kfs_top, kfs_bot, kob_top, &
+                                                     kob_bot, kbeg_a) bind(c, name='swpc3d_upload_medium')
+            import :: c_int, c_float, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(in) :: rho(*), lam(*), mu(*), taup(*), taus(*)
+            integer(c_int32_t), intent(in) :: kfs(*), kob(*), kfs_top(*), kfs_bot(*), kob_top(*), kob_bot(*), kbeg_a(*)
+        end function
+
+        integer(c_int) function swpc3d_upload_fields(h, Vx, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy) &
+            bind(c, name='swpc3d_upload_fields')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h, Vx, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy   !! c_loc(array) or c_null_ptr
+        end function
+
+        integer(c_int) function swpc3d_download_fields(h, Vx, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy) &
+            bind(c, name='swpc3d_download_fields')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h, Vx, Vy, Vz, Sxx, Syy, Szz, Syz, Sxz, Sxy
+        end function
+
+        !! gxc(4,ibeg:iend) ... gze(4,kbeg:kend), m_absorb_p.f90:75-77
+        integer(c_int) function swpc3d_setup_pml(h, gxc, gxe, gyc, gye, gzc, gze) bind(c, name='swpc3d_setup_pml')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(in) :: gxc(*), gxe(*), gyc(*), gye(*), gzc(*), gze(*)
+        end function
+
+        !! gx_c(ibeg_m:iend_m) ... gz_b(kbeg_m:kend_m), m_absorb_c.f90:45-47
+        integer(c_int) function swpc3d_setup_cerjan(h, gx_c, gx_b, gy_c, gy_b, gz_c, gz_b) bind(c, name='swpc3d_setup_cerjan')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(in) :: gx_c(*), gx_b(*), gy_c(*), gy_b(*), gz_c(*), gz_b(*)
+        end function
+
+        !! mo..mxy are real(MP) = real(c_double) in the default build (m_source.f90:32-34); bf_mode: pass fx,fy,fz as mxx,myy,mzz
+        integer(c_int) function swpc3d_set_sources(h, nsrc, isrc, jsrc, ksrc, mo, mxx, myy, mzz, myz, mxz, mxy, srcprm, &
+                                                   stftype, bf_mode, tbeg) bind(c, name='swpc3d_set_sources')
+            import :: c_int, c_int32_t, c_double, c_float, c_char, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: nsrc, bf_mode
+            integer(c_int32_t), intent(in) :: isrc(*), jsrc(*), ksrc(*)
+            real(c_double), intent(in) :: mo(*), mxx(*), myy(*), mzz(*), myz(*), mxz(*), mxy(*)
+            real(c_float), intent(in) :: srcprm(*)
+            character(kind=c_char), intent(in) :: stftype(*)   !! trim(stftype)//c_null_char
+            real(c_float), value :: tbeg
+        end function
+
+        integer(c_int) function swpc3d_set_stations(h, nst, ist, jst, kst, ntdec_w, ntw, M0, UC) &
+            bind(c, name='swpc3d_set_stations')
+            import :: c_int, c_int32_t, c_float, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: nst, ntdec_w, ntw
+            integer(c_int32_t), intent(in) :: ist(*), jst(*), kst(*)
+            real(c_float), value :: M0, UC
+        end function
+
+        integer(c_int) function swpc3d_update_stress(h) bind(c, name='swpc3d_update_stress')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpc3d_stressglut(h, it) bind(c, name='swpc3d_stressglut')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_comm_stress(h) bind(c, name='swpc3d_comm_stress')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpc3d_update_vel(h) bind(c, name='swpc3d_update_vel')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpc3d_bodyforce(h, it) bind(c, name='swpc3d_bodyforce')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_comm_vel(h) bind(c, name='swpc3d_comm_vel')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpc3d_wav_store(h, it) bind(c, name='swpc3d_wav_store')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_step(h, it) bind(c, name='swpc3d_step')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_sync(h) bind(c, name='swpc3d_sync')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpc3d_vmax(h, vm) bind(c, name='swpc3d_vmax')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(out) :: vm(3)
+        end function
+        integer(c_int) function swpc3d_vmax_global(h, vm) bind(c, name='swpc3d_vmax_global')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(out) :: vm(3)
+        end function
+        integer(c_int) function swpc3d_get_wav(h, wav_vel) bind(c, name='swpc3d_get_wav')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(out) :: wav_vel(*)     !! wav_vel(ntw,3,nst), m_wav.f90:106
+        end function
+        integer(c_int) function swpc3d_nccl_unique_id(id) bind(c, name='swpc3d_nccl_unique_id')
+            import :: c_int, c_char
+            character(kind=c_char), intent(out) :: id(128)
+        end function
+        integer(c_int) function swpc3d_comm_init(h, id, nranks, rank) bind(c, name='swpc3d_comm_init')
+            import :: c_int, c_int32_t, c_char, c_ptr
+            type(c_ptr), value :: h
+            character(kind=c_char), intent(in) :: id(128)
+            integer(c_int32_t), value :: nranks, rank
+        end function
+
+    end interface
+
+contains
+
+    !! non-zero return -> the reference's convention: message + stop (m_debug.f90:206-221)
+    subroutine swpc3d_check(ierr)
+        use iso_fortran_env, only: error_unit
+        integer(c_int), intent(in) :: ierr
+        character(kind=c_char), pointer :: msg(:)
+        integer :: n
+        if (ierr == 0) return
+        call c_f_pointer(swpc3d_last_error(), msg, [512])
+        n = 1
+        do while (n < 512 .and. msg(n) /= c_null_char); n = n + 1; end do
+        write (error_unit, '(A,512A1)') '[swpc3d_b200] ', msg(1:n - 1)
+        stop 1
+    end subroutine swpc3d_check
+
+end module m_swpc3d_b200
