@@ -3,6 +3,7 @@
 // every entry point fails loudly when CUDA is not usable.
 #include "../../include/swpc3d_b200.h"
 #include "kernels.cuh"
+#include "stress_tma.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -92,6 +93,8 @@ struct swpc3d_handle {
     long long ncell = 0;
     int fb = 8;                            // field bytes
     int nm = 0;
+    void *Fall = nullptr;                  // 9 fields, contiguous
+    float *Mall = nullptr;                 // 5 medium arrays, contiguous: rho mu lam taup taus
     void *F[9] = {};                       // Vx Vy Vz Sxx Syy Szz Syz Sxz Sxy
     float *R = nullptr;
     float *med[5] = {};                    // rho lam mu taup taus
@@ -129,9 +132,15 @@ struct swpc3d_handle {
     int comm_rank = -1, comm_size = 0;
     // streams
     cudaStream_t st = nullptr;
+    cudaStream_t side[5] = {};             // absorber-shell boxes run beside the TMA interior kernel
+    cudaEvent_t ev_fork = nullptr, ev_join[5] = {};
+    int use_side = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tuning
     int tk = 32, ti = 8, jlen = 16, pf = 1;
+    int use_tma = 1, tma_jl = 32;
+    bool tma_ready = false, tma_ok = false;
+    TmaMaps tmaps{};
     int variant = 1;
     long long launches = 0;
     // per-kernel CUDA-event timing of the two sweeps (option "kernel_timing"): event pairs recorded on the launch
@@ -234,19 +243,27 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
     if (h->fb == 8) setup_coefs<double>(h, ts);
     else setup_coefs<float>(h, ts);
     CK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (int q = 0; q < 5; q++) {
+        CK(cudaStreamCreateWithFlags(&h->side[q], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->ev_join[q], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
-    for (int a = 0; a < 9; a++) {
-        CK(cudaMalloc(&h->F[a], (size_t)h->ncell * h->fb));
-        CK(cudaMemsetAsync(h->F[a], 0, (size_t)h->ncell * h->fb, h->st));
-    }
+    // the nine fields live in ONE allocation (field f at f*ncell) so that a single 4-D TMA tensor covers them
+    CK(cudaMalloc(&h->Fall, (size_t)h->ncell * h->fb * 9));
+    CK(cudaMemsetAsync(h->Fall, 0, (size_t)h->ncell * h->fb * 9, h->st));
+    for (int a = 0; a < 9; a++) h->F[a] = (char *)h->Fall + (size_t)a * h->ncell * h->fb;
     if (h->nm > 0) {
         CK(cudaMalloc(&h->R, (size_t)h->ncell * 6 * h->nm * sizeof(float)));
         CK(cudaMemsetAsync(h->R, 0, (size_t)h->ncell * 6 * h->nm * sizeof(float), h->st));
     }
-    for (int a = 0; a < 5; a++) {
-        CK(cudaMalloc(&h->med[a], (size_t)h->ncell * sizeof(float)));
-        CK(cudaMemsetAsync(h->med[a], 0, (size_t)h->ncell * sizeof(float), h->st));
+    // medium: one allocation, order rho, mu, lam, taup, taus (lam..taus consecutive for one TMA box)
+    CK(cudaMalloc(&h->Mall, (size_t)h->ncell * sizeof(float) * 5));
+    CK(cudaMemsetAsync(h->Mall, 0, (size_t)h->ncell * sizeof(float) * 5, h->st));
+    {
+        const int slot[5] = {0, 2, 1, 3, 4};   // med[] order is rho lam mu taup taus
+        for (int a = 0; a < 5; a++) h->med[a] = h->Mall + (size_t)slot[a] * h->ncell;
     }
     const size_t n2 = (size_t)h->NXM * h->NYM;
     CK(cudaMalloc(&h->band, n2 * sizeof(int4)));
@@ -289,9 +306,9 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaSetDevice(h->dev);
     cudaDeviceSynchronize();
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
-    for (int a = 0; a < 9; a++) cudaFree(h->F[a]);
+    cudaFree(h->Fall);
     cudaFree(h->R);
-    for (int a = 0; a < 5; a++) cudaFree(h->med[a]);
+    cudaFree(h->Mall);
     cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->aoff); cudaFree(h->aux);
     for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
     cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
@@ -299,6 +316,11 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     for (int f = 0; f < 4; f++) { cudaFree(h->sbuf[f]); cudaFree(h->rbuf[f]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int q = 0; q < 5; q++) {
+        if (h->side[q]) cudaStreamDestroy(h->side[q]);
+        if (h->ev_join[q]) cudaEventDestroy(h->ev_join[q]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return 0;
@@ -515,12 +537,122 @@ extern "C" int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t 
 // ------------------------------------------------------------------------------------------------
 // sweeps
 template <typename F, bool STRESS>
+static int launch_direct_box(swpc3d_handle *h, const KParams<F> &p, const Box3 &b, cudaStream_t st = nullptr) {
+    if (!st) st = h->st;
+    if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) return 0;
+    dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
+    const int jlen = std::max(1, h->jlen);
+    dim3 grd((unsigned)((b.k1 - b.k0 + 1 + h->tk - 1) / h->tk), (unsigned)((b.li1 - b.li0 + 1 + h->ti - 1) / h->ti),
+             (unsigned)((b.lj1 - b.lj0 + 1 + jlen - 1) / jlen));
+    switch (h->nm) {
+    case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, st>>>(p, b, jlen, h->pf); break;
+    case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, st>>>(p, b, jlen, h->pf); break;
+    case 2: sweep_direct<F, 2, STRESS><<<grd, blk, 0, st>>>(p, b, jlen, h->pf); break;
+    default: sweep_direct<F, 3, STRESS><<<grd, blk, 0, st>>>(p, b, jlen, h->pf); break;
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// TMA tensor maps over the contiguous field / memory-variable / medium allocations (4-D: k, i, j, array)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+static bool make_map(swpc3d_handle *h, CUtensorMap *m, void *base, int elem, int narr, int bk, int bi, int barr) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)h->NZP, (cuuint64_t)h->NXM, (cuuint64_t)h->NYM, (cuuint64_t)narr};
+    const cuuint64_t strides[3] = {(cuuint64_t)h->NZP * elem, (cuuint64_t)h->NZP * h->NXM * elem, (cuuint64_t)h->ncell * elem};
+    const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)bi, 1u, (cuuint32_t)barr};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(m, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename F, int NM>
+static int tma_prepare(swpc3d_handle *h) {
+    using C = TmaCfg<F, NM>;
+    h->tma_ready = true;
+    h->tma_ok = false;
+    if (C::SMEM > 227 * 1024) return 0;
+    bool ok = make_map(h, &h->tmaps.S, h->Fall, sizeof(F), 9, C::TK, C::TI, 6) && make_map(h, &h->tmaps.V, h->Fall, sizeof(F), 9, C::VK, C::VI, 3) &&
+              make_map(h, &h->tmaps.M, h->Mall, 4, 5, C::TK, C::TI, C::NMED) && make_map(h, &h->tmaps.Mu, h->Mall, 4, 5, C::MUK, C::MUI, 1);
+    if (NM > 0) ok = ok && make_map(h, &h->tmaps.R, h->R, 4, 6 * NM, C::TK, C::TI, 6 * NM);
+    if (!ok) return 0;
+    if (cudaFuncSetAttribute(stress_tma<F, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    h->tma_ok = true;
+    return 0;
+}
+
+// The box of whole TK x TI tiles inside the interior kernel box that stress_tma handles; empty if TMA is off.
+template <typename F, int NM>
+static Box3 tma_box(const swpc3d_handle *h) {
+    using C = TmaCfg<F, NM>;
+    Box3 b{1, 0, 0, -1, 0, -1, 0};
+    if (!h->use_tma || !h->tma_ok) return b;
+    const swpc3d_grid &g = h->g;
+    const int nkt = (g.kend_k + C::TK - 1) / C::TK;                     // interior k is 1..kend_k; the last tile may be partial
+    const int li0 = g.ibeg_k - g.ibeg, li1 = g.iend_k - g.ibeg, lj0 = g.jbeg_k - g.jbeg, lj1 = g.jend_k - g.jbeg;
+    const int nit = (li1 - li0 + 1) / C::TI;
+    if (nkt < 1 || nit < 1 || lj1 < lj0) return b;
+    // (the last tile may reach past the padded column: TMA zero-fills out-of-bounds elements, and those lanes are masked)
+    b.k0 = 1; b.k1 = nkt * C::TK; b.li0 = li0; b.li1 = li0 + nit * C::TI - 1; b.lj0 = lj0; b.lj1 = lj1;
+    return b;
+}
+
+template <typename F, int NM>
+static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p) {
+    using C = TmaCfg<F, NM>;
+    if (!h->tma_ready) tma_prepare<F, NM>(h);
+    const Box3 t = tma_box<F, NM>(h);
+    const Box3 all{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0};
+    if (t.k1 < t.k0) return launch_direct_box<F, true>(h, p, all);
+    TmaGeom g{};
+    g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
+    dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + 1) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
+    const int kE = (h->g.kend_k / C::TK) * C::TK + 1;   // first k of the tile that contains kend_k + 1 (warp-aligned)
+    // complement of the TMA box inside the owned box: two j slabs, two i slabs, one k slab (absorber cells only: the TMA
+    // tiles already did every interior cell, also in the partial last k-tile).  All six launches touch disjoint cells and
+    // only read V, so the shell boxes run on side streams next to the interior kernel.
+    const Box3 boxes[5] = {Box3{1, h->g.nz, 0, h->nxp - 1, 0, t.lj0 - 1, 0}, Box3{1, h->g.nz, 0, h->nxp - 1, t.lj1 + 1, h->nyp - 1, 0},
+                           Box3{1, h->g.nz, 0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, h->nxp - 1, t.lj0, t.lj1, 0},
+                           Box3{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1}};
+    if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
+    stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
+    h->launches++;
+    CK(cudaGetLastError());
+    for (int q = 0; q < 5; q++) {
+        const Box3 &b = boxes[q];
+        if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
+        if (h->use_side) {
+            CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
+            if (launch_direct_box<F, true>(h, p, b, h->side[q])) return 1;
+            CK(cudaEventRecord(h->ev_join[q], h->side[q]));
+            CK(cudaStreamWaitEvent(h->st, h->ev_join[q], 0));
+        } else if (launch_direct_box<F, true>(h, p, b)) return 1;
+    }
+    return 0;
+}
+
+template <typename F, bool STRESS>
 static int launch_sweep(swpc3d_handle *h) {
     const KParams<F> p = make_params<F>(h);
     if (h->tk * h->ti > 256) return fail("tk*ti must be <= 256 (launch bounds)");
-    dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
-    const int jlen = std::max(1, h->jlen);
-    dim3 grd((unsigned)((h->g.nz + h->tk - 1) / h->tk), (unsigned)((h->nxp + h->ti - 1) / h->ti), (unsigned)((h->nyp + jlen - 1) / jlen));
     const int w = STRESS ? 0 : 1;
     const bool timed = h->ktiming && h->kev_used[w] < 4096;
     if (timed) {
@@ -533,18 +665,22 @@ static int launch_sweep(swpc3d_handle *h) {
         }
         CK(cudaEventRecord(h->kev[w][0][h->kev_used[w]], h->st));
     }
-    switch (h->nm) {
-    case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
-    case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
-    case 2: sweep_direct<F, 2, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
-    default: sweep_direct<F, 3, STRESS><<<grd, blk, 0, h->st>>>(p, jlen, 0, h->nyp, h->pf); break;
+    int rc = 0;
+    if (STRESS) {
+        switch (h->nm) {
+        case 0: rc = launch_stress_nm<F, 0>(h, p); break;
+        case 1: rc = launch_stress_nm<F, 1>(h, p); break;
+        case 2: rc = launch_stress_nm<F, 2>(h, p); break;
+        default: rc = launch_stress_nm<F, 3>(h, p); break;
+        }
+    } else {
+        rc = launch_direct_box<F, false>(h, p, Box3{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0});
     }
+    if (rc) return rc;
     if (timed) {
         CK(cudaEventRecord(h->kev[w][1][h->kev_used[w]], h->st));
         h->kev_used[w]++;
     }
-    h->launches++;
-    CK(cudaGetLastError());
     return 0;
 }
 
@@ -871,6 +1007,9 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "jlen")) { if (value < 1) return fail("jlen must be >= 1"); h->jlen = value; }
     else if (!strcmp(key, "pf")) { if (value < 0 || value > 8) return fail("pf must be 0..8"); h->pf = value; }
     else if (!strcmp(key, "variant")) h->variant = value;
+    else if (!strcmp(key, "tma")) h->use_tma = value;
+    else if (!strcmp(key, "side_streams")) h->use_side = value;
+    else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }
     else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; }
     else return fail(std::string("unknown option ") + key);
     return 0;
@@ -884,6 +1023,7 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "NYM")) *value = h->NYM;
     else if (!strcmp(key, "naux")) *value = (double)h->naux;
     else if (!strcmp(key, "device")) *value = h->dev;
+    else if (!strcmp(key, "tma_ok")) *value = h->tma_ok ? 1.0 : 0.0;
     else if (!strcmp(key, "ms_stress") || !strcmp(key, "ms_vel") || !strcmp(key, "n_stress") || !strcmp(key, "n_vel")) {
         const int w = strstr(key, "stress") ? 0 : 1;
         if (key[0] == 'n') { *value = (double)h->kev_used[w]; return 0; }

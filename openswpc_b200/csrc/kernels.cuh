@@ -97,86 +97,150 @@ __device__ __forceinline__ float mu_harm(float a, float b, float c, float d) {
 // stress update of one interior cell: kernel__update_stress, m_kernel.f90:179-242 (normal) and
 // :266-337 (shear) in ONE pass so that V and mu are read once; Cerjan multiply (m_absorb_c.f90:113-168)
 // fused as a post-multiply of the freshly updated value.
+//
+// The arithmetic is written once, against an accessor `A` that says where the operands live:
+//   AccDirect  -- global memory through the read-only / streaming paths (sweep_direct)
+//   AccTma     -- shared-memory tiles staged by TMA (stress_tma), results stored straight to global
+// V<f,dk,di,dj>: field f (0 Vx, 1 Vy, 2 Vz) at (k+dk, i+di, j+dj); S/R component order xx yy zz yz xz xy.
 template <typename F, int NM>
-__device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n, int k, int mi, int mj, const int4 bnd) {
-    const long long si = p.SI, sj = p.SJ;
+struct AccDirect {
+    const KParams<F> &p;
+    long long n;
+    __device__ __forceinline__ AccDirect(const KParams<F> &p_, long long n_) : p(p_), n(n_) {}
+    template <int f, int dk, int di, int dj> __device__ __forceinline__ F V() const {
+        const F *b = (f == 0) ? p.Vx : (f == 1) ? p.Vy : p.Vz;
+        return ldro(b + n + dk + di * p.SI + dj * p.SJ);
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float mu() const { return ldro(p.mu + n + dk + di * p.SI + dj * p.SJ); }
+    __device__ __forceinline__ float lam() const { return ldro(p.lam + n); }
+    __device__ __forceinline__ float taup() const { return ldro(p.taup + n); }
+    __device__ __forceinline__ float taus() const { return ldro(p.taus + n); }
+    __device__ __forceinline__ F *sptr(int c) const { return c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy; }
+    __device__ __forceinline__ F S(int c) const { return lds_(sptr(c) + n); }
+    __device__ __forceinline__ void setS(int c, F v) const { sts_(sptr(c) + n, v); }
+    __device__ __forceinline__ float R(int q) const { return lds_(p.R + n + q * p.ncell); }
+    __device__ __forceinline__ void setR(int q, float v) const { sts_(p.R + n + q * p.ncell, v); }
+};
+
+// DO_N: normal components (m_kernel.f90:179-242); DO_S: shear components (:266-337).  The two halves share no
+// intermediate, so they may run in different warps (stress_tma) or back to back (sweep_direct) with identical results.
+template <typename F, int NM, typename A, bool DO_N = true, bool DO_S = true>
+__device__ __forceinline__ void stress_interior_t(const KParams<F> &p, const A &a, int k, int mi, int mj, const int4 bnd) {
     const int o = fd_order_sel(k, bnd);
     const F re40x = p.r40x[o], re41x = p.r41x[o], re40y = p.r40y[o], re41y = p.r41y[o], re40z = p.r40z[o], re41z = p.r41z[o];
-    const F *__restrict__ Vx = p.Vx, *__restrict__ Vy = p.Vy, *__restrict__ Vz = p.Vz;
     const float dt = p.dt;
+    const float taus1 = (NM > 0) ? a.taus() : 0.0f;
+    const float taus_plus1 = 1 + taus1 * (1 + p.d2);
+    const float mu0 = a.template mu<0, 0, 0>();
+    float gxc = 1.0f, gxb = 1.0f, gyc = 1.0f, gyb = 1.0f, gzc = 1.0f, gzb = 1.0f;
+    const bool cerjan = (p.abc == 2);   // Cerjan sponge, m_absorb_c.f90:129-133, :155-157
+    if (cerjan) {
+        const int kk = k + KOFF - 1;
+        gxc = p.cgx_c[mi]; gxb = p.cgx_b[mi]; gyc = p.cgy_c[mj]; gyb = p.cgy_b[mj]; gzc = p.cgz_c[kk]; gzb = p.cgz_b[kk];
+    }
+    F sn[6];
+    float rn[6][NM > 0 ? NM : 1];
 
-    const F vx0 = ldro(Vx + n), vy0 = ldro(Vy + n), vz0 = ldro(Vz + n);
-    const F vx_im1 = ldro(Vx + n - si), vx_ip1 = ldro(Vx + n + si), vx_im2 = ldro(Vx + n - 2 * si);
-    const F vy_jm1 = ldro(Vy + n - sj), vy_jp1 = ldro(Vy + n + sj), vy_jm2 = ldro(Vy + n - 2 * sj);
-    const F vz_km1 = ldro(Vz + n - 1), vz_kp1 = ldro(Vz + n + 1), vz_km2 = ldro(Vz + n - 2);
+    if (DO_N) {
+        const F vx0 = a.template V<0, 0, 0, 0>(), vy0 = a.template V<1, 0, 0, 0>(), vz0 = a.template V<2, 0, 0, 0>();
+        const F vx_im1 = a.template V<0, 0, -1, 0>(), vx_ip1 = a.template V<0, 0, 1, 0>(), vx_im2 = a.template V<0, 0, -2, 0>();
+        const F vy_jm1 = a.template V<1, 0, 0, -1>(), vy_jp1 = a.template V<1, 0, 0, 1>(), vy_jm2 = a.template V<1, 0, 0, -2>();
+        const F vz_km1 = a.template V<2, -1, 0, 0>(), vz_kp1 = a.template V<2, 1, 0, 0>(), vz_km2 = a.template V<2, -2, 0, 0>();
 
-    const F dxVx = (vx0 - vx_im1) * re40x - (vx_ip1 - vx_im2) * re41x;
-    const F dyVy = (vy0 - vy_jm1) * re40y - (vy_jp1 - vy_jm2) * re41y;
-    const F dzVz = (vz0 - vz_km1) * re40z - (vz_kp1 - vz_km2) * re41z;
+        const F dxVx = (vx0 - vx_im1) * re40x - (vx_ip1 - vx_im2) * re41x;
+        const F dyVy = (vy0 - vy_jm1) * re40y - (vy_jp1 - vy_jm2) * re41y;
+        const F dzVz = (vz0 - vz_km1) * re40z - (vz_kp1 - vz_km2) * re41z;
 
-    const F dxVy_dyVx = (ldro(Vy + n + si) - vy0) * re40x - (ldro(Vy + n + 2 * si) - ldro(Vy + n - si)) * re41x +
-                        (ldro(Vx + n + sj) - vx0) * re40y - (ldro(Vx + n + 2 * sj) - ldro(Vx + n - sj)) * re41y;
-    const F dxVz_dzVx = (ldro(Vz + n + si) - vz0) * re40x - (ldro(Vz + n + 2 * si) - ldro(Vz + n - si)) * re41x +
-                        (ldro(Vx + n + 1) - vx0) * re40z - (ldro(Vx + n + 2) - ldro(Vx + n - 1)) * re41z;
-    const F dyVz_dzVy = (ldro(Vz + n + sj) - vz0) * re40y - (ldro(Vz + n + 2 * sj) - ldro(Vz + n - sj)) * re41y +
-                        (ldro(Vy + n + 1) - vy0) * re40z - (ldro(Vy + n + 2) - ldro(Vy + n - 1)) * re41z;
+        const float mu2 = 2 * mu0;
+        const float lam2mu = a.lam() + mu2;
+        const float taup1 = (NM > 0) ? a.taup() : 0.0f;
 
-    const float mu0 = ldro(p.mu + n), mu_k = ldro(p.mu + n + 1), mu_i = ldro(p.mu + n + si), mu_j = ldro(p.mu + n + sj);
-    const float mu2 = 2 * mu0;
-    const float lam2mu = ldro(p.lam + n) + mu2;
-    const float taup1 = ldro(p.taup + n), taus1 = ldro(p.taus + n);
+        const float d3v3 = (float)(dxVx + dyVy + dzVz);
+        const float dyVy_dzVz = (float)(dyVy + dzVz);
+        const float dxVx_dzVz = (float)(dxVx + dzVz);
+        const float dxVx_dyVy = (float)(dxVx + dyVy);
 
-    const float d3v3 = (float)(dxVx + dyVy + dzVz);
-    const float dyVy_dzVz = (float)(dyVy + dzVz);
-    const float dxVx_dzVz = (float)(dxVx + dzVz);
-    const float dxVx_dyVy = (float)(dxVx + dyVy);
-
-    const float muxz = mu_harm(mu0, mu_k, mu_i, ldro(p.mu + n + 1 + si));
-    const float muxy = mu_harm(mu0, mu_i, mu_j, ldro(p.mu + n + si + sj));
-    const float muyz = mu_harm(mu0, mu_k, mu_j, ldro(p.mu + n + 1 + sj));
-
-    float Rxx_n = 0.0f, Ryy_n = 0.0f, Rzz_n = 0.0f, Ryz_n = 0.0f, Rxz_n = 0.0f, Rxy_n = 0.0f;
-    if (NM > 0) {
-        float *__restrict__ R = p.R + n;
-        const long long nc = p.ncell;
+        float Rxx_n = 0.0f, Ryy_n = 0.0f, Rzz_n = 0.0f;
+        if (NM > 0) {
 #pragma unroll
-        for (int m = 0; m < NM; m++) {
-            const float c1 = p.c1[m], c2 = p.c2[m], d1 = p.d1[m];
-            float *rxx = R + (0 * NM + m) * nc, *ryy = R + (1 * NM + m) * nc, *rzz = R + (2 * NM + m) * nc;
-            float *ryz = R + (3 * NM + m) * nc, *rxz = R + (4 * NM + m) * nc, *rxy = R + (5 * NM + m) * nc;
-            const float oxx = lds_(rxx), oyy = lds_(ryy), ozz = lds_(rzz), oyz = lds_(ryz), oxz = lds_(rxz), oxy = lds_(rxy);
-            const float nxx = c1 * (oxx) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dyVy_dzVz) * dt;
-            const float nyy = c1 * (oyy) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dzVz) * dt;
-            const float nzz = c1 * (ozz) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dyVy) * dt;
-            // shear R: the product with the F-kind strain rate is an F expression rounded on store (m_kernel.f90:320-322)
-            const float nyz = (float)(c1 * (oyz) - c2 * muyz * taus1 * dyVz_dzVy * dt);
-            const float nxz = (float)(c1 * (oxz) - c2 * muxz * taus1 * dxVz_dzVx * dt);
-            const float nxy = (float)(c1 * (oxy) - c2 * muxy * taus1 * dxVy_dyVx * dt);
-            sts_(rxx, nxx); sts_(ryy, nyy); sts_(rzz, nzz); sts_(ryz, nyz); sts_(rxz, nxz); sts_(rxy, nxy);
-            Rxx_n = Rxx_n + d1 * nxx; Ryy_n = Ryy_n + d1 * nyy; Rzz_n = Rzz_n + d1 * nzz;
-            Ryz_n = Ryz_n + d1 * nyz; Rxz_n = Rxz_n + d1 * nxz; Rxy_n = Rxy_n + d1 * nxy;
+            for (int m = 0; m < NM; m++) {
+                const float c1 = p.c1[m], c2 = p.c2[m], d1 = p.d1[m];
+                const float oxx = a.R(0 * NM + m), oyy = a.R(1 * NM + m), ozz = a.R(2 * NM + m);
+                const float nxx = c1 * (oxx) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dyVy_dzVz) * dt;
+                const float nyy = c1 * (oyy) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dzVz) * dt;
+                const float nzz = c1 * (ozz) - c2 * (lam2mu * taup1 * d3v3 - mu2 * taus1 * dxVx_dyVy) * dt;
+                rn[0][m] = nxx; rn[1][m] = nyy; rn[2][m] = nzz;
+                Rxx_n = Rxx_n + d1 * nxx; Ryy_n = Ryy_n + d1 * nyy; Rzz_n = Rzz_n + d1 * nzz;
+            }
+        }
+        const float taup_plus1 = 1 + taup1 * (1 + p.d2);
+        sn[0] = a.S(0) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dyVy_dzVz + Rxx_n) * dt;
+        sn[1] = a.S(1) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dzVz + Ryy_n) * dt;
+        sn[2] = a.S(2) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dyVy + Rzz_n) * dt;
+        if (cerjan) {
+            const float gcc = gxc * gyc * gzc;
+            sn[0] = sn[0] * gcc; sn[1] = sn[1] * gcc; sn[2] = sn[2] * gcc;
         }
     }
-    const float taup_plus1 = 1 + taup1 * (1 + p.d2);
-    const float taus_plus1 = 1 + taus1 * (1 + p.d2);
 
-    F sxx = lds_(p.Sxx + n) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dyVy_dzVz + Rxx_n) * dt;
-    F syy = lds_(p.Syy + n) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dzVz + Ryy_n) * dt;
-    F szz = lds_(p.Szz + n) + (lam2mu * taup_plus1 * d3v3 - mu2 * taus_plus1 * dxVx_dyVy + Rzz_n) * dt;
-    F syz = lds_(p.Syz + n) + (muyz * taus_plus1 * dyVz_dzVy + Ryz_n) * dt;
-    F sxz = lds_(p.Sxz + n) + (muxz * taus_plus1 * dxVz_dzVx + Rxz_n) * dt;
-    F sxy = lds_(p.Sxy + n) + (muxy * taus_plus1 * dxVy_dyVx + Rxy_n) * dt;
+    if (DO_S) {
+        const F vx0 = a.template V<0, 0, 0, 0>(), vy0 = a.template V<1, 0, 0, 0>(), vz0 = a.template V<2, 0, 0, 0>();
+        const F dxVy_dyVx = (a.template V<1, 0, 1, 0>() - vy0) * re40x - (a.template V<1, 0, 2, 0>() - a.template V<1, 0, -1, 0>()) * re41x +
+                            (a.template V<0, 0, 0, 1>() - vx0) * re40y - (a.template V<0, 0, 0, 2>() - a.template V<0, 0, 0, -1>()) * re41y;
+        const F dxVz_dzVx = (a.template V<2, 0, 1, 0>() - vz0) * re40x - (a.template V<2, 0, 2, 0>() - a.template V<2, 0, -1, 0>()) * re41x +
+                            (a.template V<0, 1, 0, 0>() - vx0) * re40z - (a.template V<0, 2, 0, 0>() - a.template V<0, -1, 0, 0>()) * re41z;
+        const F dyVz_dzVy = (a.template V<2, 0, 0, 1>() - vz0) * re40y - (a.template V<2, 0, 0, 2>() - a.template V<2, 0, 0, -1>()) * re41y +
+                            (a.template V<1, 1, 0, 0>() - vy0) * re40z - (a.template V<1, 2, 0, 0>() - a.template V<1, -1, 0, 0>()) * re41z;
 
-    if (p.abc == 2) {   // Cerjan sponge, m_absorb_c.f90:129-133, :155-157
-        const int kk = k + KOFF - 1;
-        const float gxc = p.cgx_c[mi], gxb = p.cgx_b[mi], gyc = p.cgy_c[mj], gyb = p.cgy_b[mj], gzc = p.cgz_c[kk], gzb = p.cgz_b[kk];
-        const float gcc = gxc * gyc * gzc;
-        sxx = sxx * gcc; syy = syy * gcc; szz = szz * gcc;
-        syz = syz * gxc * gyb * gzb;
-        sxz = sxz * gxb * gyc * gzb;
-        sxy = sxy * gxb * gyb * gzc;
+        const float mu_k = a.template mu<1, 0, 0>(), mu_i = a.template mu<0, 1, 0>(), mu_j = a.template mu<0, 0, 1>();
+        const float muxz = mu_harm(mu0, mu_k, mu_i, a.template mu<1, 1, 0>());
+        const float muxy = mu_harm(mu0, mu_i, mu_j, a.template mu<0, 1, 1>());
+        const float muyz = mu_harm(mu0, mu_k, mu_j, a.template mu<1, 0, 1>());
+
+        float Ryz_n = 0.0f, Rxz_n = 0.0f, Rxy_n = 0.0f;
+        if (NM > 0) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) {
+                const float c1 = p.c1[m], c2 = p.c2[m], d1 = p.d1[m];
+                const float oyz = a.R(3 * NM + m), oxz = a.R(4 * NM + m), oxy = a.R(5 * NM + m);
+                // shear R: the product with the F-kind strain rate is an F expression rounded on store (m_kernel.f90:320-322)
+                const float nyz = (float)(c1 * (oyz) - c2 * muyz * taus1 * dyVz_dzVy * dt);
+                const float nxz = (float)(c1 * (oxz) - c2 * muxz * taus1 * dxVz_dzVx * dt);
+                const float nxy = (float)(c1 * (oxy) - c2 * muxy * taus1 * dxVy_dyVx * dt);
+                rn[3][m] = nyz; rn[4][m] = nxz; rn[5][m] = nxy;
+                Ryz_n = Ryz_n + d1 * nyz; Rxz_n = Rxz_n + d1 * nxz; Rxy_n = Rxy_n + d1 * nxy;
+            }
+        }
+        sn[3] = a.S(3) + (muyz * taus_plus1 * dyVz_dzVy + Ryz_n) * dt;
+        sn[4] = a.S(4) + (muxz * taus_plus1 * dxVz_dzVx + Rxz_n) * dt;
+        sn[5] = a.S(5) + (muxy * taus_plus1 * dxVy_dyVx + Rxy_n) * dt;
+        if (cerjan) {
+            sn[3] = sn[3] * gxc * gyb * gzb;
+            sn[4] = sn[4] * gxb * gyc * gzb;
+            sn[5] = sn[5] * gxb * gyb * gzc;
+        }
     }
-    sts_(p.Sxx + n, sxx); sts_(p.Syy + n, syy); sts_(p.Szz + n, szz); sts_(p.Syz + n, syz); sts_(p.Sxz + n, sxz); sts_(p.Sxy + n, sxy);
+
+    // all loads above, all stores below: without `restrict` knowledge the compiler may not hoist a load over a store
+    if (DO_N) {
+        if (NM > 0) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) { a.setR(0 * NM + m, rn[0][m]); a.setR(1 * NM + m, rn[1][m]); a.setR(2 * NM + m, rn[2][m]); }
+        }
+        a.setS(0, sn[0]); a.setS(1, sn[1]); a.setS(2, sn[2]);
+    }
+    if (DO_S) {
+        if (NM > 0) {
+#pragma unroll
+            for (int m = 0; m < NM; m++) { a.setR(3 * NM + m, rn[3][m]); a.setR(4 * NM + m, rn[4][m]); a.setR(5 * NM + m, rn[5][m]); }
+        }
+        a.setS(3, sn[3]); a.setS(4, sn[4]); a.setS(5, sn[5]);
+    }
+}
+
+template <typename F, int NM>
+__device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n, int k, int mi, int mj, const int4 bnd) {
+    stress_interior_t<F, NM>(p, AccDirect<F, NM>(p, n), k, mi, mj, bnd);
 }
 
 // stress update of one PML cell: absorb_p__update_stress, m_absorb_p.f90:453-519 (both k-loops fused)
@@ -359,14 +423,16 @@ __device__ __forceinline__ void prefetch_cell(const KParams<F> &p, long long n, 
     }
 }
 
+struct Box3 { int k0, k1, li0, li1, lj0, lj1; int skip_interior; };   // inclusive: k 1-based, li / lj local 0-based; skip_interior: absorber cells only
+
 template <typename F, int NM, bool STRESS>
-__global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_constant__ KParams<F> p, int jlen, int lj_begin, int lj_end, int pf) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    const int li = blockIdx.y * blockDim.y + threadIdx.y;
-    if (k > p.nz || li >= p.nxp) return;
+__global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
+    const int k = b.k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int li = b.li0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (k > b.k1 || li > b.li1) return;
     const int mi = li + HALO;
-    const int ljs = lj_begin + blockIdx.z * jlen;
-    const int lje = min(ljs + jlen, lj_end);
+    const int ljs = b.lj0 + blockIdx.z * jlen;
+    const int lje = min(ljs + jlen, b.lj1 + 1);
     const bool pml_mode = (p.abc == 1);
     const bool i_interior = (li >= p.li0_k && li <= p.li1_k);
     for (int lj = ljs; lj < lje; lj++) {
@@ -390,7 +456,7 @@ __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_cons
             const long long a = p.aoff[li + (long long)p.nxp * lj] + (k - p.kbeg_a[col]);
             if (STRESS) stress_pml<F>(p, n, k, li, lj, a);
             else vel_pml<F>(p, n, k, li, lj, a);
-        } else if (i_interior && lj >= p.lj0_k && lj <= p.lj1_k && k <= p.k1_k) {
+        } else if (!b.skip_interior && i_interior && lj >= p.lj0_k && lj <= p.lj1_k && k <= p.k1_k) {
             const int4 bnd = p.band[col];
             if (STRESS) stress_interior<F, NM>(p, n, k, mi, mj, bnd);
             else vel_interior<F>(p, n, k, mi, mj, bnd);

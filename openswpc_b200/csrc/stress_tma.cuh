@@ -1,0 +1,218 @@
+// stress_tma.cuh -- fused interior stress sweep, version 2: TMA-staged, warp-specialised, mbarrier-pipelined.
+//
+// Why: the direct kernel (kernels.cuh) is latency-bound -- ~840 instructions per cell, 40 % of them 64-bit address
+// arithmetic, and its memory-level parallelism is capped by registers.  Here one producer lane issues five
+// `cp.async.bulk.tensor` (TMA) loads per j-plane into a shared-memory ring; sixteen consumer warps read their operands
+// with immediate-offset LDS, run the SAME arithmetic body (stress_interior_t) and store S / R straight to HBM.
+// Bytes in flight are bounded by shared memory (2-3 stages x 45 KB per SM), not by registers.
+//
+// Tile: TK = 32 cells along k (one warp lane each) x TI = 8 columns along i (one consumer warp each), marching along
+// j.  Per step t (plane j = j0 + t) the producer loads, under ONE full-barrier:
+//   S   box (TK, TI, 1, 6)        fields 3..8 of the field tensor      -> stage t % NS
+//   R   box (TK, TI, 1, 6*NM)     memory variables                     -> stage t % NS
+//   M   box (TK, TI, 1, 3|1)      lam, taup, taus (lam only if NM = 0) -> stage t % NS
+//   V   box (TK+8, TI+4, 1, 3)    Vx, Vy, Vz of plane j+2, with halo   -> ring slot (t+4) % (NS+4)
+//   mu  box (TK+4, TI+1, 1, 1)    mu of plane j+1                      -> ring slot (t+1) % (NS+1)
+// (step 0 also brings V planes j0-2..j0+1 and mu plane j0).  A consumer warp arrives on the stage's empty-barrier when
+// it has finished step t; the producer refills stage t % NS (and the V / mu slots whose last reader was step t-NS... t)
+// only after that.  Only tiles that lie completely inside the interior kernel box are handled here; the absorber
+// shell and the ragged edges stay with sweep_direct.
+#pragma once
+
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace swpc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+struct TmaMaps {
+    CUtensorMap S, V, R, M, Mu;
+};
+struct TmaGeom {
+    int li0, lj0, lj1;   // first interior column handled (local i), j range (local, inclusive)
+    int jl;              // planes per block
+    int m_first;         // index of lam in the medium tensor's 4th dimension (lam, taup, taus are consecutive)
+    int mu_index;        // index of mu in the medium tensor's 4th dimension
+};
+
+constexpr int align128(int x) { return (x + 127) / 128 * 128; }
+
+template <typename F, int NM>
+struct TmaCfg {
+#ifndef SWPC_TMA_TK
+#define SWPC_TMA_TK 32
+#endif
+#ifndef SWPC_TMA_TI
+#define SWPC_TMA_TI 8
+#endif
+    static constexpr int TK = SWPC_TMA_TK, TI = SWPC_TMA_TI, NS = 3;
+    static constexpr int NHW = (TK / 32) * TI;   // warps per half: one warp = 32 consecutive k of one column
+    static constexpr int NCW = 2 * NHW;          // consumer warps: NHW for the normal, NHW for the shear components
+    static constexpr int VHK = 4;   // k halo of the V box: 4 (not 2) so that the box start stays 16-byte aligned for float fields
+    static constexpr int VK = TK + 2 * VHK, VI = TI + 4;
+    static constexpr int NMED = (NM > 0) ? 3 : 1;
+    static constexpr int S_BYTES = 6 * TK * TI * (int)sizeof(F);
+    static constexpr int R_BYTES = 6 * NM * TK * TI * 4;
+    static constexpr int M_BYTES = NMED * TK * TI * 4;
+    static constexpr int R_OFF = align128(S_BYTES), M_OFF = R_OFF + align128(R_BYTES);
+    static constexpr int STAGE = M_OFF + align128(M_BYTES);
+    static constexpr int V_BYTES = 3 * VK * VI * (int)sizeof(F), V_STRIDE = align128(V_BYTES);
+    static constexpr int MUK = TK + 4, MUI = TI + 1;
+    static constexpr int MU_BYTES = MUK * MUI * 4, MU_STRIDE = align128(MU_BYTES);
+    static constexpr int NV = NS + 4, NMU = NS + 1;
+    static constexpr int V_OFF = NS * STAGE, MU_OFF = V_OFF + NV * V_STRIDE, BAR_OFF = MU_OFF + NMU * MU_STRIDE;
+    static constexpr int SMEM = BAR_OFF + 128;
+    static constexpr int STEP_TX = S_BYTES + R_BYTES + M_BYTES + V_BYTES + MU_BYTES;
+    static constexpr int THREADS = (NCW + 1) * 32;
+};
+
+// operands in shared memory (tiles written by TMA), results to global
+template <typename F, int NM>
+struct AccTma {
+    using C = TmaCfg<F, NM>;
+    const KParams<F> &p;
+    const F *v[5];          // V planes j-2 .. j+2, each [3][VI][VK]; pointers already offset to this thread's cell
+    const float *mu0, *mu1; // mu planes j, j+1, each [MUI][MUK]; offset to this thread's cell
+    const F *s;             // [6][TI][TK]
+    const float *r;         // [6*NM][TI][TK]
+    const float *m;         // [NMED][TI][TK]
+    long long n;            // global linear index of the cell
+    __device__ __forceinline__ AccTma(const KParams<F> &p_) : p(p_) {}
+    template <int f, int dk, int di, int dj> __device__ __forceinline__ F V() const { return v[dj + 2][f * (C::VI * C::VK) + di * C::VK + dk]; }
+    template <int dk, int di, int dj> __device__ __forceinline__ float mu() const { return (dj == 0 ? mu0 : mu1)[di * C::MUK + dk]; }
+    __device__ __forceinline__ float lam() const { return m[0]; }
+    __device__ __forceinline__ float taup() const { return m[1 * C::TI * C::TK]; }
+    __device__ __forceinline__ float taus() const { return m[2 * C::TI * C::TK]; }
+    __device__ __forceinline__ F *sptr(int c) const { return c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy; }
+    __device__ __forceinline__ F S(int c) const { return s[c * (C::TI * C::TK)]; }
+    __device__ __forceinline__ void setS(int c, F val) const { sts_(sptr(c) + n, val); }
+    __device__ __forceinline__ float R(int q) const { return r[q * (C::TI * C::TK)]; }
+    __device__ __forceinline__ void setR(int q, float val) const { sts_(p.R + n + q * p.ncell, val); }
+};
+
+template <typename F, int NM>
+#ifndef SWPC_TMA_MAXREG
+#define SWPC_TMA_MAXREG 80
+#endif
+// register cap (instead of __launch_bounds__): 17 warps x 80 registers leave room for one sweep_direct block of the
+// absorber shell on the same SM
+__global__ void __maxnreg__(SWPC_TMA_MAXREG)
+stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps tm, const TmaGeom g) {
+    using C = TmaCfg<F, NM>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::BAR_OFF);
+    uint64_t *empty = full + C::NS;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = 1 + blockIdx.x * C::TK;                 // first k of the tile (1-based)
+    const int li0 = g.li0 + blockIdx.y * C::TI;            // first local i of the tile
+    const int lj0 = g.lj0 + blockIdx.z * g.jl;             // first local j of the march
+    const int nsteps = min(g.jl, g.lj1 - lj0 + 1);
+    // tensor coordinates (elements): k -> k + KOFF - 1, i -> li + HALO, j -> lj + HALO
+    const int ck = k0 + KOFF - 1, ci = li0 + HALO, cj = lj0 + HALO;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NS; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], C::NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == C::NCW) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            for (int t = 0; t < nsteps; t++) {
+                const int s = t % C::NS;
+                if (t >= C::NS) mbar_wait(&empty[s], ((t / C::NS) - 1) & 1);
+                unsigned char *st = smem + s * C::STAGE;
+                uint32_t tx = C::STEP_TX;
+                if (t == 0) tx += 4 * C::V_BYTES + C::MU_BYTES;
+                mbar_expect_tx(&full[s], tx);
+                if (t == 0) {
+                    for (int q = 0; q < 4; q++)
+                        tma_load_4d(smem + C::V_OFF + q * C::V_STRIDE, &tm.V, &full[s], ck - C::VHK, ci - 2, cj - 2 + q, 0);
+                    tma_load_4d(smem + C::MU_OFF, &tm.Mu, &full[s], ck, ci, cj, g.mu_index);
+                }
+                tma_load_4d(st, &tm.S, &full[s], ck, ci, cj + t, 3);
+                if (NM > 0) tma_load_4d(st + C::R_OFF, &tm.R, &full[s], ck, ci, cj + t, 0);
+                tma_load_4d(st + C::M_OFF, &tm.M, &full[s], ck, ci, cj + t, g.m_first);
+                tma_load_4d(smem + C::V_OFF + ((t + 4) % C::NV) * C::V_STRIDE, &tm.V, &full[s], ck - C::VHK, ci - 2, cj + t + 2, 0);
+                tma_load_4d(smem + C::MU_OFF + ((t + 1) % C::NMU) * C::MU_STRIDE, &tm.Mu, &full[s], ck, ci, cj + t + 1, g.mu_index);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers: warp = column (x2: warps 0..TI-1
+    // update the normal components, warps TI..2TI-1 the shear components of the same cells), lane = k
+    const bool shear = warp >= C::NHW;
+    const int wq = shear ? warp - C::NHW : warp;
+    const int tk = (wq % (C::TK / 32)) * 32 + lane, ti = wq / (C::TK / 32);
+    const bool active = (k0 + tk) <= p.k1_k;   // last k-tile may reach into the absorber: those lanes only idle
+    const int k = k0 + tk, li = li0 + ti, mi = li + HALO;
+    AccTma<F, NM> a(p);
+    const int voff = (ti + 2) * C::VK + (tk + C::VHK);
+    const int muoff = ti * C::MUK + tk;
+    const int coff = ti * C::TK + tk;
+    long long col = (long long)mi + (long long)p.NXM * (lj0 + HALO);
+    a.n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+    for (int t = 0; t < nsteps; t++) {
+        const int s = t % C::NS;
+        const int4 bnd = p.band[col];
+        mbar_wait(&full[s], (t / C::NS) & 1);
+        const unsigned char *st = smem + s * C::STAGE;
+#pragma unroll
+        for (int q = 0; q < 5; q++) a.v[q] = reinterpret_cast<const F *>(smem + C::V_OFF + ((t + q) % C::NV) * C::V_STRIDE) + voff;
+        a.mu0 = reinterpret_cast<const float *>(smem + C::MU_OFF + (t % C::NMU) * C::MU_STRIDE) + muoff;
+        a.mu1 = reinterpret_cast<const float *>(smem + C::MU_OFF + ((t + 1) % C::NMU) * C::MU_STRIDE) + muoff;
+        a.s = reinterpret_cast<const F *>(st) + coff;
+        a.r = reinterpret_cast<const float *>(st + C::R_OFF) + coff;
+        a.m = reinterpret_cast<const float *>(st + C::M_OFF) + coff;
+        if (active) {
+            if (shear) stress_interior_t<F, NM, AccTma<F, NM>, false, true>(p, a, k, mi, lj0 + t + HALO, bnd);
+            else stress_interior_t<F, NM, AccTma<F, NM>, true, false>(p, a, k, mi, lj0 + t + HALO, bnd);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        a.n += p.SJ;
+        col += p.NXM;
+    }
+}
+
+}   // namespace swpc

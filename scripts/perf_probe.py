@@ -89,7 +89,12 @@ def main():
     pml_frac = 1 - ((a.nx - 2 * a.na) * (a.ny - 2 * a.na) * (a.nz - a.na)) / ncell if a.abc == "pml" else 0.0
     bpc = bytes_per_cell(a.nm, W, pml_frac)
     for cfg in a.configs.split(";"):
-        tk, ti, jlen, pf = (list(map(int, cfg.split(","))) + [0])[:4]
+        vals = list(map(int, cfg.split(",")))
+        tk, ti, jlen, pf = (vals + [0])[:4]
+        if len(vals) > 4:
+            dev.set_option("tma_jl", vals[4])
+        if len(vals) > 5:
+            dev.set_option("tma", vals[5])
         dev.set_option("tk", tk)
         dev.set_option("ti", ti)
         dev.set_option("jlen", jlen)
