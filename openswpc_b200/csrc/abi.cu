@@ -138,9 +138,11 @@ struct swpc3d_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tuning
     int tk = 32, ti = 8, jlen = 16, pf = 1;
-    int use_tma = 1, tma_jl = 32;
+    int use_tma = 1, tma_jl = 32;   // use_tma: 0 off, 1 stress sweep only (default: measured fastest), 2 stress + velocity sweeps
     bool tma_ready = false, tma_ok = false;
     TmaMaps tmaps{};
+    TmaMapsVel vmaps{};
+    bool vtma_ok = false;
     int variant = 1;
     long long launches = 0;
     // per-kernel CUDA-event timing of the two sweeps (option "kernel_timing"): event pairs recorded on the launch
@@ -253,7 +255,11 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
     // the nine fields live in ONE allocation (field f at f*ncell) so that a single 4-D TMA tensor covers them
     CK(cudaMalloc(&h->Fall, (size_t)h->ncell * h->fb * 9));
     CK(cudaMemsetAsync(h->Fall, 0, (size_t)h->ncell * h->fb * 9, h->st));
-    for (int a = 0; a < 9; a++) h->F[a] = (char *)h->Fall + (size_t)a * h->ncell * h->fb;
+    {   // device slot order: Vx Vy Vz | Sxx Szz Sxz | Syy Syz Sxy  (the velocity sweep needs the last three as a j-ring,
+        // the middle three only in-plane; F[] keeps the reference's order Vx Vy Vz Sxx Syy Szz Syz Sxz Sxy)
+        const int slot[9] = {0, 1, 2, 3, 6, 4, 7, 5, 8};
+        for (int a = 0; a < 9; a++) h->F[a] = (char *)h->Fall + (size_t)slot[a] * h->ncell * h->fb;
+    }
     if (h->nm > 0) {
         CK(cudaMalloc(&h->R, (size_t)h->ncell * 6 * h->nm * sizeof(float)));
         CK(cudaMemsetAsync(h->R, 0, (size_t)h->ncell * 6 * h->nm * sizeof(float), h->st));
@@ -596,6 +602,13 @@ static int tma_prepare(swpc3d_handle *h) {
         return 0;
     }
     h->tma_ok = true;
+    using CV = TmaCfgVel<F>;
+    h->vtma_ok = CV::SMEM <= 227 * 1024 && make_map(h, &h->vmaps.Vv, h->Fall, sizeof(F), 9, CV::TK, CV::TI, 3) &&
+                 make_map(h, &h->vmaps.Sh, h->Fall, sizeof(F), 9, CV::SK, CV::SI_, 3) && make_map(h, &h->vmaps.Rho, h->Mall, 4, 5, CV::RK, CV::RI, 1);
+    if (h->vtma_ok && cudaFuncSetAttribute(vel_tma<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, CV::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        h->vtma_ok = false;
+    }
     return 0;
 }
 
@@ -649,6 +662,38 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p) {
     return 0;
 }
 
+template <typename F, int NM>
+static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p) {
+    using C = TmaCfg<F, NM>;
+    using CV = TmaCfgVel<F>;
+    if (!h->tma_ready) tma_prepare<F, NM>(h);
+    const Box3 t = tma_box<F, NM>(h);
+    const Box3 all{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0};
+    if (t.k1 < t.k0 || !h->vtma_ok || h->use_tma < 2) return launch_direct_box<F, false>(h, p, all);
+    TmaGeom g{};
+    g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl);
+    dim3 grd((unsigned)((t.k1 - t.k0 + 1) / CV::TK), (unsigned)((t.li1 - t.li0 + 1) / CV::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
+    const int kE = (h->g.kend_k / C::TK) * C::TK + 1;
+    const Box3 boxes[5] = {Box3{1, h->g.nz, 0, h->nxp - 1, 0, t.lj0 - 1, 0}, Box3{1, h->g.nz, 0, h->nxp - 1, t.lj1 + 1, h->nyp - 1, 0},
+                           Box3{1, h->g.nz, 0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, h->nxp - 1, t.lj0, t.lj1, 0},
+                           Box3{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1}};
+    if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
+    vel_tma<F><<<grd, CV::THREADS, CV::SMEM, h->st>>>(p, h->vmaps, g);
+    h->launches++;
+    CK(cudaGetLastError());
+    for (int q = 0; q < 5; q++) {
+        const Box3 &b = boxes[q];
+        if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
+        if (h->use_side) {
+            CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
+            if (launch_direct_box<F, false>(h, p, b, h->side[q])) return 1;
+            CK(cudaEventRecord(h->ev_join[q], h->side[q]));
+            CK(cudaStreamWaitEvent(h->st, h->ev_join[q], 0));
+        } else if (launch_direct_box<F, false>(h, p, b)) return 1;
+    }
+    return 0;
+}
+
 template <typename F, bool STRESS>
 static int launch_sweep(swpc3d_handle *h) {
     const KParams<F> p = make_params<F>(h);
@@ -674,7 +719,12 @@ static int launch_sweep(swpc3d_handle *h) {
         default: rc = launch_stress_nm<F, 3>(h, p); break;
         }
     } else {
-        rc = launch_direct_box<F, false>(h, p, Box3{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0});
+        switch (h->nm) {
+        case 0: rc = launch_vel_nm<F, 0>(h, p); break;
+        case 1: rc = launch_vel_nm<F, 1>(h, p); break;
+        case 2: rc = launch_vel_nm<F, 2>(h, p); break;
+        default: rc = launch_vel_nm<F, 3>(h, p); break;
+        }
     }
     if (rc) return rc;
     if (timed) {

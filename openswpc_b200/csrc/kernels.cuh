@@ -302,31 +302,43 @@ __device__ __forceinline__ void stress_pml(const KParams<F> &p, long long n, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// velocity update of one interior cell: kernel__update_vel m_kernel.f90:99-129 (+ Cerjan m_absorb_c.f90:185-187)
+// velocity update of one interior cell: kernel__update_vel m_kernel.f90:99-129 (+ Cerjan m_absorb_c.f90:185-187).
+// Accessor form as for the stress body: S<c,dk,di,dj> with c = 0 xx, 1 yy, 2 zz, 3 yz, 4 xz, 5 xy.
 template <typename F>
-__device__ __forceinline__ void vel_interior(const KParams<F> &p, long long n, int k, int mi, int mj, const int4 bnd) {
-    const long long si = p.SI, sj = p.SJ;
+struct AccVelDirect {
+    const KParams<F> &p;
+    long long n;
+    __device__ __forceinline__ AccVelDirect(const KParams<F> &p_, long long n_) : p(p_), n(n_) {}
+    template <int c, int dk, int di, int dj> __device__ __forceinline__ F S() const {
+        const F *b = c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy;
+        return ldro(b + n + dk + di * p.SI + dj * p.SJ);
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float rho() const { return ldro(p.rho + n + dk + di * p.SI + dj * p.SJ); }
+    __device__ __forceinline__ F V(int f) const { return (f == 0 ? p.Vx : f == 1 ? p.Vy : p.Vz)[n]; }
+    __device__ __forceinline__ void setV(int f, F v) const { (f == 0 ? p.Vx : f == 1 ? p.Vy : p.Vz)[n] = v; }
+};
+
+template <typename F, typename A>
+__device__ __forceinline__ void vel_interior_t(const KParams<F> &p, const A &a, int k, int mi, int mj, const int4 bnd) {
     const int o = fd_order_sel(k, bnd);
     const F re40x = p.r40x[o], re41x = p.r41x[o], re40y = p.r40y[o], re41y = p.r41y[o], re40z = p.r40z[o], re41z = p.r41z[o];
-    const F *__restrict__ Sxx = p.Sxx, *__restrict__ Syy = p.Syy, *__restrict__ Szz = p.Szz;
-    const F *__restrict__ Syz = p.Syz, *__restrict__ Sxz = p.Sxz, *__restrict__ Sxy = p.Sxy;
     const float dt = p.dt;
-    const F sxy0 = ldro(Sxy + n), sxz0 = ldro(Sxz + n), syz0 = ldro(Syz + n);
+    const F sxy0 = a.template S<5, 0, 0, 0>(), sxz0 = a.template S<4, 0, 0, 0>(), syz0 = a.template S<3, 0, 0, 0>();
 
-    const F d3Sx3 = (ldro(Sxx + n + si) - ldro(Sxx + n)) * re40x - (ldro(Sxx + n + 2 * si) - ldro(Sxx + n - si)) * re41x +
-                    (sxy0 - ldro(Sxy + n - sj)) * re40y - (ldro(Sxy + n + sj) - ldro(Sxy + n - 2 * sj)) * re41y +
-                    (sxz0 - ldro(Sxz + n - 1)) * re40z - (ldro(Sxz + n + 1) - ldro(Sxz + n - 2)) * re41z;
-    const F d3Sy3 = (sxy0 - ldro(Sxy + n - si)) * re40x - (ldro(Sxy + n + si) - ldro(Sxy + n - 2 * si)) * re41x +
-                    (ldro(Syy + n + sj) - ldro(Syy + n)) * re40y - (ldro(Syy + n + 2 * sj) - ldro(Syy + n - sj)) * re41y +
-                    (syz0 - ldro(Syz + n - 1)) * re40z - (ldro(Syz + n + 1) - ldro(Syz + n - 2)) * re41z;
-    const F d3Sz3 = (sxz0 - ldro(Sxz + n - si)) * re40x - (ldro(Sxz + n + si) - ldro(Sxz + n - 2 * si)) * re41x +
-                    (syz0 - ldro(Syz + n - sj)) * re40y - (ldro(Syz + n + sj) - ldro(Syz + n - 2 * sj)) * re41y +
-                    (ldro(Szz + n + 1) - ldro(Szz + n)) * re40z - (ldro(Szz + n + 2) - ldro(Szz + n - 1)) * re41z;
+    const F d3Sx3 = (a.template S<0, 0, 1, 0>() - a.template S<0, 0, 0, 0>()) * re40x - (a.template S<0, 0, 2, 0>() - a.template S<0, 0, -1, 0>()) * re41x +
+                    (sxy0 - a.template S<5, 0, 0, -1>()) * re40y - (a.template S<5, 0, 0, 1>() - a.template S<5, 0, 0, -2>()) * re41y +
+                    (sxz0 - a.template S<4, -1, 0, 0>()) * re40z - (a.template S<4, 1, 0, 0>() - a.template S<4, -2, 0, 0>()) * re41z;
+    const F d3Sy3 = (sxy0 - a.template S<5, 0, -1, 0>()) * re40x - (a.template S<5, 0, 1, 0>() - a.template S<5, 0, -2, 0>()) * re41x +
+                    (a.template S<1, 0, 0, 1>() - a.template S<1, 0, 0, 0>()) * re40y - (a.template S<1, 0, 0, 2>() - a.template S<1, 0, 0, -1>()) * re41y +
+                    (syz0 - a.template S<3, -1, 0, 0>()) * re40z - (a.template S<3, 1, 0, 0>() - a.template S<3, -2, 0, 0>()) * re41z;
+    const F d3Sz3 = (sxz0 - a.template S<4, 0, -1, 0>()) * re40x - (a.template S<4, 0, 1, 0>() - a.template S<4, 0, -2, 0>()) * re41x +
+                    (syz0 - a.template S<3, 0, 0, -1>()) * re40y - (a.template S<3, 0, 0, 1>() - a.template S<3, 0, 0, -2>()) * re41y +
+                    (a.template S<2, 1, 0, 0>() - a.template S<2, 0, 0, 0>()) * re40z - (a.template S<2, 2, 0, 0>() - a.template S<2, -1, 0, 0>()) * re41z;
 
-    const float rho0 = ldro(p.rho + n);
-    F vx = p.Vx[n] + 2.0f / (rho0 + ldro(p.rho + n + si)) * d3Sx3 * dt;
-    F vy = p.Vy[n] + 2.0f / (rho0 + ldro(p.rho + n + sj)) * d3Sy3 * dt;
-    F vz = p.Vz[n] + 2.0f / (rho0 + ldro(p.rho + n + 1)) * d3Sz3 * dt;
+    const float rho0 = a.template rho<0, 0, 0>();
+    F vx = a.V(0) + 2.0f / (rho0 + a.template rho<0, 1, 0>()) * d3Sx3 * dt;
+    F vy = a.V(1) + 2.0f / (rho0 + a.template rho<0, 0, 1>()) * d3Sy3 * dt;
+    F vz = a.V(2) + 2.0f / (rho0 + a.template rho<1, 0, 0>()) * d3Sz3 * dt;
     if (p.abc == 2) {
         const int kk = k + KOFF - 1;
         const float gxc = p.cgx_c[mi], gxb = p.cgx_b[mi], gyc = p.cgy_c[mj], gyb = p.cgy_b[mj], gzc = p.cgz_c[kk], gzb = p.cgz_b[kk];
@@ -334,7 +346,12 @@ __device__ __forceinline__ void vel_interior(const KParams<F> &p, long long n, i
         vy = vy * gxc * gyb * gzc;
         vz = vz * gxc * gyc * gzb;
     }
-    p.Vx[n] = vx; p.Vy[n] = vy; p.Vz[n] = vz;
+    a.setV(0, vx); a.setV(1, vy); a.setV(2, vz);
+}
+
+template <typename F>
+__device__ __forceinline__ void vel_interior(const KParams<F> &p, long long n, int k, int mi, int mj, const int4 bnd) {
+    vel_interior_t<F>(p, AccVelDirect<F>(p, n), k, mi, mj, bnd);
 }
 
 // velocity update of one PML cell: absorb_p__update_vel m_absorb_p.f90:261-308

@@ -118,7 +118,8 @@ struct AccTma {
     __device__ __forceinline__ float taup() const { return m[1 * C::TI * C::TK]; }
     __device__ __forceinline__ float taus() const { return m[2 * C::TI * C::TK]; }
     __device__ __forceinline__ F *sptr(int c) const { return c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy; }
-    __device__ __forceinline__ F S(int c) const { return s[c * (C::TI * C::TK)]; }
+    // S box = field slots 3..8 = Sxx Szz Sxz Syy Syz Sxy (device slot order, see abi.cu); c = xx yy zz yz xz xy
+    __device__ __forceinline__ F S(int c) const { return s[(c == 0 ? 0 : c == 1 ? 3 : c == 2 ? 1 : c == 3 ? 4 : c == 4 ? 2 : 5) * (C::TI * C::TK)]; }
     __device__ __forceinline__ void setS(int c, F val) const { sts_(sptr(c) + n, val); }
     __device__ __forceinline__ float R(int q) const { return r[q * (C::TI * C::TK)]; }
     __device__ __forceinline__ void setR(int q, float val) const { sts_(p.R + n + q * p.ncell, val); }
@@ -208,6 +209,132 @@ stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps
             if (shear) stress_interior_t<F, NM, AccTma<F, NM>, false, true>(p, a, k, mi, lj0 + t + HALO, bnd);
             else stress_interior_t<F, NM, AccTma<F, NM>, true, false>(p, a, k, mi, lj0 + t + HALO, bnd);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        a.n += p.SJ;
+        col += p.NXM;
+    }
+}
+
+// ================================================================================================
+// velocity sweep, same scheme.  Per step t (plane j = j0 + t), one full-barrier:
+//   V    box (TK, TI, 1, 3)        Vx Vy Vz (field slots 0..2), read-modify-write   -> stage t % NS
+//   SA   box (TK+8, TI+4, 1, 3)    Sxx Szz Sxz (slots 3..5): only plane j is needed -> stage t % NS
+//   SB   box (TK+8, TI+4, 1, 3)    Syy Syz Sxy (slots 6..8) of plane j+2            -> ring slot (t+4) % (NS+4)
+//   rho  box (TK+4, TI+1, 1, 1)    rho of plane j+1                                 -> ring slot (t+1) % (NS+1)
+struct TmaMapsVel {
+    CUtensorMap Vv, Sh, Rho;   // Sh serves SA and SB (same box, different 4th coordinate)
+};
+
+template <typename F>
+struct TmaCfgVel {
+    static constexpr int TK = SWPC_TMA_TK, TI = SWPC_TMA_TI, NS = 3;
+    static constexpr int NCW = (TK / 32) * TI;
+    static constexpr int HK = 4;
+    static constexpr int SK = TK + 2 * HK, SI_ = TI + 4;
+    static constexpr int V_BYTES = 3 * TK * TI * (int)sizeof(F);
+    static constexpr int S_BYTES = 3 * SK * SI_ * (int)sizeof(F), S_STRIDE = align128(S_BYTES);
+    static constexpr int SA_OFF = align128(V_BYTES);
+    static constexpr int STAGE = SA_OFF + S_STRIDE;
+    static constexpr int RK = TK + 4, RI = TI + 1;
+    static constexpr int RHO_BYTES = RK * RI * 4, RHO_STRIDE = align128(RHO_BYTES);
+    static constexpr int NB = NS + 4, NRHO = NS + 1;
+    static constexpr int SB_OFF = NS * STAGE, RHO_OFF = SB_OFF + NB * S_STRIDE, BAR_OFF = RHO_OFF + NRHO * RHO_STRIDE;
+    static constexpr int SMEM = BAR_OFF + 128;
+    static constexpr int STEP_TX = V_BYTES + 2 * S_BYTES + RHO_BYTES;
+    static constexpr int THREADS = (NCW + 1) * 32;
+};
+
+template <typename F>
+struct AccVelTma {
+    using C = TmaCfgVel<F>;
+    const KParams<F> &p;
+    const F *sa;            // [3][SI_][SK] plane j: Sxx Szz Sxz, offset to this thread's cell
+    const F *sb[5];         // planes j-2..j+2: [3][SI_][SK] Syy Syz Sxy
+    const float *rho0, *rho1;
+    const F *v;             // [3][TI][TK]
+    long long n;
+    __device__ __forceinline__ AccVelTma(const KParams<F> &p_) : p(p_) {}
+    template <int c, int dk, int di, int dj> __device__ __forceinline__ F S() const {
+        constexpr int PL = C::SI_ * C::SK;
+        if (c == 0 || c == 2 || c == 4) {   // xx zz xz live in the per-step tile (dj is always 0 for them)
+            return sa[(c == 0 ? 0 : c == 2 ? 1 : 2) * PL + di * C::SK + dk];
+        } else {                              // yy yz xy in the j ring
+            return sb[dj + 2][(c == 1 ? 0 : c == 3 ? 1 : 2) * PL + di * C::SK + dk];
+        }
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float rho() const { return (dj == 0 ? rho0 : rho1)[di * C::RK + dk]; }
+    __device__ __forceinline__ F V(int f) const { return v[f * (C::TI * C::TK)]; }
+    __device__ __forceinline__ void setV(int f, F val) const { (f == 0 ? p.Vx : f == 1 ? p.Vy : p.Vz)[n] = val; }
+};
+
+template <typename F>
+__global__ void __maxnreg__(SWPC_TMA_MAXREG)
+vel_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMapsVel tm, const TmaGeom g) {
+    using C = TmaCfgVel<F>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::BAR_OFF);
+    uint64_t *empty = full + C::NS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k0 = 1 + blockIdx.x * C::TK;
+    const int li0 = g.li0 + blockIdx.y * C::TI;
+    const int lj0 = g.lj0 + blockIdx.z * g.jl;
+    const int nsteps = min(g.jl, g.lj1 - lj0 + 1);
+    const int ck = k0 + KOFF - 1, ci = li0 + HALO, cj = lj0 + HALO;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NS; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], C::NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == C::NCW) {
+        if (lane == 0) {
+            for (int t = 0; t < nsteps; t++) {
+                const int s = t % C::NS;
+                if (t >= C::NS) mbar_wait(&empty[s], ((t / C::NS) - 1) & 1);
+                unsigned char *st = smem + s * C::STAGE;
+                uint32_t tx = C::STEP_TX;
+                if (t == 0) tx += 4 * C::S_BYTES + C::RHO_BYTES;
+                mbar_expect_tx(&full[s], tx);
+                if (t == 0) {
+                    for (int q = 0; q < 4; q++)
+                        tma_load_4d(smem + C::SB_OFF + q * C::S_STRIDE, &tm.Sh, &full[s], ck - C::HK, ci - 2, cj - 2 + q, 6);
+                    tma_load_4d(smem + C::RHO_OFF, &tm.Rho, &full[s], ck, ci, cj, 0);
+                }
+                tma_load_4d(st, &tm.Vv, &full[s], ck, ci, cj + t, 0);
+                tma_load_4d(st + C::SA_OFF, &tm.Sh, &full[s], ck - C::HK, ci - 2, cj + t, 3);
+                tma_load_4d(smem + C::SB_OFF + ((t + 4) % C::NB) * C::S_STRIDE, &tm.Sh, &full[s], ck - C::HK, ci - 2, cj + t + 2, 6);
+                tma_load_4d(smem + C::RHO_OFF + ((t + 1) % C::NRHO) * C::RHO_STRIDE, &tm.Rho, &full[s], ck, ci, cj + t + 1, 0);
+            }
+        }
+        return;
+    }
+
+    const int tk = (warp % (C::TK / 32)) * 32 + lane, ti = warp / (C::TK / 32);
+    const bool active = (k0 + tk) <= p.k1_k;
+    const int k = k0 + tk, li = li0 + ti, mi = li + HALO;
+    AccVelTma<F> a(p);
+    const int soff = (ti + 2) * C::SK + (tk + C::HK);
+    const int roff = ti * C::RK + tk;
+    const int coff = ti * C::TK + tk;
+    long long col = (long long)mi + (long long)p.NXM * (lj0 + HALO);
+    a.n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+    for (int t = 0; t < nsteps; t++) {
+        const int s = t % C::NS;
+        const int4 bnd = p.band[col];
+        mbar_wait(&full[s], (t / C::NS) & 1);
+        const unsigned char *st = smem + s * C::STAGE;
+#pragma unroll
+        for (int q = 0; q < 5; q++) a.sb[q] = reinterpret_cast<const F *>(smem + C::SB_OFF + ((t + q) % C::NB) * C::S_STRIDE) + soff;
+        a.rho0 = reinterpret_cast<const float *>(smem + C::RHO_OFF + (t % C::NRHO) * C::RHO_STRIDE) + roff;
+        a.rho1 = reinterpret_cast<const float *>(smem + C::RHO_OFF + ((t + 1) % C::NRHO) * C::RHO_STRIDE) + roff;
+        a.v = reinterpret_cast<const F *>(st) + coff;
+        a.sa = reinterpret_cast<const F *>(st + C::SA_OFF) + soff;
+        if (active) vel_interior_t<F>(p, a, k, mi, lj0 + t + HALO, bnd);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         a.n += p.SJ;
