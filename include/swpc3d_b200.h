@@ -93,6 +93,13 @@ int swpc3d_set_sources(swpc3d_handle *h, int32_t nsrc, const int32_t *isrc, cons
 int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t *ist, const int32_t *jst, const int32_t *kst,
                         int32_t ntdec_w, int32_t ntw, float M0, float UC);
 
+/* which station products wav__store keeps (m_wav.f90:67-70 sw_wav_v/u/stress/strain); call after swpc3d_set_stations.
+ * Default: velocity only. */
+int swpc3d_set_wav_products(swpc3d_handle *h, int32_t sw_v, int32_t sw_u, int32_t sw_stress, int32_t sw_strain);
+/* `!$acc update self(wav_*)` m_wav.f90:672-675; which: 0 velocity (ntw,3,nst) [nm/s], 1 displacement (ntw,3,nst) [nm],
+ * 2 stress (ntw,6,nst) [Pa], 3 strain (ntw,6,nst) */
+int swpc3d_get_wav_product(swpc3d_handle *h, int32_t which, float *out);
+
 /* the hot path, one call per reference subroutine */
 int swpc3d_update_stress(swpc3d_handle *h);            /* kernel__update_stress m_kernel.f90:142 + absorb__update_stress m_absorb.f90:60 (fused) */
 int swpc3d_stressglut(swpc3d_handle *h, int32_t it);   /* source__stressglut    m_source.f90:776 */

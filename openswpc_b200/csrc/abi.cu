@@ -122,7 +122,9 @@ struct swpc3d_handle {
     // stations
     int nst = 0, ntdec_w = 0, ntw = 0;
     int *st_ijk = nullptr;
-    float *wav = nullptr;
+    float *wav = nullptr;                  // velocity traces
+    float *wav_u = nullptr, *wav_s = nullptr, *wav_e = nullptr, *wav_acc = nullptr;
+    int sw_v = 1, sw_u = 0, sw_stress = 0, sw_strain = 0;
     float M0 = 1.f, UC = 1e-15f;
     unsigned int *vmax_d = nullptr;
     // halo
@@ -318,7 +320,7 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->aoff); cudaFree(h->aux);
     for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
     cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
-    cudaFree(h->st_ijk); cudaFree(h->wav); cudaFree(h->vmax_d);
+    cudaFree(h->st_ijk); cudaFree(h->wav); cudaFree(h->wav_u); cudaFree(h->wav_s); cudaFree(h->wav_e); cudaFree(h->wav_acc); cudaFree(h->vmax_d);
     for (int f = 0; f < 4; f++) { cudaFree(h->sbuf[f]); cudaFree(h->rbuf[f]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -408,6 +410,7 @@ extern "C" int swpc3d_zero_state(swpc3d_handle *h) {
     if (h->R) CK(cudaMemsetAsync(h->R, 0, (size_t)h->ncell * 6 * h->nm * sizeof(float), h->st));
     if (h->aux) CK(cudaMemsetAsync(h->aux, 0, (size_t)h->naux * 18 * sizeof(float), h->st));
     if (h->wav) CK(cudaMemsetAsync(h->wav, 0, (size_t)h->ntw * 3 * h->nst * sizeof(float), h->st));
+    if (h->wav_acc) CK(cudaMemsetAsync(h->wav_acc, 0, (size_t)9 * h->nst * sizeof(float), h->st));
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -818,16 +821,53 @@ extern "C" int swpc3d_bodyforce(swpc3d_handle *h, int32_t it) {
     return h->fb == 8 ? launch_source<double>(h, it, true) : launch_source<float>(h, it, true);
 }
 
+extern "C" int swpc3d_set_wav_products(swpc3d_handle *h, int32_t sw_v, int32_t sw_u, int32_t sw_stress, int32_t sw_strain) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->dev));
+    h->sw_v = sw_v; h->sw_u = sw_u; h->sw_stress = sw_stress; h->sw_strain = sw_strain;
+    cudaFree(h->wav_u); cudaFree(h->wav_s); cudaFree(h->wav_e); cudaFree(h->wav_acc);
+    h->wav_u = h->wav_s = h->wav_e = h->wav_acc = nullptr;
+    if (h->nst <= 0 || h->ntw <= 0) return 0;
+    const size_t n3 = (size_t)h->ntw * 3 * h->nst * sizeof(float), n6 = 2 * n3;
+    if (sw_u) { CK(cudaMalloc(&h->wav_u, n3)); CK(cudaMemset(h->wav_u, 0, n3)); }
+    if (sw_stress) { CK(cudaMalloc(&h->wav_s, n6)); CK(cudaMemset(h->wav_s, 0, n6)); }
+    if (sw_strain) { CK(cudaMalloc(&h->wav_e, n6)); CK(cudaMemset(h->wav_e, 0, n6)); }
+    CK(cudaMalloc(&h->wav_acc, (size_t)9 * h->nst * sizeof(float)));
+    CK(cudaMemset(h->wav_acc, 0, (size_t)9 * h->nst * sizeof(float)));
+    return 0;
+}
+
 extern "C" int swpc3d_wav_store(swpc3d_handle *h, int32_t it) {
     if (ready(h)) return 1;
-    if (h->nst <= 0 || h->ntdec_w <= 0 || (it - 1) % h->ntdec_w != 0) return 0;
-    const int itw = (it - 1) / h->ntdec_w + 1;
-    if (itw > h->ntw) return 0;
+    if (h->nst <= 0 || h->ntdec_w <= 0) return 0;
+    const bool sample = (it - 1) % h->ntdec_w == 0 && (it - 1) / h->ntdec_w + 1 <= h->ntw;
+    const bool accum = (h->sw_u || h->sw_strain) && h->wav_acc;
+    if (!sample && !accum) return 0;
+    WavParams w{};
+    w.nst = h->nst; w.ntw = h->ntw; w.itw = (it - 1) / h->ntdec_w + 1; w.sample = sample ? 1 : 0;
+    w.sw_v = h->sw_v && h->wav; w.sw_u = h->sw_u && h->wav_u; w.sw_stress = h->sw_stress && h->wav_s; w.sw_strain = h->sw_strain && h->wav_e;
+    w.ijk = h->st_ijk; w.wav_v = h->wav; w.wav_u = h->wav_u; w.wav_s = h->wav_s; w.wav_e = h->wav_e; w.acc = h->wav_acc;
+    w.M0 = h->M0; w.UC = h->UC;
+    const double d[3] = {h->g.dx, h->g.dy, h->g.dz};
+    for (int a = 0; a < 3; a++) {
+        if (h->fb == 8) { w.r40[a] = 9.0 / 8.0 / d[a]; w.r41[a] = 1.0 / 24.0 / d[a]; }
+        else { w.r40[a] = (double)(9.0f / 8.0f / (float)d[a]); w.r41[a] = (double)(1.0f / 24.0f / (float)d[a]); }
+    }
     const int nb = (h->nst + 127) / 128;
-    if (h->fb == 8) wav_store_kernel<double><<<nb, 128, 0, h->st>>>(make_params<double>(h), h->nst, h->st_ijk, h->wav, h->ntw, itw, h->M0, h->UC);
-    else wav_store_kernel<float><<<nb, 128, 0, h->st>>>(make_params<float>(h), h->nst, h->st_ijk, h->wav, h->ntw, itw, h->M0, h->UC);
+    if (h->fb == 8) wav_store_kernel<double><<<nb, 128, 0, h->st>>>(make_params<double>(h), w);
+    else wav_store_kernel<float><<<nb, 128, 0, h->st>>>(make_params<float>(h), w);
     h->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swpc3d_get_wav_product(swpc3d_handle *h, int32_t which, float *out) {
+    if (!h || !out) return fail("null argument");
+    const float *src = which == 0 ? h->wav : which == 1 ? h->wav_u : which == 2 ? h->wav_s : which == 3 ? h->wav_e : nullptr;
+    if (!src) return fail("swpc3d_get_wav_product: product not enabled (swpc3d_set_wav_products)");
+    CK(cudaSetDevice(h->dev));
+    CK(cudaMemcpyAsync(out, src, (size_t)h->ntw * (which < 2 ? 3 : 6) * h->nst * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
     return 0;
 }
 

@@ -364,7 +364,7 @@ struct swpc3d_host {
     float fq_min = 0.05f, fq_max = 5.0f, fq_ref = 1.0f, vcut = 0.0f;
     bool pw_mode = false, green_mode = false, bf_mode = false, earth_flattening = false;
     int ntdec_w = 10, ntdec_r = 10, ntw = 0;
-    bool sw_wav_v = false;
+    bool sw_wav_v = false, sw_wav_u = false, sw_wav_stress = false, sw_wav_strain = false;
     float vmin = 0, vmax = 0, vmin_local = 0, vmax_local = 0, fmax = 0, fcut = 0, M0 = 0, UC = 1e-15f, zeta = 0, d2 = 0;
     float ts[8] = {}, c1[8] = {}, c2[8] = {}, d1[8] = {};
     float evlo = 0, evla = 0, evdp = 0, m0ij[6] = {}, f0[3] = {}, otim = 0, sx0 = 0, sy0 = 0;
@@ -387,6 +387,7 @@ struct swpc3d_host {
     // device
     swpc3d_handle *dev = nullptr;
     std::vector<float> wav;
+    std::vector<float> wav_all[4];
     double loop_seconds = 0;
 
     size_t i3(int k, int i, int j) const { return (size_t)(k - kbeg_m) + (size_t)nzm * ((size_t)(i - ibeg_m) + (size_t)nxm * (size_t)(j - jbeg_m)); }
@@ -785,7 +786,10 @@ int swpc3d_host::setup_absorb() {
 int swpc3d_host::setup_wav(const IniFile &ini) {   // m_wav.f90:54-271
     ntdec_w = ini.get_i("ntdec_w", 10);
     sw_wav_v = ini.get_l("sw_wav_v", false);
-    const bool other = ini.get_l("sw_wav_u", false) || ini.get_l("sw_wav_stress", false) || ini.get_l("sw_wav_strain", false);
+    sw_wav_u = ini.get_l("sw_wav_u", false);
+    sw_wav_stress = ini.get_l("sw_wav_stress", false);
+    sw_wav_strain = ini.get_l("sw_wav_strain", false);
+    const bool other = sw_wav_u || sw_wav_stress || sw_wav_strain;
     wav_format = ini.get("wav_format", "sac");
     st_format = ini.get("st_format", "xy");
     fn_stloc = ini.get("fn_stloc", "");
@@ -943,6 +947,9 @@ int swpc3d_host_get_array(swpc3d_host *h, const char *name, void *out, int64_t c
     GA(rho) GA(lam) GA(mu) GA(taup) GA(taus) GA(kfs) GA(kob) GA(kfs_top) GA(kfs_bot) GA(kob_top) GA(kob_bot) GA(kbeg_a)
     GA(gxc) GA(gxe) GA(gyc) GA(gye) GA(gzc) GA(gze) GA(src_ijk) GA(st_ijk) GA(mo) GA(mij) GA(srcprm) GA(xc) GA(yc) GA(zc)
     GA(stlo) GA(stla) GA(wav)
+    if (s == "wav_u") return put(h->wav_all[1], out, cap, n);
+    if (s == "wav_stress") return put(h->wav_all[2], out, cap, n);
+    if (s == "wav_strain") return put(h->wav_all[3], out, cap, n);
 #undef GA
     if (s == "gx_c") return put(h->cgx_c, out, cap, n);
     if (s == "gx_b") return put(h->cgx_b, out, cap, n);
@@ -993,10 +1000,11 @@ int swpc3d_host_attach_device(swpc3d_host *h, int32_t device) {
                               m[4].data(), m[5].data(), h->srcprm.data(), h->stftype.c_str(), h->bf_mode ? 1 : 0, h->tbeg));
     }
     const int nst = (int)(h->st_ijk.size() / 3);
-    if (nst > 0 && h->sw_wav_v) {
+    if (nst > 0 && (h->sw_wav_v || h->sw_wav_u || h->sw_wav_stress || h->sw_wav_strain)) {
         std::vector<int> a(nst), b(nst), c(nst);
         for (int i = 0; i < nst; i++) { a[i] = h->st_ijk[3 * i]; b[i] = h->st_ijk[3 * i + 1]; c[i] = h->st_ijk[3 * i + 2]; }
         DV(swpc3d_set_stations(h->dev, nst, a.data(), b.data(), c.data(), h->ntdec_w, h->ntw, h->M0, h->UC));
+        DV(swpc3d_set_wav_products(h->dev, h->sw_wav_v, h->sw_wav_u, h->sw_wav_stress, h->sw_wav_strain));
     }
 #undef DV
     return 0;
@@ -1065,56 +1073,73 @@ int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles) {
     if (!h) return hfail("null handle");
     if (nfiles) *nfiles = 0;
     const int nst = (int)(h->st_ijk.size() / 3);
-    if (!h->sw_wav_v || nst == 0 || h->ntw <= 0) return 0;
+    const bool sw[4] = {h->sw_wav_v, h->sw_wav_u, h->sw_wav_stress, h->sw_wav_strain};
+    if (!(sw[0] || sw[1] || sw[2] || sw[3]) || nst == 0 || h->ntw <= 0) return 0;
     if (!h->dev) return hfail("swpc3d_host_write_sac: no device attached");
-    h->wav.assign((size_t)h->ntw * 3 * nst, 0.0f);
-    if (swpc3d_get_wav(h->dev, h->wav.data())) return hfail(std::string("device: ") + swpc3d_last_error());   // `update self(wav_vel)` m_wav.f90:672
+    if (h->wav_format != "sac") return hfail("wav_format '" + h->wav_format + "' is outside the hot-path scope of this build (sac)");
     const std::string dir = std::string(odir ? odir : h->odir.c_str()) + "/wav";
     mkdirs(dir);
-    const char *cmpnm[3] = {"Vx", "Vy", "Vz"};
+    static const char *cmpnm[4][6] = {{"Vx", "Vy", "Vz", "", "", ""}, {"Ux", "Uy", "Uz", "", "", ""},
+                                      {"Sxx", "Syy", "Szz", "Syz", "Sxz", "Sxy"}, {"Exx", "Eyy", "Ezz", "Eyz", "Exz", "Exy"}};
     const time_t tt = (time_t)h->exedate + (time_t)h->tz_minutes * 60;   // daytim__localtime m_daytim.f90:262-264
     struct tm g;
     gmtime_r(&tt, &g);
     int count = 0;
+    std::vector<float> buf;
+    // `update self(wav_*)` m_wav.f90:672-675, one product at a time
+    for (int prod = 0; prod < 4; prod++) {
+        if (!sw[prod]) continue;
+        const int ncmp = prod < 2 ? 3 : 6;
+        buf.assign((size_t)h->ntw * ncmp * nst, 0.0f);
+        if (swpc3d_get_wav_product(h->dev, prod, buf.data())) return hfail(std::string("device: ") + swpc3d_last_error());
+        if (prod == 0) h->wav = buf;
+        h->wav_all[prod] = buf;
+    }
     for (int s = 0; s < nst; s++)
-        for (int c = 0; c < 3; c++) {
-            float f[70];
-            int32_t iv[35], lv[5];
-            char a[192];
-            std::fill(f, f + 70, -12345.0f);
-            std::fill(iv, iv + 35, -12345);
-            std::fill(lv, lv + 5, 0);
-            for (int q = 0; q < 24; q++) put_chars(a + 8 * q, "-12345", 8);
-            put_chars(a + 8, "-12345", 16);
-            const double delta = (double)(h->ntdec_w * h->dt);
-            f[0] = (float)((int)(delta * 1e7)) / 1e7f;
-            f[5] = h->tbeg; f[7] = h->otim;
-            f[31] = h->stla[s]; f[32] = h->stlo[s]; f[34] = h->zst[s] * 1000;
-            f[35] = h->evla; f[36] = h->evlo; f[38] = h->evdp; f[39] = moment_magnitude(h->M0);
-            if (h->bf_mode) { f[40] = h->f0[0]; f[41] = h->f0[1]; f[42] = h->f0[2]; }
-            else for (int q = 0; q < 6; q++) f[40 + q] = h->m0ij[q];
-            f[46] = h->clon; f[47] = h->clat; f[48] = h->phi;
-            const float ddx = h->sx0 - h->xst[s], ddy = h->sy0 - h->yst[s];
-            f[50] = std::sqrt(ddx * ddx + ddy * ddy);
-            f[51] = rad2deg_s(std::atan2(h->yst[s] - h->sy0, h->xst[s] - h->sx0));
-            f[52] = rad2deg_s(std::atan2(h->sy0 - h->yst[s], h->sx0 - h->xst[s]));
-            f[57] = c == 0 ? 0.0f + h->phi : (c == 1 ? 90.0f + h->phi : 0.0f);
-            f[58] = 90.0f;
-            iv[0] = g.tm_year + 1900; iv[1] = g.tm_yday + 1; iv[2] = g.tm_hour; iv[3] = g.tm_min; iv[4] = g.tm_sec; iv[5] = 0;
-            iv[6] = 6; iv[9] = h->ntw; iv[15] = 1; iv[16] = 7;
-            lv[0] = 1; lv[2] = 1;
-            put_chars(a, h->stnm[s], 8);
-            std::string t = h->title;
-            t.erase(0, t.find_first_not_of(' ') == std::string::npos ? t.size() : t.find_first_not_of(' '));
-            put_chars(a + 8, t.substr(0, 16), 16);
-            put_chars(a + 160, cmpnm[c], 8);
-            const std::string fn = dir + "/" + h->title + ".3d." + h->stnm[s] + "." + cmpnm[c] + ".sac";
-            FILE *fp = std::fopen(fn.c_str(), "wb");
-            if (!fp) return hfail("cannot write " + fn);
-            std::fwrite(f, 4, 70, fp); std::fwrite(iv, 4, 35, fp); std::fwrite(lv, 4, 5, fp); std::fwrite(a, 1, 192, fp);
-            std::fwrite(h->wav.data() + (size_t)h->ntw * 3 * s + (size_t)h->ntw * c, 4, (size_t)h->ntw, fp);
-            std::fclose(fp);
-            count++;
+        for (int prod = 0; prod < 4; prod++) {   // order of m_wav.f90:679-705: per station v, u, stress, strain
+            if (!sw[prod]) continue;
+            const int ncmp = prod < 2 ? 3 : 6;
+            for (int c = 0; c < ncmp; c++) {
+                float f[70];
+                int32_t iv[35], lv[5];
+                char a[192];
+                std::fill(f, f + 70, -12345.0f);
+                std::fill(iv, iv + 35, -12345);
+                std::fill(lv, lv + 5, 0);
+                for (int q = 0; q < 24; q++) put_chars(a + 8 * q, "-12345", 8);
+                put_chars(a + 8, "-12345", 16);
+                const double delta = (double)(h->ntdec_w * h->dt);
+                f[0] = (float)((int)(delta * 1e7)) / 1e7f;
+                f[5] = h->tbeg; f[7] = h->otim;
+                f[31] = h->stla[s]; f[32] = h->stlo[s]; f[34] = h->zst[s] * 1000;
+                f[35] = h->evla; f[36] = h->evlo; f[38] = h->evdp; f[39] = moment_magnitude(h->M0);
+                if (h->bf_mode) { f[40] = h->f0[0]; f[41] = h->f0[1]; f[42] = h->f0[2]; }
+                else for (int q = 0; q < 6; q++) f[40 + q] = h->m0ij[q];
+                f[46] = h->clon; f[47] = h->clat; f[48] = h->phi;
+                const float ddx = h->sx0 - h->xst[s], ddy = h->sy0 - h->yst[s];
+                f[50] = std::sqrt(ddx * ddx + ddy * ddy);
+                f[51] = rad2deg_s(std::atan2(h->yst[s] - h->sy0, h->xst[s] - h->sx0));
+                f[52] = rad2deg_s(std::atan2(h->sy0 - h->yst[s], h->sx0 - h->xst[s]));
+                if (prod < 2) {   // cmpaz / cmpinc only for the vector products (m_wav.f90:286-288, :297-299)
+                    f[57] = c == 0 ? 0.0f + h->phi : (c == 1 ? 90.0f + h->phi : 0.0f);
+                    f[58] = 90.0f;
+                }
+                iv[0] = g.tm_year + 1900; iv[1] = g.tm_yday + 1; iv[2] = g.tm_hour; iv[3] = g.tm_min; iv[4] = g.tm_sec; iv[5] = 0;
+                iv[6] = 6; iv[9] = h->ntw; iv[15] = 1; iv[16] = prod == 0 ? 7 : (prod == 1 ? 6 : 5);
+                lv[0] = 1; lv[2] = 1;
+                put_chars(a, h->stnm[s], 8);
+                std::string t = h->title;
+                t.erase(0, t.find_first_not_of(' ') == std::string::npos ? t.size() : t.find_first_not_of(' '));
+                put_chars(a + 8, t.substr(0, 16), 16);
+                put_chars(a + 160, cmpnm[prod][c], 8);
+                const std::string fn = dir + "/" + h->title + ".3d." + h->stnm[s] + "." + cmpnm[prod][c] + ".sac";
+                FILE *fp = std::fopen(fn.c_str(), "wb");
+                if (!fp) return hfail("cannot write " + fn);
+                std::fwrite(f, 4, 70, fp); std::fwrite(iv, 4, 35, fp); std::fwrite(lv, 4, 5, fp); std::fwrite(a, 1, 192, fp);
+                std::fwrite(h->wav_all[prod].data() + (size_t)h->ntw * ncmp * s + (size_t)h->ntw * c, 4, (size_t)h->ntw, fp);
+                std::fclose(fp);
+                count++;
+            }
         }
     if (nfiles) *nfiles = count;
     return 0;

@@ -568,17 +568,97 @@ __global__ void bodyforce_kernel(const __grid_constant__ KParams<F> p, const Src
     atomicAdd(p.Vz + n - 1, (F)((2.0f / (rho[n] + rho[n - 1])) * fz * stime * dtd / 2));
 }
 
-// wav__store (velocity) m_wav.f90:527-532
+// wav__store m_wav.f90:397-625: per station, every step: displacement / strain accumulation (:430-513); when
+// `sample`: velocity, displacement, stress, strain traces (:515-617).  Products are switched by bit flags.
+struct WavParams {
+    int nst, ntw, itw, sample;
+    int sw_v, sw_u, sw_stress, sw_strain;
+    const int *ijk;
+    float *wav_v, *wav_u, *wav_s, *wav_e;   // (ntw,3,nst) (ntw,3,nst) (ntw,6,nst) (ntw,6,nst)
+    float *acc;                             // 9 running sums per station: ux uy uz exx eyy ezz eyz exz exy
+    float M0, UC;
+    double r40[3], r41[3];                  // 9/8/d, 1/24/d in the field kind (m_wav.f90:127-132)
+};
+
 template <typename F>
-__global__ void wav_store_kernel(const __grid_constant__ KParams<F> p, int nst, const int *ijk, float *wav, int ntw, int itw, float M0, float UC) {
+__global__ void wav_store_kernel(const __grid_constant__ KParams<F> p, const WavParams w) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nst) return;
+    if (s >= w.nst) return;
     const long long si = p.SI, sj = p.SJ;
-    const long long n = (long long)(ijk[3 * s + 2] + KOFF - 1) + (long long)p.NZP * ((long long)ijk[3 * s] + (long long)p.NXM * ijk[3 * s + 1]);
-    float *w = wav + (long long)ntw * 3 * s + (itw - 1);
-    w[0] = (float)(p.Vx[n] + p.Vx[n - si]) / 2.0f * M0 * UC * 1e9f;
-    w[ntw] = (float)(p.Vy[n] + p.Vy[n - sj]) / 2.0f * M0 * UC * 1e9f;
-    w[2 * ntw] = -(float)(p.Vz[n] + p.Vz[n - 1]) / 2.0f * M0 * UC * 1e9f;
+    const long long n = (long long)(w.ijk[3 * s + 2] + KOFF - 1) + (long long)p.NZP * ((long long)w.ijk[3 * s] + (long long)p.NXM * w.ijk[3 * s + 1]);
+    const F *Vx = p.Vx, *Vy = p.Vy, *Vz = p.Vz;
+    const float dt = p.dt;
+    float *a = w.acc + 9 * s;
+    if (w.sw_u) {
+        a[0] = a[0] + (float)(Vx[n] + Vx[n - si]) * 0.5f * dt;
+        a[1] = a[1] + (float)(Vy[n] + Vy[n - sj]) * 0.5f * dt;
+        a[2] = a[2] - (float)(Vz[n] + Vz[n - 1]) * 0.5f * dt;
+    }
+    if (w.sw_strain) {
+        const F r40x = (F)w.r40[0], r40y = (F)w.r40[1], r40z = (F)w.r40[2], r41x = (F)w.r41[0], r41y = (F)w.r41[1], r41z = (F)w.r41[2];
+        const F dxVx = (Vx[n] - Vx[n - si]) * r40x - (Vx[n + si] - Vx[n - 2 * si]) * r41x;
+        const F dyVy = (Vy[n] - Vy[n - sj]) * r40y - (Vy[n + sj] - Vy[n - 2 * sj]) * r41y;
+        const F dzVz = (Vz[n] - Vz[n - 1]) * r40z - (Vz[n + 1] - Vz[n - 2]) * r41z;
+        const F dxVy = ((Vy[n + si] - Vy[n]) * r40x - (Vy[n + 2 * si] - Vy[n - si]) * r41x +
+                        (Vy[n + si - sj] - Vy[n - sj]) * r40x - (Vy[n + 2 * si - sj] - Vy[n - si - sj]) * r41x +
+                        (Vy[n] - Vy[n - si]) * r40x - (Vy[n + si] - Vy[n - 2 * si]) * r41x +
+                        (Vy[n - sj] - Vy[n - si - sj]) * r40x - (Vy[n + si - sj] - Vy[n - 2 * si - sj]) * r41x) / 4.0f;
+        const F dxVz = ((Vz[n + si] - Vz[n]) * r40x - (Vz[n + 2 * si] - Vz[n - si]) * r41x +
+                        (Vz[n - 1 + si] - Vz[n - 1]) * r40x - (Vz[n - 1 + 2 * si] - Vz[n - 1 - si]) * r41x +
+                        (Vz[n] - Vz[n - si]) * r40x - (Vz[n + si] - Vz[n - 2 * si]) * r41x +
+                        (Vz[n - 1] - Vz[n - 1 - si]) * r40x - (Vz[n - 1 + si] - Vz[n - 1 - 2 * si]) * r41x) / 4.0f;
+        const F dyVx = ((Vx[n + sj] - Vx[n]) * r40y - (Vx[n + 2 * sj] - Vx[n - sj]) * r41y +
+                        (Vx[n - si + sj] - Vx[n - si]) * r40y - (Vx[n - si + 2 * sj] - Vx[n - si - sj]) * r41y +
+                        (Vx[n] - Vx[n - sj]) * r40y - (Vx[n + sj] - Vx[n - 2 * sj]) * r41y +
+                        (Vx[n - si] - Vx[n - si - sj]) * r40y - (Vx[n - si + sj] - Vx[n - si - 2 * sj]) * r41y) / 4.0f;
+        const F dyVz = ((Vz[n + sj] - Vz[n]) * r40y - (Vz[n + 2 * sj] - Vz[n - sj]) * r41y +
+                        (Vz[n - 1 + sj] - Vz[n - 1]) * r40y - (Vz[n - 1 + 2 * sj] - Vz[n - 1 - sj]) * r41y +
+                        (Vz[n] - Vz[n - sj]) * r40y - (Vz[n + sj] - Vz[n - 2 * sj]) * r41y +
+                        (Vz[n - 1] - Vz[n - 1 - sj]) * r40y - (Vz[n - 1 + sj] - Vz[n - 1 - 2 * sj]) * r41y) / 4.0f;
+        const F dzVx = ((Vx[n + 1] - Vx[n]) * r40z - (Vx[n + 2] - Vx[n - 1]) * r41z +
+                        (Vx[n + 1 - si] - Vx[n - si]) * r40z - (Vx[n + 2 - si] - Vx[n - 1 - si]) * r41z +
+                        (Vx[n] - Vx[n - 1]) * r40z - (Vx[n + 1] - Vx[n - 2]) * r41z +
+                        (Vx[n - si] - Vx[n - 1 - si]) * r40z - (Vx[n + 1 - si] - Vx[n - 2 - si]) * r41z) / 4.0f;
+        const F dzVy = ((Vy[n + 1] - Vy[n]) * r40z - (Vy[n + 2] - Vy[n - 1]) * r41z +
+                        (Vy[n + 1 - sj] - Vy[n - sj]) * r40z - (Vy[n + 2 - sj] - Vy[n - 1 - sj]) * r41z +
+                        (Vy[n] - Vy[n - 1]) * r40z - (Vy[n + 1] - Vy[n - 2]) * r41z +
+                        (Vy[n - sj] - Vy[n - 1 - sj]) * r40z - (Vy[n + 1 - sj] - Vy[n - 2 - sj]) * r41z) / 4.0f;
+        a[3] = a[3] + (float)(dxVx) * dt;
+        a[4] = a[4] + (float)(dyVy) * dt;
+        a[5] = a[5] + (float)(dzVz) * dt;
+        a[6] = a[6] + (float)(dyVz + dzVy) / 2.0f * dt;
+        a[7] = a[7] + (float)(dxVz + dzVx) / 2.0f * dt;
+        a[8] = a[8] + (float)(dxVy + dyVx) / 2.0f * dt;
+    }
+    if (!w.sample) return;
+    const long long ntw = w.ntw;
+    const float M0 = w.M0, UC = w.UC;
+    if (w.sw_v) {
+        float *o = w.wav_v + ntw * 3 * s + (w.itw - 1);
+        o[0] = (float)(Vx[n] + Vx[n - si]) / 2.0f * M0 * UC * 1e9f;
+        o[ntw] = (float)(Vy[n] + Vy[n - sj]) / 2.0f * M0 * UC * 1e9f;
+        o[2 * ntw] = -(float)(Vz[n] + Vz[n - 1]) / 2.0f * M0 * UC * 1e9f;
+    }
+    if (w.sw_u) {
+        float *o = w.wav_u + ntw * 3 * s + (w.itw - 1);
+        o[0] = a[0] * M0 * UC * 1e9f;
+        o[ntw] = a[1] * M0 * UC * 1e9f;
+        o[2 * ntw] = a[2] * M0 * UC * 1e9f;
+    }
+    if (w.sw_stress) {
+        float *o = w.wav_s + ntw * 6 * s + (w.itw - 1);
+        o[0] = (float)(p.Sxx[n]) * M0 * UC * 1e6f;
+        o[ntw] = (float)(p.Syy[n]) * M0 * UC * 1e6f;
+        o[2 * ntw] = (float)(p.Szz[n]) * M0 * UC * 1e6f;
+        o[3 * ntw] = (float)(p.Syz[n] + p.Syz[n - sj] + p.Syz[n - 1] + p.Syz[n - 1 - sj]) / 4.0f * M0 * UC * 1e6f;
+        o[4 * ntw] = (float)(p.Sxz[n] + p.Sxz[n - si] + p.Sxz[n - 1] + p.Sxz[n - 1 - si]) / 4.0f * M0 * UC * 1e6f;
+        o[5 * ntw] = (float)(p.Sxy[n] + p.Sxy[n - sj] + p.Sxy[n - si] + p.Sxy[n - si - sj]) / 4.0f * M0 * UC * 1e6f;
+    }
+    if (w.sw_strain) {
+        float *o = w.wav_e + ntw * 6 * s + (w.itw - 1);
+#pragma unroll
+        for (int c = 0; c < 6; c++) o[c * ntw] = a[3 + c] * M0 * UC * 1e-3f;
+    }
 }
 
 // kernel__vmax m_kernel.f90:360-372: max |V| at k = kob(i,j)+1 over the given local (i,j) window

@@ -249,3 +249,21 @@ def comm_local(ranks: list[DeviceRank], which: str):
     """Single-process emulation of global__comm_stress / global__comm_vel for ranks sharing this process."""
     arr = (C.c_void_p * len(ranks))(*[r.h for r in ranks])
     check(_lib.load().swpc3d_comm_local(arr, len(ranks), 0 if which == "stress" else 1))
+
+
+def _set_wav_products(self, sw_v=True, sw_u=False, sw_stress=False, sw_strain=False):
+    """which products wav__store keeps (m_wav.f90:67-70); call after set_stations"""
+    check(self.lib.swpc3d_set_wav_products(self.h, int(sw_v), int(sw_u), int(sw_stress), int(sw_strain)))
+
+
+def _get_wav_product(self, which: int) -> np.ndarray:
+    """which: 0 velocity, 1 displacement (nst,3,ntw); 2 stress, 3 strain (nst,6,ntw)"""
+    nc = 3 if which < 2 else 6
+    out = np.zeros((max(self.nst, 1), nc, max(self.ntw, 1)), dtype=np.float32)
+    if self.nst and self.ntw:
+        check(self.lib.swpc3d_get_wav_product(self.h, which, _fp(out)))
+    return out[: self.nst]
+
+
+DeviceRank.set_wav_products = _set_wav_products
+DeviceRank.get_wav_product = _get_wav_product

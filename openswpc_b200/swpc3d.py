@@ -24,7 +24,7 @@ _DOUBLES = {"dx", "dy", "dz", "dt", "xbeg", "ybeg", "zbeg", "tbeg", "vmin", "vma
             "UC", "zeta", "d2", "c", "r", "loop_seconds", "evlo", "evla", "evdp", "clon", "clat", "phi"}
 _STRS = {"title", "odir", "abc_type", "stftype", "vmodel_type", "stf_format", "wav_format"}
 _F32 = {"rho", "lam", "mu", "taup", "taus", "gxc", "gxe", "gyc", "gye", "gzc", "gze", "gx_c", "gx_b", "gy_c", "gy_b", "gz_c", "gz_b",
-        "ts", "c1", "c2", "d1", "srcprm", "xc", "yc", "zc", "stlo", "stla", "wav"}
+        "ts", "c1", "c2", "d1", "srcprm", "xc", "yc", "zc", "stlo", "stla", "wav", "wav_u", "wav_stress", "wav_strain"}
 _I32 = {"kfs", "kob", "kfs_top", "kfs_bot", "kob_top", "kob_bot", "kbeg_a", "src_ijk", "st_ijk"}
 _F64 = {"mo", "mij"}
 
@@ -128,8 +128,10 @@ class Swpc3d:
             return out.reshape(-1, 6)
         if name == "srcprm":
             return out.reshape(-1, 2)
-        if name == "wav":
+        if name in ("wav", "wav_u"):
             return out.reshape(-1, 3, max(self["ntw"], 1))
+        if name in ("wav_stress", "wav_strain"):
+            return out.reshape(-1, 6, max(self["ntw"], 1))
         return out
 
     def station_names(self) -> list[str]:

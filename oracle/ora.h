@@ -168,6 +168,10 @@ typedef struct {
     float *xst, *yst, *zst, *stlo, *stla;
     char (*stnm)[9];
     float *wav_vel;               /* (ntw,3,nst) */
+    float *wav_disp;              /* (ntw,3,nst) */
+    float *wav_stress, *wav_strain; /* (ntw,6,nst) */
+    float *ux, *uy, *uz;          /* running displacement at stations, m_wav.f90:41 */
+    float *exx, *eyy, *ezz, *eyz, *exz, *exy;   /* running strain, m_wav.f90:42 */
     /* halo buffers m_global.f90:251-258 */
     ora_mp *sbuf_ip, *sbuf_im, *sbuf_jp, *sbuf_jm, *rbuf_ip, *rbuf_im, *rbuf_jp, *rbuf_jm;
 } ora_rank;
@@ -230,6 +234,8 @@ int ora_get_sources(const ora_sim *s, int rank, int *ijk /*3*nsrc*/, double *mo 
 int ora_get_source_details(const ora_sim *s, int rank, double *mij /*6*nsrc*/, float *srcprm /*2*nsrc*/);
 int ora_get_stations(const ora_sim *s, int rank, int *ijk /*3*nst*/, char *names /*9*nst*/);
 int ora_get_wav(const ora_sim *s, int rank, float *out /*(ntw,3,nst)*/);
+/* which: 0 velocity (ntw,3,nst), 1 displacement (ntw,3,nst), 2 stress (ntw,6,nst), 3 strain (ntw,6,nst) */
+int ora_get_wav_product(const ora_sim *s, int rank, int which, float *out);
 /* PML profile g?c/g?e: name gxc gxe gyc gye gzc gze -> (4,n) floats */
 int ora_get_profile(const ora_sim *s, int rank, const char *name, float *out);
 /* SAC output of all stations of all ranks (m_wav.f90:658-792); returns number of files */

@@ -242,6 +242,14 @@ int ora_get_wav(const ora_sim *s, int rank, float *out) {
     return r->nst;
 }
 
+int ora_get_wav_product(const ora_sim *s, int rank, int which, float *out) {
+    const ora_rank *r = &s->r[rank];
+    const float *src = which == 0 ? r->wav_vel : which == 1 ? r->wav_disp : which == 2 ? r->wav_stress : r->wav_strain;
+    if (!src) return 0;
+    memcpy(out, src, sizeof(float) * (size_t)s->cfg.ntw * (which < 2 ? 3 : 6) * r->nst);
+    return r->nst;
+}
+
 int ora_get_profile(const ora_sim *s, int rank, const char *name, float *out) {
     const ora_rank *r = &s->r[rank];
     const float *p = NULL;
@@ -277,7 +285,14 @@ static void put8(char *dst, const char *src, int n) {
     for (int q = 0; q < n; q++) dst[q] = (q < l) ? src[q] : ' ';
 }
 
-static void sac_header(const ora_cfg *c, const ora_rank *r, int n, int cmp, sac_raw *h) {
+static const char *ora_cmpnm(int prod, int cmp) {
+    static const char *nm[4][6] = {{"Vx", "Vy", "Vz", "", "", ""}, {"Ux", "Uy", "Uz", "", "", ""},
+                                   {"Sxx", "Syy", "Szz", "Syz", "Sxz", "Sxy"}, {"Exx", "Eyy", "Ezz", "Eyz", "Exz", "Exy"}};
+    return nm[prod][cmp];
+}
+
+/* prod: 0 velocity, 1 displacement, 2 stress, 3 strain (m_wav.f90:280-334) */
+static void sac_header(const ora_cfg *c, const ora_rank *r, int n, int prod, int cmp, sac_raw *h) {
     /* sac__whdr initial fill, m_sac.f90:330-337 */
     for (int q = 0; q < 70; q++) h->f[q] = -12345.0f;
     for (int q = 0; q < 35; q++) h->i[q] = -12345;
@@ -309,8 +324,10 @@ static void sac_header(const ora_cfg *c, const ora_rank *r, int n, int cmp, sac_
     h->f[50] = sqrtf(ddx * ddx + ddy * ddy);
     h->f[51] = ora_rad2deg_s(atan2f(r->yst[n] - c->sy0, r->xst[n] - c->sx0));
     h->f[52] = ora_rad2deg_s(atan2f(c->sy0 - r->yst[n], c->sx0 - r->xst[n]));
-    h->f[58] = 90.0f; /* cmpinc */
-    h->f[57] = (cmp == 0) ? 0.0f + c->phi : (cmp == 1) ? 90.0f + c->phi : 0.0f; /* cmpaz m_wav.f90:286-288 */
+    if (prod < 2) {
+        h->f[58] = 90.0f; /* cmpinc */
+        h->f[57] = (cmp == 0) ? 0.0f + c->phi : (cmp == 1) ? 90.0f + c->phi : 0.0f; /* cmpaz m_wav.f90:286-288, :297-299 */
+    }
 
     /* daytim__localtime(exedate) m_daytim.f90:246-314 : local time = utc + values(4) minutes */
     time_t tt = (time_t)c->exedate + (time_t)c->tz_minutes * 60;
@@ -325,7 +342,7 @@ static void sac_header(const ora_cfg *c, const ora_rank *r, int n, int cmp, sac_
     h->i[6] = 6;          /* nvhdr */
     h->i[9] = c->ntw;     /* npts */
     h->i[15] = 1;         /* iftype */
-    h->i[16] = 7;         /* idep: velocity, m_wav.f90:290 */
+    h->i[16] = prod == 0 ? 7 : prod == 1 ? 6 : 5; /* idep m_wav.f90:290, :301, :316, :331 */
     /* ievtyp, iuser0-7 stay -12345 */
     h->l[0] = 1;          /* leven */
     h->l[1] = 0;          /* lpspol */
@@ -342,8 +359,7 @@ static void sac_header(const ora_cfg *c, const ora_rank *r, int n, int cmp, sac_
         t16[16] = 0;
         put8(h->a + 8, t16, 16);
     }
-    const char *cn[3] = {"Vx", "Vy", "Vz"};
-    put8(h->a + 8 * 20, cn[cmp], 8); /* kcmpnm is words 151-152 -> 8-byte slot index 20 */
+    put8(h->a + 8 * 20, ora_cmpnm(prod, cmp), 8); /* kcmpnm is words 151-152 -> 8-byte slot index 20 */
 }
 
 static void mkdir_p(const char *path) {
@@ -360,29 +376,33 @@ static void mkdir_p(const char *path) {
 
 int ora_write_sac(const ora_sim *s, const char *odir) {
     const ora_cfg *c = &s->cfg;
-    if (!c->sw_wav_v) return 0;
+    if (!(c->sw_wav_v || c->sw_wav_u || c->sw_wav_stress || c->sw_wav_strain)) return 0;
     char dir[1024];
     snprintf(dir, sizeof(dir), "%s/wav", odir);
     mkdir_p(dir);
-    const char *cn[3] = {"Vx", "Vy", "Vz"};
     int nfiles = 0;
     for (int q = 0; q < s->nranks; q++) {
         const ora_rank *r = &s->r[q];
         for (int n = 0; n < r->nst; n++)
-            for (int cmp = 0; cmp < 3; cmp++) {
-                sac_raw h;
-                sac_header(c, r, n, cmp, &h);
-                char fn[1400];
-                snprintf(fn, sizeof(fn), "%s/%s.3d.%s.%s.sac", dir, c->title, r->stnm[n], cn[cmp]);
-                FILE *fp = fopen(fn, "wb");
-                if (!fp) return -1;
-                fwrite(h.f, 4, 70, fp);
-                fwrite(h.i, 4, 35, fp);
-                fwrite(h.l, 4, 5, fp);
-                fwrite(h.a, 1, 192, fp);
-                fwrite(r->wav_vel + (size_t)c->ntw * 3 * n + (size_t)c->ntw * cmp, 4, (size_t)c->ntw, fp);
-                fclose(fp);
-                nfiles++;
+            for (int prod = 0; prod < 4; prod++) { /* m_wav.f90:679-705 */
+                const float *src = prod == 0 ? r->wav_vel : prod == 1 ? r->wav_disp : prod == 2 ? r->wav_stress : r->wav_strain;
+                const int ncmp = prod < 2 ? 3 : 6;
+                if (!src) continue;
+                for (int cmp = 0; cmp < ncmp; cmp++) {
+                    sac_raw h;
+                    sac_header(c, r, n, prod, cmp, &h);
+                    char fn[1400];
+                    snprintf(fn, sizeof(fn), "%s/%s.3d.%s.%s.sac", dir, c->title, r->stnm[n], ora_cmpnm(prod, cmp));
+                    FILE *fp = fopen(fn, "wb");
+                    if (!fp) return -1;
+                    fwrite(h.f, 4, 70, fp);
+                    fwrite(h.i, 4, 35, fp);
+                    fwrite(h.l, 4, 5, fp);
+                    fwrite(h.a, 1, 192, fp);
+                    fwrite(src + (size_t)c->ntw * ncmp * n + (size_t)c->ntw * cmp, 4, (size_t)c->ntw, fp);
+                    fclose(fp);
+                    nfiles++;
+                }
             }
     }
     return nfiles;

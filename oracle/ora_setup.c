@@ -914,7 +914,21 @@ static int wav_setup(ora_sim *s, const ora_ini *ini, const char *base) {
     fclose(fp);
     for (int q = 0; q < s->nranks; q++) {
         ora_rank *r = &s->r[q];
-        if (c->sw_wav_v && r->nst > 0) r->wav_vel = (float *)xcalloc((size_t)c->ntw * 3 * r->nst, sizeof(float));
+        if (r->nst <= 0) continue;
+        size_t n3 = (size_t)c->ntw * 3 * r->nst, n6 = (size_t)c->ntw * 6 * r->nst;
+        if (c->sw_wav_v) r->wav_vel = (float *)xcalloc(n3, sizeof(float));
+        if (c->sw_wav_u) {
+            r->wav_disp = (float *)xcalloc(n3, sizeof(float));
+            r->ux = (float *)xcalloc((size_t)r->nst, sizeof(float)); r->uy = (float *)xcalloc((size_t)r->nst, sizeof(float));
+            r->uz = (float *)xcalloc((size_t)r->nst, sizeof(float));
+        }
+        if (c->sw_wav_stress) r->wav_stress = (float *)xcalloc(n6, sizeof(float));
+        if (c->sw_wav_strain) {
+            r->wav_strain = (float *)xcalloc(n6, sizeof(float));
+            r->exx = (float *)xcalloc((size_t)r->nst, sizeof(float)); r->eyy = (float *)xcalloc((size_t)r->nst, sizeof(float));
+            r->ezz = (float *)xcalloc((size_t)r->nst, sizeof(float)); r->eyz = (float *)xcalloc((size_t)r->nst, sizeof(float));
+            r->exz = (float *)xcalloc((size_t)r->nst, sizeof(float)); r->exy = (float *)xcalloc((size_t)r->nst, sizeof(float));
+        }
     }
     return 0;
 }
@@ -997,7 +1011,7 @@ void ora_destroy(ora_sim *s) {
                         r->azVz, r->axSxx, r->aySxy, r->azSxz, r->axSxy, r->aySyy, r->azSyz, r->axSxz, r->aySyz, r->azSzz,
                         r->gx_c, r->gx_b, r->gy_c, r->gy_b, r->gz_c, r->gz_b, r->isrc, r->jsrc, r->ksrc, r->sx, r->sy, r->sz,
                         r->srcprm, r->mo, r->mxx, r->myy, r->mzz, r->myz, r->mxz, r->mxy, r->fx, r->fy, r->fz, r->ist, r->jst,
-                        r->kst, r->xst, r->yst, r->zst, r->stlo, r->stla, r->stnm, r->wav_vel, r->sbuf_ip, r->sbuf_im,
+                        r->kst, r->xst, r->yst, r->zst, r->stlo, r->stla, r->stnm, r->wav_vel, r->wav_disp, r->wav_stress, r->wav_strain, r->ux, r->uy, r->uz, r->exx, r->eyy, r->ezz, r->eyz, r->exz, r->exy, r->sbuf_ip, r->sbuf_im,
                         r->sbuf_jp, r->sbuf_jm, r->rbuf_ip, r->rbuf_im, r->rbuf_jp, r->rbuf_jm};
         for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
     }

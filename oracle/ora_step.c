@@ -542,22 +542,95 @@ void ora_comm_stress(ora_sim *s) {
 }
 
 /* ---------------------------------------------------------------------------------------- */
-/* wav__store (velocity traces only)  m_wav.f90:515-539 */
+/* wav__store  m_wav.f90:397-625: displacement / strain are accumulated EVERY step (:430-513), then, when
+ * mod(it-1, ntdec_w) == 0, velocity, displacement, stress and strain are sampled (:515-617). */
 void ora_wav_store(ora_sim *s, int it) {
     const ora_cfg *c = &s->cfg;
-    if (!c->sw_wav_v || c->ntdec_w <= 0) return;
-    if ((it - 1) % c->ntdec_w != 0) return;
-    int itw = (it - 1) / c->ntdec_w + 1;
-    if (itw > c->ntw) return;
+    if (!(c->sw_wav_v || c->sw_wav_u || c->sw_wav_stress || c->sw_wav_strain) || c->ntdec_w <= 0) return;
+    const float dt = c->dt;
+    /* m_wav.f90:127-132 */
+    const ora_mp r40x = (ora_mp)9.0 / (ora_mp)8.0 / (ora_mp)c->dx, r40y = (ora_mp)9.0 / (ora_mp)8.0 / (ora_mp)c->dy, r40z = (ora_mp)9.0 / (ora_mp)8.0 / (ora_mp)c->dz;
+    const ora_mp r41x = (ora_mp)1.0 / (ora_mp)24.0 / (ora_mp)c->dx, r41y = (ora_mp)1.0 / (ora_mp)24.0 / (ora_mp)c->dy, r41z = (ora_mp)1.0 / (ora_mp)24.0 / (ora_mp)c->dz;
+    const int sample = ((it - 1) % c->ntdec_w == 0);
+    const int itw = (it - 1) / c->ntdec_w + 1;
     for (int q = 0; q < s->nranks; q++) {
         ora_rank *r = &s->r[q];
         const ptrdiff_t si = r->nzm, sj = (ptrdiff_t)r->nzm * r->nxm;
+        const ora_mp *Vx = r->Vx, *Vy = r->Vy, *Vz = r->Vz;
         for (int n = 0; n < r->nst; n++) {
             ptrdiff_t p = (ptrdiff_t)ora_idx3(r, r->kst[n], r->ist[n], r->jst[n]);
-            float *w = r->wav_vel + (size_t)c->ntw * 3 * n;
-            w[(itw - 1) + 0 * c->ntw] = (float)(r->Vx[p] + r->Vx[p - si]) / 2.0f * c->M0 * c->UC * 1e9f;
-            w[(itw - 1) + 1 * c->ntw] = (float)(r->Vy[p] + r->Vy[p - sj]) / 2.0f * c->M0 * c->UC * 1e9f;
-            w[(itw - 1) + 2 * c->ntw] = -(float)(r->Vz[p] + r->Vz[p - 1]) / 2.0f * c->M0 * c->UC * 1e9f;
+            if (c->sw_wav_u) { /* :439-444 */
+                r->ux[n] = r->ux[n] + (float)(Vx[p] + Vx[p - si]) * 0.5f * dt;
+                r->uy[n] = r->uy[n] + (float)(Vy[p] + Vy[p - sj]) * 0.5f * dt;
+                r->uz[n] = r->uz[n] - (float)(Vz[p] + Vz[p - 1]) * 0.5f * dt;
+            }
+            if (c->sw_wav_strain) { /* :462-506 */
+                ora_mp dxVx = (Vx[p] - Vx[p - si]) * r40x - (Vx[p + si] - Vx[p - 2 * si]) * r41x;
+                ora_mp dyVy = (Vy[p] - Vy[p - sj]) * r40y - (Vy[p + sj] - Vy[p - 2 * sj]) * r41y;
+                ora_mp dzVz = (Vz[p] - Vz[p - 1]) * r40z - (Vz[p + 1] - Vz[p - 2]) * r41z;
+                ora_mp dxVy = ((Vy[p + si] - Vy[p]) * r40x - (Vy[p + 2 * si] - Vy[p - si]) * r41x +
+                               (Vy[p + si - sj] - Vy[p - sj]) * r40x - (Vy[p + 2 * si - sj] - Vy[p - si - sj]) * r41x +
+                               (Vy[p] - Vy[p - si]) * r40x - (Vy[p + si] - Vy[p - 2 * si]) * r41x +
+                               (Vy[p - sj] - Vy[p - si - sj]) * r40x - (Vy[p + si - sj] - Vy[p - 2 * si - sj]) * r41x) / 4.0f;
+                ora_mp dxVz = ((Vz[p + si] - Vz[p]) * r40x - (Vz[p + 2 * si] - Vz[p - si]) * r41x +
+                               (Vz[p - 1 + si] - Vz[p - 1]) * r40x - (Vz[p - 1 + 2 * si] - Vz[p - 1 - si]) * r41x +
+                               (Vz[p] - Vz[p - si]) * r40x - (Vz[p + si] - Vz[p - 2 * si]) * r41x +
+                               (Vz[p - 1] - Vz[p - 1 - si]) * r40x - (Vz[p - 1 + si] - Vz[p - 1 - 2 * si]) * r41x) / 4.0f;
+                ora_mp dyVx = ((Vx[p + sj] - Vx[p]) * r40y - (Vx[p + 2 * sj] - Vx[p - sj]) * r41y +
+                               (Vx[p - si + sj] - Vx[p - si]) * r40y - (Vx[p - si + 2 * sj] - Vx[p - si - sj]) * r41y +
+                               (Vx[p] - Vx[p - sj]) * r40y - (Vx[p + sj] - Vx[p - 2 * sj]) * r41y +
+                               (Vx[p - si] - Vx[p - si - sj]) * r40y - (Vx[p - si + sj] - Vx[p - si - 2 * sj]) * r41y) / 4.0f;
+                ora_mp dyVz = ((Vz[p + sj] - Vz[p]) * r40y - (Vz[p + 2 * sj] - Vz[p - sj]) * r41y +
+                               (Vz[p - 1 + sj] - Vz[p - 1]) * r40y - (Vz[p - 1 + 2 * sj] - Vz[p - 1 - sj]) * r41y +
+                               (Vz[p] - Vz[p - sj]) * r40y - (Vz[p + sj] - Vz[p - 2 * sj]) * r41y +
+                               (Vz[p - 1] - Vz[p - 1 - sj]) * r40y - (Vz[p - 1 + sj] - Vz[p - 1 - 2 * sj]) * r41y) / 4.0f;
+                ora_mp dzVx = ((Vx[p + 1] - Vx[p]) * r40z - (Vx[p + 2] - Vx[p - 1]) * r41z +
+                               (Vx[p + 1 - si] - Vx[p - si]) * r40z - (Vx[p + 2 - si] - Vx[p - 1 - si]) * r41z +
+                               (Vx[p] - Vx[p - 1]) * r40z - (Vx[p + 1] - Vx[p - 2]) * r41z +
+                               (Vx[p - si] - Vx[p - 1 - si]) * r40z - (Vx[p + 1 - si] - Vx[p - 2 - si]) * r41z) / 4.0f;
+                ora_mp dzVy = ((Vy[p + 1] - Vy[p]) * r40z - (Vy[p + 2] - Vy[p - 1]) * r41z +
+                               (Vy[p + 1 - sj] - Vy[p - sj]) * r40z - (Vy[p + 2 - sj] - Vy[p - 1 - sj]) * r41z +
+                               (Vy[p] - Vy[p - 1]) * r40z - (Vy[p + 1] - Vy[p - 2]) * r41z +
+                               (Vy[p - sj] - Vy[p - 1 - sj]) * r40z - (Vy[p + 1 - sj] - Vy[p - 2 - sj]) * r41z) / 4.0f;
+                r->exx[n] = r->exx[n] + (float)(dxVx)*dt;
+                r->eyy[n] = r->eyy[n] + (float)(dyVy)*dt;
+                r->ezz[n] = r->ezz[n] + (float)(dzVz)*dt;
+                r->eyz[n] = r->eyz[n] + (float)(dyVz + dzVy) / 2.0f * dt;
+                r->exz[n] = r->exz[n] + (float)(dxVz + dzVx) / 2.0f * dt;
+                r->exy[n] = r->exy[n] + (float)(dxVy + dyVx) / 2.0f * dt;
+            }
+            if (!sample || itw > c->ntw) continue;
+            const size_t ntw = (size_t)c->ntw;
+            if (c->sw_wav_v) { /* :527-532 */
+                float *w = r->wav_vel + ntw * 3 * n + (itw - 1);
+                w[0 * ntw] = (float)(Vx[p] + Vx[p - si]) / 2.0f * c->M0 * c->UC * 1e9f;
+                w[1 * ntw] = (float)(Vy[p] + Vy[p - sj]) / 2.0f * c->M0 * c->UC * 1e9f;
+                w[2 * ntw] = -(float)(Vz[p] + Vz[p - 1]) / 2.0f * c->M0 * c->UC * 1e9f;
+            }
+            if (c->sw_wav_u) { /* :550-554 */
+                float *w = r->wav_disp + ntw * 3 * n + (itw - 1);
+                w[0 * ntw] = r->ux[n] * c->M0 * c->UC * 1e9f;
+                w[1 * ntw] = r->uy[n] * c->M0 * c->UC * 1e9f;
+                w[2 * ntw] = r->uz[n] * c->M0 * c->UC * 1e9f;
+            }
+            if (c->sw_wav_stress) { /* :572-583 */
+                float *w = r->wav_stress + ntw * 6 * n + (itw - 1);
+                w[0 * ntw] = (float)(r->Sxx[p]) * c->M0 * c->UC * 1e6f;
+                w[1 * ntw] = (float)(r->Syy[p]) * c->M0 * c->UC * 1e6f;
+                w[2 * ntw] = (float)(r->Szz[p]) * c->M0 * c->UC * 1e6f;
+                w[3 * ntw] = (float)(r->Syz[p] + r->Syz[p - sj] + r->Syz[p - 1] + r->Syz[p - 1 - sj]) / 4.0f * c->M0 * c->UC * 1e6f;
+                w[4 * ntw] = (float)(r->Sxz[p] + r->Sxz[p - si] + r->Sxz[p - 1] + r->Sxz[p - 1 - si]) / 4.0f * c->M0 * c->UC * 1e6f;
+                w[5 * ntw] = (float)(r->Sxy[p] + r->Sxy[p - sj] + r->Sxy[p - si] + r->Sxy[p - si - sj]) / 4.0f * c->M0 * c->UC * 1e6f;
+            }
+            if (c->sw_wav_strain) { /* :601-608 */
+                float *w = r->wav_strain + ntw * 6 * n + (itw - 1);
+                w[0 * ntw] = r->exx[n] * c->M0 * c->UC * 1e-3f;
+                w[1 * ntw] = r->eyy[n] * c->M0 * c->UC * 1e-3f;
+                w[2 * ntw] = r->ezz[n] * c->M0 * c->UC * 1e-3f;
+                w[3 * ntw] = r->eyz[n] * c->M0 * c->UC * 1e-3f;
+                w[4 * ntw] = r->exz[n] * c->M0 * c->UC * 1e-3f;
+                w[5 * ntw] = r->exy[n] * c->M0 * c->UC * 1e-3f;
+            }
         }
     }
 }
