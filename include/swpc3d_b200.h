@@ -122,6 +122,27 @@ int swpc3d_vmax_global(swpc3d_handle *h, float out[3]);
 /* `!$acc update self(wav_vel)` (m_wav.f90:672): (ntw,3,nst) floats */
 int swpc3d_get_wav(swpc3d_handle *h, float *wav_vel);
 
+/* ---- snapshots (m_snap.f90): decimated 2-D slices gathered on the device.  product = section*3 + type with
+ * section 0 xy, 1 xz, 2 yz, 3 fs, 4 ob and type 0 ps (div, rot_x, rot_y, rot_z), 1 v (Vx,Vy,Vz), 2 u (Ux,Uy,Uz). */
+typedef struct {
+    int32_t idec, jdec, kdec, ntdec_s;          /* m_snap.f90:116-119 */
+    int32_t nxs, nys, nzs;                      /* :123-125 */
+    int32_t is0, is1, js0, js1, ks0, ks1;       /* :143-149, this rank's part of the slices */
+    int32_t k0_xy, i0_yz, j0_xz;                /* :152-154 */
+    int32_t sw[15];                             /* switches xy_ps xy_v xy_u xz_ps ... ob_u */
+    float M0, UC;
+} swpc3d_snap_cfg;
+int swpc3d_snap_setup(swpc3d_handle *h, const swpc3d_snap_cfg *cfg);
+/* snap__write(it) device part (m_snap.f90:919-948): displacement accumulation and fs/ob running maxima every step,
+ * slice evaluation when mod(it-1, ntdec_s) == 0.  Call at the top of iteration it, after swpc3d_wav_store. */
+int swpc3d_snap_step(swpc3d_handle *h, int32_t it);
+/* the slice buffer buf(n1,n2,nvar) summed over ranks to `root` (mpi_reduce SUM of m_snap.f90:1064; NCCL when a communicator
+ * is attached); out is written on the root only.  _max: max-V/H/A arrays of the fs/ob v and u products (:2295-2348). */
+int swpc3d_snap_fetch(swpc3d_handle *h, int32_t product, int32_t root, float *out);
+int swpc3d_snap_fetch_max(swpc3d_handle *h, int32_t product, int32_t root, float *out);
+/* sum-reduce a host float buffer over all ranks to root (setup-time medium slices of the snapshot headers, :600-607) */
+int swpc3d_reduce_sum(swpc3d_handle *h, float *buf, int64_t n, int32_t root);
+
 /* multi-GPU: NCCL send/recv replaces the MPI p2p of m_global.f90:408-456, 517-567.  The 128-byte
  * unique id is created on one rank and broadcast by the host (MPI_Bcast in a Fortran host,
  * torch.distributed in the Python host). */

@@ -56,6 +56,12 @@ swpc3d_handle *swpc3d_host_handle(swpc3d_host *h);
 int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, float *vm, int32_t nvm, int32_t *nrec);
 /* wav__write (m_wav.f90:658-792), SAC format: <odir>/wav/<title>.3d.<stnm>.<cmp>.sac ; returns file count in *nfiles */
 int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles);
+/* snapshots (m_snap.f90, snp_format = 'netcdf'): create <odir>/<title>.3d.<xy|xz|yz|fs|ob>.<ps|v|u>.nc on the I/O ranks
+ * (call after attach_device / comm init and before the first swpc3d_host_run); swpc3d_host_run then writes one record every
+ * ntdec_s steps; swpc3d_host_snap_close flushes the running maxima (max-V/H/A) and closes (snap__closefiles). */
+int swpc3d_host_snap_open(swpc3d_host *h, const char *odir);
+int swpc3d_host_snap_close(swpc3d_host *h);
+int swpc3d_host_nc_selftest(const char *path);   /* writes a tiny CDF-1 file with the in-tree writer (tests) */
 /* report__setup banner values (m_report.f90:71-105) to stderr */
 int swpc3d_host_banner(swpc3d_host *h);
 

@@ -51,7 +51,8 @@ SYMBOLS = [
     "swpc3d_download_fields", "swpc3d_zero_state", "swpc3d_setup_pml", "swpc3d_setup_cerjan", "swpc3d_set_sources",
     "swpc3d_set_stations", "swpc3d_update_stress", "swpc3d_stressglut", "swpc3d_comm_stress", "swpc3d_update_vel",
     "swpc3d_bodyforce", "swpc3d_comm_vel", "swpc3d_wav_store", "swpc3d_step", "swpc3d_run", "swpc3d_sync", "swpc3d_vmax",
-    "swpc3d_get_wav", "swpc3d_vmax_global", "swpc3d_set_wav_products", "swpc3d_get_wav_product", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
+    "swpc3d_get_wav", "swpc3d_vmax_global", "swpc3d_set_wav_products", "swpc3d_get_wav_product", "swpc3d_snap_setup", "swpc3d_snap_step", "swpc3d_snap_fetch",
+    "swpc3d_snap_fetch_max", "swpc3d_reduce_sum", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
 ]
 
 _lib = None

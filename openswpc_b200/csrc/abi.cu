@@ -4,6 +4,7 @@
 #include "../../include/swpc3d_b200.h"
 #include "kernels.cuh"
 #include "stress_tma.cuh"
+#include "snap.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -46,6 +47,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -68,6 +70,7 @@ static int nccl_load() {
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(Reduce, "ncclReduce");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
@@ -99,7 +102,7 @@ struct swpc3d_handle {
     float *R = nullptr;
     float *med[5] = {};                    // rho lam mu taup taus
     int4 *band = nullptr;
-    int *kbeg_a = nullptr, *kob = nullptr;
+    int *kbeg_a = nullptr, *kob = nullptr, *kfs = nullptr;
     std::vector<int> h_kbeg_a;
     long long *aoff = nullptr;
     float *aux = nullptr;
@@ -127,6 +130,11 @@ struct swpc3d_handle {
     int sw_v = 1, sw_u = 0, sw_stress = 0, sw_strain = 0;
     float M0 = 1.f, UC = 1e-15f;
     unsigned int *vmax_d = nullptr;
+    // snapshots
+    swpc3d_snap_cfg snap{};
+    bool snap_on = false;
+    float *snap_buf[15] = {}, *snap_max[15] = {}, *snap_tmp = nullptr;
+    size_t snap_tmp_n = 0;
     // halo
     void *sbuf[4] = {}, *rbuf[4] = {};     // 0: +x (ip) 1: -x (im) 2: +y (jp) 3: -y (jm)
     int nbr[4] = {-1, -1, -1, -1};
@@ -277,6 +285,8 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
     CK(cudaMalloc(&h->band, n2 * sizeof(int4)));
     CK(cudaMalloc(&h->kbeg_a, n2 * sizeof(int)));
     CK(cudaMalloc(&h->kob, n2 * sizeof(int)));
+    CK(cudaMalloc(&h->kfs, n2 * sizeof(int)));
+    CK(cudaMemsetAsync(h->kfs, 0, n2 * sizeof(int), h->st));
     CK(cudaMemsetAsync(h->band, 0, n2 * sizeof(int4), h->st));
     CK(cudaMemsetAsync(h->kob, 0, n2 * sizeof(int), h->st));
     // kbeg_a: m_global.f90:334-343
@@ -317,7 +327,8 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaFree(h->Fall);
     cudaFree(h->R);
     cudaFree(h->Mall);
-    cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->aoff); cudaFree(h->aux);
+    cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->kfs); cudaFree(h->snap_tmp);
+    for (int q = 0; q < 15; q++) { cudaFree(h->snap_buf[q]); cudaFree(h->snap_max[q]); } cudaFree(h->aoff); cudaFree(h->aux);
     for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
     cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
     cudaFree(h->st_ijk); cudaFree(h->wav); cudaFree(h->wav_u); cudaFree(h->wav_s); cudaFree(h->wav_e); cudaFree(h->wav_acc); cudaFree(h->vmax_d);
@@ -355,7 +366,6 @@ extern "C" int swpc3d_upload_medium(swpc3d_handle *h, const float *rho, const fl
     if (!h) return fail("null handle");
     if (!rho || !lam || !mu || !taup || !taus || !kob || !kfs_top || !kfs_bot || !kob_top || !kob_bot)
         return fail("swpc3d_upload_medium: null array");
-    (void)kfs;
     CK(cudaSetDevice(h->dev));
     const float *src[5] = {rho, lam, mu, taup, taus};
     for (int a = 0; a < 5; a++)
@@ -369,6 +379,7 @@ extern "C" int swpc3d_upload_medium(swpc3d_handle *h, const float *rho, const fl
             if (mi < HALO || mi >= HALO + h->nxp || mj < HALO || mj >= HALO + h->nyp) band[(size_t)mi + (size_t)h->NXM * mj] = make_int4(1, 1, 1, 1);
     CK(cudaMemcpyAsync(h->band, band.data(), n2 * sizeof(int4), cudaMemcpyHostToDevice, h->st));
     CK(cudaMemcpyAsync(h->kob, kob, n2 * sizeof(int), cudaMemcpyHostToDevice, h->st));
+    if (kfs) CK(cudaMemcpyAsync(h->kfs, kfs, n2 * sizeof(int), cudaMemcpyHostToDevice, h->st));
     if (kbeg_a) {
         for (int lj = 0; lj < h->nyp; lj++)
             for (int li = 0; li < h->nxp; li++) {
@@ -907,6 +918,121 @@ extern "C" int swpc3d_get_wav(swpc3d_handle *h, float *wav_vel) {
     if (h->nst <= 0 || h->ntw <= 0) return 0;
     CK(cudaSetDevice(h->dev));
     CK(cudaMemcpyAsync(wav_vel, h->wav, (size_t)h->ntw * 3 * h->nst * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// snapshots (m_snap.f90)
+static void snap_dims(const swpc3d_snap_cfg &c, int product, int &n1, int &n2, int &nvar) {
+    const int sec = product / 3, typ = product % 3;
+    n1 = sec == SEC_YZ ? c.nys : c.nxs;
+    n2 = (sec == SEC_XZ || sec == SEC_YZ) ? c.nzs : c.nys;
+    nvar = typ == TYP_PS ? 4 : 3;
+}
+
+extern "C" int swpc3d_snap_setup(swpc3d_handle *h, const swpc3d_snap_cfg *cfg) {
+    if (!h || !cfg) return fail("null argument");
+    CK(cudaSetDevice(h->dev));
+    h->snap = *cfg;
+    h->snap_on = false;
+    for (int q = 0; q < 15; q++) {
+        cudaFree(h->snap_buf[q]); cudaFree(h->snap_max[q]);
+        h->snap_buf[q] = h->snap_max[q] = nullptr;
+        if (!cfg->sw[q]) continue;
+        int n1, n2, nvar;
+        snap_dims(*cfg, q, n1, n2, nvar);
+        const size_t bytes = (size_t)n1 * n2 * nvar * sizeof(float);
+        CK(cudaMalloc(&h->snap_buf[q], bytes));
+        CK(cudaMemset(h->snap_buf[q], 0, bytes));
+        const int sec = q / 3, typ = q % 3;
+        if ((sec == SEC_FS || sec == SEC_OB) && typ != TYP_PS) {
+            CK(cudaMalloc(&h->snap_max[q], (size_t)n1 * n2 * 3 * sizeof(float)));
+            CK(cudaMemset(h->snap_max[q], 0, (size_t)n1 * n2 * 3 * sizeof(float)));
+        }
+        h->snap_on = true;
+    }
+    return 0;
+}
+
+template <typename F>
+static int snap_launch(swpc3d_handle *h, int product) {
+    const swpc3d_snap_cfg &c = h->snap;
+    const int sec = product / 3, typ = product % 3;
+    // ranks that do not hold the section keep their zero buffer (m_snap.f90:1527 "if (idy /= idy_xz) return")
+    if (sec == SEC_XZ && !(h->g.jbeg <= c.j0_xz && c.j0_xz <= h->g.jend)) return 0;
+    if (sec == SEC_YZ && !(h->g.ibeg <= c.i0_yz && c.i0_yz <= h->g.iend)) return 0;
+    SnapGeom g{};
+    g.idec = c.idec; g.jdec = c.jdec; g.kdec = c.kdec; g.nxs = c.nxs; g.nys = c.nys; g.nzs = c.nzs;
+    g.is0 = c.is0; g.is1 = c.is1; g.js0 = c.js0; g.js1 = c.js1; g.ks0 = c.ks0; g.ks1 = c.ks1;
+    g.k0_xy = c.k0_xy; g.i0_yz = c.i0_yz; g.j0_xz = c.j0_xz; g.ibeg = h->g.ibeg; g.jbeg = h->g.jbeg;
+    g.UC = c.UC; g.M0 = c.M0; g.kfs = h->kfs; g.kob = h->kob;
+    const int a0 = sec == SEC_YZ ? c.js0 : c.is0, a1 = sec == SEC_YZ ? c.js1 : c.is1;
+    const int b0 = (sec == SEC_XZ || sec == SEC_YZ) ? c.ks0 : c.js0, b1 = (sec == SEC_XZ || sec == SEC_YZ) ? c.ks1 : c.js1;
+    if (a1 < a0 || b1 < b0) return 0;
+    dim3 blk(32, 8, 1), grd((unsigned)((a1 - a0 + 1 + 31) / 32), (unsigned)((b1 - b0 + 1 + 7) / 8), 1);
+    snap_kernel<F><<<grd, blk, 0, h->st>>>(make_params<F>(h), g, sec, typ, h->snap_buf[product], h->snap_max[product]);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swpc3d_snap_step(swpc3d_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (!h->snap_on) return 0;
+    const bool out = h->snap.ntdec_s > 0 && (it - 1) % h->snap.ntdec_s == 0;
+    for (int q = 0; q < 15; q++) {
+        if (!h->snap_buf[q]) continue;
+        const int sec = q / 3, typ = q % 3;
+        const bool every = typ == TYP_U || (typ == TYP_V && (sec == SEC_FS || sec == SEC_OB));
+        if (!(every || out)) continue;
+        if (h->fb == 8 ? snap_launch<double>(h, q) : snap_launch<float>(h, q)) return 1;
+    }
+    return 0;
+}
+
+static int snap_fetch_impl(swpc3d_handle *h, const float *src, size_t n, int root, float *out) {
+    if (!src) return fail("swpc3d_snap_fetch: product not enabled");
+    CK(cudaSetDevice(h->dev));
+    const float *from = src;
+    if (h->comm) {
+        if (h->snap_tmp_n < n) {
+            cudaFree(h->snap_tmp);
+            CK(cudaMalloc(&h->snap_tmp, n * sizeof(float)));
+            h->snap_tmp_n = n;
+        }
+        NK(g_nccl.Reduce(src, h->snap_tmp, n, ncclFloat, ncclSum, root, h->comm, h->st));
+        from = h->snap_tmp;
+    }
+    if (out && (!h->comm || h->g.myid == root)) CK(cudaMemcpyAsync(out, from, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+
+extern "C" int swpc3d_snap_fetch(swpc3d_handle *h, int32_t product, int32_t root, float *out) {
+    if (!h || product < 0 || product >= 15) return fail("swpc3d_snap_fetch: bad argument");
+    int n1, n2, nvar;
+    snap_dims(h->snap, product, n1, n2, nvar);
+    return snap_fetch_impl(h, h->snap_buf[product], (size_t)n1 * n2 * nvar, root, out);
+}
+extern "C" int swpc3d_snap_fetch_max(swpc3d_handle *h, int32_t product, int32_t root, float *out) {
+    if (!h || product < 0 || product >= 15) return fail("swpc3d_snap_fetch_max: bad argument");
+    int n1, n2, nvar;
+    snap_dims(h->snap, product, n1, n2, nvar);
+    return snap_fetch_impl(h, h->snap_max[product], (size_t)n1 * n2 * 3, root, out);
+}
+extern "C" int swpc3d_reduce_sum(swpc3d_handle *h, float *buf, int64_t n, int32_t root) {
+    if (!h || !buf || n < 0) return fail("swpc3d_reduce_sum: bad argument");
+    if (!h->comm || n == 0) return 0;
+    CK(cudaSetDevice(h->dev));
+    if (h->snap_tmp_n < (size_t)n) {
+        cudaFree(h->snap_tmp);
+        CK(cudaMalloc(&h->snap_tmp, (size_t)n * sizeof(float)));
+        h->snap_tmp_n = (size_t)n;
+    }
+    CK(cudaMemcpyAsync(h->snap_tmp, buf, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    NK(g_nccl.Reduce(h->snap_tmp, h->snap_tmp, (size_t)n, ncclFloat, ncclSum, root, h->comm, h->st));
+    if (h->g.myid == root) CK(cudaMemcpyAsync(buf, h->snap_tmp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }

@@ -386,6 +386,11 @@ struct swpc3d_host {
     std::vector<std::string> stnm;
     // device
     swpc3d_handle *dev = nullptr;
+    struct SnapHost *snap = nullptr;       // snapshot products (m_snap.f90)
+    int setup_snap(const IniFile &ini);
+    int snap_open_files(const std::string &dir);
+    int snap_write(int it);
+    int snap_close();
     std::vector<float> wav;
     std::vector<float> wav_all[4];
     double loop_seconds = 0;
@@ -842,7 +847,322 @@ int swpc3d_host::setup(const IniFile &ini, int nm_, int myid_, int npx, int npy,
     setup_kernel();
     if (setup_source(ini)) return 1;
     if (setup_absorb()) return 1;
+    if (setup_snap(ini)) return 1;   // main.f90:76 snap__setup (files are created when a device is attached)
     if (setup_wav(ini)) return 1;
+    return 0;
+}
+
+// ============================================================================================================
+// snapshots: m_snap.f90.  netCDF classic (CDF-1) files written by a small in-tree writer (no netCDF library in the
+// image): dimensions, variables, attributes and their order follow write_nc_header (:627-745), newfile_*_nc
+// (:475-845), wbuf_nc (:950-979), close_nc (:2191-2204) and output__put_maxval (:2295-2348).
+namespace {
+
+void make_dirs(const std::string &p) {
+    for (size_t q = 1; q <= p.size(); q++)
+        if (q == p.size() || p[q] == '/') mkdir(p.substr(0, q).c_str(), 0777);
+}
+struct NcAtt { std::string name; int type; std::vector<unsigned char> val; int nelems; };
+struct NcVar {
+    std::string name; std::vector<int> dimids; std::vector<NcAtt> atts; int type = 5; bool rec = false;
+    std::vector<float> data; long long vsize = 0, begin = 0;
+};
+void be32(std::vector<unsigned char> &b, uint32_t v) { for (int q = 3; q >= 0; q--) b.push_back((unsigned char)(v >> (8 * q))); }
+void bef(std::vector<unsigned char> &b, float f) { uint32_t u; std::memcpy(&u, &f, 4); be32(b, u); }
+NcAtt att_text(const std::string &n, const std::string &v) { NcAtt a{n, 2, {}, (int)v.size()}; a.val.assign(v.begin(), v.end()); while (a.val.size() % 4) a.val.push_back(0); return a; }
+NcAtt att_int(const std::string &n, int v) { NcAtt a{n, 4, {}, 1}; be32(a.val, (uint32_t)v); return a; }
+NcAtt att_floats(const std::string &n, std::initializer_list<float> v) { NcAtt a{n, 5, {}, (int)v.size()}; for (float f : v) bef(a.val, f); return a; }
+
+class NcFile {
+  public:
+    std::vector<std::pair<std::string, int>> dims;   // length 0 = record dimension
+    std::vector<NcAtt> gatts;
+    std::vector<NcVar> vars;
+    int numrecs = 0;
+    FILE *fp = nullptr;
+    long long recsize = 0, rec_begin = 0;
+    ~NcFile() { if (fp) std::fclose(fp); }
+    int var_index(const std::string &n) const { for (size_t q = 0; q < vars.size(); q++) if (vars[q].name == n) return (int)q; return -1; }
+    NcAtt *find_att(NcVar &v, const std::string &n) { for (auto &a : v.atts) if (a.name == n) return &a; return nullptr; }
+    static void put_name(std::vector<unsigned char> &b, const std::string &n) { be32(b, (uint32_t)n.size()); for (char c : n) b.push_back((unsigned char)c); while (b.size() % 4) b.push_back(0); }
+    static void put_atts(std::vector<unsigned char> &b, const std::vector<NcAtt> &atts) {
+        if (atts.empty()) { be32(b, 0); be32(b, 0); return; }
+        be32(b, 0x0C); be32(b, (uint32_t)atts.size());
+        for (const NcAtt &a : atts) { put_name(b, a.name); be32(b, (uint32_t)a.type); be32(b, (uint32_t)a.nelems); b.insert(b.end(), a.val.begin(), a.val.end()); }
+    }
+    std::vector<unsigned char> header() const {
+        std::vector<unsigned char> b = {'C', 'D', 'F', 1};
+        be32(b, (uint32_t)numrecs);
+        be32(b, 0x0A); be32(b, (uint32_t)dims.size());
+        for (auto &d : dims) { put_name(b, d.first); be32(b, (uint32_t)d.second); }
+        put_atts(b, gatts);
+        be32(b, 0x0B); be32(b, (uint32_t)vars.size());
+        for (const NcVar &v : vars) {
+            put_name(b, v.name); be32(b, (uint32_t)v.dimids.size());
+            for (int d : v.dimids) be32(b, (uint32_t)d);
+            put_atts(b, v.atts); be32(b, (uint32_t)v.type); be32(b, (uint32_t)v.vsize); be32(b, (uint32_t)v.begin);
+        }
+        return b;
+    }
+    // lay out: fixed-size variables first (definition order), then the record section
+    bool create(const std::string &path) {
+        for (NcVar &v : vars) {
+            long long n = 1;
+            for (int d : v.dimids) if (dims[(size_t)d].second > 0) n *= dims[(size_t)d].second;
+            v.vsize = (n * 4 + 3) / 4 * 4;
+        }
+        const long long hsize = (long long)header().size();
+        long long off = hsize;
+        for (NcVar &v : vars) if (!v.rec) { v.begin = off; off += v.vsize; }
+        rec_begin = off; recsize = 0;
+        for (NcVar &v : vars) if (v.rec) { v.begin = off; off += v.vsize; recsize += v.vsize; }
+        fp = std::fopen(path.c_str(), "wb+");
+        if (!fp) return false;
+        flush_header();
+        for (NcVar &v : vars) if (!v.rec && !v.data.empty()) put_fixed(v);
+        return true;
+    }
+    void flush_header() { const auto b = header(); std::fseek(fp, 0, SEEK_SET); std::fwrite(b.data(), 1, b.size(), fp); std::fflush(fp); }
+    static void write_floats(FILE *f, const float *p, size_t n) { std::vector<unsigned char> b; b.reserve(4 * n); for (size_t q = 0; q < n; q++) bef(b, p[q]); std::fwrite(b.data(), 1, b.size(), f); }
+    void put_fixed(const NcVar &v) { std::fseek(fp, (long)v.begin, SEEK_SET); write_floats(fp, v.data.data(), v.data.size()); }
+    void put_record(int vidx, int rec, const float *p, size_t n) {
+        const NcVar &v = vars[(size_t)vidx];
+        std::fseek(fp, (long)(v.begin + (long long)rec * recsize), SEEK_SET);
+        write_floats(fp, p, n);
+        if (rec + 1 > numrecs) numrecs = rec + 1;
+    }
+};
+
+}   // namespace
+
+struct SnapProd {
+    bool on = false; int sec = 0, typ = 0, n1 = 0, n2 = 0, nvar = 0, ionode = 0;
+    std::string coordinate, snaptype, fname; std::vector<std::string> vname; std::string vunit;
+    float vmin[4] = {0, 0, 0, 0}, vmax[4] = {0, 0, 0, 0};
+    NcFile *nc = nullptr;
+};
+struct SnapHost {
+    int idec = 1, jdec = 1, kdec = 1, ntdec_s = 10, nxs = 0, nys = 0, nzs = 0, is0 = 0, is1 = 0, js0 = 0, js1 = 0, ks0 = 0, ks1 = 0;
+    int k0_xy = 0, i0_yz = 0, j0_xz = 0;
+    float z0_xy = 0, x0_yz = 0, y0_xz = 0;
+    std::string snp_format;
+    std::vector<float> xsnp, ysnp, zsnp;
+    SnapProd p[15];
+    bool any = false, opened = false;
+    std::vector<float> tmp;
+    ~SnapHost() { for (auto &q : p) delete q.nc; }
+};
+
+int swpc3d_host::setup_snap(const IniFile &ini) {   // m_snap.f90:95-322
+    delete snap;
+    snap = new SnapHost();
+    SnapHost &S = *snap;
+    static const char *sec_name[5] = {"xy", "xz", "yz", "fs", "ob"}, *typ_name[3] = {"ps", "v", "u"};
+    for (int sec = 0; sec < 5; sec++)
+        for (int typ = 0; typ < 3; typ++) {
+            SnapProd &P = S.p[sec * 3 + typ];
+            P.sec = sec; P.typ = typ;
+            P.on = ini.get_l(std::string(sec_name[sec]) + "_" + typ_name[typ] + "%sw", false);
+            S.any = S.any || P.on;
+        }
+    S.z0_xy = ini.get_s("z0_xy", std::max(std::min(10.0f, zend), zbeg));
+    S.x0_yz = ini.get_s("x0_yz", std::max(std::min(0.0f, xend), xbeg));
+    S.y0_xz = ini.get_s("y0_xz", std::max(std::min(0.0f, yend), ybeg));
+    S.idec = ini.get_i("idec", 1); S.jdec = ini.get_i("jdec", 1); S.kdec = ini.get_i("kdec", 1);
+    S.ntdec_s = ini.get_i("ntdec_s", 10);
+    S.snp_format = ini.get("snp_format", "native");
+    S.nxs = (nx + (S.idec / 2)) / S.idec; S.nys = (ny + (S.jdec / 2)) / S.jdec; S.nzs = (nz + (S.kdec / 2)) / S.kdec;
+    S.xsnp.resize(S.nxs); S.ysnp.resize(S.nys); S.zsnp.resize(S.nzs);
+    for (int i = 1; i <= S.nxs; i++) S.xsnp[i - 1] = i2x(i * S.idec - (S.idec / 2), xbeg, (float)dx);
+    for (int j = 1; j <= S.nys; j++) S.ysnp[j - 1] = i2x(j * S.jdec - (S.jdec / 2), ybeg, (float)dy);
+    for (int k = 1; k <= S.nzs; k++) S.zsnp[k - 1] = i2x(k * S.kdec - (S.kdec / 2), zbeg, (float)dz);
+    S.is0 = (int)std::ceil((float)(ibeg + S.idec / 2) / (float)S.idec); S.is1 = (int)std::floor((float)(iend + S.idec / 2) / (float)S.idec);
+    S.js0 = (int)std::ceil((float)(jbeg + S.jdec / 2) / (float)S.jdec); S.js1 = (int)std::floor((float)(jend + S.jdec / 2) / (float)S.jdec);
+    S.ks0 = (int)std::ceil((float)(1 + S.kdec / 2) / (float)S.kdec); S.ks1 = (int)std::floor((float)(nz + S.kdec / 2) / (float)S.kdec);
+    S.k0_xy = x2i(S.z0_xy, zbeg, (float)dz); S.i0_yz = x2i(S.x0_yz, xbeg, (float)dx); S.j0_xz = x2i(S.y0_xz, ybeg, (float)dy);
+    if (!S.any) return 0;
+    if (S.snp_format != "netcdf") return hfail("snp_format '" + S.snp_format + "' is outside the scope of this build (netcdf)");
+    // owner of a global index along one axis (global__getnode, m_global.f90:644-683)
+    auto owner = [](int n, int nproc, int g) { for (int q = 0; q < nproc; q++) { int np, b, e; decomp1d(n, nproc, q, np, b, e); if (b <= g && g <= e) return q; } return 0; };
+    const int idy_xz = owner(ny, nproc_y, S.j0_xz), idx_yz = owner(nx, nproc_x, S.i0_yz), nproc = nproc_x * nproc_y;
+    for (int q = 0; q < 15; q++) {
+        SnapProd &P = S.p[q];
+        P.n1 = P.sec == 2 ? S.nys : S.nxs;
+        P.n2 = (P.sec == 1 || P.sec == 2) ? S.nzs : S.nys;
+        P.nvar = P.typ == 0 ? 4 : 3;
+        P.coordinate = sec_name[P.sec];
+        P.snaptype = P.typ == 0 ? "ps" : (P.typ == 1 ? "v3" : "u3");
+        if (P.typ == 0) { P.vname = {"div", "rot_x", "rot_y", "rot_z"}; P.vunit = "1/s"; }
+        else if (P.typ == 1) { P.vname = {"Vx", "Vy", "Vz"}; P.vunit = "m/s"; }
+        else { P.vname = {"Ux", "Uy", "Uz"}; P.vunit = "m"; }
+        // output node, m_snap.f90:163-191: v, u, ps -> 0, 1, 2 (xy: +0, fs: +3, ob: +6) mod nproc; xz / yz within their row / column
+        const int ord = P.typ == 1 ? 0 : (P.typ == 2 ? 1 : 2);
+        if (P.sec == 0) P.ionode = (ord) % nproc;
+        else if (P.sec == 3) P.ionode = (3 + ord) % nproc;
+        else if (P.sec == 4) P.ionode = (6 + ord) % nproc;
+        else if (P.sec == 1) P.ionode = (ord % nproc_x) + nproc_x * idy_xz;
+        else P.ionode = idx_yz + nproc_x * (ord % nproc_y);
+        P.fname = title + ".3d." + sec_name[P.sec] + "." + typ_name[P.typ] + ".nc";
+    }
+    return 0;
+}
+
+// newfile_{xy,xz,yz}_nc: header + medium slices on the I/O rank (every rank takes part in the sum-reduce)
+int swpc3d_host::snap_open_files(const std::string &dir) {
+    SnapHost &S = *snap;
+    if (!S.any || S.opened) return 0;
+    make_dirs(dir);
+    const size_t n2m = (size_t)nxm * nym;
+    for (int q = 0; q < 15; q++) {
+        SnapProd &P = S.p[q];
+        if (!P.on) continue;
+        const bool horiz = P.sec == 0 || P.sec == 3 || P.sec == 4;
+        const int nmed = horiz ? 6 : 3;
+        const size_t np = (size_t)P.n1 * P.n2;
+        std::vector<std::vector<float>> med((size_t)nmed, std::vector<float>(np, 0.0f));
+        const bool part = (P.sec == 1) ? (jbeg <= S.j0_xz && S.j0_xz <= jend) : (P.sec == 2 ? (ibeg <= S.i0_yz && S.i0_yz <= iend) : true);
+        if (part) {
+            const int a0 = P.sec == 2 ? S.js0 : S.is0, a1 = P.sec == 2 ? S.js1 : S.is1;
+            const int b0 = (P.sec == 1 || P.sec == 2) ? S.ks0 : S.js0, b1 = (P.sec == 1 || P.sec == 2) ? S.ks1 : S.js1;
+            for (int b = b0; b <= b1; b++)
+                for (int a = a0; a <= a1; a++) {
+                    int i, j, k;
+                    if (P.sec == 1) { i = a * S.idec - S.idec / 2; j = S.j0_xz; k = b * S.kdec - S.kdec / 2; }
+                    else if (P.sec == 2) { i = S.i0_yz; j = a * S.jdec - S.jdec / 2; k = b * S.kdec - S.kdec / 2; }
+                    else { i = a * S.idec - S.idec / 2; j = b * S.jdec - S.jdec / 2; k = S.k0_xy; }
+                    if (P.sec == 3) k = kfs[i2(i, j)] + 1;
+                    if (P.sec == 4) k = kob[i2(i, j)] + 1;
+                    const size_t o = (size_t)(a - 1) + (size_t)P.n1 * (size_t)(b - 1), n = i3(k, i, j);
+                    med[0][o] = rho[n]; med[1][o] = lam[n]; med[2][o] = mu[n];
+                    if (horiz) {
+                        med[3][o] = -bddep[i2(i, j)] * 1000;
+                        geomap_c2g(S.xsnp[(size_t)a - 1], S.ysnp[(size_t)b - 1], clon, clat, phi, med[4][o], med[5][o]);
+                    }
+                }
+        }
+        (void)n2m;
+        for (int m = 0; m < nmed; m++)
+            if (swpc3d_reduce_sum(dev, med[(size_t)m].data(), (int64_t)np, P.ionode)) return hfail(std::string("device: ") + swpc3d_last_error());
+        if (myid != P.ionode) continue;
+        NcFile *nc = new NcFile();
+        P.nc = nc;
+        const std::vector<float> &x1 = P.sec == 2 ? S.ysnp : S.xsnp, &x2 = (P.sec == 1 || P.sec == 2) ? S.zsnp : S.ysnp;
+        const std::string n1s = P.sec == 2 ? "y" : "x", n2s = (P.sec == 1 || P.sec == 2) ? "z" : "y";
+        nc->dims = {{n1s, P.n1}, {n2s, P.n2}, {"t", 0}};
+        auto mm = [](const std::vector<float> &v) { float lo = v[0], hi = v[0]; for (float f : v) { lo = std::min(lo, f); hi = std::max(hi, f); } return std::make_pair(lo, hi); };
+        NcVar vx1; vx1.name = n1s; vx1.dimids = {0}; vx1.data = x1;
+        NcVar vx2; vx2.name = n2s; vx2.dimids = {1}; vx2.data = x2;
+        vx1.atts.push_back(att_text("long_name", n1s)); vx2.atts.push_back(att_text("long_name", n2s));
+        if (horiz) { vx1.atts.push_back(att_text("standard_name", "projection_x_coordinate")); vx2.atts.push_back(att_text("standard_name", "projection_y_coordinate")); }
+        vx1.atts.push_back(att_text("units", "km")); vx2.atts.push_back(att_text("units", "km"));
+        vx1.atts.push_back(att_floats("actual_range", {x1.front(), x1.back()})); vx2.atts.push_back(att_floats("actual_range", {x2.front(), x2.back()}));
+        NcVar vt; vt.name = "t"; vt.dimids = {2}; vt.rec = true;
+        vt.atts = {att_text("long_name", "t"), att_text("units", "s")};
+        nc->vars = {vx1, vx2, vt};
+        static const char *mname[6] = {"rho", "lambda", "mu", "topo", "lon", "lat"};
+        static const char *mlong[6] = {"rho", "lambda", "mu", "Topography", "Longitude", "Latitude"};
+        static const char *munit[6] = {"10^3 kg/cm^3", "10^9 Pa", "10^9 Pa", "m", "degrees_east", "degrees_north"};
+        for (int m = 0; m < nmed; m++) {
+            NcVar v; v.name = mname[m]; v.dimids = {1, 0}; v.data = med[(size_t)m];
+            if (horiz && m < 3) v.atts.push_back(att_text("coordinates", "lat lon"));
+            v.atts.push_back(att_text("long_name", mlong[m]));
+            v.atts.push_back(att_text("units", munit[m]));
+            if (horiz && m == 3) v.atts.push_back(att_text("coordinates", "lat lon"));
+            const auto r = mm(med[(size_t)m]);
+            v.atts.push_back(att_floats("actual_range", {r.first, r.second}));
+            nc->vars.push_back(v);
+        }
+        for (int v = 0; v < P.nvar; v++) {
+            NcVar sv; sv.name = P.vname[(size_t)v]; sv.dimids = {2, 1, 0}; sv.rec = true;
+            sv.atts = {att_text("long_name", P.vname[(size_t)v]), att_text("units", P.vunit)};
+            if (horiz) sv.atts.push_back(att_text("coordinates", "lat lon"));
+            sv.atts.push_back(att_floats("actual_range", {0.0f, 0.0f}));
+            nc->vars.push_back(sv);
+        }
+        if ((P.sec == 3 || P.sec == 4) && P.typ != 0) {   // output__put_maxval defines these at close; reserved here
+            static const char *xn[3] = {"max-V", "max-H", "max-A"};
+            static const char *xl[3] = {"Maximum amplitude of the vertical component", "Maximum amplitude of the horizontal components", "Maximum amplitude of the vector motion"};
+            for (int v = 0; v < 3; v++) {
+                NcVar xv; xv.name = xn[v]; xv.dimids = {1, 0}; xv.data.assign(np, 0.0f);
+                xv.atts = {att_text("long_name", xl[v]), att_text("coordinates", "lat lon"), att_text("units", P.typ == 1 ? "m/s" : "m"), att_floats("actual_range", {0.0f, 0.0f})};
+                nc->vars.push_back(xv);
+            }
+        }
+        const int d1 = P.sec == 2 ? S.jdec : S.idec, d2 = (P.sec == 1 || P.sec == 2) ? S.kdec : S.jdec;
+        const float ds1 = (float)(d1 * (P.sec == 2 ? dy : dx)), ds2 = (float)(d2 * ((P.sec == 1 || P.sec == 2) ? dz : dy));
+        nc->gatts = {att_text("generated_by", "SWPC"), att_text("codetype", "SWPC_3D "), att_int("hdrver", 6), att_text("title", title), att_int("exedate", exedate),
+                     att_int("ns1", P.n1), att_int("ns2", P.n2), att_floats("beg1", {x1.front()}), att_floats("beg2", {x2.front()}), att_int("na1", na / d1), att_int("na2", na / d2),
+                     att_floats("ds1", {ds1}), att_floats("ds2", {ds2}), att_int("nmed", nmed), att_int("nsnp", P.nvar), att_text("coordinate", P.coordinate),
+                     att_text("datatype", P.snaptype), att_floats("dt", {dt * S.ntdec_s}), att_floats("evlo", {evlo}), att_floats("evla", {evla}), att_floats("evdp", {evdp}),
+                     att_floats("evx", {sx0}), att_floats("evy", {sy0}), att_floats("clon", {clon}), att_floats("clat", {clat}), att_floats("phi", {phi})};
+        if (!nc->create(dir + "/" + P.fname)) return hfail("cannot create " + dir + "/" + P.fname);
+    }
+    // device side
+    swpc3d_snap_cfg c{};
+    c.idec = S.idec; c.jdec = S.jdec; c.kdec = S.kdec; c.ntdec_s = S.ntdec_s; c.nxs = S.nxs; c.nys = S.nys; c.nzs = S.nzs;
+    c.is0 = S.is0; c.is1 = S.is1; c.js0 = S.js0; c.js1 = S.js1; c.ks0 = S.ks0; c.ks1 = S.ks1; c.k0_xy = S.k0_xy; c.i0_yz = S.i0_yz; c.j0_xz = S.j0_xz;
+    for (int q = 0; q < 15; q++) c.sw[q] = S.p[q].on ? 1 : 0;
+    c.M0 = M0; c.UC = UC;
+    if (swpc3d_snap_setup(dev, &c)) return hfail(std::string("device: ") + swpc3d_last_error());
+    S.opened = true;
+    return 0;
+}
+
+// snap__write(it): device step, and at output steps reduce + record write (wbuf_nc :950-979; written at once instead of
+// one cycle later -- same record index it0/ntdec_s+1, same time it0*dt, same data)
+int swpc3d_host::snap_write(int it) {
+    SnapHost &S = *snap;
+    if (!S.any || !S.opened) return 0;
+    if (swpc3d_snap_step(dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
+    if (!(S.ntdec_s > 0 && (it - 1) % S.ntdec_s == 0)) return 0;
+    for (int q = 0; q < 15; q++) {
+        SnapProd &P = S.p[q];
+        if (!P.on) continue;
+        const size_t np = (size_t)P.n1 * P.n2;
+        S.tmp.assign(np * (size_t)P.nvar, 0.0f);
+        if (swpc3d_snap_fetch(dev, q, P.ionode, S.tmp.data())) return hfail(std::string("device: ") + swpc3d_last_error());
+        if (!P.nc) continue;
+        const int rec = it / S.ntdec_s;   // stt(3) = it0/ntdec_s + 1, zero-based here
+        const float tval = it * dt;
+        P.nc->put_record(P.nc->var_index("t"), rec, &tval, 1);
+        for (int v = 0; v < P.nvar; v++) {
+            const float *d = S.tmp.data() + np * (size_t)v;
+            const int vi = P.nc->var_index(P.vname[(size_t)v]);
+            P.nc->put_record(vi, rec, d, np);
+            for (size_t n = 0; n < np; n++) { P.vmax[v] = std::max(P.vmax[v], d[n]); P.vmin[v] = std::min(P.vmin[v], d[n]); }
+            *P.nc->find_att(P.nc->vars[(size_t)vi], "actual_range") = att_floats("actual_range", {P.vmin[v], P.vmax[v]});
+        }
+        P.nc->flush_header();
+    }
+    return 0;
+}
+
+// snap__closefiles :2206-2293 (+ output__put_maxval)
+int swpc3d_host::snap_close() {
+    SnapHost &S = *snap;
+    if (!S.any || !S.opened) return 0;
+    for (int q = 0; q < 15; q++) {
+        SnapProd &P = S.p[q];
+        if (!P.on) continue;
+        const size_t np = (size_t)P.n1 * P.n2;
+        if ((P.sec == 3 || P.sec == 4) && P.typ != 0) {
+            S.tmp.assign(np * 3, 0.0f);
+            if (swpc3d_snap_fetch_max(dev, q, P.ionode, S.tmp.data())) return hfail(std::string("device: ") + swpc3d_last_error());
+            if (P.nc) {
+                static const char *xn[3] = {"max-V", "max-H", "max-A"};
+                for (int v = 0; v < 3; v++) {
+                    NcVar &xv = P.nc->vars[(size_t)P.nc->var_index(xn[v])];
+                    xv.data.assign(S.tmp.begin() + (long)(np * (size_t)v), S.tmp.begin() + (long)(np * (size_t)(v + 1)));
+                    float lo = xv.data[0], hi = xv.data[0];
+                    for (float f : xv.data) { lo = std::min(lo, f); hi = std::max(hi, f); }
+                    *P.nc->find_att(xv, "actual_range") = att_floats("actual_range", {lo, hi});
+                    P.nc->put_fixed(xv);
+                }
+            }
+        }
+        if (P.nc) { P.nc->flush_header(); delete P.nc; P.nc = nullptr; }
+    }
+    S.opened = false;
     return 0;
 }
 
@@ -876,6 +1196,7 @@ int swpc3d_host_create_from_text(const char *text, const char *base_dir, int32_t
 }
 int swpc3d_host_destroy(swpc3d_host *h) {
     if (!h) return 0;
+    delete h->snap;
     if (h->dev) swpc3d_destroy(h->dev);
     delete h;
     return 0;
@@ -1011,6 +1332,37 @@ int swpc3d_host_attach_device(swpc3d_host *h, int32_t device) {
 }
 swpc3d_handle *swpc3d_host_handle(swpc3d_host *h) { return h ? h->dev : nullptr; }
 
+// snapshot files: created on the I/O ranks (newfile_*_nc), one record per ntdec_s steps during swpc3d_host_run, closed here
+int swpc3d_host_snap_open(swpc3d_host *h, const char *odir) {
+    if (!h || !h->dev) return hfail("swpc3d_host_snap_open: no device attached");
+    return h->snap_open_files(odir ? odir : h->odir.c_str());
+}
+int swpc3d_host_snap_close(swpc3d_host *h) {
+    if (!h) return hfail("null handle");
+    return h->snap_close();
+}
+
+// writer self-test (no GPU): a 3 x 2 grid, one fixed and one record variable, two records
+int swpc3d_host_nc_selftest(const char *path) {
+    NcFile nc;
+    nc.dims = {{"x", 3}, {"z", 2}, {"t", 0}};
+    NcVar x; x.name = "x"; x.dimids = {0}; x.data = {0.5f, 1.5f, 2.5f}; x.atts = {att_text("units", "km"), att_floats("actual_range", {0.5f, 2.5f})};
+    NcVar t; t.name = "t"; t.dimids = {2}; t.rec = true; t.atts = {att_text("units", "s")};
+    NcVar m; m.name = "rho"; m.dimids = {1, 0}; m.data = {1, 2, 3, 4, 5, 6};
+    NcVar v; v.name = "Vx"; v.dimids = {2, 1, 0}; v.rec = true; v.atts = {att_text("long_name", "Vx"), att_floats("actual_range", {0.0f, 0.0f})};
+    nc.vars = {x, t, m, v};
+    nc.gatts = {att_text("generated_by", "SWPC"), att_int("hdrver", 6), att_floats("dt", {0.25f})};
+    if (!nc.create(path ? path : "")) return hfail("cannot create file");
+    for (int r = 0; r < 2; r++) {
+        const float tv = 0.25f * (float)r, d[6] = {10.f * r, 10.f * r + 1, 10.f * r + 2, 10.f * r + 3, 10.f * r + 4, -10.f * r - 5};
+        nc.put_record(1, r, &tv, 1);
+        nc.put_record(3, r, d, 6);
+    }
+    *nc.find_att(nc.vars[3], "actual_range") = att_floats("actual_range", {-15.0f, 14.0f});
+    nc.flush_header();
+    return 0;
+}
+
 int swpc3d_host_banner(swpc3d_host *h) {   // m_report.f90:64-92
     if (!h) return hfail("null handle");
     double c, r;
@@ -1053,7 +1405,14 @@ int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, f
                              (int)etas, (double)v[0], (double)v[1], (double)v[2]);
             }
         }
-        if (swpc3d_step(h->dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
+        if (h->snap && h->snap->any && h->snap->opened) {   // main.f90:123-138 with snap__write between wav__store and the sweeps
+#define DS(call) if (call) return hfail(std::string("device: ") + swpc3d_last_error());
+            DS(swpc3d_wav_store(h->dev, it));
+            if (h->snap_write(it)) return 1;
+            DS(swpc3d_update_stress(h->dev)); DS(swpc3d_stressglut(h->dev, it)); DS(swpc3d_comm_stress(h->dev));
+            DS(swpc3d_update_vel(h->dev)); DS(swpc3d_bodyforce(h->dev, it)); DS(swpc3d_comm_vel(h->dev));
+#undef DS
+        } else if (swpc3d_step(h->dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
     }
     if (swpc3d_sync(h->dev)) return hfail(std::string("device: ") + swpc3d_last_error());
     h->loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -53,6 +53,8 @@ def _bind(lib):
     lib.swpc3d_host_run.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
     lib.swpc3d_host_write_sac.argtypes = [vp, cp, C.POINTER(i32)]
     lib.swpc3d_host_banner.argtypes = [vp]
+    lib.swpc3d_host_snap_open.argtypes = [vp, cp]
+    lib.swpc3d_host_snap_close.argtypes = [vp]
     _bound = True
 
 
@@ -177,6 +179,14 @@ class Swpc3d:
         self._ck(self.lib.swpc3d_host_write_sac(self.h, os.fspath(odir).encode() if odir is not None else None, C.byref(n)))
         return n.value
 
+    def snap_open(self, odir=None):
+        """Create the netCDF snapshot files (m_snap.f90 newfile_*_nc); call after attach_device (and attach_nccl)."""
+        self._ck(self.lib.swpc3d_host_snap_open(self.h, os.fspath(odir).encode() if odir is not None else None))
+
+    def snap_close(self):
+        """snap__closefiles: running maxima + close."""
+        self._ck(self.lib.swpc3d_host_snap_close(self.h))
+
     def wav(self) -> np.ndarray:
         """(nst, 3, ntw) float32 [nm/s] after write_sac() / fetch_wav()."""
         return self.array("wav")
@@ -208,3 +218,4 @@ class Swpc3d:
         args = [out[n].ctypes.data_as(C.c_void_p) if n in out else None for n in allf]
         self.device_call("swpc3d_download_fields", *args)
         return out
+

@@ -181,6 +181,7 @@ typedef struct {
     int nranks;
     ora_rank *r;
     int *itbl;                    /* (-1:nproc_x, -1:nproc_y), -1 == MPI_PROC_NULL */
+    void *snap;                   /* snapshot state (ora_snap.c) */
     char errmsg[512];
 } ora_sim;
 
@@ -238,6 +239,16 @@ int ora_get_wav(const ora_sim *s, int rank, float *out /*(ntw,3,nst)*/);
 int ora_get_wav_product(const ora_sim *s, int rank, int which, float *out);
 /* PML profile g?c/g?e: name gxc gxe gyc gye gzc gze -> (4,n) floats */
 int ora_get_profile(const ora_sim *s, int rank, const char *name, float *out);
+/* snapshots (ora_snap.c) */
+int ora_snap_setup(ora_sim *s, const ora_ini *ini);
+void ora_snap_write(ora_sim *s, int it);
+void ora_snap_free(ora_sim *s);
+int ora_snap_info(const ora_sim *s, int *info);
+int ora_snap_coords(const ora_sim *s, float *x, float *y, float *z);
+int ora_snap_nrec(const ora_sim *s, int q);
+int ora_snap_rec(const ora_sim *s, int q, int rec, float *out, int *it0);
+int ora_snap_max(const ora_sim *s, int q, float *out);
+int ora_snap_medium(const ora_sim *s, int q, int which, float *out);
 /* SAC output of all stations of all ranks (m_wav.f90:658-792); returns number of files */
 int ora_write_sac(const ora_sim *s, const char *odir);
 

@@ -975,6 +975,7 @@ static ora_sim *create_from_ini(ora_ini *ini, const char *base_dir, int nm, int 
     kernel_setup(s);
     if (source_setup(s, ini, base_dir)) { ora_destroy(s); return NULL; }
     if (absorb_setup(s)) { ora_destroy(s); return NULL; }
+    ora_snap_setup(s, ini); /* main.f90:76 */
     if (wav_setup(s, ini, base_dir)) { ora_destroy(s); return NULL; }
     ora_readini_i(ini, "ntdec_r", &c->ntdec_r, 10); /* m_report.f90:47 */
     return s;
@@ -1002,6 +1003,7 @@ ora_sim *ora_create_from_text(const char *inf_text, const char *base_dir, int nm
 
 void ora_destroy(ora_sim *s) {
     if (!s) return;
+    ora_snap_free(s);
     for (int q = 0; q < s->nranks; q++) {
         ora_rank *r = &s->r[q];
         void *ptrs[] = {r->Vx, r->Vy, r->Vz, r->Sxx, r->Syy, r->Szz, r->Syz, r->Sxz, r->Sxy, r->Rxx, r->Ryy, r->Rzz, r->Ryz,

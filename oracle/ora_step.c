@@ -660,6 +660,7 @@ void ora_vmax(ora_sim *s, float out[3]) {
 /* one iteration, main.f90:119-139 (report__progress is ora_vmax; snapshots/green are out of scope) */
 void ora_step(ora_sim *s, int it) {
     ora_wav_store(s, it);
+    ora_snap_write(s, it);
     ora_update_stress(s);
     ora_stressglut(s, it);
     ora_comm_stress(s);

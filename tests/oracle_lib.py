@@ -231,3 +231,73 @@ class Oracle:
 
     def write_sac(self, odir: str | os.PathLike) -> int:
         return self.lib.ora_write_sac(self.h, str(odir).encode())
+
+
+# ---- snapshots (oracle/ora_snap.c)
+SNAP_SECTIONS = ("xy", "xz", "yz", "fs", "ob")
+SNAP_TYPES = ("ps", "v", "u")
+
+
+def _snap_bind(o):
+    L = o.lib
+    vp, ci, fp = C.c_void_p, C.c_int, C.POINTER(C.c_float)
+    L.ora_snap_info.argtypes = [vp, C.POINTER(ci)]
+    L.ora_snap_coords.argtypes = [vp, fp, fp, fp]
+    L.ora_snap_nrec.argtypes = [vp, ci]
+    L.ora_snap_nrec.restype = ci
+    L.ora_snap_rec.argtypes = [vp, ci, ci, fp, C.POINTER(ci)]
+    L.ora_snap_max.argtypes = [vp, ci, fp]
+    L.ora_snap_medium.argtypes = [vp, ci, ci, fp]
+
+
+def snap_info(o) -> dict:
+    _snap_bind(o)
+    v = (C.c_int * 10)()
+    o.lib.ora_snap_info(o.h, v)
+    return dict(zip(["idec", "jdec", "kdec", "ntdec_s", "nxs", "nys", "nzs", "k0_xy", "i0_yz", "j0_xz"], list(v)))
+
+
+def snap_dims(o, q):
+    i = snap_info(o)
+    sec, typ = divmod(q, 3)
+    n1 = i["nys"] if sec == 2 else i["nxs"]
+    n2 = i["nzs"] if sec in (1, 2) else i["nys"]
+    return n1, n2, (4 if typ == 0 else 3)
+
+
+def snap_records(o, q):
+    """(nrec, nvar, n2, n1) array and the list of it0"""
+    _snap_bind(o)
+    n1, n2, nv = snap_dims(o, q)
+    nrec = o.lib.ora_snap_nrec(o.h, q)
+    out = np.zeros((nrec, nv, n2, n1), dtype=np.float32)
+    its = []
+    for r in range(nrec):
+        it0 = C.c_int()
+        o.lib.ora_snap_rec(o.h, q, r, out[r].ctypes.data_as(C.POINTER(C.c_float)), C.byref(it0))
+        its.append(it0.value)
+    return out, its
+
+
+def snap_max(o, q):
+    _snap_bind(o)
+    n1, n2, _ = snap_dims(o, q)
+    out = np.zeros((3, n2, n1), dtype=np.float32)
+    rc = o.lib.ora_snap_max(o.h, q, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out if rc == 0 else None
+
+
+def snap_medium(o, q, which):
+    _snap_bind(o)
+    n1, n2, _ = snap_dims(o, q)
+    out = np.zeros((n2, n1), dtype=np.float32)
+    o.lib.ora_snap_medium(o.h, q, which, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def snap_coords(o):
+    _snap_bind(o)
+    i = snap_info(o)
+    x, y, z = (np.zeros(i[k], dtype=np.float32) for k in ("nxs", "nys", "nzs"))
+    o.lib.ora_snap_coords(o.h, *(a.ctypes.data_as(C.POINTER(C.c_float)) for a in (x, y, z)))
+    return x, y, z
