@@ -193,6 +193,12 @@ float stable_dt(float dx, float dy, float dz, float vmax) {   // fdm_stable_dt :
     return cc * hh / vmax;
 }
 float moment_magnitude(float m0) { return m0 < EPS_SP ? -12345.0f : (std::log10(m0) - 9.1f) * 2.0f / 3.0f; }   // :281-293
+float powi_sp(float x, int m) {   // real(SP) ** integer the way gfortran does it (libgcc __powisf2)
+    unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
+    float y = (n % 2) ? x : 1.0f;
+    while (n >>= 1) { x = x * x; if (n % 2) y *= x; }
+    return m < 0 ? 1.0f / y : y;
+}
 float seismic_moment(float mw) { return std::pow(10.0f, 1.5f * mw + 9.05f); }                                     // :296-304
 
 void sdr2moment(float strike, float dip, float rake, float m[6]) {   // :307-336 ; m = mxx myy mzz myz mxz mxy
@@ -689,8 +695,30 @@ int swpc3d_host::setup_source(const IniFile &ini) {   // m_source.f90:41-314
                 g.push_back(s);
                 continue;
             }
+            if (stf_format == "psmeca") {   // :641-666  lon lat z mzz mxx myy mxz myz mxy iex (dyn-cm)
+                if (v.size() < 10) return hfail("source file: bad psmeca record");
+                s.z = v[2]; s.m[2] = v[3]; s.m[0] = v[4]; s.m[1] = v[5]; s.m[4] = v[6]; s.m[3] = -v[7]; s.m[5] = -v[8];
+                geomap_g2c(v[0], v[1], clon, clat, phi, s.x, s.y);
+                const float M0tmp = std::sqrt(s.m[0] * s.m[0] + s.m[1] * s.m[1] + s.m[2] * s.m[2] + 2 * (s.m[4] * s.m[4] + s.m[3] * s.m[3] + s.m[5] * s.m[5])) / std::sqrt(2.0f);
+                s.mo = M0tmp * powi_sp(10.0f, (int)v[9]);
+                s.t0 = 0.0f;
+                s.tr = (float)((double)(2 * 1.05f * 1e-8f) * std::pow((double)s.mo, 1.0 / 3.0));   // 2 x empirical half-duration
+                s.mo = s.mo * 1e-7f;
+                for (int q = 0; q < 6; q++) s.m[q] = s.m[q] / M0tmp;
+            } else if ((ll || xy) && kind == "dsdc") {   // :585-639  x y z tbeg trise D S strike dip rake
+                if (v.size() < 10) return hfail("source file: bad dsdc record");
+                if (xy) { s.x = v[0]; s.y = v[1]; } else geomap_g2c(v[0], v[1], clon, clat, phi, s.x, s.y);
+                s.z = v[2]; s.t0 = v[3]; s.tr = v[4];
+                sdr2moment(v[7] - phi, v[8], v[9], s.m);
+                const int is0 = x2i(s.x, xbeg, (float)dx), js0 = x2i(s.y, ybeg, (float)dy);
+                const int ks0 = earth_flattening ? x2i((float)(-R_EARTH * std::log((R_EARTH - (double)s.z) / R_EARTH)), zbeg, (float)dz) : x2i(s.z, zbeg, (float)dz);
+                // mo = 1e9 mu(ks0,is0,js0) D S on the ranks that hold the cell, MPI_MAX over ranks (:691-696).  Every
+                // velocity model of this build is laterally uniform, so the owner's mu equals this rank's own column.
+                if (-1 <= is0 && is0 <= nx + 3 && -1 <= js0 && js0 <= ny + 3 && -1 <= ks0 && ks0 <= nz + 3) s.mo = (1e9f * mu[i3(ks0, ibeg, jbeg)]) * v[5] * v[6];
+                else s.mo = 0.0f;
+            } else {
             if (!(ll || xy) || !(kind == "m0ij" || kind == "m0dc" || kind == "mwij" || kind == "mwdc"))
-                return hfail("stf_format '" + stf_format + "' is outside the hot-path scope of this build (xy|ll + m0|mw + ij|dc)");
+                return hfail("invalid source type (stf_format '" + stf_format + "', m_source.f90:668-670)");
             const size_t need = kind[2] == 'i' ? 12 : 9;
             if (v.size() < need) return hfail("source file: bad moment record (assert(ierr == 0), m_source.f90:517)");
             if (xy) { s.x = v[0]; s.y = v[1]; } else geomap_g2c(v[0], v[1], clon, clat, phi, s.x, s.y);
@@ -698,6 +726,7 @@ int swpc3d_host::setup_source(const IniFile &ini) {   // m_source.f90:41-314
             s.mo = kind[1] == '0' ? v[5] : seismic_moment(v[5]);
             if (kind[2] == 'i') std::copy(v.begin() + 6, v.begin() + 12, s.m);
             else sdr2moment(v[6] - phi, v[7], v[8], s.m);
+            }
             if (g.empty()) {   // :675-687
                 geomap_c2g(s.x, s.y, clon, clat, phi, evlo, evla);
                 sx0 = s.x; sy0 = s.y; evdp = s.z; std::copy(s.m, s.m + 6, m0ij); otim = s.t0;
@@ -940,6 +969,7 @@ struct SnapProd {
     std::string coordinate, snaptype, fname; std::vector<std::string> vname; std::string vunit;
     float vmin[4] = {0, 0, 0, 0}, vmax[4] = {0, 0, 0, 0};
     NcFile *nc = nullptr;
+    FILE *snp = nullptr;   // native stream file (snp_format='native')
 };
 struct SnapHost {
     int idec = 1, jdec = 1, kdec = 1, ntdec_s = 10, nxs = 0, nys = 0, nzs = 0, is0 = 0, is1 = 0, js0 = 0, js1 = 0, ks0 = 0, ks1 = 0;
@@ -950,7 +980,8 @@ struct SnapHost {
     SnapProd p[15];
     bool any = false, opened = false;
     std::vector<float> tmp;
-    ~SnapHost() { for (auto &q : p) delete q.nc; }
+    bool native = false;
+    ~SnapHost() { for (auto &q : p) { delete q.nc; if (q.snp) std::fclose(q.snp); } }
 };
 
 int swpc3d_host::setup_snap(const IniFile &ini) {   // m_snap.f90:95-322
@@ -981,7 +1012,8 @@ int swpc3d_host::setup_snap(const IniFile &ini) {   // m_snap.f90:95-322
     S.ks0 = (int)std::ceil((float)(1 + S.kdec / 2) / (float)S.kdec); S.ks1 = (int)std::floor((float)(nz + S.kdec / 2) / (float)S.kdec);
     S.k0_xy = x2i(S.z0_xy, zbeg, (float)dz); S.i0_yz = x2i(S.x0_yz, xbeg, (float)dx); S.j0_xz = x2i(S.y0_xz, ybeg, (float)dy);
     if (!S.any) return 0;
-    if (S.snp_format != "netcdf") return hfail("snp_format '" + S.snp_format + "' is outside the scope of this build (netcdf)");
+    if (S.snp_format != "netcdf" && S.snp_format != "native") return hfail("snp_format '" + S.snp_format + "': expected 'native' or 'netcdf'");
+    S.native = S.snp_format == "native";
     // owner of a global index along one axis (global__getnode, m_global.f90:644-683)
     auto owner = [](int n, int nproc, int g) { for (int q = 0; q < nproc; q++) { int np, b, e; decomp1d(n, nproc, q, np, b, e); if (b <= g && g <= e) return q; } return 0; };
     const int idy_xz = owner(ny, nproc_y, S.j0_xz), idx_yz = owner(nx, nproc_x, S.i0_yz), nproc = nproc_x * nproc_y;
@@ -1002,7 +1034,7 @@ int swpc3d_host::setup_snap(const IniFile &ini) {   // m_snap.f90:95-322
         else if (P.sec == 4) P.ionode = (6 + ord) % nproc;
         else if (P.sec == 1) P.ionode = (ord % nproc_x) + nproc_x * idy_xz;
         else P.ionode = idx_yz + nproc_x * (ord % nproc_y);
-        P.fname = title + ".3d." + sec_name[P.sec] + "." + typ_name[P.typ] + ".nc";
+        P.fname = title + ".3d." + sec_name[P.sec] + "." + typ_name[P.typ] + (S.native ? ".snp" : ".nc");
     }
     return 0;
 }
@@ -1044,6 +1076,24 @@ int swpc3d_host::snap_open_files(const std::string &dir) {
         for (int m = 0; m < nmed; m++)
             if (swpc3d_reduce_sum(dev, med[(size_t)m].data(), (int64_t)np, P.ionode)) return hfail(std::string("device: ") + swpc3d_last_error());
         if (myid != P.ionode) continue;
+        if (S.native) {   // newfile_{xy,xz,yz} + write_snp_header :846-892: fixed stream header, then rho, lam, mu (, topo)
+            P.snp = std::fopen((dir + "/" + P.fname).c_str(), "wb");
+            if (!P.snp) return hfail("cannot create " + dir + "/" + P.fname);
+            const std::vector<float> &a1 = P.sec == 2 ? S.ysnp : S.xsnp, &a2 = (P.sec == 1 || P.sec == 2) ? S.zsnp : S.ysnp;
+            const int e1 = P.sec == 2 ? S.jdec : S.idec, e2 = (P.sec == 1 || P.sec == 2) ? S.kdec : S.jdec;
+            std::string ttl = title; ttl.resize(80, ' ');
+            auto wi = [&](int32_t v) { std::fwrite(&v, 4, 1, P.snp); };
+            auto wf = [&](float v) { std::fwrite(&v, 4, 1, P.snp); };
+            std::fwrite("STREAMIO", 1, 8, P.snp); std::fwrite("SWPC_3D ", 1, 8, P.snp); wi(6);
+            std::fwrite(ttl.data(), 1, 80, P.snp); wi(exedate);
+            std::fwrite(P.coordinate.data(), 1, 2, P.snp); std::fwrite(P.snaptype.data(), 1, 2, P.snp);
+            wi(P.n1); wi(P.n2); wf(a1[0]); wf(a2[0]);
+            wf(a1.size() > 1 ? a1[1] - a1[0] : 0.0f); wf(a2.size() > 1 ? a2[1] - a2[0] : 0.0f);
+            wf(dt * (float)S.ntdec_s); wi(na / e1); wi(na / e2); wi(nmed); wi(P.nvar);
+            wf(clon); wf(clat); wf(phi); wf(1.0f); wf(1.0f); wf(1.0f);
+            for (int m = 0; m < (horiz ? 4 : 3); m++) std::fwrite(med[(size_t)m].data(), 4, np, P.snp);
+            continue;
+        }
         NcFile *nc = new NcFile();
         P.nc = nc;
         const std::vector<float> &x1 = P.sec == 2 ? S.ysnp : S.xsnp, &x2 = (P.sec == 1 || P.sec == 2) ? S.zsnp : S.ysnp;
@@ -1121,6 +1171,7 @@ int swpc3d_host::snap_write(int it) {
         const size_t np = (size_t)P.n1 * P.n2;
         S.tmp.assign(np * (size_t)P.nvar, 0.0f);
         if (swpc3d_snap_fetch(dev, q, P.ionode, S.tmp.data())) return hfail(std::string("device: ") + swpc3d_last_error());
+        if (P.snp) { std::fwrite(S.tmp.data(), 4, np * (size_t)P.nvar, P.snp); std::fflush(P.snp); continue; }   // write_reduce_array2d_r per component
         if (!P.nc) continue;
         const int rec = it / S.ntdec_s;   // stt(3) = it0/ntdec_s + 1, zero-based here
         const float tval = it * dt;
@@ -1161,6 +1212,7 @@ int swpc3d_host::snap_close() {
             }
         }
         if (P.nc) { P.nc->flush_header(); delete P.nc; P.nc = nullptr; }
+        if (P.snp) { std::fclose(P.snp); P.snp = nullptr; }
     }
     S.opened = false;
     return 0;
@@ -1435,7 +1487,7 @@ int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles) {
     const bool sw[4] = {h->sw_wav_v, h->sw_wav_u, h->sw_wav_stress, h->sw_wav_strain};
     if (!(sw[0] || sw[1] || sw[2] || sw[3]) || nst == 0 || h->ntw <= 0) return 0;
     if (!h->dev) return hfail("swpc3d_host_write_sac: no device attached");
-    if (h->wav_format != "sac") return hfail("wav_format '" + h->wav_format + "' is outside the hot-path scope of this build (sac)");
+    // wav_format other than sac / csf / tar_st / tar_node: wav__write has no branch for it and writes nothing (m_wav.f90:677-763)
     const std::string dir = std::string(odir ? odir : h->odir.c_str()) + "/wav";
     mkdirs(dir);
     static const char *cmpnm[4][6] = {{"Vx", "Vy", "Vz", "", "", ""}, {"Ux", "Uy", "Uz", "", "", ""},
@@ -1454,52 +1506,129 @@ int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles) {
         if (prod == 0) h->wav = buf;
         h->wav_all[prod] = buf;
     }
-    for (int s = 0; s < nst; s++)
-        for (int prod = 0; prod < 4; prod++) {   // order of m_wav.f90:679-705: per station v, u, stress, strain
+    // one SAC record = 632-byte header (sac__whdr) + ntw samples
+    auto sac_record = [&](int s, int prod, int c, std::vector<unsigned char> &out) {
+        const int ncmp = prod < 2 ? 3 : 6;
+        float f[70];
+        int32_t iv[35], lv[5];
+        char a[192];
+        std::fill(f, f + 70, -12345.0f);
+        std::fill(iv, iv + 35, -12345);
+        std::fill(lv, lv + 5, 0);
+        for (int q = 0; q < 24; q++) put_chars(a + 8 * q, "-12345", 8);
+        put_chars(a + 8, "-12345", 16);
+        const double delta = (double)(h->ntdec_w * h->dt);
+        f[0] = (float)((int)(delta * 1e7)) / 1e7f;
+        f[5] = h->tbeg; f[7] = h->otim;
+        f[31] = h->stla[s]; f[32] = h->stlo[s]; f[34] = h->zst[s] * 1000;
+        f[35] = h->evla; f[36] = h->evlo; f[38] = h->evdp; f[39] = moment_magnitude(h->M0);
+        if (h->bf_mode) { f[40] = h->f0[0]; f[41] = h->f0[1]; f[42] = h->f0[2]; }
+        else for (int q = 0; q < 6; q++) f[40 + q] = h->m0ij[q];
+        f[46] = h->clon; f[47] = h->clat; f[48] = h->phi;
+        const float ddx = h->sx0 - h->xst[s], ddy = h->sy0 - h->yst[s];
+        f[50] = std::sqrt(ddx * ddx + ddy * ddy);
+        f[51] = rad2deg_s(std::atan2(h->yst[s] - h->sy0, h->xst[s] - h->sx0));
+        f[52] = rad2deg_s(std::atan2(h->sy0 - h->yst[s], h->sx0 - h->xst[s]));
+        if (prod < 2) {   // cmpaz / cmpinc only for the vector products (m_wav.f90:286-288, :297-299)
+            f[57] = c == 0 ? 0.0f + h->phi : (c == 1 ? 90.0f + h->phi : 0.0f);
+            f[58] = 90.0f;
+        }
+        iv[0] = g.tm_year + 1900; iv[1] = g.tm_yday + 1; iv[2] = g.tm_hour; iv[3] = g.tm_min; iv[4] = g.tm_sec; iv[5] = 0;
+        iv[6] = 6; iv[9] = h->ntw; iv[15] = 1; iv[16] = prod == 0 ? 7 : (prod == 1 ? 6 : 5);
+        lv[0] = 1; lv[2] = 1;
+        put_chars(a, h->stnm[s], 8);
+        std::string t = h->title;
+        t.erase(0, t.find_first_not_of(' ') == std::string::npos ? t.size() : t.find_first_not_of(' '));
+        put_chars(a + 8, t.substr(0, 16), 16);
+        put_chars(a + 160, cmpnm[prod][c], 8);
+        out.resize(632 + 4 * (size_t)h->ntw);
+        std::memcpy(out.data(), f, 280); std::memcpy(out.data() + 280, iv, 140); std::memcpy(out.data() + 420, lv, 20); std::memcpy(out.data() + 440, a, 192);
+        std::memcpy(out.data() + 632, h->wav_all[prod].data() + (size_t)h->ntw * ncmp * s + (size_t)h->ntw * c, 4 * (size_t)h->ntw);
+    };
+    std::vector<unsigned char> rec;
+    const std::string &fmt = h->wav_format;
+    if (fmt == "sac") {
+        for (int s = 0; s < nst; s++)
+            for (int prod = 0; prod < 4; prod++) {   // order of m_wav.f90:679-705: per station v, u, stress, strain
+                if (!sw[prod]) continue;
+                for (int c = 0; c < (prod < 2 ? 3 : 6); c++) {
+                    sac_record(s, prod, c, rec);
+                    const std::string fn = dir + "/" + h->title + ".3d." + h->stnm[s] + "." + cmpnm[prod][c] + ".sac";
+                    FILE *fp = std::fopen(fn.c_str(), "wb");
+                    if (!fp) return hfail("cannot write " + fn);
+                    std::fwrite(rec.data(), 1, rec.size(), fp);
+                    std::fclose(fp);
+                    count++;
+                }
+            }
+    } else if (fmt == "csf") {
+        // export_wav__csf m_wav.f90:795-808 + wcsf_s m_sac.f90:585-648: 'CSFD', ntrace, npts, then (header, data) per trace,
+        // one file per rank.  Every enabled product goes to the SAME file name in the reference (the second one stops at
+        // an interactive overwrite prompt); here the later product replaces the earlier one.
+        char cid[16];
+        std::snprintf(cid, sizeof(cid), "%05d", h->myid);
+        const std::string fn = dir + "/" + h->title + "__" + cid + "__.csf";
+        for (int prod = 0; prod < 4; prod++) {
             if (!sw[prod]) continue;
             const int ncmp = prod < 2 ? 3 : 6;
-            for (int c = 0; c < ncmp; c++) {
-                float f[70];
-                int32_t iv[35], lv[5];
-                char a[192];
-                std::fill(f, f + 70, -12345.0f);
-                std::fill(iv, iv + 35, -12345);
-                std::fill(lv, lv + 5, 0);
-                for (int q = 0; q < 24; q++) put_chars(a + 8 * q, "-12345", 8);
-                put_chars(a + 8, "-12345", 16);
-                const double delta = (double)(h->ntdec_w * h->dt);
-                f[0] = (float)((int)(delta * 1e7)) / 1e7f;
-                f[5] = h->tbeg; f[7] = h->otim;
-                f[31] = h->stla[s]; f[32] = h->stlo[s]; f[34] = h->zst[s] * 1000;
-                f[35] = h->evla; f[36] = h->evlo; f[38] = h->evdp; f[39] = moment_magnitude(h->M0);
-                if (h->bf_mode) { f[40] = h->f0[0]; f[41] = h->f0[1]; f[42] = h->f0[2]; }
-                else for (int q = 0; q < 6; q++) f[40 + q] = h->m0ij[q];
-                f[46] = h->clon; f[47] = h->clat; f[48] = h->phi;
-                const float ddx = h->sx0 - h->xst[s], ddy = h->sy0 - h->yst[s];
-                f[50] = std::sqrt(ddx * ddx + ddy * ddy);
-                f[51] = rad2deg_s(std::atan2(h->yst[s] - h->sy0, h->xst[s] - h->sx0));
-                f[52] = rad2deg_s(std::atan2(h->sy0 - h->yst[s], h->sx0 - h->xst[s]));
-                if (prod < 2) {   // cmpaz / cmpinc only for the vector products (m_wav.f90:286-288, :297-299)
-                    f[57] = c == 0 ? 0.0f + h->phi : (c == 1 ? 90.0f + h->phi : 0.0f);
-                    f[58] = 90.0f;
-                }
-                iv[0] = g.tm_year + 1900; iv[1] = g.tm_yday + 1; iv[2] = g.tm_hour; iv[3] = g.tm_min; iv[4] = g.tm_sec; iv[5] = 0;
-                iv[6] = 6; iv[9] = h->ntw; iv[15] = 1; iv[16] = prod == 0 ? 7 : (prod == 1 ? 6 : 5);
-                lv[0] = 1; lv[2] = 1;
-                put_chars(a, h->stnm[s], 8);
-                std::string t = h->title;
-                t.erase(0, t.find_first_not_of(' ') == std::string::npos ? t.size() : t.find_first_not_of(' '));
-                put_chars(a + 8, t.substr(0, 16), 16);
-                put_chars(a + 160, cmpnm[prod][c], 8);
-                const std::string fn = dir + "/" + h->title + ".3d." + h->stnm[s] + "." + cmpnm[prod][c] + ".sac";
-                FILE *fp = std::fopen(fn.c_str(), "wb");
-                if (!fp) return hfail("cannot write " + fn);
-                std::fwrite(f, 4, 70, fp); std::fwrite(iv, 4, 35, fp); std::fwrite(lv, 4, 5, fp); std::fwrite(a, 1, 192, fp);
-                std::fwrite(h->wav_all[prod].data() + (size_t)h->ntw * ncmp * s + (size_t)h->ntw * c, 4, (size_t)h->ntw, fp);
-                std::fclose(fp);
-                count++;
-            }
+            FILE *fp = std::fopen(fn.c_str(), "wb");
+            if (!fp) return hfail("cannot write " + fn);
+            const int32_t ntrace = nst * ncmp, npts = h->ntw;
+            std::fwrite("CSFD", 1, 4, fp); std::fwrite(&ntrace, 4, 1, fp); std::fwrite(&npts, 4, 1, fp);
+            for (int s = 0; s < nst; s++)
+                for (int c = 0; c < ncmp; c++) { sac_record(s, prod, c, rec); std::fwrite(rec.data(), 1, rec.size(), fp); count++; }
+            std::fclose(fp);
         }
+    } else if (fmt == "tar_st" || fmt == "tar_node") {
+        // m_wav.f90:714-761 + sac__wtar m_sac.f90:812-829 + tar__whdr m_tar.f90:165-199 (ustar header, octal fields filling
+        // their width, no version digits, checksum over the block with the checksum field blank) + tar__wpad (:212-224, a full
+        // null block when the size is a multiple of 512) + tar__wend
+        static const char zeros[1024] = {0};
+        auto tar_member = [&](FILE *fp, const std::string &name, const std::vector<unsigned char> &body) {
+            char hd[513];
+            std::memset(hd, 0, sizeof(hd));
+            std::memcpy(hd, name.data(), std::min<size_t>(name.size(), 100));
+            char num[16];
+            std::snprintf(num, sizeof(num), "%08o", 420u); std::memcpy(hd + 100, num, 8);
+            std::snprintf(num, sizeof(num), "%08o", 0u); std::memcpy(hd + 108, num, 8); std::memcpy(hd + 116, num, 8);
+            std::snprintf(num, sizeof(num), "%012o", (unsigned)body.size()); std::memcpy(hd + 124, num, 12);
+            std::snprintf(num, sizeof(num), "%012o", (unsigned)h->exedate); std::memcpy(hd + 136, num, 12);
+            std::memset(hd + 148, ' ', 8);
+            hd[156] = '0';
+            std::memcpy(hd + 257, "ustar", 5);
+            std::memcpy(hd + 265, "root", 4);
+            std::memcpy(hd + 297, "root", 4);
+            unsigned sum = 0;
+            for (int q = 0; q < 512; q++) sum += (unsigned char)hd[q];
+            std::snprintf(num, sizeof(num), "%08o", sum); std::memcpy(hd + 148, num, 8);
+            std::fwrite(hd, 1, 512, fp);
+            std::fwrite(body.data(), 1, body.size(), fp);
+            std::fwrite(zeros, 1, 512 - body.size() % 512, fp);
+        };
+        FILE *fp = nullptr;
+        if (fmt == "tar_node") {
+            char cid[16];
+            std::snprintf(cid, sizeof(cid), "%06d", h->myid);
+            const std::string fn = dir + "/" + h->title + ".3d." + cid + ".sac.tar";
+            if (!(fp = std::fopen(fn.c_str(), "wb"))) return hfail("cannot write " + fn);
+        }
+        for (int s = 0; s < nst; s++) {
+            if (fmt == "tar_st") {
+                const std::string fn = dir + "/" + h->title + ".3d." + h->stnm[s] + ".sac.tar";
+                if (!(fp = std::fopen(fn.c_str(), "wb"))) return hfail("cannot write " + fn);
+            }
+            for (int prod = 0; prod < 4; prod++) {
+                if (!sw[prod]) continue;
+                for (int c = 0; c < (prod < 2 ? 3 : 6); c++) {
+                    sac_record(s, prod, c, rec);
+                    tar_member(fp, h->title + "." + h->stnm[s] + ".3d." + cmpnm[prod][c] + ".sac", rec);
+                    count++;
+                }
+            }
+            if (fmt == "tar_st") { std::fwrite(zeros, 1, 1024, fp); std::fclose(fp); fp = nullptr; }
+        }
+        if (fp) { std::fwrite(zeros, 1, 1024, fp); std::fclose(fp); }
+    }
     if (nfiles) *nfiles = count;
     return 0;
 }

@@ -65,6 +65,8 @@ void ora_visco_set_relaxtime(int nm, float *ts, float fmin, float fmax); /* m_fd
 float ora_visco_constq_zeta(int nm, float fmin, float fmax, const float *ts); /* :756-812 */
 void ora_fdm_stable_dt(float dx, float dy, float dz, float vmax, float *dt); /* :81-96 */
 float ora_moment_magnitude(float m0);                       /* m_fdtool.f90:281-293 */
+float ora_deg2rad(float deg);                                  /* m_std.f90:132-139 */
+float ora_powi_sp(float x, int m);                             /* real ** integer (libgcc __powisf2) */
 float ora_seismic_moment(float mw);                         /* m_fdtool.f90:296-304 */
 void ora_sdr2moment(float strike, float dip, float rake, float *mxx, float *myy, float *mzz,
                     float *myz, float *mxz, float *mxy);    /* m_fdtool.f90:307-336 */

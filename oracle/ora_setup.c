@@ -558,14 +558,101 @@ static void kernel_setup(ora_sim *s) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* pw_setup  m_source.f90:316-466: plane-wave initial condition over the whole memory box; no source grid afterwards */
+static int pw_setup(ora_sim *s, const ora_ini *ini) {
+    ora_cfg *c = &s->cfg;
+    float pw_ztop, pw_zlen, strike, dip, rake;
+    char ps[ORA_STRLEN], tmp[ORA_STRLEN];
+    ora_readini_s(ini, "pw_ztop", &pw_ztop, 1e30f);
+    if (!(pw_ztop < c->zend)) { set_err("assert: pw_ztop < zend (m_source.f90:332)"); return -1; }
+    ora_readini_s(ini, "pw_zlen", &pw_zlen, -1.0f);
+    if (!(pw_zlen > 0.0f)) { set_err("assert: pw_zlen > 0 (m_source.f90:335)"); return -1; }
+    ora_readini_c(ini, "pw_ps", ps, "");
+    const int is_p = (ps[0] == 'p' || ps[0] == 'P'), is_s = (ps[0] == 's' || ps[0] == 'S');
+    if (!(is_p || is_s) || ps[1]) { set_err("assert: pw_ps must be p or s (m_source.f90:338)"); return -1; }
+    ora_readini_s(ini, "pw_strike", &strike, 0.0f);
+    ora_readini_s(ini, "pw_dip", &dip, 0.0f);
+    ora_readini_s(ini, "pw_rake", &rake, 0.0f);
+    strike = ora_deg2rad(strike); dip = ora_deg2rad(dip); rake = ora_deg2rad(rake);
+    ora_readini_c(ini, "stftype", tmp, "kupper");
+    strncpy(c->stftype, tmp, sizeof(c->stftype) - 1);
+    const float sd = sinf(dip), cd = cosf(dip), sf = sinf(strike), cf = cosf(strike), sl = sinf(rake), cl = cosf(rake);
+    const float c2d = cosf(2 * dip), c2f = cosf(2 * strike);
+    const float prm[2] = {0.0f, pw_zlen};
+    const float dt = c->dt;
+    const ora_mp dx = c->dx, dy = c->dy, dz = c->dz;
+    const char *st = c->stftype;
+    float fcut = 0.0f;
+    for (int q = 0; q < s->nranks; q++) {
+        ora_rank *r = &s->r[q];
+        for (int j = r->jbeg_m; j <= r->jend_m; j++)
+            for (int i = r->ibeg_m; i <= r->iend_m; i++)
+                for (int k = r->kbeg_m; k <= r->kend_m; k++) {
+                    const size_t n = ora_idx3(r, k, i, j);
+                    const float la0 = r->lam[n], mu0 = r->mu[n];
+                    const float v = is_p ? sqrtf((la0 + 2 * mu0) / r->rho[n]) : sqrtf(mu0 / r->rho[n]);
+                    if (v < FLT_EPS) continue;
+                    const float x0 = (float)(c->xbeg + (i - 0.5f) * dx), y0 = (float)(c->ybeg + (j - 0.5f) * dy);
+                    const float z0 = (float)(c->zbeg + (k - 0.5f) * dz - pw_ztop);
+                    const float x1 = (float)(x0 + dx / 2.0f), y1 = (float)(y0 + dy / 2.0f), z1 = (float)(z0 + dz / 2.0f);
+                    const float a = sd * sf, b = sd * cf;
+                    const float stf_ii = ora_momentrate(a * x0 - b * y0 + cd * z0, st, prm);
+                    const float stf_vx = ora_momentrate(a * x1 - b * y0 + cd * z0 + dt / 2.0f * v, st, prm);
+                    const float stf_vy = ora_momentrate(a * x0 - b * y1 + cd * z0 + dt / 2.0f * v, st, prm);
+                    const float stf_vz = ora_momentrate(a * x0 - b * y0 + cd * z1 + dt / 2.0f * v, st, prm);
+                    const float stf_yz = ora_momentrate(a * x0 - b * y1 + cd * z1, st, prm);
+                    const float stf_xz = ora_momentrate(a * x1 - b * y0 + cd * z1, st, prm);
+                    const float stf_xy = ora_momentrate(a * x1 - b * y1 + cd * z0, st, prm);
+                    if (is_p) {
+                        r->Vx[n] = -sd * sf * stf_vx;
+                        r->Vy[n] = sd * cf * stf_vy;
+                        r->Vz[n] = -cd * stf_vz;
+                        r->Sxx[n] = -(la0 + 2 * mu0 * sd * sd * sf * sf) * stf_ii / v;
+                        r->Syy[n] = -(la0 + 2 * mu0 * sd * sd * cf * cf) * stf_ii / v;
+                        r->Szz[n] = -(la0 + 2 * mu0 * cd * cd) * stf_ii / v;
+                        r->Syz[n] = 2 * mu0 * sd * cd * cf * stf_yz / v;
+                        r->Sxz[n] = -(2 * mu0 * sd * cd * sf * stf_xz / v);
+                        r->Sxy[n] = 2 * mu0 * sd * cd * sf * stf_xy / v;
+                    } else {
+                        r->Vx[n] = (cl * cf + sl * cd * sf) * stf_vx;
+                        r->Vy[n] = (cl * sf - sl * cd * cf) * stf_vy;
+                        r->Vz[n] = -sl * sd * stf_vz;
+                        r->Sxx[n] = 2 * mu0 * sd * sf * (cl * cf + sl * cd * sf) * stf_ii / v;
+                        r->Syy[n] = -(2 * mu0 * sd * cf * (cl * sf - sl * cd * cf) * stf_ii / v);
+                        r->Szz[n] = -(2 * mu0 * cd * sl * sd * stf_ii / v);
+                        r->Syz[n] = mu0 * (cl * cd * sf - sl * c2d * cf) * stf_yz / v;
+                        r->Sxz[n] = mu0 * (cl * cd * cf + sl * c2d * sf) * stf_xz / v;
+                        r->Sxy[n] = -(mu0 * (cl * sd * c2f + 2 * sl * sd * cd * sf * cf) * stf_xy / v);
+                    }
+                }
+        /* wavelength condition :445-464 (MPI_MAX over the ranks) */
+        const int i = ora_x2i((c->xbeg + c->xend) / 2, c->xbeg, (float)c->dx), j = ora_x2i((c->ybeg + c->yend) / 2, c->ybeg, (float)c->dy);
+        const int k = ora_x2i(pw_ztop, c->zbeg, (float)c->dz);
+        if (r->ibeg <= i && i <= r->iend && r->jbeg <= j && j <= r->jend) {
+            const size_t n = ora_idx3(r, k, i, j);
+            const float v = is_p ? sqrtf((r->lam[n] + 2 * r->mu[n]) / r->rho[n]) : sqrtf(r->mu[n] / r->rho[n]);
+            if (v / pw_zlen > fcut) fcut = v / pw_zlen;
+        }
+        r->nsrc = 0;
+    }
+    c->fcut = fcut;
+    c->fmax = fcut * 2.0f;
+    c->M0 = 1.0f / c->UC; /* fictitious scalar moment for output :77 */
+    c->dt_dxyz = (ora_mp)c->dt / ((ora_mp)c->dx * (ora_mp)c->dy * (ora_mp)c->dz);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* m_source.f90:41-314 (+ grid_moment :468-700, grid_bodyforce :702-774)                        */
 static int source_setup(ora_sim *s, const ora_ini *ini, const char *base) {
     ora_cfg *c = &s->cfg;
     ora_readini_l(ini, "pw_mode", &c->pw_mode, 0);
     ora_readini_l(ini, "green_mode", &c->green_mode, 0);
     ora_readini_l(ini, "bf_mode", &c->bf_mode, 0);
-    if ((c->pw_mode || c->green_mode) && !c->benchmark_mode) {
-        set_err("pw_mode / green_mode are outside the hot-path scope");
+    if (c->pw_mode && c->green_mode) { set_err("assert: pw_mode and green_mode are exclusive (m_source.f90:70)"); return -1; }
+    if (c->pw_mode && !c->benchmark_mode) return pw_setup(s, ini); /* :73-82 */
+    if (c->green_mode && !c->benchmark_mode) {
+        set_err("green_mode is outside the hot-path scope");
         return -1;
     }
     char tmp[ORA_STRLEN];
@@ -641,11 +728,40 @@ static int source_setup(ora_sim *s, const ora_ini *ini, const char *base) {
             }
             int is_ll = (fmt[0] == 'l' && fmt[1] == 'l');
             int is_xy = (fmt[0] == 'x' && fmt[1] == 'y');
-            const char *kind = fmt + 2; /* m0ij m0dc mwij mwdc */
+            const char *kind = fmt + 2; /* m0ij m0dc mwij mwdc dsdc */
+            if (!strcmp(fmt, "psmeca")) { /* :641-666  lon lat z mzz mxx myy mxz myz mxy iex (dyn-cm, GMT psmeca order) */
+                if (nv < 10) { set_err("source file: bad psmeca record"); fclose(fp); return -1; }
+                sz[ns] = v[2];
+                M[2] = v[3]; M[0] = v[4]; M[1] = v[5]; M[4] = v[6]; M[3] = -v[7]; M[5] = -v[8];
+                int iex = (int)v[9];
+                ora_geomap_g2c(v[0], v[1], c->clon, c->clat, c->phi, &sx[ns], &sy[ns]);
+                float M0tmp = sqrtf(M[0] * M[0] + M[1] * M[1] + M[2] * M[2] + 2 * (M[4] * M[4] + M[3] * M[3] + M[5] * M[5])) / sqrtf(2.0f);
+                mo[ns] = M0tmp * ora_powi_sp(10.0f, iex);
+                p1[ns] = 0.0f;
+                p2[ns] = (float)((double)(2 * 1.05f * 1e-8f) * pow((double)mo[ns], 1.0 / 3.0));
+                mo[ns] = mo[ns] * 1e-7f;
+                M[0] = M[0] / M0tmp; M[1] = M[1] / M0tmp; M[2] = M[2] / M0tmp; M[4] = M[4] / M0tmp; M[3] = M[3] / M0tmp; M[5] = M[5] / M0tmp;
+            } else if ((is_ll || is_xy) && !strcmp(kind, "dsdc")) { /* :585-639  x y z tbeg trise D S strike dip rake */
+                if (nv < 10) { set_err("source file: bad dsdc record"); fclose(fp); return -1; }
+                if (is_xy) { sx[ns] = v[0]; sy[ns] = v[1]; }
+                else ora_geomap_g2c(v[0], v[1], c->clon, c->clat, c->phi, &sx[ns], &sy[ns]);
+                sz[ns] = v[2]; p1[ns] = v[3]; p2[ns] = v[4];
+                ora_sdr2moment(v[7] - c->phi, v[8], v[9], &M[0], &M[1], &M[2], &M[3], &M[4], &M[5]);
+                int is0 = ora_x2i(sx[ns], c->xbeg, (float)c->dx), js0 = ora_x2i(sy[ns], c->ybeg, (float)c->dy), ks0;
+                if (c->earth_flattening) ks0 = ora_x2i((float)(-ora_r_earth() * log((ora_r_earth() - (double)sz[ns]) / ora_r_earth())), c->zbeg, (float)c->dz);
+                else ks0 = ora_x2i(sz[ns], c->zbeg, (float)c->dz);
+                float best = 0.0f; /* mpi_allreduce(MAX) over the ranks :691-696 */
+                for (int q = 0; q < s->nranks; q++) {
+                    const ora_rank *r = &s->r[q];
+                    float m = 0.0f;
+                    if (r->ibeg - 2 <= is0 && is0 <= r->iend + 3 && r->jbeg - 2 <= js0 && js0 <= r->jend + 3 && r->kbeg - 2 <= ks0 && ks0 <= r->kend + 3)
+                        m = (1e9f * r->mu[ora_idx3(r, ks0, is0, js0)]) * v[5] * v[6];
+                    if (q == 0 || m > best) best = m;
+                }
+                mo[ns] = best;
+            } else {
             if (!(is_ll || is_xy) || !(!strcmp(kind, "m0ij") || !strcmp(kind, "m0dc") || !strcmp(kind, "mwij") || !strcmp(kind, "mwdc"))) {
-                char m[200];
-                snprintf(m, sizeof(m), "stf_format '%s' is outside the hot-path scope", fmt);
-                set_err(m); fclose(fp); return -1;
+                set_err("invalid source type"); fclose(fp); return -1; /* :668-670 */
             }
             int need = (kind[2] == 'i') ? 12 : 9;
             if (nv < need) { set_err("source file: bad moment record"); fclose(fp); return -1; }
@@ -655,6 +771,7 @@ static int source_setup(ora_sim *s, const ora_ini *ini, const char *base) {
             mo[ns] = (kind[1] == '0') ? v[5] : ora_seismic_moment(v[5]);
             if (kind[2] == 'i') { for (int q = 0; q < 6; q++) M[q] = v[6 + q]; }
             else ora_sdr2moment(v[6] - c->phi, v[7], v[8], &M[0], &M[1], &M[2], &M[3], &M[4], &M[5]);
+            }
             if (ns == 0) { /* :675-687 */
                 ora_geomap_c2g(sx[0], sy[0], c->clon, c->clat, c->phi, &c->evlo, &c->evla);
                 c->sx0 = sx[0]; c->sy0 = sy[0]; c->evdp = sz[0];

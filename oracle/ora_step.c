@@ -179,7 +179,28 @@ static void kernel_update_stress(const ora_cfg *c, ora_rank *r) {
 }
 
 /* ---------------------------------------------------------------------------------------- */
-/* absorb_p__update_vel  m_absorb_p.f90:246-317 (time-marching part; pw_mode edges not in scope) */
+/* Horizontal zero-derivative boundary of the plane-wave mode (m_absorb_p.f90:137-243 for the stresses, :332-424 for the
+ * velocities): linear extrapolation into the first plane outside the model on the outer ranks, owned rows only */
+static void pw_edges(const ora_cfg *c, ora_rank *r, ora_mp **f, int nf) {
+    for (int q = 0; q < nf; q++) {
+        ora_mp *a = f[q];
+        if (r->idx == 0)
+            for (int j = r->jbeg; j <= r->jend; j++)
+                for (int k = 1; k <= c->nz; k++) a[ora_idx3(r, k, 0, j)] = 2 * a[ora_idx3(r, k, 1, j)] - a[ora_idx3(r, k, 2, j)];
+        if (r->idx == c->nproc_x - 1)
+            for (int j = r->jbeg; j <= r->jend; j++)
+                for (int k = 1; k <= c->nz; k++) a[ora_idx3(r, k, c->nx + 1, j)] = 2 * a[ora_idx3(r, k, c->nx, j)] - a[ora_idx3(r, k, c->nx - 1, j)];
+        if (r->idy == 0)
+            for (int i = r->ibeg; i <= r->iend; i++)
+                for (int k = 1; k <= c->nz; k++) a[ora_idx3(r, k, i, 0)] = 2 * a[ora_idx3(r, k, i, 1)] - a[ora_idx3(r, k, i, 2)];
+        if (r->idy == c->nproc_y - 1)
+            for (int i = r->ibeg; i <= r->iend; i++)
+                for (int k = 1; k <= c->nz; k++) a[ora_idx3(r, k, i, c->ny + 1)] = 2 * a[ora_idx3(r, k, i, c->ny)] - a[ora_idx3(r, k, i, c->ny - 1)];
+    }
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* absorb_p__update_vel  m_absorb_p.f90:246-317 (time-marching part) */
 static void absorb_p_update_vel(const ora_cfg *c, ora_rank *r) {
     const ptrdiff_t si = r->nzm, sj = (ptrdiff_t)r->nzm * r->nxm;
     const float dt = c->dt;
@@ -343,6 +364,7 @@ void ora_update_stress(ora_sim *s) {
     int pml = !strcmp(s->cfg.abc_type, "pml");
     for (int q = 0; q < s->nranks; q++) {
         kernel_update_stress(&s->cfg, &s->r[q]);
+        if (pml && s->cfg.pw_mode) { ora_mp *f[3] = {s->r[q].Vx, s->r[q].Vy, s->r[q].Vz}; pw_edges(&s->cfg, &s->r[q], f, 3); }
         if (pml) absorb_p_update_stress(&s->cfg, &s->r[q]);
         else absorb_c_update_stress(&s->r[q]);
     }
@@ -352,6 +374,11 @@ void ora_update_vel(ora_sim *s) {
     int pml = !strcmp(s->cfg.abc_type, "pml");
     for (int q = 0; q < s->nranks; q++) {
         kernel_update_vel(&s->cfg, &s->r[q]);
+        if (pml && s->cfg.pw_mode) {
+            ora_rank *r = &s->r[q];
+            ora_mp *f[6] = {r->Sxx, r->Syy, r->Szz, r->Syz, r->Sxz, r->Sxy};
+            pw_edges(&s->cfg, r, f, 6);
+        }
         if (pml) absorb_p_update_vel(&s->cfg, &s->r[q]);
         else absorb_c_update_vel(&s->r[q]);
     }

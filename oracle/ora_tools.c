@@ -159,6 +159,16 @@ float ora_moment_magnitude(float m0) {
 }
 
 /* m_fdtool.f90:296-304 */
+/* real(SP) ** integer as gfortran evaluates it (libgcc __powisf2: square-and-multiply in float) */
+float ora_powi_sp(float x, int m) {
+    unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
+    float y = (n % 2) ? x : 1.0f;
+    while (n >>= 1) {
+        x = x * x;
+        if (n % 2) y *= x;
+    }
+    return m < 0 ? 1.0f / y : y;
+}
 float ora_seismic_moment(float mw) { return powf(10.0f, 1.5f * mw + 9.05f); }
 
 /* m_std.f90:132-139  d2r_s = real(PI / 180.0_SP * deg) */
@@ -166,6 +176,8 @@ static float d2r_s(float deg) { return (float)(ORA_PI / (double)180.0f * (double
 /* m_std.f90:152-159 */
 static float r2d_s(float rad) { return (float)((double)180.0f / ORA_PI * (double)rad); }
 float ora_rad2deg_s(float rad) { return r2d_s(rad); }
+
+float ora_deg2rad(float deg) { return d2r_s(deg); } /* std__deg2rad, m_std.f90:132-139 */
 
 /* m_fdtool.f90:307-336 */
 void ora_sdr2moment(float strike, float dip, float rake, float *mxx, float *myy, float *mzz,

@@ -27,7 +27,7 @@ LHM_LAND = """# depth rho vp vs Qp Qs
 
 def write_case(d: Path, *, nx=48, ny=40, nz=44, nt=40, dx=0.5, dy=0.5, dz=0.5, dt=0.02, na=6, nproc_x=1, nproc_y=1,
                abc_type="pml", vmodel="lhm_ocean", zbeg=-3.0, sources=None, stations=None, stftype="kupper",
-               stf_format="xym0ij", bf_mode=False, ntdec_w=2, ntdec_r=10, extra="", benchmark=False, title="case") -> Path:
+               stf_format="xym0ij", sdep_fit="asis", wav_format="sac", bf_mode=False, ntdec_w=2, ntdec_r=10, extra="", benchmark=False, title="case") -> Path:
     d = Path(d)
     d.mkdir(parents=True, exist_ok=True)
     xbeg, ybeg = -nx * dx / 2, -ny * dy / 2
@@ -73,11 +73,11 @@ def write_case(d: Path, *, nx=48, ny=40, nz=44, nt=40, dx=0.5, dy=0.5, dz=0.5, d
  ntdec_w = {ntdec_w}
  st_format = 'xy'
  fn_stloc = 'stloc.xy'
- wav_format = 'sac'
+ wav_format = '{wav_format}'
  stf_format = '{stf_format}'
  stftype = '{stftype}'
  fn_stf = "source.dat"
- sdep_fit = 'asis'
+ sdep_fit = '{sdep_fit}'
  bf_mode = {'.true.' if bf_mode else '.false.'}
  abc_type = '{abc_type}'
  na = {na}

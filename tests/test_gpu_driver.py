@@ -72,6 +72,49 @@ def test_all_station_products_sac(tmp_path):
     assert np.abs(run.array("wav_strain")).max() > 0 and np.abs(run.array("wav_u")).max() > 0
 
 
+@pytest.mark.parametrize("fmt", ["csf", "tar_st", "tar_node"])
+def test_waveform_containers(tmp_path, fmt):
+    """wav_format = csf / tar_st / tar_node (m_wav.f90:707-761): the containers hold the very SAC records of the sac format."""
+    import io
+    import struct
+    import tarfile
+
+    nt = 24
+    kw = dict(nt=nt, title="box", extra="sw_wav_u = .true.\n sw_wav_strain = .true." if fmt != "csf" else "")
+    o = Oracle(write_case(tmp_path / "o", **kw), base_dir=tmp_path / "o", nm=3)
+    o.lib.ora_set_exedate(o.h, 1_700_000_000, 540)
+    o.run(1, nt)
+    o.write_sac(tmp_path / "ref")
+    run = Swpc3d(write_case(tmp_path / "g", wav_format=fmt, **kw), base_dir=tmp_path / "g", nm=3)
+    run.set_exedate(1_700_000_000, 540)
+    run.attach_device(0)
+    run.run(1, nt)
+    nfiles = run.write_sac(tmp_path / "gpu")
+    names, nst, ntw = run.station_names(), run["nst"], run["ntw"]
+    ref = lambda st, cmp: (tmp_path / "ref" / "wav" / f"box.3d.{st}.{cmp}.sac").read_bytes()
+    cmps = ["Vx", "Vy", "Vz"] if fmt == "csf" else ["Vx", "Vy", "Vz", "Ux", "Uy", "Uz", "Exx", "Eyy", "Ezz", "Eyz", "Exz", "Exy"]
+    assert nfiles == nst * len(cmps)
+    if fmt == "csf":
+        raw = (tmp_path / "gpu" / "wav" / "box__00000__.csf").read_bytes()
+        assert raw == b"CSFD" + struct.pack("<ii", 3 * nst, ntw) + b"".join(ref(st, c) for st in names for c in cmps)
+        return
+    files = {"tar_node": ["box.3d.000000.sac.tar"], "tar_st": [f"box.3d.{st}.sac.tar" for st in names]}[fmt]
+    assert sorted(p.name for p in (tmp_path / "gpu" / "wav").iterdir()) == sorted(files)
+    for fn in files:
+        raw = (tmp_path / "gpu" / "wav" / fn).read_bytes()
+        sts = names if fmt == "tar_node" else [fn.split(".")[2]]
+        want = [(f"box.{st}.3d.{c}.sac", ref(st, c)) for st in sts for c in cmps]
+        with tarfile.open(fileobj=io.BytesIO(raw)) as tf:       # an independent reader accepts it (checksums included)
+            mem = tf.getmembers()
+            assert [m.name for m in mem] == [w[0] for w in want]
+            for m, w in zip(mem, want):
+                assert tf.extractfile(m).read() == w[1], m.name
+                assert m.mtime == 1_700_000_000 and m.mode == 0o644 and m.uname == "root"
+        blk = 512 + (632 + 4 * ntw + 511) // 512 * 512 + (512 if (632 + 4 * ntw) % 512 == 0 else 0)
+        assert len(raw) == blk * len(want) + 1024 and raw[-1024:] == bytes(1024)
+        assert raw[257:263] == b"ustar\0" and raw[263:265] == b"\0\0" and raw[100:108] == b"00000644"   # tar__whdr quirks
+
+
 def test_station_products_decomposed(tmp_path):
     """2x2 emulated ranks: the strain sampler reads corner halo cells that no exchange fills -- same on both sides."""
     import ctypes as C

@@ -47,7 +47,49 @@ def test_snapshot_subset_and_cerjan(tmp_path):
         check_file(tmp_path / "g" / f"sub.3d.{OL.SNAP_SECTIONS[sec]}.{OL.SNAP_TYPES[typ]}.nc", o, q, "sub", run["dt"], 5)
 
 
-def test_snapshot_native_format_refused(tmp_path):
-    inf = write_case(tmp_path, nt=4, extra="snp_format = 'native'\n xy_v%sw = .true.")
+def native_expected(o, q, title, exedate, dt, ntdec_s, na, dec, clon, clat, phi):
+    """write_snp_header (m_snap.f90:846-892) + medium arrays + records, from the oracle's slices"""
+    import struct
+
+    sec, typ = divmod(q, 3)
+    horiz = sec in (0, 3, 4)
+    n1, n2, nv = OL.snap_dims(o, q)
+    x, y, z = OL.snap_coords(o)
+    a1 = y if sec == 2 else x
+    a2 = z if sec in (1, 2) else y
+    e1 = dec[1] if sec == 2 else dec[0]
+    e2 = dec[2] if sec in (1, 2) else dec[1]
+    f32 = np.float32
+    b = b"STREAMIO" + b"SWPC_3D " + struct.pack("<i", 6) + title.ljust(80).encode() + struct.pack("<i", exedate)
+    b += OL.SNAP_SECTIONS[sec].encode() + [b"ps", b"v3", b"u3"][typ]
+    b += struct.pack("<ii", n1, n2) + np.array([a1[0], a2[0], a1[1] - a1[0], a2[1] - a2[0], f32(dt) * f32(ntdec_s)], dtype="<f4").tobytes()
+    b += struct.pack("<iiii", na // e1, na // e2, 6 if horiz else 3, nv)
+    b += np.array([clon, clat, phi, 1, 1, 1], dtype="<f4").tobytes()
+    for m in range(4 if horiz else 3):
+        b += OL.snap_medium(o, q, m).astype("<f4").tobytes()
+    recs, _ = OL.snap_records(o, q)
+    return b + recs.astype("<f4").tobytes()
+
+
+def test_native_snapshot_files(tmp_path):
+    nt, dec = 21, (2, 3, 2)
+    inf = write_case(tmp_path, nt=nt, title="nat", extra=snap_extra(*dec, 5).replace("'netcdf'", "'native'"))
+    o = Oracle(inf, base_dir=tmp_path, nm=3)
+    o.run(1, nt)
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    run.set_exedate(1_700_000_000, 540)
+    run.attach_device(0)
+    run.snap_open(tmp_path / "g")
+    run.run(1, nt)
+    run.snap_close()
+    for q in range(15):
+        sec, typ = divmod(q, 3)
+        got = (tmp_path / "g" / f"nat.3d.{OL.SNAP_SECTIONS[sec]}.{OL.SNAP_TYPES[typ]}.snp").read_bytes()
+        ref = native_expected(o, q, "nat", 1_700_000_000, run["dt"], 5, run["na"], dec, run["clon"], run["clat"], run["phi"])
+        assert got == ref, (q, len(got), len(ref))
+
+
+def test_unknown_snapshot_format_refused(tmp_path):
+    inf = write_case(tmp_path, nt=4, extra="snp_format = 'hdf5'\n xy_v%sw = .true.")
     with pytest.raises(Exception, match="snp_format"):
         Swpc3d(inf, base_dir=tmp_path, nm=3)

@@ -20,6 +20,10 @@ CASES = {
     "bodyforce": dict(bf_mode=True, sources=["0.3 -0.2 4.1 0.05 0.6 1e12 2e12 -3e12"]),
     "dc_sources": dict(stf_format="xym0dc", stftype="herrmann", sources=["1.3 -0.7 5.2 0.0 0.8 2e15 30.0 45.0 90.0", "-1.0 2.0 3.3 0.2 0.4 1e15 210 80 -170"]),
     "mw_sources": dict(stf_format="xymwij", stftype="texp", sources=["1.3 -0.7 5.2 0.0 0.8 4.5 0.7 -0.3 0.5 0.4 -0.6 0.8"]),
+    "dsdc_xy_2x2": dict(stf_format="xydsdc", nproc_x=2, nproc_y=2, sources=["1.3 -0.7 5.2 0.0 0.8 1.5 2.0e6 30.0 45.0 90.0", "-0.2 0.1 7.3 0.2 0.4 0.5 1e6 210 80 -170"]),
+    "dsdc_ll": dict(stf_format="lldsdc", sources=["139.77 35.73 5.2 0.0 0.8 1.5 2.0e6 30.0 45.0 90.0"]),
+    "psmeca": dict(stf_format="psmeca", sources=["139.765 35.715 5.0 1.21 -0.92 -0.29 0.56 -1.34 0.27 23", "139.75 35.70 6.5 -2.0 1.1 0.9 0.3 0.2 -0.7 22"]),
+    "sdep_fit_bd0": dict(sdep_fit="bd0", sources=["0.3 -0.2 9.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"]),
     "ll_sources": dict(stf_format="llm0ij", stftype="cosine", sources=["139.77 35.73 5.2 0.0 0.8 2e15 0.7 -0.3 0.5 0.4 -0.6 0.8"]),
 }
 
