@@ -154,6 +154,8 @@ struct swpc3d_handle {
     TmaMapsVel vmaps{};
     bool vtma_ok = false;
     int variant = 1;
+    int pw_mode = 0;   // plane-wave mode: edge extrapolation ahead of the PML sweeps
+    int zero_outer = 0;   // re-zero the outer halo planes at every exchange (see launch_halo)
     long long launches = 0;
     // per-kernel CUDA-event timing of the two sweeps (option "kernel_timing"): event pairs recorded on the launch
     // stream, read back after a synchronisation by swpc3d_get_info("ms_stress" / "ms_vel")
@@ -510,6 +512,8 @@ extern "C" int swpc3d_set_sources(swpc3d_handle *h, int32_t nsrc, const int32_t 
     std::vector<double> vmo((size_t)nsrc), mij(6 * (size_t)nsrc);
     for (int i = 0; i < nsrc; i++) {
         const int mi = isrc[i] - h->g.ibeg + HALO, mj = jsrc[i] - h->g.jbeg + HALO;
+        // a source stencil that reaches an outer halo plane: the reference re-zeroes that plane at every exchange
+        if (isrc[i] <= 1 || isrc[i] >= h->g.nx || jsrc[i] <= 1 || jsrc[i] >= h->g.ny) h->zero_outer = 1;
         // the reference keeps sources in the sleeve [ibeg-2, iend+3] (m_source.f90:209-211); the 4-node shear
         // stencil then touches mi-1 >= 0
         if (mi < 1 || mi >= h->NXM || mj < 1 || mj >= h->NYM || ksrc[i] < 1 - 2 + 1 || ksrc[i] > h->g.nz + 3)
@@ -723,6 +727,22 @@ static int launch_sweep(swpc3d_handle *h) {
             h->kev[w][1].push_back(b);
         }
         CK(cudaEventRecord(h->kev[w][0][h->kev_used[w]], h->st));
+    }
+    if (h->pw_mode && h->g.abc_type == SWPC3D_ABC_PML) {   // absorb_p__update_stress extrapolates V, absorb_p__update_vel the stresses
+        const swpc3d_grid &g = h->g;
+        const int idx = g.myid % g.nproc_x, idy = g.myid / g.nproc_x;
+        PwEdges e{};
+        for (int q = 0; q < 4; q++) e.dst[q] = -1;
+        const int mx = HALO + h->nxp, my = HALO + h->nyp;   // memory index of iend+1 / jend+1
+        if (idx == 0) { e.dst[0] = HALO - 1; e.s1[0] = HALO; e.s2[0] = HALO + 1; e.nrow[0] = h->nyp; }
+        if (idx == g.nproc_x - 1) { e.dst[1] = mx; e.s1[1] = mx - 1; e.s2[1] = mx - 2; e.nrow[1] = h->nyp; }
+        if (idy == 0) { e.dst[2] = HALO - 1; e.s1[2] = HALO; e.s2[2] = HALO + 1; e.nrow[2] = h->nxp; }
+        if (idy == g.nproc_y - 1) { e.dst[3] = my; e.s1[3] = my - 1; e.s2[3] = my - 2; e.nrow[3] = h->nxp; }
+        dim3 blk(32, 8, 1), grd((unsigned)((g.nz + 31) / 32), (unsigned)((std::max(h->nxp, h->nyp) + 7) / 8), 4);
+        F *base = (F *)h->Fall + (STRESS ? 0 : 3) * h->ncell;
+        pw_edge_kernel<F><<<grd, blk, 0, h->st>>>(base, h->ncell, STRESS ? 3 : 6, g.nz, h->NZP, h->NXM, e);
+        h->launches++;
+        CK(cudaGetLastError());
     }
     int rc = 0;
     if (STRESS) {
@@ -1084,12 +1104,16 @@ template <typename F>
 static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack) {
     const int nz = h->g.nz;
     for (int f = 0; f < 4; f++) {
-        if (h->nbr[f] < 0) continue;
+        // A face without a neighbour: the reference still unpacks its (all-zero) receive buffer into the outer halo
+        // planes (m_global.f90:458-488).  Those planes are zero anyway unless something else wrote them:
+        // the plane-wave initial condition / edge extrapolation, or a source stencil at the model edge.
+        const bool outer = h->nbr[f] < 0;
+        if (outer && (pack || !h->zero_outer)) continue;
         const bool xface = f < 2;
         const int nline = xface ? h->nyp : h->nxp;
         const PlaneList &pl = pack ? L.send[f] : L.recv[f];
         dim3 blk(128, 1, 1), grd((unsigned)((nz + 127) / 128), (unsigned)nline, (unsigned)pl.n);
-        F *buf = (F *)(pack ? h->sbuf[f] : h->rbuf[f]);
+        F *buf = outer ? nullptr : (F *)(pack ? h->sbuf[f] : h->rbuf[f]);
         if (xface) {
             if (pack) halo_kernel<F, true, true><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
             else halo_kernel<F, true, false><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
@@ -1111,9 +1135,10 @@ static int comm_exchange(swpc3d_handle *h, int which) {
     if (ready(h)) return 1;
     bool any = false;
     for (int f = 0; f < 4; f++) any |= (h->nbr[f] >= 0);
-    if (!any) return 0;   // all neighbours MPI_PROC_NULL: outer halos keep their zeros
-    if (!h->comm) return fail("swpc3d_comm_*: this rank has neighbours but swpc3d_comm_init was not called");
+    if (!any && !h->zero_outer) return 0;   // all neighbours MPI_PROC_NULL: outer halos keep their zeros
     const FaceLists L = face_lists(h, which);
+    if (!any) return h->fb == 8 ? launch_halo<double>(h, L, false) : launch_halo<float>(h, L, false);
+    if (!h->comm) return fail("swpc3d_comm_*: this rank has neighbours but swpc3d_comm_init was not called");
     if (h->fb == 8 ? launch_halo<double>(h, L, true) : launch_halo<float>(h, L, true)) return 1;
     const ncclDataType_t ty = h->fb == 8 ? ncclDouble : ncclFloat;
     NK(g_nccl.GroupStart());
@@ -1223,6 +1248,8 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "jlen")) { if (value < 1) return fail("jlen must be >= 1"); h->jlen = value; }
     else if (!strcmp(key, "pf")) { if (value < 0 || value > 8) return fail("pf must be 0..8"); h->pf = value; }
     else if (!strcmp(key, "variant")) h->variant = value;
+    else if (!strcmp(key, "pw_mode")) { h->pw_mode = value != 0; if (value) h->zero_outer = 1; }
+    else if (!strcmp(key, "zero_outer_halo")) h->zero_outer = value != 0;
     else if (!strcmp(key, "tma")) h->use_tma = value;
     else if (!strcmp(key, "side_streams")) h->use_side = value;
     else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }

@@ -193,6 +193,33 @@ float stable_dt(float dx, float dy, float dz, float vmax) {   // fdm_stable_dt :
     return cc * hh / vmax;
 }
 float moment_magnitude(float m0) { return m0 < EPS_SP ? -12345.0f : (std::log10(m0) - 9.1f) * 2.0f / 3.0f; }   // :281-293
+// source time functions, m_fdtool.f90:339-497 (PI is DP: the trigonometric ones are evaluated in double and rounded)
+float momentrate(float t, const std::string &stf, float ts, float tr) {
+    if (stf == "boxcar") return (ts <= t && t <= ts + tr) ? 1.0f / tr : 0.0f;
+    if (stf == "triangle") {
+        if (ts <= t && t <= ts + tr / 2) return 4 * (t - ts) / (tr * tr);
+        if (ts + tr / 2 < t && t <= ts + tr) return -4 * (t - ts - tr) / (tr * tr);
+        return 0.0f;
+    }
+    if (stf == "herrmann") {
+        const float t1 = ts + tr / 4, t2 = ts + 3 * tr / 4, tr3 = tr * tr * tr;
+        if (ts <= t && t < t1) return 16 * ((t - ts) * (t - ts)) / tr3;
+        if (t1 <= t && t < t2) return -2 * (8 * (t * t + tr * ts + ts * ts - t * tr - 2 * t * ts) + tr * tr) / tr3;
+        if (t2 <= t && t <= ts + tr) return 16 * ((ts + tr - t) * (ts + tr - t)) / tr3;
+        return 0.0f;
+    }
+    if (stf == "cosine") return (ts <= t && t <= ts + tr) ? (float)((1 - std::cos(2 * PI_D * (double)(t - ts) / (double)tr)) / (double)tr) : 0.0f;
+    if (stf == "texp") {
+        if (!(ts <= t)) return 0.0f;
+        const float tt = t - ts;
+        return (float)((2 * PI_D) * (2 * PI_D) * (double)tt / (double)(tr * tr) * std::exp(-2 * PI_D * (double)tt / (double)tr));
+    }
+    if (ts <= t && t <= ts + tr) {   // kupper, also the default branch (:494)
+        const double sn = std::sin(PI_D * (double)(t - ts) / (double)tr);
+        return (float)(3 * PI_D * (sn * sn * sn) / (double)(4 * tr));
+    }
+    return 0.0f;
+}
 float powi_sp(float x, int m) {   // real(SP) ** integer the way gfortran does it (libgcc __powisf2)
     unsigned n = m < 0 ? 0u - (unsigned)m : (unsigned)m;
     float y = (n % 2) ? x : 1.0f;
@@ -394,6 +421,8 @@ struct swpc3d_host {
     swpc3d_handle *dev = nullptr;
     struct SnapHost *snap = nullptr;       // snapshot products (m_snap.f90)
     int setup_snap(const IniFile &ini);
+    int setup_planewave(const IniFile &ini);
+    std::vector<double> pw_init[9];        // plane-wave initial fields Vx Vy Vz Sxx Syy Szz Syz Sxz Sxy over the memory box
     int snap_open_files(const std::string &dir);
     int snap_write(int it);
     int snap_close();
@@ -654,11 +683,81 @@ void swpc3d_host::setup_kernel() {   // m_kernel.f90:58-67 (the device computes 
     }
 }
 
+// pw_setup, m_source.f90:316-466: plane P / S wave as the initial condition of all nine fields over the whole memory
+// box; no source grid afterwards, M0 = 1/UC
+int swpc3d_host::setup_planewave(const IniFile &ini) {
+    const float pw_ztop = ini.get_s("pw_ztop", 1e30f);
+    if (!(pw_ztop < zend)) return hfail("assert: pw_ztop < zend (m_source.f90:332)");
+    const float pw_zlen = ini.get_s("pw_zlen", -1.0f);
+    if (!(pw_zlen > 0.0f)) return hfail("assert: pw_zlen > 0 (m_source.f90:335)");
+    const std::string ps = ini.get("pw_ps", "");
+    const bool is_p = ps == "p" || ps == "P", is_s = ps == "s" || ps == "S";
+    if (!(is_p || is_s)) return hfail("assert: pw_ps must be 'p' or 's' (m_source.f90:338)");
+    const float strike = deg2rad_s(ini.get_s("pw_strike", 0.0f)), dip = deg2rad_s(ini.get_s("pw_dip", 0.0f)), rake = deg2rad_s(ini.get_s("pw_rake", 0.0f));
+    stftype = ini.get("stftype", "kupper");
+    const float sd = std::sin(dip), cd = std::cos(dip), sf = std::sin(strike), cf = std::cos(strike), sl = std::sin(rake), cl = std::cos(rake);
+    const float c2d = std::cos(2 * dip), c2f = std::cos(2 * strike);
+    const size_t nc = (size_t)nzm * nxm * nym;
+    for (auto &a : pw_init) a.assign(nc, 0.0);
+    const bool sp = field_bytes == 4;   // MP = SP: dx, dy, dz are single there
+    auto coord = [&](float beg, int i, double d, float sub) {
+        return sp ? (beg + ((float)i - 0.5f) * (float)d) - sub : (float)(((double)beg + (double)((float)i - 0.5f) * d) - (double)sub);
+    };
+    auto half = [&](float x, double d) { return sp ? x + (float)d / 2.0f : (float)((double)x + d / 2.0); };
+    const float a = sd * sf, b = sd * cf;
+    for (int j = jbeg - 3; j <= jend + 3 + jpad; j++)
+        for (int i = ibeg - 3; i <= iend + 3 + ipad; i++)
+            for (int k = kbeg_m; k < kbeg_m + nzm; k++) {
+                const size_t n = i3(k, i, j);
+                const float la0 = lam[n], mu0 = mu[n];
+                const float v = is_p ? std::sqrt((la0 + 2 * mu0) / rho[n]) : std::sqrt(mu0 / rho[n]);
+                if (v < EPS_SP) continue;
+                const float x0 = coord(xbeg, i, dx, 0.0f), y0 = coord(ybeg, j, dy, 0.0f), z0 = coord(zbeg, k, dz, pw_ztop);
+                const float x1 = half(x0, dx), y1 = half(y0, dy), z1 = half(z0, dz);
+                const float stf_ii = momentrate(a * x0 - b * y0 + cd * z0, stftype, 0.0f, pw_zlen);
+                const float stf_vx = momentrate(a * x1 - b * y0 + cd * z0 + dt / 2.0f * v, stftype, 0.0f, pw_zlen);
+                const float stf_vy = momentrate(a * x0 - b * y1 + cd * z0 + dt / 2.0f * v, stftype, 0.0f, pw_zlen);
+                const float stf_vz = momentrate(a * x0 - b * y0 + cd * z1 + dt / 2.0f * v, stftype, 0.0f, pw_zlen);
+                const float stf_yz = momentrate(a * x0 - b * y1 + cd * z1, stftype, 0.0f, pw_zlen);
+                const float stf_xz = momentrate(a * x1 - b * y0 + cd * z1, stftype, 0.0f, pw_zlen);
+                const float stf_xy = momentrate(a * x1 - b * y1 + cd * z0, stftype, 0.0f, pw_zlen);
+                float f[9];
+                if (is_p) {
+                    f[0] = -sd * sf * stf_vx; f[1] = sd * cf * stf_vy; f[2] = -cd * stf_vz;
+                    f[3] = -(la0 + 2 * mu0 * sd * sd * sf * sf) * stf_ii / v;
+                    f[4] = -(la0 + 2 * mu0 * sd * sd * cf * cf) * stf_ii / v;
+                    f[5] = -(la0 + 2 * mu0 * cd * cd) * stf_ii / v;
+                    f[6] = 2 * mu0 * sd * cd * cf * stf_yz / v;
+                    f[7] = -(2 * mu0 * sd * cd * sf * stf_xz / v);
+                    f[8] = 2 * mu0 * sd * cd * sf * stf_xy / v;
+                } else {
+                    f[0] = (cl * cf + sl * cd * sf) * stf_vx; f[1] = (cl * sf - sl * cd * cf) * stf_vy; f[2] = -sl * sd * stf_vz;
+                    f[3] = 2 * mu0 * sd * sf * (cl * cf + sl * cd * sf) * stf_ii / v;
+                    f[4] = -(2 * mu0 * sd * cf * (cl * sf - sl * cd * cf) * stf_ii / v);
+                    f[5] = -(2 * mu0 * cd * sl * sd * stf_ii / v);
+                    f[6] = mu0 * (cl * cd * sf - sl * c2d * cf) * stf_yz / v;
+                    f[7] = mu0 * (cl * cd * cf + sl * c2d * sf) * stf_xz / v;
+                    f[8] = -(mu0 * (cl * sd * c2f + 2 * sl * sd * cd * sf * cf) * stf_xy / v);
+                }
+                for (int q = 0; q < 9; q++) pw_init[q][n] = (double)f[q];
+            }
+    // wavelength condition :445-464; the MPI_MAX over the ranks is trivial here: the medium is laterally uniform
+    const int kk = x2i(pw_ztop, zbeg, (float)dz);
+    const size_t n = i3(kk, ibeg, jbeg);
+    fcut = (is_p ? std::sqrt((lam[n] + 2 * mu[n]) / rho[n]) : std::sqrt(mu[n] / rho[n])) / pw_zlen;
+    fmax = fcut * 2.0f;
+    M0 = 1.0f / UC;   // fictitious scalar moment for output :77
+    src_ijk.clear(); mo.clear(); mij.clear(); srcprm.clear();
+    return 0;
+}
+
 int swpc3d_host::setup_source(const IniFile &ini) {   // m_source.f90:41-314
     pw_mode = ini.get_l("pw_mode", false);
     green_mode = ini.get_l("green_mode", false);
     bf_mode = ini.get_l("bf_mode", false);
-    if ((pw_mode || green_mode) && !benchmark_mode) return hfail("pw_mode / green_mode are outside the hot-path scope of this build");
+    if (pw_mode && green_mode) return hfail("assert: pw_mode and green_mode are exclusive (m_source.f90:70)");
+    if (pw_mode && !benchmark_mode) return setup_planewave(ini);   // :73-82
+    if (green_mode && !benchmark_mode) return hfail("green_mode is outside the hot-path scope of this build");
     fn_stf = ini.get("fn_stf", "");
     stftype = ini.get("stftype", "kupper");
     if (stftype == "scosine") stftype = "cosine";
@@ -1324,6 +1423,8 @@ int swpc3d_host_get_array(swpc3d_host *h, const char *name, void *out, int64_t c
     if (s == "wav_stress") return put(h->wav_all[2], out, cap, n);
     if (s == "wav_strain") return put(h->wav_all[3], out, cap, n);
 #undef GA
+    static const char *fn[9] = {"init_Vx", "init_Vy", "init_Vz", "init_Sxx", "init_Syy", "init_Szz", "init_Syz", "init_Sxz", "init_Sxy"};
+    for (int q = 0; q < 9; q++) if (s == fn[q]) return put(h->pw_init[q], out, cap, n);   // plane-wave initial condition (pw_mode)
     if (s == "gx_c") return put(h->cgx_c, out, cap, n);
     if (s == "gx_b") return put(h->cgx_b, out, cap, n);
     if (s == "gy_c") return put(h->cgy_c, out, cap, n);
@@ -1371,6 +1472,16 @@ int swpc3d_host_attach_device(swpc3d_host *h, int32_t device) {
         }
         DV(swpc3d_set_sources(h->dev, nsrc, a.data(), b.data(), c.data(), h->mo.data(), m[0].data(), m[1].data(), m[2].data(), m[3].data(),
                               m[4].data(), m[5].data(), h->srcprm.data(), h->stftype.c_str(), h->bf_mode ? 1 : 0, h->tbeg));
+    }
+    if (h->pw_mode && !h->pw_init[0].empty()) {   // `!$acc enter data copyin(Vx..Sxy)` with the plane-wave initial condition
+        const void *f[9];
+        std::vector<float> f32[9];
+        for (int q = 0; q < 9; q++) {
+            if (h->field_bytes == 4) { f32[q].assign(h->pw_init[q].begin(), h->pw_init[q].end()); f[q] = f32[q].data(); }
+            else f[q] = h->pw_init[q].data();
+        }
+        DV(swpc3d_upload_fields(h->dev, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8]));
+        DV(swpc3d_set_option(h->dev, "pw_mode", 1));
     }
     const int nst = (int)(h->st_ijk.size() / 3);
     if (nst > 0 && (h->sw_wav_v || h->sw_wav_u || h->sw_wav_stress || h->sw_wav_strain)) {

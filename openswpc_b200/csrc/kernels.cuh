@@ -710,7 +710,31 @@ __global__ void halo_kernel(int nz, int nline, int NZP, int NXM, const PlaneList
     const long long n = (long long)(k + KOFF) + (long long)NZP * col;
     const long long b = (long long)s * nline * nz + (long long)line * nz + k;
     if (PACK) buf[b] = f[n];
-    else f[n] = buf[b];
+    else f[n] = buf ? buf[b] : F(0);   // no buffer: the never-written, zero-initialised rbuf of an MPI_PROC_NULL neighbour
+}
+
+// ------------------------------------------------------------------------------------------------
+// Plane-wave mode: horizontal zero-derivative boundary (m_absorb_p.f90:137-243 / :332-424).  Linear extrapolation into
+// the first plane outside the model on the outer ranks, owned rows and k = 1..nz only.  blockIdx.z = edge
+// (0: i=0, 1: i=nx+1, 2: j=0, 3: j=ny+1); `dst/s1/s2[e]` are memory-box indices along the edge's normal, < 0 = edge off.
+struct PwEdges { int dst[4], s1[4], s2[4]; int nrow[4]; };
+
+template <typename F>
+__global__ void pw_edge_kernel(F *fields, long long ncell, int nf, int nz, int NZP, int NXM, PwEdges e) {
+    const int edge = blockIdx.z;
+    if (e.dst[edge] < 0) return;
+    const int k = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (k > nz || r >= e.nrow[edge]) return;
+    const long long SI = NZP, SJ = (long long)NZP * NXM;
+    const long long kk = k + KOFF - 1;
+    long long d, a, b;
+    if (edge < 2) { const long long row = (long long)(r + HALO) * SJ + kk; d = row + e.dst[edge] * SI; a = row + e.s1[edge] * SI; b = row + e.s2[edge] * SI; }
+    else { const long long row = (long long)(r + HALO) * SI + kk; d = row + e.dst[edge] * SJ; a = row + e.s1[edge] * SJ; b = row + e.s2[edge] * SJ; }
+    for (int q = 0; q < nf; q++) {
+        F *f = fields + (long long)q * ncell;
+        f[d] = 2 * f[a] - f[b];
+    }
 }
 
 }   // namespace swpc

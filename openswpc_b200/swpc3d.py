@@ -26,7 +26,7 @@ _STRS = {"title", "odir", "abc_type", "stftype", "vmodel_type", "stf_format", "w
 _F32 = {"rho", "lam", "mu", "taup", "taus", "gxc", "gxe", "gyc", "gye", "gzc", "gze", "gx_c", "gx_b", "gy_c", "gy_b", "gz_c", "gz_b",
         "ts", "c1", "c2", "d1", "srcprm", "xc", "yc", "zc", "stlo", "stla", "wav", "wav_u", "wav_stress", "wav_strain"}
 _I32 = {"kfs", "kob", "kfs_top", "kfs_bot", "kob_top", "kob_bot", "kbeg_a", "src_ijk", "st_ijk"}
-_F64 = {"mo", "mij"}
+_F64 = {"mo", "mij"} | {"init_" + f for f in ("Vx", "Vy", "Vz", "Sxx", "Syy", "Szz", "Syz", "Sxz", "Sxy")}
 
 _bound = False
 
@@ -118,7 +118,7 @@ class Swpc3d:
         if n.value:
             self._ck(self.lib.swpc3d_host_get_array(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         nym, nxm, nzm = self["nym"], self["nxm"], self["nzm"]
-        if name in ("rho", "lam", "mu", "taup", "taus"):
+        if name in ("rho", "lam", "mu", "taup", "taus") or (name.startswith("init_") and n.value):
             return out.reshape(nym, nxm, nzm)
         if name in ("kfs", "kob", "kfs_top", "kfs_bot", "kob_top", "kob_bot", "kbeg_a"):
             return out.reshape(nym, nxm)

@@ -36,6 +36,23 @@ def test_driver_sac_matches_oracle(tmp_path, case):
         np.testing.assert_array_equal(w, o.wav(0))
 
 
+def test_source_on_the_model_edge(tmp_path):
+    """A stress-glut stencil at i = 1, j = ny reaches the outer halo planes; the reference zeroes them again at every exchange
+    (unconditional unpack of the never-received buffers, m_global.f90:458-488): the whole memory box must agree."""
+    nt = 12
+    inf = write_case(tmp_path, nt=nt, sources=["-11.9 9.9 4.1 0.0 0.3 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
+    o = Oracle(inf, base_dir=tmp_path, nm=3)
+    o.run(1, nt)
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    assert run.array("src_ijk").tolist() == [[1, 40, 15]]
+    run.attach_device(0)
+    run.run(1, nt)
+    got, nz = run.download_fields(), run["nz"]
+    for f, a in got.items():
+        np.testing.assert_array_equal(a[:, :, 3:3 + nz], o.field(0, f)[:, :, 3:3 + nz], err_msg=f)
+    assert np.abs(got["Sxy"]).max() > 0
+
+
 def test_sac_header_fields(tmp_path):
     inf = write_case(tmp_path, nt=20, title="hdrtest")
     run = Swpc3d(inf, base_dir=tmp_path, nm=3)
