@@ -39,7 +39,19 @@ module m_swpc3d_b200
     public :: swpc3d_update_vel, swpc3d_bodyforce, swpc3d_comm_vel
     public :: swpc3d_wav_store, swpc3d_step, swpc3d_sync, swpc3d_vmax, swpc3d_vmax_global, swpc3d_get_wav
     public :: swpc3d_nccl_unique_id, swpc3d_comm_init, swpc3d_last_error
+    public :: swpc3d_set_wav_products, swpc3d_get_wav_product, swpc3d_set_option
+    public :: swpc3d_snap_cfg, swpc3d_snap_setup, swpc3d_snap_step, swpc3d_snap_fetch, swpc3d_snap_fetch_max, swpc3d_reduce_sum
     public :: swpc3d_check
+
+    !! mirrors `swpc3d_snap_cfg` of include/swpc3d_b200.h: the integers snap__setup computes (m_snap.f90:116-154)
+    type, bind(c) :: swpc3d_snap_cfg
+        integer(c_int32_t) :: idec, jdec, kdec, ntdec_s
+        integer(c_int32_t) :: nxs, nys, nzs
+        integer(c_int32_t) :: is0, is1, js0, js1, ks0, ks1
+        integer(c_int32_t) :: k0_xy, i0_yz, j0_xz
+        integer(c_int32_t) :: sw(15)          !! xy_ps xy_v xy_u xz_ps xz_v xz_u yz_ps yz_v yz_u fs_ps fs_v fs_u ob_ps ob_v ob_u
+        real(c_float) :: M0, UC
+    end type swpc3d_snap_cfg
 
     interface
 
@@ -181,6 +193,59 @@ module m_swpc3d_b200
             type(c_ptr), value :: h
             character(kind=c_char), intent(in) :: id(128)
             integer(c_int32_t), value :: nranks, rank
+        end function
+
+        !! wav__setup switches sw_wav_v/u/stress/strain (m_wav.f90:74-77) and the `update self(wav_*)` of wav__write (:672-675);
+        !! which = 0 velocity (ntw,3,nst), 1 displacement (ntw,3,nst), 2 stress (ntw,6,nst), 3 strain (ntw,6,nst)
+        integer(c_int) function swpc3d_set_wav_products(h, sw_v, sw_u, sw_stress, sw_strain) bind(c, name='swpc3d_set_wav_products')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: sw_v, sw_u, sw_stress, sw_strain
+        end function
+        integer(c_int) function swpc3d_get_wav_product(h, which, buf) bind(c, name='swpc3d_get_wav_product')
+            import :: c_int, c_int32_t, c_float, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: which
+            real(c_float), intent(out) :: buf(*)
+        end function
+
+        !! snap__write on the device (m_snap.f90:919-948) and the reductions onto the I/O rank (:1053-1066, :2295-2305)
+        integer(c_int) function swpc3d_snap_setup(h, cfg) bind(c, name='swpc3d_snap_setup')
+            import :: c_int, c_ptr, swpc3d_snap_cfg
+            type(c_ptr), value :: h
+            type(swpc3d_snap_cfg), intent(in) :: cfg
+        end function
+        integer(c_int) function swpc3d_snap_step(h, it) bind(c, name='swpc3d_snap_step')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_snap_fetch(h, product, root, rbuf) bind(c, name='swpc3d_snap_fetch')
+            import :: c_int, c_int32_t, c_float, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: product, root      !! product = 3*section + type, 0-based, order of cfg%sw
+            real(c_float), intent(out) :: rbuf(*)           !! (n1, n2, nvar) on the root
+        end function
+        integer(c_int) function swpc3d_snap_fetch_max(h, product, root, rbuf) bind(c, name='swpc3d_snap_fetch_max')
+            import :: c_int, c_int32_t, c_float, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: product, root
+            real(c_float), intent(out) :: rbuf(*)           !! (nxs, nys, 3): max-V, max-H, max-A
+        end function
+        integer(c_int) function swpc3d_reduce_sum(h, buf, n, root) bind(c, name='swpc3d_reduce_sum')
+            import :: c_int, c_int32_t, c_int64_t, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(inout) :: buf(*)
+            integer(c_int64_t), value :: n
+            integer(c_int32_t), value :: root
+        end function
+
+        !! tuning / modes: key is a null-terminated name ("pw_mode", "tma", "jlen", ...)
+        integer(c_int) function swpc3d_set_option(h, key, value) bind(c, name='swpc3d_set_option')
+            import :: c_int, c_int32_t, c_char, c_ptr
+            type(c_ptr), value :: h
+            character(kind=c_char), intent(in) :: key(*)
+            integer(c_int32_t), value :: value
         end function
 
     end interface
