@@ -21,9 +21,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 def build(fmad: bool = False, force: bool = False, verbose: bool = False) -> Path:
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [CSRC / "abi.cu", CSRC / "host" / "driver.cpp"]
+    srcs = [CSRC / "abi.cu", CSRC / "psv_abi.cu", CSRC / "host" / "driver.cpp", CSRC / "host" / "psv_driver.cpp"]
     srcs = [s for s in srcs if s.exists()]
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((CSRC / "host").glob("*")) + [ROOT / "include" / "swpc3d_b200.h"]
+    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list((CSRC / "host").glob("*")) + [ROOT / "include" / "swpc3d_b200.h", ROOT / "include" / "swpcpsv_b200.h"]
     if LIB_PATH.exists() and not force:
         t = LIB_PATH.stat().st_mtime
         if all(d.stat().st_mtime <= t for d in deps if d.exists()):
@@ -44,6 +44,22 @@ class Grid(C.Structure):
         "ibeg_k", "iend_k", "jbeg_k", "jend_k", "kbeg_k", "kend_k", "na", "nm", "abc_type", "field_bytes", "device",
         "reserved")] + [("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("dt", C.c_float), ("reserved_f", C.c_float)]
 
+
+class PsvGrid(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "nx", "nz", "nproc_x", "myid", "ibeg", "iend", "ipad", "kpad", "ibeg_k", "iend_k", "kend_k", "na", "nm", "abc_type",
+        "field_bytes", "device")] + [("dx", C.c_double), ("dz", C.c_double), ("dt", C.c_float), ("reserved_f", C.c_float)]
+
+
+# every symbol include/swpcpsv_b200.h declares
+PSV_SYMBOLS = [
+    "swpcpsv_last_error", "swpcpsv_version", "swpcpsv_create", "swpcpsv_destroy", "swpcpsv_upload_medium", "swpcpsv_upload_fields",
+    "swpcpsv_download_fields", "swpcpsv_download_memvars", "swpcpsv_zero_state", "swpcpsv_setup_pml", "swpcpsv_setup_cerjan",
+    "swpcpsv_set_sources", "swpcpsv_set_stations", "swpcpsv_get_wav", "swpcpsv_update_stress", "swpcpsv_stressglut",
+    "swpcpsv_comm_stress", "swpcpsv_update_vel", "swpcpsv_comm_vel", "swpcpsv_wav_store", "swpcpsv_step", "swpcpsv_run",
+    "swpcpsv_sync", "swpcpsv_vmax", "swpcpsv_vmax_global", "swpcpsv_nccl_unique_id", "swpcpsv_comm_init", "swpcpsv_comm_local",
+    "swpcpsv_timer_start", "swpcpsv_timer_stop", "swpcpsv_set_option", "swpcpsv_get_info",
+]
 
 # every symbol include/swpc3d_b200.h declares
 SYMBOLS = [
@@ -103,6 +119,36 @@ def load() -> C.CDLL:
     for s in SYMBOLS:
         if s not in ("swpc3d_last_error", "swpc3d_version"):
             getattr(lib, s).restype = C.c_int
+    # ---- swpc_psv (include/swpcpsv_b200.h)
+    lib.swpcpsv_last_error.restype = cp
+    lib.swpcpsv_version.restype = cp
+    lib.swpcpsv_create.argtypes = [C.POINTER(PsvGrid), fp, C.POINTER(vp)]
+    lib.swpcpsv_destroy.argtypes = [vp]
+    lib.swpcpsv_upload_medium.argtypes = [vp] + [fp] * 5 + [ip] * 7
+    lib.swpcpsv_upload_fields.argtypes = [vp] + [vp] * 5
+    lib.swpcpsv_download_fields.argtypes = [vp] + [vp] * 5
+    lib.swpcpsv_download_memvars.argtypes = [vp, fp, fp, fp]
+    lib.swpcpsv_setup_pml.argtypes = [vp] + [fp] * 4
+    lib.swpcpsv_setup_cerjan.argtypes = [vp] + [fp] * 4
+    lib.swpcpsv_set_sources.argtypes = [vp, i32, ip, ip] + [dp] * 4 + [fp, cp, i32, C.c_float]
+    lib.swpcpsv_set_stations.argtypes = [vp, i32, ip, ip, i32, i32, C.c_float, C.c_float, i32, i32, i32, i32]
+    lib.swpcpsv_get_wav.argtypes = [vp, i32, fp]
+    for f in ("swpcpsv_zero_state", "swpcpsv_update_stress", "swpcpsv_comm_stress", "swpcpsv_comm_vel", "swpcpsv_sync", "swpcpsv_timer_start"):
+        getattr(lib, f).argtypes = [vp]
+    for f in ("swpcpsv_stressglut", "swpcpsv_update_vel", "swpcpsv_wav_store", "swpcpsv_step"):
+        getattr(lib, f).argtypes = [vp, i32]
+    lib.swpcpsv_run.argtypes = [vp, i32, i32]
+    lib.swpcpsv_vmax.argtypes = [vp, fp]
+    lib.swpcpsv_vmax_global.argtypes = [vp, fp]
+    lib.swpcpsv_nccl_unique_id.argtypes = [C.c_char_p]
+    lib.swpcpsv_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
+    lib.swpcpsv_comm_local.argtypes = [C.POINTER(vp), i32, i32]
+    lib.swpcpsv_timer_stop.argtypes = [vp, fp]
+    lib.swpcpsv_set_option.argtypes = [vp, cp, i32]
+    lib.swpcpsv_get_info.argtypes = [vp, cp, dp]
+    for s in PSV_SYMBOLS:
+        if s not in ("swpcpsv_last_error", "swpcpsv_version"):
+            getattr(lib, s).restype = C.c_int
     _lib = lib
     return lib
 
@@ -114,3 +160,8 @@ class Swpc3dError(RuntimeError):
 def check(rc: int) -> None:
     if rc != 0:
         raise Swpc3dError(load().swpc3d_last_error().decode())
+
+
+def check_psv(rc: int) -> None:
+    if rc != 0:
+        raise Swpc3dError(load().swpcpsv_last_error().decode())

@@ -319,7 +319,7 @@ struct AccVelDirect {
 };
 
 template <typename F, typename A>
-__device__ __forceinline__ void vel_interior_t(const KParams<F> &p, const A &a, int k, int mi, int mj, const int4 bnd) {
+__device__ __forceinline__ void vel_interior_calc(const KParams<F> &p, const A &a, int k, int mi, int mj, const int4 bnd, F &vx, F &vy, F &vz) {
     const int o = fd_order_sel(k, bnd);
     const F re40x = p.r40x[o], re41x = p.r41x[o], re40y = p.r40y[o], re41y = p.r41y[o], re40z = p.r40z[o], re41z = p.r41z[o];
     const float dt = p.dt;
@@ -336,9 +336,9 @@ __device__ __forceinline__ void vel_interior_t(const KParams<F> &p, const A &a, 
                     (a.template S<2, 1, 0, 0>() - a.template S<2, 0, 0, 0>()) * re40z - (a.template S<2, 2, 0, 0>() - a.template S<2, -1, 0, 0>()) * re41z;
 
     const float rho0 = a.template rho<0, 0, 0>();
-    F vx = a.V(0) + 2.0f / (rho0 + a.template rho<0, 1, 0>()) * d3Sx3 * dt;
-    F vy = a.V(1) + 2.0f / (rho0 + a.template rho<0, 0, 1>()) * d3Sy3 * dt;
-    F vz = a.V(2) + 2.0f / (rho0 + a.template rho<1, 0, 0>()) * d3Sz3 * dt;
+    vx = a.V(0) + 2.0f / (rho0 + a.template rho<0, 1, 0>()) * d3Sx3 * dt;
+    vy = a.V(1) + 2.0f / (rho0 + a.template rho<0, 0, 1>()) * d3Sy3 * dt;
+    vz = a.V(2) + 2.0f / (rho0 + a.template rho<1, 0, 0>()) * d3Sz3 * dt;
     if (p.abc == 2) {
         const int kk = k + KOFF - 1;
         const float gxc = p.cgx_c[mi], gxb = p.cgx_b[mi], gyc = p.cgy_c[mj], gyb = p.cgy_b[mj], gzc = p.cgz_c[kk], gzb = p.cgz_b[kk];
@@ -346,6 +346,12 @@ __device__ __forceinline__ void vel_interior_t(const KParams<F> &p, const A &a, 
         vy = vy * gxc * gyb * gzc;
         vz = vz * gxc * gyc * gzb;
     }
+}
+
+template <typename F, typename A>
+__device__ __forceinline__ void vel_interior_t(const KParams<F> &p, const A &a, int k, int mi, int mj, const int4 bnd) {
+    F vx, vy, vz;
+    vel_interior_calc<F, A>(p, a, k, mi, mj, bnd, vx, vy, vz);
     a.setV(0, vx); a.setV(1, vy); a.setV(2, vz);
 }
 
@@ -477,6 +483,55 @@ __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_cons
             const int4 bnd = p.band[col];
             if (STRESS) stress_interior<F, NM>(p, n, k, mi, mj, bnd);
             else vel_interior<F>(p, n, k, mi, mj, bnd);
+        }
+    }
+}
+
+// Velocity sweep over interior cells only, NC cells per thread (columns li, li+TI, ...) per plane.  The velocity update
+// streams only ~100 B per cell, so one cell per thread leaves too few bytes in flight to cover the DRAM latency (the ncu
+// capture of sweep_direct<.,.,0> shows long-scoreboard stalls at 36 % occupancy); all loads of the NC cells are issued
+// before the first store, which multiplies the memory-level parallelism per thread by NC.  Same arithmetic body as
+// sweep_direct (vel_interior_calc) -> bit-identical results.  Streamed V values use evict-first loads/stores.
+template <typename F>
+struct AccVelStream : AccVelDirect<F> {
+    __device__ __forceinline__ AccVelStream(const KParams<F> &p_, long long n_) : AccVelDirect<F>(p_, n_) {}
+    __device__ __forceinline__ F V(int f) const { return lds_((f == 0 ? this->p.Vx : f == 1 ? this->p.Vy : this->p.Vz) + this->n); }
+};
+
+#ifndef SWPC_VEL_MINB
+#define SWPC_VEL_MINB 2
+#endif
+template <typename F, int NC>
+__global__ void __launch_bounds__(256, SWPC_VEL_MINB) vel_multi(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
+    const int k = b.k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > b.k1) return;
+    const int li0 = b.li0 + blockIdx.y * (blockDim.y * NC) + threadIdx.y;
+    const int ljs = b.lj0 + blockIdx.z * jlen;
+    const int lje = min(ljs + jlen, b.lj1 + 1);
+    bool ok[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) ok[c] = (li0 + c * (int)blockDim.y) <= b.li1;
+    for (int lj = ljs; lj < lje; lj++) {
+        const int mj = lj + HALO;
+        F v[NC][3];
+        long long n[NC];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const int mi = li0 + c * (int)blockDim.y + HALO;
+            const long long col = (long long)mi + (long long)p.NXM * mj;
+            n[c] = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+            if (ok[c] && pf > 0 && lj + pf < lje) prefetch_cell<F, 0, false>(p, n[c] + p.SJ * pf, false, 0);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            if (!ok[c]) continue;
+            const int mi = li0 + c * (int)blockDim.y + HALO;
+            vel_interior_calc<F>(p, AccVelStream<F>(p, n[c]), k, mi, mj, p.band[(long long)mi + (long long)p.NXM * mj], v[c][0], v[c][1], v[c][2]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            if (!ok[c]) continue;
+            sts_(p.Vx + n[c], v[c][0]); sts_(p.Vy + n[c], v[c][1]); sts_(p.Vz + n[c], v[c][2]);
         }
     }
 }

@@ -32,15 +32,18 @@ int psv_run(psv_sim *s, int it0, int it1, float *vm, int nvm); /* + report__prog
 void psv_vmax(psv_sim *s, float out[2]);
 
 int psv_nranks(const psv_sim *s);
-/* which: 0 ibeg 1 iend 2 ibeg_k 3 iend_k 4 kbeg_k 5 kend_k 6 nsrc 7 nst 8 nzm 9 nxm 10 ibeg_m 11 kbeg_m 12 kbeg_min */
+/* which: 0 ibeg 1 iend 2 ibeg_k 3 iend_k 4 kbeg_k 5 kend_k 6 nsrc 7 nst 8 nzm 9 nxm 10 ibeg_m 11 kbeg_m 12 kbeg_min 13 nxp */
 int psv_rank_int(const psv_sim *s, int q, int which);
-/* which: 0 vmin 1 vmax 2 fmax 3 fcut 4 M0 5 UC 6 zeta 7 d2 8 dt 9 xbeg 10 zbeg 11 dx 12 dz 13 evlo 14 evla 15.. ts[m] 23.. c1 31.. c2 39.. d1 */
+/* which: 0 vmin 1 vmax 2 fmax 3 fcut 4 M0 5 UC 6 zeta 7 d2 8 dt 9 xbeg 10 zbeg 11 dx 12 dz 13 evlo 14 evla 15.. ts[m] 23.. c1 31.. c2 39.. d1 47 tbeg 48 r20x 49 r20z */
 double psv_cfg_value(const psv_sim *s, int which);
-/* which: 0 nx 1 nz 2 nt 3 na 4 nm 5 nproc_x 6 ntw 7 ntdec_w 8 ntdec_r 9 bf_mode 10 pw_mode */
+/* which: 0 nx 1 nz 2 nt 3 na 4 nm 5 nproc_x 6 ntw 7 ntdec_w 8 ntdec_r 9 bf_mode 10 pw_mode 11 sw_v 12 sw_u 13 sw_stress 14 sw_strain */
 int psv_cfg_int(const psv_sim *s, int which);
 const char *psv_cfg_str(const psv_sim *s, int which);     /* 0 title 1 odir 2 abc_type 3 stftype */
 
 int psv_get_field(const psv_sim *s, int q, const char *name, double *out);   /* Vx Vz Sxx Szz Sxz rho lam mu taup taus: (nxm, nzm) */
+int psv_set_field(psv_sim *s, int q, const char *name, const double *in);         /* tests: replace a field / medium array */
+void psv_redetect_surface(psv_sim *s);                                          /* ... and re-run surface_detection */
+int psv_get_memvar(const psv_sim *s, int q, const char *name, float *out);      /* Rxx Rzz Rxz: (nm, nzm, nxm) */
 int psv_get_map(const psv_sim *s, int q, const char *name, int *out);        /* kfs kob kfs_top kfs_bot kob_top kob_bot kbeg_a: (nxm) */
 int psv_get_profile(const psv_sim *s, int q, const char *name, float *out);  /* gxc gxe (4,nxp) gzc gze (4,nz) gx_c gx_b (nxm) gz_c gz_b (nzm) */
 int psv_get_sources(const psv_sim *s, int q, int *ik, double *val);          /* ik (2,nsrc); val (6,nsrc): mo mxx mzz mxz t0 tr  (bf: fx fz in mxx mzz) */

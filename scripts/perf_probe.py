@@ -81,6 +81,7 @@ def main():
     ap.add_argument("--abc", default="pml")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--configs", default="128,2,32", help="semicolon separated tk,ti,jlen[,pf] tuples")
+    ap.add_argument("--opts", default="", help="comma separated key=value library options applied before every config")
     a = ap.parse_args()
     dtype = np.float64 if a.dtype == "f64" else np.float32
     dev, geom = make_rank(a.nx, a.ny, a.nz, a.nm, dtype, abc=a.abc, na=a.na)
@@ -88,6 +89,8 @@ def main():
     W = np.dtype(dtype).itemsize
     pml_frac = 1 - ((a.nx - 2 * a.na) * (a.ny - 2 * a.na) * (a.nz - a.na)) / ncell if a.abc == "pml" else 0.0
     bpc = bytes_per_cell(a.nm, W, pml_frac)
+    for kv in filter(None, a.opts.split(",")):
+        dev.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     for cfg in a.configs.split(";"):
         vals = list(map(int, cfg.split(",")))
         tk, ti, jlen, pf = (vals + [0])[:4]
@@ -114,7 +117,7 @@ def main():
         for it in range(4, 4 + a.steps):
             dev.step(it)
         ms_t = dev.timer_stop() / a.steps
-        print(json.dumps({"grid": [a.nx, a.ny, a.nz], "nm": a.nm, "dtype": a.dtype, "abc": a.abc, "tk": tk, "ti": ti, "jlen": jlen, "pf": pf,
+        print(json.dumps({"grid": [a.nx, a.ny, a.nz], "nm": a.nm, "dtype": a.dtype, "abc": a.abc, "tk": tk, "ti": ti, "jlen": jlen, "pf": pf, "opts": a.opts,
                           "ms_stress": round(ms_s, 3), "ms_vel": round(ms_v, 3), "ms_step": round(ms_t, 3),
                           "gcells_s": round(ncell / ms_t / 1e6, 3), "bytes_per_cell": round(bpc, 1),
                           "GBs": round(ncell * bpc / ms_t / 1e6, 1), "vmax": [float(x) for x in dev.vmax()]}), flush=True)

@@ -16,11 +16,14 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("Vx", "Vy", "Vz", "Sxx", "Syy", "Szz", "Syz", "Sxz", "Sxy")
 
 
-def _run_pair(tmp_path, nt, *, nm=3, mp="dp", nranks=(1, 1), **case):
+def _run_pair(tmp_path, nt, *, nm=3, mp="dp", nranks=(1, 1), options=None, **case):
     inf = write_case(tmp_path, nt=nt, nproc_x=nranks[0], nproc_y=nranks[1], **case)
     o = Oracle(inf, base_dir=tmp_path, nm=nm, mp=mp)
     fd = np.float64 if mp == "dp" else np.float32
     devs = [device_from_oracle(o, q, field_dtype=fd, device=0) for q in range(o.nranks)]
+    for d in devs:
+        for key, val in (options or {}).items():
+            d.set_option(key, val)
     from openswpc_b200.device import comm_local
 
     for it in range(1, nt + 1):
@@ -113,3 +116,12 @@ def test_step_entry_point_and_run(tmp_path):
     d.run(1, 24)
     d.sync()
     _compare(o, [d], exact=True)
+
+
+@pytest.mark.parametrize("variant", [{"vel_nc": 1, "tma": 0}, {"vel_nc": 2}, {"vel_nc": 3}, {"vel_nc": 4}, {"tma": 2, "vel_nc": 1}])
+@pytest.mark.parametrize("abc", ["pml", "cerjan"])
+def test_kernel_variants_bit_exact(tmp_path, variant, abc):
+    # every kernel variant of the two sweeps (direct, TMA-staged, several cells per thread) shares one arithmetic body
+    o, devs = _run_pair(tmp_path, 24, nranks=(2, 1), nx=70, ny=44, abc_type=abc, options=variant,
+                        sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
+    _compare(o, devs, exact=True)
