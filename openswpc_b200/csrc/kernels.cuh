@@ -487,55 +487,6 @@ __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_cons
     }
 }
 
-// Velocity sweep over interior cells only, NC cells per thread (columns li, li+TI, ...) per plane.  The velocity update
-// streams only ~100 B per cell, so one cell per thread leaves too few bytes in flight to cover the DRAM latency (the ncu
-// capture of sweep_direct<.,.,0> shows long-scoreboard stalls at 36 % occupancy); all loads of the NC cells are issued
-// before the first store, which multiplies the memory-level parallelism per thread by NC.  Same arithmetic body as
-// sweep_direct (vel_interior_calc) -> bit-identical results.  Streamed V values use evict-first loads/stores.
-template <typename F>
-struct AccVelStream : AccVelDirect<F> {
-    __device__ __forceinline__ AccVelStream(const KParams<F> &p_, long long n_) : AccVelDirect<F>(p_, n_) {}
-    __device__ __forceinline__ F V(int f) const { return lds_((f == 0 ? this->p.Vx : f == 1 ? this->p.Vy : this->p.Vz) + this->n); }
-};
-
-#ifndef SWPC_VEL_MINB
-#define SWPC_VEL_MINB 2
-#endif
-template <typename F, int NC>
-__global__ void __launch_bounds__(256, SWPC_VEL_MINB) vel_multi(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
-    const int k = b.k0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (k > b.k1) return;
-    const int li0 = b.li0 + blockIdx.y * (blockDim.y * NC) + threadIdx.y;
-    const int ljs = b.lj0 + blockIdx.z * jlen;
-    const int lje = min(ljs + jlen, b.lj1 + 1);
-    bool ok[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) ok[c] = (li0 + c * (int)blockDim.y) <= b.li1;
-    for (int lj = ljs; lj < lje; lj++) {
-        const int mj = lj + HALO;
-        F v[NC][3];
-        long long n[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const int mi = li0 + c * (int)blockDim.y + HALO;
-            const long long col = (long long)mi + (long long)p.NXM * mj;
-            n[c] = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
-            if (ok[c] && pf > 0 && lj + pf < lje) prefetch_cell<F, 0, false>(p, n[c] + p.SJ * pf, false, 0);
-        }
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            if (!ok[c]) continue;
-            const int mi = li0 + c * (int)blockDim.y + HALO;
-            vel_interior_calc<F>(p, AccVelStream<F>(p, n[c]), k, mi, mj, p.band[(long long)mi + (long long)p.NXM * mj], v[c][0], v[c][1], v[c][2]);
-        }
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            if (!ok[c]) continue;
-            sts_(p.Vx + n[c], v[c][0]); sts_(p.Vy + n[c], v[c][1]); sts_(p.Vz + n[c], v[c][2]);
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // source time functions, m_fdtool.f90:339-497 (PI is real(DP) there)
 __device__ __forceinline__ float momentrate_dev(float t, int stf, float ts, float tr) {
