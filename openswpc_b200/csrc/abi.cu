@@ -154,6 +154,7 @@ struct swpc3d_handle {
     TmaMapsVel vmaps{};
     bool vtma_ok = false;
     int variant = 1;
+    int use_ring = 1, ring_jlen = 32, ring_pf = 2;   // vel_ring: register-pipelined interior velocity sweep
     int pw_mode = 0;   // plane-wave mode: edge extrapolation ahead of the PML sweeps
     int zero_outer = 0;   // re-zero the outer halo planes at every exchange (see launch_halo)
     long long launches = 0;
@@ -687,6 +688,33 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p) {
     if (!h->tma_ready) tma_prepare<F, NM>(h);
     const Box3 t = tma_box<F, NM>(h);
     const Box3 all{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0};
+    if (h->use_ring && h->g.iend_k >= h->g.ibeg_k && h->g.jend_k >= h->g.jbeg_k && h->tk * h->ti <= 256) {
+        // interior kernel box with the register-ring kernel; the absorber shell (all PML cells: two j slabs, two i slabs,
+        // the bottom k slab) with the direct kernel on side streams.  Every launch writes disjoint cells and only reads S.
+        const swpc3d_grid &gg = h->g;
+        const Box3 in{1, gg.kend_k, gg.ibeg_k - gg.ibeg, gg.iend_k - gg.ibeg, gg.jbeg_k - gg.jbeg, gg.jend_k - gg.jbeg, 0};
+        const Box3 sh[5] = {Box3{1, gg.nz, 0, h->nxp - 1, 0, in.lj0 - 1, 0}, Box3{1, gg.nz, 0, h->nxp - 1, in.lj1 + 1, h->nyp - 1, 0},
+                            Box3{1, gg.nz, 0, in.li0 - 1, in.lj0, in.lj1, 0}, Box3{1, gg.nz, in.li1 + 1, h->nxp - 1, in.lj0, in.lj1, 0},
+                            Box3{gg.kend_k + 1, gg.nz, in.li0, in.li1, in.lj0, in.lj1, 0}};
+        const int jlen = std::max(1, h->ring_jlen);
+        dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
+        dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
+        if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
+        vel_ring<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
+        h->launches++;
+        CK(cudaGetLastError());
+        for (int q = 0; q < 5; q++) {
+            const Box3 &b = sh[q];
+            if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
+            if (h->use_side) {
+                CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
+                if (launch_direct_box<F, false>(h, p, b, h->side[q])) return 1;
+                CK(cudaEventRecord(h->ev_join[q], h->side[q]));
+                CK(cudaStreamWaitEvent(h->st, h->ev_join[q], 0));
+            } else if (launch_direct_box<F, false>(h, p, b)) return 1;
+        }
+        return 0;
+    }
     if (t.k1 < t.k0 || !h->vtma_ok || h->use_tma < 2) return launch_direct_box<F, false>(h, p, all);
     TmaGeom g{};
     g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl);
@@ -1251,6 +1279,9 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "pw_mode")) { h->pw_mode = value != 0; if (value) h->zero_outer = 1; }
     else if (!strcmp(key, "zero_outer_halo")) h->zero_outer = value != 0;
     else if (!strcmp(key, "tma")) h->use_tma = value;
+    else if (!strcmp(key, "vel_ring")) h->use_ring = value;
+    else if (!strcmp(key, "ring_jlen")) { if (value < 1) return fail("ring_jlen must be >= 1"); h->ring_jlen = value; }
+    else if (!strcmp(key, "ring_pf")) { if (value < 0 || value > 8) return fail("ring_pf must be 0..8"); h->ring_pf = value; }
     else if (!strcmp(key, "side_streams")) h->use_side = value;
     else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }
     else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; }

@@ -7,6 +7,7 @@
 #include "../../../include/swpc3d_host.h"
 
 #include "common.hpp"
+#include "models.hpp"
 
 // ============================================================================================================
 struct swpc3d_host {
@@ -59,6 +60,10 @@ struct swpc3d_host {
     int setup_global(const IniFile &ini, int npx, int npy, int nt_o);
     int setup_geometry();
     int setup_medium(const IniFile &ini);
+    int finish_medium_3d(const IniFile &ini);
+    int finish_surface(const IniFile &ini);
+    bool stabilize_pending = false;
+    void apply_stabilize();
     void setup_kernel();
     int setup_source(const IniFile &ini);
     int setup_absorb();
@@ -143,6 +148,7 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
     // every supported model is laterally uniform at build time: fill one column profile, then broadcast
     std::vector<float> p_rho(nzm), p_lam(nzm), p_mu(nzm), p_qp(nzm), p_qs(nzm);
     float bd0 = 0.0f;
+    bool lateral = false;   // laterally heterogeneous builder: 3-D arrays are filled directly
     if (benchmark_mode) {   // m_medium.f90:55-74
         fq_min = 0.05f; fq_max = 5.0f; fq_ref = 1.0f;
         for (int q = 0; q < nzm; q++) {
@@ -207,11 +213,21 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
                     if (zs[q] >= depth[l]) { r1 = r0[l]; vp1 = Cv[q] * vp0[l]; vs1 = Cv[q] * vs0[l]; a = qp0[l]; b = qs0[l]; }
                 p_rho[q] = r1; p_mu[q] = r1 * vs1 * vs1; p_lam[q] = r1 * (vp1 * vp1 - 2 * vs1 * vs1); p_qp[q] = a; p_qs[q] = b;
             }
+        } else if (vmodel_type == "lgm" || vmodel_type == "uni_rmed" || vmodel_type == "lhm_rmed" || vmodel_type == "lgm_rmed") {
+            // models.hpp: these fill the 3-D arrays directly (Qp / Qs go to taup / taus, as in the reference's call)
+            lateral = true;
+            const MediumBox mb{ibeg_m, iend_m, jbeg_m, jend_m, kbeg_m, kend_m, zc.data(), rho.data(), lam.data(), mu.data(), taup.data(), taus.data()};
+            const ModelEnv env{&ini, base, vcut, dt, dx, dy, dz, munk, ef};
+            const int rc = vmodel_type == "lgm" ? vmodel_lgm(env, mb, bd0) : vmodel_type == "uni_rmed" ? vmodel_uni_rmed(env, mb, bd0)
+                         : vmodel_type == "lhm_rmed" ? vmodel_lhm_rmed(env, mb, bd0) : vmodel_lgm_rmed(env, mb, bd0);
+            if (rc) return 1;
         } else {
-            return hfail("vmodel_type '" + vmodel_type + "' is outside the hot-path scope of this build (uni, lhm, benchmark_mode)");
+            return hfail("vmodel_type '" + vmodel_type + "' is not available in this build: 'user' is a compile-time plug-in of the reference, "
+                         "'grd' / 'grd_rmed' need GMT netCDF-4 grids (no netCDF/HDF5 library in the image)");
         }
     }
     for (size_t n = 0; n < n2; n++) bddep[n] = bd0;
+    if (lateral) return finish_medium_3d(ini);
 
     // absorber homogenisation (m_medium.f90:124-190) copies columns outward; with laterally uniform input it is the
     // identity in x and y, and in z it repeats the value at k = nz-na below it
@@ -253,6 +269,55 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
             std::copy(p_tsx.begin(), p_tsx.end(), taus.begin() + o);
         }
 
+    return finish_surface(ini);
+}
+
+// medium__setup after a laterally heterogeneous vmodel_*: absorber homogenisation (m_medium.f90:124-190), tau-method
+// (:193-207) and relaxed moduli (:231-271) cell by cell
+int swpc3d_host::finish_medium_3d(const IniFile &ini) {
+    auto cp5 = [&](size_t d, size_t s_) { rho[d] = rho[s_]; lam[d] = lam[s_]; mu[d] = mu[s_]; taup[d] = taup[s_]; taus[d] = taus[s_]; };
+    for (int i = ibeg_m; i <= na; i++)
+        for (int j = jbeg_m; j <= jend_m; j++)
+            for (int k = kbeg_m; k <= kend_m; k++) cp5(i3(k, i, j), i3(k, na + 1, j));
+    for (int i = nx - na + 1; i <= iend_m; i++)
+        for (int j = jbeg_m; j <= jend_m; j++)
+            for (int k = kbeg_m; k <= kend_m; k++) cp5(i3(k, i, j), i3(k, nx - na, j));
+    for (int j = jbeg_m; j <= na; j++)
+        for (int i = ibeg_m; i <= iend_m; i++)
+            for (int k = kbeg_m; k <= kend_m; k++) cp5(i3(k, i, j), i3(k, i, na + 1));
+    for (int j = ny - na + 1; j <= jend_m; j++)
+        for (int i = ibeg_m; i <= iend_m; i++)
+            for (int k = kbeg_m; k <= kend_m; k++) cp5(i3(k, i, j), i3(k, i, ny - na));
+    for (int j = jbeg_m; j <= jend_m; j++)
+        for (int i = ibeg_m; i <= iend_m; i++)
+            for (int k = nz - na + 1; k <= kend_m; k++) cp5(i3(k, i, j), i3(nz - na, i, j));
+    relax_times(nm, ts, fq_min, fq_max);
+    zeta = constq_zeta(nm, fq_min, fq_max, ts);
+    const size_t nc = rho.size();
+    for (size_t n = 0; n < nc; n++) { taup[n] = nm * zeta / taup[n]; taus[n] = nm * zeta / taus[n]; }
+    if (nm > 0) {
+        const float omega = (float)(2 * PI_D * (double)fq_ref);
+        std::complex<float> cc(0.0f, 0.0f);
+        for (int m = 0; m < nm; m++) {
+            const std::complex<double> w = std::complex<double>(0.0, 1.0) * (double)omega * (double)ts[m];
+            const std::complex<double> qd = w / (1.0 - w);
+            cc = cc + std::complex<float>((float)qd.real(), (float)qd.imag());
+        }
+        cc = std::complex<float>(cc.real() / (float)nm, cc.imag() / (float)nm);
+        for (size_t n = 0; n < nc; n++) {
+            const float rb2 = mu[n], ra2 = lam[n] + 2 * mu[n];
+            const std::complex<float> zs_ = 1.0f - cc * taus[n], zp_ = 1.0f - cc * taup[n];
+            const float chi_mu = 1.0f / (1.0f / std::sqrt(zs_)).real();
+            const float chi_lam = 1.0f / (1.0f / std::sqrt(zp_)).real();
+            mu[n] = rb2 / (chi_mu * chi_mu);
+            lam[n] = ra2 / (chi_lam * chi_lam) - 2 * mu[n];
+        }
+    }
+    return finish_surface(ini);
+}
+
+int swpc3d_host::finish_surface(const IniFile &ini) {
+    const size_t n2 = (size_t)nxm * nym;
     // surface_detection m_medium.f90:339-394 -- evaluated per column exactly as the reference does (Q1: only
     // i in [ibeg-1, iend+2], j likewise are scanned; the outermost margin keeps kbeg-1 = 0)
     kfs.assign(n2, 0); kob.assign(n2, 0); kfs_top.assign(n2, 0); kfs_bot.assign(n2, 0); kob_top.assign(n2, 0); kob_bot.assign(n2, 0);
@@ -287,8 +352,18 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
             }
     vmin_local = vmin = vmn;
     vmax_local = vmax = vmx;
-    if (ini.get_l("stabilize_pml", false)) return hfail("stabilize_pml = .true. is outside the hot-path scope of this build");
+    // stabilize_absorber (m_medium.f90:218-222) needs the GLOBAL vmax: applied here for a single-rank run, otherwise when
+    // the caller hands over the reduced values (swpc3d_host_set_minmax) or, at the latest, before the upload
+    stabilize_pending = ini.get_l("stabilize_pml", false);
+    if (stabilize_pending && nproc_x * nproc_y == 1) apply_stabilize();
     return 0;
+}
+
+void swpc3d_host::apply_stabilize() {
+    if (!stabilize_pending) return;
+    stabilize_pending = false;
+    const MediumBox mb{ibeg_m, iend_m, jbeg_m, jend_m, kbeg_m, kend_m, zc.data(), rho.data(), lam.data(), mu.data(), taup.data(), taus.data()};
+    stabilize_absorber(mb, kbeg_a.data(), ibeg, iend, jbeg, jend, nz, vmax);
 }
 
 void swpc3d_host::setup_kernel() {   // m_kernel.f90:58-67 (the device computes its own copy; kept for reporting)
@@ -1014,6 +1089,7 @@ int swpc3d_host_get_string(swpc3d_host *h, const char *name, char *buf, int32_t 
 int swpc3d_host_set_minmax(swpc3d_host *h, float vmin, float vmax) {
     if (!h) return hfail("null handle");
     h->vmin = vmin; h->vmax = vmax;
+    h->apply_stabilize();
     return 0;
 }
 int swpc3d_host_set_exedate(swpc3d_host *h, int32_t exedate, int32_t tz) {
@@ -1067,6 +1143,7 @@ int swpc3d_host_station_name(swpc3d_host *h, int32_t i, char *buf9) {
 int swpc3d_host_attach_device(swpc3d_host *h, int32_t device) {
     if (!h) return hfail("null handle");
     if (h->dev) { swpc3d_destroy(h->dev); h->dev = nullptr; }
+    h->apply_stabilize();
     swpc3d_grid g{};
     g.nx = h->nx; g.ny = h->ny; g.nz = h->nz; g.nproc_x = h->nproc_x; g.nproc_y = h->nproc_y; g.myid = h->myid;
     g.ibeg = h->ibeg; g.iend = h->iend; g.jbeg = h->jbeg; g.jend = h->jend; g.ipad = h->ipad; g.jpad = h->jpad; g.kpad = h->kpad;

@@ -1,0 +1,394 @@
+// models.hpp -- host-side builders for the heavier velocity models of swpc_3d (setup-only CPU code):
+//   vmodel_lgm        src/swpc_3d/m_vmodel_lgm.f90:20-175        linear-gradient layers
+//   vmodel_uni_rmed   src/swpc_3d/m_vmodel_uni_rmed.f90:22-170   homogeneous + random-media volume
+//   vmodel_lhm_rmed   src/swpc_3d/m_vmodel_lhm_rmed.f90:22-244   layered + one random-media volume per layer
+//   vmodel_lgm_rmed   src/swpc_3d/m_vmodel_lgm_rmed.f90:22-258   gradient layers + random media (with the reference's
+//                                                                whole-plane assignment quirk, :236-240)
+//   rdrmed__3d        src/shared/m_rdrmed.f90:73-134             cyclic read of the volume written by gen_rmed3d
+//   stabilize_absorber src/swpc_3d/m_medium.f90:273-337
+// The image has no netCDF library; gen_rmed3d creates its file with NF90_CLOBBER (tools/gen_rmed3d.f90:91), i.e. the
+// netCDF classic format, which ClassicNc below parses directly.  vmodel_grd / grd_rmed read GMT grids (netCDF-4/HDF5 by
+// default) and vmodel_user is a compile-time plug-in: both stay out of this build.
+#pragma once
+
+#include "common.hpp"
+
+namespace {
+
+// the memory box of one rank and the medium arrays being built, (k,i,j) with k fastest as m_medium.f90:441-452
+struct MediumBox {
+    int ib, ie, jb, je, kb, ke;          // ibeg_m..iend_m, jbeg_m..jend_m, kbeg_m..kend_m
+    const float *zc;                     // zc(kb:ke)
+    float *rho, *lam, *mu, *qp, *qs;     // the reference passes taup / taus as the Qp / Qs outputs
+    int nk() const { return ke - kb + 1; }
+    int ni() const { return ie - ib + 1; }
+    size_t ncell() const { return (size_t)nk() * ni() * (size_t)(je - jb + 1); }
+    size_t at(int k, int i, int j) const { return (size_t)(k - kb) + (size_t)nk() * ((size_t)(i - ib) + (size_t)ni() * (size_t)(j - jb)); }
+};
+
+// netCDF classic (CDF-1 / CDF-2) header: dimension lengths and, per variable, type and data offset
+class ClassicNc {
+  public:
+    std::vector<long long> dim;
+    struct Var { std::string name; int type = 0; long long begin = 0; std::vector<int> dimid; };
+    std::vector<Var> var;
+    std::vector<unsigned char> bytes;
+
+    bool open(const std::string &path, std::string &err) {
+        std::ifstream is(path, std::ios::binary);
+        if (!is) { err = "cannot open " + path; return false; }
+        bytes.assign(std::istreambuf_iterator<char>(is), std::istreambuf_iterator<char>());
+        if (bytes.size() < 32 || bytes[0] != 'C' || bytes[1] != 'D' || bytes[2] != 'F' || (bytes[3] != 1 && bytes[3] != 2)) {
+            err = path + " is not a netCDF classic (CDF-1/2) file";
+            return false;
+        }
+        const int offw = bytes[3] == 2 ? 8 : 4;
+        pos_ = 8;   // magic, numrecs
+        static const int tsz[7] = {0, 1, 1, 2, 4, 4, 8};
+        auto skip_atts = [&]() {
+            const unsigned tag = u4(), n = u4();
+            if (tag != 0x0C) return;
+            for (unsigned a = 0; a < n; a++) {
+                name();
+                const unsigned ty = u4(), ne = u4();
+                pos_ += ((size_t)ne * tsz[ty < 7 ? ty : 0] + 3) / 4 * 4;
+            }
+        };
+        unsigned tag = u4(), n = u4();
+        if (tag == 0x0A)
+            for (unsigned d = 0; d < n; d++) { name(); dim.push_back(u4()); }
+        skip_atts();
+        tag = u4(); n = u4();
+        if (tag == 0x0B)
+            for (unsigned v = 0; v < n; v++) {
+                Var x;
+                x.name = name();
+                const unsigned nd = u4();
+                for (unsigned d = 0; d < nd; d++) x.dimid.push_back((int)u4());
+                skip_atts();
+                x.type = (int)u4();
+                u4();   // vsize
+                x.begin = (long long)ube(offw);
+                var.push_back(x);
+            }
+        return true;
+    }
+    float f32(long long byte_off) const {
+        const unsigned char *p = bytes.data() + byte_off;
+        const uint32_t u = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+        float v;
+        std::memcpy(&v, &u, 4);
+        return v;
+    }
+
+  private:
+    size_t pos_ = 0;
+    unsigned long long ube(int n) {
+        unsigned long long v = 0;
+        for (int q = 0; q < n; q++) v = (v << 8) | bytes[pos_ + q];
+        pos_ += n;
+        return v;
+    }
+    unsigned u4() { return (unsigned)ube(4); }
+    std::string name() {
+        const unsigned n = u4();
+        std::string s((const char *)bytes.data() + pos_, n);
+        pos_ += (n + 3) / 4 * 4;
+        return s;
+    }
+};
+
+// m_rdrmed.f90:73-134: the volume is periodic in x and y, wraps upward for k <= 0 and repeats below its last plane
+inline int rdrmed3d(const MediumBox &b, const std::string &fn, float *vol) {
+    ClassicNc nc;
+    std::string err;
+    if (!nc.open(fn, err)) return hfail("rdrmed__3d: " + err);
+    if (nc.dim.size() < 3 || nc.var.size() < 4 || nc.var[3].type != 5)
+        return hfail("rdrmed__3d: " + fn + " needs dimensions x, y, z and a float volume as its 4th variable (gen_rmed3d.f90:91-126)");
+    const long long nxc = nc.dim[0], nyc = nc.dim[1], nzc = nc.dim[2], beg = nc.var[3].begin;
+    if (beg + 4 * nxc * nyc * nzc > (long long)nc.bytes.size()) return hfail("rdrmed__3d: " + fn + " is truncated");
+    auto wrap = [](long long v, long long n) { long long r = v % n; return r <= 0 ? r + n : r; };
+    for (int k = b.kb; k <= std::min<long long>(b.ke, nzc); k++) {
+        const long long plane = beg + 4 * nxc * nyc * ((k <= 0 ? k + nzc : k) - 1);
+        for (int j = b.jb; j <= b.je; j++) {
+            const long long row = plane + 4 * nxc * (wrap(j, nyc) - 1);
+            for (int i = b.ib; i <= b.ie; i++) vol[b.at(k, i, j)] = nc.f32(row + 4 * (wrap(i, nxc) - 1));
+        }
+    }
+    for (long long k = nzc + 1; k <= b.ke; k++)
+        for (int j = b.jb; j <= b.je; j++)
+            for (int i = b.ib; i <= b.ie; i++) vol[b.at((int)k, i, j)] = vol[b.at((int)(k % nzc), i, j)];
+    return 0;
+}
+
+struct LayerTable {
+    std::vector<float> depth, rho, vp, vs, qp, qs;
+    std::vector<std::string> rmed;
+    int n() const { return (int)depth.size(); }
+};
+
+// "depth rho vp vs Qp Qs [random-media file]" rows, '#' comments; then the velocity cut-off (m_vmodel_lgm.f90:92-101)
+inline int read_layer_table(const std::string &fn, bool with_rmed, float vcut, LayerTable &t) {
+    std::ifstream is(fn);
+    if (!is) return hfail("layer file " + fn + " not found (assert, m_vmodel_lgm.f90:56-57)");
+    std::string line;
+    while (std::getline(is, line)) {
+        if (blank_or_comment(line)) continue;
+        const std::vector<float> v = parse_reals(line);
+        if (v.size() < 6) continue;
+        t.depth.push_back(v[0]); t.rho.push_back(v[1]); t.vp.push_back(v[2]); t.vs.push_back(v[3]); t.qp.push_back(v[4]); t.qs.push_back(v[5]);
+        std::string name;
+        if (with_rmed) {   // 7th list-directed item: a (possibly quoted) file name
+            std::istringstream ss(line);
+            std::string tok;
+            for (int q = 0; q < 7 && (ss >> tok); q++)
+                if (q == 6) name = tok;
+            for (auto &ch : name) if (ch == ',') ch = ' ';
+            while (!name.empty() && name.back() == ' ') name.pop_back();
+            if (name.size() >= 2 && (name[0] == '\'' || name[0] == '"') && name.back() == name[0]) name = name.substr(1, name.size() - 2);
+        }
+        t.rmed.push_back(name);
+    }
+    if (t.n() == 0) return hfail("no layer in " + fn);
+    for (int l = t.n() - 2; l >= 0; l--)
+        if ((t.vp[l] < vcut || t.vs[l] < vcut) && (t.vp[l] > 0 && t.vs[l] > 0)) {
+            t.vp[l] = t.vp[l + 1]; t.vs[l] = t.vs[l + 1]; t.rho[l] = t.rho[l + 1]; t.qp[l] = t.qp[l + 1]; t.qs[l] = t.qs[l + 1];
+        }
+    return 0;
+}
+
+// m_fdtool.f90:15-48
+inline void vcheck(float &vp, float &vs, float &rho, float xi, float vmin, float vmax, float rhomin) {
+    float gamma = vp / vs;
+    if (gamma < EPS_SP) gamma = std::sqrt(3.0f);
+    if (vp > vmax || vs > vmax) {
+        const float xi2 = (1 + xi) * vmax / vp - 1;
+        vp = vmax;
+        vs = vmax / gamma;
+        rho = rho * (1 + 0.8f * xi2) / (1 + 0.8f * xi);
+    }
+    if (vp < vmin || vs < vmin) { vs = vmin; vp = vmin * gamma; }
+    if (rho < rhomin) rho = rhomin;
+}
+
+struct ModelEnv {
+    const IniFile *ini;
+    std::string base;
+    float vcut, dt;
+    double dx, dy, dz;
+    bool munk, flatten;
+    // spherical depth / velocity scaling of the earth-flattening transformation (m_vmodel_lgm.f90:64-73)
+    void depth(float zc, float &zs, float &cv) const {
+        if (flatten) { zs = (float)(R_EARTH - R_EARTH * std::exp(-(double)zc / R_EARTH)); cv = (float)std::exp((double)zc / R_EARTH); }
+        else { zs = zc; cv = 1.0f; }
+    }
+    float rmed_vmax() const {   // cc * dh / dt, m_vmodel_uni_rmed.f90:79-83
+        const float dh = (float)(1.0 / std::sqrt(1.0 / (dx * dx) + 1.0 / (dy * dy) + 1.0 / (dz * dz)));
+        return (6.0f / 7.0f) * dh / dt;
+    }
+};
+
+inline void set_cell(const MediumBox &b, size_t n, float rho, float vp, float vs, float qp, float qs) {
+    b.rho[n] = rho; b.mu[n] = rho * vs * vs; b.lam[n] = rho * (vp * vp - 2 * vs * vs); b.qp[n] = qp; b.qs[n] = qs;
+}
+inline void set_plane(const MediumBox &b, int k, float rho, float vp, float vs, float qp, float qs) {
+    for (int j = b.jb; j <= b.je; j++)
+        for (int i = b.ib; i <= b.ie; i++) set_cell(b, b.at(k, i, j), rho, vp, vs, qp, qs);
+}
+
+// air / ocean plane above the first interface, shared by the lhm / lgm families; returns false inside the solid
+inline bool air_or_ocean(const ModelEnv &e, float zc, float zs, float cv, float top, float &rho, float &vp, float &vs, float &qp, float &qs) {
+    if (!(zs < top)) return false;
+    if (zs < 0.0f) { rho = 0.001f; vp = 0.0f; vs = 0.0f; qp = 10.0f; qs = 10.0f; }
+    else { rho = 1.0f; vp = cv * seawater_vel(zc, e.munk); vs = 0.0f; qp = 1000000.0f; qs = 1000000.0f; }
+    return true;
+}
+
+// linear interpolation inside layer l (m_vmodel_lgm.f90:137-141)
+inline void gradient_at(const LayerTable &t, int l, float zs, float cv, float &rho, float &vp, float &vs, float &qp, float &qs) {
+    const float dd = t.depth[l + 1] - t.depth[l], dz = zs - t.depth[l];
+    rho = t.rho[l] + (t.rho[l + 1] - t.rho[l]) / dd * dz;
+    vp = cv * (t.vp[l] + (t.vp[l + 1] - t.vp[l]) / dd * dz);
+    vs = cv * (t.vs[l] + (t.vs[l + 1] - t.vs[l]) / dd * dz);
+    qp = t.qp[l] + (t.qp[l + 1] - t.qp[l]) / dd * dz;
+    qs = t.qs[l] + (t.qs[l + 1] - t.qs[l]) / dd * dz;
+}
+
+inline int vmodel_lgm(const ModelEnv &e, const MediumBox &b, float &bd0) {
+    LayerTable t;
+    if (read_layer_table(join_path(e.base, e.ini->get("fn_lhm", "")), false, e.vcut, t)) return 1;
+    const int nl = t.n();
+    bd0 = t.depth[0];
+    for (int k = b.kb; k <= b.ke; k++) {
+        const float zc = b.zc[k - b.kb];
+        float zs, cv, rho, vp, vs, qp, qs;
+        e.depth(zc, zs, cv);
+        if (!air_or_ocean(e, zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
+            rho = t.rho[nl - 1]; vp = cv * t.vp[nl - 1]; vs = cv * t.vs[nl - 1]; qp = t.qp[nl - 1]; qs = t.qs[nl - 1];
+            for (int l = 0; l + 1 < nl; l++)
+                if (t.depth[l] <= zs && zs < t.depth[l + 1]) { gradient_at(t, l, zs, cv, rho, vp, vs, qp, qs); break; }
+        }
+        set_plane(b, k, rho, vp, vs, qp, qs);
+    }
+    return 0;
+}
+
+// the distinct random-media files of a layer table (independent_list, m_fdtool.f90:815-855) read over the memory box;
+// a missing file means "no perturbation" (m_vmodel_lhm_rmed.f90:134-140)
+inline int read_rmed_set(const ModelEnv &e, const MediumBox &b, const LayerTable &t, std::vector<int> &tbl, std::vector<std::vector<float>> &xi) {
+    const std::string dir = e.ini->get("dir_rmed", "");
+    std::vector<std::string> uniq;
+    tbl.assign(t.n(), 0);
+    for (int l = 0; l < t.n(); l++) {
+        const std::string full = dir + "/" + t.rmed[l];
+        const auto it = std::find(uniq.begin(), uniq.end(), full);
+        tbl[l] = (int)(it - uniq.begin());
+        if (it == uniq.end()) uniq.push_back(full);
+    }
+    xi.assign(uniq.size(), std::vector<float>());
+    for (size_t q = 0; q < uniq.size(); q++) {
+        xi[q].assign(b.ncell(), 0.0f);
+        const std::string path = join_path(e.base, uniq[q]);
+        if (std::ifstream(path).good() && rdrmed3d(b, path, xi[q].data())) return 1;
+    }
+    return 0;
+}
+
+inline int vmodel_uni_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
+    const IniFile &ini = *e.ini;
+    const float vp0 = ini.get_s("vp0", 5.0f), vs0 = ini.get_s("vs0", vp0 / std::sqrt(3.0f)), rho0 = ini.get_s("rho0", 2.7f);
+    const float qp0 = ini.get_s("qp0", 1000000.0f), qs0 = ini.get_s("qs0", 1000000.0f), topo0 = ini.get_s("topo0", 0.0f);
+    const float rhomin = ini.get_s("rhomin", 1.0f), vmin = e.vcut, vmax = e.rmed_vmax();
+    std::vector<float> xi(b.ncell(), 0.0f);
+    const std::string path = join_path(e.base, ini.get("dir_rmed", "") + "/" + ini.get("fn_rmed0", ""));
+    if (std::ifstream(path).good() && rdrmed3d(b, path, xi.data())) return 1;
+    bd0 = topo0;
+    for (int k = b.kb; k <= b.ke; k++) {
+        const float zc = b.zc[k - b.kb];
+        float zs, cv;
+        e.depth(zc, zs, cv);
+        if (zs > topo0) {
+            for (int j = b.jb; j <= b.je; j++)
+                for (int i = b.ib; i <= b.ie; i++) {
+                    const size_t n = b.at(k, i, j);
+                    float rho = (1.0f + 0.8f * xi[n]) * rho0, vp = (1.0f + xi[n]) * cv * vp0, vs = (1.0f + xi[n]) * cv * vs0;
+                    vcheck(vp, vs, rho, xi[n], vmin, vmax, rhomin);
+                    set_cell(b, n, rho, vp, vs, qp0, qs0);
+                }
+        } else if (zs > 0.0f) set_plane(b, k, 1.0f, cv * seawater_vel(zc, e.munk), 0.0f, 1000000.0f, 1000000.0f);
+        else set_plane(b, k, 0.001f, 0.0f, 0.0f, 10.0f, 10.0f);
+    }
+    return 0;
+}
+
+inline int vmodel_lhm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
+    LayerTable t;
+    if (read_layer_table(join_path(e.base, e.ini->get("fn_lhm_rmed", "")), true, e.vcut, t)) return 1;
+    const float rhomin = e.ini->get_s("rhomin", 1.0f), vmin = e.vcut, vmax = e.rmed_vmax();
+    std::vector<int> tbl;
+    std::vector<std::vector<float>> xi;
+    if (read_rmed_set(e, b, t, tbl, xi)) return 1;
+    bd0 = t.depth[0];
+    for (int k = b.kb; k <= b.ke; k++) {
+        const float zc = b.zc[k - b.kb];
+        float zs, cv, rho = 0, vp = 0, vs = 0, qp = 0, qs = 0;
+        e.depth(zc, zs, cv);
+        if (air_or_ocean(e, zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
+            if (zs < 0.0f) set_plane(b, k, rho, vp, vs, qp, qs);
+            else   // m_vmodel_lhm_rmed.f90:176-178 writes lam = 1.0 * vp1 * vp1 directly
+                for (int j = b.jb; j <= b.je; j++)
+                    for (int i = b.ib; i <= b.ie; i++) {
+                        const size_t n = b.at(k, i, j);
+                        b.rho[n] = 1.0f; b.mu[n] = 0.0f; b.lam[n] = 1.0f * vp * vp; b.qp[n] = qp; b.qs[n] = qs;
+                    }
+            continue;
+        }
+        for (int j = b.jb; j <= b.je; j++)
+            for (int i = b.ib; i <= b.ie; i++) {
+                const size_t n = b.at(k, i, j);
+                for (int l = 0; l < t.n(); l++)
+                    if (zs >= t.depth[l]) {
+                        const float x = xi[tbl[l]][n];
+                        rho = t.rho[l] * (1 + 0.8f * x); vp = cv * t.vp[l] * (1 + x); vs = cv * t.vs[l] * (1 + x);
+                        if (t.vp[l] > 0 && t.vs[l] > 0) vcheck(vp, vs, rho, x, vmin, vmax, rhomin);
+                        qp = t.qp[l]; qs = t.qs[l];
+                    }
+                set_cell(b, n, rho, vp, vs, qp, qs);
+            }
+    }
+    return 0;
+}
+
+inline int vmodel_lgm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
+    LayerTable t;
+    if (read_layer_table(join_path(e.base, e.ini->get("fn_lhm_rmed", "")), true, e.vcut, t)) return 1;
+    const float rhomin = e.ini->get_s("rhomin", 1.0f), vmin = e.vcut, vmax = e.rmed_vmax();
+    std::vector<int> tbl;
+    std::vector<std::vector<float>> xi;
+    if (read_rmed_set(e, b, t, tbl, xi)) return 1;
+    const int nl = t.n();
+    bd0 = t.depth[0];
+    for (int k = b.kb; k <= b.ke; k++) {
+        const float zc = b.zc[k - b.kb];
+        float zs, cv, rho, vp, vs, qp, qs;
+        e.depth(zc, zs, cv);
+        if (!air_or_ocean(e, zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
+            // the reference assigns the WHOLE plane inside its (i,j) loops (:236-240): what survives is the value
+            // computed at the last column (iend_m, jend_m) of this rank's memory box
+            const size_t n = b.at(k, b.ie, b.je);
+            const float xl = xi[tbl[nl - 1]][n];
+            rho = t.rho[nl - 1] * (1 + 0.8f * xl); vp = cv * t.vp[nl - 1] * (1 + xl); vs = cv * t.vs[nl - 1] * (1 + xl);
+            qp = t.qp[nl - 1]; qs = t.qs[nl - 1];
+            for (int l = 0; l + 1 < nl; l++)
+                if (t.depth[l] <= zs && zs < t.depth[l + 1]) {
+                    gradient_at(t, l, zs, cv, rho, vp, vs, qp, qs);
+                    const float x = xi[tbl[l]][n];
+                    rho = rho * (1 + 0.8f * x); vp = vp * (1 + x); vs = vs * (1 + x);
+                    if (t.vp[l] > 0 && t.vs[l] > 0) vcheck(vp, vs, rho, x, vmin, vmax, rhomin);
+                    break;
+                }
+        }
+        set_plane(b, k, rho, vp, vs, qp, qs);
+    }
+    return 0;
+}
+
+// m_medium.f90:273-337.  `b` carries taup / taus in qp / qs here; vmax is the global maximum P velocity.
+inline void stabilize_absorber(const MediumBox &b, const int *kbeg_a /* (i,j) over the memory box */, int ibeg, int iend, int jbeg, int jend,
+                               int kend, float vmax) {
+    const float vmin_pml = vmax * 0.4f;   // V_DYNAMIC_RANGE
+    const int LV_THICK = 20;
+    auto top_of = [&](int i, int j) {
+        int k = 1 << 30;
+        for (int jj = j - 2; jj <= j + 2; jj++)
+            for (int ii = i - 2; ii <= i + 2; ii++) k = std::min(k, kbeg_a[(size_t)(ii - b.ib) + (size_t)b.ni() * (size_t)(jj - b.jb)]);
+        return k;
+    };
+    for (int j = jbeg - 1; j <= jend + 1; j++)
+        for (int i = ibeg - 1; i <= iend + 1; i++) {
+            for (int k = top_of(i, j); k <= kend; k++) {
+                const size_t n = b.at(k, i, j), m = b.at(k - 1, i, j);
+                if (!(b.lam[n] < b.lam[m] || b.mu[n] < b.mu[m])) continue;
+                int k2 = k + 1;
+                for (; k2 <= kend; k2++)
+                    if (b.lam[b.at(k2, i, j)] > b.lam[b.at(k2 - 1, i, j)] || b.mu[b.at(k2, i, j)] > b.mu[b.at(k2 - 1, i, j)]) break;
+                if (k2 - k <= LV_THICK) {
+                    b.rho[n] = b.rho[m]; b.lam[n] = b.lam[m]; b.mu[n] = b.mu[m]; b.qp[n] = b.qp[m]; b.qs[n] = b.qs[m];
+                    k = k2 - 1;
+                }
+            }
+            for (int k = top_of(i, j); k <= kend; k++) {
+                const size_t n = b.at(k, i, j);
+                float vs = std::sqrt(b.mu[n] / b.rho[n]);
+                if (vs < EPS_SP) continue;
+                if (vs < vmin_pml) {
+                    vs = vmin_pml;
+                    const float vp = vs * std::sqrt(3.0f);
+                    b.lam[n] = b.rho[n] * (vp * vp - 2 * (vs * vs));
+                    b.mu[n] = b.rho[n] * (vs * vs);
+                }
+            }
+        }
+}
+
+}   // namespace

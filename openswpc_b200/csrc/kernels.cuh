@@ -488,6 +488,115 @@ __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Velocity sweep over INTERIOR cells, version 2 ("ring"): software-pipelined in registers.  The direct kernel issues its
+// ~36 loads per cell in register-limited batches that each wait for an L2 round trip (long-scoreboard stalls at 36 %
+// occupancy, profiles/r01_ncu_full_sweeps_*.txt).  Here a thread marches along j and
+//   * keeps the j-direction stencil of its own column in a register ring (Syy j-1..j+2, Sxy / Syz j-2..j+1),
+//   * loads everything plane j+1 needs from its own column (Sxx, Szz, Sxz, Vx, Vy, Vz, rho and the ring's new heads
+//     Syy(j+3), Sxy(j+2), Syz(j+2)) while plane j is being computed, so those HBM-latency loads have a full iteration
+//     to land, and
+//   * reads only the in-plane (k, i) neighbours on demand -- lines its neighbour threads pulled into L1 one or two
+//     iterations earlier.
+// Same arithmetic body (vel_interior_calc) -> bit-identical results.  Absorber cells stay with sweep_direct.
+template <typename F>
+struct AccVelRing {
+    const KParams<F> &p;
+    long long n;
+    F sxx0, szz0, sxz0;
+    F syy[4];   // j-1 .. j+2
+    F sxy[4];   // j-2 .. j+1
+    F syz[4];   // j-2 .. j+1
+    F v[3];
+    float rho0, rho_j1;
+    __device__ __forceinline__ AccVelRing(const KParams<F> &p_) : p(p_) {}
+    template <int c, int dk, int di, int dj> __device__ __forceinline__ F S() const {
+        if constexpr (dk == 0 && di == 0) {
+            if constexpr (c == 0) return sxx0;
+            else if constexpr (c == 1) return syy[dj + 1];
+            else if constexpr (c == 2) return szz0;
+            else if constexpr (c == 3) return syz[dj + 2];
+            else if constexpr (c == 4) return sxz0;
+            else return sxy[dj + 2];
+        } else {
+            static_assert(dj == 0, "in-plane neighbour expected");
+            const F *b = c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy;
+            return ldro(b + n + dk + di * p.SI);
+        }
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float rho() const {
+        if constexpr (dk == 0 && di == 0) return dj == 0 ? rho0 : rho_j1;
+        else return ldro(p.rho + n + dk + di * p.SI);
+    }
+    __device__ __forceinline__ F V(int f) const { return v[f]; }
+};
+
+#ifndef SWPC_RING_MINB
+#define SWPC_RING_MINB 2
+#endif
+#ifndef SWPC_RING_THREADS
+#define SWPC_RING_THREADS 256
+#endif
+template <typename F>
+__global__ void __launch_bounds__(SWPC_RING_THREADS, SWPC_RING_MINB) vel_ring(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
+    const int k = b.k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int li = b.li0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (k > b.k1 || li > b.li1) return;
+    const int mi = li + HALO;
+    const int ljs = b.lj0 + blockIdx.z * jlen;
+    const int lje = min(ljs + jlen, b.lj1 + 1);
+    const long long sj = p.SJ;
+    AccVelRing<F> a(p);
+    long long col = (long long)mi + (long long)p.NXM * (ljs + HALO);
+    a.n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+    {   // prologue: the ring and the own-column values of the first plane
+        const long long n = a.n;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            a.syy[q] = ldro(p.Syy + n + (q - 1) * sj);
+            a.sxy[q] = ldro(p.Sxy + n + (q - 2) * sj);
+            a.syz[q] = ldro(p.Syz + n + (q - 2) * sj);
+        }
+        a.sxx0 = ldro(p.Sxx + n); a.szz0 = ldro(p.Szz + n); a.sxz0 = ldro(p.Sxz + n);
+        a.v[0] = lds_(p.Vx + n); a.v[1] = lds_(p.Vy + n); a.v[2] = lds_(p.Vz + n);
+        a.rho0 = ldro(p.rho + n); a.rho_j1 = ldro(p.rho + n + sj);
+    }
+    int4 bnd = p.band[col];
+    for (int lj = ljs; lj < lje; lj++) {
+        const long long n = a.n;
+        const bool more = (lj + 1 < lje);
+        // loads for plane j+1 (consumed next iteration)
+        F nsxx = 0, nszz = 0, nsxz = 0, nsyy = 0, nsxy = 0, nsyz = 0, nv0 = 0, nv1 = 0, nv2 = 0;
+        float nrho = 0.0f;
+        int4 nbnd = bnd;
+        if (more) {
+            nsxx = ldro(p.Sxx + n + sj); nszz = ldro(p.Szz + n + sj); nsxz = ldro(p.Sxz + n + sj);
+            nsyy = ldro(p.Syy + n + 3 * sj); nsxy = ldro(p.Sxy + n + 2 * sj); nsyz = ldro(p.Syz + n + 2 * sj);
+            nv0 = lds_(p.Vx + n + sj); nv1 = lds_(p.Vy + n + sj); nv2 = lds_(p.Vz + n + sj);
+            nrho = ldro(p.rho + n + 2 * sj);
+            nbnd = p.band[col + p.NXM];
+            if (pf > 0 && lj + 1 + pf < lje) {   // optional L2 prefetch further ahead
+                const long long q = n + sj * (1 + pf);
+                pf_l2(p.Sxx + q); pf_l2(p.Szz + q); pf_l2(p.Sxz + q); pf_l2(p.Vx + q); pf_l2(p.Vy + q); pf_l2(p.Vz + q);
+                pf_l2(p.Syy + q + 2 * sj); pf_l2(p.Sxy + q + sj); pf_l2(p.Syz + q + sj); pf_l2(p.rho + q + sj);
+            }
+        }
+        F vx, vy, vz;
+        vel_interior_calc<F>(p, a, k, mi, lj + HALO, bnd, vx, vy, vz);
+        sts_(p.Vx + n, vx); sts_(p.Vy + n, vy); sts_(p.Vz + n, vz);
+        // rotate
+        a.syy[0] = a.syy[1]; a.syy[1] = a.syy[2]; a.syy[2] = a.syy[3]; a.syy[3] = nsyy;
+        a.sxy[0] = a.sxy[1]; a.sxy[1] = a.sxy[2]; a.sxy[2] = a.sxy[3]; a.sxy[3] = nsxy;
+        a.syz[0] = a.syz[1]; a.syz[1] = a.syz[2]; a.syz[2] = a.syz[3]; a.syz[3] = nsyz;
+        a.sxx0 = nsxx; a.szz0 = nszz; a.sxz0 = nsxz;
+        a.v[0] = nv0; a.v[1] = nv1; a.v[2] = nv2;
+        a.rho0 = a.rho_j1; a.rho_j1 = nrho;
+        bnd = nbnd;
+        a.n += sj;
+        col += p.NXM;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // source time functions, m_fdtool.f90:339-497 (PI is real(DP) there)
 __device__ __forceinline__ float momentrate_dev(float t, int stf, float ts, float tr) {
     const double PI = 3.14159265358979323846;

@@ -196,6 +196,14 @@ static inline size_t ora_idx2(const ora_rank *r, int i, int j) {
     return (size_t)(i - r->ibeg_m) + (size_t)r->nxm * (size_t)(j - r->jbeg_m);
 }
 
+/* ---------------------------------------------------------------- heavier model builders (ora_models.c) */
+int ora_rdrmed3d(int ib, int ie, int jb, int je, int kb, int ke, const char *fn, float *vol, char *err, size_t cap);
+int ora_vmodel_lgm(const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
+int ora_vmodel_uni_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
+int ora_vmodel_lhm_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
+int ora_vmodel_lgm_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
+void ora_stabilize_absorber(const ora_cfg *c, ora_rank *r);
+
 /* ---------------------------------------------------------------- life cycle / driver API */
 /* base_dir: directory against which relative file names in the ini are resolved (the reference
  * resolves against the cwd of the run; tests pass the reference's top directory or a tmp dir). */

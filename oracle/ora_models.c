@@ -45,6 +45,13 @@ static unsigned long long be_u(const unsigned char *p, int n) {
     return v;
 }
 
+static void copy_name(char *dst, const unsigned char *src, unsigned n) {
+    if (!dst) return;
+    size_t c = n < 127 ? n : 127;
+    memcpy(dst, src, c);
+    dst[c] = 0;
+}
+
 static void nc_close(nc_file *f) {
     if (!f) return;
     free(f->buf);
@@ -71,7 +78,7 @@ static nc_file *nc_open_classic(const char *path, char *err, size_t cap) {
     const int offw = b[3] == 2 ? 8 : 4;
     size_t p = 8; /* magic + numrecs */
 #define U4() (p += 4, (unsigned)be_u(b + p - 4, 4))
-#define SKIPNAME(dst) do { unsigned nl_ = U4(); if (dst) { size_t c_ = nl_ < 127 ? nl_ : 127; memcpy(dst, b + p, c_); ((char *)dst)[c_] = 0; } p += (nl_ + 3u) & ~3u; } while (0)
+#define SKIPNAME(dst) do { unsigned nl_ = U4(); copy_name(dst, b + p, nl_); p += (nl_ + 3u) & ~3u; } while (0)
     /* dim_list */
     unsigned tag = U4(), n = U4();
     if (tag == 0x0A) {

@@ -404,9 +404,17 @@ static int medium_setup(ora_sim *s, ora_rank *r, const ora_ini *ini, const char 
         ora_readini_s(ini, "vcut", &c->vcut, 0.0f);
         if (!strcmp(vt, "uni")) vmodel_uni(ini, r, c->vcut, r->taup, r->taus);
         else if (!strcmp(vt, "lhm")) { if (vmodel_lhm(ini, base, r, c->vcut, r->taup, r->taus)) return -1; }
-        else {
+        else if (!strcmp(vt, "lgm") || !strcmp(vt, "uni_rmed") || !strcmp(vt, "lhm_rmed") || !strcmp(vt, "lgm_rmed")) { /* ora_models.c */
+            char m[700] = "";
+            int rc;
+            if (!strcmp(vt, "lgm")) rc = ora_vmodel_lgm(ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else if (!strcmp(vt, "uni_rmed")) rc = ora_vmodel_uni_rmed(c, ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else if (!strcmp(vt, "lhm_rmed")) rc = ora_vmodel_lhm_rmed(c, ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else rc = ora_vmodel_lgm_rmed(c, ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
+            if (rc) { set_err(m); return -1; }
+        } else {
             char m[300];
-            snprintf(m, sizeof(m), "vmodel_type '%s' is outside the hot-path scope (uni, lhm, benchmark)", vt);
+            snprintf(m, sizeof(m), "vmodel_type '%s' is not restated (user plug-in, grd / grd_rmed need GMT netCDF-4 grids)", vt);
             set_err(m);
             return -1;
         }
@@ -506,12 +514,6 @@ static int medium_setup(ora_sim *s, ora_rank *r, const ora_ini *ini, const char 
     *vmin1 = vmn;
     *vmax1 = vmx;
 
-    int stab;
-    ora_readini_l(ini, "stabilize_pml", &stab, 0);
-    if (stab) {
-        set_err("stabilize_pml=.true. is outside the hot-path scope");
-        return -1;
-    }
     return 0;
 }
 
@@ -1089,6 +1091,12 @@ static ora_sim *create_from_ini(ora_ini *ini, const char *base_dir, int nm, int 
     }
     c->vmin = vmin; /* mpi_allreduce m_medium.f90:424-425 */
     c->vmax = vmax;
+    {   /* m_medium.f90:218-222: after velocity_minmax, with the global vmax */
+        int stab;
+        ora_readini_l(ini, "stabilize_pml", &stab, 0);
+        if (stab)
+            for (int q = 0; q < s->nranks; q++) ora_stabilize_absorber(c, &s->r[q]);
+    }
     kernel_setup(s);
     if (source_setup(s, ini, base_dir)) { ora_destroy(s); return NULL; }
     if (absorb_setup(s)) { ora_destroy(s); return NULL; }

@@ -43,6 +43,8 @@ def write_case(d: Path, *, nx=48, ny=40, nz=44, nt=40, dx=0.5, dy=0.5, dz=0.5, d
     (d / "lhm_land.dat").write_text(LHM_LAND)
     if vmodel == "uni":
         vm = "vmodel_type = 'uni'\n vp0 = 5.0\n vs0 = 2.9\n rho0 = 2.6\n qp0 = 300\n qs0 = 150\n topo0 = 0.4\n"
+    elif vmodel.startswith("raw:"):   # the caller supplies the vmodel lines itself
+        vm = vmodel[4:]
     else:
         vm = f"vmodel_type = 'lhm'\n fn_lhm = '{vmodel}.dat'\n"
     inf = f"""
@@ -139,3 +141,45 @@ def rel_l2(a, b):
     d = np.sqrt(np.sum((a - b) ** 2))
     n = np.sqrt(np.sum(b ** 2))
     return d / n if n > 0 else d
+
+
+def write_rmed(path: Path, xi: np.ndarray, dx=0.5) -> None:
+    """A random-media volume laid out as tools/gen_rmed3d.f90:91-135 creates it: netCDF classic (NF90_CLOBBER), dimensions
+    x, y, z, variables x, y, z and -- 4th, which is how m_rdrmed.f90:93 finds it -- the volume with x fastest.  Written
+    byte by byte from the classic-format specification (scipy's writer reorders variables); tests read it back with scipy's
+    reader as an independent check.  xi has shape (nz, ny, nx)."""
+    import struct
+
+    nz, ny, nx = xi.shape
+
+    def name(s):
+        b = s.encode()
+        return struct.pack(">I", len(b)) + b + b"\0" * (-len(b) % 4)
+
+    def att_text(k, v):
+        b = v.encode()
+        return name(k) + struct.pack(">II", 2, len(b)) + b + b"\0" * (-len(b) % 4)
+
+    dims = struct.pack(">II", 0x0A, 3) + b"".join(name(n) + struct.pack(">I", m) for n, m in (("x", nx), ("y", ny), ("z", nz)))
+    gatts = struct.pack(">II", 0x0C, 1) + att_text("title", "random media")
+    shapes = [("x", [0], nx), ("y", [1], ny), ("z", [2], nz), ("random media", [2, 1, 0], nx * ny * nz)]
+
+    def var_list(begins):
+        out = struct.pack(">II", 0x0B, len(shapes))
+        for (n, dimids, cnt), beg in zip(shapes, begins):
+            out += name(n) + struct.pack(">I", len(dimids)) + b"".join(struct.pack(">I", d) for d in dimids)
+            out += struct.pack(">II", 0, 0)                      # no attributes
+            out += struct.pack(">III", 5, cnt * 4, beg)          # NC_FLOAT, vsize, begin
+        return out
+
+    head = b"CDF\x01" + struct.pack(">I", 0) + dims + gatts
+    off = len(head) + len(var_list([0] * 4))
+    begins = []
+    for _, _, cnt in shapes:
+        begins.append(off)
+        off += cnt * 4
+    with open(path, "wb") as f:
+        f.write(head + var_list(begins))
+        for n in (nx, ny, nz):
+            f.write((np.arange(n) * dx).astype(">f4").tobytes())
+        f.write(np.ascontiguousarray(xi).astype(">f4").tobytes())

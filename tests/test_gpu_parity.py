@@ -118,10 +118,10 @@ def test_step_entry_point_and_run(tmp_path):
     _compare(o, [d], exact=True)
 
 
-@pytest.mark.parametrize("variant", [{"tma": 0}, {"tma": 1}, {"tma": 2}])
+@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}])
 @pytest.mark.parametrize("abc", ["pml", "cerjan"])
 def test_kernel_variants_bit_exact(tmp_path, variant, abc):
-    # every kernel variant of the two sweeps (direct, TMA-staged stress, TMA-staged stress + velocity) shares one arithmetic body
+    # every kernel variant of the two sweeps (direct, TMA-staged stress, TMA-staged stress + velocity, register-ring velocity) shares one arithmetic body
     o, devs = _run_pair(tmp_path, 24, nranks=(2, 1), nx=70, ny=44, abc_type=abc, options=variant,
                         sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
     _compare(o, devs, exact=True)
