@@ -5,8 +5,8 @@ Metric (BASELINE.json): 3-D viscoelastic cell-updates/s (+ % of the HBM roofline
   N = 1 : BASELINE configs[3] -- swpc_3d, NM=3 GZB, ADE-CFS PML (na=20), synthetic layered model (the 8-layer table
           of the reference's example/lhm.dat), 1024 x 1024 x 512 on one B200, float64 fields (reference default MP=DP).
   N > 1 : BASELINE configs[4] shape -- weak scaling, 512 x 1024 x 1024 cells per GPU, x-y decomposition 2x1 / 4x1 / 4x2,
-          NCCL send/recv halo exchange (the layered model stands in for the heterogeneous crust: the kernels' traffic
-          does not depend on the medium values).
+          NCCL send/recv halo exchange overlapped with the core sweeps; synthetic heterogeneous crust = the layered table
+          with Gaussian random media per layer (vmodel lhm_rmed).
 A "step" is one iteration of main.f90:119-139 (stress sweep, stress glut, halo, velocity sweep, halo).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -45,9 +45,20 @@ LHM = """# depth  rho  vp  vs  Qp  Qs   (example/lhm.dat of the reference)
 """
 
 
-def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: int, dx=0.5, dt=0.025, na=20) -> Path:
+def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: int, dx=0.5, dt=0.025, na=20, hetero=False) -> Path:
     d.mkdir(parents=True, exist_ok=True)
     (d / "lhm.dat").write_text(LHM)
+    if hetero:
+        # configs[4]: heterogeneous crust = the layered table with a random-media volume per layer (vmodel lhm_rmed,
+        # m_vmodel_lhm_rmed.f90: Vp, Vs * (1 + xi), rho * (1 + 0.8 xi)); xi ~ N(0, 0.03^2), Gaussian-smoothed, periodic,
+        # two independent 96^3 volumes alternating between layers, seeds 20251017 / 20251018
+        from openswpc_b200.rmed import smoothed_gaussian, write_rmed3d
+
+        for q in range(2):
+            write_rmed3d(d / f"rmed{q}.nc", smoothed_gaussian((96, 96, 96), 3.0, 0.03, 20251017 + q), dx)
+        rows = [ln for ln in LHM.splitlines() if ln.strip() and not ln.lstrip().startswith("#")]
+        (d / "lhm_rmed.dat").write_text("# depth rho vp vs Qp Qs rmed\n" + "\n".join(f"{ln} rmed{q % 2}.nc" for q, ln in enumerate(rows)) + "\n")
+    vm = " vmodel_type = 'lhm_rmed'\n fn_lhm_rmed = 'lhm_rmed.dat'\n dir_rmed = '.'\n rhomin = 1.0" if hetero else " vmodel_type = 'lhm'\n fn_lhm = 'lhm.dat'"
     (d / "source.dat").write_text("# x y z tbeg trise mo mxx myy mzz myz mxz mxy\n 0.0 0.0 10.0 0.1 4.0 1.e15 0.8165 0.8165 0.8165 0.0 0.0 0.0\n")
     st = []
     for a in range(8):
@@ -88,8 +99,7 @@ def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: i
  fn_stf = 'source.dat'
  abc_type = 'pml'
  na = {na}
- vmodel_type = 'lhm'
- fn_lhm = 'lhm.dat'
+{vm}
  munk_profile = .true.
 """
     p = d / "input.inf"
@@ -207,6 +217,7 @@ def main():
     ap.add_argument("--grid", default="", help="nx,ny,nz per GPU (development only; default = the BASELINE workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--opts", default="", help="key=value,... library options (development only, e.g. overlap=0)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -223,7 +234,10 @@ def main():
     else:
         bx, by, bz = 512, 1024, 1024
     nx, ny, nz = bx * npx, by * npy, bz
-    workload = (f"swpc_3d viscoelastic NM=3 GZB + ADE-CFS PML na=20, synthetic layered model (lhm, 8 layers), "
+    hetero = world > 1
+    model = ("synthetic heterogeneous crust (lhm_rmed: 8 layers x Gaussian random media, eps = 3 %)" if hetero
+             else "synthetic layered model (lhm, 8 layers)")
+    workload = (f"swpc_3d viscoelastic NM=3 GZB + ADE-CFS PML na=20, {model}, "
                 f"{nx}x{ny}x{nz} global, {npx}x{npy} x-y decomposition, {bx}x{by}x{bz} per GPU")
     config = {"workload": workload, "grid": [nx, ny, nz], "per_gpu_grid": [bx, by, bz], "decomposition": [npx, npy], "nm": nm,
               "abc_type": "pml", "na": 20, "field_type": a.dtype, "other_arrays": "f32", "dt": 0.025, "dx": 0.5,
@@ -263,7 +277,7 @@ def main():
     nt = Wm + 2 * K + 2
     td = tempfile.TemporaryDirectory()
     wdir = Path(td.name) / f"rank{rank}"
-    inf = write_workload(wdir, nx, ny, nz, nt, npx, npy)
+    inf = write_workload(wdir, nx, ny, nz, nt, npx, npy, hetero=hetero)
     t_setup = time.perf_counter()
     run = Swpc3d(inf, base_dir=wdir, nm=nm, myid=rank, field_dtype=fdt)
     allreduce_minmax(run)
@@ -273,6 +287,8 @@ def main():
     attach_nccl(run)
     run.device_call("swpc3d_sync")
     t_upload = time.perf_counter() - t_up
+    for kv in filter(None, a.opts.split(",")):
+        run.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 
     def barrier():
         run.device_call("swpc3d_sync")
@@ -301,7 +317,18 @@ def main():
     barrier()
     launches = run.info("launches") - l0
     ms_stress, ms_vel = run.info("ms_stress"), run.info("ms_vel")
+    ms_halo, n_halo, halo_bytes = run.info("ms_halo"), run.info("n_halo"), run.info("halo_bytes")
     run.set_option("kernel_timing", 0)
+    # the halo phase on its own (nothing else on the GPU): 10 velocity exchanges, idempotent on an up-to-date halo
+    ms_halo_alone = 0.0
+    if world > 1:
+        run.set_option("kernel_timing", 1)
+        barrier()
+        for _ in range(10):
+            run.device_call("swpc3d_comm_vel")
+        barrier()
+        ms_halo_alone = run.info("ms_halo")
+        run.set_option("kernel_timing", 0)
 
     # ---- timed region 2 (e2e): the call a user makes -- Swpc3d.run() + waveform read-back, host wall clock.
     # Every step the host evaluates the moment-rate values and copies them to the device; every ntdec_r steps the
@@ -319,8 +346,8 @@ def main():
     h2d = 4.0 * nsrc
     d2h = (12.0 * len(vm) + 4.0 * 3 * nst * ntw) / K
     interior, pml = cell_counts(run)
-    stats = torch.tensor([ms, t_e2e * 1e3, launches, h2d, d2h, float(interior), float(pml), ms_stress, ms_vel], dtype=torch.float64,
-                         device="cuda")
+    stats = torch.tensor([ms, t_e2e * 1e3, launches, h2d, d2h, float(interior), float(pml), ms_stress, ms_vel, ms_halo,
+                          halo_bytes / max(n_halo, 1.0), ms_halo_alone], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -357,7 +384,7 @@ def main():
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": config,
-        "roofline": {"bound": "hbm", "kernel": "sweep_direct<F,NM=3,STRESS> (fused interior+PML stress sweep)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "fused stress sweep: stress_tma<F,NM=3> (interior tiles) + sweep_direct<F,3,1> (absorber shell)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": stress_bytes, "ms_per_launch": ms_stress,
                      "bytes_per_cell": bpc, "cells_interior": interior, "cells_absorber": pml},
@@ -370,6 +397,17 @@ def main():
                 "what": "Swpc3d.run() (host-evaluated source terms H2D every step, max-amplitude D2H every ntdec_r steps) + station "
                         "traces D2H + SAC write; fields stay device-resident as in the reference's `!$acc enter data` design",
                 "one_time_upload_s": t_upload, "host_setup_s": t_host},
+        "halo": None if world == 1 else {
+            "what": "one exchange = pack kernels + ncclSend/ncclRecv with up to 4 neighbours + unpack kernels of one field family "
+                    "(2 exchanges per step), CUDA events on the exchange stream; it runs beside the core sweep (boundary-first overlap)",
+            "ms_per_exchange_overlapped_max": float(mx[9]), "ms_per_exchange_alone_max": float(mx[11]),
+            "bytes_sent_per_exchange_max": float(mx[10]),
+            "achieved_GBs_per_direction": float(mx[10]) / (float(mx[11]) / 1e3) / 1e9 if mx[11] > 0 else None,
+            "nvlink_peak_GBs_per_direction": 900.0,
+            "nvlink_frac": float(mx[10]) / (float(mx[11]) / 1e3) / 1e9 / 900.0 if mx[11] > 0 else None,
+            "nvlink_frac_note": "bytes sent by the busiest rank / time of the exchange run alone (pack + NCCL + unpack kernels included) / 900 GB/s",
+            "exposed_ms_per_step": max(0.0, ms_max / K - float(mx[7]) - float(mx[8])),
+            "overlap": "boundary-first: exchange stream overlaps the core sweeps"},
         "gpu_launches": int(sm[2]),
         "clocks": clocks,
         "progress_lines": [[float(x) for x in r] for r in vm[-2:]],

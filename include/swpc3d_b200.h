@@ -100,6 +100,17 @@ int swpc3d_set_wav_products(swpc3d_handle *h, int32_t sw_v, int32_t sw_u, int32_
  * 2 stress (ntw,6,nst) [Pa], 3 strain (ntw,6,nst) */
 int swpc3d_get_wav_product(swpc3d_handle *h, int32_t which, float *out);
 
+/* Green's-function mode, m_green.f90.  green__setup's device copy-in (:351): the grid points of this rank (global 1-based
+ * indices), the pseudo source (a station; is_src as redefined at :185-186, i.e. inside ibeg..iend+1 x jbeg..jend+1), the unit
+ * force direction fx1 fy1 fz1 (:146-154), green_trise, stftype, ntdec_w and ntw.  bforce = green_bforce (9 instead of 6 traces). */
+int swpc3d_set_green(swpc3d_handle *h, int32_t ng, const int32_t *ig, const int32_t *jg, const int32_t *kg, int32_t bforce,
+                     int32_t is_src, int32_t isrc, int32_t jsrc, int32_t ksrc, float fx1, float fy1, float fz1, float trise,
+                     const char *stftype, int32_t ntdec_w, int32_t ntw, float tbeg);
+int swpc3d_green_store(swpc3d_handle *h, int32_t it);    /* green__store  m_green.f90:357-551 */
+int swpc3d_green_source(swpc3d_handle *h, int32_t it);   /* green__source m_green.f90:606-649 */
+/* `!$acc update self(gf)` m_green.f90:562: gf(ntw, ncmp*ng), ntw fastest, sign as stored (green__export flips z) */
+int swpc3d_get_green(swpc3d_handle *h, float *gf);
+
 /* the hot path, one call per reference subroutine */
 int swpc3d_update_stress(swpc3d_handle *h);            /* kernel__update_stress m_kernel.f90:142 + absorb__update_stress m_absorb.f90:60 (fused) */
 int swpc3d_stressglut(swpc3d_handle *h, int32_t it);   /* source__stressglut    m_source.f90:776 */
@@ -108,7 +119,8 @@ int swpc3d_update_vel(swpc3d_handle *h);               /* kernel__update_vel m_k
 int swpc3d_bodyforce(swpc3d_handle *h, int32_t it);    /* source__bodyforce     m_source.f90:850 */
 int swpc3d_comm_vel(swpc3d_handle *h);                 /* global__comm_vel      m_global.f90:391 */
 int swpc3d_wav_store(swpc3d_handle *h, int32_t it);    /* wav__store (velocity) m_wav.f90:515-539 */
-/* one whole iteration of main.f90:119-139 (wav_store, stress, glut, comm, vel, bodyforce, comm) */
+/* one whole iteration of main.f90:119-139 (green_store, wav_store, stress, glut, comm, vel, bodyforce, green_source, comm);
+ * with neighbours the exchange runs boundary-first on a second stream beside the core sweeps (option "overlap", default 1) */
 int swpc3d_step(swpc3d_handle *h, int32_t it);
 /* it = it0..it1 without returning to the host in between */
 int swpc3d_run(swpc3d_handle *h, int32_t it0, int32_t it1);

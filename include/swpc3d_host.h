@@ -56,6 +56,14 @@ swpc3d_handle *swpc3d_host_handle(swpc3d_host *h);
 int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, float *vm, int32_t nvm, int32_t *nrec);
 /* wav__write (m_wav.f90:658-792), SAC format: <odir>/wav/<title>.3d.<stnm>.<cmp>.sac ; returns file count in *nfiles */
 int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles);
+/* Green's-function mode (green_mode = .true., m_green.f90).  The pseudo source is a station: its owner rank finds it with
+ * wav__stquery and the reference broadcasts indices and coordinates (m_green.f90:161-183).  A multi-rank host does the
+ * same: query every rank, hand the owner's answer to all of them (single-rank runs need neither call).
+ * swpc3d_host_write_green = green__export (:553-604): wav_format 'sac' -> <odir>/green/<stnm>/<title>__<gid>__<stnm>__<cmp>__<mij>__.sac,
+ * 'csf' -> one container per rank.  Extra get_int names: green_mode ng green_ncmp green_ntw; arrays: green_ijk (3,ng) green_gid green_gf. */
+int swpc3d_host_green_query(swpc3d_host *h, int32_t *found, int32_t ijk[3], float xyz[3], float lonlat[2]);
+int swpc3d_host_green_set_source(swpc3d_host *h, const int32_t ijk[3], const float xyz[3], const float lonlat[2]);
+int swpc3d_host_write_green(swpc3d_host *h, const char *odir, int32_t *nfiles);
 /* snapshots (m_snap.f90, snp_format = 'netcdf'): create <odir>/<title>.3d.<xy|xz|yz|fs|ob>.<ps|v|u>.nc on the I/O ranks
  * (call after attach_device / comm init and before the first swpc3d_host_run); swpc3d_host_run then writes one record every
  * ntdec_s steps; swpc3d_host_snap_close flushes the running maxima (max-V/H/A) and closes (snap__closefiles). */

@@ -16,7 +16,7 @@ CSRC = PKG / "csrc"
 ROOT = PKG.parent
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-Xcompiler", "-ffp-contract=off", "-shared", "-diag-suppress", "177"]
+              "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-fopenmp", "-shared", "-diag-suppress", "177"]
 
 
 def build(fmad: bool = False, force: bool = False, verbose: bool = False) -> Path:
@@ -30,7 +30,7 @@ def build(fmad: bool = False, force: bool = False, verbose: bool = False) -> Pat
             return LIB_PATH
     LIB_PATH.parent.mkdir(parents=True, exist_ok=True)
     cmd = ["nvcc", *NVCC_FLAGS, f"-fmad={'true' if fmad else 'false'}", "-I", str(ROOT / "include"), "-o", str(LIB_PATH),
-           *map(str, srcs), "-ldl"]
+           *map(str, srcs), "-ldl", "-lgomp"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
@@ -69,6 +69,7 @@ SYMBOLS = [
     "swpc3d_bodyforce", "swpc3d_comm_vel", "swpc3d_wav_store", "swpc3d_step", "swpc3d_run", "swpc3d_sync", "swpc3d_vmax",
     "swpc3d_get_wav", "swpc3d_vmax_global", "swpc3d_set_wav_products", "swpc3d_get_wav_product", "swpc3d_snap_setup", "swpc3d_snap_step", "swpc3d_snap_fetch",
     "swpc3d_snap_fetch_max", "swpc3d_reduce_sum", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
+    "swpc3d_set_green", "swpc3d_green_store", "swpc3d_green_source", "swpc3d_get_green",
 ]
 
 _lib = None
@@ -112,6 +113,10 @@ def load() -> C.CDLL:
     lib.swpc3d_nccl_unique_id.argtypes = [C.c_char_p]
     lib.swpc3d_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     lib.swpc3d_comm_local.argtypes = [C.POINTER(vp), i32, i32]
+    lib.swpc3d_set_green.argtypes = [vp, i32, ip, ip, ip, i32, i32, i32, i32, i32] + [C.c_float] * 4 + [cp, i32, i32, C.c_float]
+    lib.swpc3d_green_store.argtypes = [vp, i32]
+    lib.swpc3d_green_source.argtypes = [vp, i32]
+    lib.swpc3d_get_green.argtypes = [vp, fp]
     lib.swpc3d_timer_start.argtypes = [vp]
     lib.swpc3d_timer_stop.argtypes = [vp, fp]
     lib.swpc3d_set_option.argtypes = [vp, cp, i32]

@@ -129,6 +129,11 @@ struct swpc3d_handle {
     float *wav_u = nullptr, *wav_s = nullptr, *wav_e = nullptr, *wav_acc = nullptr;
     int sw_v = 1, sw_u = 0, sw_stress = 0, sw_strain = 0;
     float M0 = 1.f, UC = 1e-15f;
+    // Green's-function mode (m_green.f90)
+    int ng = 0, g_ncmp = 6, g_bforce = 0, g_ntdec_w = 1, g_ntw = 0, g_stf = 3, g_is_src = 0, g_src[3] = {0, 0, 0};
+    float g_f[3] = {0, 0, 0}, g_trise = 1.0f, g_dt_dxyz = 0.0f;
+    int *g_ijk = nullptr;
+    float *g_acc = nullptr, *g_gf = nullptr;
     unsigned int *vmax_d = nullptr;
     // snapshots
     swpc3d_snap_cfg snap{};
@@ -155,6 +160,12 @@ struct swpc3d_handle {
     bool vtma_ok = false;
     int variant = 1;
     int use_ring = 1, ring_jlen = 32, ring_pf = 2;   // vel_ring: register-pipelined interior velocity sweep
+    // boundary-first overlap of the halo exchange (swpc3d_step): the two outermost owned planes towards every neighbour are
+    // swept first, then pack / NCCL / unpack run on `cs` while the core of the subdomain is swept on `st`
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev_b = nullptr, ev_c = nullptr;
+    int overlap = 1;       // 0: the reference's fully exposed order
+    int split_test = 0;    // testing aid: split the sweeps as if all four faces had neighbours, without any exchange
     int pw_mode = 0;   // plane-wave mode: edge extrapolation ahead of the PML sweeps
     int zero_outer = 0;   // re-zero the outer halo planes at every exchange (see launch_halo)
     long long launches = 0;
@@ -163,6 +174,9 @@ struct swpc3d_handle {
     bool ktiming = false;
     std::vector<cudaEvent_t> kev[2][2];   // [stress|vel][begin|end]
     size_t kev_used[2] = {0, 0};
+    std::vector<cudaEvent_t> cev[2];      // halo exchange (pack + NCCL + unpack) [begin|end]
+    size_t cev_used = 0;
+    double halo_bytes = 0.0;              // bytes this rank sent since kernel_timing was switched on
 };
 
 static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
@@ -263,6 +277,9 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
         CK(cudaEventCreateWithFlags(&h->ev_join[q], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0));
     CK(cudaEventCreate(&h->ev1));
     // the nine fields live in ONE allocation (field f at f*ncell) so that a single 4-D TMA tensor covers them
@@ -334,6 +351,7 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     for (int q = 0; q < 15; q++) { cudaFree(h->snap_buf[q]); cudaFree(h->snap_max[q]); } cudaFree(h->aoff); cudaFree(h->aux);
     for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
     cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
+    cudaFree(h->g_ijk); cudaFree(h->g_acc); cudaFree(h->g_gf);
     cudaFree(h->st_ijk); cudaFree(h->wav); cudaFree(h->wav_u); cudaFree(h->wav_s); cudaFree(h->wav_e); cudaFree(h->wav_acc); cudaFree(h->vmax_d);
     for (int f = 0; f < 4; f++) { cudaFree(h->sbuf[f]); cudaFree(h->rbuf[f]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -343,6 +361,9 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
         if (h->ev_join[q]) cudaEventDestroy(h->ev_join[q]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_b) cudaEventDestroy(h->ev_b);
+    if (h->ev_c) cudaEventDestroy(h->ev_c);
+    if (h->cs) cudaStreamDestroy(h->cs);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
     return 0;
@@ -631,15 +652,41 @@ static int tma_prepare(swpc3d_handle *h) {
     return 0;
 }
 
-// The box of whole TK x TI tiles inside the interior kernel box that stress_tma handles; empty if TMA is off.
+// A sweep covers a rectangle of owned columns (local 0-based, inclusive): the whole subdomain, or -- boundary-first
+// overlap -- its core (everything but the two outermost planes towards each neighbour) and the boundary slabs.
+struct Region { int li0, li1, lj0, lj1; };
+static Region whole_region(const swpc3d_handle *h) { return Region{0, h->nxp - 1, 0, h->nyp - 1}; }
+static bool face_split(const swpc3d_handle *h, int f) { return h->split_test || h->nbr[f] >= 0; }
+static Region core_region(const swpc3d_handle *h) {   // faces: 0 +x, 1 -x, 2 +y, 3 -y; planes sent: 2 per face (m_global.f90:416-443, 527-553)
+    Region r = whole_region(h);
+    if (face_split(h, 1)) r.li0 += 2;
+    if (face_split(h, 0)) r.li1 -= 2;
+    if (face_split(h, 3)) r.lj0 += 2;
+    if (face_split(h, 2)) r.lj1 -= 2;
+    return r;
+}
+// the boundary slabs: x slabs over every owned j, y slabs over the core's i range only (each cell exactly once)
+static int boundary_boxes(const swpc3d_handle *h, Box3 out[4]) {
+    const Region c = core_region(h);
+    const int nz = h->g.nz;
+    int n = 0;
+    if (c.li0 > 0) out[n++] = Box3{1, nz, 0, c.li0 - 1, 0, h->nyp - 1, 0};
+    if (c.li1 < h->nxp - 1) out[n++] = Box3{1, nz, c.li1 + 1, h->nxp - 1, 0, h->nyp - 1, 0};
+    if (c.lj0 > 0) out[n++] = Box3{1, nz, c.li0, c.li1, 0, c.lj0 - 1, 0};
+    if (c.lj1 < h->nyp - 1) out[n++] = Box3{1, nz, c.li0, c.li1, c.lj1 + 1, h->nyp - 1, 0};
+    return n;
+}
+
+// The box of whole TK x TI tiles inside (interior kernel box) x (region) that stress_tma handles; empty if TMA is off.
 template <typename F, int NM>
-static Box3 tma_box(const swpc3d_handle *h) {
+static Box3 tma_box(const swpc3d_handle *h, const Region &rg) {
     using C = TmaCfg<F, NM>;
     Box3 b{1, 0, 0, -1, 0, -1, 0};
     if (!h->use_tma || !h->tma_ok) return b;
     const swpc3d_grid &g = h->g;
     const int nkt = (g.kend_k + C::TK - 1) / C::TK;                     // interior k is 1..kend_k; the last tile may be partial
-    const int li0 = g.ibeg_k - g.ibeg, li1 = g.iend_k - g.ibeg, lj0 = g.jbeg_k - g.jbeg, lj1 = g.jend_k - g.jbeg;
+    const int li0 = std::max(g.ibeg_k - g.ibeg, rg.li0), li1 = std::min(g.iend_k - g.ibeg, rg.li1);
+    const int lj0 = std::max(g.jbeg_k - g.jbeg, rg.lj0), lj1 = std::min(g.jend_k - g.jbeg, rg.lj1);
     const int nit = (li1 - li0 + 1) / C::TI;
     if (nkt < 1 || nit < 1 || lj1 < lj0) return b;
     // (the last tile may reach past the padded column: TMA zero-fills out-of-bounds elements, and those lanes are masked)
@@ -648,11 +695,11 @@ static Box3 tma_box(const swpc3d_handle *h) {
 }
 
 template <typename F, int NM>
-static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p) {
+static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg) {
     using C = TmaCfg<F, NM>;
     if (!h->tma_ready) tma_prepare<F, NM>(h);
-    const Box3 t = tma_box<F, NM>(h);
-    const Box3 all{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0};
+    const Box3 t = tma_box<F, NM>(h, rg);
+    const Box3 all{1, h->g.nz, rg.li0, rg.li1, rg.lj0, rg.lj1, 0};
     if (t.k1 < t.k0) return launch_direct_box<F, true>(h, p, all);
     TmaGeom g{};
     g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
@@ -661,8 +708,8 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p) {
     // complement of the TMA box inside the owned box: two j slabs, two i slabs, one k slab (absorber cells only: the TMA
     // tiles already did every interior cell, also in the partial last k-tile).  All six launches touch disjoint cells and
     // only read V, so the shell boxes run on side streams next to the interior kernel.
-    const Box3 boxes[5] = {Box3{1, h->g.nz, 0, h->nxp - 1, 0, t.lj0 - 1, 0}, Box3{1, h->g.nz, 0, h->nxp - 1, t.lj1 + 1, h->nyp - 1, 0},
-                           Box3{1, h->g.nz, 0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, h->nxp - 1, t.lj0, t.lj1, 0},
+    const Box3 boxes[5] = {Box3{1, h->g.nz, rg.li0, rg.li1, rg.lj0, t.lj0 - 1, 0}, Box3{1, h->g.nz, rg.li0, rg.li1, t.lj1 + 1, rg.lj1, 0},
+                           Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0},
                            Box3{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1}};
     if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
     stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
@@ -682,19 +729,21 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p) {
 }
 
 template <typename F, int NM>
-static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p) {
+static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg) {
     using C = TmaCfg<F, NM>;
     using CV = TmaCfgVel<F>;
     if (!h->tma_ready) tma_prepare<F, NM>(h);
-    const Box3 t = tma_box<F, NM>(h);
-    const Box3 all{1, h->g.nz, 0, h->nxp - 1, 0, h->nyp - 1, 0};
-    if (h->use_ring && h->g.iend_k >= h->g.ibeg_k && h->g.jend_k >= h->g.jbeg_k && h->tk * h->ti <= 256) {
+    const Box3 t = tma_box<F, NM>(h, rg);
+    const Box3 all{1, h->g.nz, rg.li0, rg.li1, rg.lj0, rg.lj1, 0};
+    const int ki0 = std::max(h->g.ibeg_k - h->g.ibeg, rg.li0), ki1 = std::min(h->g.iend_k - h->g.ibeg, rg.li1);
+    const int kj0 = std::max(h->g.jbeg_k - h->g.jbeg, rg.lj0), kj1 = std::min(h->g.jend_k - h->g.jbeg, rg.lj1);
+    if (h->use_ring && ki1 >= ki0 && kj1 >= kj0 && h->tk * h->ti <= 256) {
         // interior kernel box with the register-ring kernel; the absorber shell (all PML cells: two j slabs, two i slabs,
         // the bottom k slab) with the direct kernel on side streams.  Every launch writes disjoint cells and only reads S.
         const swpc3d_grid &gg = h->g;
-        const Box3 in{1, gg.kend_k, gg.ibeg_k - gg.ibeg, gg.iend_k - gg.ibeg, gg.jbeg_k - gg.jbeg, gg.jend_k - gg.jbeg, 0};
-        const Box3 sh[5] = {Box3{1, gg.nz, 0, h->nxp - 1, 0, in.lj0 - 1, 0}, Box3{1, gg.nz, 0, h->nxp - 1, in.lj1 + 1, h->nyp - 1, 0},
-                            Box3{1, gg.nz, 0, in.li0 - 1, in.lj0, in.lj1, 0}, Box3{1, gg.nz, in.li1 + 1, h->nxp - 1, in.lj0, in.lj1, 0},
+        const Box3 in{1, gg.kend_k, ki0, ki1, kj0, kj1, 0};
+        const Box3 sh[5] = {Box3{1, gg.nz, rg.li0, rg.li1, rg.lj0, in.lj0 - 1, 0}, Box3{1, gg.nz, rg.li0, rg.li1, in.lj1 + 1, rg.lj1, 0},
+                            Box3{1, gg.nz, rg.li0, in.li0 - 1, in.lj0, in.lj1, 0}, Box3{1, gg.nz, in.li1 + 1, rg.li1, in.lj0, in.lj1, 0},
                             Box3{gg.kend_k + 1, gg.nz, in.li0, in.li1, in.lj0, in.lj1, 0}};
         const int jlen = std::max(1, h->ring_jlen);
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
@@ -720,8 +769,8 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p) {
     g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl);
     dim3 grd((unsigned)((t.k1 - t.k0 + 1) / CV::TK), (unsigned)((t.li1 - t.li0 + 1) / CV::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
     const int kE = (h->g.kend_k / C::TK) * C::TK + 1;
-    const Box3 boxes[5] = {Box3{1, h->g.nz, 0, h->nxp - 1, 0, t.lj0 - 1, 0}, Box3{1, h->g.nz, 0, h->nxp - 1, t.lj1 + 1, h->nyp - 1, 0},
-                           Box3{1, h->g.nz, 0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, h->nxp - 1, t.lj0, t.lj1, 0},
+    const Box3 boxes[5] = {Box3{1, h->g.nz, rg.li0, rg.li1, rg.lj0, t.lj0 - 1, 0}, Box3{1, h->g.nz, rg.li0, rg.li1, t.lj1 + 1, rg.lj1, 0},
+                           Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0},
                            Box3{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1}};
     if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
     vel_tma<F><<<grd, CV::THREADS, CV::SMEM, h->st>>>(p, h->vmaps, g);
@@ -740,13 +789,27 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p) {
     return 0;
 }
 
+// part 0: the whole subdomain; boundary-first overlap: 3 = prologue on the launch stream (opens the timing bracket,
+// plane-wave edges), 1 = the boundary slabs on the exchange stream, 2 = the core on the launch stream (closes the bracket)
 template <typename F, bool STRESS>
-static int launch_sweep(swpc3d_handle *h) {
+static int launch_sweep(swpc3d_handle *h, int part = 0) {
     const KParams<F> p = make_params<F>(h);
     if (h->tk * h->ti > 256) return fail("tk*ti must be <= 256 (launch bounds)");
     const int w = STRESS ? 0 : 1;
     const bool timed = h->ktiming && h->kev_used[w] < 4096;
-    if (timed) {
+    if (part == 1) {   // x slabs are 2 columns wide: a (128 k) x (2 i) block keeps every lane busy
+        Box3 bb[4];
+        const int nb = boundary_boxes(h, bb);
+        const int tk0 = h->tk, ti0 = h->ti;
+        int rc = 0;
+        for (int q = 0; q < nb && !rc; q++) {
+            if (bb[q].li1 - bb[q].li0 + 1 <= 2) { h->tk = 128; h->ti = 2; }
+            rc = launch_direct_box<F, STRESS>(h, p, bb[q], h->cs);
+            h->tk = tk0; h->ti = ti0;
+        }
+        return rc;
+    }
+    if (timed && part != 2) {
         if (h->kev_used[w] == h->kev[w][0].size()) {
             cudaEvent_t a, b;
             CK(cudaEventCreate(&a));
@@ -756,7 +819,7 @@ static int launch_sweep(swpc3d_handle *h) {
         }
         CK(cudaEventRecord(h->kev[w][0][h->kev_used[w]], h->st));
     }
-    if (h->pw_mode && h->g.abc_type == SWPC3D_ABC_PML) {   // absorb_p__update_stress extrapolates V, absorb_p__update_vel the stresses
+    if (h->pw_mode && h->g.abc_type == SWPC3D_ABC_PML && part != 2) {   // absorb_p__update_stress extrapolates V, absorb_p__update_vel the stresses
         const swpc3d_grid &g = h->g;
         const int idx = g.myid % g.nproc_x, idy = g.myid / g.nproc_x;
         PwEdges e{};
@@ -773,19 +836,22 @@ static int launch_sweep(swpc3d_handle *h) {
         CK(cudaGetLastError());
     }
     int rc = 0;
-    if (STRESS) {
+    if (part == 3) return 0;
+    const Region rg = part == 2 ? core_region(h) : whole_region(h);
+    if (rg.li1 < rg.li0 || rg.lj1 < rg.lj0) rc = 0;
+    else if (STRESS) {
         switch (h->nm) {
-        case 0: rc = launch_stress_nm<F, 0>(h, p); break;
-        case 1: rc = launch_stress_nm<F, 1>(h, p); break;
-        case 2: rc = launch_stress_nm<F, 2>(h, p); break;
-        default: rc = launch_stress_nm<F, 3>(h, p); break;
+        case 0: rc = launch_stress_nm<F, 0>(h, p, rg); break;
+        case 1: rc = launch_stress_nm<F, 1>(h, p, rg); break;
+        case 2: rc = launch_stress_nm<F, 2>(h, p, rg); break;
+        default: rc = launch_stress_nm<F, 3>(h, p, rg); break;
         }
     } else {
         switch (h->nm) {
-        case 0: rc = launch_vel_nm<F, 0>(h, p); break;
-        case 1: rc = launch_vel_nm<F, 1>(h, p); break;
-        case 2: rc = launch_vel_nm<F, 2>(h, p); break;
-        default: rc = launch_vel_nm<F, 3>(h, p); break;
+        case 0: rc = launch_vel_nm<F, 0>(h, p, rg); break;
+        case 1: rc = launch_vel_nm<F, 1>(h, p, rg); break;
+        case 2: rc = launch_vel_nm<F, 2>(h, p, rg); break;
+        default: rc = launch_vel_nm<F, 3>(h, p, rg); break;
         }
     }
     if (rc) return rc;
@@ -846,9 +912,15 @@ static float momentrate_host(float t, int stf, float ts, float tr) {
     }
 }
 
+// phase 0: upload of the host-evaluated moment rates + every target cell, on the launch stream; 3: that upload only;
+// 1: targets outside the core box, on `stream`; 2: targets inside it (1 and 2 rely on an earlier phase-3 call)
 template <typename F>
-static int launch_source(swpc3d_handle *h, int it, bool body) {
+static int launch_source(swpc3d_handle *h, int it, bool body, int phase = 0, cudaStream_t stream = nullptr) {
+    if (!stream) stream = h->st;
     SrcParams s{};
+    s.phase = phase;
+    const Region cr = core_region(h);
+    s.c_li0 = cr.li0; s.c_li1 = cr.li1; s.c_lj0 = cr.lj0; s.c_lj1 = cr.lj1;
     s.nsrc = h->nsrc; s.ijk = h->src_ijk; s.mo = h->src_mo; s.mij = h->src_mij; s.prm = h->src_prm;
     s.stf = h->stf; s.dt_dxyz = h->dt_dxyz;
     const float dt = h->g.dt;
@@ -857,13 +929,14 @@ static int launch_source(swpc3d_handle *h, int it, bool body) {
     if (h->nsrc <= 256) {
         float st[256];
         for (int i = 0; i < h->nsrc; i++) st[i] = momentrate_host(s.t, h->stf, h->h_prm[2 * i], h->h_prm[2 * i + 1]);
-        CK(cudaMemcpyAsync(h->src_stime, st, (size_t)h->nsrc * sizeof(float), cudaMemcpyHostToDevice, h->st));
+        if (phase == 0 || phase == 3) CK(cudaMemcpyAsync(h->src_stime, st, (size_t)h->nsrc * sizeof(float), cudaMemcpyHostToDevice, h->st));
         s.stime = h->src_stime;
     }
+    if (phase == 3) return 0;
     const KParams<F> p = make_params<F>(h);
     const int nb = (h->nsrc + 127) / 128;
-    if (body) bodyforce_kernel<F><<<nb, 128, 0, h->st>>>(p, s);
-    else stressglut_kernel<F><<<nb, 128, 0, h->st>>>(p, s);
+    if (body) bodyforce_kernel<F><<<nb, 128, 0, stream>>>(p, s);
+    else stressglut_kernel<F><<<nb, 128, 0, stream>>>(p, s);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -917,6 +990,86 @@ extern "C" int swpc3d_wav_store(swpc3d_handle *h, int32_t it) {
     else wav_store_kernel<float><<<nb, 128, 0, h->st>>>(make_params<float>(h), w);
     h->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Green's-function mode (m_green.f90)
+extern "C" int swpc3d_set_green(swpc3d_handle *h, int32_t ng, const int32_t *ig, const int32_t *jg, const int32_t *kg, int32_t bforce,
+                                int32_t is_src, int32_t isrc, int32_t jsrc, int32_t ksrc, float fx1, float fy1, float fz1, float trise,
+                                const char *stftype, int32_t ntdec_w, int32_t ntw, float tbeg) {
+    if (!h) return fail("null handle");
+    if (ntdec_w < 1 || ntw < 0 || ng < 0) return fail("swpc3d_set_green: bad ntdec_w / ntw / ng");
+    CK(cudaSetDevice(h->dev));
+    cudaFree(h->g_ijk); cudaFree(h->g_acc); cudaFree(h->g_gf);
+    h->g_ijk = nullptr; h->g_acc = h->g_gf = nullptr;
+    h->ng = ng; h->g_bforce = bforce != 0; h->g_ncmp = bforce ? 9 : 6; h->g_ntdec_w = ntdec_w; h->g_ntw = ntw;
+    h->g_stf = stf_code(stftype); h->g_trise = trise; h->tbeg = tbeg;
+    h->g_f[0] = fx1; h->g_f[1] = fy1; h->g_f[2] = fz1;
+    h->g_dt_dxyz = (float)((double)h->g.dt / (h->g.dx * h->g.dy * h->g.dz));   // real(dt / (dx*dy*dz)), m_green.f90:156
+    h->g_is_src = 0;
+    if (is_src) {   // redefined is_src (:185-186): the pseudo source may sit one cell into the +x / +y halo
+        const int mi = isrc - h->g.ibeg + HALO, mj = jsrc - h->g.jbeg + HALO;
+        if (mi < HALO || mi > HALO + h->nxp || mj < HALO || mj > HALO + h->nyp || ksrc < 1 || ksrc > h->g.nz)
+            return fail("swpc3d_set_green: pseudo source outside ibeg..iend+1 x jbeg..jend+1 x kbeg..kend (m_green.f90:185-186)");
+        h->g_is_src = 1; h->g_src[0] = mi; h->g_src[1] = mj; h->g_src[2] = ksrc;
+    }
+    if (ng == 0 || ntw == 0) return 0;
+    std::vector<int> ijk(3 * (size_t)ng);
+    for (int i = 0; i < ng; i++) {
+        const int mi = ig[i] - h->g.ibeg + HALO, mj = jg[i] - h->g.jbeg + HALO;
+        if (mi < HALO || mi >= HALO + h->nxp || mj < HALO || mj >= HALO + h->nyp || kg[i] < 1 || kg[i] > h->g.nz)
+            return fail("swpc3d_set_green: grid point outside of the owned box (m_green.f90:227-228)");
+        ijk[3 * i] = mi; ijk[3 * i + 1] = mj; ijk[3 * i + 2] = kg[i];
+    }
+    CK(cudaMalloc(&h->g_ijk, ijk.size() * sizeof(int)));
+    CK(cudaMemcpy(h->g_ijk, ijk.data(), ijk.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->g_acc, (size_t)12 * ng * sizeof(float)));
+    CK(cudaMemset(h->g_acc, 0, (size_t)12 * ng * sizeof(float)));
+    CK(cudaMalloc(&h->g_gf, (size_t)ntw * h->g_ncmp * ng * sizeof(float)));
+    CK(cudaMemset(h->g_gf, 0, (size_t)ntw * h->g_ncmp * ng * sizeof(float)));
+    return 0;
+}
+
+extern "C" int swpc3d_green_store(swpc3d_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (h->ng <= 0 || !h->g_gf) return 0;
+    GreenParams g{};
+    g.ng = h->ng; g.ncmp = h->g_ncmp; g.ntw = h->g_ntw; g.bforce = h->g_bforce;
+    g.itw = (it - 1) / h->g_ntdec_w + 1;
+    g.sample = ((it - 1) % h->g_ntdec_w == 0 && g.itw <= h->g_ntw) ? 1 : 0;
+    g.ijk = h->g_ijk; g.acc = h->g_acc; g.gf = h->g_gf;
+    const double d[3] = {h->g.dx, h->g.dy, h->g.dz};
+    for (int a = 0; a < 3; a++) {
+        if (h->fb == 8) { g.r40[a] = 9.0 / 8.0 / d[a]; g.r41[a] = 1.0 / 24.0 / d[a]; }
+        else { g.r40[a] = (double)(9.0f / 8.0f / (float)d[a]); g.r41[a] = (double)(1.0f / 24.0f / (float)d[a]); }
+    }
+    const int nb = (h->ng + 127) / 128;
+    if (h->fb == 8) green_store_kernel<double><<<nb, 128, 0, h->st>>>(make_params<double>(h), g);
+    else green_store_kernel<float><<<nb, 128, 0, h->st>>>(make_params<float>(h), g);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swpc3d_green_source(swpc3d_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (!h->g_is_src) return 0;
+    const float stf = momentrate_host(h->tbeg + it * h->g.dt, h->g_stf, 0.0f, h->g_trise);   // green_tbeg = 0 (:62)
+    const float fx = h->g_f[0] * h->g_dt_dxyz * stf, fy = h->g_f[1] * h->g_dt_dxyz * stf, fz = h->g_f[2] * h->g_dt_dxyz * stf;
+    if (h->fb == 8) green_source_kernel<double><<<1, 32, 0, h->st>>>(make_params<double>(h), h->g_src[0], h->g_src[1], h->g_src[2], fx, fy, fz);
+    else green_source_kernel<float><<<1, 32, 0, h->st>>>(make_params<float>(h), h->g_src[0], h->g_src[1], h->g_src[2], fx, fy, fz);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int swpc3d_get_green(swpc3d_handle *h, float *gf) {
+    if (!h || !gf) return fail("null argument");
+    if (h->ng <= 0 || !h->g_gf) return 0;
+    CK(cudaSetDevice(h->dev));
+    CK(cudaMemcpyAsync(gf, h->g_gf, (size_t)h->g_ntw * h->g_ncmp * h->ng * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
     return 0;
 }
 
@@ -1129,7 +1282,7 @@ static FaceLists face_lists(const swpc3d_handle *h, int which) {
 }
 
 template <typename F>
-static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack) {
+static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack, cudaStream_t st_) {
     const int nz = h->g.nz;
     for (int f = 0; f < 4; f++) {
         // A face without a neighbour: the reference still unpacks its (all-zero) receive buffer into the outer halo
@@ -1143,11 +1296,11 @@ static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack) {
         dim3 blk(128, 1, 1), grd((unsigned)((nz + 127) / 128), (unsigned)nline, (unsigned)pl.n);
         F *buf = outer ? nullptr : (F *)(pack ? h->sbuf[f] : h->rbuf[f]);
         if (xface) {
-            if (pack) halo_kernel<F, true, true><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
-            else halo_kernel<F, true, false><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+            if (pack) halo_kernel<F, true, true><<<grd, blk, 0, st_>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+            else halo_kernel<F, true, false><<<grd, blk, 0, st_>>>(nz, nline, h->NZP, h->NXM, pl, buf);
         } else {
-            if (pack) halo_kernel<F, false, true><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
-            else halo_kernel<F, false, false><<<grd, blk, 0, h->st>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+            if (pack) halo_kernel<F, false, true><<<grd, blk, 0, st_>>>(nz, nline, h->NZP, h->NXM, pl, buf);
+            else halo_kernel<F, false, false><<<grd, blk, 0, st_>>>(nz, nline, h->NZP, h->NXM, pl, buf);
         }
         h->launches++;
         CK(cudaGetLastError());
@@ -1159,24 +1312,49 @@ static size_t face_count(const swpc3d_handle *h, const PlaneList &pl, int f) {
     return (size_t)pl.n * (size_t)(f < 2 ? h->nyp : h->nxp) * (size_t)h->g.nz;
 }
 
-static int comm_exchange(swpc3d_handle *h, int which) {
+static bool has_neighbour(const swpc3d_handle *h) {
+    for (int f = 0; f < 4; f++)
+        if (h->nbr[f] >= 0) return true;
+    return false;
+}
+
+// pack -> ncclSend/ncclRecv with up to four neighbours -> unpack, all on `st_` (the launch stream, or the exchange
+// stream of the boundary-first overlap); with kernel_timing the exchange is bracketed by an event pair (halo phase)
+static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr) {
     if (ready(h)) return 1;
-    bool any = false;
-    for (int f = 0; f < 4; f++) any |= (h->nbr[f] >= 0);
+    if (!st_) st_ = h->st;
+    const bool any = has_neighbour(h);
     if (!any && !h->zero_outer) return 0;   // all neighbours MPI_PROC_NULL: outer halos keep their zeros
     const FaceLists L = face_lists(h, which);
-    if (!any) return h->fb == 8 ? launch_halo<double>(h, L, false) : launch_halo<float>(h, L, false);
+    if (!any) return h->fb == 8 ? launch_halo<double>(h, L, false, st_) : launch_halo<float>(h, L, false, st_);
     if (!h->comm) return fail("swpc3d_comm_*: this rank has neighbours but swpc3d_comm_init was not called");
-    if (h->fb == 8 ? launch_halo<double>(h, L, true) : launch_halo<float>(h, L, true)) return 1;
+    const bool timed = h->ktiming && h->cev_used < 4096;
+    if (timed) {
+        if (h->cev_used == h->cev[0].size()) {
+            cudaEvent_t a, b;
+            CK(cudaEventCreate(&a));
+            CK(cudaEventCreate(&b));
+            h->cev[0].push_back(a);
+            h->cev[1].push_back(b);
+        }
+        CK(cudaEventRecord(h->cev[0][h->cev_used], st_));
+    }
+    if (h->fb == 8 ? launch_halo<double>(h, L, true, st_) : launch_halo<float>(h, L, true, st_)) return 1;
     const ncclDataType_t ty = h->fb == 8 ? ncclDouble : ncclFloat;
     NK(g_nccl.GroupStart());
     for (int f = 0; f < 4; f++) {
         if (h->nbr[f] < 0) continue;
-        NK(g_nccl.Send(h->sbuf[f], face_count(h, L.send[f], f), ty, h->nbr[f], h->comm, h->st));
-        NK(g_nccl.Recv(h->rbuf[f], face_count(h, L.recv[f], f), ty, h->nbr[f], h->comm, h->st));
+        NK(g_nccl.Send(h->sbuf[f], face_count(h, L.send[f], f), ty, h->nbr[f], h->comm, st_));
+        NK(g_nccl.Recv(h->rbuf[f], face_count(h, L.recv[f], f), ty, h->nbr[f], h->comm, st_));
+        h->halo_bytes += (double)(face_count(h, L.send[f], f) * (size_t)h->fb);
     }
     NK(g_nccl.GroupEnd());
-    return h->fb == 8 ? launch_halo<double>(h, L, false) : launch_halo<float>(h, L, false);
+    if (h->fb == 8 ? launch_halo<double>(h, L, false, st_) : launch_halo<float>(h, L, false, st_)) return 1;
+    if (timed) {
+        CK(cudaEventRecord(h->cev[1][h->cev_used], st_));
+        h->cev_used++;
+    }
+    return 0;
 }
 
 extern "C" int swpc3d_comm_stress(swpc3d_handle *h) { return comm_exchange(h, 0); }
@@ -1212,7 +1390,7 @@ extern "C" int swpc3d_comm_local(swpc3d_handle **hs, int32_t n, int32_t which) {
         if (ready(hs[q])) return 1;
         if (hs[q]->g.myid != q) return fail("swpc3d_comm_local: handles must be ordered by myid");
         const FaceLists L = face_lists(hs[q], which);
-        if (hs[q]->fb == 8 ? launch_halo<double>(hs[q], L, true) : launch_halo<float>(hs[q], L, true)) return 1;
+        if (hs[q]->fb == 8 ? launch_halo<double>(hs[q], L, true, hs[q]->st) : launch_halo<float>(hs[q], L, true, hs[q]->st)) return 1;
     }
     for (int q = 0; q < n; q++) { CK(cudaSetDevice(hs[q]->dev)); CK(cudaStreamSynchronize(hs[q]->st)); }
     const int opp[4] = {1, 0, 3, 2};
@@ -1223,27 +1401,59 @@ extern "C" int swpc3d_comm_local(swpc3d_handle **hs, int32_t n, int32_t which) {
             if (h->nbr[f] < 0) continue;
             if (h->nbr[f] >= n) return fail("swpc3d_comm_local: neighbour not in the handle list");
             swpc3d_handle *o = hs[h->nbr[f]];
-            CK(cudaMemcpy(o->rbuf[opp[f]], h->sbuf[f], face_count(h, L.send[f], f) * (size_t)h->fb, cudaMemcpyDefault));
+            // on the receiver's own (non-blocking) stream, ahead of its unpack kernels: a device-to-device cudaMemcpy on the
+            // legacy default stream neither blocks the host nor orders against non-blocking streams
+            CK(cudaMemcpyAsync(o->rbuf[opp[f]], h->sbuf[f], face_count(h, L.send[f], f) * (size_t)h->fb, cudaMemcpyDefault, o->st));
         }
     }
     for (int q = 0; q < n; q++) {
         const FaceLists L = face_lists(hs[q], which);
         CK(cudaSetDevice(hs[q]->dev));
-        if (hs[q]->fb == 8 ? launch_halo<double>(hs[q], L, false) : launch_halo<float>(hs[q], L, false)) return 1;
+        if (hs[q]->fb == 8 ? launch_halo<double>(hs[q], L, false, hs[q]->st) : launch_halo<float>(hs[q], L, false, hs[q]->st)) return 1;
     }
     for (int q = 0; q < n; q++) { CK(cudaSetDevice(hs[q]->dev)); CK(cudaStreamSynchronize(hs[q]->st)); }
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
+// One field family of the boundary-first schedule: [exchange stream: boundary slabs, source terms that land outside the
+// core, pack, NCCL, unpack] beside [launch stream: core sweep, source terms inside the core] -> join.
+// The arithmetic per cell and the order sweep -> source -> exchange per cell are the reference's, so the results are
+// bit-identical to the exposed order.
+template <typename F, bool STRESS>
+static int family_overlapped(swpc3d_handle *h, int it) {
+    const bool src = h->nsrc > 0 && (STRESS ? !h->bf_mode : h->bf_mode);
+    if (launch_sweep<F, STRESS>(h, 3)) return 1;
+    if (src && launch_source<F>(h, it, !STRESS, 3)) return 1;
+    CK(cudaEventRecord(h->ev_b, h->st));
+    CK(cudaStreamWaitEvent(h->cs, h->ev_b, 0));
+    if (launch_sweep<F, STRESS>(h, 1)) return 1;
+    if (src && launch_source<F>(h, it, !STRESS, 1, h->cs)) return 1;
+    if (!h->split_test && comm_exchange(h, STRESS ? 0 : 1, h->cs)) return 1;
+    CK(cudaEventRecord(h->ev_c, h->cs));
+    if (launch_sweep<F, STRESS>(h, 2)) return 1;
+    if (src && launch_source<F>(h, it, !STRESS, 2)) return 1;
+    CK(cudaStreamWaitEvent(h->st, h->ev_c, 0));
+    return 0;
+}
+
 extern "C" int swpc3d_step(swpc3d_handle *h, int32_t it) {
     // main.f90:119-139
+    if (swpc3d_green_store(h, it)) return 1;
     if (swpc3d_wav_store(h, it)) return 1;
+    // (green__source writes V cells next to the subdomain edge between the sweep and the exchange: exposed order then)
+    if (((h->overlap && has_neighbour(h) && h->comm) || h->split_test) && !h->g_is_src) {
+        if (ready(h)) return 1;
+        if (h->fb == 8 ? family_overlapped<double, true>(h, it) : family_overlapped<float, true>(h, it)) return 1;
+        if (h->fb == 8 ? family_overlapped<double, false>(h, it) : family_overlapped<float, false>(h, it)) return 1;
+        return 0;
+    }
     if (swpc3d_update_stress(h)) return 1;
     if (swpc3d_stressglut(h, it)) return 1;
     if (swpc3d_comm_stress(h)) return 1;
     if (swpc3d_update_vel(h)) return 1;
     if (swpc3d_bodyforce(h, it)) return 1;
+    if (swpc3d_green_source(h, it)) return 1;
     if (swpc3d_comm_vel(h)) return 1;
     return 0;
 }
@@ -1280,11 +1490,13 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "zero_outer_halo")) h->zero_outer = value != 0;
     else if (!strcmp(key, "tma")) h->use_tma = value;
     else if (!strcmp(key, "vel_ring")) h->use_ring = value;
+    else if (!strcmp(key, "overlap")) h->overlap = value != 0;
+    else if (!strcmp(key, "split_test")) h->split_test = value != 0;
     else if (!strcmp(key, "ring_jlen")) { if (value < 1) return fail("ring_jlen must be >= 1"); h->ring_jlen = value; }
     else if (!strcmp(key, "ring_pf")) { if (value < 0 || value > 8) return fail("ring_pf must be 0..8"); h->ring_pf = value; }
     else if (!strcmp(key, "side_streams")) h->use_side = value;
     else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }
-    else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; }
+    else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; h->cev_used = 0; h->halo_bytes = 0.0; }
     else return fail(std::string("unknown option ") + key);
     return 0;
 }
@@ -1310,6 +1522,21 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
             sum += ms;
         }
         *value = h->kev_used[w] ? sum / (double)h->kev_used[w] : 0.0;   // average launch duration [ms]
+    }
+    else if (!strcmp(key, "ms_halo") || !strcmp(key, "n_halo") || !strcmp(key, "halo_bytes")) {
+        // the halo phase: pack + ncclSend/Recv + unpack of one field family, CUDA events on the stream it ran on
+        if (key[0] == 'n') { *value = (double)h->cev_used; return 0; }
+        if (key[0] == 'h') { *value = h->halo_bytes; return 0; }
+        CK(cudaSetDevice(h->dev));
+        CK(cudaStreamSynchronize(h->st));
+        CK(cudaStreamSynchronize(h->cs));
+        double sum = 0;
+        for (size_t q = 0; q < h->cev_used; q++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h->cev[0][q], h->cev[1][q]));
+            sum += ms;
+        }
+        *value = h->cev_used ? sum / (double)h->cev_used : 0.0;
     }
     else if (!strcmp(key, "device_bytes")) {
         double b = (double)h->ncell * (9.0 * h->fb + 5 * 4 + 6.0 * h->nm * 4) + (double)h->naux * 18 * 4;

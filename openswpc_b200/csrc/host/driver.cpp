@@ -68,6 +68,20 @@ struct swpc3d_host {
     int setup_source(const IniFile &ini);
     int setup_absorb();
     int setup_wav(const IniFile &ini);
+    // Green's-function mode (m_green.f90)
+    struct Green {
+        std::string stnm, fn_glst, fmt, stftype, wav_format;
+        char cmp = ' ';
+        float trise = 1.0f, maxdist = 1e30f, f1[3] = {0, 0, 0};
+        bool bforce = false, have_src = false, finalized = false;
+        int src_ijk[3] = {0, 0, 0}, ntdec_w = 10, ntw = 0, ncmp = 6;
+        float src_xyz[3] = {0, 0, 0}, evlo0 = 0, evla0 = 0;
+        std::vector<int> ijk, gid;                       // owned grid points (3 per point) and their ids
+        std::vector<float> xg, yg, zg, lon, lat;
+        std::vector<float> gf;                           // (ntw, ncmp*ng) after swpc3d_host_write_green
+    } green;
+    int setup_green(const IniFile &ini);
+    int green_finalize();
 };
 
 int swpc3d_host::setup_global(const IniFile &ini, int npx, int npy, int nt_o) {
@@ -227,6 +241,7 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
         }
     }
     for (size_t n = 0; n < n2; n++) bddep[n] = bd0;
+    if (std::getenv("SWPC3D_HOST_TIMING")) std::fprintf(stderr, "[swpc3d_host] vmodel done\n");
     if (lateral) return finish_medium_3d(ini);
 
     // absorber homogenisation (m_medium.f90:124-190) copies columns outward; with laterally uniform input it is the
@@ -294,6 +309,7 @@ int swpc3d_host::finish_medium_3d(const IniFile &ini) {
     relax_times(nm, ts, fq_min, fq_max);
     zeta = constq_zeta(nm, fq_min, fq_max, ts);
     const size_t nc = rho.size();
+#pragma omp parallel for schedule(static)
     for (size_t n = 0; n < nc; n++) { taup[n] = nm * zeta / taup[n]; taus[n] = nm * zeta / taus[n]; }
     if (nm > 0) {
         const float omega = (float)(2 * PI_D * (double)fq_ref);
@@ -304,13 +320,19 @@ int swpc3d_host::finish_medium_3d(const IniFile &ini) {
             cc = cc + std::complex<float>((float)qd.real(), (float)qd.imag());
         }
         cc = std::complex<float>(cc.real() / (float)nm, cc.imag() / (float)nm);
-        for (size_t n = 0; n < nc; n++) {
-            const float rb2 = mu[n], ra2 = lam[n] + 2 * mu[n];
-            const std::complex<float> zs_ = 1.0f - cc * taus[n], zp_ = 1.0f - cc * taup[n];
-            const float chi_mu = 1.0f / (1.0f / std::sqrt(zs_)).real();
-            const float chi_lam = 1.0f / (1.0f / std::sqrt(zp_)).real();
-            mu[n] = rb2 / (chi_mu * chi_mu);
-            lam[n] = ra2 / (chi_lam * chi_lam) - 2 * mu[n];
+        // chi depends on the cell only through taus / taup, which take a handful of values (one per layer): remember the
+        // last evaluation per column instead of two complex square roots per cell
+        const long long ncol = (long long)nxm * nym;
+#pragma omp parallel for schedule(static)
+        for (long long col = 0; col < ncol; col++) {
+            float last_ts = -1.0f, last_tp = -1.0f, chi_mu = 1.0f, chi_lam = 1.0f;
+            for (size_t n = (size_t)col * nzm; n < (size_t)(col + 1) * nzm; n++) {
+                const float rb2 = mu[n], ra2 = lam[n] + 2 * mu[n];
+                if (taus[n] != last_ts) { last_ts = taus[n]; chi_mu = 1.0f / (1.0f / std::sqrt(1.0f - cc * taus[n])).real(); }
+                if (taup[n] != last_tp) { last_tp = taup[n]; chi_lam = 1.0f / (1.0f / std::sqrt(1.0f - cc * taup[n])).real(); }
+                mu[n] = rb2 / (chi_mu * chi_mu);
+                lam[n] = ra2 / (chi_lam * chi_lam) - 2 * mu[n];
+            }
         }
     }
     return finish_surface(ini);
@@ -321,6 +343,7 @@ int swpc3d_host::finish_surface(const IniFile &ini) {
     // surface_detection m_medium.f90:339-394 -- evaluated per column exactly as the reference does (Q1: only
     // i in [ibeg-1, iend+2], j likewise are scanned; the outermost margin keeps kbeg-1 = 0)
     kfs.assign(n2, 0); kob.assign(n2, 0); kfs_top.assign(n2, 0); kfs_bot.assign(n2, 0); kob_top.assign(n2, 0); kob_bot.assign(n2, 0);
+#pragma omp parallel for schedule(static)
     for (int j = jbeg - 1; j <= jend + 2; j++)
         for (int i = ibeg - 1; i <= iend + 2; i++)
             for (int k = 1; k <= nz - 1; k++) {
@@ -341,6 +364,7 @@ int swpc3d_host::finish_surface(const IniFile &ini) {
         }
     // velocity_minmax :396-427 (local part)
     float vmx = -1.0f, vmn = 1e30f;
+#pragma omp parallel for schedule(static) reduction(max : vmx) reduction(min : vmn)
     for (int j = jbeg; j <= jend; j++)
         for (int i = ibeg; i <= iend; i++)
             for (int k = kfs[i2(i, j)] + 1; k <= nz; k++) {
@@ -454,7 +478,7 @@ int swpc3d_host::setup_source(const IniFile &ini) {   // m_source.f90:41-314
     bf_mode = ini.get_l("bf_mode", false);
     if (pw_mode && green_mode) return hfail("assert: pw_mode and green_mode are exclusive (m_source.f90:70)");
     if (pw_mode && !benchmark_mode) return setup_planewave(ini);   // :73-82
-    if (green_mode && !benchmark_mode) return hfail("green_mode is outside the hot-path scope of this build");
+    if (green_mode && !benchmark_mode) { pw_mode = false; return 0; }   // :84-91: no source grid; M0 / fmax come from green__setup
     fn_stf = ini.get("fn_stf", "");
     stftype = ini.get("stftype", "kupper");
     if (stftype == "scosine") stftype = "cosine";
@@ -624,7 +648,8 @@ int swpc3d_host::setup_wav(const IniFile &ini) {   // m_wav.f90:54-271
     st_format = ini.get("st_format", "xy");
     fn_stloc = ini.get("fn_stloc", "");
     ntdec_r = ini.get_i("ntdec_r", 10);   // m_report.f90:47
-    if (!(sw_wav_v || other)) return 0;
+    if (ini.get_l("green_mode", false)) sw_wav_v = sw_wav_u = sw_wav_stress = sw_wav_strain = false;   // m_wav.f90:76-81: table only
+    else if (!(sw_wav_v || other)) return 0;
     ntw = (int)std::floor((float)(nt - 1) / (float)ntdec_w + 1.0f);
     std::ifstream is(join_path(base, fn_stloc));
     if (!is) return 0;   // 'no station location file found' :157-161
@@ -662,18 +687,108 @@ int swpc3d_host::setup_wav(const IniFile &ini) {   // m_wav.f90:54-271
     return 0;
 }
 
+// green__setup, m_green.f90:67-355.  The pseudo source is a station: wav__stquery finds it on its owner rank and the
+// reference broadcasts location and indices (:161-183).  A host that runs several ranks does the same with
+// swpc3d_host_green_query / swpc3d_host_green_set_source; a single-rank run resolves it here.  The list of grid points
+// needs the source position (green_maxdist) and is read by green_finalize().
+int swpc3d_host::setup_green(const IniFile &ini) {
+    if (benchmark_mode) { green_mode = false; return 0; }
+    green_mode = ini.get_l("green_mode", false);
+    if (!green_mode) return 0;
+    Green &g = green;
+    g.stnm = ini.get("green_stnm", "").substr(0, 8);
+    const std::string c = ini.get("green_cmp", "");
+    g.cmp = c.empty() ? ' ' : c[0];
+    g.trise = ini.get_s("green_trise", 1.0f);
+    g.bforce = ini.get_l("green_bforce", false);
+    g.maxdist = ini.get_s("green_maxdist", 1e30f);
+    if (!(g.maxdist > 0.0f)) return hfail("assert: green_maxdist > 0 (m_green.f90:124)");
+    M0 = 1;
+    fmax = 2.0f / g.trise;
+    g.fn_glst = ini.get("fn_glst", "");
+    if (!std::ifstream(join_path(base, g.fn_glst)).good()) return hfail("assert: fn_glst '" + g.fn_glst + "' exists (m_green.f90:131-132)");
+    g.fmt = ini.get("green_fmt", "xyz");
+    if (g.fmt != "xyz" && g.fmt != "llz") return hfail("assert: green_fmt is 'xyz' or 'llz' (m_green.f90:135)");
+    g.ntdec_w = ini.get_i("ntdec_w", 10);
+    g.stftype = ini.get("stftype", "kupper");
+    if (g.stftype == "scosine") g.stftype = "cosine";
+    g.wav_format = ini.get("wav_format", "sac");
+    if (g.cmp == 'x') g.f1[0] = 1.0f;
+    else if (g.cmp == 'y') g.f1[1] = 1.0f;
+    else if (g.cmp == 'z') g.f1[2] = 1.0f;
+    else return hfail("no matching green_cmp (m_green.f90:151-153)");
+    g.ntw = (int)std::floor((float)(nt - 1) / (float)g.ntdec_w + 1.0f);
+    g.ncmp = g.bforce ? 9 : 6;
+    for (size_t n = 0; n < stnm.size(); n++)
+        if (stnm[n] == g.stnm) {
+            for (int q = 0; q < 3; q++) g.src_ijk[q] = st_ijk[3 * n + q];
+            g.src_xyz[0] = xst[n]; g.src_xyz[1] = yst[n]; g.src_xyz[2] = zst[n]; g.evlo0 = stlo[n]; g.evla0 = stla[n];
+            g.have_src = true;
+            break;
+        }
+    if (nproc_x * nproc_y == 1) {
+        if (!g.have_src) return hfail("assert: station '" + g.stnm + "' (green_stnm) is inside the model (m_green.f90:165)");
+        return green_finalize();
+    }
+    return 0;
+}
+
+int swpc3d_host::green_finalize() {   // m_green.f90:188-280
+    Green &g = green;
+    if (g.finalized) return 0;
+    if (!g.have_src) return hfail("Green's-function mode: the pseudo source is unknown on this rank -- broadcast it from its owner "
+                                  "(swpc3d_host_green_query / swpc3d_host_green_set_source, mpi_bcast of m_green.f90:176-183)");
+    std::ifstream is(join_path(base, g.fn_glst));
+    const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz;
+    std::string line;
+    while (std::getline(is, line)) {
+        if (blank_or_comment(line)) continue;
+        for (auto &ch : line) if (ch == ',') ch = ' ';
+        std::istringstream ls(line);
+        float a, b, z, x, y, lo, la;
+        int id;
+        if (!(ls >> a >> b >> z >> id)) return hfail("assert: fn_glst line '" + line + "' reads as three reals and an integer (m_green.f90:205-213)");
+        if (g.fmt == "xyz") { x = a; y = b; geomap_c2g(x, y, clon, clat, phi, lo, la); }
+        else { lo = a; la = b; geomap_g2c(lo, la, clon, clat, phi, x, y); }
+        if (!(0 <= id && id <= 99999999)) return hfail("assert: 0 <= gid <= 99999999 (m_green.f90:214)");
+        const float ddx = x - g.src_xyz[0], ddy = y - g.src_xyz[1];
+        if (std::sqrt(ddx * ddx + ddy * ddy) > g.maxdist) continue;
+        const int ii = x2i(x, xbeg, fdx), jj = x2i(y, ybeg, fdy), kk = x2i(z, zbeg, fdz);
+        if (!(ibeg <= ii && ii <= iend && jbeg <= jj && jj <= jend)) continue;
+        if (!(kob[i2(ii, jj)] <= kk && kk <= nz)) continue;   // only the solid part
+        g.ijk.push_back(ii); g.ijk.push_back(jj); g.ijk.push_back(kk); g.gid.push_back(id);
+        g.xg.push_back(x); g.yg.push_back(y); g.zg.push_back(z); g.lon.push_back(lo); g.lat.push_back(la);
+    }
+    g.finalized = true;
+    return 0;
+}
+
 int swpc3d_host::setup(const IniFile &ini, int nm_, int myid_, int npx, int npy, int nt_o) {
     if (nm_ < 0 || nm_ > 3) return hfail("nm must be 0..3");
     nm = nm_;
     myid = myid_;
+    const bool timing = std::getenv("SWPC3D_HOST_TIMING") != nullptr;   // development aid: seconds per setup stage to stderr
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!timing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[swpc3d_host] %-8s %.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     if (setup_global(ini, npx, npy, nt_o)) return 1;   // main.f90:64 order
     if (setup_geometry()) return 1;
+    lap("geometry");
     if (setup_medium(ini)) return 1;
+    lap("medium");
     setup_kernel();
     if (setup_source(ini)) return 1;
+    lap("source");
     if (setup_absorb()) return 1;
+    lap("absorb");
     if (setup_snap(ini)) return 1;   // main.f90:76 snap__setup (files are created when a device is attached)
     if (setup_wav(ini)) return 1;
+    if (setup_green(ini)) return 1;   // main.f90:78
+    lap("snap+wav");
     return 0;
 }
 
@@ -1058,6 +1173,10 @@ int swpc3d_host_get_int(swpc3d_host *h, const char *name, int32_t *v) {
 #undef GI
     if (n == "nsrc") { *v = (int32_t)(h->src_ijk.size() / 3); return 0; }
     if (n == "nst") { *v = (int32_t)(h->st_ijk.size() / 3); return 0; }
+    if (n == "green_mode") { *v = h->green_mode ? 1 : 0; return 0; }
+    if (n == "ng") { *v = (int32_t)h->green.gid.size(); return 0; }
+    if (n == "green_ncmp") { *v = h->green.ncmp; return 0; }
+    if (n == "green_ntw") { *v = h->green.ntw; return 0; }
     return hfail("unknown int " + n);
 }
 int swpc3d_host_get_double(swpc3d_host *h, const char *name, double *v) {
@@ -1113,6 +1232,9 @@ int swpc3d_host_get_array(swpc3d_host *h, const char *name, void *out, int64_t c
     GA(rho) GA(lam) GA(mu) GA(taup) GA(taus) GA(kfs) GA(kob) GA(kfs_top) GA(kfs_bot) GA(kob_top) GA(kob_bot) GA(kbeg_a)
     GA(gxc) GA(gxe) GA(gyc) GA(gye) GA(gzc) GA(gze) GA(src_ijk) GA(st_ijk) GA(mo) GA(mij) GA(srcprm) GA(xc) GA(yc) GA(zc)
     GA(stlo) GA(stla) GA(wav)
+    if (s == "green_ijk") return put(h->green.ijk, out, cap, n);
+    if (s == "green_gid") return put(h->green.gid, out, cap, n);
+    if (s == "green_gf") return put(h->green.gf, out, cap, n);
     if (s == "wav_u") return put(h->wav_all[1], out, cap, n);
     if (s == "wav_stress") return put(h->wav_all[2], out, cap, n);
     if (s == "wav_strain") return put(h->wav_all[3], out, cap, n);
@@ -1177,6 +1299,17 @@ int swpc3d_host_attach_device(swpc3d_host *h, int32_t device) {
         }
         DV(swpc3d_upload_fields(h->dev, f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8]));
         DV(swpc3d_set_option(h->dev, "pw_mode", 1));
+    }
+    if (h->green_mode) {   // `!$acc enter data copyin(ig, jg, kg, gf, stftype)` m_green.f90:351
+        if (h->green_finalize()) return 1;
+        const swpc3d_host::Green &gr = h->green;
+        const int ng = (int)gr.gid.size();
+        std::vector<int> a(ng), b(ng), c(ng);
+        for (int i = 0; i < ng; i++) { a[i] = gr.ijk[3 * i]; b[i] = gr.ijk[3 * i + 1]; c[i] = gr.ijk[3 * i + 2]; }
+        const bool is_src = (h->ibeg <= gr.src_ijk[0] && gr.src_ijk[0] <= h->iend + 1) && (h->jbeg <= gr.src_ijk[1] && gr.src_ijk[1] <= h->jend + 1) &&
+                            (1 <= gr.src_ijk[2] && gr.src_ijk[2] <= h->nz);   // redefined is_src, :185-186
+        DV(swpc3d_set_green(h->dev, ng, a.data(), b.data(), c.data(), gr.bforce ? 1 : 0, is_src ? 1 : 0, gr.src_ijk[0], gr.src_ijk[1], gr.src_ijk[2],
+                            gr.f1[0], gr.f1[1], gr.f1[2], gr.trise, gr.stftype.c_str(), gr.ntdec_w, gr.ntw, h->tbeg));
     }
     const int nst = (int)(h->st_ijk.size() / 3);
     if (nst > 0 && (h->sw_wav_v || h->sw_wav_u || h->sw_wav_stress || h->sw_wav_strain)) {
@@ -1286,6 +1419,115 @@ static void mkdirs(const std::string &p) {
     for (size_t q = 1; q <= p.size(); q++)
         if (q == p.size() || p[q] == '/') mkdir(p.substr(0, q).c_str(), 0777);
 }
+// wav__stquery + the broadcast of m_green.f90:161-183, for hosts that run several ranks
+int swpc3d_host_green_query(swpc3d_host *h, int32_t *found, int32_t ijk[3], float xyz[3], float lonlat[2]) {
+    if (!h || !found) return hfail("null argument");
+    if (!h->green_mode) return hfail("swpc3d_host_green_query: green_mode is off");
+    *found = h->green.have_src ? 1 : 0;
+    if (h->green.have_src) {
+        for (int q = 0; q < 3; q++) { if (ijk) ijk[q] = h->green.src_ijk[q]; if (xyz) xyz[q] = h->green.src_xyz[q]; }
+        if (lonlat) { lonlat[0] = h->green.evlo0; lonlat[1] = h->green.evla0; }
+    }
+    return 0;
+}
+int swpc3d_host_green_set_source(swpc3d_host *h, const int32_t ijk[3], const float xyz[3], const float lonlat[2]) {
+    if (!h || !ijk || !xyz || !lonlat) return hfail("null argument");
+    if (!h->green_mode) return hfail("swpc3d_host_green_set_source: green_mode is off");
+    if (h->green.finalized) return hfail("swpc3d_host_green_set_source: the grid-point list was already read");
+    for (int q = 0; q < 3; q++) { h->green.src_ijk[q] = ijk[q]; h->green.src_xyz[q] = xyz[q]; }
+    h->green.evlo0 = lonlat[0]; h->green.evla0 = lonlat[1];
+    h->green.have_src = true;
+    return h->green_finalize();
+}
+
+// green__export, m_green.f90:553-604 (wav_format sac | csf | wav).  Headers: green__setup :282-349 on sac__init defaults.
+int swpc3d_host_write_green(swpc3d_host *h, const char *odir, int32_t *nfiles) {
+    if (!h) return hfail("null handle");
+    if (nfiles) *nfiles = 0;
+    if (!h->green_mode) return 0;
+    if (!h->dev) return hfail("swpc3d_host_write_green: no device attached");
+    swpc3d_host::Green &g = h->green;
+    const int ng = (int)g.gid.size(), ncmp = g.ncmp, ntw = g.ntw;
+    g.gf.assign((size_t)ntw * ncmp * std::max(ng, 1), 0.0f);
+    if (ng > 0 && swpc3d_get_green(h->dev, g.gf.data())) return hfail(std::string("device: ") + swpc3d_last_error());
+    if (g.cmp == 'z')   // positive upward for the z component (:563-565)
+        for (auto &v : g.gf) v = -v;
+    const std::string dir = std::string(odir ? odir : h->odir.c_str()) + "/green/" + g.stnm;
+    mkdirs(dir);
+    static const char *cmpn[9] = {"mxx", "myy", "mzz", "myz", "mxz", "mxy", "fx_", "fy_", "fz_"};
+    const time_t tt = (time_t)h->exedate + (time_t)h->tz_minutes * 60;
+    struct tm gm;
+    gmtime_r(&tt, &gm);
+    const float fdx = (float)h->dx, fdy = (float)h->dy, fdz = (float)h->dz;
+    auto header = [&](int i, int j, unsigned char *out) {
+        float f[70];
+        int32_t iv[35], lv[5] = {1, 0, 1, 0, 0};
+        char a[192];
+        std::fill(f, f + 70, -12345.0f);
+        std::fill(iv, iv + 35, -12345);
+        for (int q = 0; q < 24; q++) put_chars(a + 8 * q, "-12345", 8);
+        put_chars(a + 8, "-12345", 16);
+        const double delta = (double)(g.ntdec_w * h->dt);
+        f[0] = (float)((int)(delta * 1e7)) / 1e7f;
+        f[5] = h->tbeg;
+        f[31] = g.evla0; f[32] = g.evlo0; f[34] = g.src_xyz[2] * 1000;
+        f[35] = g.lat[i]; f[36] = g.lon[i]; f[38] = g.zg[i];
+        f[40] = g.xg[i]; f[41] = g.yg[i]; f[42] = g.zg[i];
+        f[43] = i2x(g.ijk[3 * i], h->xbeg, fdx); f[44] = i2x(g.ijk[3 * i + 1], h->ybeg, fdy); f[45] = i2x(g.ijk[3 * i + 2], h->zbeg, fdz);
+        f[46] = h->clon; f[47] = h->clat; f[48] = h->phi;
+        f[58] = g.cmp == 'z' ? 0.0f : 90.0f;
+        f[57] = g.cmp == 'x' ? 0.0f + h->phi : (g.cmp == 'y' ? 90.0f + h->phi : 0.0f);
+        iv[0] = gm.tm_year + 1900; iv[1] = gm.tm_yday + 1; iv[2] = gm.tm_hour; iv[3] = gm.tm_min; iv[4] = gm.tm_sec; iv[5] = 0;
+        iv[6] = 6; iv[9] = ntw; iv[15] = 1; iv[16] = j < 6 ? 7 : 6;
+        char cid[16];
+        std::snprintf(cid, sizeof(cid), "%08d", g.gid[i]);
+        put_chars(a, g.stnm, 8);
+        put_chars(a + 8, cid, 16);
+        put_chars(a + 160, std::string("G_V") + g.cmp + "_" + cmpn[j], 8);
+        std::memcpy(out, f, 280); std::memcpy(out + 280, iv, 140); std::memcpy(out + 420, lv, 20); std::memcpy(out + 440, a, 192);
+    };
+    int count = 0;
+    if (g.wav_format == "sac") {
+        std::vector<unsigned char> rec(632 + 4 * (size_t)ntw);
+        for (int i = 0; i < ng; i++)
+            for (int j = 0; j < ncmp; j++) {
+                header(i, j, rec.data());
+                std::memcpy(rec.data() + 632, g.gf.data() + (size_t)ntw * ((size_t)ncmp * i + j), 4 * (size_t)ntw);
+                char cid[16];
+                std::snprintf(cid, sizeof(cid), "%08d", g.gid[i]);
+                const std::string fn = dir + "/" + h->title + "__" + cid + "__" + g.stnm + "__" + g.cmp + "__" + cmpn[j] + "__.sac";
+                std::ofstream os(fn, std::ios::binary);
+                if (!os) return hfail("cannot write " + fn);
+                os.write((const char *)rec.data(), (std::streamsize)rec.size());
+                count++;
+            }
+    } else if ((g.wav_format == "csf" || g.wav_format == "wav") && ng > 0) {
+        char cmyid[16];
+        std::snprintf(cmyid, sizeof(cmyid), "%06d", h->myid);
+        const std::string fn = dir + "/" + h->title + "__" + g.stnm + "__" + g.cmp + "__" + cmyid + "__." + g.wav_format;
+        std::ofstream os(fn, std::ios::binary);
+        if (!os) return hfail("cannot write " + fn);
+        const int32_t ntr = ng * ncmp, npts = ntw;
+        std::vector<unsigned char> hd(632);
+        if (g.wav_format == "csf") {   // csf__write, m_sac.f90:585-648: 'CSFD', ntrace, npts, then header + data per trace
+            os.write("CSFD", 4);
+            os.write((const char *)&ntr, 4);
+            os.write((const char *)&npts, 4);
+            for (int i = 0; i < ng; i++)
+                for (int j = 0; j < ncmp; j++) {
+                    header(i, j, hd.data());
+                    os.write((const char *)hd.data(), 632);
+                    os.write((const char *)(g.gf.data() + (size_t)ntw * ((size_t)ncmp * i + j)), 4 * (std::streamsize)ntw);
+                }
+        } else {
+            return hfail("wav_format = 'wav' of green__export writes the compiler's in-memory sac__hdr records (m_green.f90:594-596): not portable, not supported");
+        }
+        count = 1;
+    }
+    if (nfiles) *nfiles = count;
+    return 0;
+}
+
 int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles) {
     if (!h) return hfail("null handle");
     if (nfiles) *nfiles = 0;

@@ -108,7 +108,9 @@ inline int rdrmed3d(const MediumBox &b, const std::string &fn, float *vol) {
     const long long nxc = nc.dim[0], nyc = nc.dim[1], nzc = nc.dim[2], beg = nc.var[3].begin;
     if (beg + 4 * nxc * nyc * nzc > (long long)nc.bytes.size()) return hfail("rdrmed__3d: " + fn + " is truncated");
     auto wrap = [](long long v, long long n) { long long r = v % n; return r <= 0 ? r + n : r; };
-    for (int k = b.kb; k <= std::min<long long>(b.ke, nzc); k++) {
+    const int ktop = (int)std::min<long long>(b.ke, nzc);
+#pragma omp parallel for schedule(static)
+    for (int k = b.kb; k <= ktop; k++) {
         const long long plane = beg + 4 * nxc * nyc * ((k <= 0 ? k + nzc : k) - 1);
         for (int j = b.jb; j <= b.je; j++) {
             const long long row = plane + 4 * nxc * (wrap(j, nyc) - 1);
@@ -263,6 +265,7 @@ inline int vmodel_uni_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
     const std::string path = join_path(e.base, ini.get("dir_rmed", "") + "/" + ini.get("fn_rmed0", ""));
     if (std::ifstream(path).good() && rdrmed3d(b, path, xi.data())) return 1;
     bd0 = topo0;
+#pragma omp parallel for schedule(dynamic, 4)
     for (int k = b.kb; k <= b.ke; k++) {
         const float zc = b.zc[k - b.kb];
         float zs, cv;
@@ -289,6 +292,7 @@ inline int vmodel_lhm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
     std::vector<std::vector<float>> xi;
     if (read_rmed_set(e, b, t, tbl, xi)) return 1;
     bd0 = t.depth[0];
+#pragma omp parallel for schedule(dynamic, 4)
     for (int k = b.kb; k <= b.ke; k++) {
         const float zc = b.zc[k - b.kb];
         float zs, cv, rho = 0, vp = 0, vs = 0, qp = 0, qs = 0;
@@ -303,17 +307,21 @@ inline int vmodel_lhm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
                     }
             continue;
         }
+        // the reference walks all layers and lets every one with zs >= depth(l) overwrite rho1 .. qs1 (:196-209): only
+        // the LAST such layer survives, and it depends on k alone
+        int lsel = -1;
+        for (int l = 0; l < t.n(); l++)
+            if (zs >= t.depth[l]) lsel = l;
+        if (lsel < 0) { set_plane(b, k, rho, vp, vs, qp, qs); continue; }
+        const bool solid = t.vp[lsel] > 0 && t.vs[lsel] > 0;
+        const float *xl = xi[tbl[lsel]].data();
         for (int j = b.jb; j <= b.je; j++)
             for (int i = b.ib; i <= b.ie; i++) {
                 const size_t n = b.at(k, i, j);
-                for (int l = 0; l < t.n(); l++)
-                    if (zs >= t.depth[l]) {
-                        const float x = xi[tbl[l]][n];
-                        rho = t.rho[l] * (1 + 0.8f * x); vp = cv * t.vp[l] * (1 + x); vs = cv * t.vs[l] * (1 + x);
-                        if (t.vp[l] > 0 && t.vs[l] > 0) vcheck(vp, vs, rho, x, vmin, vmax, rhomin);
-                        qp = t.qp[l]; qs = t.qs[l];
-                    }
-                set_cell(b, n, rho, vp, vs, qp, qs);
+                const float x = xl[n];
+                rho = t.rho[lsel] * (1 + 0.8f * x); vp = cv * t.vp[lsel] * (1 + x); vs = cv * t.vs[lsel] * (1 + x);
+                if (solid) vcheck(vp, vs, rho, x, vmin, vmax, rhomin);
+                set_cell(b, n, rho, vp, vs, t.qp[lsel], t.qs[lsel]);
             }
     }
     return 0;

@@ -642,6 +642,15 @@ struct SrcParams {
     int stf;
     float t;                // evaluation time
     double dt_dxyz;
+    // boundary-first overlap: phase 0 = every target cell; 1 = only targets OUTSIDE the core box (boundary planes and
+    // halo cells); 2 = only targets inside the core box [c_li0,c_li1] x [c_lj0,c_lj1] (local 0-based owned indices)
+    int phase, c_li0, c_li1, c_lj0, c_lj1;
+    __device__ __forceinline__ bool hit(int mi, int mj) const {
+        if (phase == 0) return true;
+        const int li = mi - HALO, lj = mj - HALO;
+        const bool core = li >= c_li0 && li <= c_li1 && lj >= c_lj0 && lj <= c_lj1;
+        return phase == 2 ? core : !core;
+    }
 };
 
 // source__stressglut m_source.f90:798-841: 15 atomic adds per source (sources may share cells)
@@ -655,13 +664,18 @@ __global__ void stressglut_kernel(const __grid_constant__ KParams<F> p, const Sr
     const long long n = (long long)(s.ijk[3 * i + 2] + KOFF - 1) + (long long)p.NZP * ((long long)s.ijk[3 * i] + (long long)p.NXM * s.ijk[3 * i + 1]);
     const F mxx = (F)s.mij[6 * i], myy = (F)s.mij[6 * i + 1], mzz = (F)s.mij[6 * i + 2];
     const F myz = (F)s.mij[6 * i + 3], mxz = (F)s.mij[6 * i + 4], mxy = (F)s.mij[6 * i + 5];
-    atomicAdd(p.Sxx + n, -(mxx * sdrop));
-    atomicAdd(p.Syy + n, -(myy * sdrop));
-    atomicAdd(p.Szz + n, -(mzz * sdrop));
+    const int mi = s.ijk[3 * i], mj = s.ijk[3 * i + 1];
+    const bool h00 = s.hit(mi, mj), h10 = s.hit(mi - 1, mj), h01 = s.hit(mi, mj - 1), h11 = s.hit(mi - 1, mj - 1);
     const F qxy = mxy * sdrop / 4, qxz = mxz * sdrop / 4, qyz = myz * sdrop / 4;
-    atomicAdd(p.Sxy + n, -qxy); atomicAdd(p.Sxy + n - sj, -qxy); atomicAdd(p.Sxy + n - si, -qxy); atomicAdd(p.Sxy + n - si - sj, -qxy);
-    atomicAdd(p.Sxz + n, -qxz); atomicAdd(p.Sxz + n - 1, -qxz); atomicAdd(p.Sxz + n - si, -qxz); atomicAdd(p.Sxz + n - 1 - si, -qxz);
-    atomicAdd(p.Syz + n, -qyz); atomicAdd(p.Syz + n - 1, -qyz); atomicAdd(p.Syz + n - sj, -qyz); atomicAdd(p.Syz + n - 1 - sj, -qyz);
+    if (h00) {
+        atomicAdd(p.Sxx + n, -(mxx * sdrop));
+        atomicAdd(p.Syy + n, -(myy * sdrop));
+        atomicAdd(p.Szz + n, -(mzz * sdrop));
+        atomicAdd(p.Sxy + n, -qxy); atomicAdd(p.Sxz + n, -qxz); atomicAdd(p.Sxz + n - 1, -qxz); atomicAdd(p.Syz + n, -qyz); atomicAdd(p.Syz + n - 1, -qyz);
+    }
+    if (h01) { atomicAdd(p.Sxy + n - sj, -qxy); atomicAdd(p.Syz + n - sj, -qyz); atomicAdd(p.Syz + n - 1 - sj, -qyz); }
+    if (h10) { atomicAdd(p.Sxy + n - si, -qxy); atomicAdd(p.Sxz + n - si, -qxz); atomicAdd(p.Sxz + n - 1 - si, -qxz); }
+    if (h11) atomicAdd(p.Sxy + n - si - sj, -qxy);
 }
 
 // source__bodyforce m_source.f90:870-892
@@ -675,12 +689,15 @@ __global__ void bodyforce_kernel(const __grid_constant__ KParams<F> p, const Src
     const F fx = (F)s.mij[6 * i], fy = (F)s.mij[6 * i + 1], fz = (F)s.mij[6 * i + 2];
     const F dtd = (F)s.dt_dxyz;
     const float *rho = p.rho;
-    atomicAdd(p.Vx + n, (F)((2.0f / (rho[n] + rho[n + si])) * fx * stime * dtd / 2));
-    atomicAdd(p.Vx + n - si, (F)((2.0f / (rho[n] + rho[n - si])) * fx * stime * dtd / 2));
-    atomicAdd(p.Vy + n, (F)((2.0f / (rho[n] + rho[n + sj])) * fy * stime * dtd / 2));
-    atomicAdd(p.Vy + n - sj, (F)((2.0f / (rho[n] + rho[n - sj])) * fy * stime * dtd / 2));
-    atomicAdd(p.Vz + n, (F)((2.0f / (rho[n] + rho[n + 1])) * fz * stime * dtd / 2));
-    atomicAdd(p.Vz + n - 1, (F)((2.0f / (rho[n] + rho[n - 1])) * fz * stime * dtd / 2));
+    const int mi = s.ijk[3 * i], mj = s.ijk[3 * i + 1];
+    if (s.hit(mi, mj)) {
+        atomicAdd(p.Vx + n, (F)((2.0f / (rho[n] + rho[n + si])) * fx * stime * dtd / 2));
+        atomicAdd(p.Vy + n, (F)((2.0f / (rho[n] + rho[n + sj])) * fy * stime * dtd / 2));
+        atomicAdd(p.Vz + n, (F)((2.0f / (rho[n] + rho[n + 1])) * fz * stime * dtd / 2));
+        atomicAdd(p.Vz + n - 1, (F)((2.0f / (rho[n] + rho[n - 1])) * fz * stime * dtd / 2));
+    }
+    if (s.hit(mi - 1, mj)) atomicAdd(p.Vx + n - si, (F)((2.0f / (rho[n] + rho[n - si])) * fx * stime * dtd / 2));
+    if (s.hit(mi, mj - 1)) atomicAdd(p.Vy + n - sj, (F)((2.0f / (rho[n] + rho[n - sj])) * fy * stime * dtd / 2));
 }
 
 // wav__store m_wav.f90:397-625: per station, every step: displacement / strain accumulation (:430-513); when
@@ -774,6 +791,81 @@ __global__ void wav_store_kernel(const __grid_constant__ KParams<F> p, const Wav
 #pragma unroll
         for (int c = 0; c < 6; c++) o[c * ntw] = a[3 + c] * M0 * UC * 1e-3f;
     }
+}
+
+// Green's-function mode, m_green.f90.  green__store (:404-521): nine displacement-gradient sums per grid point (4th-order
+// differences, the six off-diagonal ones averaged over the four surrounding staggered nodes) and, with green_bforce,
+// three displacement sums; every ntdec_w steps the sums are written to gf(itw, (i-1)*ncmp + c) (:523-547).
+struct GreenParams {
+    int ng, ncmp, ntw, itw, sample, bforce;
+    const int *ijk;          // 3*ng: LOCAL memory-box indices (mi, mj) and k
+    float *acc;              // 12 per point: dxUx dxUy dxUz dyUx dyUy dyUz dzUx dzUy dzUz Ux Uy Uz
+    float *gf;               // (ntw, ncmp*ng), itw fastest
+    double r40[3], r41[3];   // C40/d, C41/d in the field kind (:111-116)
+};
+
+template <typename F>
+__global__ void green_store_kernel(const __grid_constant__ KParams<F> p, const GreenParams g) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= g.ng) return;
+    const long long si = p.SI, sj = p.SJ;
+    const long long n = (long long)(g.ijk[3 * s + 2] + KOFF - 1) + (long long)p.NZP * ((long long)g.ijk[3 * s] + (long long)p.NXM * g.ijk[3 * s + 1]);
+    const F *Vx = p.Vx, *Vy = p.Vy, *Vz = p.Vz;
+    const float dt = p.dt;
+    const F r40x = (F)g.r40[0], r40y = (F)g.r40[1], r40z = (F)g.r40[2], r41x = (F)g.r41[0], r41y = (F)g.r41[1], r41z = (F)g.r41[2];
+    // d<a>V<b> at offset o: 4th-order difference of component b along a, staggered forward (fwd) or backward
+    auto dxb = [&](const F *V, long long o) { return (V[n + o] - V[n + o - si]) * r40x - (V[n + o + si] - V[n + o - 2 * si]) * r41x; };
+    auto dxf = [&](const F *V, long long o) { return (V[n + o + si] - V[n + o]) * r40x - (V[n + o + 2 * si] - V[n + o - si]) * r41x; };
+    auto dyb = [&](const F *V, long long o) { return (V[n + o] - V[n + o - sj]) * r40y - (V[n + o + sj] - V[n + o - 2 * sj]) * r41y; };
+    auto dyf = [&](const F *V, long long o) { return (V[n + o + sj] - V[n + o]) * r40y - (V[n + o + 2 * sj] - V[n + o - sj]) * r41y; };
+    auto dzb = [&](const F *V, long long o) { return (V[n + o] - V[n + o - 1]) * r40z - (V[n + o + 1] - V[n + o - 2]) * r41z; };
+    auto dzf = [&](const F *V, long long o) { return (V[n + o + 1] - V[n + o]) * r40z - (V[n + o + 2] - V[n + o - 1]) * r41z; };
+    const F dxVx = dxb(Vx, 0), dyVy = dyb(Vy, 0), dzVz = dzb(Vz, 0);
+    const F dxVy = (dxf(Vy, 0) + dxf(Vy, -sj) + dxb(Vy, 0) + dxb(Vy, -sj)) * 0.25f;
+    const F dxVz = (dxf(Vz, 0) + dxf(Vz, -1) + dxb(Vz, 0) + dxb(Vz, -1)) * 0.25f;
+    const F dyVx = (dyf(Vx, 0) + dyf(Vx, -si) + dyb(Vx, 0) + dyb(Vx, -si)) * 0.25f;
+    const F dyVz = (dyf(Vz, 0) + dyf(Vz, -1) + dyb(Vz, 0) + dyb(Vz, -1)) * 0.25f;
+    const F dzVx = (dzf(Vx, 0) + dzf(Vx, -si) + dzb(Vx, 0) + dzb(Vx, -si)) * 0.25f;
+    const F dzVy = (dzf(Vy, 0) + dzf(Vy, -sj) + dzb(Vy, 0) + dzb(Vy, -sj)) * 0.25f;
+    float *a = g.acc + 12 * (long long)s;
+    a[0] = a[0] + (float)(dxVx * dt); a[1] = a[1] + (float)(dxVy * dt); a[2] = a[2] + (float)(dxVz * dt);
+    a[3] = a[3] + (float)(dyVx * dt); a[4] = a[4] + (float)(dyVy * dt); a[5] = a[5] + (float)(dyVz * dt);
+    a[6] = a[6] + (float)(dzVx * dt); a[7] = a[7] + (float)(dzVy * dt); a[8] = a[8] + (float)(dzVz * dt);
+    if (g.bforce) {
+        a[9] = a[9] + 0.5f * (float)(Vx[n] + Vx[n - si]) * dt;
+        a[10] = a[10] + 0.5f * (float)(Vy[n] + Vy[n - sj]) * dt;
+        a[11] = a[11] + 0.5f * (float)(Vz[n] + Vz[n - 1]) * dt;
+    }
+    if (!g.sample) return;
+    const float UC_BF = 1e-12f, UC_DERIV = 1e-15f;   // m_green.f90:30-31
+    const long long nt = g.ntw;
+    float *o = g.gf + nt * g.ncmp * s + (g.itw - 1);
+    o[0] = a[0] * UC_DERIV * 1e9f;
+    o[nt] = a[4] * UC_DERIV * 1e9f;
+    o[2 * nt] = a[8] * UC_DERIV * 1e9f;
+    o[3 * nt] = (a[5] + a[7]) * UC_DERIV * 1e9f;
+    o[4 * nt] = (a[2] + a[6]) * UC_DERIV * 1e9f;
+    o[5 * nt] = (a[1] + a[3]) * UC_DERIV * 1e9f;
+    if (g.bforce) {
+        o[6 * nt] = a[9] * UC_BF * 1e9f;
+        o[7 * nt] = a[10] * UC_BF * 1e9f;
+        o[8 * nt] = a[11] * UC_BF * 1e9f;
+    }
+}
+
+// green__source m_green.f90:606-649: unit body force at the pseudo source (a station), six single-thread adds
+template <typename F>
+__global__ void green_source_kernel(const __grid_constant__ KParams<F> p, int mi, int mj, int k, float fx, float fy, float fz) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const long long si = p.SI, sj = p.SJ;
+    const long long n = (long long)(k + KOFF - 1) + (long long)p.NZP * ((long long)mi + (long long)p.NXM * mj);
+    const float *rho = p.rho;
+    p.Vx[n] = p.Vx[n] + (2.0f / (rho[n] + rho[n + si])) * fx / 2;
+    p.Vx[n - si] = p.Vx[n - si] + (2.0f / (rho[n] + rho[n - si])) * fx / 2;
+    p.Vy[n] = p.Vy[n] + (2.0f / (rho[n] + rho[n + sj])) * fy / 2;
+    p.Vy[n - sj] = p.Vy[n - sj] + (2.0f / (rho[n] + rho[n - sj])) * fy / 2;
+    p.Vz[n] = p.Vz[n] + (2.0f / (rho[n] + rho[n + 1])) * fz / 2;
+    p.Vz[n - 1] = p.Vz[n - 1] + (2.0f / (rho[n] + rho[n - 1])) * fz / 2;
 }
 
 // kernel__vmax m_kernel.f90:360-372: max |V| at k = kob(i,j)+1 over the given local (i,j) window

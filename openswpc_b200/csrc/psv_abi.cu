@@ -493,11 +493,12 @@ template <typename F, int NM, bool STRESS>
 static int launch_phase(swpcpsv_handle *h, const PsvParams<F> &p, int phase) {
     const int tk = std::min(h->tk, (h->g.nz + 31) / 32 * 32);
     dim3 blk((unsigned)tk), grd((unsigned)((h->g.nz + tk - 1) / tk), (unsigned)((h->nxp + h->ilen - 1) / h->ilen));
-    psv_sweep<F, NM, STRESS><<<grd, blk, 0, h->st>>>(p, phase, 0, h->nxp - 1, h->ilen, h->pf);
+    psv_sweep<F, NM, STRESS><<<grd, blk, 0, h->st>>>(p, phase, 0, h->nxp - 1, h->ilen, h->pf, 1);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
 }
+
 template <typename F, bool STRESS>
 static int launch_sweep(swpcpsv_handle *h, int phase) {
     const PsvParams<F> p = make_params<F>(h);
@@ -697,7 +698,8 @@ extern "C" int swpcpsv_comm_local(swpcpsv_handle **hs, int32_t n, int32_t which)
         for (int f = 0; f < 2; f++) {
             if (h->nbr[f] < 0) continue;
             if (h->nbr[f] >= n) return fail("swpcpsv_comm_local: neighbour not in the handle list");
-            CK(cudaMemcpy(hs[h->nbr[f]]->rbuf[1 - f], h->sbuf[f], (size_t)3 * h->g.nz * h->fb, cudaMemcpyDefault));
+            // on the receiver's own non-blocking stream, ahead of its unpack (a default-stream D2D cudaMemcpy orders against neither)
+            CK(cudaMemcpyAsync(hs[h->nbr[f]]->rbuf[1 - f], h->sbuf[f], (size_t)3 * h->g.nz * h->fb, cudaMemcpyDefault, hs[h->nbr[f]]->st));
         }
     }
     for (int q = 0; q < n; q++) {

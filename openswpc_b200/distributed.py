@@ -44,6 +44,24 @@ def allreduce_minmax(run) -> None:
     run.set_minmax(float(a.item()), float(b.item()))
 
 
+def broadcast_green_source(run) -> None:
+    """Green's-function mode: wav__stquery on every rank + mpi_bcast from the owner (m_green.f90:161-183)."""
+    import torch.distributed as dist
+
+    if not run["green_mode"]:
+        return
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    mine = run.green_query()
+    allq = [None] * dist.get_world_size()
+    dist.all_gather_object(allq, mine)
+    owners = [q for q in allq if q[0]]
+    if not owners:
+        raise RuntimeError("green_stnm is not inside the model (assert, m_green.f90:165)")
+    _, ijk, xyz, ll = owners[-1]   # mpi_allreduce(MAX) of the owner's rank (:168-174)
+    run.green_set_source(ijk, xyz, ll)
+
+
 def attach_nccl(run) -> None:
     """Create the library's own NCCL communicator: rank 0 makes the unique id, torch.distributed broadcasts it."""
     import torch.distributed as dist

@@ -240,7 +240,33 @@ module m_swpc3d_b200
             integer(c_int32_t), value :: root
         end function
 
-        !! tuning / modes: key is a null-terminated name ("pw_mode", "tma", "jlen", ...)
+        !! Green's-function mode (m_green.f90): device copy-in of green__setup (:351), green__store, green__source, update self(gf)
+        integer(c_int) function swpc3d_set_green(h, ng, ig, jg, kg, bforce, is_src, isrc, jsrc, ksrc, fx1, fy1, fz1, trise, &
+                                                 stftype, ntdec_w, ntw, tbeg) bind(c, name='swpc3d_set_green')
+            import :: c_int, c_int32_t, c_float, c_char, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: ng, bforce, is_src, isrc, jsrc, ksrc, ntdec_w, ntw
+            integer(c_int32_t), intent(in) :: ig(*), jg(*), kg(*)
+            real(c_float), value :: fx1, fy1, fz1, trise, tbeg
+            character(kind=c_char), intent(in) :: stftype(*)
+        end function
+        integer(c_int) function swpc3d_green_store(h, it) bind(c, name='swpc3d_green_store')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_green_source(h, it) bind(c, name='swpc3d_green_source')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
+        integer(c_int) function swpc3d_get_green(h, gf) bind(c, name='swpc3d_get_green')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(out) :: gf(*)             !! gf(ntw, ncmp*ng) as m_green.f90:325
+        end function
+
+        !! tuning / modes: key is a null-terminated name ("pw_mode", "tma", "jlen", "overlap", ...)
         integer(c_int) function swpc3d_set_option(h, key, value) bind(c, name='swpc3d_set_option')
             import :: c_int, c_int32_t, c_char, c_ptr
             type(c_ptr), value :: h

@@ -19,13 +19,13 @@ from . import _lib
 
 _INTS = {"nx", "ny", "nz", "nt", "na", "nm", "nproc_x", "nproc_y", "myid", "ibeg", "iend", "jbeg", "jend", "nxp", "nyp", "ibeg_k",
          "iend_k", "jbeg_k", "jend_k", "kbeg_k", "kend_k", "nsrc", "nst", "ntw", "ntdec_w", "ntdec_r", "bf_mode", "nzm", "nxm",
-         "nym", "exedate", "tz_minutes", "field_bytes"}
+         "nym", "exedate", "tz_minutes", "field_bytes", "green_mode", "ng", "green_ncmp", "green_ntw"}
 _DOUBLES = {"dx", "dy", "dz", "dt", "xbeg", "ybeg", "zbeg", "tbeg", "vmin", "vmax", "vmin_local", "vmax_local", "fmax", "fcut", "M0",
             "UC", "zeta", "d2", "c", "r", "loop_seconds", "evlo", "evla", "evdp", "clon", "clat", "phi"}
 _STRS = {"title", "odir", "abc_type", "stftype", "vmodel_type", "stf_format", "wav_format"}
 _F32 = {"rho", "lam", "mu", "taup", "taus", "gxc", "gxe", "gyc", "gye", "gzc", "gze", "gx_c", "gx_b", "gy_c", "gy_b", "gz_c", "gz_b",
-        "ts", "c1", "c2", "d1", "srcprm", "xc", "yc", "zc", "stlo", "stla", "wav", "wav_u", "wav_stress", "wav_strain"}
-_I32 = {"kfs", "kob", "kfs_top", "kfs_bot", "kob_top", "kob_bot", "kbeg_a", "src_ijk", "st_ijk"}
+        "ts", "c1", "c2", "d1", "srcprm", "xc", "yc", "zc", "stlo", "stla", "wav", "wav_u", "wav_stress", "wav_strain", "green_gf"}
+_I32 = {"kfs", "kob", "kfs_top", "kfs_bot", "kob_top", "kob_bot", "kbeg_a", "src_ijk", "st_ijk", "green_ijk", "green_gid"}
 _F64 = {"mo", "mij"} | {"init_" + f for f in ("Vx", "Vy", "Vz", "Sxx", "Syy", "Szz", "Syz", "Sxz", "Sxy")}
 
 _bound = False
@@ -53,6 +53,9 @@ def _bind(lib):
     lib.swpc3d_host_run.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
     lib.swpc3d_host_write_sac.argtypes = [vp, cp, C.POINTER(i32)]
     lib.swpc3d_host_banner.argtypes = [vp]
+    lib.swpc3d_host_green_query.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.swpc3d_host_green_set_source.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.swpc3d_host_write_green.argtypes = [vp, cp, C.POINTER(i32)]
     lib.swpc3d_host_snap_open.argtypes = [vp, cp]
     lib.swpc3d_host_snap_close.argtypes = [vp]
     _bound = True
@@ -124,8 +127,10 @@ class Swpc3d:
             return out.reshape(nym, nxm)
         if name in ("gxc", "gxe", "gyc", "gye", "gzc", "gze"):
             return out.reshape(-1, 4)
-        if name in ("src_ijk", "st_ijk"):
+        if name in ("src_ijk", "st_ijk", "green_ijk"):
             return out.reshape(-1, 3)
+        if name == "green_gf":
+            return out.reshape(-1, max(self["green_ntw"], 1))
         if name == "mij":
             return out.reshape(-1, 6)
         if name == "srcprm":
@@ -177,6 +182,23 @@ class Swpc3d:
     def write_sac(self, odir=None) -> int:
         n = C.c_int32()
         self._ck(self.lib.swpc3d_host_write_sac(self.h, os.fspath(odir).encode() if odir is not None else None, C.byref(n)))
+        return n.value
+
+    # ---- Green's-function mode (m_green.f90)
+    def green_query(self):
+        """(found, ijk[3], xyz[3], lonlat[2]) of the pseudo source on this rank (wav__stquery)."""
+        f, ijk, xyz, ll = C.c_int32(), (C.c_int32 * 3)(), (C.c_float * 3)(), (C.c_float * 2)()
+        self._ck(self.lib.swpc3d_host_green_query(self.h, C.byref(f), ijk, xyz, ll))
+        return bool(f.value), list(ijk), list(xyz), list(ll)
+
+    def green_set_source(self, ijk, xyz, lonlat):
+        """The broadcast of m_green.f90:176-183: hand every rank the owner's answer; reads the grid-point list."""
+        self._ck(self.lib.swpc3d_host_green_set_source(self.h, (C.c_int32 * 3)(*ijk), (C.c_float * 3)(*xyz), (C.c_float * 2)(*lonlat)))
+
+    def write_green(self, odir=None) -> int:
+        """green__export: SAC / CSF files of the Green's-function traces; returns the file count."""
+        n = C.c_int32()
+        self._ck(self.lib.swpc3d_host_write_green(self.h, os.fspath(odir).encode() if odir is not None else None, C.byref(n)))
         return n.value
 
     def snap_open(self, odir=None):

@@ -178,12 +178,38 @@ typedef struct {
     ora_mp *sbuf_ip, *sbuf_im, *sbuf_jp, *sbuf_jm, *rbuf_ip, *rbuf_im, *rbuf_jp, *rbuf_jm;
 } ora_rank;
 
+/* ---------------------------------------------------------------- Green's function mode (m_green.f90, ora_green.c) */
+typedef struct {
+    int ng;                       /* grid points of the list file owned by this rank (m_green.f90:216-280) */
+    int *ig, *jg, *kg, *gid;
+    float *xg, *yg, *zg, *lon, *lat;
+    float *gf;                    /* (ntw, ncmp*ng) */
+    float *acc;                   /* 12 running sums per point: dxUx dxUy dxUz dyUx dyUy dyUz dzUx dzUy dzUz Ux Uy Uz */
+    int is_src;                   /* redefined is_src, m_green.f90:185-186 */
+} ora_green_rank;
+
+typedef struct {
+    char stnm[9];
+    char cmp;                     /* 'x' 'y' 'z' */
+    float trise, maxdist;
+    int bforce, ncmp;
+    int isrc, jsrc, ksrc;
+    float xsrc, ysrc, zsrc, evlo0, evla0;
+    float fx1, fy1, fz1;
+    float dt_dxyz;                /* real(SP) in m_green.f90:32 */
+    int ntdec_w, ntw;
+    char stftype[16], wav_format[16];
+    ora_mp r40x, r40y, r40z, r41x, r41y, r41z;
+    ora_green_rank *r;            /* one per emulated rank */
+} ora_green;
+
 typedef struct {
     ora_cfg cfg;
     int nranks;
     ora_rank *r;
     int *itbl;                    /* (-1:nproc_x, -1:nproc_y), -1 == MPI_PROC_NULL */
     void *snap;                   /* snapshot state (ora_snap.c) */
+    ora_green *green;             /* NULL unless green_mode */
     char errmsg[512];
 } ora_sim;
 
@@ -259,6 +285,17 @@ int ora_snap_nrec(const ora_sim *s, int q);
 int ora_snap_rec(const ora_sim *s, int q, int rec, float *out, int *it0);
 int ora_snap_max(const ora_sim *s, int q, float *out);
 int ora_snap_medium(const ora_sim *s, int q, int which, float *out);
+/* Green's function mode (m_green.f90): setup after wav_setup, store / source inside ora_step */
+int ora_green_setup(ora_sim *s, const ora_ini *ini, const char *base, char *err, size_t cap);
+void ora_green_store(ora_sim *s, int it);
+void ora_green_source(ora_sim *s, int it);
+void ora_green_free(ora_sim *s);
+/* ints: 0 ng(rank) 1 ncmp 2 isrc 3 jsrc 4 ksrc 5 is_src(rank) 6 ntw */
+int ora_green_int(const ora_sim *s, int rank, int what);
+int ora_green_points(const ora_sim *s, int rank, int *ijk /*3*ng*/, int *gid /*ng*/);
+int ora_get_green(const ora_sim *s, int rank, float *out /*(ncmp*ng, ntw) C order*/);
+/* green__export (m_green.f90:553-604), wav_format = 'sac': <odir>/green/<stnm>/<title>__<gid>__<stnm>__<cmp>__<mij>__.sac */
+int ora_write_green_sac(const ora_sim *s, const char *odir);
 /* SAC output of all stations of all ranks (m_wav.f90:658-792); returns number of files */
 int ora_write_sac(const ora_sim *s, const char *odir);
 

@@ -407,3 +407,64 @@ int ora_write_sac(const ora_sim *s, const char *odir) {
     }
     return nfiles;
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* green__export, wav_format = 'sac' (m_green.f90:553-573); headers of green__setup :282-349 on sac__init defaults */
+int ora_write_green_sac(const ora_sim *s, const char *odir) {
+    const ora_green *g = s->green;
+    if (!g) return 0;
+    const ora_cfg *c = &s->cfg;
+    static const char *cmpn[9] = {"mxx", "myy", "mzz", "myz", "mxz", "mxy", "fx_", "fy_", "fz_"};
+    char dir[1200];
+    snprintf(dir, sizeof(dir), "%s/green/%s", odir, g->stnm);
+    mkdir_p(dir);
+    int nfiles = 0;
+    const float dx = (float)c->dx, dy = (float)c->dy, dz = (float)c->dz;
+    for (int q = 0; q < s->nranks; q++) {
+        const ora_green_rank *gr = &g->r[q];
+        for (int i = 0; i < gr->ng; i++)
+            for (int j = 0; j < g->ncmp; j++) {
+                sac_raw h;
+                for (int w = 0; w < 70; w++) h.f[w] = -12345.0f;
+                for (int w = 0; w < 35; w++) h.i[w] = -12345;
+                for (int w = 0; w < 24; w++) put8(h.a + 8 * w, "-12345", 8);
+                put8(h.a + 8, "-12345", 16);
+                const double delta = (double)(g->ntdec_w * c->dt);
+                h.f[0] = (float)((int)(delta * 1e7)) / 1e7f;
+                h.f[5] = c->tbeg;
+                h.f[31] = g->evla0; h.f[32] = g->evlo0; h.f[34] = g->zsrc * 1000;   /* station = pseudo source */
+                h.f[35] = gr->lat[i]; h.f[36] = gr->lon[i]; h.f[38] = gr->zg[i];
+                h.f[40] = gr->xg[i]; h.f[41] = gr->yg[i]; h.f[42] = gr->zg[i];
+                h.f[43] = ora_i2x(gr->ig[i], c->xbeg, dx); h.f[44] = ora_i2x(gr->jg[i], c->ybeg, dy); h.f[45] = ora_i2x(gr->kg[i], c->zbeg, dz);
+                h.f[46] = c->clon; h.f[47] = c->clat; h.f[48] = c->phi;
+                char kc[9];
+                if (g->cmp == 'x') { snprintf(kc, sizeof(kc), "G_Vx_%s", cmpn[j]); h.f[58] = 90.0f; h.f[57] = 0.0f + c->phi; }
+                else if (g->cmp == 'y') { snprintf(kc, sizeof(kc), "G_Vy_%s", cmpn[j]); h.f[58] = 90.0f; h.f[57] = 90.0f + c->phi; }
+                else { snprintf(kc, sizeof(kc), "G_Vz_%s", cmpn[j]); h.f[58] = 0.0f; h.f[57] = 0.0f; }
+                time_t tt = (time_t)c->exedate + (time_t)c->tz_minutes * 60;
+                struct tm gm;
+                gmtime_r(&tt, &gm);
+                h.i[0] = gm.tm_year + 1900; h.i[1] = gm.tm_yday + 1; h.i[2] = gm.tm_hour; h.i[3] = gm.tm_min; h.i[4] = gm.tm_sec; h.i[5] = 0;
+                h.i[6] = 6; h.i[9] = g->ntw; h.i[15] = 1; h.i[16] = j < 6 ? 7 : 6;
+                h.l[0] = 1; h.l[1] = 0; h.l[2] = 1; h.l[3] = 0; h.l[4] = 0;
+                char cid8[16];
+                snprintf(cid8, sizeof(cid8), "%08d", gr->gid[i]);
+                put8(h.a + 0, g->stnm, 8);
+                put8(h.a + 8, cid8, 16);
+                put8(h.a + 8 * 20, kc, 8);
+                char fn[1600];
+                snprintf(fn, sizeof(fn), "%s/%s__%s__%s__%c__%s__.sac", dir, c->title, cid8, g->stnm, g->cmp, cmpn[j]);
+                FILE *fp = fopen(fn, "wb");
+                if (!fp) return -1;
+                fwrite(h.f, 4, 70, fp); fwrite(h.i, 4, 35, fp); fwrite(h.l, 4, 5, fp); fwrite(h.a, 1, 192, fp);
+                const float *src = gr->gf + (size_t)g->ntw * (g->ncmp * (size_t)i + j);
+                for (int t = 0; t < g->ntw; t++) {   /* positive upward for the z component :563-565 */
+                    const float v = g->cmp == 'z' ? -src[t] : src[t];
+                    fwrite(&v, 4, 1, fp);
+                }
+                fclose(fp);
+                nfiles++;
+            }
+    }
+    return nfiles;
+}

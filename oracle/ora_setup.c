@@ -653,9 +653,9 @@ static int source_setup(ora_sim *s, const ora_ini *ini, const char *base) {
     ora_readini_l(ini, "bf_mode", &c->bf_mode, 0);
     if (c->pw_mode && c->green_mode) { set_err("assert: pw_mode and green_mode are exclusive (m_source.f90:70)"); return -1; }
     if (c->pw_mode && !c->benchmark_mode) return pw_setup(s, ini); /* :73-82 */
-    if (c->green_mode && !c->benchmark_mode) {
-        set_err("green_mode is outside the hot-path scope");
-        return -1;
+    if (c->green_mode && !c->benchmark_mode) { /* :84-91: no regular source grid; M0 / fmax come from green__setup */
+        c->pw_mode = 0;
+        return 0;
     }
     char tmp[ORA_STRLEN];
     ora_readini_c(ini, "fn_stf", c->fn_stf, "");
@@ -974,7 +974,12 @@ static int wav_setup(ora_sim *s, const ora_ini *ini, const char *base) {
     ora_readini_c(ini, "st_format", tmp, "xy");
     strncpy(c->st_format, tmp, sizeof(c->st_format) - 1);
     ora_readini_c(ini, "fn_stloc", c->fn_stloc, "");
-    if (!(c->sw_wav_v || c->sw_wav_u || c->sw_wav_stress || c->sw_wav_strain)) return 0;
+    {   /* m_wav.f90:76-86: Green's-function mode keeps the station table (wav__stquery) but records nothing */
+        int gm;
+        ora_readini_l(ini, "green_mode", &gm, 0);
+        if (gm) c->sw_wav_v = c->sw_wav_u = c->sw_wav_stress = c->sw_wav_strain = 0;
+        else if (!(c->sw_wav_v || c->sw_wav_u || c->sw_wav_stress || c->sw_wav_strain)) return 0;
+    }
     c->ntw = (int)floorf((float)(c->nt - 1) / (float)c->ntdec_w + 1.0f); /* :89 */
 
     char path[2 * ORA_STRLEN];
@@ -1102,6 +1107,10 @@ static ora_sim *create_from_ini(ora_ini *ini, const char *base_dir, int nm, int 
     if (absorb_setup(s)) { ora_destroy(s); return NULL; }
     ora_snap_setup(s, ini); /* main.f90:76 */
     if (wav_setup(s, ini, base_dir)) { ora_destroy(s); return NULL; }
+    {   /* main.f90:78 */
+        char m[600] = "";
+        if (ora_green_setup(s, ini, base_dir, m, sizeof(m))) { set_err(m); ora_destroy(s); return NULL; }
+    }
     ora_readini_i(ini, "ntdec_r", &c->ntdec_r, 10); /* m_report.f90:47 */
     return s;
 }
@@ -1129,6 +1138,7 @@ ora_sim *ora_create_from_text(const char *inf_text, const char *base_dir, int nm
 void ora_destroy(ora_sim *s) {
     if (!s) return;
     ora_snap_free(s);
+    ora_green_free(s);
     for (int q = 0; q < s->nranks; q++) {
         ora_rank *r = &s->r[q];
         void *ptrs[] = {r->Vx, r->Vy, r->Vz, r->Sxx, r->Syy, r->Szz, r->Syz, r->Sxz, r->Sxy, r->Rxx, r->Ryy, r->Rzz, r->Ryz,

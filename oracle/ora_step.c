@@ -686,6 +686,7 @@ void ora_vmax(ora_sim *s, float out[3]) {
 
 /* one iteration, main.f90:119-139 (report__progress is ora_vmax; snapshots/green are out of scope) */
 void ora_step(ora_sim *s, int it) {
+    ora_green_store(s, it);
     ora_wav_store(s, it);
     ora_snap_write(s, it);
     ora_update_stress(s);
@@ -693,6 +694,7 @@ void ora_step(ora_sim *s, int it) {
     ora_comm_stress(s);
     ora_update_vel(s);
     ora_bodyforce(s, it);
+    ora_green_source(s, it);
     ora_comm_vel(s);
 }
 

@@ -69,6 +69,15 @@ def _load(name: str) -> C.CDLL:
     lib.ora_get_profile.argtypes = [vp, ci, cc, C.POINTER(C.c_float)]
     lib.ora_write_sac.restype = ci
     lib.ora_write_sac.argtypes = [vp, cc]
+    # Green's-function mode (ora_green.c)
+    lib.ora_green_int.restype = ci
+    lib.ora_green_int.argtypes = [vp, ci, ci]
+    lib.ora_green_points.restype = ci
+    lib.ora_green_points.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    lib.ora_get_green.restype = ci
+    lib.ora_get_green.argtypes = [vp, ci, C.POINTER(C.c_float)]
+    lib.ora_write_green_sac.restype = ci
+    lib.ora_write_green_sac.argtypes = [vp, cc]
     # small helpers
     lib.ora_x2i.restype = ci
     lib.ora_x2i.argtypes = [C.c_float, C.c_float, C.c_float]
@@ -228,6 +237,25 @@ class Oracle:
             raise KeyError(name)
         a = np.frombuffer(buf, dtype=np.float32)[:n].copy()
         return a.reshape(-1, 4) if name in ("gxc", "gxe", "gyc", "gye", "gzc", "gze") else a
+
+    # ---- Green's-function mode
+    GREEN_INTS = ["ng", "ncmp", "isrc", "jsrc", "ksrc", "is_src", "ntw"]
+
+    def green(self, q: int) -> dict:
+        """ints of ora_green_int + the owned grid points (ijk (ng,3), gid) + traces gf (ncmp*ng, ntw) of rank q."""
+        d = {n: self.lib.ora_green_int(self.h, q, i) for i, n in enumerate(self.GREEN_INTS)}
+        ng = max(d["ng"], 0)
+        ijk = np.zeros((max(ng, 1), 3), dtype=np.int32)
+        gid = np.zeros(max(ng, 1), dtype=np.int32)
+        self.lib.ora_green_points(self.h, q, ijk.ctypes.data_as(C.POINTER(C.c_int)), gid.ctypes.data_as(C.POINTER(C.c_int)))
+        gf = np.zeros((max(ng, 1) * d["ncmp"], max(d["ntw"], 1)), dtype=np.float32)
+        if ng:
+            self.lib.ora_get_green(self.h, q, gf.ctypes.data_as(C.POINTER(C.c_float)))
+        d.update(ijk=ijk[:ng], gid=gid[:ng], gf=gf[: ng * d["ncmp"]])
+        return d
+
+    def write_green_sac(self, odir: str | os.PathLike) -> int:
+        return self.lib.ora_write_green_sac(self.h, str(odir).encode())
 
     def write_sac(self, odir: str | os.PathLike) -> int:
         return self.lib.ora_write_sac(self.h, str(odir).encode())

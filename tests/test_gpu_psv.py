@@ -79,8 +79,11 @@ def _compare(o, devs, products=(0,)):
             assert np.array_equal(d.get_wav(prod), o.wav(q, prod)), f"rank {q} station product {prod}"
 
 
-def test_pml_nm3_bit_exact(tmp_path):
+@pytest.mark.parametrize("opts", [{}, {"ilen": 7, "pf": 0}])
+def test_pml_nm3_bit_exact(tmp_path, opts):
     o, devs = _pair(tmp_path, 80, products="v,u,stress,strain")
+    for key, val in opts.items():
+        devs[0].set_option(key, val)
     _step_all(o, devs, 80)
     assert np.abs(o.field(0, "Vz")).max() > 0
     _compare(o, devs, products=(0, 1, 2, 3))
