@@ -267,6 +267,8 @@ def main():
     from openswpc_b200.distributed import allreduce_minmax, attach_nccl, init_process_group
     from openswpc_b200.swpc3d import Swpc3d
 
+    # host-side setup is OpenMP code: share the box's cores between the ranks instead of oversubscribing them
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     _lib.load()
     init_process_group("nccl" if world > 1 else None)
     import torch.distributed as dist

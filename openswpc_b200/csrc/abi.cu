@@ -277,7 +277,11 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
         CK(cudaEventCreateWithFlags(&h->ev_join[q], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    CK(cudaStreamCreateWithFlags(&h->cs, cudaStreamNonBlocking));
+    {   // the exchange stream outranks the sweeps: its short kernels (slabs, pack, NCCL, unpack) take the next free SM slots
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&h->cs, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&h->ev_b, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_c, cudaEventDisableTiming));
     CK(cudaEventCreate(&h->ev0));

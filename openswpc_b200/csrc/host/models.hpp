@@ -108,18 +108,16 @@ inline int rdrmed3d(const MediumBox &b, const std::string &fn, float *vol) {
     const long long nxc = nc.dim[0], nyc = nc.dim[1], nzc = nc.dim[2], beg = nc.var[3].begin;
     if (beg + 4 * nxc * nyc * nzc > (long long)nc.bytes.size()) return hfail("rdrmed__3d: " + fn + " is truncated");
     auto wrap = [](long long v, long long n) { long long r = v % n; return r <= 0 ? r + n : r; };
+    // (k innermost: contiguous writes; the reads stride through the volume, which is small and cache-resident)
     const int ktop = (int)std::min<long long>(b.ke, nzc);
-#pragma omp parallel for schedule(static)
-    for (int k = b.kb; k <= ktop; k++) {
-        const long long plane = beg + 4 * nxc * nyc * ((k <= 0 ? k + nzc : k) - 1);
-        for (int j = b.jb; j <= b.je; j++) {
-            const long long row = plane + 4 * nxc * (wrap(j, nyc) - 1);
-            for (int i = b.ib; i <= b.ie; i++) vol[b.at(k, i, j)] = nc.f32(row + 4 * (wrap(i, nxc) - 1));
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int j = b.jb; j <= b.je; j++)
+        for (int i = b.ib; i <= b.ie; i++) {
+            const long long col = beg + 4 * (nxc * (wrap(j, nyc) - 1) + (wrap(i, nxc) - 1));
+            float *v = vol + b.at(b.kb, i, j);
+            for (int k = b.kb; k <= ktop; k++) v[k - b.kb] = nc.f32(col + 4 * nxc * nyc * ((k <= 0 ? k + nzc : k) - 1));
+            for (long long k = nzc + 1; k <= b.ke; k++) v[k - b.kb] = v[(k % nzc) - b.kb];
         }
-    }
-    for (long long k = nzc + 1; k <= b.ke; k++)
-        for (int j = b.jb; j <= b.je; j++)
-            for (int i = b.ib; i <= b.ie; i++) vol[b.at((int)k, i, j)] = vol[b.at((int)(k % nzc), i, j)];
     return 0;
 }
 
@@ -193,9 +191,31 @@ struct ModelEnv {
 inline void set_cell(const MediumBox &b, size_t n, float rho, float vp, float vs, float qp, float qs) {
     b.rho[n] = rho; b.mu[n] = rho * vs * vs; b.lam[n] = rho * (vp * vp - 2 * vs * vs); b.qp[n] = qp; b.qs[n] = qs;
 }
-inline void set_plane(const MediumBox &b, int k, float rho, float vp, float vs, float qp, float qs) {
+
+// The reference's builders loop over k outermost; k is the FASTEST index in memory, so that order strides through all
+// five arrays.  Here every builder first decides, per plane k, whether the plane is laterally uniform (air, ocean, 1-D
+// models) or needs a per-cell evaluation, and the arrays are then filled column by column (k innermost, contiguous).
+struct PlanePlan {
+    bool uniform = true;
+    float rho = 0, mu = 0, lam = 0, qp = 0, qs = 0;   // uniform planes
+    int layer = -1;                                   // per-cell planes: what the cell function needs
+    float cv = 1.0f;
+    void set(float r, float vp, float vs, float a, float b_) { rho = r; mu = r * vs * vs; lam = r * (vp * vp - 2 * vs * vs); qp = a; qs = b_; }
+};
+template <typename CellFn>
+inline void fill_columns(const MediumBox &b, const std::vector<PlanePlan> &pl, CellFn &&cell) {
+    const int nk = b.nk();
+#pragma omp parallel for collapse(2) schedule(static)
     for (int j = b.jb; j <= b.je; j++)
-        for (int i = b.ib; i <= b.ie; i++) set_cell(b, b.at(k, i, j), rho, vp, vs, qp, qs);
+        for (int i = b.ib; i <= b.ie; i++) {
+            const size_t n0 = b.at(b.kb, i, j);
+            for (int q = 0; q < nk; q++) {
+                const PlanePlan &p = pl[(size_t)q];
+                const size_t n = n0 + (size_t)q;
+                if (p.uniform) { b.rho[n] = p.rho; b.mu[n] = p.mu; b.lam[n] = p.lam; b.qp[n] = p.qp; b.qs[n] = p.qs; }
+                else cell(p, n);
+            }
+        }
 }
 
 // air / ocean plane above the first interface, shared by the lhm / lgm families; returns false inside the solid
@@ -221,6 +241,7 @@ inline int vmodel_lgm(const ModelEnv &e, const MediumBox &b, float &bd0) {
     if (read_layer_table(join_path(e.base, e.ini->get("fn_lhm", "")), false, e.vcut, t)) return 1;
     const int nl = t.n();
     bd0 = t.depth[0];
+    std::vector<PlanePlan> pl((size_t)b.nk());
     for (int k = b.kb; k <= b.ke; k++) {
         const float zc = b.zc[k - b.kb];
         float zs, cv, rho, vp, vs, qp, qs;
@@ -230,8 +251,9 @@ inline int vmodel_lgm(const ModelEnv &e, const MediumBox &b, float &bd0) {
             for (int l = 0; l + 1 < nl; l++)
                 if (t.depth[l] <= zs && zs < t.depth[l + 1]) { gradient_at(t, l, zs, cv, rho, vp, vs, qp, qs); break; }
         }
-        set_plane(b, k, rho, vp, vs, qp, qs);
+        pl[(size_t)(k - b.kb)].set(rho, vp, vs, qp, qs);
     }
+    fill_columns(b, pl, [](const PlanePlan &, size_t) {});
     return 0;
 }
 
@@ -265,22 +287,22 @@ inline int vmodel_uni_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
     const std::string path = join_path(e.base, ini.get("dir_rmed", "") + "/" + ini.get("fn_rmed0", ""));
     if (std::ifstream(path).good() && rdrmed3d(b, path, xi.data())) return 1;
     bd0 = topo0;
-#pragma omp parallel for schedule(dynamic, 4)
+    std::vector<PlanePlan> pl((size_t)b.nk());
     for (int k = b.kb; k <= b.ke; k++) {
+        PlanePlan &p = pl[(size_t)(k - b.kb)];
         const float zc = b.zc[k - b.kb];
         float zs, cv;
         e.depth(zc, zs, cv);
-        if (zs > topo0) {
-            for (int j = b.jb; j <= b.je; j++)
-                for (int i = b.ib; i <= b.ie; i++) {
-                    const size_t n = b.at(k, i, j);
-                    float rho = (1.0f + 0.8f * xi[n]) * rho0, vp = (1.0f + xi[n]) * cv * vp0, vs = (1.0f + xi[n]) * cv * vs0;
-                    vcheck(vp, vs, rho, xi[n], vmin, vmax, rhomin);
-                    set_cell(b, n, rho, vp, vs, qp0, qs0);
-                }
-        } else if (zs > 0.0f) set_plane(b, k, 1.0f, cv * seawater_vel(zc, e.munk), 0.0f, 1000000.0f, 1000000.0f);
-        else set_plane(b, k, 0.001f, 0.0f, 0.0f, 10.0f, 10.0f);
+        if (zs > topo0) { p.uniform = false; p.cv = cv; }
+        else if (zs > 0.0f) p.set(1.0f, cv * seawater_vel(zc, e.munk), 0.0f, 1000000.0f, 1000000.0f);
+        else p.set(0.001f, 0.0f, 0.0f, 10.0f, 10.0f);
     }
+    const float *x = xi.data();
+    fill_columns(b, pl, [&](const PlanePlan &p, size_t n) {
+        float rho = (1.0f + 0.8f * x[n]) * rho0, vp = (1.0f + x[n]) * p.cv * vp0, vs = (1.0f + x[n]) * p.cv * vs0;
+        vcheck(vp, vs, rho, x[n], vmin, vmax, rhomin);
+        set_cell(b, n, rho, vp, vs, qp0, qs0);
+    });
     return 0;
 }
 
@@ -292,38 +314,34 @@ inline int vmodel_lhm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
     std::vector<std::vector<float>> xi;
     if (read_rmed_set(e, b, t, tbl, xi)) return 1;
     bd0 = t.depth[0];
-#pragma omp parallel for schedule(dynamic, 4)
+    std::vector<PlanePlan> pl((size_t)b.nk());
     for (int k = b.kb; k <= b.ke; k++) {
+        PlanePlan &p = pl[(size_t)(k - b.kb)];
         const float zc = b.zc[k - b.kb];
         float zs, cv, rho = 0, vp = 0, vs = 0, qp = 0, qs = 0;
         e.depth(zc, zs, cv);
         if (air_or_ocean(e, zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
-            if (zs < 0.0f) set_plane(b, k, rho, vp, vs, qp, qs);
-            else   // m_vmodel_lhm_rmed.f90:176-178 writes lam = 1.0 * vp1 * vp1 directly
-                for (int j = b.jb; j <= b.je; j++)
-                    for (int i = b.ib; i <= b.ie; i++) {
-                        const size_t n = b.at(k, i, j);
-                        b.rho[n] = 1.0f; b.mu[n] = 0.0f; b.lam[n] = 1.0f * vp * vp; b.qp[n] = qp; b.qs[n] = qs;
-                    }
+            p.set(rho, vp, vs, qp, qs);
+            if (!(zs < 0.0f)) p.lam = 1.0f * vp * vp;   // m_vmodel_lhm_rmed.f90:176-178 writes lam = 1.0 * vp1 * vp1 directly
             continue;
         }
         // the reference walks all layers and lets every one with zs >= depth(l) overwrite rho1 .. qs1 (:196-209): only
         // the LAST such layer survives, and it depends on k alone
-        int lsel = -1;
         for (int l = 0; l < t.n(); l++)
-            if (zs >= t.depth[l]) lsel = l;
-        if (lsel < 0) { set_plane(b, k, rho, vp, vs, qp, qs); continue; }
-        const bool solid = t.vp[lsel] > 0 && t.vs[lsel] > 0;
-        const float *xl = xi[tbl[lsel]].data();
-        for (int j = b.jb; j <= b.je; j++)
-            for (int i = b.ib; i <= b.ie; i++) {
-                const size_t n = b.at(k, i, j);
-                const float x = xl[n];
-                rho = t.rho[lsel] * (1 + 0.8f * x); vp = cv * t.vp[lsel] * (1 + x); vs = cv * t.vs[lsel] * (1 + x);
-                if (solid) vcheck(vp, vs, rho, x, vmin, vmax, rhomin);
-                set_cell(b, n, rho, vp, vs, t.qp[lsel], t.qs[lsel]);
-            }
+            if (zs >= t.depth[l]) p.layer = l;
+        if (p.layer < 0) { p.set(rho, vp, vs, qp, qs); continue; }
+        p.uniform = false;
+        p.cv = cv;
     }
+    std::vector<const float *> xl((size_t)t.n());
+    for (int l = 0; l < t.n(); l++) xl[(size_t)l] = xi[tbl[l]].data();
+    fill_columns(b, pl, [&](const PlanePlan &p, size_t n) {
+        const int l = p.layer;
+        const float x = xl[(size_t)l][n];
+        float rho = t.rho[l] * (1 + 0.8f * x), vp = p.cv * t.vp[l] * (1 + x), vs = p.cv * t.vs[l] * (1 + x);
+        if (t.vp[l] > 0 && t.vs[l] > 0) vcheck(vp, vs, rho, x, vmin, vmax, rhomin);
+        set_cell(b, n, rho, vp, vs, t.qp[l], t.qs[l]);
+    });
     return 0;
 }
 
@@ -336,6 +354,7 @@ inline int vmodel_lgm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
     if (read_rmed_set(e, b, t, tbl, xi)) return 1;
     const int nl = t.n();
     bd0 = t.depth[0];
+    std::vector<PlanePlan> pl((size_t)b.nk());
     for (int k = b.kb; k <= b.ke; k++) {
         const float zc = b.zc[k - b.kb];
         float zs, cv, rho, vp, vs, qp, qs;
@@ -356,8 +375,9 @@ inline int vmodel_lgm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
                     break;
                 }
         }
-        set_plane(b, k, rho, vp, vs, qp, qs);
+        pl[(size_t)(k - b.kb)].set(rho, vp, vs, qp, qs);
     }
+    fill_columns(b, pl, [](const PlanePlan &, size_t) {});
     return 0;
 }
 

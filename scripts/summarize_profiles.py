@@ -41,7 +41,7 @@ def launch_list(src: Path, dst: Path, header: str, key: str):
     for o in step:
         share[o[1]] = share.get(o[1], 0.0) + o[2]
     stress = [o for o in step if o[1].startswith("stress_tma") or ("sweep_direct" in o[1] and ", 1>" in o[1])]
-    vel = [o for o in step if "sweep_direct" in o[1] and ", 0>" in o[1] or o[1].startswith("vel_tma")]
+    vel = [o for o in step if "sweep_direct" in o[1] and ", 0>" in o[1] or o[1].startswith("vel_tma") or o[1].startswith("vel_ring")]
     res = {"stress_dram_bytes_per_launch": sum(o[3] + o[4] for o in stress), "vel_dram_bytes_per_launch": sum(o[3] + o[4] for o in vel),
            "stress_ms_under_ncu": sum(o[2] for o in stress), "vel_ms_under_ncu": sum(o[2] for o in vel),
            "step_share": {k: round(v / tot, 4) for k, v in share.items()}, "source": str(dst.relative_to(ROOT)),
