@@ -471,7 +471,8 @@ __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_cons
                 pt = (k >= kb);
                 if (pt) ap = p.aoff[li + (long long)p.nxp * (lj + pf)] + (k - kb);
             }
-            prefetch_cell<F, NM, STRESS>(p, n + p.SJ * pf, pt, ap);
+            // (an absorber-only box skips its interior lanes: prefetching their S / R / medium lines would be pure waste)
+            if (!b.skip_interior || pt) prefetch_cell<F, NM, STRESS>(p, n + p.SJ * pf, pt, ap);
         }
         bool is_pml = false;
         if (pml_mode) is_pml = (k >= p.kbeg_a[col]);

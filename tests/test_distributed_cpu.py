@@ -60,3 +60,52 @@ def test_two_rank_gloo_setup(tmp_path):
     assert r0[5] == r1[5] and r0[6] == r1[6]                         # one global (vmin, vmax) pair after the reduction
     assert np.isclose(r0[5], min(r0[10][0], r1[10][0])) and np.isclose(r0[6], max(r0[10][1], r1[10][1]))
     assert np.isclose(r0[7], r0[10][0]) and np.isclose(r0[8], r0[10][1])   # MIN / MAX semantics of the raw all-reduce
+
+
+def _green_worker(rank, world, work, port, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from openswpc_b200.distributed import allreduce_minmax, broadcast_green_source, init_process_group
+    from openswpc_b200.swpc3d import Swpc3d
+    from test_green import _case
+
+    init_process_group("gloo")
+    d = Path(work) / f"r{rank}"
+    d.mkdir(parents=True, exist_ok=True)
+    inf = _case(d, ranks=(2, 1))
+    run = Swpc3d(inf, base_dir=d, nm=3, myid=rank)
+    allreduce_minmax(run)
+    found_before = run.green_query()[0]
+    broadcast_green_source(run)            # wav__stquery everywhere + mpi_bcast from the owner, m_green.f90:161-183
+    q.put((rank, found_before, run.green_query()[1], run["ng"], run.array("green_gid").tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_green_source_broadcast(tmp_path):
+    """Green's-function mode on two ranks: only the owner of the station knows the pseudo source before the broadcast; after
+    it both agree with the oracle and each holds its own share of the grid-point list."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from oracle_lib import Oracle
+    from test_green import _case
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29800 + os.getpid() % 90
+    ps = [ctx.Process(target=_green_worker, args=(r, 2, str(tmp_path), port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (tmp_path / "ref").mkdir()
+    o = Oracle(_case(tmp_path / "ref", ranks=(2, 1)), base_dir=tmp_path / "ref", nm=3)
+    assert [r[1] for r in res].count(True) == 1                       # exactly one owner
+    for r in res:
+        g = o.green(r[0])
+        assert r[2] == [g["isrc"], g["jsrc"], g["ksrc"]]
+        assert r[3] == g["ng"] and r[4] == g["gid"].tolist()
+    assert sum(r[3] for r in res) == 3
