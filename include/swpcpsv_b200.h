@@ -45,6 +45,13 @@ typedef struct {
     float reserved_f;
 } swpcpsv_grid;
 
+/* snap__setup (m_snap.f90:78-164): decimation, snapshot grid size, this rank's region is0..is1 x ks0..ks1 (1-based snapshot
+ * indices, :111-114), the three product switches xz_ps / xz_v / xz_u, and the output scaling */
+typedef struct {
+    int32_t idec, kdec, ntdec_s, nxs, nzs, is0, is1, ks0, ks1, sw_ps, sw_v, sw_u;
+    float M0, UC;
+} swpcpsv_snap_cfg;
+
 const char *swpcpsv_last_error(void);
 const char *swpcpsv_version(void);
 
@@ -90,7 +97,16 @@ int swpcpsv_comm_stress(swpcpsv_handle *h);              /* global__comm_stress 
 int swpcpsv_update_vel(swpcpsv_handle *h, int32_t it);
 int swpcpsv_comm_vel(swpcpsv_handle *h);                 /* global__comm_vel      m_global.f90:312 */
 int swpcpsv_wav_store(swpcpsv_handle *h, int32_t it);    /* wav__store            m_wav.f90:143-306 */
-int swpcpsv_step(swpcpsv_handle *h, int32_t it);         /* one iteration (without report / snap) */
+int swpcpsv_step(swpcpsv_handle *h, int32_t it);         /* one iteration (snap_step, wav_store, stress .. comm_vel; without report) */
+
+/* snapshots (m_snap.f90).  swpcpsv_snap_step = the device part of snap__write(it) (:435-650): displacement accumulation
+ * every step, ps / v slices when mod(it-1, ntdec_s) == 0.  swpcpsv_snap_fetch = mpi_reduce(SUM) of buf(nxs, nzs, 2) onto the
+ * I/O rank (product 0 ps, 1 v, 2 u; :395-417, :500-507): every rank calls it, `out` is filled on `root`.
+ * swpcpsv_reduce_sum does the same for a host array (the medium slices of newfile_xz, :167-269). */
+int swpcpsv_snap_setup(swpcpsv_handle *h, const swpcpsv_snap_cfg *cfg);
+int swpcpsv_snap_step(swpcpsv_handle *h, int32_t it);
+int swpcpsv_snap_fetch(swpcpsv_handle *h, int32_t product, int32_t root, float *out);
+int swpcpsv_reduce_sum(swpcpsv_handle *h, float *buf, int64_t n, int32_t root);
 int swpcpsv_run(swpcpsv_handle *h, int32_t it0, int32_t it1);
 int swpcpsv_sync(swpcpsv_handle *h);
 

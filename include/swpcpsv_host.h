@@ -6,8 +6,8 @@
  * /root/reference/src/swpc_psv.
  *
  * Scope of this build: vmodel_type uni | lhm and benchmark_mode; stf_format {xy,ll}{m0,mw}{ij,dc} and body forces; PML and
- * Cerjan; station products v / u / stress / strain in sac | csf | tar_st | tar_node containers.  pw_mode, snapshots
- * (m_snap.f90) and the grd / rmed / lgm / user models return an error.
+ * Cerjan; station products v / u / stress / strain in sac | csf | tar_st | tar_node containers; snapshots (m_snap.f90:
+ * xz_ps / xz_v / xz_u, netcdf or native).  pw_mode and the grd / rmed / lgm / user models return an error.
  */
 #ifndef SWPCPSV_HOST_H
 #define SWPCPSV_HOST_H
@@ -51,6 +51,10 @@ swpcpsv_handle *swpcpsv_host_handle(swpcpsv_host *h);
 int swpcpsv_host_run(swpcpsv_host *h, int32_t it0, int32_t it1, int32_t verbose, float *vm, int32_t nvm, int32_t *nrec);
 /* wav__write (m_wav.f90:308-420): <odir>/wav/<title>.psv.<stnm>.<cmp>.sac and the csf / tar containers */
 int swpcpsv_host_write_wav(swpcpsv_host *h, const char *odir, int32_t *nfiles);
+/* snapshots (m_snap.f90): create <odir>/<title>.psv.xz.<ps|v|u>.<nc|snp> on the I/O ranks (after attach_device / comm init and
+ * before the first swpcpsv_host_run, which then writes one record every ntdec_s steps); close flushes and closes. */
+int swpcpsv_host_snap_open(swpcpsv_host *h, const char *odir);
+int swpcpsv_host_snap_close(swpcpsv_host *h);
 /* report__setup banner (m_report.f90:52-100) to stderr; fails when the stability condition is violated */
 int swpcpsv_host_banner(swpcpsv_host *h);
 

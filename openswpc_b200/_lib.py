@@ -59,6 +59,7 @@ PSV_SYMBOLS = [
     "swpcpsv_comm_stress", "swpcpsv_update_vel", "swpcpsv_comm_vel", "swpcpsv_wav_store", "swpcpsv_step", "swpcpsv_run",
     "swpcpsv_sync", "swpcpsv_vmax", "swpcpsv_vmax_global", "swpcpsv_nccl_unique_id", "swpcpsv_comm_init", "swpcpsv_comm_local",
     "swpcpsv_timer_start", "swpcpsv_timer_stop", "swpcpsv_set_option", "swpcpsv_get_info",
+    "swpcpsv_snap_setup", "swpcpsv_snap_step", "swpcpsv_snap_fetch", "swpcpsv_reduce_sum",
 ]
 
 # every symbol include/swpc3d_b200.h declares
@@ -149,6 +150,10 @@ def load() -> C.CDLL:
     lib.swpcpsv_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     lib.swpcpsv_comm_local.argtypes = [C.POINTER(vp), i32, i32]
     lib.swpcpsv_timer_stop.argtypes = [vp, fp]
+    lib.swpcpsv_snap_setup.argtypes = [vp, vp]
+    lib.swpcpsv_snap_step.argtypes = [vp, i32]
+    lib.swpcpsv_snap_fetch.argtypes = [vp, i32, i32, fp]
+    lib.swpcpsv_reduce_sum.argtypes = [vp, fp, C.c_int64, i32]
     lib.swpcpsv_set_option.argtypes = [vp, cp, i32]
     lib.swpcpsv_get_info.argtypes = [vp, cp, dp]
     for s in PSV_SYMBOLS:

@@ -796,81 +796,6 @@ int swpc3d_host::setup(const IniFile &ini, int nm_, int myid_, int npx, int npy,
 // snapshots: m_snap.f90.  netCDF classic (CDF-1) files written by a small in-tree writer (no netCDF library in the
 // image): dimensions, variables, attributes and their order follow write_nc_header (:627-745), newfile_*_nc
 // (:475-845), wbuf_nc (:950-979), close_nc (:2191-2204) and output__put_maxval (:2295-2348).
-namespace {
-
-struct NcAtt { std::string name; int type; std::vector<unsigned char> val; int nelems; };
-struct NcVar {
-    std::string name; std::vector<int> dimids; std::vector<NcAtt> atts; int type = 5; bool rec = false;
-    std::vector<float> data; long long vsize = 0, begin = 0;
-};
-void be32(std::vector<unsigned char> &b, uint32_t v) { for (int q = 3; q >= 0; q--) b.push_back((unsigned char)(v >> (8 * q))); }
-void bef(std::vector<unsigned char> &b, float f) { uint32_t u; std::memcpy(&u, &f, 4); be32(b, u); }
-NcAtt att_text(const std::string &n, const std::string &v) { NcAtt a{n, 2, {}, (int)v.size()}; a.val.assign(v.begin(), v.end()); while (a.val.size() % 4) a.val.push_back(0); return a; }
-NcAtt att_int(const std::string &n, int v) { NcAtt a{n, 4, {}, 1}; be32(a.val, (uint32_t)v); return a; }
-NcAtt att_floats(const std::string &n, std::initializer_list<float> v) { NcAtt a{n, 5, {}, (int)v.size()}; for (float f : v) bef(a.val, f); return a; }
-
-class NcFile {
-  public:
-    std::vector<std::pair<std::string, int>> dims;   // length 0 = record dimension
-    std::vector<NcAtt> gatts;
-    std::vector<NcVar> vars;
-    int numrecs = 0;
-    FILE *fp = nullptr;
-    long long recsize = 0, rec_begin = 0;
-    ~NcFile() { if (fp) std::fclose(fp); }
-    int var_index(const std::string &n) const { for (size_t q = 0; q < vars.size(); q++) if (vars[q].name == n) return (int)q; return -1; }
-    NcAtt *find_att(NcVar &v, const std::string &n) { for (auto &a : v.atts) if (a.name == n) return &a; return nullptr; }
-    static void put_name(std::vector<unsigned char> &b, const std::string &n) { be32(b, (uint32_t)n.size()); for (char c : n) b.push_back((unsigned char)c); while (b.size() % 4) b.push_back(0); }
-    static void put_atts(std::vector<unsigned char> &b, const std::vector<NcAtt> &atts) {
-        if (atts.empty()) { be32(b, 0); be32(b, 0); return; }
-        be32(b, 0x0C); be32(b, (uint32_t)atts.size());
-        for (const NcAtt &a : atts) { put_name(b, a.name); be32(b, (uint32_t)a.type); be32(b, (uint32_t)a.nelems); b.insert(b.end(), a.val.begin(), a.val.end()); }
-    }
-    std::vector<unsigned char> header() const {
-        std::vector<unsigned char> b = {'C', 'D', 'F', 1};
-        be32(b, (uint32_t)numrecs);
-        be32(b, 0x0A); be32(b, (uint32_t)dims.size());
-        for (auto &d : dims) { put_name(b, d.first); be32(b, (uint32_t)d.second); }
-        put_atts(b, gatts);
-        be32(b, 0x0B); be32(b, (uint32_t)vars.size());
-        for (const NcVar &v : vars) {
-            put_name(b, v.name); be32(b, (uint32_t)v.dimids.size());
-            for (int d : v.dimids) be32(b, (uint32_t)d);
-            put_atts(b, v.atts); be32(b, (uint32_t)v.type); be32(b, (uint32_t)v.vsize); be32(b, (uint32_t)v.begin);
-        }
-        return b;
-    }
-    // lay out: fixed-size variables first (definition order), then the record section
-    bool create(const std::string &path) {
-        for (NcVar &v : vars) {
-            long long n = 1;
-            for (int d : v.dimids) if (dims[(size_t)d].second > 0) n *= dims[(size_t)d].second;
-            v.vsize = (n * 4 + 3) / 4 * 4;
-        }
-        const long long hsize = (long long)header().size();
-        long long off = hsize;
-        for (NcVar &v : vars) if (!v.rec) { v.begin = off; off += v.vsize; }
-        rec_begin = off; recsize = 0;
-        for (NcVar &v : vars) if (v.rec) { v.begin = off; off += v.vsize; recsize += v.vsize; }
-        fp = std::fopen(path.c_str(), "wb+");
-        if (!fp) return false;
-        flush_header();
-        for (NcVar &v : vars) if (!v.rec && !v.data.empty()) put_fixed(v);
-        return true;
-    }
-    void flush_header() { const auto b = header(); std::fseek(fp, 0, SEEK_SET); std::fwrite(b.data(), 1, b.size(), fp); std::fflush(fp); }
-    static void write_floats(FILE *f, const float *p, size_t n) { std::vector<unsigned char> b; b.reserve(4 * n); for (size_t q = 0; q < n; q++) bef(b, p[q]); std::fwrite(b.data(), 1, b.size(), f); }
-    void put_fixed(const NcVar &v) { std::fseek(fp, (long)v.begin, SEEK_SET); write_floats(fp, v.data.data(), v.data.size()); }
-    void put_record(int vidx, int rec, const float *p, size_t n) {
-        const NcVar &v = vars[(size_t)vidx];
-        std::fseek(fp, (long)(v.begin + (long long)rec * recsize), SEEK_SET);
-        write_floats(fp, p, n);
-        if (rec + 1 > numrecs) numrecs = rec + 1;
-    }
-};
-
-}   // namespace
-
 struct SnapProd {
     bool on = false; int sec = 0, typ = 0, n1 = 0, n2 = 0, nvar = 0, ionode = 0;
     std::string coordinate, snaptype, fname; std::vector<std::string> vname; std::string vunit;

@@ -30,6 +30,20 @@ struct swpcpsv_host {
     std::vector<float> srcprm, xst, zst, stlo, stla;
     std::vector<std::string> stnm;
     swpcpsv_handle *dev = nullptr;
+    // snapshots (m_snap.f90): products 0 ps (divergence, rotation), 1 v, 2 u over the decimated xz plane
+    struct Snap {
+        bool sw[3] = {false, false, false}, opened = false, native = true;
+        int idec = 1, kdec = 1, ntdec_s = 10, nxs = 0, nzs = 0, is0 = 0, is1 = -1, ks0 = 0, ks1 = -1, ionode[3] = {0, 0, 0};
+        std::vector<float> xsnp, zsnp, tmp;
+        NcFile *nc[3] = {nullptr, nullptr, nullptr};
+        FILE *snp[3] = {nullptr, nullptr, nullptr};
+        float vmin[3][2] = {}, vmax[3][2] = {};
+        ~Snap() { for (int q = 0; q < 3; q++) { delete nc[q]; if (snp[q]) std::fclose(snp[q]); } }
+    } snap;
+    void setup_snap(const IniFile &ini);
+    int snap_open(const std::string &dir);
+    int snap_write(int it);
+    int snap_close();
     std::vector<float> wav_all[4];
     double loop_seconds = 0;
 
@@ -438,9 +452,142 @@ int swpcpsv_host::setup(const IniFile &ini, int nm_, int myid_, int npx, int nt_
     if (setup_medium(ini)) return 1;
     if (setup_source(ini)) return 1;
     setup_absorb();
-    for (const char *key : {"xz_ps%sw", "xz_v%sw", "xz_u%sw"})   // snap__setup m_snap.f90:88-90
-        if (ini.get_l(key, false)) return hfail(std::string("swpc_psv snapshots (") + key + ") are outside the scope of this build");
+    setup_snap(ini);
     if (setup_wav(ini)) return 1;
+    return 0;
+}
+
+// ============================================================================================================
+// snapshots: snap__setup m_snap.f90:78-164 (files are created when a device is attached: swpcpsv_host_snap_open)
+static const char *PSV_SNAP_TYPE[3] = {"ps", "v2", "u2"}, *PSV_SNAP_TAG[3] = {"ps", "v", "u"};
+static const char *PSV_SNAP_VAR[3][2] = {{"divergence", "rotation"}, {"Vx", "Vz"}, {"Ux", "Uz"}}, *PSV_SNAP_UNIT[3] = {"1/s", "m/s", "m"};
+
+void swpcpsv_host::setup_snap(const IniFile &ini) {
+    Snap &S = snap;
+    S.sw[0] = ini.get_l("xz_ps%sw", false); S.sw[1] = ini.get_l("xz_v%sw", false); S.sw[2] = ini.get_l("xz_u%sw", false);
+    S.idec = ini.get_i("idec", 1); S.kdec = ini.get_i("kdec", 1); S.ntdec_s = ini.get_i("ntdec_s", 10);
+    S.native = ini.get("snp_format", "native") == "native";
+    S.nxs = (nx + (S.idec / 2)) / S.idec;
+    S.nzs = (nz + (S.kdec / 2)) / S.kdec;
+    S.xsnp.resize((size_t)S.nxs); S.zsnp.resize((size_t)S.nzs);
+    for (int i = 1; i <= S.nxs; i++) S.xsnp[(size_t)i - 1] = i2x(i * S.idec - (S.idec / 2), xbeg, (float)dx);
+    for (int k = 1; k <= S.nzs; k++) S.zsnp[(size_t)k - 1] = i2x(k * S.kdec - (S.kdec / 2), zbeg, (float)dz);
+    S.is0 = (int)std::ceil((float)(ibeg + S.idec / 2) / (float)S.idec);
+    S.is1 = (int)std::floor((float)(iend + S.idec / 2) / (float)S.idec);
+    S.ks0 = (int)std::ceil((float)(1 + S.kdec / 2) / (float)S.kdec);
+    S.ks1 = (int)std::floor((float)(nz + S.kdec / 2) / (float)S.kdec);
+    for (int q = 0; q < 3; q++) S.ionode[q] = (q + 1) % nproc_x;   // :117-119
+}
+
+// newfile_xz / newfile_xz_nc (:167-269) + write_snp_header (:272-315) / write_nc_header (:317-393)
+int swpcpsv_host::snap_open(const std::string &dir) {
+    Snap &S = snap;
+    if (!(S.sw[0] || S.sw[1] || S.sw[2]) || S.opened) return 0;
+    if (!dev) return hfail("swpcpsv_host_snap_open: no device attached");
+    make_dirs(dir);
+    const size_t np = (size_t)S.nxs * S.nzs;
+    for (int q = 0; q < 3; q++) {
+        if (!S.sw[q]) continue;
+        std::vector<std::vector<float>> med(3, std::vector<float>(np, 0.0f));
+        for (int i = S.is0; i <= S.is1; i++)
+            for (int k = S.ks0; k <= S.ks1; k++) {
+                const int ii = i * S.idec - S.idec / 2, kk = k * S.kdec - S.kdec / 2;
+                const size_t o = (size_t)(i - 1) + (size_t)S.nxs * (size_t)(k - 1), n = i2(kk, ii);
+                med[0][o] = rho[n]; med[1][o] = lam[n]; med[2][o] = mu[n];
+            }
+        for (int m = 0; m < 3; m++)
+            if (swpcpsv_reduce_sum(dev, med[(size_t)m].data(), (int64_t)np, S.ionode[q])) return hfail(std::string("device: ") + swpcpsv_last_error());
+        if (myid != S.ionode[q]) continue;
+        const std::string fname = dir + "/" + title + ".psv.xz." + PSV_SNAP_TAG[q] + (S.native ? ".snp" : ".nc");
+        if (S.native) {
+            FILE *f = S.snp[q] = std::fopen(fname.c_str(), "wb");
+            if (!f) return hfail("cannot create " + fname);
+            std::string ttl = title; ttl.resize(80, ' ');
+            auto wi = [&](int32_t v) { std::fwrite(&v, 4, 1, f); };
+            auto wf = [&](float v) { std::fwrite(&v, 4, 1, f); };
+            std::fwrite("STREAMIO", 1, 8, f); std::fwrite("SWPC_PSV", 1, 8, f); wi(6);
+            std::fwrite(ttl.data(), 1, 80, f); wi(exedate);
+            std::fwrite("xz", 1, 2, f); std::fwrite(PSV_SNAP_TYPE[q], 1, 2, f);
+            wi(S.nxs); wi(S.nzs); wf(S.xsnp[0]); wf(S.zsnp[0]);
+            wf(S.nxs > 1 ? S.xsnp[1] - S.xsnp[0] : 0.0f); wf(S.nzs > 1 ? S.zsnp[1] - S.zsnp[0] : 0.0f);
+            wf(dt * (float)S.ntdec_s); wi(na / S.idec); wi(na / S.kdec); wi(3); wi(2);
+            wf(clon); wf(clat); wf(phi); wf(0.0f); wf(0.0f); wf(0.0f);
+            for (int m = 0; m < 3; m++) std::fwrite(med[(size_t)m].data(), 4, np, f);
+            continue;
+        }
+        NcFile *nc = S.nc[q] = new NcFile();
+        nc->dims = {{"x", S.nxs}, {"z", S.nzs}, {"t", 0}};
+        auto mm = [](const std::vector<float> &v) { float lo = v[0], hi = v[0]; for (float f : v) { lo = std::min(lo, f); hi = std::max(hi, f); } return std::make_pair(lo, hi); };
+        NcVar vx; vx.name = "x"; vx.dimids = {0}; vx.data = S.xsnp;
+        NcVar vz; vz.name = "z"; vz.dimids = {1}; vz.data = S.zsnp;
+        NcVar vt; vt.name = "t"; vt.dimids = {2}; vt.rec = true;
+        vx.atts = {att_text("long_name", "x"), att_text("units", "km"), att_floats("actual_range", {S.xsnp.front(), S.xsnp.back()})};
+        vz.atts = {att_text("long_name", "z"), att_text("units", "km"), att_floats("actual_range", {S.zsnp.front(), S.zsnp.back()})};
+        vt.atts = {att_text("long_name", "t"), att_text("units", "s")};
+        nc->vars = {vx, vz, vt};
+        static const char *mname[3] = {"rho", "lambda", "mu"}, *munit[3] = {"10^3 kg/cm^3", "10^9 Pa", "10^9 Pa"};
+        for (int m = 0; m < 3; m++) {
+            NcVar v; v.name = mname[m]; v.dimids = {1, 0}; v.data = med[(size_t)m];
+            const auto r = mm(med[(size_t)m]);
+            v.atts = {att_text("long_name", mname[m]), att_text("units", munit[m]), att_floats("actual_range", {r.first, r.second})};
+            nc->vars.push_back(v);
+        }
+        for (int v = 0; v < 2; v++) {
+            NcVar sv; sv.name = PSV_SNAP_VAR[q][v]; sv.dimids = {2, 1, 0}; sv.rec = true;
+            sv.atts = {att_text("long_name", PSV_SNAP_VAR[q][v]), att_text("units", PSV_SNAP_UNIT[q]), att_floats("actual_range", {0.0f, 0.0f})};
+            nc->vars.push_back(sv);
+        }
+        nc->gatts = {att_text("generated_by", "SWPC"), att_text("title", title), att_int("exedate", exedate), att_int("hdrver", 6), att_text("codetype", "SWPC_PSV"),
+                     att_int("ns1", S.nxs), att_int("ns2", S.nzs), att_floats("beg1", {S.xsnp.front()}), att_floats("beg2", {S.zsnp.front()}),
+                     att_int("na1", na / S.idec), att_int("na2", na / S.kdec), att_floats("ds1", {S.idec * (float)dx}), att_floats("ds2", {S.kdec * (float)dz}),
+                     att_int("nmed", 3), att_int("nsnp", 2), att_text("coordinate", "xz"), att_text("datatype", PSV_SNAP_TYPE[q]),
+                     att_floats("dt", {dt * S.ntdec_s}), att_floats("evlo", {evlo}), att_floats("evla", {evla}), att_floats("evdp", {evdp}),
+                     att_floats("evx", {sx0}), att_floats("evy", {sy0}), att_floats("clon", {clon}), att_floats("clat", {clat}), att_floats("phi", {phi})};
+        if (!nc->create(fname)) return hfail("cannot create " + fname);
+    }
+    swpcpsv_snap_cfg c{};
+    c.idec = S.idec; c.kdec = S.kdec; c.ntdec_s = S.ntdec_s; c.nxs = S.nxs; c.nzs = S.nzs; c.is0 = S.is0; c.is1 = S.is1; c.ks0 = S.ks0; c.ks1 = S.ks1;
+    c.sw_ps = S.sw[0]; c.sw_v = S.sw[1]; c.sw_u = S.sw[2]; c.M0 = M0; c.UC = UC;
+    if (swpcpsv_snap_setup(dev, &c)) return hfail(std::string("device: ") + swpcpsv_last_error());
+    S.opened = true;
+    return 0;
+}
+
+// the host part of snap__write(it) at an output step (the device part runs inside swpcpsv_step): reduce + record write
+// (wbuf_nc :652-681; written at once instead of one cycle later -- same record index it0/ntdec_s+1, same time, same data)
+int swpcpsv_host::snap_write(int it) {
+    Snap &S = snap;
+    if (!S.opened || !(S.ntdec_s > 0 && (it - 1) % S.ntdec_s == 0)) return 0;
+    const size_t np = (size_t)S.nxs * S.nzs;
+    for (int q = 0; q < 3; q++) {
+        if (!S.sw[q]) continue;
+        S.tmp.assign(2 * np, 0.0f);
+        if (swpcpsv_snap_fetch(dev, q, S.ionode[q], S.tmp.data())) return hfail(std::string("device: ") + swpcpsv_last_error());
+        if (S.snp[q]) { std::fwrite(S.tmp.data(), 4, 2 * np, S.snp[q]); std::fflush(S.snp[q]); continue; }
+        NcFile *nc = S.nc[q];
+        if (!nc) continue;
+        const int rec = it / S.ntdec_s;
+        const float tval = it * dt;
+        nc->put_record(nc->var_index("t"), rec, &tval, 1);
+        for (int v = 0; v < 2; v++) {
+            const float *d = S.tmp.data() + np * (size_t)v;
+            const int vi = nc->var_index(PSV_SNAP_VAR[q][v]);
+            nc->put_record(vi, rec, d, np);
+            for (size_t n = 0; n < np; n++) { S.vmax[q][v] = std::max(S.vmax[q][v], d[n]); S.vmin[q][v] = std::min(S.vmin[q][v], d[n]); }
+            *nc->find_att(nc->vars[(size_t)vi], "actual_range") = att_floats("actual_range", {S.vmin[q][v], S.vmax[q][v]});
+        }
+        nc->flush_header();
+    }
+    return 0;
+}
+
+int swpcpsv_host::snap_close() {   // snap__closefiles :683-719
+    Snap &S = snap;
+    for (int q = 0; q < 3; q++) {
+        if (S.nc[q]) { S.nc[q]->flush_header(); delete S.nc[q]; S.nc[q] = nullptr; }
+        if (S.snp[q]) { std::fclose(S.snp[q]); S.snp[q] = nullptr; }
+    }
+    S.opened = false;
     return 0;
 }
 
@@ -617,7 +764,15 @@ int swpcpsv_host_run(swpcpsv_host *h, int32_t it0, int32_t it1, int32_t verbose,
                              (double)v[0], (double)v[1]);
             }
         }
-        if (swpcpsv_step(h->dev, it)) return hfail(std::string("device: ") + swpcpsv_last_error());
+        // snap__write(it) at the top of the iteration (main.f90:99): slices on the device, then -- on output steps -- the
+        // reduction onto the I/O rank and the record; the rest of the iteration follows (swpcpsv_step minus its snap_step)
+        if (h->snap.opened) {
+            if (swpcpsv_snap_step(h->dev, it) || swpcpsv_wav_store(h->dev, it)) return hfail(std::string("device: ") + swpcpsv_last_error());
+            if (h->snap_write(it)) return 1;
+            if (swpcpsv_update_stress(h->dev) || swpcpsv_stressglut(h->dev, it) || swpcpsv_comm_stress(h->dev) || swpcpsv_update_vel(h->dev, it) ||
+                swpcpsv_comm_vel(h->dev))
+                return hfail(std::string("device: ") + swpcpsv_last_error());
+        } else if (swpcpsv_step(h->dev, it)) return hfail(std::string("device: ") + swpcpsv_last_error());
     }
     if (swpcpsv_sync(h->dev)) return hfail(std::string("device: ") + swpcpsv_last_error());
     h->loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -629,6 +784,14 @@ int swpcpsv_host_run(swpcpsv_host *h, int32_t it0, int32_t it1, int32_t verbose,
 // src/shared/m_sac.f90:314-449
 static void put_chars(char *dst, const std::string &s, int n) {
     for (int q = 0; q < n; q++) dst[q] = q < (int)s.size() ? s[q] : ' ';
+}
+int swpcpsv_host_snap_open(swpcpsv_host *h, const char *odir) {
+    if (!h) return hfail("null handle");
+    return h->snap_open(odir ? odir : h->odir.c_str());
+}
+int swpcpsv_host_snap_close(swpcpsv_host *h) {
+    if (!h) return hfail("null handle");
+    return h->snap_close();
 }
 int swpcpsv_host_write_wav(swpcpsv_host *h, const char *odir, int32_t *nfiles) {
     if (!h) return hfail("null handle");

@@ -103,6 +103,12 @@ struct swpcpsv_handle {
     int *st_ik = nullptr;
     float *wav[4] = {}, *wav_acc = nullptr;
     float M0 = 1.f, UC = 1e-12f;
+    // snapshots (m_snap.f90)
+    swpcpsv_snap_cfg snap{};
+    bool snap_on = false;
+    float *snap_buf[3] = {nullptr, nullptr, nullptr};   // ps, v, u: (2, nzs, nxs) over the whole snapshot grid
+    float *snap_tmp = nullptr;
+    size_t snap_tmp_n = 0;
     unsigned int *vmax_d = nullptr;
     // halo: 0 = +x (ip), 1 = -x (im)
     void *sbuf[2] = {}, *rbuf[2] = {};
@@ -250,6 +256,8 @@ extern "C" int swpcpsv_destroy(swpcpsv_handle *h) {
     for (int a = 0; a < 4; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); cudaFree(h->wav[a]); }
     cudaFree(h->src_ik); cudaFree(h->src_mo); cudaFree(h->src_m3); cudaFree(h->src_prm);
     cudaFree(h->st_ik); cudaFree(h->wav_acc); cudaFree(h->vmax_d);
+    for (int q = 0; q < 3; q++) cudaFree(h->snap_buf[q]);
+    cudaFree(h->snap_tmp);
     for (int f = 0; f < 2; f++) { cudaFree(h->sbuf[f]); cudaFree(h->rbuf[f]); }
     for (int w = 0; w < 2; w++) for (int b = 0; b < 2; b++) for (cudaEvent_t ev : h->kev[w][b]) cudaEventDestroy(ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -711,7 +719,84 @@ extern "C" int swpcpsv_comm_local(swpcpsv_handle **hs, int32_t n, int32_t which)
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// snapshots, m_snap.f90
+extern "C" int swpcpsv_snap_setup(swpcpsv_handle *h, const swpcpsv_snap_cfg *cfg) {
+    if (!h || !cfg) return fail("null argument");
+    CK(cudaSetDevice(h->dev));
+    for (int q = 0; q < 3; q++) { cudaFree(h->snap_buf[q]); h->snap_buf[q] = nullptr; }
+    h->snap = *cfg;
+    h->snap_on = cfg->sw_ps || cfg->sw_v || cfg->sw_u;
+    if (!h->snap_on) return 0;
+    if (cfg->idec < 1 || cfg->kdec < 1 || cfg->ntdec_s < 1 || cfg->nxs < 1 || cfg->nzs < 1) return fail("swpcpsv_snap_setup: bad decimation / size");
+    if (cfg->is1 >= cfg->is0 && (cfg->is0 * cfg->idec - cfg->idec / 2 < h->g.ibeg || cfg->is1 * cfg->idec - cfg->idec / 2 > h->g.iend || cfg->is1 > cfg->nxs))
+        return fail("swpcpsv_snap_setup: is0..is1 outside of the owned columns (m_snap.f90:111-112)");
+    if (cfg->ks1 >= cfg->ks0 && (cfg->ks0 * cfg->kdec - cfg->kdec / 2 < 1 || cfg->ks1 * cfg->kdec - cfg->kdec / 2 > h->g.nz || cfg->ks1 > cfg->nzs))
+        return fail("swpcpsv_snap_setup: ks0..ks1 outside of 1..nz (m_snap.f90:113-114)");
+    const int sw[3] = {cfg->sw_ps, cfg->sw_v, cfg->sw_u};
+    const size_t n = (size_t)2 * cfg->nxs * cfg->nzs * sizeof(float);
+    for (int q = 0; q < 3; q++)
+        if (sw[q]) { CK(cudaMalloc(&h->snap_buf[q], n)); CK(cudaMemsetAsync(h->snap_buf[q], 0, n, h->st)); }
+    return 0;
+}
+
+extern "C" int swpcpsv_snap_step(swpcpsv_handle *h, int32_t it) {
+    if (ready(h)) return 1;
+    if (!h->snap_on) return 0;
+    const swpcpsv_snap_cfg &c = h->snap;
+    const bool sample = (it - 1) % c.ntdec_s == 0;
+    if (!(c.sw_u || sample) || c.is1 < c.is0 || c.ks1 < c.ks0) return 0;
+    PsvSnap g{};
+    g.idec = c.idec; g.kdec = c.kdec; g.nxs = c.nxs; g.nzs = c.nzs; g.is0 = c.is0; g.is1 = c.is1; g.ks0 = c.ks0; g.ks1 = c.ks1; g.ibeg = h->g.ibeg;
+    g.do_ps = c.sw_ps && sample; g.do_v = c.sw_v && sample; g.do_u = c.sw_u;
+    g.UC = c.UC; g.M0 = c.M0;
+    if (h->fb == 8) { g.r20x = 1.0 / h->g.dx; g.r20z = 1.0 / h->g.dz; }
+    else { g.r20x = (double)(1.0f / (float)h->g.dx); g.r20z = (double)(1.0f / (float)h->g.dz); }
+    g.buf_ps = h->snap_buf[0]; g.buf_v = h->snap_buf[1]; g.buf_u = h->snap_buf[2];
+    dim3 blk(128), grd((unsigned)((c.ks1 - c.ks0 + 1 + 127) / 128), (unsigned)(c.is1 - c.is0 + 1));
+    if (h->fb == 8) psv_snap_kernel<double><<<grd, blk, 0, h->st>>>(make_params<double>(h), g);
+    else psv_snap_kernel<float><<<grd, blk, 0, h->st>>>(make_params<float>(h), g);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// mpi_reduce(SUM) onto the I/O rank (m_snap.f90:395-417, :500-507): every rank calls; `out` is filled on `root` only
+static int snap_reduce_to_host(swpcpsv_handle *h, const float *dev_src, size_t n, int root, float *out) {
+    const float *src = dev_src;
+    if (h->comm) {
+        if (h->snap_tmp_n < n) {
+            cudaFree(h->snap_tmp);
+            CK(cudaMalloc(&h->snap_tmp, n * sizeof(float)));
+            h->snap_tmp_n = n;
+        }
+        NK(g_nc.AllReduce(dev_src, h->snap_tmp, n, ncclFloat, ncclSum, h->comm, h->st));
+        src = h->snap_tmp;
+    }
+    if ((!h->comm || h->g.myid == root) && out) CK(cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return 0;
+}
+extern "C" int swpcpsv_snap_fetch(swpcpsv_handle *h, int32_t product, int32_t root, float *out) {
+    if (!h) return fail("null handle");
+    if (product < 0 || product > 2 || !h->snap_buf[product]) return fail("swpcpsv_snap_fetch: product not enabled (swpcpsv_snap_setup)");
+    CK(cudaSetDevice(h->dev));
+    return snap_reduce_to_host(h, h->snap_buf[product], (size_t)2 * h->snap.nxs * h->snap.nzs, root, out);
+}
+extern "C" int swpcpsv_reduce_sum(swpcpsv_handle *h, float *buf, int64_t n, int32_t root) {
+    if (!h || !buf || n < 0) return fail("swpcpsv_reduce_sum: bad argument");
+    if (!h->comm || n == 0) return 0;
+    CK(cudaSetDevice(h->dev));
+    float *tmp = nullptr;
+    CK(cudaMalloc(&tmp, (size_t)n * sizeof(float)));
+    CK(cudaMemcpyAsync(tmp, buf, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    const int rc = snap_reduce_to_host(h, tmp, (size_t)n, root, buf);
+    cudaFree(tmp);
+    return rc;
+}
+
 extern "C" int swpcpsv_step(swpcpsv_handle *h, int32_t it) {   // main.f90:99-111
+    if (swpcpsv_snap_step(h, it)) return 1;
     if (swpcpsv_wav_store(h, it)) return 1;
     if (swpcpsv_update_stress(h)) return 1;
     if (swpcpsv_stressglut(h, it)) return 1;

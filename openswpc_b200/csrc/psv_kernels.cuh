@@ -287,6 +287,49 @@ __global__ void __launch_bounds__(256, 3) psv_sweep(const __grid_constant__ PsvP
     }
 }
 
+// snap__write, m_snap.f90:435-650: decimated xz slices.  One thread per snapshot node (ii, kk) of this rank's region;
+// ps = masked divergence / rotation (:468-494), v = Vx, Vz (:550-551), u = running displacement, accumulated every step
+// (:609-610).  Buffers are the reference's buf(nxs, nzs, 2) over the WHOLE snapshot grid (zero outside the rank's region,
+// summed onto the I/O rank afterwards).
+struct PsvSnap {
+    int idec, kdec, nxs, nzs, is0, is1, ks0, ks1, ibeg;
+    int do_ps, do_v, do_u;          // ps / v only on sampled steps, u every step
+    float UC, M0;
+    double r20x, r20z;              // 1/dx, 1/dz in the field kind
+    float *buf_ps, *buf_v, *buf_u;
+};
+
+template <typename F>
+__global__ void psv_snap_kernel(const __grid_constant__ PsvParams<F> p, const PsvSnap g) {
+    const int kk = g.ks0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int ii = g.is0 + blockIdx.y;
+    if (kk > g.ks1 || ii > g.is1) return;
+    const int k = kk * g.kdec - g.kdec / 2, i = ii * g.idec - g.idec / 2;
+    const long long SI = p.NZP;
+    const long long n = (long long)(k + KOFF - 1) + SI * (i - g.ibeg + HALO);
+    const long long o = (long long)(ii - 1) + (long long)g.nxs * (kk - 1), n2 = (long long)g.nxs * g.nzs;
+    const F *Vx = p.Vx, *Vz = p.Vz;
+    if (g.do_ps) {
+        const F r20x = (F)g.r20x, r20z = (F)g.r20z;
+        float div = (float)((Vx[n] - Vx[n - SI]) * r20x + (Vz[n] - Vz[n - 1]) * r20z);
+        float rot = (float)((Vx[n + 1] - Vx[n]) * r20z - (Vz[n + SI] - Vz[n]) * r20x);
+        const float mu_xz = mu_harm(p.mu[n], p.mu[n + 1], p.mu[n + SI], p.mu[n + 1 + SI]);
+        const float lam0 = p.lam[n];
+        div = div * lam0 / (fabsf(lam0) + FLT_EPS_);
+        rot = rot * mu_xz / fabsf(mu_xz + FLT_EPS_);
+        g.buf_ps[o] = div * g.UC * g.M0 * 1e-3f;
+        g.buf_ps[n2 + o] = rot * g.UC * g.M0 * 1e-3f;
+    }
+    if (g.do_v) {
+        g.buf_v[o] = (float)(Vx[n] * g.UC * g.M0);
+        g.buf_v[n2 + o] = (float)(Vz[n] * g.UC * g.M0);
+    }
+    if (g.do_u) {
+        g.buf_u[o] = (float)(g.buf_u[o] + Vx[n] * g.UC * g.M0 * p.dt);
+        g.buf_u[n2 + o] = (float)(g.buf_u[n2 + o] + Vz[n] * g.UC * g.M0 * p.dt);
+    }
+}
+
 struct PsvSrc {
     int nsrc;
     const int *ik;          // 2*nsrc: memory column mi and k

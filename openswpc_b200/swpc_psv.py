@@ -27,7 +27,7 @@ _F64 = {"mo", "m3"}
 HOST_SYMBOLS = ["swpcpsv_host_create", "swpcpsv_host_create_from_text", "swpcpsv_host_destroy", "swpcpsv_host_last_error", "swpcpsv_host_get_int",
                 "swpcpsv_host_get_double", "swpcpsv_host_set_minmax", "swpcpsv_host_set_exedate", "swpcpsv_host_get_array",
                 "swpcpsv_host_station_name", "swpcpsv_host_attach_device", "swpcpsv_host_handle", "swpcpsv_host_run", "swpcpsv_host_write_wav",
-                "swpcpsv_host_banner"]
+                "swpcpsv_host_banner", "swpcpsv_host_snap_open", "swpcpsv_host_snap_close"]
 
 _bound = False
 
@@ -53,6 +53,8 @@ def _bind(lib):
     lib.swpcpsv_host_run.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
     lib.swpcpsv_host_write_wav.argtypes = [vp, cp, C.POINTER(i32)]
     lib.swpcpsv_host_banner.argtypes = [vp]
+    lib.swpcpsv_host_snap_open.argtypes = [vp, cp]
+    lib.swpcpsv_host_snap_close.argtypes = [vp]
     _bound = True
 
 
@@ -141,6 +143,13 @@ class SwpcPsv:
         n = C.c_int32()
         self._ck(self.lib.swpcpsv_host_run(self.h, it0, it1, int(verbose), vm.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return vm[:n.value]
+
+    def snap_open(self, odir=None):
+        """Create <title>.psv.xz.<ps|v|u>.<nc|snp> (m_snap.f90 newfile_xz[_nc]); call after attach_device, before run()."""
+        self._ck(self.lib.swpcpsv_host_snap_open(self.h, None if odir is None else os.fspath(odir).encode()))
+
+    def snap_close(self):
+        self._ck(self.lib.swpcpsv_host_snap_close(self.h))
 
     def write_wav(self, odir=None) -> int:
         n = C.c_int32()

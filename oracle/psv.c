@@ -125,10 +125,24 @@ typedef struct {
     ora_mp *sbuf_ip, *sbuf_im, *rbuf_ip, *rbuf_im;
 } psv_rank;
 
+/* snapshots, m_snap.f90: three products over the decimated xz plane, each with two components */
+typedef struct {
+    int sw[3];                        /* xz_ps, xz_v, xz_u */
+    int idec, kdec, ntdec_s, nxs, nzs;
+    char snp_format[8];
+    float *xsnp, *zsnp;
+    float *medium;                    /* (3, nzs, nxs): rho lambda mu, summed over ranks */
+    float *buf_u;                     /* (2, nzs, nxs): running displacement, m_snap.f90:588-612 */
+    int nrec[3], cap[3];
+    int *it0[3];
+    float *rec[3];                    /* records (nrec, 2, nzs, nxs) of the netCDF files / native streams */
+} psv_snap;
+
 struct psv_sim {
     psv_cfg cfg;
     int nranks;
     psv_rank *r;
+    psv_snap snap;
 };
 
 static inline size_t IX(const psv_rank *r, int k, int i) { return (size_t)(k - r->kbeg_m) + (size_t)r->nzm * (size_t)(i - r->ibeg_m); }
@@ -732,6 +746,103 @@ static int wav_setup(psv_sim *s, const ora_ini *ini, const char *base) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------------------------ */
+/* snap__setup m_snap.f90:78-164 (+ the medium slices of newfile_xz[_nc] :167-269)                                  */
+static void snap_region(const psv_snap *sn, const psv_rank *r, int *is0, int *is1, int *ks0, int *ks1) {
+    *is0 = (int)ceilf((float)(r->ibeg + sn->idec / 2) / (float)sn->idec);
+    *is1 = (int)floorf((float)(r->iend + sn->idec / 2) / (float)sn->idec);
+    *ks0 = (int)ceilf((float)(r->kbeg + sn->kdec / 2) / (float)sn->kdec);
+    *ks1 = (int)floorf((float)(r->kend + sn->kdec / 2) / (float)sn->kdec);
+}
+static void snap_setup(psv_sim *s, const ora_ini *ini) {
+    psv_snap *sn = &s->snap;
+    const psv_cfg *c = &s->cfg;
+    ora_readini_l(ini, "xz_ps%sw", &sn->sw[0], 0);
+    ora_readini_l(ini, "xz_v%sw", &sn->sw[1], 0);
+    ora_readini_l(ini, "xz_u%sw", &sn->sw[2], 0);
+    ora_readini_i(ini, "idec", &sn->idec, 1);
+    ora_readini_i(ini, "kdec", &sn->kdec, 1);
+    ora_readini_i(ini, "ntdec_s", &sn->ntdec_s, 10);
+    char tmp[ORA_STRLEN];
+    ora_readini_c(ini, "snp_format", tmp, "native");
+    snprintf(sn->snp_format, sizeof(sn->snp_format), "%.7s", tmp);
+    sn->nxs = (c->nx + (sn->idec / 2)) / sn->idec;
+    sn->nzs = (c->nz + (sn->kdec / 2)) / sn->kdec;
+    sn->xsnp = (float *)xcalloc((size_t)sn->nxs, sizeof(float));
+    sn->zsnp = (float *)xcalloc((size_t)sn->nzs, sizeof(float));
+    for (int i = 1; i <= sn->nxs; i++) sn->xsnp[i - 1] = ora_i2x(i * sn->idec - (sn->idec / 2), c->xbeg, (float)c->dx);
+    for (int k = 1; k <= sn->nzs; k++) sn->zsnp[k - 1] = ora_i2x(k * sn->kdec - (sn->kdec / 2), c->zbeg, (float)c->dz);
+    const size_t n2 = (size_t)sn->nxs * sn->nzs;
+    sn->medium = (float *)xcalloc(3 * n2, sizeof(float));
+    sn->buf_u = (float *)xcalloc(2 * n2, sizeof(float));
+    for (int q = 0; q < s->nranks; q++) {
+        const psv_rank *r = &s->r[q];
+        int is0, is1, ks0, ks1;
+        snap_region(sn, r, &is0, &is1, &ks0, &ks1);
+        for (int i = is0; i <= is1; i++)
+            for (int k = ks0; k <= ks1; k++) {
+                const int ii = i * sn->idec - sn->idec / 2, kk = k * sn->kdec - sn->kdec / 2;
+                const size_t o = (size_t)(i - 1) + (size_t)sn->nxs * (size_t)(k - 1);
+                sn->medium[o] += r->rho[IX(r, kk, ii)];
+                sn->medium[n2 + o] += r->lam[IX(r, kk, ii)];
+                sn->medium[2 * n2 + o] += r->mu[IX(r, kk, ii)];
+            }
+    }
+}
+
+/* snap__write m_snap.f90:419-650, called at the top of the iteration (main.f90:99); the mpi_reduce(SUM) onto the I/O
+ * rank is the disjoint fill below.  A record is kept for every it with mod(it-1, ntdec_s) == 0. */
+static void snap_write(psv_sim *s, int it) {
+    psv_snap *sn = &s->snap;
+    const psv_cfg *c = &s->cfg;
+    if (!(sn->sw[0] || sn->sw[1] || sn->sw[2])) return;
+    const size_t n2 = (size_t)sn->nxs * sn->nzs;
+    const int sample = (it - 1) % sn->ntdec_s == 0;
+    const ora_mp r20x = (ora_mp)1.0 / (ora_mp)c->dx, r20z = (ora_mp)1.0 / (ora_mp)c->dz;
+    float *out[3] = {NULL, NULL, NULL};
+    for (int p = 0; p < 3; p++) {
+        if (!sn->sw[p] || !sample) continue;
+        if (sn->nrec[p] == sn->cap[p]) {
+            sn->cap[p] = sn->cap[p] ? 2 * sn->cap[p] : 16;
+            sn->rec[p] = (float *)realloc(sn->rec[p], sizeof(float) * 2 * n2 * (size_t)sn->cap[p]);
+            sn->it0[p] = (int *)realloc(sn->it0[p], sizeof(int) * (size_t)sn->cap[p]);
+        }
+        out[p] = sn->rec[p] + 2 * n2 * (size_t)sn->nrec[p];
+        memset(out[p], 0, sizeof(float) * 2 * n2);
+        sn->it0[p][sn->nrec[p]++] = it;
+    }
+    for (int q = 0; q < s->nranks; q++) {
+        const psv_rank *r = &s->r[q];
+        int is0, is1, ks0, ks1;
+        snap_region(sn, r, &is0, &is1, &ks0, &ks1);
+        for (int ii = is0; ii <= is1; ii++)
+            for (int kk = ks0; kk <= ks1; kk++) {
+                const int k = kk * sn->kdec - sn->kdec / 2, i = ii * sn->idec - sn->idec / 2;
+                const size_t o = (size_t)(ii - 1) + (size_t)sn->nxs * (size_t)(kk - 1);
+                if (out[0]) { /* :468-494 */
+                    float div = (float)((r->Vx[IX(r, k, i)] - r->Vx[IX(r, k, i - 1)]) * r20x + (r->Vz[IX(r, k, i)] - r->Vz[IX(r, k - 1, i)]) * r20z);
+                    float rot = (float)((r->Vx[IX(r, k + 1, i)] - r->Vx[IX(r, k, i)]) * r20z - (r->Vz[IX(r, k, i + 1)] - r->Vz[IX(r, k, i)]) * r20x);
+                    const float nnn = r->mu[IX(r, k, i)], pnn = r->mu[IX(r, k + 1, i)], npn = r->mu[IX(r, k, i + 1)], ppn = r->mu[IX(r, k + 1, i + 1)];
+                    const float mu_xz = 4 * nnn * pnn * npn * ppn / (nnn * pnn * npn + nnn * pnn * ppn + nnn * npn * ppn + pnn * npn * ppn + FLT_EPS);
+                    const float lam0 = r->lam[IX(r, k, i)];
+                    div = div * lam0 / (fabsf(lam0) + FLT_EPS);
+                    rot = rot * mu_xz / fabsf(mu_xz + FLT_EPS);
+                    out[0][o] = div * c->UC * c->M0 * 1e-3f;   /* buf = buf * UC * M0 * 1e-3 */
+                    out[0][n2 + o] = rot * c->UC * c->M0 * 1e-3f;
+                }
+                if (out[1]) { /* :550-551 */
+                    out[1][o] = (float)(r->Vx[IX(r, k, i)] * c->UC * c->M0);
+                    out[1][n2 + o] = (float)(r->Vz[IX(r, k, i)] * c->UC * c->M0);
+                }
+                if (sn->sw[2]) { /* every step, :609-610 */
+                    sn->buf_u[o] = (float)(sn->buf_u[o] + r->Vx[IX(r, k, i)] * c->UC * c->M0 * c->dt);
+                    sn->buf_u[n2 + o] = (float)(sn->buf_u[n2 + o] + r->Vz[IX(r, k, i)] * c->UC * c->M0 * c->dt);
+                }
+            }
+    }
+    if (out[2]) memcpy(out[2], sn->buf_u, sizeof(float) * 2 * n2);
+}
+
 static psv_sim *create_from_ini(ora_ini *ini, const char *base, int nm, int npx, int nt) {
     psv_sim *s = (psv_sim *)xcalloc(1, sizeof(psv_sim));
     psv_cfg *c = &s->cfg;
@@ -755,6 +866,7 @@ static psv_sim *create_from_ini(ora_ini *ini, const char *base, int nm, int npx,
     kernel_setup(s);
     if (source_setup(s, ini, base) || absorb_setup(s) || wav_setup(s, ini, base)) { psv_destroy(s); return NULL; }
     ora_readini_i(ini, "ntdec_r", &c->ntdec_r, 10);
+    snap_setup(s, ini);
     return s;
 }
 psv_sim *psv_create(const char *inf_path, const char *base, int nm, int npx, int nt) {
@@ -784,6 +896,8 @@ void psv_destroy(psv_sim *s) {
         for (int a = 0; a < 4; a++) free(r->wav[a]);
     }
     free(s->r);
+    free(s->snap.xsnp); free(s->snap.zsnp); free(s->snap.medium); free(s->snap.buf_u);
+    for (int p = 0; p < 3; p++) { free(s->snap.rec[p]); free(s->snap.it0[p]); }
     free(s);
 }
 void psv_set_exedate(psv_sim *s, int exedate, int tz_minutes) { s->cfg.exedate = exedate; s->cfg.tz_minutes = tz_minutes; }
@@ -1119,6 +1233,7 @@ void psv_vmax(psv_sim *s, float out[2]) {
 void psv_step(psv_sim *s, int it) {
     const psv_cfg *c = &s->cfg;
     const int pml = !strcmp(c->abc_type, "pml");
+    snap_write(s, it);
     wav_store(s, it);
     for (int q = 0; q < s->nranks; q++) {
         psv_rank *r = &s->r[q];
@@ -1143,6 +1258,34 @@ int psv_run(psv_sim *s, int it0, int it1, float *vm, int nvm) {
         psv_step(s, it);
     }
     return rec;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
+/* snapshot accessors                                                                                              */
+int psv_snap_info(const psv_sim *s, int *info) {   /* idec kdec ntdec_s nxs nzs sw_ps sw_v sw_u */
+    const psv_snap *sn = &s->snap;
+    info[0] = sn->idec; info[1] = sn->kdec; info[2] = sn->ntdec_s; info[3] = sn->nxs; info[4] = sn->nzs;
+    for (int p = 0; p < 3; p++) info[5 + p] = sn->sw[p];
+    return 0;
+}
+int psv_snap_coords(const psv_sim *s, float *x, float *z) {
+    memcpy(x, s->snap.xsnp, sizeof(float) * (size_t)s->snap.nxs);
+    memcpy(z, s->snap.zsnp, sizeof(float) * (size_t)s->snap.nzs);
+    return 0;
+}
+int psv_snap_nrec(const psv_sim *s, int p) { return (p >= 0 && p < 3) ? s->snap.nrec[p] : -1; }
+int psv_snap_rec(const psv_sim *s, int p, int rec, float *out, int *it0) {   /* out (2, nzs, nxs) */
+    const psv_snap *sn = &s->snap;
+    if (p < 0 || p > 2 || rec < 0 || rec >= sn->nrec[p]) return -1;
+    const size_t n = 2 * (size_t)sn->nxs * sn->nzs;
+    memcpy(out, sn->rec[p] + n * (size_t)rec, sizeof(float) * n);
+    *it0 = sn->it0[p][rec];
+    return 0;
+}
+int psv_snap_medium(const psv_sim *s, int which, float *out) {   /* 0 rho 1 lambda 2 mu: (nzs, nxs) */
+    const size_t n2 = (size_t)s->snap.nxs * s->snap.nzs;
+    memcpy(out, s->snap.medium + n2 * (size_t)which, sizeof(float) * n2);
+    return 0;
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */

@@ -49,6 +49,12 @@ int psv_get_profile(const psv_sim *s, int q, const char *name, float *out);  /* 
 int psv_get_sources(const psv_sim *s, int q, int *ik, double *val);          /* ik (2,nsrc); val (6,nsrc): mo mxx mzz mxz t0 tr  (bf: fx fz in mxx mzz) */
 int psv_get_stations(const psv_sim *s, int q, int *ik, char *names9);
 int psv_get_wav(const psv_sim *s, int q, int prod, float *out);              /* prod 0 v 1 u (ntw,2,nst); 2 stress 3 strain (ntw,3,nst) */
+/* snapshots (m_snap.f90): info = idec kdec ntdec_s nxs nzs sw_ps sw_v sw_u; products 0 ps (div, rot) 1 v 2 u; records (2, nzs, nxs) */
+int psv_snap_info(const psv_sim *s, int *info);
+int psv_snap_coords(const psv_sim *s, float *x, float *z);
+int psv_snap_nrec(const psv_sim *s, int p);
+int psv_snap_rec(const psv_sim *s, int p, int rec, float *out, int *it0);
+int psv_snap_medium(const psv_sim *s, int which, float *out);
 int psv_write_sac(psv_sim *s, const char *odir);                             /* wav_format = sac; returns the number of files */
 
 #endif

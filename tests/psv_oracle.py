@@ -63,6 +63,12 @@ def _bind(lib):
     lib.psv_get_wav.argtypes = [vp, ci, ci, fp]
     lib.psv_write_sac.restype = ci
     lib.psv_write_sac.argtypes = [vp, cc]
+    lib.psv_snap_info.argtypes = [vp, C.POINTER(ci)]
+    lib.psv_snap_coords.argtypes = [vp, fp, fp]
+    lib.psv_snap_nrec.argtypes = [vp, ci]
+    lib.psv_snap_nrec.restype = ci
+    lib.psv_snap_rec.argtypes = [vp, ci, ci, fp, C.POINTER(ci)]
+    lib.psv_snap_medium.argtypes = [vp, ci, fp]
     lib._psv_bound = True
     return lib
 
@@ -186,6 +192,37 @@ class PsvOracle:
             r = self.rank(q)
             f = self.field(q, name)
             out[r["ibeg"] - 1:r["iend"], :] = f[3:3 + r["iend"] - r["ibeg"] + 1, 3:3 + nz]
+        return out
+
+    # ---- snapshots (m_snap.f90)
+    def snap_info(self):
+        v = (C.c_int * 8)()
+        self.lib.psv_snap_info(self.h, v)
+        return dict(zip(["idec", "kdec", "ntdec_s", "nxs", "nzs", "sw_ps", "sw_v", "sw_u"], list(v)))
+
+    def snap_coords(self):
+        i = self.snap_info()
+        x, z = np.zeros(i["nxs"], dtype=np.float32), np.zeros(i["nzs"], dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        self.lib.psv_snap_coords(self.h, x.ctypes.data_as(fp), z.ctypes.data_as(fp))
+        return x, z
+
+    def snap_records(self, p):
+        """(nrec, 2, nzs, nxs) float32 and the list of it0 of product p (0 ps, 1 v, 2 u)"""
+        i = self.snap_info()
+        n = self.lib.psv_snap_nrec(self.h, p)
+        out = np.zeros((n, 2, i["nzs"], i["nxs"]), dtype=np.float32)
+        its = []
+        for r in range(n):
+            it0 = C.c_int()
+            self.lib.psv_snap_rec(self.h, p, r, out[r].ctypes.data_as(C.POINTER(C.c_float)), C.byref(it0))
+            its.append(it0.value)
+        return out, its
+
+    def snap_medium(self, which):
+        i = self.snap_info()
+        out = np.zeros((i["nzs"], i["nxs"]), dtype=np.float32)
+        self.lib.psv_snap_medium(self.h, which, out.ctypes.data_as(C.POINTER(C.c_float)))
         return out
 
     def write_sac(self, odir):

@@ -175,3 +175,88 @@ def test_host_driver_end_to_end_files_identical(tmp_path, wav_format):
             assert names[0] == "psvtest.psv.st02.Vx.sac" and len(names) == 10     # m_wav.f90:428: title.psv.stnm.cmp.sac
             body = t.extractfile(names[1]).read()
         assert np.array_equal(np.frombuffer(body[632:], dtype="<f4"), o.wav(0, 0)[1, 1])
+
+
+PSV_SNAP_TAGS = ("ps", "v", "u")
+PSV_SNAP_VARS = (("divergence", "rotation"), ("Vx", "Vz"), ("Ux", "Uz"))
+
+
+@pytest.mark.parametrize("dec", [(2, 2, 5), (1, 1, 4), (3, 4, 7)])
+def test_snapshot_files_netcdf(tmp_path, dec):
+    """m_snap.f90 of swpc_psv: the three xz products written by the product's driver from the device slices, read back with an
+    independent netCDF reader and compared record by record, bit for bit, with the oracle."""
+    from scipy.io import netcdf_file
+
+    from openswpc_b200.swpc_psv import SwpcPsv
+
+    nt = 43
+    write_psv_files(tmp_path)
+    inf = tmp_path / "input.inf"
+    extra = f" snp_format = 'netcdf'\n xz_ps%sw = .true.\n xz_v%sw = .true.\n xz_u%sw = .true.\n idec = {dec[0]}\n kdec = {dec[1]}\n ntdec_s = {dec[2]}"
+    inf.write_text(psv_case_text(nt=nt, extra=extra))
+    o = PsvOracle(inf, base_dir=tmp_path, nm=3)
+    o.run(1, nt)
+    run = SwpcPsv(inf, base_dir=tmp_path, nm=3)
+    run.attach_device(0)
+    run.snap_open(tmp_path / "gpu")
+    run.run(1, nt)
+    run.snap_close()
+    info = o.snap_info()
+    x, z = o.snap_coords()
+    title = o.cfg("title")
+    for p in range(3):
+        path = tmp_path / "gpu" / f"{title}.psv.xz.{PSV_SNAP_TAGS[p]}.nc"
+        assert path.exists(), path.name
+        recs, its = o.snap_records(p)
+        with netcdf_file(str(path), "r", mmap=False) as f:
+            assert f.dimensions == {"x": info["nxs"], "z": info["nzs"], "t": None}
+            assert f.generated_by == b"SWPC" and f.codetype == b"SWPC_PSV" and f.hdrver == 6 and f.coordinate == b"xz"
+            assert f.datatype == [b"ps", b"v2", b"u2"][p] and f.nsnp == 2 and f.nmed == 3 and f.ns1 == info["nxs"] and f.ns2 == info["nzs"]
+            np.testing.assert_array_equal(f.variables["x"][:], x)
+            np.testing.assert_array_equal(f.variables["z"][:], z)
+            for m, name in enumerate(["rho", "lambda", "mu"]):
+                np.testing.assert_array_equal(f.variables[name][:], o.snap_medium(m), err_msg=name)
+            assert len(its) == f.variables["t"].shape[0] > 1
+            np.testing.assert_array_equal(f.variables["t"][:], np.array([np.float32(it) * np.float32(run["dt"]) for it in its], dtype=np.float32))
+            for v, name in enumerate(PSV_SNAP_VARS[p]):
+                var = f.variables[name]
+                assert var.dimensions == ("t", "z", "x")
+                np.testing.assert_array_equal(var[:], recs[:, v], err_msg=f"{path.name}:{name}")
+                np.testing.assert_array_equal(var.actual_range, [min(recs[:, v].min(), 0), max(recs[:, v].max(), 0)])
+        assert np.abs(recs).max() > 0, path.name
+
+
+def test_snapshot_native_stream(tmp_path):
+    """snp_format = 'native': write_snp_header (m_snap.f90:272-315), the three medium slices, then two arrays per output step."""
+    import struct
+
+    from openswpc_b200.swpc_psv import SwpcPsv
+
+    nt = 21
+    write_psv_files(tmp_path)
+    inf = tmp_path / "input.inf"
+    inf.write_text(psv_case_text(nt=nt, extra=" xz_v%sw = .true.\n idec = 2\n kdec = 2\n ntdec_s = 5"))
+    o = PsvOracle(inf, base_dir=tmp_path, nm=3)
+    o.run(1, nt)
+    run = SwpcPsv(inf, base_dir=tmp_path, nm=3)
+    run.set_exedate(1_700_000_000, 540)
+    run.attach_device(0)
+    run.snap_open(tmp_path / "gpu")
+    run.run(1, nt)
+    run.snap_close()
+    info = o.snap_info()
+    x, z = o.snap_coords()
+    recs, its = o.snap_records(1)
+    raw = (tmp_path / "gpu" / f"{o.cfg('title')}.psv.xz.v.snp").read_bytes()
+    title = o.cfg("title").ljust(80).encode()
+    hdr = (b"STREAMIO" + b"SWPC_PSV" + struct.pack("<i", 6) + title + struct.pack("<i", 1_700_000_000) + b"xz" + b"v2" +
+           struct.pack("<ii", info["nxs"], info["nzs"]) + struct.pack("<ffff", x[0], z[0], x[1] - x[0], z[1] - z[0]) +
+           struct.pack("<f", np.float32(run["dt"]) * np.float32(5)) + struct.pack("<iiii", o.cfg("na") // 2, o.cfg("na") // 2, 3, 2) +
+           struct.pack("<ffffff", np.float32(139.7604), np.float32(35.7182), 0.0, 0.0, 0.0, 0.0))   # clon clat phi defaults (m_global.f90:140-142), 3 x dum
+    assert raw[:len(hdr)] == hdr
+    body = np.frombuffer(raw[len(hdr):], dtype=np.float32)
+    np2 = info["nxs"] * info["nzs"]
+    assert body.size == np2 * (3 + 2 * len(its))
+    for m in range(3):
+        np.testing.assert_array_equal(body[m * np2:(m + 1) * np2].reshape(info["nzs"], info["nxs"]), o.snap_medium(m))
+    np.testing.assert_array_equal(body[3 * np2:].reshape(len(its), 2, info["nzs"], info["nxs"]), recs)

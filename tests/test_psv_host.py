@@ -83,7 +83,7 @@ def test_scope_errors_are_explicit(tmp_path):
     from openswpc_b200.swpc_psv import SwpcPsv, SwpcPsvError
 
     write_psv_files(tmp_path)
-    for extra, msg in ((" pw_mode = .true.", "pw_mode"), (" vmodel_type = 'grd'", "vmodel_type"), (" xz_v%sw = .true.", "snapshots")):
+    for extra, msg in ((" pw_mode = .true.", "pw_mode"), (" vmodel_type = 'grd'", "vmodel_type")):
         inf = tmp_path / "input.inf"
         inf.write_text(psv_case_text(nt=4, extra=extra) if "vmodel" not in extra else psv_case_text(nt=4, vmodel="grd"))
         with pytest.raises(SwpcPsvError, match=msg):
