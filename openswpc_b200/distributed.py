@@ -79,6 +79,23 @@ def attach_nccl(run) -> None:
     _lib.check(lib.swpc3d_comm_init(run.handle, box[0], world, rank))
 
 
+def attach_nccl_psv(run) -> None:
+    """The same for a `SwpcPsv` run (swpcpsv_nccl_unique_id / swpcpsv_comm_init; 1-D decomposition along x)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    lib = _lib.load()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(128)
+        _lib.check_psv(lib.swpcpsv_nccl_unique_id(buf))
+        box[0] = buf.raw
+    dist.broadcast_object_list(box, src=0)
+    _lib.check_psv(lib.swpcpsv_comm_init(run.handle, box[0], world, rank))
+
+
 def layout_for(world: int) -> tuple[int, int]:
     """x-y decomposition used by the benchmark: 1x1, 2x1, 4x1, 4x2."""
     return {1: (1, 1), 2: (2, 1), 4: (4, 1), 8: (4, 2)}.get(world, (world, 1))

@@ -144,6 +144,13 @@ class SwpcPsv:
         self._ck(self.lib.swpcpsv_host_run(self.h, it0, it1, int(verbose), vm.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return vm[:n.value]
 
+    def download_fields(self) -> dict:
+        """Vx Vz Sxx Szz Sxz over the memory box, (nxm, nzm), from the attached device."""
+        nxm, nzm = self["iend"] - self["ibeg"] + 7, self["nz"] + 6
+        out = {n: np.zeros((nxm, nzm), dtype=self.field_dtype) for n in ("Vx", "Vz", "Sxx", "Szz", "Sxz")}
+        _lib.check_psv(self.lib.swpcpsv_download_fields(self.handle, *[out[n].ctypes.data_as(C.c_void_p) for n in ("Vx", "Vz", "Sxx", "Szz", "Sxz")]))
+        return out
+
     def snap_open(self, odir=None):
         """Create <title>.psv.xz.<ps|v|u>.<nc|snp> (m_snap.f90 newfile_xz[_nc]); call after attach_device, before run()."""
         self._ck(self.lib.swpcpsv_host_snap_open(self.h, None if odir is None else os.fspath(odir).encode()))

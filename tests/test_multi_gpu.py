@@ -27,3 +27,17 @@ def test_nccl_halo_exchange_matches_oracle(tmp_path, layout):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count(" ok:") == n
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_psv_nccl(tmp_path, n):
+    """swpc_psv over NCCL: column exchange (m_global.f90:296-420 of swpc_psv), max-amplitude reduce and the snapshot
+    sum-reduce onto the I/O ranks, against the oracle's emulated ranks."""
+    if _ngpu() < n:
+        pytest.skip(f"needs {n} GPUs")
+    port = 29300 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "mgpu_psv_worker.py"), str(tmp_path), "40"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    assert p.stdout.count(" psv ok:") == n
