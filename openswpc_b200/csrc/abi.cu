@@ -160,6 +160,7 @@ struct swpc3d_handle {
     bool vtma_ok = false;
     int variant = 1;
     int use_ring = 1, ring_jlen = 32, ring_pf = 2;   // vel_ring: register-pipelined interior velocity sweep
+    int flat_bottom = 1;                             // flat thread numbering for the bottom absorber slab (Box3::flat)
     // boundary-first overlap of the halo exchange (swpc3d_step): the two outermost owned planes towards every neighbour are
     // swept first, then pack / NCCL / unpack run on `cs` while the core of the subdomain is swept on `st`
     cudaStream_t cs = nullptr;
@@ -594,6 +595,11 @@ static int launch_direct_box(swpc3d_handle *h, const KParams<F> &p, const Box3 &
     const int jlen = std::max(1, h->jlen);
     dim3 grd((unsigned)((b.k1 - b.k0 + 1 + h->tk - 1) / h->tk), (unsigned)((b.li1 - b.li0 + 1 + h->ti - 1) / h->ti),
              (unsigned)((b.lj1 - b.lj0 + 1 + jlen - 1) / jlen));
+    if (b.flat) {   // threads numbered over the (k, i) cells of the box
+        const long long cells = (long long)(b.k1 - b.k0 + 1) * (b.li1 - b.li0 + 1), per = (long long)h->tk * h->ti;
+        grd.x = (unsigned)((cells + per - 1) / per);
+        grd.y = 1;
+    }
     switch (h->nm) {
     case 0: sweep_direct<F, 0, STRESS><<<grd, blk, 0, st>>>(p, b, jlen, h->pf); break;
     case 1: sweep_direct<F, 1, STRESS><<<grd, blk, 0, st>>>(p, b, jlen, h->pf); break;
@@ -712,9 +718,11 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
     // complement of the TMA box inside the owned box: two j slabs, two i slabs, one k slab (absorber cells only: the TMA
     // tiles already did every interior cell, also in the partial last k-tile).  All six launches touch disjoint cells and
     // only read V, so the shell boxes run on side streams next to the interior kernel.
+    Box3 bottom{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1, 0};
+    if (h->flat_bottom) { bottom.k0 = h->g.kend_k + 1; bottom.skip_interior = 0; bottom.flat = 1; }
     const Box3 boxes[5] = {Box3{1, h->g.nz, rg.li0, rg.li1, rg.lj0, t.lj0 - 1, 0}, Box3{1, h->g.nz, rg.li0, rg.li1, t.lj1 + 1, rg.lj1, 0},
                            Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0},
-                           Box3{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1}};
+                           bottom};
     if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
     stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
     h->launches++;
@@ -748,7 +756,7 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         const Box3 in{1, gg.kend_k, ki0, ki1, kj0, kj1, 0};
         const Box3 sh[5] = {Box3{1, gg.nz, rg.li0, rg.li1, rg.lj0, in.lj0 - 1, 0}, Box3{1, gg.nz, rg.li0, rg.li1, in.lj1 + 1, rg.lj1, 0},
                             Box3{1, gg.nz, rg.li0, in.li0 - 1, in.lj0, in.lj1, 0}, Box3{1, gg.nz, in.li1 + 1, rg.li1, in.lj0, in.lj1, 0},
-                            Box3{gg.kend_k + 1, gg.nz, in.li0, in.li1, in.lj0, in.lj1, 0}};
+                            Box3{gg.kend_k + 1, gg.nz, in.li0, in.li1, in.lj0, in.lj1, 0, h->flat_bottom}};
         const int jlen = std::max(1, h->ring_jlen);
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
         dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
@@ -1494,6 +1502,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "zero_outer_halo")) h->zero_outer = value != 0;
     else if (!strcmp(key, "tma")) h->use_tma = value;
     else if (!strcmp(key, "vel_ring")) h->use_ring = value;
+    else if (!strcmp(key, "flat_bottom")) h->flat_bottom = value != 0;
     else if (!strcmp(key, "overlap")) h->overlap = value != 0;
     else if (!strcmp(key, "split_test")) h->split_test = value != 0;
     else if (!strcmp(key, "ring_jlen")) { if (value < 1) return fail("ring_jlen must be >= 1"); h->ring_jlen = value; }

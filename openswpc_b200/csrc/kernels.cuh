@@ -446,12 +446,23 @@ __device__ __forceinline__ void prefetch_cell(const KParams<F> &p, long long n, 
     }
 }
 
-struct Box3 { int k0, k1, li0, li1, lj0, lj1; int skip_interior; };   // inclusive: k 1-based, li / lj local 0-based; skip_interior: absorber cells only
+// inclusive: k 1-based, li / lj local 0-based; skip_interior: absorber cells only; flat: threads are numbered over the
+// (k, i) cells of the box, k fastest, instead of one warp per 32 consecutive k -- for boxes that are thin in k (the
+// bottom absorber slab: 20 cells per column) every lane then has a cell and a warp spans one and a half columns
+struct Box3 { int k0, k1, li0, li1, lj0, lj1; int skip_interior; int flat; };
 
 template <typename F, int NM, bool STRESS>
 __global__ void __launch_bounds__(256, SWPC_MINB) sweep_direct(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
-    const int k = b.k0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int li = b.li0 + blockIdx.y * blockDim.y + threadIdx.y;
+    int k, li;
+    if (b.flat) {
+        const int nk = b.k1 - b.k0 + 1;
+        const long long t = (long long)blockIdx.x * (blockDim.x * blockDim.y) + threadIdx.y * blockDim.x + threadIdx.x;
+        k = b.k0 + (int)(t % nk);
+        li = b.li0 + (int)(t / nk);
+    } else {
+        k = b.k0 + blockIdx.x * blockDim.x + threadIdx.x;
+        li = b.li0 + blockIdx.y * blockDim.y + threadIdx.y;
+    }
     if (k > b.k1 || li > b.li1) return;
     const int mi = li + HALO;
     const int ljs = b.lj0 + blockIdx.z * jlen;
