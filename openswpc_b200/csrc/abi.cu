@@ -720,8 +720,9 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
     // only read V, so the shell boxes run on side streams next to the interior kernel.
     Box3 bottom{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1, 0};
     if (h->flat_bottom) { bottom.k0 = h->g.kend_k + 1; bottom.skip_interior = 0; bottom.flat = 1; }
+    // (the two i slabs are 20-odd columns wide, not a multiple of the block's 8: flat numbering there too)
     const Box3 boxes[5] = {Box3{1, h->g.nz, rg.li0, rg.li1, rg.lj0, t.lj0 - 1, 0}, Box3{1, h->g.nz, rg.li0, rg.li1, t.lj1 + 1, rg.lj1, 0},
-                           Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0},
+                           Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0, h->flat_bottom}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0, h->flat_bottom},
                            bottom};
     if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
     stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
@@ -755,7 +756,7 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         const swpc3d_grid &gg = h->g;
         const Box3 in{1, gg.kend_k, ki0, ki1, kj0, kj1, 0};
         const Box3 sh[5] = {Box3{1, gg.nz, rg.li0, rg.li1, rg.lj0, in.lj0 - 1, 0}, Box3{1, gg.nz, rg.li0, rg.li1, in.lj1 + 1, rg.lj1, 0},
-                            Box3{1, gg.nz, rg.li0, in.li0 - 1, in.lj0, in.lj1, 0}, Box3{1, gg.nz, in.li1 + 1, rg.li1, in.lj0, in.lj1, 0},
+                            Box3{1, gg.nz, rg.li0, in.li0 - 1, in.lj0, in.lj1, 0, h->flat_bottom}, Box3{1, gg.nz, in.li1 + 1, rg.li1, in.lj0, in.lj1, 0, h->flat_bottom},
                             Box3{gg.kend_k + 1, gg.nz, in.li0, in.li1, in.lj0, in.lj1, 0, h->flat_bottom}};
         const int jlen = std::max(1, h->ring_jlen);
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
