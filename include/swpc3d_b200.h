@@ -122,6 +122,9 @@ int swpc3d_wav_store(swpc3d_handle *h, int32_t it);    /* wav__store (velocity) 
 /* one whole iteration of main.f90:119-139 (green_store, wav_store, stress, glut, comm, vel, bodyforce, green_source, comm);
  * with neighbours the exchange runs boundary-first on a second stream beside the core sweeps (option "overlap", default 1) */
 int swpc3d_step(swpc3d_handle *h, int32_t it);
+/* the part of swpc3d_step after the sampling calls (main.f90:126-138: stress .. comm_vel, overlapped like swpc3d_step), for
+ * hosts that put their own snap__write between wav__store and the sweeps */
+int swpc3d_advance(swpc3d_handle *h, int32_t it);
 /* it = it0..it1 without returning to the host in between */
 int swpc3d_run(swpc3d_handle *h, int32_t it0, int32_t it1);
 int swpc3d_sync(swpc3d_handle *h);

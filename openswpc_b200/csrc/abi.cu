@@ -1454,6 +1454,11 @@ extern "C" int swpc3d_step(swpc3d_handle *h, int32_t it) {
     // main.f90:119-139
     if (swpc3d_green_store(h, it)) return 1;
     if (swpc3d_wav_store(h, it)) return 1;
+    return swpc3d_advance(h, it);
+}
+
+// main.f90:126-138: everything of iteration `it` after the sampling calls (green__store, wav__store, snap__write)
+extern "C" int swpc3d_advance(swpc3d_handle *h, int32_t it) {
     // (green__source writes V cells next to the subdomain edge between the sweep and the exchange: exposed order then)
     if (((h->overlap && has_neighbour(h) && h->comm) || h->split_test) && !h->g_is_src) {
         if (ready(h)) return 1;

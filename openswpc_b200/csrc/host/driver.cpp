@@ -1323,10 +1323,10 @@ int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, f
         }
         if (h->snap && h->snap->any && h->snap->opened) {   // main.f90:123-138 with snap__write between wav__store and the sweeps
 #define DS(call) if (call) return hfail(std::string("device: ") + swpc3d_last_error());
+            DS(swpc3d_green_store(h->dev, it));
             DS(swpc3d_wav_store(h->dev, it));
             if (h->snap_write(it)) return 1;
-            DS(swpc3d_update_stress(h->dev)); DS(swpc3d_stressglut(h->dev, it)); DS(swpc3d_comm_stress(h->dev));
-            DS(swpc3d_update_vel(h->dev)); DS(swpc3d_bodyforce(h->dev, it)); DS(swpc3d_comm_vel(h->dev));
+            DS(swpc3d_advance(h->dev, it));
 #undef DS
         } else if (swpc3d_step(h->dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
     }

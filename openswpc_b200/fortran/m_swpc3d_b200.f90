@@ -250,6 +250,11 @@ module m_swpc3d_b200
             real(c_float), value :: fx1, fy1, fz1, trise, tbeg
             character(kind=c_char), intent(in) :: stftype(*)
         end function
+        integer(c_int) function swpc3d_advance(h, it) bind(c, name='swpc3d_advance')   !! main.f90:126-138 (stress .. comm_vel)
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it
+        end function
         integer(c_int) function swpc3d_green_store(h, it) bind(c, name='swpc3d_green_store')
             import :: c_int, c_int32_t, c_ptr
             type(c_ptr), value :: h
