@@ -7,7 +7,7 @@
  *
  * Scope of this build: vmodel_type uni | lhm and benchmark_mode; stf_format {xy,ll}{m0,mw}{ij,dc} and body forces; PML and
  * Cerjan; station products v / u / stress / strain in sac | csf | tar_st | tar_node containers; snapshots (m_snap.f90:
- * xz_ps / xz_v / xz_u, netcdf or native).  pw_mode and the grd / rmed / lgm / user models return an error.
+ * xz_ps / xz_v / xz_u, netcdf or native); plane-wave mode (pw_mode).  The grd / rmed / lgm / user models return an error.
  */
 #ifndef SWPCPSV_HOST_H
 #define SWPCPSV_HOST_H

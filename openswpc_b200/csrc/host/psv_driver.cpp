@@ -54,6 +54,8 @@ struct swpcpsv_host {
     int setup_medium(const IniFile &ini);
     void surface_detection();
     int setup_source(const IniFile &ini);
+    int setup_planewave(const IniFile &ini);
+    std::vector<double> pw_init[5];   // plane-wave initial fields Vx Vz Sxx Szz Sxz over the memory box
     void setup_absorb();
     int setup_wav(const IniFile &ini);
 };
@@ -270,9 +272,63 @@ int swpcpsv_host::setup_medium(const IniFile &ini) {   // m_medium.f90:36-178
     return 0;
 }
 
+// pw_setup, m_source.f90:656-785: plane P / SV wave as the initial condition of the five fields over the memory box;
+// pw_strike and pw_rake are read and then forced to 90 degrees (:684-686)
+int swpcpsv_host::setup_planewave(const IniFile &ini) {
+    const float pw_ztop = ini.get_s("pw_ztop", 1e30f);
+    if (!(pw_ztop < zend)) return hfail("assert: pw_ztop < zend (m_source.f90:672)");
+    const float pw_zlen = ini.get_s("pw_zlen", -1.0f);
+    if (!(pw_zlen > 0.0f)) return hfail("assert: pw_zlen > 0 (m_source.f90:675)");
+    const std::string ps = ini.get("pw_ps", "");
+    const bool is_p = ps == "p" || ps == "P", is_s = ps == "s" || ps == "S";
+    if (!(is_p || is_s)) return hfail("assert: pw_ps must be 'p' or 's' (m_source.f90:678)");
+    const float strike = deg2rad_s(90.0f), dip = deg2rad_s(ini.get_s("pw_dip", 0.0f)), rake = deg2rad_s(90.0f);
+    stftype = ini.get("stftype", "kupper");
+    const float sd = std::sin(dip), cd = std::cos(dip), sf = std::sin(strike), cf = std::cos(strike), sl = std::sin(rake), cl = std::cos(rake);
+    const float c2d = std::cos(2 * dip);
+    const size_t nc = (size_t)nzm * nxm;
+    for (auto &f : pw_init) f.assign(nc, 0.0);
+    auto speed = [&](size_t n) { return is_p ? std::sqrt((lam[n] + 2 * mu[n]) / rho[n]) : std::sqrt(mu[n] / rho[n]); };
+    for (int i = ibeg_m; i <= iend_m; i++)
+        for (int k = kbeg_m; k <= kend_m; k++) {
+            const size_t n = i2(k, i);
+            const float la0 = lam[n], mu0 = mu[n], v = speed(n);
+            if (v < EPS_SP) continue;
+            const float x0 = (float)(xbeg + (i - 0.5f) * dx), z0 = (float)(zbeg + (k - 0.5f) * dz - pw_ztop);
+            const float x1 = (float)(x0 + dx / 2.0f), z1 = (float)(z0 + dz / 2.0f);
+            const float stf_ii = momentrate(sd * sf * x0 + cd * z0, stftype, 0.0f, pw_zlen);
+            const float stf_vx = momentrate(sd * sf * x1 + cd * z0 + dt / 2.0f * v, stftype, 0.0f, pw_zlen);
+            const float stf_vz = momentrate(sd * sf * x0 + cd * z1 + dt / 2.0f * v, stftype, 0.0f, pw_zlen);
+            const float stf_xz = momentrate(sd * sf * x1 + cd * z1, stftype, 0.0f, pw_zlen);
+            float vx, vz, sxx, szz, sxz;
+            if (is_p) {
+                vx = -sd * sf * stf_vx; vz = -cd * stf_vz;
+                sxx = -(la0 + 2 * mu0 * sd * sd * sf * sf) * stf_ii / v;
+                szz = -(la0 + 2 * mu0 * cd * cd) * stf_ii / v;
+                sxz = -2 * mu0 * sd * cd * sf * stf_xz / v;
+            } else {
+                vx = (cl * cf + sl * cd * sf) * stf_vx; vz = -sl * sd * stf_vz;
+                sxx = 2 * mu0 * sd * sf * (cl * cf + sl * cd * sf) * stf_ii / v;
+                szz = -2 * mu0 * cd * sl * sd * stf_ii / v;
+                sxz = mu0 * (cl * cd * cf + sl * c2d * sf) * stf_xz / v;
+            }
+            pw_init[0][n] = vx; pw_init[1][n] = vz; pw_init[2][n] = sxx; pw_init[3][n] = szz; pw_init[4][n] = sxz;
+        }
+    // wavelength condition :764-783: the velocity at the model's centre column, MPI_MAX over the ranks.  The models of this
+    // host (uni, lhm) are laterally uniform, so every rank evaluates it on a column of its own
+    const int kc = x2i(pw_ztop, zbeg, (float)dz);
+    fcut = speed(i2(kc, ibeg)) / pw_zlen;
+    fmax = fcut * 2.0f;
+    return 0;
+}
+
 int swpcpsv_host::setup_source(const IniFile &ini) {   // m_source.f90:41-258
     pw_mode = ini.get_l("pw_mode", false);
-    if (pw_mode && !benchmark_mode) return hfail("swpc_psv pw_mode is outside the scope of this build");
+    if (pw_mode && !benchmark_mode) {   // :68-76: no regular source grid, fictitious scalar moment for the output scaling
+        if (setup_planewave(ini)) return 1;
+        M0 = 1.0f / UC;
+        return 0;
+    }
     bf_mode = ini.get_l("bf_mode", false);
     fn_stf = ini.get("fn_stf", "");
     stftype = ini.get("stftype", "kupper");
@@ -678,6 +734,9 @@ int swpcpsv_host_get_array(swpcpsv_host *h, const char *name, void *out, int64_t
     if (s == "ts") return put(std::vector<float>(h->ts, h->ts + h->nm), out, cap, n);
     for (int p = 0; p < 4; p++)
         if (s == std::string("wav") + char('0' + p)) return put(h->wav_all[p], out, cap, n);
+    static const char *init[5] = {"init_Vx", "init_Vz", "init_Sxx", "init_Szz", "init_Sxz"};   // plane-wave initial condition (pw_mode)
+    for (int q = 0; q < 5; q++)
+        if (s == init[q]) return put(h->pw_init[q], out, cap, n);
     return hfail("unknown array " + s);
 }
 int swpcpsv_host_station_name(swpcpsv_host *h, int32_t i, char *buf9) {
@@ -712,6 +771,16 @@ int swpcpsv_host_attach_device(swpcpsv_host *h, int32_t device) {   // main.f90:
         }
         DV(swpcpsv_set_sources(h->dev, nsrc, a.data(), b.data(), h->mo.data(), m[0].data(), m[1].data(), m[2].data(), h->srcprm.data(), h->stftype.c_str(),
                                h->bf_mode ? 1 : 0, h->tbeg));
+    }
+    if (h->pw_mode && !h->pw_init[0].empty()) {   // `!$acc enter data copyin(Vx..Sxz)` with the plane-wave initial condition
+        const void *f[5];
+        std::vector<float> f32[5];
+        for (int q = 0; q < 5; q++) {
+            if (h->field_bytes == 4) { f32[q].assign(h->pw_init[q].begin(), h->pw_init[q].end()); f[q] = f32[q].data(); }
+            else f[q] = h->pw_init[q].data();
+        }
+        DV(swpcpsv_upload_fields(h->dev, f[0], f[1], f[2], f[3], f[4]));
+        DV(swpcpsv_set_option(h->dev, "pw_mode", 1));
     }
     const int nst = (int)(h->st_ik.size() / 2);
     if (nst > 0 && (h->sw[0] || h->sw[1] || h->sw[2] || h->sw[3])) {

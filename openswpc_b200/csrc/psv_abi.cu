@@ -103,6 +103,7 @@ struct swpcpsv_handle {
     int *st_ik = nullptr;
     float *wav[4] = {}, *wav_acc = nullptr;
     float M0 = 1.f, UC = 1e-12f;
+    bool pw_mode = false;   // plane-wave mode: edge extrapolation ahead of the PML updates
     // snapshots (m_snap.f90)
     swpcpsv_snap_cfg snap{};
     bool snap_on = false;
@@ -518,9 +519,31 @@ static int launch_sweep(swpcpsv_handle *h, int phase) {
     }
 }
 
+// plane-wave mode + PML: absorb_p__update_stress extrapolates the velocities, absorb_p__update_vel the stresses, into
+// column 0 / nx+1 on the outer ranks ahead of the update (the interior kernel never reads those columns)
+static int pw_edges(swpcpsv_handle *h, bool stress_fields) {
+    if (!h->pw_mode || h->g.abc_type != SWPCPSV_ABC_PML) return 0;
+    const int dstL = h->g.myid == 0 ? HALO - 1 : -1, dstR = h->g.myid == h->g.nproc_x - 1 ? HALO + h->nxp : -1;
+    if (dstL < 0 && dstR < 0) return 0;
+    dim3 blk(128), grd((unsigned)((h->g.nz + 127) / 128), 2);
+    if (h->fb == 8) {
+        const PsvParams<double> p = make_params<double>(h);
+        if (stress_fields) psv_pw_edge_kernel<double><<<grd, blk, 0, h->st>>>(p.Sxx, p.Szz, p.Sxz, h->g.nz, h->NZP, dstL, dstR);
+        else psv_pw_edge_kernel<double><<<grd, blk, 0, h->st>>>(p.Vx, p.Vz, (double *)nullptr, h->g.nz, h->NZP, dstL, dstR);
+    } else {
+        const PsvParams<float> p = make_params<float>(h);
+        if (stress_fields) psv_pw_edge_kernel<float><<<grd, blk, 0, h->st>>>(p.Sxx, p.Szz, p.Sxz, h->g.nz, h->NZP, dstL, dstR);
+        else psv_pw_edge_kernel<float><<<grd, blk, 0, h->st>>>(p.Vx, p.Vz, (float *)nullptr, h->g.nz, h->NZP, dstL, dstR);
+    }
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int swpcpsv_update_stress(swpcpsv_handle *h) {
     if (ready(h)) return 1;
     if (ktime(h, 0, 0)) return 1;
+    if (pw_edges(h, false)) return 1;
     if (h->fb == 8 ? launch_sweep<double, true>(h, PSV_FUSED) : launch_sweep<float, true>(h, PSV_FUSED)) return 1;
     return ktime(h, 0, 1);
 }
@@ -549,6 +572,7 @@ extern "C" int swpcpsv_stressglut(swpcpsv_handle *h, int32_t it) {
 extern "C" int swpcpsv_update_vel(swpcpsv_handle *h, int32_t it) {
     if (ready(h)) return 1;
     if (ktime(h, 1, 0)) return 1;
+    if (pw_edges(h, true)) return 1;
     if (!h->bf_mode || h->nsrc <= 0) {
         if (h->fb == 8 ? launch_sweep<double, false>(h, PSV_FUSED) : launch_sweep<float, false>(h, PSV_FUSED)) return 1;
     } else {   // main.f90:108-110: update_vel -> bodyforce -> absorb_vel
@@ -831,6 +855,7 @@ extern "C" int swpcpsv_set_option(swpcpsv_handle *h, const char *key, int32_t va
     if (!strcmp(key, "tk")) { if (value < 32 || value > 256 || value % 32) return fail("tk must be a multiple of 32 in 32..256"); h->tk = value; }
     else if (!strcmp(key, "ilen")) { if (value < 1) return fail("ilen must be >= 1"); h->ilen = value; }
     else if (!strcmp(key, "pf")) { if (value < 0 || value > 8) return fail("pf must be 0..8"); h->pf = value; }
+    else if (!strcmp(key, "pw_mode")) h->pw_mode = value != 0;
     else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; }
     else return fail(std::string("unknown option ") + key);
     return 0;

@@ -330,6 +330,22 @@ __global__ void psv_snap_kernel(const __grid_constant__ PsvParams<F> p, const Ps
     }
 }
 
+// Plane-wave mode: horizontal zero-derivative boundary (m_absorb_p.f90:114-155 / :287-326): linear extrapolation into the
+// first column outside the model on the outer ranks, k = 1..nz.  dst / s1 / s2 are memory columns; side < 0 = off.
+template <typename F>
+__global__ void psv_pw_edge_kernel(F *f0, F *f1, F *f2, int nz, int NZP, int dstL, int dstR) {
+    const int k = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > nz) return;
+    const int side = blockIdx.y;
+    const int dst = side == 0 ? dstL : dstR;
+    if (dst < 0) return;
+    const int s1 = side == 0 ? dst + 1 : dst - 1, s2 = side == 0 ? dst + 2 : dst - 2;
+    const long long kk = k + KOFF - 1, d = kk + (long long)NZP * dst, a = kk + (long long)NZP * s1, b = kk + (long long)NZP * s2;
+    f0[d] = 2 * f0[a] - f0[b];
+    f1[d] = 2 * f1[a] - f1[b];
+    if (f2) f2[d] = 2 * f2[a] - f2[b];
+}
+
 struct PsvSrc {
     int nsrc;
     const int *ik;          // 2*nsrc: memory column mi and k

@@ -21,7 +21,7 @@ _DOUBLES = {"dx", "dz", "dt", "xbeg", "zbeg", "tbeg", "vmin", "vmax", "vmin_loca
             "loop_seconds", "evlo", "evla", "evdp"}
 _F32 = {"rho", "lam", "mu", "taup", "taus", "gxc", "gxe", "gzc", "gze", "gx_c", "gx_b", "gz_c", "gz_b", "ts", "srcprm", "wav0", "wav1", "wav2", "wav3"}
 _I32 = {"kfs", "kob", "kfs_top", "kfs_bot", "kob_top", "kob_bot", "kbeg_a", "src_ik", "st_ik"}
-_F64 = {"mo", "m3"}
+_F64 = {"mo", "m3", "init_Vx", "init_Vz", "init_Sxx", "init_Szz", "init_Sxz"}
 
 # every symbol include/swpcpsv_host.h declares
 HOST_SYMBOLS = ["swpcpsv_host_create", "swpcpsv_host_create_from_text", "swpcpsv_host_destroy", "swpcpsv_host_last_error", "swpcpsv_host_get_int",

@@ -13,8 +13,8 @@
  * association; built with -ffp-contract=off and no fast-math.  PARITY UNPINNED: the reference holds no swpc_psv output.
  *
  * Scope: vmodel_type uni | lhm (+ benchmark_mode), all moment / body-force source formats of m_source.f90 except the
- * slip-based ones, PML and Cerjan absorbers, station products v / u / stress / strain, SAC files.  pw_mode, snapshots
- * and the grd / rmed / lgm / user models are outside this restatement and raise an error.
+ * slip-based ones, PML and Cerjan absorbers, station products v / u / stress / strain, SAC files, plane-wave mode, snapshots.
+ * The grd / rmed / lgm / user models are outside this restatement and raise an error.
  */
 #include "psv.h"
 
@@ -464,11 +464,99 @@ static void kernel_setup(psv_sim *s) {
 }
 
 /* ------------------------------------------------------------------------------------------------------------ */
+/* pw_setup, m_source.f90:656-785: plane P / SV wave as the initial condition over the whole memory box.  pw_strike and
+ * pw_rake are read but then forced to 90 degrees (:684-686).                                                        */
+static int pw_setup(psv_sim *s, const ora_ini *ini) {
+    psv_cfg *c = &s->cfg;
+    float pw_ztop, pw_zlen, strike, dip, rake;
+    char ps[ORA_STRLEN], tmp[ORA_STRLEN];
+    ora_readini_s(ini, "pw_ztop", &pw_ztop, 1e30f);
+    if (!(pw_ztop < c->zend)) { set_err("assert: pw_ztop < zend (m_source.f90:672)"); return -1; }
+    ora_readini_s(ini, "pw_zlen", &pw_zlen, -1.0f);
+    if (!(pw_zlen > 0.0f)) { set_err("assert: pw_zlen > 0 (m_source.f90:675)"); return -1; }
+    ora_readini_c(ini, "pw_ps", ps, "");
+    const int is_p = (ps[0] == 'p' || ps[0] == 'P'), is_s = (ps[0] == 's' || ps[0] == 'S');
+    if (!(is_p || is_s) || ps[1]) { set_err("assert: pw_ps must be p or s (m_source.f90:678)"); return -1; }
+    ora_readini_s(ini, "pw_strike", &strike, 0.0f);
+    ora_readini_s(ini, "pw_dip", &dip, 0.0f);
+    ora_readini_s(ini, "pw_rake", &rake, 0.0f);
+    strike = ora_deg2rad(90.0f); dip = ora_deg2rad(dip); rake = ora_deg2rad(90.0f);
+    ora_readini_c(ini, "stftype", tmp, "kupper");
+    snprintf(c->stftype, sizeof(c->stftype), "%.15s", tmp);
+    const float sd = sinf(dip), cd = cosf(dip), sf = sinf(strike), cf = cosf(strike), sl = sinf(rake), cl = cosf(rake);
+    const float c2d = cosf(2 * dip);
+    const float prm[2] = {0.0f, pw_zlen};
+    const float dt = c->dt;
+    const ora_mp dx = (ora_mp)c->dx, dz = (ora_mp)c->dz;
+    const char *st = c->stftype;
+    float fcut = 0.0f;
+    for (int q = 0; q < s->nranks; q++) {
+        psv_rank *r = &s->r[q];
+        for (int i = r->ibeg_m; i <= r->iend_m; i++)
+            for (int k = r->kbeg_m; k <= r->kend_m; k++) {
+                const size_t n = IX(r, k, i);
+                const float la0 = r->lam[n], mu0 = r->mu[n];
+                const float v = is_p ? sqrtf((la0 + 2 * mu0) / r->rho[n]) : sqrtf(mu0 / r->rho[n]);
+                if (v < FLT_EPS) continue;
+                const float x0 = (float)(c->xbeg + (i - 0.5f) * dx);
+                const float z0 = (float)(c->zbeg + (k - 0.5f) * dz - pw_ztop);
+                const float x1 = (float)(x0 + dx / 2.0f), z1 = (float)(z0 + dz / 2.0f);
+                const float stf_ii = ora_momentrate(sd * sf * x0 + cd * z0, st, prm);
+                const float stf_vx = ora_momentrate(sd * sf * x1 + cd * z0 + dt / 2.0f * v, st, prm);
+                const float stf_vz = ora_momentrate(sd * sf * x0 + cd * z1 + dt / 2.0f * v, st, prm);
+                const float stf_xz = ora_momentrate(sd * sf * x1 + cd * z1, st, prm);
+                if (is_p) {
+                    r->Vx[n] = -sd * sf * stf_vx;
+                    r->Vz[n] = -cd * stf_vz;
+                    r->Sxx[n] = -(la0 + 2 * mu0 * sd * sd * sf * sf) * stf_ii / v;
+                    r->Szz[n] = -(la0 + 2 * mu0 * cd * cd) * stf_ii / v;
+                    r->Sxz[n] = -2 * mu0 * sd * cd * sf * stf_xz / v;
+                } else {
+                    r->Vx[n] = (cl * cf + sl * cd * sf) * stf_vx;
+                    r->Vz[n] = -sl * sd * stf_vz;
+                    r->Sxx[n] = 2 * mu0 * sd * sf * (cl * cf + sl * cd * sf) * stf_ii / v;
+                    r->Szz[n] = -2 * mu0 * cd * sl * sd * stf_ii / v;
+                    r->Sxz[n] = mu0 * (cl * cd * cf + sl * c2d * sf) * stf_xz / v;
+                }
+            }
+        /* wavelength condition :764-783 (MPI_MAX over the ranks) */
+        const int i = ora_x2i((c->xbeg + c->xend) / 2, c->xbeg, (float)c->dx), k = ora_x2i(pw_ztop, c->zbeg, (float)c->dz);
+        if (r->ibeg <= i && i <= r->iend) {
+            const size_t n = IX(r, k, i);
+            const float v = is_p ? sqrtf((r->lam[n] + 2 * r->mu[n]) / r->rho[n]) : sqrtf(r->mu[n] / r->rho[n]);
+            if (v / pw_zlen > fcut) fcut = v / pw_zlen;
+        }
+    }
+    c->fcut = fcut;
+    c->fmax = fcut * 2.0f;
+    return 0;
+}
+
+/* Horizontal zero-derivative boundary of the plane-wave mode: linear extrapolation into the first column outside the
+ * model on the outer ranks, ahead of the PML update (m_absorb_p.f90:114-155 stresses, :287-326 velocities)           */
+static void pw_edges(const psv_cfg *c, psv_rank *r, int nproc_x, int stress_fields) {
+    ora_mp *f[3] = {stress_fields ? r->Sxx : r->Vx, stress_fields ? r->Szz : r->Vz, stress_fields ? r->Sxz : NULL};
+    const int nf = stress_fields ? 3 : 2;
+    for (int side = 0; side < 2; side++) {
+        if (side == 0 && r->idx != 0) continue;
+        if (side == 1 && r->idx != nproc_x - 1) continue;
+        const int dst = side == 0 ? 0 : c->nx + 1, s1 = side == 0 ? 1 : c->nx, s2 = side == 0 ? 2 : c->nx - 1;
+        for (int k = r->kbeg_a[s1 - r->ibeg_m]; k <= r->kend; k++)
+            for (int q = 0; q < nf; q++) f[q][IX(r, k, dst)] = 2 * f[q][IX(r, k, s1)] - f[q][IX(r, k, s2)];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------------ */
 /* m_source.f90:41-258 (+ source__grid_moment :260-474, source__grid_bodyforce :476-548)                           */
 static int source_setup(psv_sim *s, const ora_ini *ini, const char *base) {
     psv_cfg *c = &s->cfg;
     ora_readini_l(ini, "pw_mode", &c->pw_mode, 0);
-    if (c->pw_mode && !c->benchmark_mode) { set_err("swpc_psv pw_mode is outside the restated scope"); return -1; }
+    if (c->pw_mode && !c->benchmark_mode) { /* :68-76 */
+        if (pw_setup(s, ini)) return -1;
+        for (int q = 0; q < s->nranks; q++) s->r[q].nsrc = 0;
+        c->M0 = 1.0f / c->UC;
+        return 0;
+    }
     ora_readini_l(ini, "bf_mode", &c->bf_mode, 0);
     char tmp[ORA_STRLEN];
     ora_readini_c(ini, "fn_stf", c->fn_stf, "");
@@ -1238,6 +1326,7 @@ void psv_step(psv_sim *s, int it) {
     for (int q = 0; q < s->nranks; q++) {
         psv_rank *r = &s->r[q];
         kernel_update_stress(c, r);
+        if (pml && c->pw_mode) pw_edges(c, r, c->nproc_x, 0);   /* absorb_p__update_stress extrapolates the velocities */
         if (pml) absorb_p_update_stress(c, r); else absorb_c_update_stress(r);
         stressglut(c, r, it);
     }
@@ -1246,6 +1335,7 @@ void psv_step(psv_sim *s, int it) {
         psv_rank *r = &s->r[q];
         kernel_update_vel(c, r);
         bodyforce(c, r, it);
+        if (pml && c->pw_mode) pw_edges(c, r, c->nproc_x, 1);   /* absorb_p__update_vel extrapolates the stresses */
         if (pml) absorb_p_update_vel(c, r); else absorb_c_update_vel(r);
     }
     comm(s, 1);

@@ -260,3 +260,28 @@ def test_snapshot_native_stream(tmp_path):
     for m in range(3):
         np.testing.assert_array_equal(body[m * np2:(m + 1) * np2].reshape(info["nzs"], info["nxs"]), o.snap_medium(m))
     np.testing.assert_array_equal(body[3 * np2:].reshape(len(its), 2, info["nzs"], info["nxs"]), recs)
+
+
+@pytest.mark.parametrize("ps,abc", [("p", "pml"), ("s", "pml"), ("s", "cerjan")])
+def test_planewave_mode_bit_exact(tmp_path, ps, abc):
+    """pw_mode through the product's driver: initial condition on the host, edge extrapolation on the device ahead of the
+    PML updates (m_absorb_p.f90:114-155, :287-326), against the oracle."""
+    from openswpc_b200.swpc_psv import SwpcPsv
+
+    nt = 60
+    write_psv_files(tmp_path)
+    inf = tmp_path / "input.inf"
+    inf.write_text(psv_case_text(nt=nt, abc=abc, extra=f" pw_mode = .true.\n pw_ztop = 14.0\n pw_zlen = 6.0\n pw_ps = '{ps}'\n pw_dip = 20.0"))
+    o = PsvOracle(inf, base_dir=tmp_path, nm=3)
+    vm_ref = o.run(1, nt)
+    run = SwpcPsv(inf, base_dir=tmp_path, nm=3)
+    run.attach_device(0)
+    vm = run.run(1, nt)
+    assert np.array_equal(vm, vm_ref) and np.abs(vm_ref).max() > 0
+    got = run.download_fields()
+    nz, nxo = o.cfg("nz"), o.rank(0)["iend"] - o.rank(0)["ibeg"] + 1
+    for n, a in got.items():
+        ref = o.field(0, n)
+        assert np.array_equal(a[3:3 + nxo, 3:3 + nz], ref[3:3 + nxo, 3:3 + nz]), n
+    run.write_wav(tmp_path / "out")
+    assert np.array_equal(run.wav(0), o.wav(0, 0)) and np.abs(o.wav(0, 0)).max() > 0

@@ -83,8 +83,30 @@ def test_scope_errors_are_explicit(tmp_path):
     from openswpc_b200.swpc_psv import SwpcPsv, SwpcPsvError
 
     write_psv_files(tmp_path)
-    for extra, msg in ((" pw_mode = .true.", "pw_mode"), (" vmodel_type = 'grd'", "vmodel_type")):
+    for extra, msg in ((" vmodel_type = 'grd'", "vmodel_type"),):
         inf = tmp_path / "input.inf"
         inf.write_text(psv_case_text(nt=4, extra=extra) if "vmodel" not in extra else psv_case_text(nt=4, vmodel="grd"))
         with pytest.raises(SwpcPsvError, match=msg):
             SwpcPsv(inf, base_dir=tmp_path)
+
+
+@pytest.mark.parametrize("ps,dip", [("p", 0.0), ("s", 25.0), ("P", -30.0)])
+def test_planewave_initial_condition_matches_oracle(tmp_path, ps, dip):
+    """pw_setup (swpc_psv/m_source.f90:656-785): the five initial fields over the memory box, fcut / fmax / M0, no source grid."""
+    from openswpc_b200.swpc_psv import SwpcPsv
+
+    write_psv_files(tmp_path)
+    inf = tmp_path / "input.inf"
+    inf.write_text(psv_case_text(nt=10, nproc_x=2, nx=100, extra=f" pw_mode = .true.\n pw_ztop = 12.0\n pw_zlen = 6.0\n pw_ps = '{ps}'\n pw_dip = {dip}\n pw_strike = 33.0\n pw_rake = 12.0"))
+    o = PsvOracle(inf, base_dir=tmp_path, nm=3)
+    for q in range(o.nranks):
+        h = SwpcPsv(inf, base_dir=tmp_path, nm=3, myid=q)
+        assert h["nsrc"] == 0 == o.rank(q)["nsrc"]
+        for n in ("fcut", "fmax", "M0"):
+            assert np.float32(h[n]) == np.float32(o.cfg(n)), n
+        for n in ("Vx", "Vz", "Sxx", "Szz", "Sxz"):
+            a, ref = h["init_" + n].reshape(o.shape2(q)), o.field(q, n)
+            assert np.array_equal(a, ref), n
+        assert np.abs(o.field(q, "Vz")).max() > 0 and np.abs(o.field(q, "Szz")).max() > 0
+        for n in ("gxc", "gze"):
+            assert np.array_equal(h[n], o.profile(q, n)), n
