@@ -145,3 +145,22 @@ def test_boundary_first_split_bit_exact(tmp_path, abc, bf):
     d.sync()
     assert np.abs(o.field(0, "Vz")).max() > 0
     _compare(o, [d], exact=True)
+
+
+@pytest.mark.parametrize("abc", ["pml", "cerjan"])
+def test_ranks_entirely_inside_the_absorber(tmp_path, abc):
+    # 4 x 1 ranks of 10 columns with na = 10: the first and the last rank own absorber cells only (empty interior kernel box,
+    # m_global.f90:355-376), the middle ones interior columns only
+    o, devs = _run_pair(tmp_path, 30, nranks=(4, 1), nx=40, ny=36, nz=40, na=10, abc_type=abc,
+                        sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
+    r0 = o.rank(0)
+    if abc == "pml":
+        assert r0["iend_k"] < r0["ibeg_k"]
+    assert all(np.abs(o.field(q, "Vz")).max() > 0 for q in range(4))
+    _compare(o, devs, exact=True)
+
+
+def test_odd_sizes_and_padding(tmp_path):
+    # sizes that are multiples of nothing, and a source one cell from the PML
+    o, devs = _run_pair(tmp_path, 30, nranks=(1, 1), nx=37, ny=29, nz=35, na=5, sources=["-5.9 3.7 3.3 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
+    _compare(o, devs, exact=True)
