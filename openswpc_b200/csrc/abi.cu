@@ -152,7 +152,7 @@ struct swpc3d_handle {
     int use_side = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tuning
-    int tk = 32, ti = 8, jlen = 16, pf = 1;
+    int tk = 64, ti = 4, jlen = 16, pf = 1;
     int use_tma = 1, tma_jl = 16;   // use_tma: 0 off, 1 stress sweep only (default: measured fastest), 2 stress + velocity sweeps
     bool tma_ready = false, tma_ok = false;
     TmaMaps tmaps{};
