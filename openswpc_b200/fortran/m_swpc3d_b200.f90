@@ -41,6 +41,7 @@ module m_swpc3d_b200
     public :: swpc3d_nccl_unique_id, swpc3d_comm_init, swpc3d_last_error
     public :: swpc3d_set_wav_products, swpc3d_get_wav_product, swpc3d_set_option
     public :: swpc3d_snap_cfg, swpc3d_snap_setup, swpc3d_snap_step, swpc3d_snap_fetch, swpc3d_snap_fetch_max, swpc3d_reduce_sum
+    public :: swpc3d_set_green, swpc3d_green_store, swpc3d_green_source, swpc3d_get_green, swpc3d_advance
     public :: swpc3d_check
 
     !! mirrors `swpc3d_snap_cfg` of include/swpc3d_b200.h: the integers snap__setup computes (m_snap.f90:116-154)
