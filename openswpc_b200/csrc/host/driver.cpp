@@ -163,6 +163,7 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
     std::vector<float> p_rho(nzm), p_lam(nzm), p_mu(nzm), p_qp(nzm), p_qs(nzm);
     float bd0 = 0.0f;
     bool lateral = false;   // laterally heterogeneous builder: 3-D arrays are filled directly
+    bool grd_bddep = false; // ... which also wrote the boundary depths bd(:,:,0:NBD) itself
     if (benchmark_mode) {   // m_medium.f90:55-74
         fq_min = 0.05f; fq_max = 5.0f; fq_ref = 1.0f;
         for (int q = 0; q < nzm; q++) {
@@ -227,6 +228,13 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
                     if (zs[q] >= depth[l]) { r1 = r0[l]; vp1 = Cv[q] * vp0[l]; vs1 = Cv[q] * vs0[l]; a = qp0[l]; b = qs0[l]; }
                 p_rho[q] = r1; p_mu[q] = r1 * vs1 * vs1; p_lam[q] = r1 * (vp1 * vp1 - 2 * vs1 * vs1); p_qp[q] = a; p_qs[q] = b;
             }
+        } else if (vmodel_type == "grd" || vmodel_type == "grd_rmed") {   // models.hpp: GMT grids (netCDF classic) + bicubic interpolation
+            lateral = true;
+            grd_bddep = true;
+            const MediumBox mb{ibeg_m, iend_m, jbeg_m, jend_m, kbeg_m, kend_m, zc.data(), rho.data(), lam.data(), mu.data(), taup.data(), taus.data()};
+            const ModelEnv env{&ini, base, vcut, dt, dx, dy, dz, munk, ef};
+            const GrdGeometry gg{nx, ny, na, xbeg, ybeg, zbeg, clon, clat, phi, xc.data(), yc.data(), bddep.data(), nz};
+            if (vmodel_grd(env, mb, gg, vmodel_type == "grd_rmed")) return 1;
         } else if (vmodel_type == "lgm" || vmodel_type == "uni_rmed" || vmodel_type == "lhm_rmed" || vmodel_type == "lgm_rmed") {
             // models.hpp: these fill the 3-D arrays directly (Qp / Qs go to taup / taus, as in the reference's call)
             lateral = true;
@@ -236,11 +244,11 @@ int swpc3d_host::setup_medium(const IniFile &ini) {
                          : vmodel_type == "lhm_rmed" ? vmodel_lhm_rmed(env, mb, bd0) : vmodel_lgm_rmed(env, mb, bd0);
             if (rc) return 1;
         } else {
-            return hfail("vmodel_type '" + vmodel_type + "' is not available in this build: 'user' is a compile-time plug-in of the reference, "
-                         "'grd' / 'grd_rmed' need GMT netCDF-4 grids (no netCDF/HDF5 library in the image)");
+            return hfail("vmodel_type '" + vmodel_type + "' is not available in this build ('user' is a compile-time plug-in of the reference: "
+                         "link your own filler against swpc3d_b200.h's upload_medium instead)");
         }
     }
-    for (size_t n = 0; n < n2; n++) bddep[n] = bd0;
+    if (!grd_bddep) for (size_t n = 0; n < n2; n++) bddep[n] = bd0;
     if (std::getenv("SWPC3D_HOST_TIMING")) std::fprintf(stderr, "[swpc3d_host] vmodel done\n");
     if (lateral) return finish_medium_3d(ini);
 

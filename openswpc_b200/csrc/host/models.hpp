@@ -7,8 +7,11 @@
 //   rdrmed__3d        src/shared/m_rdrmed.f90:73-134             cyclic read of the volume written by gen_rmed3d
 //   stabilize_absorber src/swpc_3d/m_medium.f90:273-337
 // The image has no netCDF library; gen_rmed3d creates its file with NF90_CLOBBER (tools/gen_rmed3d.f90:91), i.e. the
-// netCDF classic format, which ClassicNc below parses directly.  vmodel_grd / grd_rmed read GMT grids (netCDF-4/HDF5 by
-// default) and vmodel_user is a compile-time plug-in: both stay out of this build.
+// netCDF classic format, which ClassicNc below parses directly.  vmodel_grd / grd_rmed read GMT grids: those are accepted in
+// the classic container (`gmt grdconvert in.grd out.grd=cf`, `nccopy -k classic`); netCDF-4/HDF5 grids are refused with a
+// message.  vmodel_user is a compile-time plug-in of the reference and stays out of this build.
+//   vmodel_grd        src/swpc_3d/m_vmodel_grd.f90:28-303 + src/shared/m_bicubic.f90
+//   vmodel_grd_rmed   src/swpc_3d/m_vmodel_grd_rmed.f90:28-388
 #pragma once
 
 #include "common.hpp"
@@ -72,6 +75,18 @@ class ClassicNc {
                 var.push_back(x);
             }
         return true;
+    }
+    // element `idx` of variable v as a double, for the numeric netCDF types a GMT grid may use
+    double value(int v, long long idx) const {
+        const unsigned char *p = bytes.data() + var[(size_t)v].begin;
+        auto be = [&](int n) { unsigned long long u = 0; for (int q = 0; q < n; q++) u = (u << 8) | p[(size_t)idx * n + q]; return u; };
+        switch (var[(size_t)v].type) {
+        case 5: { const uint32_t u = (uint32_t)be(4); float x; std::memcpy(&x, &u, 4); return (double)x; }
+        case 6: { const uint64_t u = be(8); double x; std::memcpy(&x, &u, 8); return x; }
+        case 4: return (double)(int32_t)be(4);
+        case 3: return (double)(int16_t)be(2);
+        default: return 0.0;
+        }
     }
     float f32(long long byte_off) const {
         const unsigned char *p = bytes.data() + byte_off;
@@ -417,6 +432,219 @@ inline void stabilize_absorber(const MediumBox &b, const int *kbeg_a /* (i,j) ov
                 }
             }
         }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// vmodel_grd, src/swpc_3d/m_vmodel_grd.f90:28-303: layers bounded by GMT grids in geographic coordinates, interpolated
+// with the bicubic patch of src/shared/m_bicubic.f90.  Grids must be netCDF *classic* files (GMT's default netCDF-4
+// container needs `gmt grdconvert in.grd out.grd=cf` or `nccopy -k classic` first: there is no HDF5 in this build).
+class BicubicPatch {   // m_bicubic.f90: bicubic__init_d (:72-110), bicubic__coef (:231-288), bicubic__interp_d (:141-228)
+  public:
+    BicubicPatch(int nx, int ny, double x0, double y0, double dx, double dy, std::vector<double> f)
+        : nx_(nx), ny_(ny), x0_(x0), y0_(y0), dx_(dx), dy_(dy), f_(std::move(f)), fx_(f_.size()), fy_(f_.size()), fxy_(f_.size()) {
+        ddx(f_, fx_); ddy(f_, fy_); ddx(fy_, fxy_);
+        for (size_t q = 0; q < f_.size(); q++) { fx_[q] = fx_[q] * dx_; fy_[q] = fy_[q] * dy_; fxy_[q] = fxy_[q] * dx_ * dy_; }
+    }
+    double operator()(double xi, double yi) {
+        int ii = (int)std::floor((xi - x0_) / dx_) + 1, jj = (int)std::floor((yi - y0_) / dy_) + 1;   // 1-based pixel
+        if (ii < 1 || ii > nx_ - 1 || jj <= 0 || jj > ny_ - 1) {   // outside: clamp to the edge pixel and its edge
+            if (ii < 1) { ii = 1; xi = x0_; }
+            if (ii > nx_ - 1) { ii = nx_ - 1; xi = x0_ + (nx_ - 1) * dx_; }
+            if (jj < 1) { jj = 1; yi = y0_; }
+            if (jj > ny_ - 1) { jj = ny_ - 1; yi = y0_ + (ny_ - 1) * dy_; }
+        }
+        if (ii != ii0_ || jj != jj0_) { coefficients(ii, jj); ii0_ = ii; jj0_ = jj; }
+        const double xd = (xi - (x0_ + (ii - 1) * dx_)) / dx_, yd = (yi - (y0_ + (jj - 1) * dy_)) / dy_;
+        const double px[4] = {1.0, xd, xd * xd, xd * xd * xd}, py[4] = {1.0, yd, yd * yd, yd * yd * yd};
+        double v = 0.0;
+        for (int j = 0; j < 4; j++)
+            for (int i = 0; i < 4; i++) v = v + a_[4 * j + i] * px[i] * py[j];
+        return v;
+    }
+
+  private:
+    int nx_, ny_, ii0_ = 0, jj0_ = 0;
+    double x0_, y0_, dx_, dy_, a_[16];
+    std::vector<double> f_, fx_, fy_, fxy_;
+    size_t at(int i, int j) const { return (size_t)i + (size_t)nx_ * j; }
+    void ddx(const std::vector<double> &g, std::vector<double> &o) const {   // diffx :291-313
+        for (int j = 0; j < ny_; j++) {
+            for (int i = 1; i < nx_ - 1; i++) o[at(i, j)] = (g[at(i + 1, j)] - g[at(i - 1, j)]) / (2 * dx_);
+            o[at(0, j)] = (g[at(1, j)] - g[at(0, j)]) / dx_;
+            o[at(nx_ - 1, j)] = (g[at(nx_ - 1, j)] - g[at(nx_ - 2, j)]) / dx_;
+        }
+    }
+    void ddy(const std::vector<double> &g, std::vector<double> &o) const {   // diffy :316-338
+        for (int i = 0; i < nx_; i++) {
+            for (int j = 1; j < ny_ - 1; j++) o[at(i, j)] = (g[at(i, j + 1)] - g[at(i, j - 1)]) / (2 * dy_);
+            o[at(i, 0)] = (g[at(i, 1)] - g[at(i, 0)]) / dy_;
+            o[at(i, ny_ - 1)] = (g[at(i, ny_ - 1)] - g[at(i, ny_ - 2)]) / dy_;
+        }
+    }
+    void coefficients(int ii, int jj) {   // a(i, j) = row 4j + i of M x, x = (f, fx, fy, fxy) at the four pixel corners
+        static const signed char M[16][16] = {
+            {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+            {-3, 3, 0, 0, -2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {2, -2, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+            {0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0},
+            {0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, -2, -1, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 2, -2, 0, 0, 1, 1, 0, 0},
+            {-3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0, 0, 0, 0, 0}, {0, 0, 0, 0, -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0},
+            {9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1}, {-6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1},
+            {2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0},
+            {-6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1}, {4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1}};
+        const std::vector<double> *src[4] = {&f_, &fx_, &fy_, &fxy_};
+        double x[16];
+        for (int q = 0; q < 4; q++) {
+            const std::vector<double> &g = *src[q];
+            x[4 * q] = g[at(ii - 1, jj - 1)]; x[4 * q + 1] = g[at(ii, jj - 1)]; x[4 * q + 2] = g[at(ii - 1, jj)]; x[4 * q + 3] = g[at(ii, jj)];
+        }
+        for (int r = 0; r < 16; r++) {
+            double acc = 0.0;
+            for (int l = 0; l < 16; l++) acc = acc + (double)M[r][l] * x[l];
+            a_[r] = acc;
+        }
+    }
+};
+
+struct GrdGeometry {   // what vmodel_grd needs beyond ModelEnv / MediumBox
+    int nx, ny, na;
+    float xbeg, ybeg, zbeg, clon, clat, phi;
+    const float *xc, *yc;       // xc(ib:ie), yc(jb:je)
+    float *bddep;               // bd(ib:ie, jb:je, 0:NBD)
+    int nz = 0;
+};
+
+// with_rmed: vmodel_grd_rmed (m_vmodel_grd_rmed.f90:28-388) -- each layer additionally carries a random-media volume that is
+// sampled at the depth below a reference interface `reflyr` (0: the top of the volume), wrapped cyclically
+inline int vmodel_grd(const ModelEnv &e, const MediumBox &b, const GrdGeometry &gg, bool with_rmed = false) {
+    const IniFile &ini = *e.ini;
+    const std::string fn_lst = ini.get(with_rmed ? "fn_grdlst_rmed" : "fn_grdlst", "."), dir_grd = ini.get("dir_grd", ".");
+    const bool topo_flatten = ini.get_l("topo_flatten", false);
+    const bool is_ocean = ini.get_l("is_ocean", true) || topo_flatten;
+    const int nk = b.nk(), ni = b.ni(), nj = b.je - b.jb + 1;
+    const size_t n2 = (size_t)ni * nj;
+    const float fdx = (float)e.dx, fdy = (float)e.dy, fdz = (float)e.dz;
+    std::vector<float> cv((size_t)nk, 1.0f);
+    if (e.flatten) for (int q = 0; q < nk; q++) cv[(size_t)q] = (float)std::exp((double)b.zc[q] / R_EARTH);
+    // air, then ocean (:88-133): one plan per plane, filled column by column
+    std::vector<PlanePlan> pl((size_t)nk);
+    for (int q = 0; q < nk; q++) {
+        PlanePlan &p = pl[(size_t)q];
+        const float zc = b.zc[q];
+        if (is_ocean && !(zc < 0)) { const float vp = cv[(size_t)q] * seawater_vel(zc, e.munk); p.rho = 1.0f; p.lam = 1.0f * (vp * vp - 2 * 0.0f * 0.0f); p.mu = 0.0f; p.qp = p.qs = 1000000.0f; }
+        else { p.rho = 0.001f; p.lam = 0.0f; p.mu = 0.0f; p.qp = p.qs = 1.0f; }
+    }
+    fill_columns(b, pl, [](const PlanePlan &, size_t) {});
+    // geographic location of every column, clamped to the inner edge of the absorber (:137-151)
+    const float x_ab = i2x(gg.na + 1, gg.xbeg, fdx), x_ae = i2x(gg.nx - gg.na, gg.xbeg, fdx);
+    const float y_ab = i2x(gg.na + 1, gg.ybeg, fdy), y_ae = i2x(gg.ny - gg.na, gg.ybeg, fdy);
+    std::vector<float> glon(n2), glat(n2);
+    for (int j = 0; j < nj; j++)
+        for (int i = 0; i < ni; i++)
+            geomap_c2g(std::min(std::max(gg.xc[i], x_ab), x_ae), std::min(std::max(gg.yc[j], y_ab), y_ae), gg.clon, gg.clat, gg.phi, glon[(size_t)i + (size_t)ni * j],
+                       glat[(size_t)i + (size_t)ni * j]);
+    // layer list (:154-173): 'file' rho vp vs qp qs pid
+    struct Layer { std::string fn; float rho, vp, vs, qp, qs; int pid; int reflyr = 0; };
+    std::vector<Layer> L;
+    LayerTable names;   // random-media file per layer, for read_rmed_set
+    {
+        std::ifstream is(join_path(e.base, fn_lst));
+        if (!is) return hfail("vmodel_grd: cannot open the layer list " + fn_lst);
+        std::string line;
+        while (std::getline(is, line)) {
+            if (blank_or_comment(line)) continue;
+            for (auto &ch : line) if (ch == ',') ch = ' ';
+            std::istringstream ls(line);
+            Layer y;
+            if (!(ls >> y.fn >> y.rho >> y.vp >> y.vs >> y.qp >> y.qs >> y.pid)) continue;
+            const auto unquote = [](std::string &t) { if (t.size() >= 2 && (t[0] == '\'' || t[0] == '"') && t.back() == t[0]) t = t.substr(1, t.size() - 2); };
+            unquote(y.fn);
+            y.fn = dir_grd + "/" + y.fn;
+            if (with_rmed) {
+                std::string rn;
+                if (!(ls >> rn >> y.reflyr)) continue;
+                unquote(rn);
+                names.rmed.push_back(rn);
+                names.depth.push_back(0.0f);
+            }
+            L.push_back(y);
+        }
+    }
+    const int ngrd = (int)L.size();
+    for (int n = ngrd - 2; n >= 0; n--)
+        if ((L[n].vp < e.vcut || L[n].vs < e.vcut) && (L[n].vp > 0 && L[n].vs > 0)) { L[n].vp = L[n + 1].vp; L[n].vs = L[n + 1].vs; L[n].rho = L[n + 1].rho; L[n].qp = L[n + 1].qp; L[n].qs = L[n + 1].qs; }
+    std::vector<int> tbl;
+    std::vector<std::vector<float>> xi;
+    const float rhomin = ini.get_s("rhomin", 1.0f), vmin = e.vcut, vmax = e.rmed_vmax();
+    if (with_rmed) {
+        for (const Layer &y : L) {
+            if (!(0 <= y.reflyr && y.reflyr <= ngrd)) return hfail("assert: 0 <= reflyr <= ngrd (m_vmodel_grd_rmed.f90:208)");
+            if (!(y.vp < vmax && y.vs < vmax)) return hfail("assert: background velocity exceeds the stability limit (m_vmodel_grd_rmed.f90:342-343)");
+        }
+        if (read_rmed_set(e, b, names, tbl, xi)) return 1;
+    }
+    std::fill(gg.bddep, gg.bddep + n2 * (NBD + 1), 0.0f);
+    // interface index of every layer in every column (:180-268)
+    std::vector<int> kgrd(n2 * (size_t)(ngrd + 1), b.kb - 1);
+    const int ktopo = x2i(0.0f - fdz / 2, gg.zbeg, fdz);
+    for (int n = 1; n <= ngrd; n++) {
+        ClassicNc nc;
+        std::string err;
+        if (!nc.open(join_path(e.base, L[n - 1].fn), err)) return hfail("vmodel_grd: " + err + " (grids must be netCDF classic files)");
+        if (nc.dim.size() != 2 || nc.var.size() < 3) return hfail("vmodel_grd: " + L[n - 1].fn + " is not a 2-D grid with variables x, y, z");
+        const int nlon = (int)nc.dim[0], nlat = (int)nc.dim[1];
+        std::vector<double> dep((size_t)nlon * nlat);
+        for (size_t q = 0; q < dep.size(); q++) dep[q] = nc.value(2, (long long)q) / 1000;   // m -> km
+        const double lon0 = nc.value(0, 0), lat0 = nc.value(1, 0);
+        const double dlon = (nc.value(0, nlon - 1) - lon0) / (nlon - 1), dlat = (nc.value(1, nlat - 1) - lat0) / (nlat - 1);
+        BicubicPatch patch(nlon, nlat, lon0, lat0, dlon, dlat, std::move(dep));
+        const int *below = kgrd.data() + n2 * (size_t)(n - 1);
+        int *mine = kgrd.data() + n2 * (size_t)n;
+        for (size_t q = 0; q < n2; q++) {
+            float z = (float)patch((double)glon[q], (double)glat[q]);
+            if (e.flatten) z = (float)(-R_EARTH * std::log((R_EARTH - (double)z) / R_EARTH));
+            if (n == 1) gg.bddep[q] = z;
+            if (topo_flatten) z = z - gg.bddep[q];
+            int k = std::max(x2i(z - fdz / 2, gg.zbeg, fdz), below[q]);
+            if (n == 1 && z > 0) k = std::max(ktopo + 2, k);   // sea column at least two cells thick
+            mine[q] = k;
+            if (L[n - 1].pid > 0 && L[n - 1].pid <= NBD) gg.bddep[n2 * (size_t)L[n - 1].pid + q] = z;
+        }
+    }
+    // every layer fills everything below its interface; deeper layers overwrite (:270-288)
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long long q = 0; q < (long long)n2; q++) {
+        const size_t n0 = (size_t)q * (size_t)nk;
+        for (int n = 1; n <= ngrd; n++) {
+            const Layer &y = L[(size_t)n - 1];
+            const float *x3 = with_rmed ? xi[(size_t)tbl[(size_t)n - 1]].data() + n0 : nullptr;
+            const int kref = kgrd[n2 * (size_t)y.reflyr + (size_t)q];
+            for (int k = std::max(kgrd[n2 * (size_t)n + (size_t)q] + 1, b.kb); k <= b.ke; k++) {
+                const size_t m = n0 + (size_t)(k - b.kb);
+                const float c = cv[(size_t)(k - b.kb)];
+                if (with_rmed) {   // m_vmodel_grd_rmed.f90:333-360
+                    int kk = k - kref + 1;   // depth index below the reference interface, cyclic
+                    if (kk < b.kb) kk = kk + gg.nz;
+                    if (kk > b.ke) kk = kk - b.ke;
+                    if (kk < b.kb || kk > b.ke) { bad++; continue; }
+                    const float x = x3[kk - b.kb];
+                    float vp2 = c * y.vp * (1.0f + x), vs2 = c * y.vs * (1.0f + x), rho2 = y.rho * (1.0f + 0.8f * x);
+                    if (y.vp > 0 && y.vs > 0) vcheck(vp2, vs2, rho2, x, vmin, vmax, rhomin);
+                    b.rho[m] = rho2;
+                    b.lam[m] = rho2 * (vp2 * vp2 - 2 * vs2 * vs2);
+                    b.mu[m] = rho2 * vs2 * vs2;
+                } else {
+                    b.rho[m] = y.rho;
+                    b.lam[m] = y.rho * (c * c) * (y.vp * y.vp - 2 * y.vs * y.vs);
+                    b.mu[m] = y.rho * (c * c) * y.vs * y.vs;
+                }
+                b.qp[m] = y.qp;
+                b.qs[m] = y.qs;
+            }
+        }
+    }
+    if (bad) return hfail("vmodel_grd_rmed: relative depth index out of the volume");
+    return 0;
 }
 
 }   // namespace

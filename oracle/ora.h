@@ -228,6 +228,7 @@ int ora_vmodel_lgm(const ora_ini *ini, const char *base, ora_rank *r, float vcut
 int ora_vmodel_uni_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
 int ora_vmodel_lhm_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
 int ora_vmodel_lgm_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
+int ora_vmodel_grd(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, int with_rmed, char *err, size_t cap);
 void ora_stabilize_absorber(const ora_cfg *c, ora_rank *r);
 
 /* ---------------------------------------------------------------- life cycle / driver API */

@@ -591,3 +591,251 @@ void ora_stabilize_absorber(const ora_cfg *c, ora_rank *r) {
             }
         }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* vmodel_grd, src/swpc_3d/m_vmodel_grd.f90:28-303: layered 3-D model whose interfaces are GMT grids in geographic
+ * coordinates, interpolated bicubically (src/shared/m_bicubic.f90) onto the FDM columns.  The reference reads the grids
+ * through the netCDF library; this restatement (and the product's host) reads netCDF *classic* files only -- grids in
+ * GMT's default netCDF-4 container have to be converted first (e.g. `gmt grdconvert in.grd out.grd=cf`, `nccopy -k classic`).
+ * The summation order inside bicubic__coef's matmul is not defined by the Fortran standard; plain left-to-right sums are
+ * used here and in the product. */
+static double nc_value(const nc_file *f, int v, long long idx) {
+    const unsigned char *p = f->buf + f->var[v].begin;
+    switch (f->var[v].type) {
+    case 5: { unsigned u = (unsigned)be_u(p + 4 * idx, 4); float x; memcpy(&x, &u, 4); return (double)x; }
+    case 6: { unsigned long long u = be_u(p + 8 * idx, 8); double x; memcpy(&x, &u, 8); return x; }
+    case 4: return (double)(int)be_u(p + 4 * idx, 4);
+    case 3: return (double)(short)be_u(p + 2 * idx, 2);
+    default: return 0.0;
+    }
+}
+
+typedef struct {
+    int nx, ny;
+    double x0, y0, dx, dy;
+    double *f, *fx, *fy, *fxy;
+    int ii0, jj0, first;
+    double aa[4][4]; /* aa[j][i] = aa(i, j) */
+} bicubic;
+
+static void bc_diffx(int nx, int ny, double dx, const double *ff, double *out) { /* m_bicubic.f90:291-313 */
+    for (int j = 0; j < ny; j++) {
+        for (int i = 1; i < nx - 1; i++) out[i + nx * j] = (ff[i + 1 + nx * j] - ff[i - 1 + nx * j]) / (2 * dx);
+        out[nx * j] = (ff[1 + nx * j] - ff[nx * j]) / dx;
+        out[nx - 1 + nx * j] = (ff[nx - 1 + nx * j] - ff[nx - 2 + nx * j]) / dx;
+    }
+}
+static void bc_diffy(int nx, int ny, double dy, const double *ff, double *out) { /* :316-338 */
+    for (int i = 0; i < nx; i++) {
+        for (int j = 1; j < ny - 1; j++) out[i + nx * j] = (ff[i + nx * (j + 1)] - ff[i + nx * (j - 1)]) / (2 * dy);
+        out[i] = (ff[i + nx] - ff[i]) / dy;
+        out[i + nx * (ny - 1)] = (ff[i + nx * (ny - 1)] - ff[i + nx * (ny - 2)]) / dy;
+    }
+}
+static void bc_init(bicubic *b, int nx, int ny, double x0, double y0, double dx, double dy, const double *dat) { /* :72-110 */
+    const size_t n = (size_t)nx * ny;
+    b->nx = nx; b->ny = ny; b->x0 = x0; b->y0 = y0; b->dx = dx; b->dy = dy;
+    b->f = (double *)malloc(4 * n * sizeof(double));
+    b->fx = b->f + n; b->fy = b->fx + n; b->fxy = b->fy + n;
+    memcpy(b->f, dat, n * sizeof(double));
+    bc_diffx(nx, ny, dx, b->f, b->fx);
+    bc_diffy(nx, ny, dy, b->f, b->fy);
+    bc_diffx(nx, ny, dx, b->fy, b->fxy);
+    for (size_t q = 0; q < n; q++) { b->fx[q] = b->fx[q] * dx; b->fy[q] = b->fy[q] * dy; b->fxy[q] = b->fxy[q] * dx * dy; }
+    b->first = 1; b->ii0 = b->jj0 = 0;
+}
+static void bc_coef(bicubic *b, int ii, int jj) { /* :231-288; ii, jj 1-based */
+    static const double mat[16][16] = {
+        {1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+        {-3, 3, 0, 0, -2, -1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, {2, -2, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+        {0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0},
+        {0, 0, 0, 0, 0, 0, 0, 0, -3, 3, 0, 0, -2, -1, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 2, -2, 0, 0, 1, 1, 0, 0},
+        {-3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0, 0, 0, 0, 0}, {0, 0, 0, 0, -3, 0, 3, 0, 0, 0, 0, 0, -2, 0, -1, 0},
+        {9, -9, -9, 9, 6, 3, -6, -3, 6, -6, 3, -3, 4, 2, 2, 1}, {-6, 6, 6, -6, -3, -3, 3, 3, -4, 4, -2, 2, -2, -2, -1, -1},
+        {2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 2, 0, -2, 0, 0, 0, 0, 0, 1, 0, 1, 0},
+        {-6, 6, 6, -6, -4, -2, 4, 2, -3, 3, -3, 3, -2, -1, -2, -1}, {4, -4, -4, 4, 2, 2, -2, -2, 2, -2, 2, -2, 1, 1, 1, 1}};
+    const int nx = b->nx, i0 = ii - 1, j0 = jj - 1;
+    double xx[16];
+    const double *src[4] = {b->f, b->fx, b->fy, b->fxy};
+    for (int q = 0; q < 4; q++) {
+        xx[4 * q] = src[q][i0 + nx * j0]; xx[4 * q + 1] = src[q][i0 + 1 + nx * j0];
+        xx[4 * q + 2] = src[q][i0 + nx * (j0 + 1)]; xx[4 * q + 3] = src[q][i0 + 1 + nx * (j0 + 1)];
+    }
+    for (int r = 0; r < 16; r++) {
+        double acc = 0.0;
+        for (int l = 0; l < 16; l++) acc = acc + mat[r][l] * xx[l];
+        b->aa[r / 4][r % 4] = acc; /* aa(0:3, r/4) = rows 4*(r/4)+1 .. +4 */
+    }
+}
+static double bc_interp(bicubic *b, double xi, double yi) { /* :141-228, no default value */
+    const double x0 = b->x0, y0 = b->y0, dx = b->dx, dy = b->dy;
+    const int nx = b->nx, ny = b->ny;
+    int ii = (int)floor((xi - x0) / dx) + 1, jj = (int)floor((yi - y0) / dy) + 1;
+    double xi2 = xi, yi2 = yi;
+    if (ii < 1 || ii > nx - 1 || jj <= 0 || jj > ny - 1) {
+        if (ii < 1) { ii = 1; xi2 = x0; }
+        if (ii > nx - 1) { ii = nx - 1; xi2 = x0 + (nx - 1) * dx; }
+        if (jj < 1) { jj = 1; yi2 = y0; }
+        if (jj > ny - 1) { jj = ny - 1; yi2 = y0 + (ny - 1) * dy; }
+    }
+    if (b->ii0 != ii || b->jj0 != jj || b->first) bc_coef(b, ii, jj);
+    const double xd = (xi2 - (x0 + (ii - 1) * dx)) / dx, yd = (yi2 - (y0 + (jj - 1) * dy)) / dy;
+    const double xda[4] = {1.0, xd, xd * xd, xd * xd * xd}, yda[4] = {1.0, yd, yd * yd, yd * yd * yd};
+    double v = 0.0;
+    for (int j = 0; j < 4; j++)
+        for (int i = 0; i < 4; i++) v = v + b->aa[j][i] * xda[i] * yda[j];
+    b->first = 0; b->ii0 = ii; b->jj0 = jj;
+    return v;
+}
+
+/* with_rmed: vmodel_grd_rmed (m_vmodel_grd_rmed.f90:28-388) -- the same layers, each perturbed by a random-media volume that is
+ * indexed by the depth below a reference interface (reflyr) */
+int ora_vmodel_grd(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, int with_rmed, char *err, size_t cap) {
+    char fn_lst[ORA_STRLEN], dir_grd[ORA_STRLEN], path[3 * ORA_STRLEN];
+    int is_ocean, is_flatten, use_munk, ef, node_grd;
+    ora_readini_c(ini, with_rmed ? "fn_grdlst_rmed" : "fn_grdlst", fn_lst, ".");
+    ora_readini_c(ini, "dir_grd", dir_grd, ".");
+    ora_readini_i(ini, "node_grd", &node_grd, 0);
+    ora_readini_l(ini, "is_ocean", &is_ocean, 1);
+    ora_readini_l(ini, "topo_flatten", &is_flatten, 0);
+    if (is_flatten) is_ocean = 1;
+    ora_readini_l(ini, "munk_profile", &use_munk, 0);
+    ora_readini_l(ini, "earth_flattening", &ef, 0);
+    const double RE = ora_r_earth();
+    const int nk = r->nzm;
+    float *Cv = (float *)malloc(sizeof(float) * (size_t)nk);
+    for (int k = r->kbeg_m; k <= r->kend_m; k++) Cv[k - r->kbeg_m] = ef ? (float)exp((double)r->zc[k - r->kbeg_m] / RE) : 1.0f;
+    /* air, then ocean :88-133 */
+    for (int j = r->jbeg_m; j <= r->jend_m; j++)
+        for (int i = r->ibeg_m; i <= r->iend_m; i++)
+            for (int k = r->kbeg_m; k <= r->kend_m; k++) {
+                const size_t n = ora_idx3(r, k, i, j);
+                const float zc = r->zc[k - r->kbeg_m];
+                float vp0 = 0.0f, vs0 = 0.0f, rho0 = 0.001f, qp0 = 1.0f, qs0 = 1.0f;
+                if (is_ocean && !(zc < 0)) { vp0 = Cv[k - r->kbeg_m] * ora_seawater_vel(zc, use_munk); rho0 = 1.0f; qp0 = 1000000.0f; qs0 = 1000000.0f; }
+                r->rho[n] = rho0; r->lam[n] = rho0 * (vp0 * vp0 - 2 * vs0 * vs0); r->mu[n] = rho0 * vs0 * vs0; qp[n] = qp0; qs[n] = qs0;
+            }
+    /* geographic location of every column, clamped to the inner edge of the absorber :137-151 */
+    const float dx = (float)c->dx, dy = (float)c->dy, dz = (float)c->dz;
+    const float x_AB = ora_i2x(c->na + 1, c->xbeg, dx), x_AE = ora_i2x(c->nx - c->na, c->xbeg, dx);
+    const float y_AB = ora_i2x(c->na + 1, c->ybeg, dy), y_AE = ora_i2x(c->ny - c->na, c->ybeg, dy);
+    const size_t n2 = (size_t)r->nxm * r->nym;
+    float *glon = (float *)malloc(sizeof(float) * n2), *glat = (float *)malloc(sizeof(float) * n2);
+    for (int j = r->jbeg_m; j <= r->jend_m; j++)
+        for (int i = r->ibeg_m; i <= r->iend_m; i++) {
+            const float xc = r->xc[i - r->ibeg_m], yc = r->yc[j - r->jbeg_m];
+            const float xx = fminf(fmaxf(xc, x_AB), x_AE), yy = fminf(fmaxf(yc, y_AB), y_AE);
+            ora_geomap_c2g(xx, yy, c->clon, c->clat, c->phi, &glon[ora_idx2(r, i, j)], &glat[ora_idx2(r, i, j)]);
+        }
+    /* layer list :154-173 */
+    join(base, fn_lst, path, sizeof(path));
+    FILE *fp = fopen(path, "r");
+    if (!fp) { snprintf(err, cap, "vmodel_grd: cannot open the layer list %s", path); free(Cv); free(glon); free(glat); return -1; }
+    int ngrd = 0;
+    static char fn_grd[64][ORA_STRLEN];
+    float rho1[64], vp1[64], vs1[64], qp1[64], qs1[64];
+    int pid[64], reflyr[64];
+    layers *LR = with_rmed ? (layers *)calloc(1, sizeof(layers)) : NULL;   /* only fn_rmed[] / nl are used */
+    char line[1024];
+    while (fgets(line, sizeof(line), fp) && ngrd < 64) {
+        char *p = line;
+        while (*p == ' ' || *p == '\t') p++;
+        if (*p == '#' || is_blank(p)) continue;
+        for (char *t = p; *t; t++) if (*t == ',') *t = ' ';
+        char name[ORA_STRLEN], rname[ORA_STRLEN] = "";
+        reflyr[ngrd] = 0;
+        const int got = sscanf(p, " %255s %f %f %f %f %f %d %255s %d", name, &rho1[ngrd], &vp1[ngrd], &vs1[ngrd], &qp1[ngrd], &qs1[ngrd], &pid[ngrd], rname, &reflyr[ngrd]);
+        if (got < (with_rmed ? 9 : 7)) continue;
+        size_t ln = strlen(name);
+        if (ln >= 2 && (name[0] == '\'' || name[0] == '"') && name[ln - 1] == name[0]) { memmove(name, name + 1, ln - 2); name[ln - 2] = 0; }
+        if (with_rmed) {
+            ln = strlen(rname);
+            if (ln >= 2 && (rname[0] == '\'' || rname[0] == '"') && rname[ln - 1] == rname[0]) { memmove(rname, rname + 1, ln - 2); rname[ln - 2] = 0; }
+            snprintf(LR->fn_rmed[ngrd], ORA_STRLEN, "%s", rname);
+        }
+        snprintf(fn_grd[ngrd], ORA_STRLEN, "%.120s/%.120s", dir_grd, name);
+        ngrd++;
+    }
+    fclose(fp);
+    for (int n = ngrd - 2; n >= 0; n--)
+        if ((vp1[n] < vcut || vs1[n] < vcut) && (vp1[n] > 0 && vs1[n] > 0)) { vp1[n] = vp1[n + 1]; vs1[n] = vs1[n + 1]; rho1[n] = rho1[n + 1]; qp1[n] = qp1[n + 1]; qs1[n] = qs1[n + 1]; }
+    int tbl[64];
+    float *xi = NULL, rhomin = 1.0f;
+    const float vmin = vcut, vmax = rmed_vmax(c);
+    if (with_rmed) {
+        ora_readini_s(ini, "rhomin", &rhomin, 1.0f);
+        LR->nl = ngrd;
+        for (int n = 0; n < ngrd; n++)
+            if (!(0 <= reflyr[n] && reflyr[n] <= ngrd)) { snprintf(err, cap, "assert: 0 <= reflyr <= ngrd (m_vmodel_grd_rmed.f90:208)"); free(LR); free(Cv); free(glon); free(glat); return -1; }
+        if (read_rmed_set(ini, base, LR, r, tbl, &xi, err, cap)) { free(LR); free(Cv); free(glon); free(glat); return -1; }
+    }
+    int *kgrd = (int *)malloc(sizeof(int) * n2 * (size_t)(ngrd + 1));   /* kgrd(0:ngrd, i, j) */
+    for (size_t q = 0; q < n2; q++) kgrd[q] = r->kbeg_m - 1;
+    const int ktopo = ora_x2i(0.0f - dz / 2, c->zbeg, dz);
+    size_t nbd = n2;
+    for (int b = 1; b <= ORA_NBD; b++)
+        for (size_t q = 0; q < nbd; q++) r->bddep[(size_t)b * n2 + q] = 0.0f;   /* bd is intent(out): only bd(:,:,0) and bd(:,:,pid) are set */
+    int rc = 0;
+    for (int n = 1; n <= ngrd && !rc; n++) {
+        char full[4 * ORA_STRLEN];
+        join(base, fn_grd[n - 1], full, sizeof(full));
+        nc_file *f = nc_open_classic(full, err, cap);
+        if (!f) { rc = -1; break; }
+        if (f->ndims != 2 || f->nvars < 3) { snprintf(err, cap, "%s: expected a 2-D grid (x, y, z)", full); nc_close(f); rc = -1; break; }
+        const int nlon = (int)f->dimlen[0], nlat = (int)f->dimlen[1];
+        double *dep = (double *)malloc(sizeof(double) * (size_t)nlon * nlat);
+        for (long long q = 0; q < (long long)nlon * nlat; q++) dep[q] = nc_value(f, 2, q) / 1000;   /* m -> km */
+        const double lon0 = nc_value(f, 0, 0), lonN = nc_value(f, 0, nlon - 1), lat0 = nc_value(f, 1, 0), latN = nc_value(f, 1, nlat - 1);
+        const double dlon = (lonN - lon0) / (nlon - 1), dlat = (latN - lat0) / (nlat - 1);
+        nc_close(f);
+        bicubic bc;
+        bc_init(&bc, nlon, nlat, lon0, lat0, dlon, dlat, dep);
+        free(dep);
+        for (int j = r->jbeg_m; j <= r->jend_m; j++)
+            for (int i = r->ibeg_m; i <= r->iend_m; i++) {
+                const size_t q = ora_idx2(r, i, j);
+                float zgrd = (float)bc_interp(&bc, (double)glon[q], (double)glat[q]);
+                if (ef) zgrd = (float)(-RE * log((RE - (double)zgrd) / RE));
+                if (n == 1) r->bddep[q] = zgrd;
+                if (is_flatten) zgrd = zgrd - r->bddep[q];
+                int kg = ora_x2i(zgrd - dz / 2, c->zbeg, dz);
+                if (kg < kgrd[(size_t)(n - 1) * n2 + q]) kg = kgrd[(size_t)(n - 1) * n2 + q];
+                if (n == 1 && zgrd > 0 && kg < ktopo + 2) kg = ktopo + 2;   /* sea column thickness >= 2 */
+                kgrd[(size_t)n * n2 + q] = kg;
+                if (pid[n - 1] > 0 && pid[n - 1] <= ORA_NBD) r->bddep[(size_t)pid[n - 1] * n2 + q] = zgrd;
+            }
+        free(bc.f);
+    }
+    if (!rc)
+        for (int j = r->jbeg_m; j <= r->jend_m; j++)
+            for (int i = r->ibeg_m; i <= r->iend_m; i++)
+                for (int n = 1; n <= ngrd; n++)
+                    for (int k = kgrd[(size_t)n * n2 + ora_idx2(r, i, j)] + 1; k <= r->kend_m; k++) {
+                        if (k < r->kbeg_m) continue;
+                        const size_t m = ora_idx3(r, k, i, j);
+                        const float cv = Cv[k - r->kbeg_m];
+                        if (with_rmed) { /* m_vmodel_grd_rmed.f90:340-366 */
+                            int kk = k - kgrd[(size_t)reflyr[n - 1] * n2 + ora_idx2(r, i, j)] + 1;   /* relative depth index */
+                            if (kk < r->kbeg_m) kk = kk + c->nz;
+                            if (kk > r->kend_m) kk = kk - r->kend_m;
+                            if (!(vp1[n - 1] < vmax && vs1[n - 1] < vmax)) { snprintf(err, cap, "assert: background velocity exceeds the stability limit (m_vmodel_grd_rmed.f90:342-343)"); rc = -1; goto done; }
+                            if (kk < r->kbeg_m || kk > r->kend_m) { snprintf(err, cap, "vmodel_grd_rmed: relative depth index out of the volume"); rc = -1; goto done; }
+                            const float x = xi[r->ncell_m * (size_t)tbl[n - 1] + ora_idx3(r, kk, i, j)];
+                            float vp2 = cv * vp1[n - 1] * (1.0f + x), vs2 = cv * vs1[n - 1] * (1.0f + x), rho2 = rho1[n - 1] * (1.0f + 0.8f * x);
+                            if (vp1[n - 1] > 0 && vs1[n - 1] > 0) vcheck(&vp2, &vs2, &rho2, x, vmin, vmax, rhomin);
+                            r->rho[m] = rho2;
+                            r->lam[m] = rho2 * (vp2 * vp2 - 2 * vs2 * vs2);
+                            r->mu[m] = rho2 * vs2 * vs2;
+                        } else {
+                            r->rho[m] = rho1[n - 1];
+                            r->lam[m] = rho1[n - 1] * (cv * cv) * (vp1[n - 1] * vp1[n - 1] - 2 * vs1[n - 1] * vs1[n - 1]);
+                            r->mu[m] = rho1[n - 1] * (cv * cv) * vs1[n - 1] * vs1[n - 1];
+                        }
+                        qp[m] = qp1[n - 1];
+                        qs[m] = qs1[n - 1];
+                    }
+done:
+    free(kgrd); free(glon); free(glat); free(Cv); free(xi); free(LR);
+    (void)node_grd;
+    return rc;
+}

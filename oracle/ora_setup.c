@@ -404,17 +404,19 @@ static int medium_setup(ora_sim *s, ora_rank *r, const ora_ini *ini, const char 
         ora_readini_s(ini, "vcut", &c->vcut, 0.0f);
         if (!strcmp(vt, "uni")) vmodel_uni(ini, r, c->vcut, r->taup, r->taus);
         else if (!strcmp(vt, "lhm")) { if (vmodel_lhm(ini, base, r, c->vcut, r->taup, r->taus)) return -1; }
-        else if (!strcmp(vt, "lgm") || !strcmp(vt, "uni_rmed") || !strcmp(vt, "lhm_rmed") || !strcmp(vt, "lgm_rmed")) { /* ora_models.c */
+        else if (!strcmp(vt, "lgm") || !strcmp(vt, "uni_rmed") || !strcmp(vt, "lhm_rmed") || !strcmp(vt, "lgm_rmed") || !strcmp(vt, "grd") || !strcmp(vt, "grd_rmed")) { /* ora_models.c */
             char m[700] = "";
             int rc;
             if (!strcmp(vt, "lgm")) rc = ora_vmodel_lgm(ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
             else if (!strcmp(vt, "uni_rmed")) rc = ora_vmodel_uni_rmed(c, ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
             else if (!strcmp(vt, "lhm_rmed")) rc = ora_vmodel_lhm_rmed(c, ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else if (!strcmp(vt, "grd")) rc = ora_vmodel_grd(c, ini, base, r, c->vcut, r->taup, r->taus, 0, m, sizeof(m));
+            else if (!strcmp(vt, "grd_rmed")) rc = ora_vmodel_grd(c, ini, base, r, c->vcut, r->taup, r->taus, 1, m, sizeof(m));
             else rc = ora_vmodel_lgm_rmed(c, ini, base, r, c->vcut, r->taup, r->taus, m, sizeof(m));
             if (rc) { set_err(m); return -1; }
         } else {
             char m[300];
-            snprintf(m, sizeof(m), "vmodel_type '%s' is not restated (user plug-in, grd / grd_rmed need GMT netCDF-4 grids)", vt);
+            snprintf(m, sizeof(m), "vmodel_type '%s' is not restated ('user' is a compile-time plug-in)", vt);
             set_err(m);
             return -1;
         }

@@ -183,3 +183,41 @@ def write_rmed(path: Path, xi: np.ndarray, dx=0.5) -> None:
         for n in (nx, ny, nz):
             f.write((np.arange(n) * dx).astype(">f4").tobytes())
         f.write(np.ascontiguousarray(xi).astype(">f4").tobytes())
+
+
+def write_grd(path: Path, lon: np.ndarray, lat: np.ndarray, z: np.ndarray, zdtype=">f4") -> None:
+    """A GMT-style 2-D grid in the netCDF classic container (what `gmt grdconvert in.grd out.grd=cf` gives): dimensions x, y,
+    variables x(x), y(y) as doubles and z(y, x).  z has shape (nlat, nlon), depths in metres, positive down."""
+    import struct
+
+    nlat, nlon = z.shape
+
+    def name(s):
+        b = s.encode()
+        return struct.pack(">I", len(b)) + b + b"\0" * (-len(b) % 4)
+
+    ztype = 5 if zdtype == ">f4" else 6
+    zsize = 4 if zdtype == ">f4" else 8
+    dims = struct.pack(">II", 0x0A, 2) + name("x") + struct.pack(">I", nlon) + name("y") + struct.pack(">I", nlat)
+    title = b"synthetic grid"
+    gatts = struct.pack(">II", 0x0C, 1) + name("title") + struct.pack(">II", 2, len(title)) + title + b"\0" * (-len(title) % 4)
+    shapes = [("x", [0], 6, nlon * 8), ("y", [1], 6, nlat * 8), ("z", [1, 0], ztype, nlon * nlat * zsize)]
+
+    def var_list(begins):
+        out = struct.pack(">II", 0x0B, len(shapes))
+        for (n, dimids, ty, nbytes), beg in zip(shapes, begins):
+            out += name(n) + struct.pack(">I", len(dimids)) + b"".join(struct.pack(">I", d) for d in dimids)
+            out += struct.pack(">II", 0, 0) + struct.pack(">III", ty, (nbytes + 3) // 4 * 4, beg)
+        return out
+
+    head = b"CDF\x01" + struct.pack(">I", 0) + dims + gatts
+    off = len(head) + len(var_list([0] * 3))
+    begins = []
+    for _, _, _, nbytes in shapes:
+        begins.append(off)
+        off += (nbytes + 3) // 4 * 4
+    with open(path, "wb") as f:
+        f.write(head + var_list(begins))
+        f.write(np.asarray(lon, dtype=">f8").tobytes())
+        f.write(np.asarray(lat, dtype=">f8").tobytes())
+        f.write(np.ascontiguousarray(z).astype(zdtype).tobytes())

@@ -95,11 +95,11 @@ def test_example_input_header_values():
 
 
 def test_error_behaviour(tmp_path):
-    inf = write_case(tmp_path, nt=10, extra="vmodel_type = 'grd'")
+    inf = write_case(tmp_path, nt=10, extra="vmodel_type = 'user'")
     # the first matching key wins (m_readini.f90:78-92): the case's own vmodel_type line comes first
     Swpc3d(inf, base_dir=tmp_path, nm=3).close()
     bad = tmp_path / "bad.inf"
-    bad.write_text(inf.read_text().replace("vmodel_type = 'lhm'", "vmodel_type = 'grd'"))
+    bad.write_text(inf.read_text().replace("vmodel_type = 'lhm'", "vmodel_type = 'user'"))
     with pytest.raises(Swpc3dHostError, match="vmodel_type"):
         Swpc3d(bad, base_dir=tmp_path, nm=3)
     with pytest.raises(Swpc3dHostError, match="cannot open parameter file"):
