@@ -5,9 +5,10 @@
  * writes the waveform files.  The time loop itself never runs on the CPU.  Citations: file:line under
  * /root/reference/src/swpc_psv.
  *
- * Scope of this build: vmodel_type uni | lhm and benchmark_mode; stf_format {xy,ll}{m0,mw}{ij,dc} and body forces; PML and
- * Cerjan; station products v / u / stress / strain in sac | csf | tar_st | tar_node containers; snapshots (m_snap.f90:
- * xz_ps / xz_v / xz_u, netcdf or native); plane-wave mode (pw_mode).  The grd / rmed / lgm / user models return an error.
+ * Scope of this build: every vmodel_type but the compile-time 'user' plug-in (uni, lhm, lgm, uni_rmed, lhm_rmed, lgm_rmed, grd,
+ * grd_rmed -- random-media sections and GMT grids in the netCDF classic container), benchmark_mode, stabilize_pml;
+ * stf_format {xy,ll}{m0,mw}{ij,dc} and body forces; PML and Cerjan; station products v / u / stress / strain in
+ * sac | csf | tar_st | tar_node containers; snapshots (m_snap.f90: xz_ps / xz_v / xz_u, netcdf or native); plane-wave mode.
  */
 #ifndef SWPCPSV_HOST_H
 #define SWPCPSV_HOST_H

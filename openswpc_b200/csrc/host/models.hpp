@@ -136,6 +136,28 @@ inline int rdrmed3d(const MediumBox &b, const std::string &fn, float *vol) {
     return 0;
 }
 
+// m_rdrmed.f90:19-70 (swpc_psv): the section of tools/gen_rmed2d.f90 (dimensions x, z; 3rd variable, x fastest), periodic in
+// x, wrapped upward for k <= 0 and repeated below its last row.  `b` is a one-plane box (jb == je).
+inline int rdrmed2d(const MediumBox &b, const std::string &fn, float *vol) {
+    ClassicNc nc;
+    std::string err;
+    if (!nc.open(fn, err)) return hfail("rdrmed__2d: " + err);
+    if (nc.dim.size() < 2 || nc.var.size() < 3 || nc.var[2].type != 5)
+        return hfail("rdrmed__2d: " + fn + " needs dimensions x, z and a float section as its 3rd variable (gen_rmed2d.f90:87-123)");
+    const long long nxc = nc.dim[0], nzc = nc.dim[1], beg = nc.var[2].begin;
+    if (beg + 4 * nxc * nzc > (long long)nc.bytes.size()) return hfail("rdrmed__2d: " + fn + " is truncated");
+    auto wrap = [](long long v, long long n) { long long r = v % n; return r <= 0 ? r + n : r; };
+    const int ktop = (int)std::min<long long>(b.ke, nzc);
+#pragma omp parallel for schedule(static)
+    for (int i = b.ib; i <= b.ie; i++) {
+        const long long col = beg + 4 * (wrap(i, nxc) - 1);
+        float *v = vol + b.at(b.kb, i, b.jb);
+        for (int k = b.kb; k <= ktop; k++) v[k - b.kb] = nc.f32(col + 4 * nxc * ((k <= 0 ? k + nzc : k) - 1));
+        for (long long k = nzc + 1; k <= b.ke; k++) v[k - b.kb] = v[wrap(k, nzc) - b.kb];
+    }
+    return 0;
+}
+
 struct LayerTable {
     std::vector<float> depth, rho, vp, vs, qp, qs;
     std::vector<std::string> rmed;
@@ -192,13 +214,15 @@ struct ModelEnv {
     float vcut, dt;
     double dx, dy, dz;
     bool munk, flatten;
+    bool psv = false;   // swpc_psv flavour of the builders: the y axis removed and a few differing expressions (cited at each use)
     // spherical depth / velocity scaling of the earth-flattening transformation (m_vmodel_lgm.f90:64-73)
     void depth(float zc, float &zs, float &cv) const {
         if (flatten) { zs = (float)(R_EARTH - R_EARTH * std::exp(-(double)zc / R_EARTH)); cv = (float)std::exp((double)zc / R_EARTH); }
         else { zs = zc; cv = 1.0f; }
     }
     float rmed_vmax() const {   // cc * dh / dt, m_vmodel_uni_rmed.f90:79-83
-        const float dh = (float)(1.0 / std::sqrt(1.0 / (dx * dx) + 1.0 / (dy * dy) + 1.0 / (dz * dz)));
+        const float dh = psv ? (float)(1.0 / std::sqrt(1.0 / (dx * dx) + 1.0 / (dz * dz)))   // swpc_psv/m_vmodel_uni_rmed.f90:80
+                             : (float)(1.0 / std::sqrt(1.0 / (dx * dx) + 1.0 / (dy * dy) + 1.0 / (dz * dz)));
         return (6.0f / 7.0f) * dh / dt;
     }
 };
@@ -242,8 +266,16 @@ inline bool air_or_ocean(const ModelEnv &e, float zc, float zs, float cv, float 
 }
 
 // linear interpolation inside layer l (m_vmodel_lgm.f90:137-141)
-inline void gradient_at(const LayerTable &t, int l, float zs, float cv, float &rho, float &vp, float &vs, float &qp, float &qs) {
+inline void gradient_at(const LayerTable &t, int l, float zs, float cv, float &rho, float &vp, float &vs, float &qp, float &qs, bool psv_order = false) {
     const float dd = t.depth[l + 1] - t.depth[l], dz = zs - t.depth[l];
+    if (psv_order) {   // swpc_psv/m_vmodel_lgm.f90:128-132 multiplies before it divides: (b - a) * dz / dd
+        rho = t.rho[l] + (t.rho[l + 1] - t.rho[l]) * dz / dd;
+        vp = cv * (t.vp[l] + (t.vp[l + 1] - t.vp[l]) * dz / dd);
+        vs = cv * (t.vs[l] + (t.vs[l + 1] - t.vs[l]) * dz / dd);
+        qp = t.qp[l] + (t.qp[l + 1] - t.qp[l]) * dz / dd;
+        qs = t.qs[l] + (t.qs[l + 1] - t.qs[l]) * dz / dd;
+        return;
+    }
     rho = t.rho[l] + (t.rho[l + 1] - t.rho[l]) / dd * dz;
     vp = cv * (t.vp[l] + (t.vp[l + 1] - t.vp[l]) / dd * dz);
     vs = cv * (t.vs[l] + (t.vs[l + 1] - t.vs[l]) / dd * dz);
@@ -261,10 +293,11 @@ inline int vmodel_lgm(const ModelEnv &e, const MediumBox &b, float &bd0) {
         const float zc = b.zc[k - b.kb];
         float zs, cv, rho, vp, vs, qp, qs;
         e.depth(zc, zs, cv);
-        if (!air_or_ocean(e, zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
+        // swpc_psv/m_vmodel_lgm.f90:110 evaluates the sea-water profile at the spherical depth zs, the 3-D code at zc (:123)
+        if (!air_or_ocean(e, e.psv ? zs : zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
             rho = t.rho[nl - 1]; vp = cv * t.vp[nl - 1]; vs = cv * t.vs[nl - 1]; qp = t.qp[nl - 1]; qs = t.qs[nl - 1];
             for (int l = 0; l + 1 < nl; l++)
-                if (t.depth[l] <= zs && zs < t.depth[l + 1]) { gradient_at(t, l, zs, cv, rho, vp, vs, qp, qs); break; }
+                if (t.depth[l] <= zs && zs < t.depth[l + 1]) { gradient_at(t, l, zs, cv, rho, vp, vs, qp, qs, e.psv); break; }
         }
         pl[(size_t)(k - b.kb)].set(rho, vp, vs, qp, qs);
     }
@@ -288,7 +321,7 @@ inline int read_rmed_set(const ModelEnv &e, const MediumBox &b, const LayerTable
     for (size_t q = 0; q < uniq.size(); q++) {
         xi[q].assign(b.ncell(), 0.0f);
         const std::string path = join_path(e.base, uniq[q]);
-        if (std::ifstream(path).good() && rdrmed3d(b, path, xi[q].data())) return 1;
+        if (std::ifstream(path).good() && (e.psv ? rdrmed2d(b, path, xi[q].data()) : rdrmed3d(b, path, xi[q].data()))) return 1;
     }
     return 0;
 }
@@ -300,7 +333,7 @@ inline int vmodel_uni_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
     const float rhomin = ini.get_s("rhomin", 1.0f), vmin = e.vcut, vmax = e.rmed_vmax();
     std::vector<float> xi(b.ncell(), 0.0f);
     const std::string path = join_path(e.base, ini.get("dir_rmed", "") + "/" + ini.get("fn_rmed0", ""));
-    if (std::ifstream(path).good() && rdrmed3d(b, path, xi.data())) return 1;
+    if (std::ifstream(path).good() && (e.psv ? rdrmed2d(b, path, xi.data()) : rdrmed3d(b, path, xi.data()))) return 1;
     bd0 = topo0;
     std::vector<PlanePlan> pl((size_t)b.nk());
     for (int k = b.kb; k <= b.ke; k++) {
@@ -335,6 +368,7 @@ inline int vmodel_lhm_rmed(const ModelEnv &e, const MediumBox &b, float &bd0) {
         const float zc = b.zc[k - b.kb];
         float zs, cv, rho = 0, vp = 0, vs = 0, qp = 0, qs = 0;
         e.depth(zc, zs, cv);
+        if (e.psv) zs = zc;   // swpc_psv/m_vmodel_lhm_rmed.f90:148-179 tests the grid depth where the 3-D code tests the spherical depth
         if (air_or_ocean(e, zc, zs, cv, t.depth[0], rho, vp, vs, qp, qs)) {
             p.set(rho, vp, vs, qp, qs);
             if (!(zs < 0.0f)) p.lam = 1.0f * vp * vp;   // m_vmodel_lhm_rmed.f90:176-178 writes lam = 1.0 * vp1 * vp1 directly
@@ -401,13 +435,15 @@ inline void stabilize_absorber(const MediumBox &b, const int *kbeg_a /* (i,j) ov
                                int kend, float vmax) {
     const float vmin_pml = vmax * 0.4f;   // V_DYNAMIC_RANGE
     const int LV_THICK = 20;
+    // (a swpc_psv section is a one-plane box: jbeg == jend == b.jb, and its stencil has no y extent, swpc_psv/m_medium.f90:323)
+    const int wy = b.jb == b.je ? 0 : 2, ey = b.jb == b.je ? 0 : 1;
     auto top_of = [&](int i, int j) {
         int k = 1 << 30;
-        for (int jj = j - 2; jj <= j + 2; jj++)
+        for (int jj = j - wy; jj <= j + wy; jj++)
             for (int ii = i - 2; ii <= i + 2; ii++) k = std::min(k, kbeg_a[(size_t)(ii - b.ib) + (size_t)b.ni() * (size_t)(jj - b.jb)]);
         return k;
     };
-    for (int j = jbeg - 1; j <= jend + 1; j++)
+    for (int j = jbeg - ey; j <= jend + ey; j++)
         for (int i = ibeg - 1; i <= iend + 1; i++) {
             for (int k = top_of(i, j); k <= kend; k++) {
                 const size_t n = b.at(k, i, j), m = b.at(k - 1, i, j);
@@ -416,7 +452,12 @@ inline void stabilize_absorber(const MediumBox &b, const int *kbeg_a /* (i,j) ov
                 for (; k2 <= kend; k2++)
                     if (b.lam[b.at(k2, i, j)] > b.lam[b.at(k2 - 1, i, j)] || b.mu[b.at(k2, i, j)] > b.mu[b.at(k2 - 1, i, j)]) break;
                 if (k2 - k <= LV_THICK) {
-                    b.rho[n] = b.rho[m]; b.lam[n] = b.lam[m]; b.mu[n] = b.mu[m]; b.qp[n] = b.qp[m]; b.qs[n] = b.qs[m];
+                    // the 3-D code replaces the top cell of the layer only (swpc_3d/m_medium.f90:299-303), the P-SV code the
+                    // whole layer k .. k2-1 (swpc_psv/m_medium.f90:337-341)
+                    for (int q = k; q <= (wy == 0 ? k2 - 1 : k); q++) {
+                        const size_t nq = b.at(q, i, j);
+                        b.rho[nq] = b.rho[m]; b.lam[nq] = b.lam[m]; b.mu[nq] = b.mu[m]; b.qp[nq] = b.qp[m]; b.qs[nq] = b.qs[m];
+                    }
                     k = k2 - 1;
                 }
             }
@@ -538,10 +579,14 @@ inline int vmodel_grd(const ModelEnv &e, const MediumBox &b, const GrdGeometry &
     const float x_ab = i2x(gg.na + 1, gg.xbeg, fdx), x_ae = i2x(gg.nx - gg.na, gg.xbeg, fdx);
     const float y_ab = i2x(gg.na + 1, gg.ybeg, fdy), y_ae = i2x(gg.ny - gg.na, gg.ybeg, fdy);
     std::vector<float> glon(n2), glat(n2);
-    for (int j = 0; j < nj; j++)
-        for (int i = 0; i < ni; i++)
-            geomap_c2g(std::min(std::max(gg.xc[i], x_ab), x_ae), std::min(std::max(gg.yc[j], y_ab), y_ae), gg.clon, gg.clat, gg.phi, glon[(size_t)i + (size_t)ni * j],
-                       glat[(size_t)i + (size_t)ni * j]);
+    if (e.psv) {   // swpc_psv/m_vmodel_grd.f90:127-129: the section runs along y = 0 and is not clamped to the absorber edge
+        for (int i = 0; i < ni; i++) geomap_c2g(gg.xc[i], 0.0f, gg.clon, gg.clat, gg.phi, glon[(size_t)i], glat[(size_t)i]);
+    } else {
+        for (int j = 0; j < nj; j++)
+            for (int i = 0; i < ni; i++)
+                geomap_c2g(std::min(std::max(gg.xc[i], x_ab), x_ae), std::min(std::max(gg.yc[j], y_ab), y_ae), gg.clon, gg.clat, gg.phi,
+                           glon[(size_t)i + (size_t)ni * j], glat[(size_t)i + (size_t)ni * j]);
+    }
     // layer list (:154-173): 'file' rho vp vs qp qs pid
     struct Layer { std::string fn; float rho, vp, vs, qp, qs; int pid; int reflyr = 0; };
     std::vector<Layer> L;
@@ -570,15 +615,17 @@ inline int vmodel_grd(const ModelEnv &e, const MediumBox &b, const GrdGeometry &
         }
     }
     const int ngrd = (int)L.size();
+    if (ngrd == 0) return hfail("vmodel_grd: no layer in the list " + fn_lst);
     for (int n = ngrd - 2; n >= 0; n--)
-        if ((L[n].vp < e.vcut || L[n].vs < e.vcut) && (L[n].vp > 0 && L[n].vs > 0)) { L[n].vp = L[n + 1].vp; L[n].vs = L[n + 1].vs; L[n].rho = L[n + 1].rho; L[n].qp = L[n + 1].qp; L[n].qs = L[n + 1].qs; }
+        // (swpc_psv/m_vmodel_grd_rmed.f90:185 drops the positivity clause the other three variants have)
+        if ((L[n].vp < e.vcut || L[n].vs < e.vcut) && ((e.psv && with_rmed) || (L[n].vp > 0 && L[n].vs > 0))) { L[n].vp = L[n + 1].vp; L[n].vs = L[n + 1].vs; L[n].rho = L[n + 1].rho; L[n].qp = L[n + 1].qp; L[n].qs = L[n + 1].qs; }
     std::vector<int> tbl;
     std::vector<std::vector<float>> xi;
     const float rhomin = ini.get_s("rhomin", 1.0f), vmin = e.vcut, vmax = e.rmed_vmax();
     if (with_rmed) {
         for (const Layer &y : L) {
             if (!(0 <= y.reflyr && y.reflyr <= ngrd)) return hfail("assert: 0 <= reflyr <= ngrd (m_vmodel_grd_rmed.f90:208)");
-            if (!(y.vp < vmax && y.vs < vmax)) return hfail("assert: background velocity exceeds the stability limit (m_vmodel_grd_rmed.f90:342-343)");
+            if (!e.psv && !(y.vp < vmax && y.vs < vmax)) return hfail("assert: background velocity exceeds the stability limit (m_vmodel_grd_rmed.f90:342-343)");
         }
         if (read_rmed_set(e, b, names, tbl, xi)) return 1;
     }

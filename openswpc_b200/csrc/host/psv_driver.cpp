@@ -6,6 +6,7 @@
 #include "../../../include/swpcpsv_host.h"
 
 #include "common.hpp"
+#include "models.hpp"
 
 struct swpcpsv_host {
     bool benchmark_mode = false;
@@ -53,6 +54,14 @@ struct swpcpsv_host {
     int setup_geometry();
     int setup_medium(const IniFile &ini);
     void surface_detection();
+    bool lateral_model = false;   // the medium varies along x (lgm_rmed excepted, all models.hpp builders)
+    bool stabilize_pending = false;
+    void apply_stabilize() {
+        if (!stabilize_pending) return;
+        stabilize_pending = false;
+        const MediumBox mb{ibeg_m, iend_m, 1, 1, kbeg_m, kend_m, zc.data(), rho.data(), lam.data(), mu.data(), taup.data(), taus.data()};
+        stabilize_absorber(mb, kbeg_a.data(), ibeg, iend, 1, 1, nz, vmax);
+    }
     int setup_source(const IniFile &ini);
     int setup_planewave(const IniFile &ini);
     std::vector<double> pw_init[5];   // plane-wave initial fields Vx Vz Sxx Szz Sxz over the memory box
@@ -146,9 +155,11 @@ int swpcpsv_host::setup_medium(const IniFile &ini) {   // m_medium.f90:36-178
     const size_t nc = (size_t)nzm * nxm;
     rho.assign(nc, 0.f); lam.assign(nc, 0.f); mu.assign(nc, 0.f); taup.assign(nc, 0.f); taus.assign(nc, 0.f);
     bddep.assign((size_t)nxm * (NBD + 1), -9999.0f);
-    // every model of this build is laterally uniform: one depth profile, broadcast over the columns
+    // uni / lhm / benchmark are laterally uniform: one depth profile, broadcast over the columns; the builders of models.hpp
+    // (lgm and the random-media family) fill the section itself (`lateral`)
     std::vector<float> p_rho(nzm), p_lam(nzm), p_mu(nzm), p_qp(nzm), p_qs(nzm);
     float bd0 = 0.0f;
+    bool lateral = false, grd_bddep = false;   // grd: the builder wrote the boundary depths bd(:, 0:NBD) itself
     if (benchmark_mode) {   // :53-72
         fq_min = 0.05f; fq_max = 5.0f; fq_ref = 1.0f;
         for (int q = 0; q < nzm; q++) {
@@ -208,11 +219,71 @@ int swpcpsv_host::setup_medium(const IniFile &ini) {   // m_medium.f90:36-178
                 }
                 p_rho[q] = r1; p_mu[q] = r1 * vs1 * vs1; p_lam[q] = r1 * (vp1 * vp1 - 2 * vs1 * vs1); p_qp[q] = a; p_qs[q] = b;
             }
+        } else if (vmodel_type == "grd" || vmodel_type == "grd_rmed") {
+            // swpc_psv/m_vmodel_grd.f90, m_vmodel_grd_rmed.f90: GMT grids (netCDF classic) sampled along the section y = 0
+            lateral = grd_bddep = true;
+            const MediumBox mb{ibeg_m, iend_m, 1, 1, kbeg_m, kend_m, zc.data(), rho.data(), lam.data(), mu.data(), taup.data(), taus.data()};
+            ModelEnv env{&ini, base, vcut, dt, dx, 0.0, dz, munk, ef};
+            env.psv = true;
+            const GrdGeometry gg{nx, 0, na, xbeg, 0.0f, zbeg, clon, clat, phi, xc.data(), nullptr, bddep.data(), nz};
+            if (vmodel_grd(env, mb, gg, vmodel_type == "grd_rmed")) return 1;
+        } else if (vmodel_type == "lgm" || vmodel_type == "uni_rmed" || vmodel_type == "lhm_rmed" || vmodel_type == "lgm_rmed") {
+            // swpc_psv/m_vmodel_{lgm,uni_rmed,lhm_rmed,lgm_rmed}.f90: the 3-D builders without the y axis (ModelEnv::psv marks
+            // the few expressions that differ); Qp / Qs go to taup / taus, as in the reference's call (m_medium.f90:101-114)
+            lateral = true;
+            const MediumBox mb{ibeg_m, iend_m, 1, 1, kbeg_m, kend_m, zc.data(), rho.data(), lam.data(), mu.data(), taup.data(), taus.data()};
+            ModelEnv env{&ini, base, vcut, dt, dx, 0.0, dz, munk, ef};
+            env.psv = true;
+            const int rc = vmodel_type == "lgm" ? vmodel_lgm(env, mb, bd0) : vmodel_type == "uni_rmed" ? vmodel_uni_rmed(env, mb, bd0)
+                         : vmodel_type == "lhm_rmed" ? vmodel_lhm_rmed(env, mb, bd0) : vmodel_lgm_rmed(env, mb, bd0);
+            if (rc) return 1;
         } else {
-            return hfail("swpc_psv vmodel_type '" + vmodel_type + "' is outside the scope of this build (uni, lhm, benchmark_mode)");
+            return hfail("swpc_psv vmodel_type '" + vmodel_type + "' is outside the scope of this build ('user' is a compile-time plug-in of the reference)");
         }
     }
-    for (int i = 0; i < nxm; i++) bddep[i] = bd0;
+    if (!grd_bddep) for (int i = 0; i < nxm; i++) bddep[i] = bd0;
+    lateral_model = lateral;
+    if (lateral) {
+        // absorber homogenisation (:118-148): the side absorbers repeat the column next to them (when this rank holds it),
+        // the bottom absorber repeats the row k = nz - na
+        const auto copy_col = [&](int dst, int src) {
+            const size_t a = i2(kbeg_m, dst), b = i2(kbeg_m, src);
+            for (std::vector<float> *f : {&rho, &lam, &mu, &taup, &taus}) std::copy(f->begin() + b, f->begin() + b + nzm, f->begin() + a);
+        };
+        if (na + 1 >= ibeg_m && na + 1 <= iend_m) for (int i = ibeg_m; i <= na; i++) copy_col(i, na + 1);
+        if (nx - na >= ibeg_m && nx - na <= iend_m) for (int i = std::max(nx - na + 1, ibeg_m); i <= iend_m; i++) copy_col(i, nx - na);
+        for (int i = ibeg_m; i <= iend_m; i++) {
+            const size_t s0 = i2(nz - na, i);
+            for (int k = nz - na + 1; k <= kend_m; k++) {
+                const size_t n = i2(k, i);
+                rho[n] = rho[s0]; lam[n] = lam[s0]; mu[n] = mu[s0]; taup[n] = taup[s0]; taus[n] = taus[s0];
+            }
+        }
+        relax_times(nm, ts, fq_min, fq_max);   // :151-162
+        zeta = constq_zeta(nm, fq_min, fq_max, ts);
+        const long long ncl = (long long)nc;
+#pragma omp parallel for schedule(static)
+        for (long long n = 0; n < ncl; n++) { taup[n] = nm * zeta / taup[n]; taus[n] = nm * zeta / taus[n]; }
+        if (nm > 0) {   // relaxed_medium :181-204 + visco_chi src/shared/m_fdtool.f90:730-753
+            const float omega = (float)(2 * PI_D * (double)fq_ref);
+            std::complex<float> cc(0.0f, 0.0f);
+            for (int m = 0; m < nm; m++) {
+                const std::complex<double> w = std::complex<double>(0.0, 1.0) * (double)omega * (double)ts[m];
+                const std::complex<double> qd = w / (1.0 - w);
+                cc = cc + std::complex<float>((float)qd.real(), (float)qd.imag());
+            }
+            cc = std::complex<float>(cc.real() / (float)nm, cc.imag() / (float)nm);
+#pragma omp parallel for schedule(static)
+            for (long long n = 0; n < ncl; n++) {
+                const float rb2 = mu[n], ra2 = lam[n] + 2 * mu[n];
+                const std::complex<float> zs_ = 1.0f - cc * taus[n], zp_ = 1.0f - cc * taup[n];
+                const float chi_mu = 1.0f / (1.0f / std::sqrt(zs_)).real();
+                const float chi_lam = 1.0f / (1.0f / std::sqrt(zp_)).real();
+                mu[n] = rb2 / (chi_mu * chi_mu);
+                lam[n] = ra2 / (chi_lam * chi_lam) - 2 * mu[n];
+            }
+        }
+    } else {
     // absorber homogenisation (:118-148): identity in x for laterally uniform input; in z it repeats the value at k = nz-na
     for (int q = nz - na + 1 - kbeg_m; q < nzm; q++) {
         const int s = nz - na - kbeg_m;
@@ -247,6 +318,7 @@ int swpcpsv_host::setup_medium(const IniFile &ini) {   // m_medium.f90:36-178
         std::copy(p_mu.begin(), p_mu.end(), mu.begin() + o); std::copy(p_tp.begin(), p_tp.end(), taup.begin() + o);
         std::copy(p_tsx.begin(), p_tsx.end(), taus.begin() + o);
     }
+    }   // laterally uniform
     surface_detection();
     float vmx = -1.0f, vmn = 1e30f;   // velocity_minmax :294-318 (local part)
     for (int i = ibeg; i <= iend; i++)
@@ -259,7 +331,10 @@ int swpcpsv_host::setup_medium(const IniFile &ini) {   // m_medium.f90:36-178
         }
     vmin_local = vmin = vmn;
     vmax_local = vmax = vmx;
-    if (ini.get_l("stabilize_pml", false)) return hfail("stabilize_pml = .true. is outside the scope of this build");
+    // stabilize_absorber (m_medium.f90:171-174, :309-366) needs the GLOBAL vmax: applied here for a single-rank run, otherwise
+    // when the caller hands over the reduced values (swpcpsv_host_set_minmax) or, at the latest, before the upload
+    stabilize_pending = ini.get_l("stabilize_pml", false);
+    if (stabilize_pending && nproc_x == 1) apply_stabilize();
     d2 = 0.0f;   // kernel__setup m_kernel.f90:57-66 (the device computes its own copy; kept for reporting)
     if (nm > 0) {
         float sum = 0.0f;
@@ -314,10 +389,17 @@ int swpcpsv_host::setup_planewave(const IniFile &ini) {
             }
             pw_init[0][n] = vx; pw_init[1][n] = vz; pw_init[2][n] = sxx; pw_init[3][n] = szz; pw_init[4][n] = sxz;
         }
-    // wavelength condition :764-783: the velocity at the model's centre column, MPI_MAX over the ranks.  The models of this
-    // host (uni, lhm) are laterally uniform, so every rank evaluates it on a column of its own
+    // wavelength condition :764-783: the velocity at the model's centre column, MPI_MAX over the ranks.  A laterally uniform
+    // model lets every rank evaluate it on a column of its own; otherwise only the rank holding that column can
     const int kc = x2i(pw_ztop, zbeg, (float)dz);
-    fcut = speed(i2(kc, ibeg)) / pw_zlen;
+    int ic = ibeg;
+    if (lateral_model) {
+        ic = x2i((xbeg + xend) / 2, xbeg, (float)dx);
+        if (!(ibeg <= ic && ic <= iend))
+            return hfail("pw_mode with a laterally varying vmodel_type on several ranks: fcut comes from the rank holding the centre column "
+                         "(m_source.f90:765-781); run this host on one rank or use a 1-D model");
+    }
+    fcut = speed(i2(kc, ic)) / pw_zlen;
     fmax = fcut * 2.0f;
     return 0;
 }
@@ -713,6 +795,7 @@ int swpcpsv_host_get_double(swpcpsv_host *h, const char *name, double *v) {
 int swpcpsv_host_set_minmax(swpcpsv_host *h, float vmin, float vmax) {
     if (!h) return hfail("null handle");
     h->vmin = vmin; h->vmax = vmax;
+    h->apply_stabilize();
     return 0;
 }
 int swpcpsv_host_set_exedate(swpcpsv_host *h, int32_t exedate, int32_t tz) {
@@ -749,6 +832,7 @@ int swpcpsv_host_station_name(swpcpsv_host *h, int32_t i, char *buf9) {
 int swpcpsv_host_attach_device(swpcpsv_host *h, int32_t device) {   // main.f90:80-93
     if (!h) return hfail("null handle");
     if (h->dev) { swpcpsv_destroy(h->dev); h->dev = nullptr; }
+    h->apply_stabilize();
     swpcpsv_grid g{};
     g.nx = h->nx; g.nz = h->nz; g.nproc_x = h->nproc_x; g.myid = h->myid; g.ibeg = h->ibeg; g.iend = h->iend; g.ipad = h->ipad; g.kpad = h->kpad;
     g.ibeg_k = h->ibeg_k; g.iend_k = h->iend_k; g.kend_k = h->kend_k; g.na = h->na; g.nm = h->nm;

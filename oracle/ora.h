@@ -148,6 +148,7 @@ typedef struct {
     /* medium */
     float *rho, *lam, *mu, *taup, *taus;
     int *kfs, *kob, *kfs_top, *kfs_bot, *kob_top, *kob_bot, *kbeg_a;   /* (i,j) over _m */
+    int psv;                      /* 1: a swpc_psv section seen as a one-plane rank by the model builders (ora_models.c) */
     float *bddep;                 /* (i,j,0:NBD) */
     float *xc, *yc, *zc;
     /* PML */
@@ -223,6 +224,7 @@ static inline size_t ora_idx2(const ora_rank *r, int i, int j) {
 }
 
 /* ---------------------------------------------------------------- heavier model builders (ora_models.c) */
+int ora_rdrmed2d(int ib, int ie, int kb, int ke, const char *fn, float *vol, char *err, size_t cap);
 int ora_rdrmed3d(int ib, int ie, int jb, int je, int kb, int ke, const char *fn, float *vol, char *err, size_t cap);
 int ora_vmodel_lgm(const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);
 int ora_vmodel_uni_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, ora_rank *r, float vcut, float *qp, float *qs, char *err, size_t cap);

@@ -170,6 +170,50 @@ int ora_rdrmed3d(int ib, int ie, int jb, int je, int kb, int ke, const char *fn,
     return 0;
 }
 
+/* m_rdrmed.f90:19-70 (swpc_psv).  vol is (kb:ke, ib:ie), k fastest; the file of tools/gen_rmed2d.f90:87-123 has dimensions
+ * x, z and the section as its 3rd variable, x fastest. */
+int ora_rdrmed2d(int ib, int ie, int kb, int ke, const char *fn, float *vol, char *err, size_t cap) {
+    nc_file *f = nc_open_classic(fn, err, cap);
+    if (!f) return -1;
+    if (f->ndims < 2 || f->nvars < 3 || f->var[2].type != 5 /* NC_FLOAT */) {
+        nc_close(f);
+        snprintf(err, cap, "%s: expected dimensions x,z and a 3rd variable of type float (gen_rmed2d.f90:87-123)", fn);
+        return -1;
+    }
+    const long long nxc = f->dimlen[0], nzc = f->dimlen[1];
+    const long long begin = f->var[2].begin;
+    if (begin + nxc * nzc * 4 > (long long)f->len) { nc_close(f); snprintf(err, cap, "%s: truncated section", fn); return -1; }
+    const int nk = ke - kb + 1;
+#define VOL(k, i) vol[(size_t)((k) - kb) + (size_t)nk * (size_t)((i) - ib)]
+    const int ktop = ke < nzc ? ke : (int)nzc;
+    for (int k = kb; k <= ktop; k++) {
+        const long long kk = k <= 0 ? k + nzc : k;
+        const unsigned char *hh = f->buf + begin + (kk - 1) * nxc * 4;
+        for (int i = ib; i <= ie; i++) {
+            long long ii = i % nxc;
+            if (ii <= 0) ii += nxc;
+            unsigned u = (unsigned)be_u(hh + (ii - 1) * 4, 4);
+            float v;
+            memcpy(&v, &u, 4);
+            VOL(k, i) = v;
+        }
+    }
+    for (long long k = nzc + 1; k <= ke; k++) { /* bottom cyclic part :64-68 (here with the kk <= 0 wrap the 3-D reader lacks) */
+        long long kk = k % nzc;
+        if (kk <= 0) kk += nzc;
+        for (int i = ib; i <= ie; i++) VOL(k, i) = VOL(kk, i);
+    }
+#undef VOL
+    nc_close(f);
+    return 0;
+}
+
+/* one random-media volume over the memory box of r: the 3-D reader, or the section reader for a swpc_psv rank */
+static int read_volume(const ora_rank *r, const char *path, float *xi, char *err, size_t cap) {
+    if (r->psv) return ora_rdrmed2d(r->ibeg_m, r->iend_m, r->kbeg_m, r->kend_m, path, xi, err, cap);
+    return ora_rdrmed3d(r->ibeg_m, r->iend_m, r->jbeg_m, r->jend_m, r->kbeg_m, r->kend_m, path, xi, err, cap);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 static int is_blank(const char *s) {
     while (*s) {
@@ -281,12 +325,21 @@ int ora_vmodel_lgm(const ora_ini *ini, const char *base, ora_rank *r, float vcut
         const float zc = r->zc[k - r->kbeg_m];
         if (zs < L->depth[0]) {
             if (zs < 0.0f) { rho1 = 0.001f; vp1 = 0.0f; vs1 = 0.0f; qp1 = 10.0f; qs1 = 10.0f; }
-            else { rho1 = 1.0f; vp1 = Cv * ora_seawater_vel(zc, use_munk); vs1 = 0.0f; qp1 = 1000000.0f; qs1 = 1000000.0f; }
+            /* swpc_psv/m_vmodel_lgm.f90:110 evaluates the sea-water profile at the spherical depth zs, the 3-D code at zc (:123) */
+            else { rho1 = 1.0f; vp1 = Cv * ora_seawater_vel(r->psv ? zs : zc, use_munk); vs1 = 0.0f; qp1 = 1000000.0f; qs1 = 1000000.0f; }
         } else {
             rho1 = L->rho0[nl - 1]; vp1 = Cv * L->vp0[nl - 1]; vs1 = Cv * L->vs0[nl - 1]; qp1 = L->qp0[nl - 1]; qs1 = L->qs0[nl - 1];
             for (int l = 0; l < nl - 1; l++)
                 if (L->depth[l] <= zs && zs < L->depth[l + 1]) {
                     const float dd = L->depth[l + 1] - L->depth[l], dz = zs - L->depth[l];
+                    if (r->psv) { /* swpc_psv/m_vmodel_lgm.f90:128-132: (b - a) * dz / dd, not (b - a) / dd * dz */
+                        rho1 = L->rho0[l] + (L->rho0[l + 1] - L->rho0[l]) * dz / dd;
+                        vp1 = Cv * (L->vp0[l] + (L->vp0[l + 1] - L->vp0[l]) * dz / dd);
+                        vs1 = Cv * (L->vs0[l] + (L->vs0[l + 1] - L->vs0[l]) * dz / dd);
+                        qp1 = L->qp0[l] + (L->qp0[l + 1] - L->qp0[l]) * dz / dd;
+                        qs1 = L->qs0[l] + (L->qs0[l + 1] - L->qs0[l]) * dz / dd;
+                        break;
+                    }
                     rho1 = L->rho0[l] + (L->rho0[l + 1] - L->rho0[l]) / dd * dz;
                     vp1 = Cv * (L->vp0[l] + (L->vp0[l + 1] - L->vp0[l]) / dd * dz);
                     vs1 = Cv * (L->vs0[l] + (L->vs0[l + 1] - L->vs0[l]) / dd * dz);
@@ -321,7 +374,9 @@ static void vcheck(float *vp, float *vs, float *rho, float xi, float vmin, float
 
 /* vmax of the random-media models: cc * dh / dt, m_vmodel_uni_rmed.f90:79-83 (dx, dy, dz are real(MP)) */
 static float rmed_vmax(const ora_cfg *c) {
-    const float dh = (float)(1.0 / sqrt(1.0 / (c->dx * c->dx) + 1.0 / (c->dy * c->dy) + 1.0 / (c->dz * c->dz)));
+    /* swpc_psv (ny = 0 in the cfg the P-SV oracle builds): dh = 1 / sqrt(1/dx**2 + 1/dz**2), swpc_psv/m_vmodel_uni_rmed.f90:80 */
+    const float dh = c->ny == 0 ? (float)(1.0 / sqrt(1.0 / (c->dx * c->dx) + 1.0 / (c->dz * c->dz)))
+                                : (float)(1.0 / sqrt(1.0 / (c->dx * c->dx) + 1.0 / (c->dy * c->dy) + 1.0 / (c->dz * c->dz)));
     const float cc = 6.0f / 7.0f;
     return cc * dh / c->dt;
 }
@@ -353,7 +408,7 @@ int ora_vmodel_uni_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, 
     snprintf(rel, sizeof(rel), "%s/%s", dir, fn);
     join(base, rel, path, sizeof(path));
     float *xi = (float *)calloc(r->ncell_m, sizeof(float));
-    if (file_exists(path) && ora_rdrmed3d(r->ibeg_m, r->iend_m, r->jbeg_m, r->jend_m, r->kbeg_m, r->kend_m, path, xi, err, cap)) { free(xi); return -1; }
+    if (file_exists(path) && read_volume(r, path, xi, err, cap)) { free(xi); return -1; }
     for (int j = r->jbeg_m; j <= r->jend_m; j++)
         for (int i = r->ibeg_m; i <= r->iend_m; i++)
             for (int k = r->kbeg_m; k <= r->kend_m; k++) {
@@ -410,7 +465,7 @@ static int read_rmed_set(const ora_ini *ini, const char *base, const layers *L, 
     for (int q = 0; q < nind; q++) {
         char path[3 * ORA_STRLEN];
         join(base, uniq[q], path, sizeof(path));
-        if (file_exists(path) && ora_rdrmed3d(r->ibeg_m, r->iend_m, r->jbeg_m, r->jend_m, r->kbeg_m, r->kend_m, path, xi + r->ncell_m * (size_t)q, err, cap)) {
+        if (file_exists(path) && read_volume(r, path, xi + r->ncell_m * (size_t)q, err, cap)) {
             free(xi);
             free(uniq);
             return -1;
@@ -441,6 +496,8 @@ int ora_vmodel_lhm_rmed(const ora_cfg *c, const ora_ini *ini, const char *base, 
         float zs, Cv;
         zs_cv(r, ef, k, &zs, &Cv);
         const float zc = r->zc[k - r->kbeg_m];
+        /* swpc_psv/m_vmodel_lhm_rmed.f90:148-179 tests the grid depth zc where the 3-D code tests the spherical depth zs */
+        if (r->psv) zs = zc;
         if (zs < L->depth[0]) {
             if (zs < 0.0f) {
                 for (int j = r->jbeg_m; j <= r->jend_m; j++)
@@ -723,6 +780,10 @@ int ora_vmodel_grd(const ora_cfg *c, const ora_ini *ini, const char *base, ora_r
     float *glon = (float *)malloc(sizeof(float) * n2), *glat = (float *)malloc(sizeof(float) * n2);
     for (int j = r->jbeg_m; j <= r->jend_m; j++)
         for (int i = r->ibeg_m; i <= r->iend_m; i++) {
+            if (r->psv) { /* swpc_psv/m_vmodel_grd.f90:127-129: the section runs along y = 0 and is not clamped to the absorber edge */
+                ora_geomap_c2g(r->xc[i - r->ibeg_m], 0.0f, c->clon, c->clat, c->phi, &glon[ora_idx2(r, i, j)], &glat[ora_idx2(r, i, j)]);
+                continue;
+            }
             const float xc = r->xc[i - r->ibeg_m], yc = r->yc[j - r->jbeg_m];
             const float xx = fminf(fmaxf(xc, x_AB), x_AE), yy = fminf(fmaxf(yc, y_AB), y_AE);
             ora_geomap_c2g(xx, yy, c->clon, c->clat, c->phi, &glon[ora_idx2(r, i, j)], &glat[ora_idx2(r, i, j)]);
@@ -757,8 +818,12 @@ int ora_vmodel_grd(const ora_cfg *c, const ora_ini *ini, const char *base, ora_r
         ngrd++;
     }
     fclose(fp);
-    for (int n = ngrd - 2; n >= 0; n--)
-        if ((vp1[n] < vcut || vs1[n] < vcut) && (vp1[n] > 0 && vs1[n] > 0)) { vp1[n] = vp1[n + 1]; vs1[n] = vs1[n + 1]; rho1[n] = rho1[n + 1]; qp1[n] = qp1[n + 1]; qs1[n] = qs1[n + 1]; }
+    if (ngrd == 0) { snprintf(err, cap, "vmodel_grd: no layer in the list %s", path); free(LR); free(Cv); free(glon); free(glat); return -1; }
+    for (int n = ngrd - 2; n >= 0; n--) {
+        /* swpc_psv/m_vmodel_grd_rmed.f90:185 drops the "(vp1 > 0 .and. vs1 > 0)" clause the other three variants have */
+        const int positive = (r->psv && with_rmed) ? 1 : (vp1[n] > 0 && vs1[n] > 0);
+        if ((vp1[n] < vcut || vs1[n] < vcut) && positive) { vp1[n] = vp1[n + 1]; vs1[n] = vs1[n + 1]; rho1[n] = rho1[n + 1]; qp1[n] = qp1[n + 1]; qs1[n] = qs1[n + 1]; }
+    }
     int tbl[64];
     float *xi = NULL, rhomin = 1.0f;
     const float vmin = vcut, vmax = rmed_vmax(c);
@@ -818,7 +883,7 @@ int ora_vmodel_grd(const ora_cfg *c, const ora_ini *ini, const char *base, ora_r
                             int kk = k - kgrd[(size_t)reflyr[n - 1] * n2 + ora_idx2(r, i, j)] + 1;   /* relative depth index */
                             if (kk < r->kbeg_m) kk = kk + c->nz;
                             if (kk > r->kend_m) kk = kk - r->kend_m;
-                            if (!(vp1[n - 1] < vmax && vs1[n - 1] < vmax)) { snprintf(err, cap, "assert: background velocity exceeds the stability limit (m_vmodel_grd_rmed.f90:342-343)"); rc = -1; goto done; }
+                            if (!r->psv && !(vp1[n - 1] < vmax && vs1[n - 1] < vmax)) { /* (no such assertion in swpc_psv) */ snprintf(err, cap, "assert: background velocity exceeds the stability limit (m_vmodel_grd_rmed.f90:342-343)"); rc = -1; goto done; }
                             if (kk < r->kbeg_m || kk > r->kend_m) { snprintf(err, cap, "vmodel_grd_rmed: relative depth index out of the volume"); rc = -1; goto done; }
                             const float x = xi[r->ncell_m * (size_t)tbl[n - 1] + ora_idx3(r, kk, i, j)];
                             float vp2 = cv * vp1[n - 1] * (1.0f + x), vs2 = cv * vs1[n - 1] * (1.0f + x), rho2 = rho1[n - 1] * (1.0f + 0.8f * x);

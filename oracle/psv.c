@@ -12,9 +12,9 @@
  * Every temporary keeps its declared kind (real(SP) -> float, real(MP) -> ora_mp) and every expression the reference's
  * association; built with -ffp-contract=off and no fast-math.  PARITY UNPINNED: the reference holds no swpc_psv output.
  *
- * Scope: vmodel_type uni | lhm (+ benchmark_mode), all moment / body-force source formats of m_source.f90 except the
+ * Scope: every vmodel_type but the compile-time 'user' plug-in (uni, lhm here; lgm, *_rmed, grd, grd_rmed through the `psv`
+ * branches of ora_models.c), benchmark_mode, stabilize_pml, all moment / body-force source formats of m_source.f90 except the
  * slip-based ones, PML and Cerjan absorbers, station products v / u / stress / strain, SAC files, plane-wave mode, snapshots.
- * The grd / rmed / lgm / user models are outside this restatement and raise an error.
  */
 #include "psv.h"
 
@@ -381,7 +381,29 @@ static int medium_setup(psv_sim *s, psv_rank *r, const ora_ini *ini, const char 
         ora_readini_s(ini, "vcut", &c->vcut, 0.0f);
         if (!strcmp(vt, "uni")) vmodel_uni(ini, r, r->taup, r->taus);
         else if (!strcmp(vt, "lhm")) { if (vmodel_lhm(ini, base, r, c->vcut, r->taup, r->taus)) return -1; }
-        else { char m[400]; snprintf(m, sizeof(m), "swpc_psv vmodel_type '%s' is outside the restated scope (uni, lhm, benchmark)", vt); set_err(m); return -1; }
+        else if (!strcmp(vt, "lgm") || !strcmp(vt, "uni_rmed") || !strcmp(vt, "lhm_rmed") || !strcmp(vt, "lgm_rmed") || !strcmp(vt, "grd") || !strcmp(vt, "grd_rmed")) {
+            /* swpc_psv/m_vmodel_{lgm,uni_rmed,lhm_rmed,lgm_rmed}.f90 are the 3-D builders with the y axis removed and a handful
+             * of differing expressions (ora_models.c, the `psv` branches): run them on a one-plane view of this section */
+            ora_cfg c3;
+            ora_rank r3;
+            memset(&c3, 0, sizeof(c3));
+            memset(&r3, 0, sizeof(r3));
+            c3.nx = c->nx; c3.ny = 0; c3.nz = c->nz; c3.dx = c->dx; c3.dy = c->dx; c3.dz = c->dz; c3.dt = c->dt; c3.na = c->na;
+            c3.xbeg = c->xbeg; c3.zbeg = c->zbeg; c3.clon = c->clon; c3.clat = c->clat; c3.phi = c->phi;
+            r3.psv = 1;
+            r3.ibeg_m = r->ibeg_m; r3.iend_m = r->iend_m; r3.jbeg_m = 1; r3.jend_m = 1; r3.kbeg_m = r->kbeg_m; r3.kend_m = r->kend_m;
+            r3.nzm = r->nzm; r3.nxm = r->nxm; r3.nym = 1; r3.ncell_m = r->ncell;
+            r3.rho = r->rho; r3.lam = r->lam; r3.mu = r->mu; r3.bddep = r->bddep; r3.zc = r->zc; r3.xc = r->xc;
+            char m[600] = "";
+            int rc;
+            if (!strcmp(vt, "lgm")) rc = ora_vmodel_lgm(ini, base, &r3, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else if (!strcmp(vt, "uni_rmed")) rc = ora_vmodel_uni_rmed(&c3, ini, base, &r3, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else if (!strcmp(vt, "lhm_rmed")) rc = ora_vmodel_lhm_rmed(&c3, ini, base, &r3, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else if (!strcmp(vt, "lgm_rmed")) rc = ora_vmodel_lgm_rmed(&c3, ini, base, &r3, c->vcut, r->taup, r->taus, m, sizeof(m));
+            else rc = ora_vmodel_grd(&c3, ini, base, &r3, c->vcut, r->taup, r->taus, !strcmp(vt, "grd_rmed"), m, sizeof(m));
+            if (rc) { set_err(m); return -1; }
+        }
+        else { char m[400]; snprintf(m, sizeof(m), "swpc_psv vmodel_type '%s' is outside the restated scope (everything but the compile-time 'user' plug-in)", vt); set_err(m); return -1; }
     }
 #define CP5(dst, src) do { r->rho[dst] = r->rho[src]; r->lam[dst] = r->lam[src]; r->mu[dst] = r->mu[src]; \
                            r->taup[dst] = r->taup[src]; r->taus[dst] = r->taus[src]; } while (0)
@@ -428,10 +450,49 @@ static int medium_setup(psv_sim *s, psv_rank *r, const ora_ini *ini, const char 
             if (vs < vmn) vmn = vs;
         }
     *vmin1 = vmn; *vmax1 = vmx;
-    int stab;
-    ora_readini_l(ini, "stabilize_pml", &stab, 0);
-    if (stab) { set_err("stabilize_pml=.true. is outside the restated scope"); return -1; }
     return 0;
+}
+
+/* m_medium.f90:309-366 stabilize_absorber, called after velocity_minmax's all-reduce (:169-174): vmax is the global maximum */
+static void stabilize_absorber(const psv_cfg *c, psv_rank *r) {
+    const float vmin_pml = c->vmax * 0.4f;   /* V_DYNAMIC_RANGE */
+    const int LV_THICK = 20;
+    for (int i = r->ibeg - 1; i <= r->iend + 1; i++) {
+        int ktop = 1 << 30;
+        for (int ii = i - 2; ii <= i + 2; ii++) if (r->kbeg_a[ii - r->ibeg_m] < ktop) ktop = r->kbeg_a[ii - r->ibeg_m];
+        int k = ktop;
+        while (k <= r->kend) {
+            if (r->lam[IX(r, k, i)] < r->lam[IX(r, k - 1, i)] || r->mu[IX(r, k, i)] < r->mu[IX(r, k - 1, i)]) {
+                int k2;
+                for (k2 = k + 1; k2 <= r->kend; k2++)   /* the bottom of the low-velocity layer */
+                    if (r->lam[IX(r, k2, i)] > r->lam[IX(r, k2 - 1, i)] || r->mu[IX(r, k2, i)] > r->mu[IX(r, k2 - 1, i)]) break;
+                if (k2 - k <= LV_THICK) {
+                    const size_t m = IX(r, k - 1, i);
+                    for (int q = k; q <= k2 - 1; q++) {
+                        const size_t n = IX(r, q, i);
+                        r->rho[n] = r->rho[m]; r->lam[n] = r->lam[m]; r->mu[n] = r->mu[m]; r->taup[n] = r->taup[m]; r->taus[n] = r->taus[m];
+                    }
+                    k = k2 - 1;
+                }
+            }
+            k = k + 1;
+        }
+    }
+    for (int i = r->ibeg - 1; i <= r->iend + 1; i++) {
+        int ktop = 1 << 30;
+        for (int ii = i - 2; ii <= i + 2; ii++) if (r->kbeg_a[ii - r->ibeg_m] < ktop) ktop = r->kbeg_a[ii - r->ibeg_m];
+        for (int k = ktop; k <= r->kend; k++) {
+            const size_t n = IX(r, k, i);
+            float vs = sqrtf(r->mu[n] / r->rho[n]);
+            if (vs < FLT_EPS) continue;
+            if (vs < vmin_pml) {
+                vs = vmin_pml;
+                const float vp = vs * sqrtf(3.0f);
+                r->lam[n] = r->rho[n] * (vp * vp - 2 * (vs * vs));
+                r->mu[n] = r->rho[n] * (vs * vs);
+            }
+        }
+    }
 }
 
 /* m_kernel.f90:30-74 + memory_allocate :329-343 */
@@ -951,6 +1012,9 @@ static psv_sim *create_from_ini(ora_ini *ini, const char *base, int nm, int npx,
         if (b > vmax) vmax = b;
     }
     c->vmin = vmin; c->vmax = vmax;
+    int stab;
+    ora_readini_l(ini, "stabilize_pml", &stab, 0);
+    if (stab) for (int q = 0; q < s->nranks; q++) stabilize_absorber(c, &s->r[q]);
     kernel_setup(s);
     if (source_setup(s, ini, base) || absorb_setup(s) || wav_setup(s, ini, base)) { psv_destroy(s); return NULL; }
     ora_readini_i(ini, "ntdec_r", &c->ntdec_r, 10);

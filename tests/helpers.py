@@ -185,6 +185,46 @@ def write_rmed(path: Path, xi: np.ndarray, dx=0.5) -> None:
         f.write(np.ascontiguousarray(xi).astype(">f4").tobytes())
 
 
+def write_rmed2d(path: Path, xi: np.ndarray, dx=0.5) -> None:
+    """A random-media section as tools/gen_rmed2d.f90:87-123 creates it: netCDF classic, dimensions x, z, variables x, z and --
+    3rd, which is how rdrmed__2d (m_rdrmed.f90:38) finds it -- the section with x fastest.  xi has shape (nz, nx)."""
+    import struct
+
+    nz, nx = xi.shape
+
+    def name(s):
+        b = s.encode()
+        return struct.pack(">I", len(b)) + b + b"\0" * (-len(b) % 4)
+
+    def att_text(k, v):
+        b = v.encode()
+        return name(k) + struct.pack(">II", 2, len(b)) + b + b"\0" * (-len(b) % 4)
+
+    dims = struct.pack(">II", 0x0A, 2) + b"".join(name(n) + struct.pack(">I", m) for n, m in (("x", nx), ("z", nz)))
+    gatts = struct.pack(">II", 0x0C, 1) + att_text("title", "random media")
+    shapes = [("x", [0], nx), ("z", [1], nz), ("random media", [1, 0], nx * nz)]
+
+    def var_list(begins):
+        out = struct.pack(">II", 0x0B, len(shapes))
+        for (n, dimids, cnt), beg in zip(shapes, begins):
+            out += name(n) + struct.pack(">I", len(dimids)) + b"".join(struct.pack(">I", d) for d in dimids)
+            out += struct.pack(">II", 0x0C, 1) + att_text("long_name", n)     # one attribute per variable, as the tool writes
+            out += struct.pack(">III", 5, cnt * 4, beg)
+        return out
+
+    head = b"CDF\x01" + struct.pack(">I", 0) + dims + gatts
+    off = len(head) + len(var_list([0] * 3))
+    begins = []
+    for _, _, cnt in shapes:
+        begins.append(off)
+        off += cnt * 4
+    with open(path, "wb") as f:
+        f.write(head + var_list(begins))
+        for n in (nx, nz):
+            f.write((np.arange(n) * dx).astype(">f4").tobytes())
+        f.write(np.ascontiguousarray(xi).astype(">f4").tobytes())
+
+
 def write_grd(path: Path, lon: np.ndarray, lat: np.ndarray, z: np.ndarray, zdtype=">f4") -> None:
     """A GMT-style 2-D grid in the netCDF classic container (what `gmt grdconvert in.grd out.grd=cf` gives): dimensions x, y,
     variables x(x), y(y) as doubles and z(y, x).  z has shape (nlat, nlon), depths in metres, positive down."""
