@@ -184,17 +184,32 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _omp_threads(n: int) -> int:
+    """Set the OpenMP thread count of the libgomp the in-tree libraries link against; returns what is in force."""
+    import ctypes
+
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
+
+
 def cpu_port_throughput(nm: int, sample=(384, 384, 384), steps: int = 24, warmup: int = 1) -> dict:
     """The reference's CPU path (oracle port, OpenMP over all host cores) on a bounded sample of the workload."""
     sys.path.insert(0, str(ROOT / "tests"))
     from oracle_lib import Oracle   # the one place outside tests/ that may execute oracle/: the CPU baseline
 
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # all the host cores this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which must not throttle
+    # the CPU arm (rank 0 runs it alone); SWPC_BENCH_CPU_THREADS overrides
+    cores = int(os.environ.get("SWPC_BENCH_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     with tempfile.TemporaryDirectory() as td:
         nx, ny, nz = sample
         inf = write_workload(Path(td), nx, ny, nz, steps + warmup, 1, 1)
         o = Oracle(inf, base_dir=td, nm=nm)
+        cores = _omp_threads(cores)   # libgomp may have read the environment before this function ran
         for it in range(1, warmup + 1):
             o.step(it)
         t0 = time.perf_counter()
@@ -268,8 +283,9 @@ def main():
     from openswpc_b200.swpc3d import Swpc3d
 
     # host-side setup is OpenMP code: share the box's cores between the ranks instead of oversubscribing them
-    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+    # (torchrun exports OMP_NUM_THREADS=1 to its workers: set the count on the runtime itself)
     _lib.load()
+    _omp_threads(int(os.environ.get("SWPC_BENCH_SETUP_THREADS", "0")) or max(1, len(os.sched_getaffinity(0)) // world))
     init_process_group("nccl" if world > 1 else None)
     import torch.distributed as dist
 

@@ -42,6 +42,7 @@ module m_swpc3d_b200
     public :: swpc3d_set_wav_products, swpc3d_get_wav_product, swpc3d_set_option
     public :: swpc3d_snap_cfg, swpc3d_snap_setup, swpc3d_snap_step, swpc3d_snap_fetch, swpc3d_snap_fetch_max, swpc3d_reduce_sum
     public :: swpc3d_set_green, swpc3d_green_store, swpc3d_green_source, swpc3d_get_green, swpc3d_advance
+    public :: swpc3d_version, swpc3d_zero_state, swpc3d_run, swpc3d_timer_start, swpc3d_timer_stop, swpc3d_get_info, swpc3d_comm_local
     public :: swpc3d_check
 
     !! mirrors `swpc3d_snap_cfg` of include/swpc3d_b200.h: the integers snap__setup computes (m_snap.f90:116-154)
@@ -278,6 +279,43 @@ module m_swpc3d_b200
             type(c_ptr), value :: h
             character(kind=c_char), intent(in) :: key(*)
             integer(c_int32_t), value :: value
+        end function
+
+        !! ---- the rest of the C ABI: run loop, stopwatch (m_pwatch replacement), introspection, test hooks
+        function swpc3d_version() bind(c, name='swpc3d_version') result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+        integer(c_int) function swpc3d_zero_state(h) bind(c, name='swpc3d_zero_state')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        !! it0 .. it1 iterations of swpc3d_step without a host round trip
+        integer(c_int) function swpc3d_run(h, it0, it1) bind(c, name='swpc3d_run')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it0, it1
+        end function
+        integer(c_int) function swpc3d_timer_start(h) bind(c, name='swpc3d_timer_start')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpc3d_timer_stop(h, ms) bind(c, name='swpc3d_timer_stop')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(out) :: ms
+        end function
+        integer(c_int) function swpc3d_get_info(h, key, value) bind(c, name='swpc3d_get_info')
+            import :: c_int, c_double, c_char, c_ptr
+            type(c_ptr), value :: h
+            character(kind=c_char), intent(in) :: key(*)      !! "launches", "ms_stress", "ms_vel", ... (NUL-terminated)
+            real(c_double), intent(out) :: value
+        end function
+        !! several ranks living on one GPU (tests): handles(n) ordered by myid; which = 0 stress, 1 velocity
+        integer(c_int) function swpc3d_comm_local(handles, n, which) bind(c, name='swpc3d_comm_local')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), intent(in) :: handles(*)
+            integer(c_int32_t), value :: n, which
         end function
 
     end interface

@@ -44,6 +44,7 @@ module m_swpcpsv_b200
     public :: swpcpsv_update_stress, swpcpsv_stressglut, swpcpsv_comm_stress, swpcpsv_update_vel, swpcpsv_comm_vel
     public :: swpcpsv_wav_store, swpcpsv_step, swpcpsv_sync, swpcpsv_vmax, swpcpsv_vmax_global
     public :: swpcpsv_snap_setup, swpcpsv_snap_step, swpcpsv_snap_fetch, swpcpsv_reduce_sum
+    public :: swpcpsv_version, swpcpsv_zero_state, swpcpsv_run, swpcpsv_timer_start, swpcpsv_timer_stop, swpcpsv_get_info, swpcpsv_comm_local, swpcpsv_download_memvars
     public :: swpcpsv_nccl_unique_id, swpcpsv_comm_init, swpcpsv_set_option, swpcpsv_check
 
     interface
@@ -208,6 +209,48 @@ module m_swpcpsv_b200
             type(c_ptr), value :: h
             character(kind=c_char), intent(in) :: key(*)      !! "pw_mode", "tk", "ilen", "pf", ...
             integer(c_int32_t), value :: value
+        end function
+
+        !! ---- the rest of the C ABI: run loop, stopwatch (m_pwatch replacement), introspection, test hooks
+        function swpcpsv_version() bind(c, name='swpcpsv_version') result(msg)
+            import :: c_ptr
+            type(c_ptr) :: msg
+        end function
+        integer(c_int) function swpcpsv_zero_state(h) bind(c, name='swpcpsv_zero_state')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        !! it0 .. it1 iterations of swpcpsv_step without a host round trip
+        integer(c_int) function swpcpsv_run(h, it0, it1) bind(c, name='swpcpsv_run')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: it0, it1
+        end function
+        integer(c_int) function swpcpsv_timer_start(h) bind(c, name='swpcpsv_timer_start')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h
+        end function
+        integer(c_int) function swpcpsv_timer_stop(h, ms) bind(c, name='swpcpsv_timer_stop')
+            import :: c_int, c_float, c_ptr
+            type(c_ptr), value :: h
+            real(c_float), intent(out) :: ms
+        end function
+        integer(c_int) function swpcpsv_get_info(h, key, value) bind(c, name='swpcpsv_get_info')
+            import :: c_int, c_double, c_char, c_ptr
+            type(c_ptr), value :: h
+            character(kind=c_char), intent(in) :: key(*)      !! "launches", "ms_stress", "ms_vel", ... (NUL-terminated)
+            real(c_double), intent(out) :: value
+        end function
+        !! several ranks living on one GPU (tests): handles(n) ordered by myid; which = 0 stress, 1 velocity
+        integer(c_int) function swpcpsv_comm_local(handles, n, which) bind(c, name='swpcpsv_comm_local')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), intent(in) :: handles(*)
+            integer(c_int32_t), value :: n, which
+        end function
+        !! memory variables in the reference layout (m, k, i) over the memory box (m_kernel.f90:337-339); c_null_ptr skips one
+        integer(c_int) function swpcpsv_download_memvars(h, Rxx, Rzz, Rxz) bind(c, name='swpcpsv_download_memvars')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: h, Rxx, Rzz, Rxz
         end function
 
     end interface
