@@ -80,8 +80,35 @@ def full_summary(rep: Path, dst: Path, header: str):
     print(open(dst).read()[:600])
 
 
+def launch_list_psv(src: Path, dst: Path, header: str):
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ik, im, iv, iid, iu = (hdr.index(x) for x in ("Kernel Name", "Metric Name", "Metric Value", "ID", "Metric Unit"))
+    L = collections.OrderedDict()
+    for r in rows[1:]:
+        d = L.setdefault(r[iid], {"k": r[ik]})
+        d[r[im]] = (float(r[iv].replace(",", "")), r[iu])
+    with open(dst, "w") as fo:
+        fo.write(header)
+        fo.write("id,kernel,ms,dram_read_GB,dram_write_GB\n")
+        for i, d in L.items():
+            t, rd, wr = d["gpu__time_duration.sum"], d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+            fo.write(f"{i},{d['k'].split('(')[0].replace('void ', '')},{t[0] * TF[t[1]]:.4f},{rd[0] * F[rd[1]] / 1e9:.3f},{wr[0] * F[wr[1]] / 1e9:.3f}\n")
+    print(open(dst).read()[:900])
+
+
 if __name__ == "__main__":
     go = ROOT / "gpurun_out"
+    if (go / "launches_psv_final.csv").exists():
+        launch_list_psv(go / "launches_psv_final.csv", OUT / "r01_launches_psv_16384x8192.csv",
+                        "# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 40 python scripts/psv_probe.py 16384,8192 3\n"
+                        "# B200, swpc_psv 16384x8192 (nx x nz), NM=3, PML na=20, f64 fields, final code of round 1; psv_sweep<F,NM,1> = stress sweep, "
+                        "psv_sweep<F,NM,0> = velocity sweep; per-launch times are cold-cache and serialised\n")
+    if (go / "prof_psv_final.ncu-rep").exists():
+        full_summary(go / "prof_psv_final.ncu-rep", OUT / "r01_ncu_full_psv_16384x8192.txt",
+                     "ncu --set full --clock-control none --import-source on -k regex:psv_sweep -s 12 -c 2 python scripts/psv_probe.py 16384,8192 3\n"
+                     "B200 (sm_100a), swpc_psv 16384x8192, NM=3, PML na=20, f64 fields, final code of round 1; one stress and one velocity sweep "
+                     "(thread = one k, block = 256 k, marching along i with L2 prefetch of column i+1; velocity operands fetched up front, PsvVelOps)")
     if (go / "launches_r01b.csv").exists():
         launch_list(go / "launches_r01b.csv", OUT / "r01_launches_bench_1024x1024x512_tma.csv",
                     "# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 80 python bench.py --steps 3 --warmup 3 --no-cpu-baseline\n"
