@@ -71,6 +71,12 @@ struct TmaGeom {
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
 
+#ifndef SWPC_TMA_NM0_TWO
+#define SWPC_TMA_NM0_TWO 1
+#endif
+#ifndef SWPC_TMA_MAXREG
+#define SWPC_TMA_MAXREG 80
+#endif
 template <typename F, int NM>
 struct TmaCfg {
 #ifndef SWPC_TMA_TK
@@ -79,7 +85,11 @@ struct TmaCfg {
 #ifndef SWPC_TMA_TI
 #define SWPC_TMA_TI 8
 #endif
-    static constexpr int TK = SWPC_TMA_TK, TI = SWPC_TMA_TI, NS = 3;
+    // elastic runs (NM = 0) move 128 B per cell instead of 280: the consumer warps of ONE resident block cannot keep up with
+    // HBM, so that instantiation takes a 2-stage ring (100 KB) and a 56-register cap (17 warps x 1792 registers): two blocks per SM
+    // (stress sweep 4.31 -> 3.89 ms at 512^3; the same change for float32 fields with NM = 3 measured 1 % slower, not kept)
+    static constexpr int TK = SWPC_TMA_TK, TI = SWPC_TMA_TI, NS = (NM == 0 && sizeof(F) == 8 && SWPC_TMA_NM0_TWO) ? 2 : 3;
+    static constexpr int MAXREG = (NM == 0 && sizeof(F) == 8 && SWPC_TMA_NM0_TWO) ? 56 : SWPC_TMA_MAXREG;
     static constexpr int NHW = (TK / 32) * TI;   // warps per half: one warp = 32 consecutive k of one column
     static constexpr int NCW = 2 * NHW;          // consumer warps: NHW for the normal, NHW for the shear components
     static constexpr int VHK = 4;   // k halo of the V box: 4 (not 2) so that the box start stays 16-byte aligned for float fields
@@ -131,7 +141,7 @@ template <typename F, int NM>
 #endif
 // register cap (instead of __launch_bounds__): 17 warps x 80 registers leave room for one sweep_direct block of the
 // absorber shell on the same SM
-__global__ void __maxnreg__(SWPC_TMA_MAXREG)
+__global__ void __maxnreg__((TmaCfg<F, NM>::MAXREG))
 stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps tm, const TmaGeom g) {
     using C = TmaCfg<F, NM>;
     extern __shared__ __align__(1024) unsigned char smem[];
