@@ -3,6 +3,7 @@
   python scripts/sanitize_case.py split   one rank through swpc3d_step with the boundary-first split forced (second stream, phased sources)
   python scripts/sanitize_case.py green   Green's-function mode through the host driver (green_store / green_source kernels)
   python scripts/sanitize_case.py psv     swpc_psv: 2 emulated ranks, PML NM=3
+  python scripts/sanitize_case.py elastic NM=0, one rank: the two-blocks-per-SM instantiation of stress_tma (2-stage ring)
 """
 import sys
 import tempfile
@@ -49,6 +50,14 @@ elif mode == "green":
     run.run(1, 12)
     run.write_green(d / "out")
     print('bit-exact:', bool(np.array_equal(run.array("green_gf"), o.green(0)["gf"])))
+elif mode == "elastic":
+    inf = write_case(d, nt=6, nx=96, ny=88, nz=76, na=8, vmodel="lhm_land")
+    o = Oracle(inf, base_dir=d, nm=0)
+    x = device_from_oracle(o, 0, device=0)
+    o.run(1, 6)
+    x.run(1, 6)
+    x.sync()
+    print('tma_ok', x.info('tma_ok'), 'bit-exact:', check(o, [x], 76))
 elif mode == "split":
     inf = write_case(d, nt=6, nx=96, ny=88, nz=76, na=8, sources=["-23.3 -21.3 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8",
                                                                   "0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
