@@ -153,6 +153,7 @@ struct swpc3d_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // tuning
     int tk = 64, ti = 4, jlen = 16, pf = 1;
+    int tma_shift = 1;              // option "tma_shift": shift stress_tma's partial last k-tile up instead of masking absorber rows
     int use_tma = 1, tma_jl = 16;   // use_tma: 0 off, 1 stress sweep only (default: measured fastest), 2 stress + velocity sweeps
     bool tma_ready = false, tma_ok = false;
     TmaMaps tmaps{};
@@ -713,6 +714,7 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
     if (t.k1 < t.k0) return launch_direct_box<F, true>(h, p, all);
     TmaGeom g{};
     g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
+    g.shift_last = h->tma_shift;
     dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + 1) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
     const int kE = (h->g.kend_k / C::TK) * C::TK + 1;   // first k of the tile that contains kend_k + 1 (warp-aligned)
     // complement of the TMA box inside the owned box: two j slabs, two i slabs, one k slab (absorber cells only: the TMA
@@ -1507,6 +1509,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "pw_mode")) { h->pw_mode = value != 0; if (value) h->zero_outer = 1; }
     else if (!strcmp(key, "zero_outer_halo")) h->zero_outer = value != 0;
     else if (!strcmp(key, "tma")) h->use_tma = value;
+    else if (!strcmp(key, "tma_shift")) h->tma_shift = value != 0;
     else if (!strcmp(key, "vel_ring")) h->use_ring = value;
     else if (!strcmp(key, "flat_bottom")) h->flat_bottom = value != 0;
     else if (!strcmp(key, "overlap")) h->overlap = value != 0;

@@ -67,6 +67,7 @@ struct TmaGeom {
     int jl;              // planes per block
     int m_first;         // index of lam in the medium tensor's 4th dimension (lam, taup, taus are consecutive)
     int mu_index;        // index of mu in the medium tensor's 4th dimension
+    int shift_last;      // 1: shift a partial last k-tile up (see stress_tma)
 };
 
 constexpr int align128(int x) { return (x + 127) / 128 * 128; }
@@ -149,7 +150,12 @@ stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps
     uint64_t *empty = full + C::NS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k0 = 1 + blockIdx.x * C::TK;                 // first k of the tile (1-based)
+    // first k of the tile (1-based).  A last tile that would reach below the interior box is shifted up instead (to the first
+    // k = 1 mod 4 -- the alignment class of every tile start, which TMA needs -- that still covers kend_k): the rows it then
+    // shares with the tile above are masked here and come out of L2 (the neighbour block pulls them at the same time),
+    // where the absorber rows below kend_k would have been fetched from HBM only to be thrown away.
+    const int k0t = 1 + blockIdx.x * C::TK;
+    const int k0 = (k0t + C::TK - 1 > p.k1_k && p.k1_k >= C::TK && g.shift_last) ? ((p.k1_k - C::TK + 3) / 4) * 4 + 1 : k0t;
     const int li0 = g.li0 + blockIdx.y * C::TI;            // first local i of the tile
     const int lj0 = g.lj0 + blockIdx.z * g.jl;             // first local j of the march
     const int nsteps = min(g.jl, g.lj1 - lj0 + 1);
@@ -195,7 +201,7 @@ stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps
     const bool shear = warp >= C::NHW;
     const int wq = shear ? warp - C::NHW : warp;
     const int tk = (wq % (C::TK / 32)) * 32 + lane, ti = wq / (C::TK / 32);
-    const bool active = (k0 + tk) <= p.k1_k;   // last k-tile may reach into the absorber: those lanes only idle
+    const bool active = (k0 + tk) <= p.k1_k && (k0 + tk) >= k0t;   // last k-tile: absorber rows / rows of the tile above idle
     const int k = k0 + tk, li = li0 + ti, mi = li + HALO;
     AccTma<F, NM> a(p);
     const int voff = (ti + 2) * C::VK + (tk + C::VHK);

@@ -118,7 +118,8 @@ def test_step_entry_point_and_run(tmp_path):
     _compare(o, [d], exact=True)
 
 
-@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}, {"flat_bottom": 0}])
+@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}, {"flat_bottom": 0},
+                                     {"tma_shift": 1}, {"tma_shift": 0}])
 @pytest.mark.parametrize("abc", ["pml", "cerjan"])
 def test_kernel_variants_bit_exact(tmp_path, variant, abc):
     # every kernel variant of the two sweeps (direct, TMA-staged stress, TMA-staged stress + velocity, register-ring velocity) shares one arithmetic body
