@@ -366,6 +366,11 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
         if (h->side[q]) cudaStreamDestroy(h->side[q]);
         if (h->ev_join[q]) cudaEventDestroy(h->ev_join[q]);
     }
+    for (auto &per_sweep : h->kev)            // kernel_timing stopwatches
+        for (auto &side : per_sweep)
+            for (cudaEvent_t e : side) cudaEventDestroy(e);
+    for (auto &side : h->cev)
+        for (cudaEvent_t e : side) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_b) cudaEventDestroy(h->ev_b);
     if (h->ev_c) cudaEventDestroy(h->ev_c);
