@@ -246,6 +246,8 @@ static void setup_coefs(swpc3d_handle *h, const float *ts) {
     h->dt_dxyz = (double)((F)dt / ((F)g.dx * (F)g.dy * (F)g.dz));   // m_source.f90:306
 }
 
+static int create_state(swpc3d_handle *h, const swpc3d_grid *g, const float *ts);
+
 extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handle **out) {
     if (!g || !out) return fail("swpc3d_create: null argument");
     *out = nullptr;
@@ -261,6 +263,18 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
     swpc3d_handle *h = new swpc3d_handle();
     h->g = *g;
     h->dev = g->device >= 0 ? g->device : (g->myid % ndev);   // m_global.f90:208-214
+    const int rc = create_state(h, g, ts);
+    if (rc) {   // e.g. out of device memory half way: give everything back, keep the message
+        const std::string msg = swpc3d_last_error();
+        swpc3d_destroy(h);
+        cudaGetLastError();   // a failed cudaMalloc is not sticky, but it stays the "last error" until it is read
+        return fail(msg);
+    }
+    *out = h;
+    return 0;
+}
+
+static int create_state(swpc3d_handle *h, const swpc3d_grid *g, const float *ts) {
     CK(cudaSetDevice(h->dev));
     h->nxp = g->iend - g->ibeg + 1;
     h->nyp = g->jend - g->jbeg + 1;
@@ -341,7 +355,6 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
     h->nbr[2] = (idy + 1 < g->nproc_y) ? g->myid + g->nproc_x : -1;
     h->nbr[3] = (idy - 1 >= 0) ? g->myid - g->nproc_x : -1;
     CK(cudaStreamSynchronize(h->st));
-    *out = h;
     return 0;
 }
 

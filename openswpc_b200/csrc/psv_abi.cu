@@ -178,6 +178,8 @@ static void setup_coefs(swpcpsv_handle *h, const float *ts) {
     h->dt_dxz = (double)((F)dt / ((F)g.dx * (F)g.dz));
 }
 
+static int create_state(swpcpsv_handle *h, const swpcpsv_grid *g, const float *ts);
+
 extern "C" int swpcpsv_create(const swpcpsv_grid *g, const float *ts, swpcpsv_handle **out) {
     if (!g || !out) return fail("swpcpsv_create: null argument");
     *out = nullptr;
@@ -193,6 +195,18 @@ extern "C" int swpcpsv_create(const swpcpsv_grid *g, const float *ts, swpcpsv_ha
     swpcpsv_handle *h = new swpcpsv_handle();
     h->g = *g;
     h->dev = g->device >= 0 ? g->device : (g->myid % ndev);
+    const int rc = create_state(h, g, ts);
+    if (rc) {   // e.g. out of device memory half way: give everything back, keep the message
+        const std::string msg = swpcpsv_last_error();
+        swpcpsv_destroy(h);
+        cudaGetLastError();   // a failed cudaMalloc is not sticky, but it stays the "last error" until it is read
+        return fail(msg);
+    }
+    *out = h;
+    return 0;
+}
+
+static int create_state(swpcpsv_handle *h, const swpcpsv_grid *g, const float *ts) {
     CK(cudaSetDevice(h->dev));
     h->nxp = g->iend - g->ibeg + 1;
     h->NXM = h->nxp + 2 * HALO + g->ipad;
@@ -243,7 +257,6 @@ extern "C" int swpcpsv_create(const swpcpsv_grid *g, const float *ts, swpcpsv_ha
         if (i >= g->ibeg_k && i <= g->iend_k) h->cells_interior += std::min(g->kend_k, kb - 1);
     }
     CK(cudaStreamSynchronize(h->st));
-    *out = h;
     return 0;
 }
 

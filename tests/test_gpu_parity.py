@@ -165,3 +165,28 @@ def test_odd_sizes_and_padding(tmp_path):
     # sizes that are multiples of nothing, and a source one cell from the PML
     o, devs = _run_pair(tmp_path, 30, nranks=(1, 1), nx=37, ny=29, nz=35, na=5, sources=["-5.9 3.7 3.3 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
     _compare(o, devs, exact=True)
+
+
+def test_create_gives_memory_back_when_it_fails_half_way():
+    """A rank that does not fit: the field block (72 B/cell) still fits, the memory variables do not.  swpc3d_create must report
+    the CUDA error and release what it had taken, so that a smaller rank can be created afterwards."""
+    import torch
+
+    from openswpc_b200._lib import Swpc3dError
+    from openswpc_b200.device import DeviceRank, RankGeometry
+
+    free0, total = torch.cuda.mem_get_info(0)
+    ncell_target = int(free0 * 0.62 / 72)                      # fields fit (62 % of what is free), fields + memory variables do not
+    nz = 1000
+    n = int((ncell_target / (nz + 56)) ** 0.5)
+    geom = RankGeometry(nx=n, ny=n, nz=nz, nproc_x=1, nproc_y=1, myid=0, ibeg=1, iend=n, jbeg=1, jend=n, ibeg_k=21, iend_k=n - 20, jbeg_k=21,
+                        jend_k=n - 20, kbeg_k=1, kend_k=nz - 20, na=20)
+    ts = np.array([7.9577475, 0.79577476, 0.07957747], dtype=np.float32)
+    with pytest.raises(Swpc3dError, match="out of memory"):
+        DeviceRank(geom, dx=0.5, dy=0.5, dz=0.5, dt=0.02, nm=3, abc_type="pml", ts=ts, device=0)
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free1 >= free0 - (256 << 20), (free0, free1)
+    small = RankGeometry(nx=64, ny=64, nz=64, nproc_x=1, nproc_y=1, myid=0, ibeg=1, iend=64, jbeg=1, jend=64, ibeg_k=11, iend_k=54, jbeg_k=11,
+                         jend_k=54, kbeg_k=1, kend_k=54, na=10)
+    d = DeviceRank(small, dx=0.5, dy=0.5, dz=0.5, dt=0.02, nm=3, abc_type="pml", ts=ts, device=0)
+    d.close()
