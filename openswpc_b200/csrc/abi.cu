@@ -501,6 +501,7 @@ extern "C" int swpc3d_setup_pml(swpc3d_handle *h, const float *gxc, const float 
     h->naux = off;
     if (h->aoff) cudaFree(h->aoff);
     if (h->aux) cudaFree(h->aux);
+    h->aoff = nullptr; h->aux = nullptr;
     CK(cudaMalloc(&h->aoff, aoff.size() * sizeof(long long)));
     CK(cudaMemcpyAsync(h->aoff, aoff.data(), aoff.size() * sizeof(long long), cudaMemcpyHostToDevice, h->st));
     CK(cudaMalloc(&h->aux, (size_t)std::max<long long>(h->naux, 1) * 18 * sizeof(float)));
@@ -587,6 +588,7 @@ extern "C" int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t 
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->dev));
     cudaFree(h->st_ijk); cudaFree(h->wav);
+    h->st_ijk = nullptr; h->wav = nullptr;
     h->st_ijk = nullptr; h->wav = nullptr;
     h->nst = nst; h->ntdec_w = ntdec_w; h->ntw = ntw; h->M0 = M0; h->UC = UC;
     if (nst <= 0 || ntw <= 0) return 0;
