@@ -589,7 +589,6 @@ extern "C" int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t 
     CK(cudaSetDevice(h->dev));
     cudaFree(h->st_ijk); cudaFree(h->wav);
     h->st_ijk = nullptr; h->wav = nullptr;
-    h->st_ijk = nullptr; h->wav = nullptr;
     h->nst = nst; h->ntdec_w = ntdec_w; h->ntw = ntw; h->M0 = M0; h->UC = UC;
     if (nst <= 0 || ntw <= 0) return 0;
     std::vector<int> ijk(3 * (size_t)nst);
