@@ -203,6 +203,8 @@ def cpu_port_throughput(nm: int, sample=(384, 384, 384), steps: int = 24, warmup
 
     # all the host cores this process may use -- torchrun exports OMP_NUM_THREADS=1 to its workers, which must not throttle
     # the CPU arm (rank 0 runs it alone); SWPC_BENCH_CPU_THREADS overrides
+    if os.environ.get("SWPC_BENCH_CPU_SAMPLE"):   # tests shrink the sample; the reported `sample` string says what was run
+        sample = tuple(int(v) for v in os.environ["SWPC_BENCH_CPU_SAMPLE"].split(","))
     cores = int(os.environ.get("SWPC_BENCH_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
     os.environ["OMP_NUM_THREADS"] = str(cores)
     with tempfile.TemporaryDirectory() as td:

@@ -19,7 +19,7 @@ def _run(args, env=None, timeout=600):
 
 def test_reference_arm_json_line():
     # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm must still use every core it is allowed to
-    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"], env={"OMP_NUM_THREADS": "1"})
+    p = _run(["--impl", "reference", "--steps", "1", "--warmup", "1"], env={"OMP_NUM_THREADS": "1", "SWPC_BENCH_CPU_SAMPLE": "160,160,160"})
     assert p.returncode == 0, p.stderr[-2000:]
     lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
@@ -31,7 +31,7 @@ def test_reference_arm_json_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] == len(os.sched_getaffinity(0)) and "384x384x384" in cb["sample"]
+    assert cb["kind"] == "port" and cb["value"] == d["value"] and cb["cores"] == len(os.sched_getaffinity(0)) and "160x160x160" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
