@@ -190,3 +190,38 @@ def test_create_gives_memory_back_when_it_fails_half_way():
                          jend_k=54, kbeg_k=1, kend_k=54, na=10)
     d = DeviceRank(small, dx=0.5, dy=0.5, dz=0.5, dt=0.02, nm=3, abc_type="pml", ts=ts, device=0)
     d.close()
+
+
+@pytest.mark.parametrize("model", ["grd", "grd_flat_land", "lhm_rmed"])
+@pytest.mark.parametrize("nranks", [(1, 1), (2, 2)])
+def test_laterally_heterogeneous_models_bit_exact(tmp_path, model, nranks):
+    """Topography / bathymetry that changes from column to column (vmodel_grd: kfs, kob and the 2nd-order bands kfs_top ..
+    kob_bot differ per column, land and sea columns side by side) and random-media perturbations of every cell (lhm_rmed):
+    the sweeps, the PML shell and the free-surface / ocean-bottom band logic on media the 1-D models of the other tests
+    cannot produce.  Sources sit under land and under sea; a long enough run for the waves to reach the surface."""
+    from helpers import write_grd, write_rmed
+
+    nt = 60
+    if model.startswith("grd"):
+        lon = 139.40 + 0.01 * np.arange(72)
+        lat = 35.50 + 0.01 * np.arange(46)
+        LO, LA = np.meshgrid(lon, lat)
+        write_grd(tmp_path / "g1.grd", lon, lat, 700.0 * np.sin((LO - 139.76) * 60.0) * np.cos((LA - 35.72) * 55.0) + 100.0)   # +-0.7 km of relief
+        write_grd(tmp_path / "g2.grd", lon, lat, 3200.0 + 900.0 * np.cos((LO - 139.7) * 25.0) + 400.0 * np.sin((LA - 35.7) * 30.0))
+        write_grd(tmp_path / "g3.grd", lon, lat, 9500.0 + 1500.0 * np.sin((LO - 139.8) * 12.0 + (LA - 35.7) * 9.0))
+        (tmp_path / "grd.lst").write_text("'g1.grd' 2.1 3.0 1.6 100 50 0\n'g2.grd'  2.5 5.0 2.9 300 150 0\n g3.grd  2.9 6.8 3.9 500 250 1\n")
+        vm = "vmodel_type = 'grd'\n fn_grdlst = 'grd.lst'\n dir_grd = '.'\n" + (" is_ocean = .false.\n" if model == "grd_flat_land" else "")
+    else:
+        rng = np.random.default_rng(3)
+        write_rmed(tmp_path / "r1.nc", (0.05 * rng.standard_normal((20, 12, 16))).astype(np.float32))
+        write_rmed(tmp_path / "r2.nc", (0.08 * rng.standard_normal((30, 25, 35))).astype(np.float32))
+        (tmp_path / "layers_rmed.dat").write_text("# depth rho vp vs Qp Qs rmed\n0.0 2.3 5.5 3.14 600 300 r1.nc\n3.0 2.4 6.0 3.55 400 200 r2.nc\n"
+                                                  "9.0 2.8 6.7 3.83 600 300 r1.nc\n15.0 3.2 7.8 4.46 600 300 r2.nc\n")
+        vm = "vmodel_type = 'lhm_rmed'\n fn_lhm_rmed = 'layers_rmed.dat'\n dir_rmed = '.'\n"
+    o, devs = _run_pair(tmp_path, nt, nranks=nranks, nx=52, ny=44, nz=48, zbeg=-2.0, vmodel="raw:" + vm, dt=0.01,
+                        sources=["0.3 -0.2 2.1 0.02 0.3 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8", "-4.1 3.7 1.6 0.05 0.25 4e14 -0.2 0.9 0.1 -0.5 0.3 0.6"])
+    _compare(o, devs, exact=True)
+    if model == "grd":
+        kfs, kob = o.imap(0, "kfs")[4:-4, 4:-4], o.imap(0, "kob")[4:-4, 4:-4]
+        assert kob.max() - kob.min() >= 2 and (kob > kfs).any() and (kob == kfs).any()      # relief; sea and land columns
+    assert np.abs(o.field(0, "Vz")[3:-3, 3:-3, 3:10]).max() > 0                              # the waves have reached the surface
