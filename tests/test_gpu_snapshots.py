@@ -93,3 +93,33 @@ def test_unknown_snapshot_format_refused(tmp_path):
     inf = write_case(tmp_path, nt=4, extra="snp_format = 'hdf5'\n xy_v%sw = .true.")
     with pytest.raises(Exception, match="snp_format"):
         Swpc3d(inf, base_dir=tmp_path, nm=3)
+
+
+def test_snapshots_follow_the_topography(tmp_path):
+    """The fs / ob products sample k = kfs(i,j) + 1 / kob(i,j) + 1 (m_snap.f90:1016-1036, 1476-1478): on a GMT-grid model with
+    relief those depths change from column to column, with land and sea side by side; all 15 products."""
+    from helpers import write_grd
+
+    lon = 139.40 + 0.01 * np.arange(72)
+    lat = 35.50 + 0.01 * np.arange(46)
+    LO, LA = np.meshgrid(lon, lat)
+    write_grd(tmp_path / "g1.grd", lon, lat, 700.0 * np.sin((LO - 139.76) * 60.0) * np.cos((LA - 35.72) * 55.0) + 100.0)
+    write_grd(tmp_path / "g2.grd", lon, lat, 3200.0 + 900.0 * np.cos((LO - 139.7) * 25.0) + 400.0 * np.sin((LA - 35.7) * 30.0))
+    (tmp_path / "grd.lst").write_text("'g1.grd' 2.1 3.0 1.6 100 50 0\n'g2.grd'  2.5 5.0 2.9 300 150 1\n")
+    vm = "vmodel_type = 'grd'\n fn_grdlst = 'grd.lst'\n dir_grd = '.'\n"
+    nt = 40
+    dec = (2, 2, 2, 4)
+    inf = write_case(tmp_path, nt=nt, title="topo", nx=52, ny=44, nz=48, zbeg=-2.0, dt=0.01, vmodel="raw:" + vm,
+                     sources=["0.3 -0.2 2.1 0.02 0.3 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"], extra=snap_extra(*dec))
+    o = Oracle(inf, base_dir=tmp_path, nm=3)
+    kfs, kob = o.imap(0, "kfs")[4:-4, 4:-4], o.imap(0, "kob")[4:-4, 4:-4]
+    assert kob.max() - kob.min() >= 2 and (kob > kfs).any() and (kob == kfs).any()
+    o.run(1, nt)
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    run.attach_device(0)
+    run.snap_open(tmp_path / "gpu")
+    run.run(1, nt)
+    run.snap_close()
+    for q in range(15):
+        sec, typ = divmod(q, 3)
+        check_file(tmp_path / "gpu" / f"topo.3d.{OL.SNAP_SECTIONS[sec]}.{OL.SNAP_TYPES[typ]}.nc", o, q, "topo", run["dt"], dec[3])
