@@ -20,6 +20,7 @@ struct swpc3d_host {
     float fq_min = 0.05f, fq_max = 5.0f, fq_ref = 1.0f, vcut = 0.0f;
     bool pw_mode = false, green_mode = false, bf_mode = false, earth_flattening = false;
     int ntdec_w = 10, ntdec_r = 10, ntw = 0;
+    int ntdec_w_prg = 0;   // m_wav.f90:74, :619-621: waveform files rewritten every ntdec_w_prg steps while the run goes on
     bool sw_wav_v = false, sw_wav_u = false, sw_wav_stress = false, sw_wav_strain = false;
     float vmin = 0, vmax = 0, vmin_local = 0, vmax_local = 0, fmax = 0, fcut = 0, M0 = 0, UC = 1e-15f, zeta = 0, d2 = 0;
     float ts[8] = {}, c1[8] = {}, c2[8] = {}, d1[8] = {};
@@ -647,6 +648,7 @@ int swpc3d_host::setup_absorb() {
 
 int swpc3d_host::setup_wav(const IniFile &ini) {   // m_wav.f90:54-271
     ntdec_w = ini.get_i("ntdec_w", 10);
+    ntdec_w_prg = ini.get_i("ntdec_w_prg", 0);
     sw_wav_v = ini.get_l("sw_wav_v", false);
     sw_wav_u = ini.get_l("sw_wav_u", false);
     sw_wav_stress = ini.get_l("sw_wav_stress", false);
@@ -1337,6 +1339,12 @@ int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, f
             DS(swpc3d_advance(h->dev, it));
 #undef DS
         } else if (swpc3d_step(h->dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
+        // wav__store's tail (m_wav.f90:619-621): the traces sampled so far, written while the run goes on (the buffers change
+        // only at the next wav__store, so writing after the sweeps of this iteration gives the reference's files)
+        if (h->ntdec_w_prg > 0 && (it - 1) % h->ntdec_w_prg == 0) {
+            int32_t nf = 0;
+            if (swpc3d_host_write_sac(h, nullptr, &nf)) return 1;
+        }
     }
     if (swpc3d_sync(h->dev)) return hfail(std::string("device: ") + swpc3d_last_error());
     h->loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

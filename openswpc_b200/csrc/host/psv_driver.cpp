@@ -17,6 +17,7 @@ struct swpcpsv_host {
     float fq_min = 0.05f, fq_max = 5.0f, fq_ref = 1.0f, vcut = 0.0f;
     bool pw_mode = false, bf_mode = false, earth_flattening = false;
     int ntdec_w = 10, ntdec_r = 10, ntw = 0;
+    int ntdec_w_prg = 0;   // m_wav.f90:71, :309-311: waveform files rewritten every ntdec_w_prg steps while the run goes on
     bool sw[4] = {false, false, false, false};   // v u stress strain
     float vmin = 0, vmax = 0, vmin_local = 0, vmax_local = 0, fmax = 0, fcut = 0, M0 = 0, UC = 1e-12f, zeta = 0, d2 = 0;
     float ts[8] = {}, c1[8] = {}, c2[8] = {}, d1[8] = {};
@@ -538,6 +539,7 @@ void swpcpsv_host::setup_absorb() {   // m_absorb_p.f90:57-101 / m_absorb_c.f90:
 
 int swpcpsv_host::setup_wav(const IniFile &ini) {   // m_wav.f90:53-141, set_stinfo :433-571
     ntdec_w = ini.get_i("ntdec_w", 10);
+    ntdec_w_prg = ini.get_i("ntdec_w_prg", 0);
     sw[0] = ini.get_l("sw_wav_v", false); sw[1] = ini.get_l("sw_wav_u", false);
     sw[2] = ini.get_l("sw_wav_stress", false); sw[3] = ini.get_l("sw_wav_strain", false);
     wav_format = ini.get("wav_format", "sac");
@@ -926,6 +928,10 @@ int swpcpsv_host_run(swpcpsv_host *h, int32_t it0, int32_t it1, int32_t verbose,
                 swpcpsv_comm_vel(h->dev))
                 return hfail(std::string("device: ") + swpcpsv_last_error());
         } else if (swpcpsv_step(h->dev, it)) return hfail(std::string("device: ") + swpcpsv_last_error());
+        if (h->ntdec_w_prg > 0 && (it - 1) % h->ntdec_w_prg == 0) {   // wav__store's tail, m_wav.f90:309-311
+            int32_t nf = 0;
+            if (swpcpsv_host_write_wav(h, nullptr, &nf)) return 1;
+        }
     }
     if (swpcpsv_sync(h->dev)) return hfail(std::string("device: ") + swpcpsv_last_error());
     h->loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

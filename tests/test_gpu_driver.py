@@ -167,3 +167,25 @@ def test_station_products_decomposed(tmp_path):
             np.testing.assert_array_equal(got, ref, err_msg=f"rank {q} product {which}")
             seen += 1
     assert seen >= 8   # the four stations sit around the 2x2 corner, one per rank
+
+
+def test_progressive_waveform_output(tmp_path):
+    """ntdec_w_prg (m_wav.f90:74, :619-621): the waveform files are (re)written every ntdec_w_prg steps while the run goes on,
+    holding the samples taken so far and zeros after them."""
+    nt = 20
+    inf = write_case(tmp_path, nt=nt, ntdec_w=1, extra="ntdec_w_prg = 7", sources=["0.3 -0.2 4.1 0.0 0.3 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"],
+                     stations=["0.5 0.5 3.0 st01 dep", "-1.0 1.5 5.0 st02 dep"])
+    inf.write_text(inf.read_text().replace("odir = './out'", f"odir = '{tmp_path}/out'"))   # (odir is relative to the working directory)
+    o = Oracle(inf, base_dir=tmp_path, nm=3)
+    o.run(1, nt)
+    ref = o.wav(0)                                   # (nst, 3, ntw), ntw = nt
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    run.attach_device(0)
+    run.run(1, 12)                                   # the files were written at it = 1 and it = 8; nobody calls write_sac here
+    files = sorted((tmp_path / "out" / "wav").glob("*.sac"))
+    assert len(files) == 3 * run["nst"] == 6
+    f = [p for p in files if "st01" in p.name and p.name.endswith("Vz.sac")][0]
+    data = np.frombuffer(f.read_bytes()[632:], dtype="<f4")
+    assert data.size == nt
+    assert np.array_equal(data[:8], ref[0, 2, :8]) and np.abs(data[:8]).max() > 0
+    assert not data[8:].any()
