@@ -56,6 +56,9 @@ swpc3d_handle *swpc3d_host_handle(swpc3d_host *h);
 int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, float *vm, int32_t nvm, int32_t *nrec);
 /* wav__write (m_wav.f90:658-792), SAC format: <odir>/wav/<title>.3d.<stnm>.<cmp>.sac ; returns file count in *nfiles */
 int swpc3d_host_write_sac(swpc3d_host *h, const char *odir, int32_t *nfiles);
+/* pwatch__report (m_pwatch.f90:146-195, main.f90:148-154): <odir>/<title>.tim for this rank when stopwatch_mode is on (the
+ * default), in the reference's table layout; the phases are the ones the library's CUDA-event stopwatches bracket */
+int swpc3d_host_write_tim(swpc3d_host *h, const char *odir);
 /* Green's-function mode (green_mode = .true., m_green.f90).  The pseudo source is a station: its owner rank finds it with
  * wav__stquery and the reference broadcasts indices and coordinates (m_green.f90:161-183).  A multi-rank host does the
  * same: query every rank, hand the owner's answer to all of them (single-rank runs need neither call).

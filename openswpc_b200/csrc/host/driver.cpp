@@ -20,6 +20,10 @@ struct swpc3d_host {
     float fq_min = 0.05f, fq_max = 5.0f, fq_ref = 1.0f, vcut = 0.0f;
     bool pw_mode = false, green_mode = false, bf_mode = false, earth_flattening = false;
     int ntdec_w = 10, ntdec_r = 10, ntw = 0;
+    // m_pwatch replacement (main.f90:58, :148-154): per-phase device time from the library's CUDA-event stopwatches
+    bool stopwatch_mode = true;
+    double tim_stress = 0, tim_vel = 0, tim_halo = 0;   // seconds
+    int harvest_timers();
     int ntdec_w_prg = 0;   // m_wav.f90:74, :619-621: waveform files rewritten every ntdec_w_prg steps while the run goes on
     bool sw_wav_v = false, sw_wav_u = false, sw_wav_stress = false, sw_wav_strain = false;
     float vmin = 0, vmax = 0, vmin_local = 0, vmax_local = 0, fmax = 0, fcut = 0, M0 = 0, UC = 1e-15f, zeta = 0, d2 = 0;
@@ -649,6 +653,7 @@ int swpc3d_host::setup_absorb() {
 int swpc3d_host::setup_wav(const IniFile &ini) {   // m_wav.f90:54-271
     ntdec_w = ini.get_i("ntdec_w", 10);
     ntdec_w_prg = ini.get_i("ntdec_w_prg", 0);
+    stopwatch_mode = ini.get_l("stopwatch_mode", true);
     sw_wav_v = ini.get_l("sw_wav_v", false);
     sw_wav_u = ini.get_l("sw_wav_u", false);
     sw_wav_stress = ini.get_l("sw_wav_stress", false);
@@ -1309,9 +1314,23 @@ int swpc3d_host_banner(swpc3d_host *h) {   // m_report.f90:64-92
     return 0;
 }
 
+// add what the device stopwatches hold to the phase totals and restart them (they keep at most 4096 brackets)
+int swpc3d_host::harvest_timers() {
+    double ms = 0, n = 0;
+    const char *key[3][2] = {{"ms_stress", "n_stress"}, {"ms_vel", "n_vel"}, {"ms_halo", "n_halo"}};
+    double *dst[3] = {&tim_stress, &tim_vel, &tim_halo};
+    for (int q = 0; q < 3; q++) {
+        if (swpc3d_get_info(dev, key[q][0], &ms) || swpc3d_get_info(dev, key[q][1], &n)) return hfail(std::string("device: ") + swpc3d_last_error());
+        *dst[q] += ms * n * 1e-3;
+    }
+    if (swpc3d_set_option(dev, "kernel_timing", 1)) return hfail(std::string("device: ") + swpc3d_last_error());
+    return 0;
+}
+
 int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, float *vm, int32_t nvm, int32_t *nrec) {
     if (!h || !h->dev) return hfail("swpc3d_host_run: no device attached");
     int rec = 0;
+    if (h->stopwatch_mode && swpc3d_set_option(h->dev, "kernel_timing", 1)) return hfail(std::string("device: ") + swpc3d_last_error());
     const auto t0 = std::chrono::steady_clock::now();
     for (int it = it0; it <= it1; it++) {
         if (h->ntdec_r > 0 && it % h->ntdec_r == 0) {   // report__progress m_report.f90:120-185
@@ -1345,10 +1364,40 @@ int swpc3d_host_run(swpc3d_host *h, int32_t it0, int32_t it1, int32_t verbose, f
             int32_t nf = 0;
             if (swpc3d_host_write_sac(h, nullptr, &nf)) return 1;
         }
+        if (h->stopwatch_mode && (it - it0 + 1) % 1000 == 0 && h->harvest_timers()) return 1;
     }
+    if (h->stopwatch_mode && h->harvest_timers()) return 1;
     if (swpc3d_sync(h->dev)) return hfail(std::string("device: ") + swpc3d_last_error());
     h->loop_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (nrec) *nrec = rec;
+    return 0;
+}
+
+// pwatch__report (m_pwatch.f90:146-195) for this rank: <odir>/<title>.tim in the reference's table layout.  The rows are the
+// phases the device stopwatches bracket -- the fused sweeps carry the reference's kernel__update_* AND absorb__update_* time,
+// the exchange its global__comm_* time -- plus everything else of the time loop (sources, stations, snapshots, host).
+static void mkdirs(const std::string &p);
+int swpc3d_host_write_tim(swpc3d_host *h, const char *odir) {
+    if (!h) return hfail("null handle");
+    if (!h->stopwatch_mode) return 0;
+    const std::string dir = odir ? odir : h->odir.c_str();
+    mkdirs(dir);
+    const std::string fn = dir + "/" + h->title + ".tim";
+    FILE *fp = std::fopen(fn.c_str(), "w");
+    if (!fp) return hfail("cannot write " + fn);
+    const char *name[4] = {"kernel__update_stress", "kernel__update_vel", "global__comm", "others"};
+    const double other = std::max(0.0, h->loop_seconds - h->tim_stress - h->tim_vel - h->tim_halo);
+    const double t[4] = {h->tim_stress, h->tim_vel, h->tim_halo, other};
+    const double tsum = std::max(t[0] + t[1] + t[2] + t[3], 1e-30);
+    std::fprintf(fp, "#   CPU     #ID       Procedure Name         Real Time[s]   Total Time[s]   Occupancy[%%]  Total Occp.[%%] \n");
+    std::fprintf(fp, "# -------+-------+-------------------------+--------------+--------------+--------------+----------------\n");
+    double acc = 0, racc = 0;
+    for (int i = 0; i < 4; i++) {   // '(I8.5,I8.5,"    ",A22,4F15.3)'
+        acc += t[i];
+        racc += t[i] / tsum * 100.0;
+        std::fprintf(fp, "   %05d   %05d    %22s%15.3f%15.3f%15.3f%15.3f\n", h->myid, i + 1, name[i], t[i], acc, t[i] / tsum * 100.0, racc);
+    }
+    std::fclose(fp);
     return 0;
 }
 

@@ -53,6 +53,7 @@ def _bind(lib):
     lib.swpc3d_host_run.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_float), i32, C.POINTER(i32)]
     lib.swpc3d_host_write_sac.argtypes = [vp, cp, C.POINTER(i32)]
     lib.swpc3d_host_banner.argtypes = [vp]
+    lib.swpc3d_host_write_tim.argtypes = [vp, cp]
     lib.swpc3d_host_green_query.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.swpc3d_host_green_set_source.argtypes = [vp, C.POINTER(i32), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.swpc3d_host_write_green.argtypes = [vp, cp, C.POINTER(i32)]
@@ -185,6 +186,10 @@ class Swpc3d:
         return n.value
 
     # ---- Green's-function mode (m_green.f90)
+    def write_tim(self, odir=None):
+        """pwatch__report: <odir>/<title>.tim (stopwatch_mode, on by default)."""
+        self._ck(self.lib.swpc3d_host_write_tim(self.h, os.fspath(odir).encode() if odir is not None else None))
+
     def green_query(self):
         """(found, ijk[3], xyz[3], lonlat[2]) of the pseudo source on this rank (wav__stquery)."""
         f, ijk, xyz, ll = C.c_int32(), (C.c_int32 * 3)(), (C.c_float * 3)(), (C.c_float * 2)()

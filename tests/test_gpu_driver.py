@@ -189,3 +189,32 @@ def test_progressive_waveform_output(tmp_path):
     assert data.size == nt
     assert np.array_equal(data[:8], ref[0, 2, :8]) and np.abs(data[:8]).max() > 0
     assert not data[8:].any()
+
+
+def test_stopwatch_report(tmp_path):
+    """stopwatch_mode (main.f90:58, :148-154; m_pwatch.f90:146-195): <odir>/<title>.tim in the reference's table layout, filled
+    from the CUDA-event stopwatches of the library; `stopwatch_mode = .false.` writes nothing."""
+    import re
+
+    nt = 30
+    inf = write_case(tmp_path, nt=nt, title="tim", nx=64, ny=64, nz=64, na=10)
+    run = Swpc3d(inf, base_dir=tmp_path, nm=3)
+    run.attach_device(0)
+    run.run(1, nt)
+    run.write_tim(tmp_path / "o")
+    lines = (tmp_path / "o" / "tim.tim").read_text().splitlines()
+    assert lines[0].startswith("#   CPU     #ID       Procedure Name         Real Time[s]") and lines[1].startswith("# -------+-------+")
+    rows = [re.match(r"^   (\d{5})   (\d{5})    (.{22})\s*([\d.]+)\s+([\d.]+)\s+([\d.]+)\s+([\d.]+)$", l) for l in lines[2:]]
+    assert len(rows) == 4 and all(rows)
+    names = [r.group(3).strip() for r in rows]
+    assert names == ["kernel__update_stress", "kernel__update_vel", "global__comm", "others"]
+    t = [float(r.group(4)) for r in rows]
+    assert t[0] > 0 and t[1] > 0 and t[2] == 0.0                     # one rank: no exchange
+    assert abs(float(rows[-1].group(5)) - sum(t)) < 2e-3 and abs(float(rows[-1].group(7)) - 100.0) < 0.01
+    assert abs(sum(t) - run["loop_seconds"]) < 5e-3
+    quiet = write_case(tmp_path / "q", nt=4, title="quiet", extra="stopwatch_mode = .false.")
+    r2 = Swpc3d(quiet, base_dir=tmp_path / "q", nm=3)
+    r2.attach_device(0)
+    r2.run(1, 4)
+    r2.write_tim(tmp_path / "o2")
+    assert not (tmp_path / "o2" / "quiet.tim").exists()
