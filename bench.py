@@ -4,9 +4,17 @@
 Metric (BASELINE.json): 3-D viscoelastic cell-updates/s (+ % of the HBM roofline).
   N = 1 : BASELINE configs[3] -- swpc_3d, NM=3 GZB, ADE-CFS PML (na=20), synthetic layered model (the 8-layer table
           of the reference's example/lhm.dat), 1024 x 1024 x 512 on one B200, float64 fields (reference default MP=DP).
+          After the headline, on the same GPU and under the same clock sampler ("secondary", CUDA-event timed):
+            psv       BASELINE configs[1]: swpc_psv 16384 x 8192, NM=3, PML
+            elastic   BASELINE configs[2]: swpc_3d benchmark_mode half-space 512^3, NM=0
+            f32       configs[3] with float32 fields (the reference's MP=SP build)
+          and "weak_base": the per-GPU workload of the N>1 runs (lhm_rmed, 512 x 1024 x 1024, 1x1) -- the base the
+          weak-scaling efficiency has to be taken against.
   N > 1 : BASELINE configs[4] shape -- weak scaling, 512 x 1024 x 1024 cells per GPU, x-y decomposition 2x1 / 4x1 / 4x2,
           NCCL send/recv halo exchange overlapped with the core sweeps; synthetic heterogeneous crust = the layered table
-          with Gaussian random media per layer (vmodel lhm_rmed).
+          with Gaussian random media per layer (vmodel lhm_rmed).  Before the timed region a small decomposed case runs
+          over NCCL on the N GPUs and is compared bit for bit with the same decomposition emulated on rank 0's GPU
+          ("parity"; the emulated exchange is what the GPU test-suite ties to the oracle); a mismatch exits non-zero.
 A "step" is one iteration of main.f90:119-139 (stress sweep, stress glut, halo, velocity sweep, halo).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -44,8 +52,36 @@ LHM = """# depth  rho  vp  vs  Qp  Qs   (example/lhm.dat of the reference)
     425          3.7       9.3      5.31      600     300
 """
 
+# the reference's example/input.inf:55-83 snapshot block (6 products on, every 5 steps, netCDF), used by the e2e_snap leg
+SNAP_BLOCK = """
+ snp_format = 'netcdf'
+ xy_ps%sw = .false.
+ xz_ps%sw = .true.
+ yz_ps%sw = .false.
+ fs_ps%sw = .false.
+ ob_ps%sw = .true.
+ xy_v%sw = .false.
+ xz_v%sw = .true.
+ yz_v%sw = .false.
+ fs_v%sw = .false.
+ ob_v%sw = .true.
+ xy_u%sw = .false.
+ xz_u%sw = .true.
+ yz_u%sw = .false.
+ fs_u%sw = .false.
+ ob_u%sw = .true.
+ z0_xy = 7.0
+ x0_yz = 0.0
+ y0_xz = 0.0
+ ntdec_s = 5
+ idec = 2
+ jdec = 2
+ kdec = 2
+"""
 
-def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: int, dx=0.5, dt=0.025, na=20, hetero=False) -> Path:
+
+def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: int, dx=0.5, dt=0.025, na=20, hetero=False,
+                   benchmark=False, extra="") -> Path:
     d.mkdir(parents=True, exist_ok=True)
     (d / "lhm.dat").write_text(LHM)
     if hetero:
@@ -71,6 +107,7 @@ def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: i
  title = 'bench'
  odir = './out'
  ntdec_r = 10
+ benchmark_mode = {'.true.' if benchmark else '.false.'}
  nproc_x = {npx}
  nproc_y = {npy}
  nx = {nx}
@@ -101,21 +138,78 @@ def write_workload(d: Path, nx: int, ny: int, nz: int, nt: int, npx: int, npy: i
  na = {na}
 {vm}
  munk_profile = .true.
+{extra}
 """
     p = d / "input.inf"
     p.write_text(inf)
     return p
 
 
-def cell_counts(run) -> tuple[int, int]:
-    """(interior cells, absorber cells) of this rank (m_global.f90:334-376)."""
-    nz, na = run["nz"], run["na"]
-    nxk = max(0, run["iend_k"] - run["ibeg_k"] + 1)
-    nyk = max(0, run["jend_k"] - run["jbeg_k"] + 1)
+def write_psv_workload(d: Path, nx: int, nz: int, nt: int, dx=0.25, dt=0.0125, na=20) -> Path:
+    """BASELINE configs[1] (SURVEY 8d input 2): swpc_psv, layered model, one moment-tensor source, 16 stations on a line."""
+    d.mkdir(parents=True, exist_ok=True)
+    (d / "lhm.dat").write_text(LHM)
+    (d / "source.dat").write_text("# x y z tbeg trise mo mxx myy mzz myz mxz mxy\n 0.0 0.0 10.0 0.1 2.0 1.e15 0.7 0.0 -0.3 0.0 0.5 0.0\n")
+    (d / "stloc.xy").write_text("\n".join(f"{(a - 7.5) * nx * dx / 20.0:.3f} 0.0 0.0 p{a:02d} obb" for a in range(16)) + "\n")
+    p = d / "input.inf"
+    p.write_text(f"""
+ title = 'benchpsv'
+ odir = './out'
+ ntdec_r = 10
+ nproc_x = 1
+ nx = {nx}
+ nz = {nz}
+ nt = {nt}
+ dx = {dx}
+ dz = {dx}
+ dt = {dt}
+ na = {na}
+ xbeg = {-nx * dx / 2}
+ zbeg = -10.0
+ tbeg = 0.0
+ vcut = 1.5
+ abc_type = 'pml'
+ vmodel_type = 'lhm'
+ fn_lhm = 'lhm.dat'
+ fq_min = 0.02
+ fq_max = 2.0
+ fq_ref = 1.0
+ fn_stf = 'source.dat'
+ stftype = 'kupper'
+ stf_format = 'xym0ij'
+ fn_stloc = 'stloc.xy'
+ st_format = 'xy'
+ ntdec_w = 5
+ sw_wav_v = .true.
+""")
+    return p
+
+
+def cell_counts(run, region=None) -> tuple[int, int]:
+    """(interior cells, absorber cells) of this rank (m_global.f90:334-376), optionally restricted to the owned columns
+    li0..li1 x lj0..lj1 (local, inclusive) -- the core region of the boundary-first overlap."""
+    nz = run["nz"]
+    li0, li1, lj0, lj1 = region if region else (0, run["nxp"] - 1, 0, run["nyp"] - 1)
+    ki0, ki1 = max(run["ibeg_k"] - run["ibeg"], li0), min(run["iend_k"] - run["ibeg"], li1)
+    kj0, kj1 = max(run["jbeg_k"] - run["jbeg"], lj0), min(run["jend_k"] - run["jbeg"], lj1)
     nzk = max(0, run["kend_k"] - run["kbeg_k"] + 1)
-    interior = nxk * nyk * nzk
-    total = run["nxp"] * run["nyp"] * nz
+    interior = max(0, ki1 - ki0 + 1) * max(0, kj1 - kj0 + 1) * nzk
+    total = max(0, li1 - li0 + 1) * max(0, lj1 - lj0 + 1) * nz
     return interior, total - interior
+
+
+def core_region(run, world: int) -> tuple[int, int, int, int]:
+    """Owned columns swept on the launch stream inside the timed brackets when the exchange is overlapped: everything but the
+    two outermost planes towards each neighbour (abi.cu core_region)."""
+    npx, npy, me = run["nproc_x"], run["nproc_y"], run["myid"]
+    idx, idy = me % npx, me // npx
+    li0, li1, lj0, lj1 = 0, run["nxp"] - 1, 0, run["nyp"] - 1
+    if world > 1:
+        if idx > 0: li0 += 2
+        if idx < npx - 1: li1 -= 2
+        if idy > 0: lj0 += 2
+        if idy < npy - 1: lj1 -= 2
+    return li0, li1, lj0, lj1
 
 
 def bytes_per_cell(nm: int, W: int) -> dict:
@@ -125,6 +219,15 @@ def bytes_per_cell(nm: int, W: int) -> dict:
         "stress_pml": 3 * W + 12 * W + 8 + 9 * 8,
         "vel_interior": 6 * W + 6 * W + 4,
         "vel_pml": 6 * W + 6 * W + 4 + 9 * 8,
+    }
+
+
+def psv_bytes_per_cell(nm: int, W: int) -> dict:
+    return {
+        "stress_interior": 2 * W + 6 * W + (16 if nm > 0 else 8) + 3 * nm * 8,
+        "stress_pml": 2 * W + 6 * W + 8 + 4 * 8,
+        "vel_interior": 3 * W + 4 * W + 4,
+        "vel_pml": 3 * W + 4 * W + 4 + 4 * 8,
     }
 
 
@@ -225,6 +328,218 @@ def cpu_port_throughput(nm: int, sample=(384, 384, 384), steps: int = 24, warmup
             "seconds": dt, "ms_per_step": dt / steps * 1e3}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# secondary lines (N = 1): each a separate run on the same GPU, CUDA events on the library's launch stream
+def time_3d_case(inf: Path, wdir: Path, *, nm: int, fdt, K: int, Wm: int, device: int, snap: bool = False) -> dict:
+    """W warm-up + K timed steps of one swpc_3d case (state resident in HBM), the per-sweep stopwatches, and the roofline
+    fractions on algorithmic bytes.  With `snap` the timed region is Swpc3d.run() with the snapshot files open (host clock)."""
+    from openswpc_b200.swpc3d import Swpc3d
+
+    W = np.dtype(fdt).itemsize
+    run = Swpc3d(inf, base_dir=wdir, nm=nm, myid=0, field_dtype=fdt)
+    try:
+        run.attach_device(device)
+        out = {"grid": [run["nx"], run["ny"], run["nz"]], "nm": nm, "field_type": "f64" if W == 8 else "f32", "steps": K, "warmup": Wm}
+        cells = run["nx"] * run["ny"] * run["nz"]
+        if snap:
+            run.snap_open(wdir / "snap")
+        run.run(1, Wm)
+        run.device_call("swpc3d_sync")
+        if snap:   # the public call with the reference example's product set (host wall clock: the files are part of it)
+            t0 = time.perf_counter()
+            run.run(Wm + 1, Wm + K)
+            run.device_call("swpc3d_sync")
+            ms = (time.perf_counter() - t0) * 1e3
+            t1 = time.perf_counter()
+            run.snap_close()
+            out["close_s"] = time.perf_counter() - t1
+            out.update({"ms_per_step": ms / K, "value": cells * K / (ms / 1e3), "unit": "cell-updates/s"})
+            return out
+        run.set_option("kernel_timing", 1)
+        l0 = run.info("launches")
+        run.timer_start()
+        run.device_call("swpc3d_run", Wm + 1, Wm + K)
+        ms = run.timer_stop()
+        run.device_call("swpc3d_sync")
+        ms_s, ms_v = run.info("ms_stress"), run.info("ms_vel")
+        run.set_option("kernel_timing", 0)
+        interior, pml = cell_counts(run)
+        bpc = bytes_per_cell(nm, W)
+        sb = interior * bpc["stress_interior"] + pml * bpc["stress_pml"]
+        vb = interior * bpc["vel_interior"] + pml * bpc["vel_pml"]
+        peak, _ = measured_peak()
+        out.update({"value": cells * K / (ms / 1e3), "unit": "cell-updates/s", "ms_per_step": ms / K, "gpu_launches": int(run.info("launches") - l0),
+                    "ms_stress": ms_s, "ms_vel": ms_v, "cells_interior": interior, "cells_absorber": pml,
+                    "bytes_per_cell_domain_weighted": (sb + vb) / cells,
+                    "roofline": {"bound": "hbm", "achieved": (sb + vb) / (ms / K / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": (sb + vb) / (ms / K / 1e3) / 1e9 / peak, "what": "algorithmic bytes of both sweeps / step time",
+                                 "stress_frac": sb / (ms_s / 1e3) / 1e9 / peak if ms_s > 0 else None,
+                                 "vel_frac": vb / (ms_v / 1e3) / 1e9 / peak if ms_v > 0 else None}})
+        return out
+    finally:
+        run.close()
+
+
+def time_psv_case(inf: Path, wdir: Path, *, nm: int, K: int, Wm: int, device: int) -> dict:
+    from openswpc_b200 import _lib
+    from openswpc_b200.swpc_psv import SwpcPsv
+
+    run = SwpcPsv(inf, base_dir=wdir, nm=nm)
+    try:
+        run.attach_device(device)
+        lib, h = run.lib, run.handle
+
+        def call(fn, *a):
+            _lib.check_psv(getattr(lib, fn)(h, *a))
+
+        def info(key):
+            v = C.c_double()
+            call("swpcpsv_get_info", key.encode(), C.byref(v))
+            return v.value
+
+        run.run(1, Wm)
+        call("swpcpsv_sync")
+        call("swpcpsv_set_option", b"kernel_timing", 1)
+        l0 = info("launches")
+        call("swpcpsv_timer_start")
+        call("swpcpsv_run", Wm + 1, Wm + K)
+        msv = C.c_float()
+        call("swpcpsv_timer_stop", C.byref(msv))
+        call("swpcpsv_sync")
+        ms = msv.value
+        ms_s, ms_v = info("ms_stress"), info("ms_vel")
+        ci, ca = info("cells_interior"), info("cells_absorber")
+        bpc = psv_bytes_per_cell(nm, 8)
+        sb = ci * bpc["stress_interior"] + ca * bpc["stress_pml"]
+        vb = ci * bpc["vel_interior"] + ca * bpc["vel_pml"]
+        peak, _ = measured_peak()
+        cells = run["nx"] * run["nz"]
+        return {"grid": [run["nx"], run["nz"]], "nm": nm, "field_type": "f64", "steps": K, "warmup": Wm, "value": cells * K / (ms / 1e3),
+                "unit": "cell-updates/s", "ms_per_step": ms / K, "gpu_launches": int(info("launches") - l0), "ms_stress": ms_s, "ms_vel": ms_v,
+                "cells_interior": int(ci), "cells_absorber": int(ca), "bytes_per_cell_domain_weighted": (sb + vb) / cells,
+                "roofline": {"bound": "hbm", "achieved": (sb + vb) / (ms / K / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": (sb + vb) / (ms / K / 1e3) / 1e9 / peak, "what": "algorithmic bytes of both sweeps / step time",
+                             "stress_frac": sb / (ms_s / 1e3) / 1e9 / peak if ms_s > 0 else None,
+                             "vel_frac": vb / (ms_v / 1e3) / 1e9 / peak if ms_v > 0 else None}}
+    finally:
+        run.close()
+
+
+def secondary_lines(td: Path, K: int, Wm: int, device: int, which: set) -> dict:
+    out = {}
+
+    def guard(name, fn):
+        if name not in which:
+            return
+        t0 = time.perf_counter()
+        try:
+            out[name] = fn()
+            out[name]["wall_s"] = time.perf_counter() - t0
+        except Exception as e:   # a secondary line never voids the headline
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+
+    guard("psv", lambda: dict(time_psv_case(write_psv_workload(td / "psv", 16384, 8192, Wm + K + 2), td / "psv", nm=3, K=K, Wm=Wm, device=device),
+                              workload="BASELINE configs[1]: swpc_psv 2-D P-SV viscoelastic NM=3, ADE-CFS PML na=20, layered model, 16384x8192, f64 fields"))
+    guard("elastic", lambda: dict(time_3d_case(write_workload(td / "el", 512, 512, 512, Wm + K + 2, 1, 1, benchmark=True), td / "el", nm=0, fdt=np.float64,
+                                               K=K, Wm=Wm, device=device),
+                                  workload="BASELINE configs[2]: swpc_3d elastic NM=0, benchmark_mode homogeneous half-space (m_medium.f90:55-74), "
+                                           "point source, PML na=20, 512x512x512, f64 fields"))
+    guard("f32", lambda: dict(time_3d_case(write_workload(td / "f32", 1024, 1024, 512, Wm + K + 2, 1, 1), td / "f32", nm=3, fdt=np.float32,
+                                           K=K, Wm=Wm, device=device),
+                              workload="BASELINE configs[3] with float32 fields (the reference's MP=SP build, m_global.f90:30): NM=3, PML, lhm, 1024x1024x512"))
+    return out
+
+
+def weak_base_line(td: Path, K: int, Wm: int, device: int) -> dict:
+    t0 = time.perf_counter()
+    try:
+        r = time_3d_case(write_workload(td / "wb", 512, 1024, 1024, Wm + K + 2, 1, 1, hetero=True), td / "wb", nm=3, fdt=np.float64, K=K, Wm=Wm, device=device)
+        r["workload"] = ("the per-GPU workload of the N>1 runs on ONE GPU: lhm_rmed heterogeneous crust, 512x1024x1024, 1x1, NM=3, PML, f64 -- "
+                         "weak-scaling efficiency at N GPUs = value(N) / (N * this value)")
+        r["wall_s"] = time.perf_counter() - t0
+        return r
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:400]}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# N > 1: the NCCL exchange against the emulated one, bit for bit, on the boxes the driver runs
+def nccl_parity(td: Path, rank: int, world: int, local: int, npx: int, npy: int, nt: int = 30) -> dict | None:
+    """A small decomposed heterogeneous case (lhm_rmed, 40 x 36 columns per rank, nz = 48, NM=3, PML na=6; boundary-first overlap on,
+    as in the timed run) stepped over NCCL on the N GPUs, and the same decomposition stepped as emulated ranks on rank 0's GPU
+    with swpc3d_comm_local (the exchange the single-GPU parity tests tie to the oracle).  Rank 0 compares every rank's nine
+    fields over the whole memory box (owned cells and halo planes), the station traces and the progress amplitudes."""
+    import torch.distributed as dist
+
+    from openswpc_b200 import _lib
+    from openswpc_b200.distributed import allreduce_minmax, attach_nccl
+    from openswpc_b200.swpc3d import Swpc3d
+
+    bx, by, nz = 40, 36, 48
+    nx, ny = bx * npx, by * npy
+    d = td / f"parity{rank}"
+    inf = write_workload(d, nx, ny, nz, nt, npx, npy, dx=0.5, dt=0.02, na=6, hetero=True)
+    # the source of the bench workload sits at the centre (on rank seams for even layouts); stations on an 8 x 8 grid
+    run = Swpc3d(inf, base_dir=d, nm=3, myid=rank)
+    allreduce_minmax(run)
+    run.attach_device(local)
+    attach_nccl(run)
+    vm = run.run(1, nt)
+    run.write_sac(d / "out")
+    mine = {"fields": run.download_fields(), "wav": run.wav() if run["nst"] else None, "vm": vm, "vmin": run["vmin"], "vmax": run["vmax"]}
+    run.close()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    res = None
+    if rank == 0:
+        lib = _lib.load()
+        emu = []
+        for q in range(world):
+            e = Swpc3d(inf, base_dir=d, nm=3, myid=q)
+            e.set_minmax(mine["vmin"], mine["vmax"])
+            e.attach_device(local)
+            emu.append(e)
+        hs = (C.c_void_p * world)(*[e.handle for e in emu])
+        for it in range(1, nt + 1):
+            for e in emu:
+                e.device_call("swpc3d_wav_store", it)
+                e.device_call("swpc3d_update_stress")
+                e.device_call("swpc3d_stressglut", it)
+            _lib.check(lib.swpc3d_comm_local(hs, world, 0))
+            for e in emu:
+                e.device_call("swpc3d_update_vel")
+                e.device_call("swpc3d_bodyforce", it)
+            _lib.check(lib.swpc3d_comm_local(hs, world, 1))
+        nf = nw = nst = 0
+        bad = []
+        amp = 0.0
+        for q, e in enumerate(emu):
+            ref = e.download_fields()
+            for n, a in ref.items():
+                amp = max(amp, float(np.abs(a).max()))
+                if np.array_equal(a, gathered[q]["fields"][n]):
+                    nf += 1
+                else:
+                    bad.append(f"rank {q} field {n}")
+            if e["nst"]:
+                e.write_sac(d / f"emu{q}")
+                nst += e["nst"]
+                if np.array_equal(e.wav(), gathered[q]["wav"]):
+                    nw += e["nst"] * 3
+                else:
+                    bad.append(f"rank {q} traces")
+            e.close()
+        vm_same = all(np.array_equal(g["vm"], gathered[0]["vm"]) for g in gathered)
+        res = {"ok": not bad and vm_same and amp > 0, "ranks": world, "decomposition": [npx, npy], "steps": nt, "grid": [nx, ny, nz],
+               "fields_bit_exact": nf, "fields_total": 9 * world, "traces_bit_exact": nw, "traces_total": 3 * nst,
+               "progress_lines_identical_on_all_ranks": vm_same, "max_abs_field": amp, "mismatches": bad[:8],
+               "what": "NCCL send/recv run on N GPUs (boundary-first overlap) vs the same ranks emulated on one GPU with swpc3d_comm_local; "
+                       "whole memory boxes incl. halo planes, station traces, progress amplitudes"}
+    box = [res]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -233,6 +548,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--grid", default="", help="nx,ny,nz per GPU (development only; default = the BASELINE workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary / weak_base / e2e_snap runs (development, profiling)")
+    ap.add_argument("--secondary", default="", help="comma separated subset of psv,elastic,f32,weak_base,e2e_snap (development)")
+    ap.add_argument("--hetero", type=int, default=-1, help="1: lhm_rmed model, 0: layered lhm (default: lhm at N=1, lhm_rmed at N>1)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--opts", default="", help="key=value,... library options (development only, e.g. overlap=0)")
     a = ap.parse_args()
@@ -251,7 +569,7 @@ def main():
     else:
         bx, by, bz = 512, 1024, 1024
     nx, ny, nz = bx * npx, by * npy, bz
-    hetero = world > 1
+    hetero = (world > 1) if a.hetero < 0 else bool(a.hetero)
     model = ("synthetic heterogeneous crust (lhm_rmed: 8 layers x Gaussian random media, eps = 3 %)" if hetero
              else "synthetic layered model (lhm, 8 layers)")
     workload = (f"swpc_3d viscoelastic NM=3 GZB + ADE-CFS PML na=20, {model}, "
@@ -265,6 +583,8 @@ def main():
         if rank != 0:
             return
         res = cpu_port_throughput(nm, steps=max(1, a.steps), warmup=max(1, a.warmup))
+        config = dict(config, reference_sample="384x384x384 sub-grid of the workload (a bounded sample: the rate metric is size-independent on "
+                                               "the CPU; the host does not change with N, so at N>1 this is still ONE host)")
         line = {"metric": "cell_updates_per_s", "value": res["value"], "unit": "cell-updates/s", "n_gpus": n_gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config, "impl": "reference",
@@ -296,6 +616,16 @@ def main():
     K, Wm = a.steps, max(a.warmup, 3)
     nt = Wm + 2 * K + 2
     td = tempfile.TemporaryDirectory()
+
+    parity = None
+    if world > 1:
+        parity = nccl_parity(Path(td.name), rank, world, local, npx, npy)
+        if not parity or not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": "cell_updates_per_s", "value": None, "n_gpus": world, "parity": parity,
+                                  "error": "NCCL run differs from the emulated decomposition"}), flush=True)
+            raise SystemExit(3)
+
     wdir = Path(td.name) / f"rank{rank}"
     inf = write_workload(wdir, nx, ny, nz, nt, npx, npy, hetero=hetero)
     t_setup = time.perf_counter()
@@ -366,8 +696,13 @@ def main():
     h2d = 4.0 * nsrc
     d2h = (12.0 * len(vm) + 4.0 * 3 * nst * ntw) / K
     interior, pml = cell_counts(run)
+    # with the boundary-first overlap the sweep stopwatches bracket the CORE region on the launch stream (the boundary slabs
+    # run on the exchange stream): count the cells those brackets cover
+    overlapped = world > 1 and "overlap=0" not in a.opts
+    c_interior, c_pml = cell_counts(run, core_region(run, world)) if overlapped else (interior, pml)
+    exposed_rank = ms / K - ms_stress - ms_vel   # this rank's step time outside its two sweep brackets (not clamped)
     stats = torch.tensor([ms, t_e2e * 1e3, launches, h2d, d2h, float(interior), float(pml), ms_stress, ms_vel, ms_halo,
-                          halo_bytes / max(n_halo, 1.0), ms_halo_alone], dtype=torch.float64, device="cuda")
+                          halo_bytes / max(n_halo, 1.0), ms_halo_alone, exposed_rank], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -376,8 +711,8 @@ def main():
     else:
         mx = sm = stats
     mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
+    run.close()
     if rank != 0:
-        run.close()
         return
 
     cells = nx * ny * nz
@@ -386,32 +721,38 @@ def main():
     e2e_value = cells * K / (e2e_ms_max / 1e3)
     bpc = bytes_per_cell(nm, W)
     # roofline of the dominant kernel (fused stress sweep) on rank 0: algorithmic bytes of ONE launch / its mean duration
-    stress_bytes = interior * bpc["stress_interior"] + pml * bpc["stress_pml"]
-    vel_bytes = interior * bpc["vel_interior"] + pml * bpc["vel_pml"]
+    stress_bytes = c_interior * bpc["stress_interior"] + c_pml * bpc["stress_pml"]
+    vel_bytes = c_interior * bpc["vel_interior"] + c_pml * bpc["vel_pml"]
+    step_bytes = (interior * (bpc["stress_interior"] + bpc["vel_interior"]) + pml * (bpc["stress_pml"] + bpc["vel_pml"]))
     peak, peak_src = measured_peak()
     achieved = stress_bytes / (ms_stress / 1e3) / 1e9 if ms_stress > 0 else None
-    traffic = None
+    traffic, traffic_source = None, None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
             tj = json.loads(tp.read_text())
             key = f"{bx}x{by}x{bz}_{a.dtype}_nm{nm}"
             traffic = tj.get(key, {}).get("stress_dram_bytes_per_launch")
+            if traffic is not None:
+                traffic_source = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of the sweep's launches, NOT measured in this run: "
+                                  + str(tj[key].get("source", "profiles/traffic.json")))
         except Exception:
             traffic = None
-    step_bytes = stress_bytes + vel_bytes
     line = {
         "metric": "cell_updates_per_s", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
         "config": config,
-        "roofline": {"bound": "hbm", "kernel": "fused stress sweep: stress_tma<F,NM=3> (interior tiles) + sweep_direct<F,3,1> (absorber shell)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "fused stress sweep: stress_tma<F,NM=3> (interior tiles) + absorber-shell kernels", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_source,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": stress_bytes, "ms_per_launch": ms_stress,
-                     "bytes_per_cell": bpc, "cells_interior": interior, "cells_absorber": pml},
+                     "bytes_per_cell": bpc, "cells_interior": c_interior, "cells_absorber": c_pml,
+                     "cells_note": ("cells of the core region the stopwatch brackets cover (boundary slabs run on the exchange stream)"
+                                    if overlapped else "all owned cells of rank 0")},
         "roofline_step": {"achieved": step_bytes / (ms_max / K / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                           "frac": step_bytes / (ms_max / K / 1e3) / 1e9 / peak, "ms_vel_per_launch": ms_vel,
                           "vel_achieved": vel_bytes / (ms_vel / 1e3) / 1e9 if ms_vel > 0 else None,
-                          "note": "per-GPU algorithmic bytes of both sweeps / step time of the slowest rank"},
+                          "note": "per-GPU algorithmic bytes of both sweeps (all owned cells of rank 0) / step time of the slowest rank"},
         "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": float(sm[3]), "d2h_bytes_per_step": float(sm[4]),
                 "ms_per_step": e2e_ms_max / K, "sac_files": nfiles,
                 "what": "Swpc3d.run() (host-evaluated source terms H2D every step, max-amplitude D2H every ntdec_r steps) + station "
@@ -426,19 +767,41 @@ def main():
             "nvlink_peak_GBs_per_direction": 900.0,
             "nvlink_frac": float(mx[10]) / (float(mx[11]) / 1e3) / 1e9 / 900.0 if mx[11] > 0 else None,
             "nvlink_frac_note": "bytes sent by the busiest rank / time of the exchange run alone (pack + NCCL + unpack kernels included) / 900 GB/s",
-            "exposed_ms_per_step": max(0.0, ms_max / K - float(mx[7]) - float(mx[8])),
+            "outside_sweeps_ms_per_step_max": float(mx[12]),
+            "outside_sweeps_note": "max over ranks of (step - core stress sweep - core velocity sweep) on that rank, not clamped: source, "
+                                   "station and join overhead plus any exchange tail the core sweep did not cover; the exposed cost of "
+                                   "the exchange proper is ms_per_step here minus weak_base.ms_per_step of the N=1 line (same per-GPU workload)",
             "overlap": "boundary-first: exchange stream overlaps the core sweeps"},
         "gpu_launches": int(sm[2]),
-        "clocks": clocks,
         "progress_lines": [[float(x) for x in r] for r in vm[-2:]],
     }
+    if parity is not None:
+        line["parity"] = parity
+    line["clocks"] = clocks
+    if world == 1 and not a.no_secondary and not a.grid:
+        which = set(filter(None, a.secondary.split(","))) or {"psv", "elastic", "f32", "weak_base", "e2e_snap"}
+        Ks, Ws = min(K, 20), 3
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        line["secondary"] = secondary_lines(Path(td.name), Ks, Ws, local, which)
+        if "weak_base" in which:
+            line["weak_base"] = weak_base_line(Path(td.name), Ks, Ws, local)
+        if "e2e_snap" in which:
+            try:   # the public call with the reference example's snapshot product set (example/input.inf:55-83) on the headline grid
+                inf_s = write_workload(Path(td.name) / "snap", nx, ny, nz, Ws + Ks + 2, 1, 1, hetero=hetero, extra=SNAP_BLOCK)
+                r = time_3d_case(inf_s, Path(td.name) / "snap", nm=nm, fdt=fdt, K=Ks, Wm=Ws, device=local, snap=True)
+                r["what"] = ("Swpc3d.run() with the snapshot files of example/input.inf:55-83 open (xz/ob x ps/v/u, ntdec_s=5, decimation 2, netCDF): "
+                             "slice kernels, D2H and file records included; compare ms_per_step with e2e.ms_per_step")
+                line["e2e_snap"] = r
+            except Exception as e:
+                line["e2e_snap"] = {"error": f"{type(e).__name__}: {e}"[:400]}
+        line["secondary"]["clocks"] = sampler2.stop()
     if world == 1 and not a.no_cpu_baseline:
         try:
             line["cpu_baseline"] = {k: v for k, v in cpu_port_throughput(nm).items() if k in ("value", "unit", "cores", "kind", "sample")}
         except Exception as e:   # the baseline is informative; never let it void the GPU measurement
             line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
-    run.close()
     td.cleanup()
 
 

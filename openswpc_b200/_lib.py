@@ -8,6 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
@@ -82,8 +83,10 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     global LIB_PATH
-    if os.environ.get("SWPC3D_LIB"):   # development: pick an experimental build of the same ABI
+    if os.environ.get("SWPC3D_LIB") and os.environ.get("SWPC3D_DEV") == "1":
+        # kernel development only (both variables needed, and it says so on stderr): an experimental build of the same ABI
         LIB_PATH = Path(os.environ["SWPC3D_LIB"])
+        print(f"openswpc_b200: SWPC3D_DEV=1, loading the experimental build {LIB_PATH}", file=sys.stderr, flush=True)
     if not LIB_PATH.exists():
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(the swpc3d_b200 path has no CPU fallback)")

@@ -14,6 +14,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -51,6 +53,8 @@ struct NcclApi {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t *) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
 };
 static NcclApi g_nccl;
 static int nccl_load() {
@@ -74,6 +78,8 @@ static int nccl_load() {
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
+    SYM(CommGetAsyncError, "ncclCommGetAsyncError");
+    SYM(CommAbort, "ncclCommAbort");
 #undef SYM
     return 0;
 }
@@ -131,7 +137,7 @@ struct swpc3d_handle {
     float M0 = 1.f, UC = 1e-15f;
     // Green's-function mode (m_green.f90)
     int ng = 0, g_ncmp = 6, g_bforce = 0, g_ntdec_w = 1, g_ntw = 0, g_stf = 3, g_is_src = 0, g_src[3] = {0, 0, 0};
-    float g_f[3] = {0, 0, 0}, g_trise = 1.0f, g_dt_dxyz = 0.0f;
+    float g_f[3] = {0, 0, 0}, g_trise = 1.0f, g_dt_dxyz = 0.0f, g_tbeg = 0.0f;
     int *g_ijk = nullptr;
     float *g_acc = nullptr, *g_gf = nullptr;
     unsigned int *vmax_d = nullptr;
@@ -145,6 +151,8 @@ struct swpc3d_handle {
     int nbr[4] = {-1, -1, -1, -1};
     ncclComm_t comm = nullptr;
     int comm_rank = -1, comm_size = 0;
+    int comm_timeout_s = 1800;             // option "comm_timeout_s": a host-side wait on a stream that carries NCCL work gives up after this
+    bool comm_dead = false;                // the communicator was aborted (peer failure / timeout): every later exchange fails at once
     // streams
     cudaStream_t st = nullptr;
     cudaStream_t side[5] = {};             // absorber-shell boxes run beside the TMA interior kernel
@@ -180,6 +188,48 @@ struct swpc3d_handle {
     size_t cev_used = 0;
     double halo_bytes = 0.0;              // bytes this rank sent since kernel_timing was switched on
 };
+
+// Host-side wait on a stream.  Without a communicator this is cudaStreamSynchronize.  With one, the stream may carry NCCL
+// work that never completes when a peer has died or diverged (it left the time loop through the divergence abort of
+// m_report.f90:144-151, say): poll the stream and ncclCommGetAsyncError instead, and turn an asynchronous NCCL error or a
+// timeout (option "comm_timeout_s") into the reference's clean abort -- ncclCommAbort, an error message, a non-zero return
+// -- where a blocking synchronise would hang for ever.
+static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
+    if (!h->comm || !g_nccl.CommGetAsyncError) {
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (long long spin = 0;; spin++) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return 0;
+        if (e != cudaErrorNotReady) {
+            char b[256];
+            snprintf(b, sizeof(b), "stream_wait: %s", cudaGetErrorString(e));
+            return fail(b);
+        }
+        if ((spin & 255) == 255) {
+            ncclResult_t ar = ncclSuccess;
+            const ncclResult_t qr = g_nccl.CommGetAsyncError(h->comm, &ar);
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const bool timeout = h->comm_timeout_s > 0 && waited > (double)h->comm_timeout_s;
+            if (qr != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress) || timeout) {
+                char b[384];
+                snprintf(b, sizeof(b), "halo exchange aborted on rank %d: %s (waited %.1f s); communicator destroyed with ncclCommAbort",
+                         h->comm_rank, timeout ? "time-out, a neighbour rank stopped exchanging" : g_nccl.GetErrorString(qr != ncclSuccess ? qr : ar), waited);
+                g_nccl.CommAbort(h->comm);
+                h->comm = nullptr;
+                h->comm_dead = true;
+                return fail(b);
+            }
+            if (waited > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    }
+}
+#define WAIT(h_, st_)                        \
+    do {                                     \
+        if (stream_wait((h_), (st_))) return 1; \
+    } while (0)
 
 static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
 
@@ -462,6 +512,8 @@ extern "C" int swpc3d_download_fields(swpc3d_handle *h, void *Vx, void *Vy, void
     return 0;
 }
 
+static void snap_dims(const swpc3d_snap_cfg &c, int product, int &n1, int &n2, int &nvar);
+
 extern "C" int swpc3d_zero_state(swpc3d_handle *h) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->dev));
@@ -470,6 +522,20 @@ extern "C" int swpc3d_zero_state(swpc3d_handle *h) {
     if (h->aux) CK(cudaMemsetAsync(h->aux, 0, (size_t)h->naux * 18 * sizeof(float), h->st));
     if (h->wav) CK(cudaMemsetAsync(h->wav, 0, (size_t)h->ntw * 3 * h->nst * sizeof(float), h->st));
     if (h->wav_acc) CK(cudaMemsetAsync(h->wav_acc, 0, (size_t)9 * h->nst * sizeof(float), h->st));
+    // every accumulating product: displacement / stress / strain traces, Green's-function sums, snapshot slices and maxima
+    const size_t n3 = (size_t)h->ntw * 3 * h->nst * sizeof(float);
+    if (h->wav_u) CK(cudaMemsetAsync(h->wav_u, 0, n3, h->st));
+    if (h->wav_s) CK(cudaMemsetAsync(h->wav_s, 0, 2 * n3, h->st));
+    if (h->wav_e) CK(cudaMemsetAsync(h->wav_e, 0, 2 * n3, h->st));
+    if (h->g_acc) CK(cudaMemsetAsync(h->g_acc, 0, (size_t)12 * h->ng * sizeof(float), h->st));
+    if (h->g_gf) CK(cudaMemsetAsync(h->g_gf, 0, (size_t)h->g_ntw * h->g_ncmp * h->ng * sizeof(float), h->st));
+    for (int q = 0; q < 15; q++) {
+        if (!h->snap_buf[q]) continue;
+        int n1, n2, nvar;
+        snap_dims(h->snap, q, n1, n2, nvar);
+        CK(cudaMemsetAsync(h->snap_buf[q], 0, (size_t)n1 * n2 * nvar * sizeof(float), h->st));
+        if (h->snap_max[q]) CK(cudaMemsetAsync(h->snap_max[q], 0, (size_t)n1 * n2 * 3 * sizeof(float), h->st));
+    }
     CK(cudaStreamSynchronize(h->st));
     return 0;
 }
@@ -1038,7 +1104,7 @@ extern "C" int swpc3d_set_green(swpc3d_handle *h, int32_t ng, const int32_t *ig,
     cudaFree(h->g_ijk); cudaFree(h->g_acc); cudaFree(h->g_gf);
     h->g_ijk = nullptr; h->g_acc = h->g_gf = nullptr;
     h->ng = ng; h->g_bforce = bforce != 0; h->g_ncmp = bforce ? 9 : 6; h->g_ntdec_w = ntdec_w; h->g_ntw = ntw;
-    h->g_stf = stf_code(stftype); h->g_trise = trise; h->tbeg = tbeg;
+    h->g_stf = stf_code(stftype); h->g_trise = trise; h->g_tbeg = tbeg;
     h->g_f[0] = fx1; h->g_f[1] = fy1; h->g_f[2] = fz1;
     h->g_dt_dxyz = (float)((double)h->g.dt / (h->g.dx * h->g.dy * h->g.dz));   // real(dt / (dx*dy*dz)), m_green.f90:156
     h->g_is_src = 0;
@@ -1089,7 +1155,7 @@ extern "C" int swpc3d_green_store(swpc3d_handle *h, int32_t it) {
 extern "C" int swpc3d_green_source(swpc3d_handle *h, int32_t it) {
     if (ready(h)) return 1;
     if (!h->g_is_src) return 0;
-    const float stf = momentrate_host(h->tbeg + it * h->g.dt, h->g_stf, 0.0f, h->g_trise);   // green_tbeg = 0 (:62)
+    const float stf = momentrate_host(h->g_tbeg + it * h->g.dt, h->g_stf, 0.0f, h->g_trise);   // green_tbeg = 0 (:62)
     const float fx = h->g_f[0] * h->g_dt_dxyz * stf, fy = h->g_f[1] * h->g_dt_dxyz * stf, fz = h->g_f[2] * h->g_dt_dxyz * stf;
     if (h->fb == 8) green_source_kernel<double><<<1, 32, 0, h->st>>>(make_params<double>(h), h->g_src[0], h->g_src[1], h->g_src[2], fx, fy, fz);
     else green_source_kernel<float><<<1, 32, 0, h->st>>>(make_params<float>(h), h->g_src[0], h->g_src[1], h->g_src[2], fx, fy, fz);
@@ -1133,7 +1199,7 @@ extern "C" int swpc3d_vmax(swpc3d_handle *h, float out[3]) {
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    WAIT(h, h->st);
     return 0;
 }
 
@@ -1144,7 +1210,7 @@ extern "C" int swpc3d_vmax_global(swpc3d_handle *h, float out[3]) {
     CK(cudaMemcpyAsync(h->vmax_d, out, 3 * sizeof(float), cudaMemcpyHostToDevice, h->st));
     NK(g_nccl.AllReduce(h->vmax_d, h->vmax_d, 3, ncclFloat, ncclMax, h->comm, h->st));
     CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    WAIT(h, h->st);
     return 0;
 }
 
@@ -1153,7 +1219,7 @@ extern "C" int swpc3d_get_wav(swpc3d_handle *h, float *wav_vel) {
     if (h->nst <= 0 || h->ntw <= 0) return 0;
     CK(cudaSetDevice(h->dev));
     CK(cudaMemcpyAsync(wav_vel, h->wav, (size_t)h->ntw * 3 * h->nst * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    WAIT(h, h->st);
     return 0;
 }
 
@@ -1233,6 +1299,7 @@ static int snap_fetch_impl(swpc3d_handle *h, const float *src, size_t n, int roo
     if (h->comm) {
         if (h->snap_tmp_n < n) {
             cudaFree(h->snap_tmp);
+            h->snap_tmp = nullptr; h->snap_tmp_n = 0;
             CK(cudaMalloc(&h->snap_tmp, n * sizeof(float)));
             h->snap_tmp_n = n;
         }
@@ -1240,7 +1307,7 @@ static int snap_fetch_impl(swpc3d_handle *h, const float *src, size_t n, int roo
         from = h->snap_tmp;
     }
     if (out && (!h->comm || h->g.myid == root)) CK(cudaMemcpyAsync(out, from, n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    WAIT(h, h->st);
     return 0;
 }
 
@@ -1262,20 +1329,21 @@ extern "C" int swpc3d_reduce_sum(swpc3d_handle *h, float *buf, int64_t n, int32_
     CK(cudaSetDevice(h->dev));
     if (h->snap_tmp_n < (size_t)n) {
         cudaFree(h->snap_tmp);
+        h->snap_tmp = nullptr; h->snap_tmp_n = 0;
         CK(cudaMalloc(&h->snap_tmp, (size_t)n * sizeof(float)));
         h->snap_tmp_n = (size_t)n;
     }
     CK(cudaMemcpyAsync(h->snap_tmp, buf, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, h->st));
     NK(g_nccl.Reduce(h->snap_tmp, h->snap_tmp, (size_t)n, ncclFloat, ncclSum, root, h->comm, h->st));
     if (h->g.myid == root) CK(cudaMemcpyAsync(buf, h->snap_tmp, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, h->st));
-    CK(cudaStreamSynchronize(h->st));
+    WAIT(h, h->st);
     return 0;
 }
 
 extern "C" int swpc3d_sync(swpc3d_handle *h) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->dev));
-    CK(cudaStreamSynchronize(h->st));
+    WAIT(h, h->st);
     return 0;
 }
 
@@ -1361,6 +1429,7 @@ static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr
     if (!any && !h->zero_outer) return 0;   // all neighbours MPI_PROC_NULL: outer halos keep their zeros
     const FaceLists L = face_lists(h, which);
     if (!any) return h->fb == 8 ? launch_halo<double>(h, L, false, st_) : launch_halo<float>(h, L, false, st_);
+    if (h->comm_dead) return fail("swpc3d_comm_*: the communicator was aborted after a peer failure");
     if (!h->comm) return fail("swpc3d_comm_*: this rank has neighbours but swpc3d_comm_init was not called");
     const bool timed = h->ktiming && h->cev_used < 4096;
     if (timed) {
@@ -1513,7 +1582,7 @@ extern "C" int swpc3d_timer_stop(swpc3d_handle *h, float *ms) {
     if (!h || !ms) return fail("null argument");
     CK(cudaSetDevice(h->dev));
     CK(cudaEventRecord(h->ev1, h->st));
-    CK(cudaEventSynchronize(h->ev1));
+    WAIT(h, h->st);
     CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return 0;
 }
@@ -1536,6 +1605,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "ring_jlen")) { if (value < 1) return fail("ring_jlen must be >= 1"); h->ring_jlen = value; }
     else if (!strcmp(key, "ring_pf")) { if (value < 0 || value > 8) return fail("ring_pf must be 0..8"); h->ring_pf = value; }
     else if (!strcmp(key, "side_streams")) h->use_side = value;
+    else if (!strcmp(key, "comm_timeout_s")) h->comm_timeout_s = value;
     else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }
     else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; h->cev_used = 0; h->halo_bytes = 0.0; }
     else return fail(std::string("unknown option ") + key);
@@ -1555,7 +1625,7 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
         const int w = strstr(key, "stress") ? 0 : 1;
         if (key[0] == 'n') { *value = (double)h->kev_used[w]; return 0; }
         CK(cudaSetDevice(h->dev));
-        CK(cudaStreamSynchronize(h->st));
+        WAIT(h, h->st);
         double sum = 0;
         for (size_t q = 0; q < h->kev_used[w]; q++) {
             float ms = 0;
@@ -1569,8 +1639,8 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
         if (key[0] == 'n') { *value = (double)h->cev_used; return 0; }
         if (key[0] == 'h') { *value = h->halo_bytes; return 0; }
         CK(cudaSetDevice(h->dev));
-        CK(cudaStreamSynchronize(h->st));
-        CK(cudaStreamSynchronize(h->cs));
+        WAIT(h, h->st);
+        WAIT(h, h->cs);
         double sum = 0;
         for (size_t q = 0; q < h->cev_used; q++) {
             float ms = 0;
