@@ -243,62 +243,95 @@ __device__ __forceinline__ void stress_interior(const KParams<F> &p, long long n
     stress_interior_t<F, NM>(p, AccDirect<F, NM>(p, n), k, mi, mj, bnd);
 }
 
-// stress update of one PML cell: absorb_p__update_stress, m_absorb_p.f90:453-519 (both k-loops fused)
+// stress update of one PML cell: absorb_p__update_stress, m_absorb_p.f90:453-519 (both k-loops fused).  As for the interior
+// body the arithmetic is written once against an accessor: AccPmlDirect (global memory, sweep_direct) or AccPmlTma (shared-memory
+// tiles staged by TMA, pml_tma.cuh).  V<f,dk,di,dj>, mu<dk,di,dj>, lam(), S(c) / setS(c, v) with c = xx yy zz yz xz xy,
+// aux(q) / setAux(q, v) with q from enum Aux.
 template <typename F>
-__device__ __forceinline__ void stress_pml(const KParams<F> &p, long long n, int k, int li, int lj, long long a) {
-    const long long si = p.SI, sj = p.SJ, na = p.naux;
-    const F *__restrict__ Vx = p.Vx, *__restrict__ Vy = p.Vy, *__restrict__ Vz = p.Vz;
+struct AccPmlDirect {
+    const KParams<F> &p;
+    long long n;
+    float *A;
+    __device__ __forceinline__ AccPmlDirect(const KParams<F> &p_, long long n_, long long a_) : p(p_), n(n_), A(p_.aux + a_) {}
+    template <int f, int dk, int di, int dj> __device__ __forceinline__ F V() const {
+        const F *b = (f == 0) ? p.Vx : (f == 1) ? p.Vy : p.Vz;
+        return ldro(b + n + dk + di * p.SI + dj * p.SJ);
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float mu() const { return ldro(p.mu + n + dk + di * p.SI + dj * p.SJ); }
+    __device__ __forceinline__ float lam() const { return ldro(p.lam + n); }
+    __device__ __forceinline__ F *sptr(int c) const { return c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy; }
+    __device__ __forceinline__ F S(int c) const { return sptr(c)[n]; }
+    __device__ __forceinline__ void setS(int c, F v) const { sptr(c)[n] = v; }
+    __device__ __forceinline__ float aux(int q) const { return A[q * p.naux]; }
+    __device__ __forceinline__ void setAux(int q, float v) const { A[q * p.naux] = v; }
+    // velocity side
+    template <int c, int dk, int di, int dj> __device__ __forceinline__ F Sn() const {
+        const F *b = c == 0 ? p.Sxx : c == 1 ? p.Syy : c == 2 ? p.Szz : c == 3 ? p.Syz : c == 4 ? p.Sxz : p.Sxy;
+        return ldro(b + n + dk + di * p.SI + dj * p.SJ);
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float rho() const { return ldro(p.rho + n + dk + di * p.SI + dj * p.SJ); }
+    __device__ __forceinline__ F Vc(int f) const { return (f == 0 ? p.Vx : f == 1 ? p.Vy : p.Vz)[n]; }
+    __device__ __forceinline__ void setV(int f, F v) const { (f == 0 ? p.Vx : f == 1 ? p.Vy : p.Vz)[n] = v; }
+};
+
+template <typename F, typename A>
+__device__ __forceinline__ void stress_pml_t(const KParams<F> &p, const A &a, const float4 gxc, const float4 gxe, const float4 gyc,
+                                             const float4 gye, const float4 gzc, const float4 gze) {
     const float dt = p.dt;
     const F r20x = p.r20x, r20y = p.r20y, r20z = p.r20z;
-    const float4 gxc = ldro(p.gxc + li), gxe = ldro(p.gxe + li), gyc = ldro(p.gyc + lj), gye = ldro(p.gye + lj);
-    const float4 gzc = ldro(p.gzc + (k - 1)), gze = ldro(p.gze + (k - 1));
-    float *__restrict__ A = p.aux + a;
 
-    const F vx0 = ldro(Vx + n), vy0 = ldro(Vy + n), vz0 = ldro(Vz + n);
-    const F dxVx = (vx0 - ldro(Vx + n - si)) * r20x;
-    const F dyVy = (vy0 - ldro(Vy + n - sj)) * r20y;
-    const F dzVz = (vz0 - ldro(Vz + n - 1)) * r20z;
-    const float mu0 = ldro(p.mu + n), mu_k = ldro(p.mu + n + 1), mu_i = ldro(p.mu + n + si), mu_j = ldro(p.mu + n + sj);
-    const float lam2mu_R = (ldro(p.lam + n) + 2 * mu0);
+    const F vx0 = a.template V<0, 0, 0, 0>(), vy0 = a.template V<1, 0, 0, 0>(), vz0 = a.template V<2, 0, 0, 0>();
+    const F dxVx = (vx0 - a.template V<0, 0, -1, 0>()) * r20x;
+    const F dyVy = (vy0 - a.template V<1, 0, 0, -1>()) * r20y;
+    const F dzVz = (vz0 - a.template V<2, -1, 0, 0>()) * r20z;
+    const float mu0 = a.template mu<0, 0, 0>(), mu_k = a.template mu<1, 0, 0>(), mu_i = a.template mu<0, 1, 0>(), mu_j = a.template mu<0, 0, 1>();
+    const float lam2mu_R = (a.lam() + 2 * mu0);
     const float lam_R = lam2mu_R - 2 * mu0;
 
-    const float a_xVx = A[axVx * na], a_yVy = A[ayVy * na], a_zVz = A[azVz * na];
+    const float a_xVx = a.aux(axVx), a_yVy = a.aux(ayVy), a_zVz = a.aux(azVz);
     const float dxVx_ade = gxc.x * (float)(dxVx) + gxc.y * a_xVx;
     const float dyVy_ade = gyc.x * (float)(dyVy) + gyc.y * a_yVy;
     const float dzVz_ade = gzc.x * (float)(dzVz) + gzc.y * a_zVz;
 
-    p.Sxx[n] = p.Sxx[n] + (lam2mu_R * dxVx_ade + lam_R * (dyVy_ade + dzVz_ade)) * dt;
-    p.Syy[n] = p.Syy[n] + (lam2mu_R * dyVy_ade + lam_R * (dxVx_ade + dzVz_ade)) * dt;
-    p.Szz[n] = p.Szz[n] + (lam2mu_R * dzVz_ade + lam_R * (dxVx_ade + dyVy_ade)) * dt;
+    a.setS(0, a.S(0) + (lam2mu_R * dxVx_ade + lam_R * (dyVy_ade + dzVz_ade)) * dt);
+    a.setS(1, a.S(1) + (lam2mu_R * dyVy_ade + lam_R * (dxVx_ade + dzVz_ade)) * dt);
+    a.setS(2, a.S(2) + (lam2mu_R * dzVz_ade + lam_R * (dxVx_ade + dyVy_ade)) * dt);
 
-    A[axVx * na] = gxc.z * a_xVx + gxc.w * (float)(dxVx) * dt;
-    A[ayVy * na] = gyc.z * a_yVy + gyc.w * (float)(dyVy) * dt;
-    A[azVz * na] = gzc.z * a_zVz + gzc.w * (float)(dzVz) * dt;
+    a.setAux(axVx, gxc.z * a_xVx + gxc.w * (float)(dxVx) * dt);
+    a.setAux(ayVy, gyc.z * a_yVy + gyc.w * (float)(dyVy) * dt);
+    a.setAux(azVz, gzc.z * a_zVz + gzc.w * (float)(dzVz) * dt);
 
-    const F dxVy = (ldro(Vy + n + si) - vy0) * r20x;
-    const F dxVz = (ldro(Vz + n + si) - vz0) * r20x;
-    const F dyVx = (ldro(Vx + n + sj) - vx0) * r20y;
-    const F dyVz = (ldro(Vz + n + sj) - vz0) * r20y;
-    const F dzVx = (ldro(Vx + n + 1) - vx0) * r20z;
-    const F dzVy = (ldro(Vy + n + 1) - vy0) * r20z;
+    const F dxVy = (a.template V<1, 0, 1, 0>() - vy0) * r20x;
+    const F dxVz = (a.template V<2, 0, 1, 0>() - vz0) * r20x;
+    const F dyVx = (a.template V<0, 0, 0, 1>() - vx0) * r20y;
+    const F dyVz = (a.template V<2, 0, 0, 1>() - vz0) * r20y;
+    const F dzVx = (a.template V<0, 1, 0, 0>() - vx0) * r20z;
+    const F dzVy = (a.template V<1, 1, 0, 0>() - vy0) * r20z;
 
-    const float muxz = mu_harm(mu0, mu_k, mu_i, ldro(p.mu + n + 1 + si));
-    const float muxy = mu_harm(mu0, mu_i, mu_j, ldro(p.mu + n + si + sj));
-    const float muyz = mu_harm(mu0, mu_k, mu_j, ldro(p.mu + n + 1 + sj));
+    const float muxz = mu_harm(mu0, mu_k, mu_i, a.template mu<1, 1, 0>());
+    const float muxy = mu_harm(mu0, mu_i, mu_j, a.template mu<0, 1, 1>());
+    const float muyz = mu_harm(mu0, mu_k, mu_j, a.template mu<1, 0, 1>());
 
-    const float a_yVx = A[ayVx * na], a_zVx = A[azVx * na], a_xVy = A[axVy * na];
-    const float a_zVy = A[azVy * na], a_xVz = A[axVz * na], a_yVz = A[ayVz * na];
+    const float a_yVx = a.aux(ayVx), a_zVx = a.aux(azVx), a_xVy = a.aux(axVy);
+    const float a_zVy = a.aux(azVy), a_xVz = a.aux(axVz), a_yVz = a.aux(ayVz);
 
-    p.Syz[n] = p.Syz[n] + muyz * (gye.x * dyVz + gze.x * dzVy + gye.y * a_yVz + gze.y * a_zVy) * dt;
-    p.Sxz[n] = p.Sxz[n] + muxz * (gxe.x * dxVz + gze.x * dzVx + gxe.y * a_xVz + gze.y * a_zVx) * dt;
-    p.Sxy[n] = p.Sxy[n] + muxy * (gxe.x * dxVy + gye.x * dyVx + gxe.y * a_xVy + gye.y * a_yVx) * dt;
+    a.setS(3, a.S(3) + muyz * (gye.x * dyVz + gze.x * dzVy + gye.y * a_yVz + gze.y * a_zVy) * dt);
+    a.setS(4, a.S(4) + muxz * (gxe.x * dxVz + gze.x * dzVx + gxe.y * a_xVz + gze.y * a_zVx) * dt);
+    a.setS(5, a.S(5) + muxy * (gxe.x * dxVy + gye.x * dyVx + gxe.y * a_xVy + gye.y * a_yVx) * dt);
 
-    A[ayVx * na] = gye.z * a_yVx + gye.w * (float)(dyVx) * dt;
-    A[azVx * na] = gze.z * a_zVx + gze.w * (float)(dzVx) * dt;
-    A[axVy * na] = gxe.z * a_xVy + gxe.w * (float)(dxVy) * dt;
-    A[azVy * na] = gze.z * a_zVy + gze.w * (float)(dzVy) * dt;
-    A[axVz * na] = gxe.z * a_xVz + gxe.w * (float)(dxVz) * dt;
-    A[ayVz * na] = gye.z * a_yVz + gye.w * (float)(dyVz) * dt;
+    a.setAux(ayVx, gye.z * a_yVx + gye.w * (float)(dyVx) * dt);
+    a.setAux(azVx, gze.z * a_zVx + gze.w * (float)(dzVx) * dt);
+    a.setAux(axVy, gxe.z * a_xVy + gxe.w * (float)(dxVy) * dt);
+    a.setAux(azVy, gze.z * a_zVy + gze.w * (float)(dzVy) * dt);
+    a.setAux(axVz, gxe.z * a_xVz + gxe.w * (float)(dxVz) * dt);
+    a.setAux(ayVz, gye.z * a_yVz + gye.w * (float)(dyVz) * dt);
+}
+
+template <typename F>
+__device__ __forceinline__ void stress_pml(const KParams<F> &p, long long n, int k, int li, int lj, long long a) {
+    const float4 gxc = ldro(p.gxc + li), gxe = ldro(p.gxe + li), gyc = ldro(p.gyc + lj), gye = ldro(p.gye + lj);
+    const float4 gzc = ldro(p.gzc + (k - 1)), gze = ldro(p.gze + (k - 1));
+    stress_pml_t<F>(p, AccPmlDirect<F>(p, n, a), gxc, gxe, gyc, gye, gzc, gze);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -360,51 +393,54 @@ __device__ __forceinline__ void vel_interior(const KParams<F> &p, long long n, i
     vel_interior_t<F>(p, AccVelDirect<F>(p, n), k, mi, mj, bnd);
 }
 
-// velocity update of one PML cell: absorb_p__update_vel m_absorb_p.f90:261-308
-template <typename F>
-__device__ __forceinline__ void vel_pml(const KParams<F> &p, long long n, int k, int li, int lj, long long a) {
-    const long long si = p.SI, sj = p.SJ, na = p.naux;
-    const F *__restrict__ Sxx = p.Sxx, *__restrict__ Syy = p.Syy, *__restrict__ Szz = p.Szz;
-    const F *__restrict__ Syz = p.Syz, *__restrict__ Sxz = p.Sxz, *__restrict__ Sxy = p.Sxy;
+// velocity update of one PML cell: absorb_p__update_vel m_absorb_p.f90:261-308.  Accessor: Sn<c,dk,di,dj> (c = xx yy zz yz xz xy),
+// rho<dk,di,dj>, Vc(f) / setV(f, v), aux(q) / setAux(q, v).
+template <typename F, typename A>
+__device__ __forceinline__ void vel_pml_t(const KParams<F> &p, const A &a, const float4 gxc, const float4 gxe, const float4 gyc,
+                                          const float4 gye, const float4 gzc, const float4 gze) {
     const float dt = p.dt;
     const F r20x = p.r20x, r20y = p.r20y, r20z = p.r20z;
+    const F sxy0 = a.template Sn<5, 0, 0, 0>(), sxz0 = a.template Sn<4, 0, 0, 0>(), syz0 = a.template Sn<3, 0, 0, 0>();
+
+    const F dxSxx = (a.template Sn<0, 0, 1, 0>() - a.template Sn<0, 0, 0, 0>()) * r20x;
+    const F dySyy = (a.template Sn<1, 0, 0, 1>() - a.template Sn<1, 0, 0, 0>()) * r20y;
+    const F dzSzz = (a.template Sn<2, 1, 0, 0>() - a.template Sn<2, 0, 0, 0>()) * r20z;
+    const F dySyz = (syz0 - a.template Sn<3, 0, 0, -1>()) * r20y;
+    const F dzSyz = (syz0 - a.template Sn<3, -1, 0, 0>()) * r20z;
+    const F dxSxz = (sxz0 - a.template Sn<4, 0, -1, 0>()) * r20x;
+    const F dzSxz = (sxz0 - a.template Sn<4, -1, 0, 0>()) * r20z;
+    const F dxSxy = (sxy0 - a.template Sn<5, 0, -1, 0>()) * r20x;
+    const F dySxy = (sxy0 - a.template Sn<5, 0, 0, -1>()) * r20y;
+
+    const float rho0 = a.template rho<0, 0, 0>();
+    const float bx = 2.0f / (rho0 + a.template rho<0, 1, 0>());
+    const float by = 2.0f / (rho0 + a.template rho<0, 0, 1>());
+    const float bz = 2.0f / (rho0 + a.template rho<1, 0, 0>());
+
+    const float a_xSxx = a.aux(axSxx), a_ySxy = a.aux(aySxy), a_zSxz = a.aux(azSxz);
+    const float a_xSxy = a.aux(axSxy), a_ySyy = a.aux(aySyy), a_zSyz = a.aux(azSyz);
+    const float a_xSxz = a.aux(axSxz), a_ySyz = a.aux(aySyz), a_zSzz = a.aux(azSzz);
+
+    a.setV(0, a.Vc(0) + bx * (float)(gxe.x * dxSxx + gyc.x * dySxy + gzc.x * dzSxz + gxe.y * a_xSxx + gyc.y * a_ySxy + gzc.y * a_zSxz) * dt);
+    a.setV(1, a.Vc(1) + by * (float)(gxc.x * dxSxy + gye.x * dySyy + gzc.x * dzSyz + gxc.y * a_xSxy + gye.y * a_ySyy + gzc.y * a_zSyz) * dt);
+    a.setV(2, a.Vc(2) + bz * (float)(gxc.x * dxSxz + gyc.x * dySyz + gze.x * dzSzz + gxc.y * a_xSxz + gyc.y * a_ySyz + gze.y * a_zSzz) * dt);
+
+    a.setAux(axSxx, gxe.z * a_xSxx + gxe.w * (float)(dxSxx) * dt);
+    a.setAux(aySxy, gyc.z * a_ySxy + gyc.w * (float)(dySxy) * dt);
+    a.setAux(azSxz, gzc.z * a_zSxz + gzc.w * (float)(dzSxz) * dt);
+    a.setAux(axSxy, gxc.z * a_xSxy + gxc.w * (float)(dxSxy) * dt);
+    a.setAux(aySyy, gye.z * a_ySyy + gye.w * (float)(dySyy) * dt);
+    a.setAux(azSyz, gzc.z * a_zSyz + gzc.w * (float)(dzSyz) * dt);
+    a.setAux(axSxz, gxc.z * a_xSxz + gxc.w * (float)(dxSxz) * dt);
+    a.setAux(aySyz, gyc.z * a_ySyz + gyc.w * (float)(dySyz) * dt);
+    a.setAux(azSzz, gze.z * a_zSzz + gze.w * (float)(dzSzz) * dt);
+}
+
+template <typename F>
+__device__ __forceinline__ void vel_pml(const KParams<F> &p, long long n, int k, int li, int lj, long long a) {
     const float4 gxc = ldro(p.gxc + li), gxe = ldro(p.gxe + li), gyc = ldro(p.gyc + lj), gye = ldro(p.gye + lj);
     const float4 gzc = ldro(p.gzc + (k - 1)), gze = ldro(p.gze + (k - 1));
-    float *__restrict__ A = p.aux + a;
-    const F sxy0 = ldro(Sxy + n), sxz0 = ldro(Sxz + n), syz0 = ldro(Syz + n);
-
-    const F dxSxx = (ldro(Sxx + n + si) - ldro(Sxx + n)) * r20x;
-    const F dySyy = (ldro(Syy + n + sj) - ldro(Syy + n)) * r20y;
-    const F dzSzz = (ldro(Szz + n + 1) - ldro(Szz + n)) * r20z;
-    const F dySyz = (syz0 - ldro(Syz + n - sj)) * r20y;
-    const F dzSyz = (syz0 - ldro(Syz + n - 1)) * r20z;
-    const F dxSxz = (sxz0 - ldro(Sxz + n - si)) * r20x;
-    const F dzSxz = (sxz0 - ldro(Sxz + n - 1)) * r20z;
-    const F dxSxy = (sxy0 - ldro(Sxy + n - si)) * r20x;
-    const F dySxy = (sxy0 - ldro(Sxy + n - sj)) * r20y;
-
-    const float rho0 = ldro(p.rho + n);
-    const float bx = 2.0f / (rho0 + ldro(p.rho + n + si));
-    const float by = 2.0f / (rho0 + ldro(p.rho + n + sj));
-    const float bz = 2.0f / (rho0 + ldro(p.rho + n + 1));
-
-    const float a_xSxx = A[axSxx * na], a_ySxy = A[aySxy * na], a_zSxz = A[azSxz * na];
-    const float a_xSxy = A[axSxy * na], a_ySyy = A[aySyy * na], a_zSyz = A[azSyz * na];
-    const float a_xSxz = A[axSxz * na], a_ySyz = A[aySyz * na], a_zSzz = A[azSzz * na];
-
-    p.Vx[n] = p.Vx[n] + bx * (float)(gxe.x * dxSxx + gyc.x * dySxy + gzc.x * dzSxz + gxe.y * a_xSxx + gyc.y * a_ySxy + gzc.y * a_zSxz) * dt;
-    p.Vy[n] = p.Vy[n] + by * (float)(gxc.x * dxSxy + gye.x * dySyy + gzc.x * dzSyz + gxc.y * a_xSxy + gye.y * a_ySyy + gzc.y * a_zSyz) * dt;
-    p.Vz[n] = p.Vz[n] + bz * (float)(gxc.x * dxSxz + gyc.x * dySyz + gze.x * dzSzz + gxc.y * a_xSxz + gyc.y * a_ySyz + gze.y * a_zSzz) * dt;
-
-    A[axSxx * na] = gxe.z * a_xSxx + gxe.w * (float)(dxSxx) * dt;
-    A[aySxy * na] = gyc.z * a_ySxy + gyc.w * (float)(dySxy) * dt;
-    A[azSxz * na] = gzc.z * a_zSxz + gzc.w * (float)(dzSxz) * dt;
-    A[axSxy * na] = gxc.z * a_xSxy + gxc.w * (float)(dxSxy) * dt;
-    A[aySyy * na] = gye.z * a_ySyy + gye.w * (float)(dySyy) * dt;
-    A[azSyz * na] = gzc.z * a_zSyz + gzc.w * (float)(dzSyz) * dt;
-    A[axSxz * na] = gxc.z * a_xSxz + gxc.w * (float)(dxSxz) * dt;
-    A[aySyz * na] = gyc.z * a_ySyz + gyc.w * (float)(dySyz) * dt;
-    A[azSzz * na] = gze.z * a_zSzz + gze.w * (float)(dzSzz) * dt;
+    vel_pml_t<F>(p, AccPmlDirect<F>(p, n, a), gxc, gxe, gyc, gye, gzc, gze);
 }
 
 // ------------------------------------------------------------------------------------------------
