@@ -4,6 +4,7 @@
 #include "../../include/swpc3d_b200.h"
 #include "kernels.cuh"
 #include "stress_tma.cuh"
+#include "pml_tma.cuh"
 #include "snap.cuh"
 
 #include <cuda_runtime.h>
@@ -110,6 +111,15 @@ struct swpc3d_handle {
     int4 *band = nullptr;
     int *kbeg_a = nullptr, *kob = nullptr, *kfs = nullptr;
     std::vector<int> h_kbeg_a;
+    std::vector<long long> h_aoff;         // host copy of aoff (per owned column)
+    struct PmlPlan *pml[2][2] = {};        // [whole | core region][stress | velocity]: TMA-staged absorber shell (pml_tma.cuh)
+    struct TmaPlan *tplan[2] = {};         // [whole | core region]: work lists of the persistent interior stress kernel (stress_tma_p)
+    int tma_persist = 0;                   // option "tma_persist": 1 = stress_tma_p (persistent blocks, ticket counter) instead of one block per 16-plane chunk; measured slower
+    int tma_pl = 64;                       // option "tma_pl": planes per work item of the persistent kernel
+    int use_pml = 1;                       // option "pml_tma": 0 = the whole shell with sweep_direct
+    int pml_jl = 32, pml_jl_bottom = 41;   // planes per work item (targets; evened out over the region)
+    int l2promo = 2, l2promo_halo = 2;     // options "l2promo" / "l2promo_halo": L2 promotion of stress_tma's centre / halo boxes (0 none, 1 64 B, 2 128 B, 3 256 B)
+    int pml_promo = 1, pml_promo_b = 1;    // options "pml_promo" / "pml_promo_bottom": the same for pml_tma's wall / bottom items
     long long *aoff = nullptr;
     float *aux = nullptr;
     long long naux = 0;
@@ -230,6 +240,9 @@ static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
     do {                                     \
         if (stream_wait((h_), (st_))) return 1; \
     } while (0)
+
+static void pml_drop(swpc3d_handle *h);
+static void tplan_drop(swpc3d_handle *h);
 
 static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
 
@@ -416,6 +429,8 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaFree(h->Fall);
     cudaFree(h->R);
     cudaFree(h->Mall);
+    pml_drop(h);
+    tplan_drop(h);
     cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->kfs); cudaFree(h->snap_tmp);
     for (int q = 0; q < 15; q++) { cudaFree(h->snap_buf[q]); cudaFree(h->snap_max[q]); } cudaFree(h->aoff); cudaFree(h->aux);
     for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
@@ -565,6 +580,8 @@ extern "C" int swpc3d_setup_pml(swpc3d_handle *h, const float *gxc, const float 
             off += ((phase + len_k) + 31) / 32 * 32;
         }
     h->naux = off;
+    h->h_aoff = aoff;
+    pml_drop(h);
     if (h->aoff) cudaFree(h->aoff);
     if (h->aux) cudaFree(h->aux);
     h->aoff = nullptr; h->aux = nullptr;
@@ -711,7 +728,10 @@ static EncodeTiledFn get_encode() {
     }
     return fn;
 }
-static bool make_map(swpc3d_handle *h, CUtensorMap *m, void *base, int elem, int narr, int bk, int bi, int barr) {
+static CUtensorMapL2promotion l2promo_of(int v) {
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
+static bool make_map(swpc3d_handle *h, CUtensorMap *m, void *base, int elem, int narr, int bk, int bi, int barr, int promo = 2) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)h->NZP, (cuuint64_t)h->NXM, (cuuint64_t)h->NYM, (cuuint64_t)narr};
@@ -720,7 +740,7 @@ static bool make_map(swpc3d_handle *h, CUtensorMap *m, void *base, int elem, int
     const cuuint32_t es[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     return enc(m, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               l2promo_of(promo), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <typename F, int NM>
@@ -729,11 +749,13 @@ static int tma_prepare(swpc3d_handle *h) {
     h->tma_ready = true;
     h->tma_ok = false;
     if (C::SMEM > 227 * 1024) return 0;
-    bool ok = make_map(h, &h->tmaps.S, h->Fall, sizeof(F), 9, C::TK, C::TI, 6) && make_map(h, &h->tmaps.V, h->Fall, sizeof(F), 9, C::VK, C::VI, 3) &&
-              make_map(h, &h->tmaps.M, h->Mall, 4, 5, C::TK, C::TI, C::NMED) && make_map(h, &h->tmaps.Mu, h->Mall, 4, 5, C::MUK, C::MUI, 1);
-    if (NM > 0) ok = ok && make_map(h, &h->tmaps.R, h->R, 4, 6 * NM, C::TK, C::TI, 6 * NM);
+    const int pc = h->l2promo, ph = h->l2promo_halo;
+    bool ok = make_map(h, &h->tmaps.S, h->Fall, sizeof(F), 9, C::TK, C::TI, 6, pc) && make_map(h, &h->tmaps.V, h->Fall, sizeof(F), 9, C::VK, C::VI, 3, ph) &&
+              make_map(h, &h->tmaps.M, h->Mall, 4, 5, C::TK, C::TI, C::NMED, pc) && make_map(h, &h->tmaps.Mu, h->Mall, 4, 5, C::MUK, C::MUI, 1, ph);
+    if (NM > 0) ok = ok && make_map(h, &h->tmaps.R, h->R, 4, 6 * NM, C::TK, C::TI, 6 * NM, pc);
     if (!ok) return 0;
-    if (cudaFuncSetAttribute(stress_tma<F, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(stress_tma<F, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(stress_tma_p<F, NM>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -790,6 +812,300 @@ static Box3 tma_box(const swpc3d_handle *h, const Region &rg) {
     return b;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The absorber shell of a region, split into work items of pml_tma (tiles whose active cells are all PML cells and whose
+// ADE columns are regularly spaced in the aux arrays) and the boxes that stay with sweep_direct (ragged interior columns,
+// regions thinner than the pipeline is deep, rows that do not fit the bottom box).
+// The kernel classes (columns x rows of a tile): 0 = wall slabs, 1 = the bottom rows (one box of 20 rows), 2 = wall slabs whose
+// width is a multiple of 10 but not of 8 (the reference's default absorber is 20 columns thick)
+constexpr int PML_NCLS = 3;
+template <int CLS> struct PmlClass;
+template <> struct PmlClass<0> { static constexpr int TI = 8, BK = 32; };
+template <> struct PmlClass<1> { static constexpr int TI = 16, BK = 20; };
+template <> struct PmlClass<2> { static constexpr int TI = 10, BK = 32; };
+static const int PML_TI[PML_NCLS] = {8, 16, 10}, PML_BK[PML_NCLS] = {32, 20, 32};
+
+struct PmlPlan {
+    Region rg{};
+    Box3 cols{};                         // the interior columns whose bottom rows this plan covers (stress: the TMA box; velocity: the kernel box)
+    int n_items[PML_NCLS] = {};
+    PmlItem *d_items[PML_NCLS] = {};
+    unsigned int *d_ticket = nullptr;    // one counter per kernel class
+    unsigned int base[PML_NCLS] = {};
+    PmlMaps maps[PML_NCLS]{};
+    std::vector<Box3> direct;
+    int jl = 0, jlb = 0;
+};
+static void pml_drop(swpc3d_handle *h) {
+    bool any = false;
+    for (auto &per_region : h->pml)
+        for (PmlPlan *&pl : per_region) any = any || pl;
+    if (!any) return;
+    cudaSetDevice(h->dev);
+    cudaDeviceSynchronize();
+    for (auto &per_region : h->pml)
+        for (PmlPlan *&pl : per_region) {
+            if (!pl) continue;
+            for (int c = 0; c < PML_NCLS; c++) cudaFree(pl->d_items[c]);
+            cudaFree(pl->d_ticket);
+            delete pl;
+            pl = nullptr;
+        }
+}
+
+static bool make_map_generic(CUtensorMap *m, void *base, int elem, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3], const cuuint32_t box[4],
+                             int promo) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(m, dt, 4, base, dims, strides_bytes, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               l2promo_of(promo), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// split `planes` into chunks of about `target` planes, none shorter than `minlen`; returns the chunk count (0: too thin)
+static int even_chunks(int planes, int target, int minlen) {
+    if (planes < minlen) return 0;
+    int n = std::max(1, (planes + target / 2) / std::max(1, target));
+    while (n > 1 && planes / n < minlen) n--;
+    return n;
+}
+
+template <typename F, bool STRESS, int CLS>
+static cudaError_t pml_set_smem() {
+    using C = PmlCfg<F, STRESS, PmlClass<CLS>::TI, PmlClass<CLS>::BK>;
+    return cudaFuncSetAttribute(pml_tma<F, STRESS, PmlClass<CLS>::TI, PmlClass<CLS>::BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+}
+template <typename F, bool STRESS, int CLS>
+static int pml_ns() { return PmlCfg<F, STRESS, PmlClass<CLS>::TI, PmlClass<CLS>::BK>::NS; }
+
+template <typename F, bool STRESS>
+static int pml_build(swpc3d_handle *h, const Region &rg, const Box3 &cols, PmlPlan *pl) {
+    const swpc3d_grid &g = h->g;
+    const int nz = g.nz, nxp = h->nxp;
+    pl->rg = rg; pl->cols = cols; pl->jl = h->pml_jl; pl->jlb = h->pml_jl_bottom;
+    pl->direct.clear();
+    for (int c = 0; c < PML_NCLS; c++) pl->n_items[c] = 0;
+    const int ki0 = std::max(g.ibeg_k - g.ibeg, rg.li0), ki1 = std::min(g.iend_k - g.ibeg, rg.li1);
+    const int kj0 = std::max(g.jbeg_k - g.jbeg, rg.lj0), kj1 = std::min(g.jend_k - g.jbeg, rg.lj1);
+    std::vector<PmlItem> items[PML_NCLS];
+    auto aoff = [&](int li, int lj) { return h->h_aoff[(size_t)li + (size_t)nxp * lj]; };
+    auto kba = [&](int li, int lj) { return h->h_kbeg_a[(size_t)(li + HALO) + (size_t)h->NXM * (lj + HALO)]; };
+    const bool usable = h->use_pml && g.abc_type == SWPC3D_ABC_PML && get_encode() && !h->h_aoff.empty() && ki1 >= ki0 && kj1 >= kj0;
+    const int nstage[PML_NCLS] = {pml_ns<F, STRESS, 0>(), pml_ns<F, STRESS, 1>(), pml_ns<F, STRESS, 2>()};
+    int nmap[PML_NCLS] = {};
+    // one region: columns [a0,a1] x planes [b0,b1], rows kb..nz (kb = 1: wall columns)
+    auto add_region = [&](int a0, int a1, int b0, int b1, int kb, bool bottom, bool flat) {
+        if (a1 < a0 || b1 < b0 || kb > nz) return;   // empty: nothing to do
+        const Box3 whole{kb, nz, a0, a1, b0, b1, 0, flat ? 1 : 0};
+        const int ncols = a1 - a0 + 1, nrows_j = b1 - b0 + 1;
+        int cls = bottom ? 1 : 0;
+        if (!bottom && (ncols + 9) / 10 * 10 < (ncols + 7) / 8 * 8) cls = 2;   // fewer idle columns with 10-wide tiles
+        const int TI = PML_TI[cls], BK = PML_BK[cls], NS = nstage[cls];
+        bool ok = usable && nmap[cls] < PML_NMAP;
+        const int nch = ok ? even_chunks(nrows_j, bottom ? h->pml_jl_bottom : h->pml_jl, std::max(NS, 2)) : 0;
+        if (nch < 1) ok = false;
+        const int shift = (kb - 1) % 4;                  // the boxes start at kb - shift (16-byte aligned for float arrays)
+        if (ok && bottom && shift + (nz - kb + 1) > BK) ok = false;
+        long long asi = 0, asj = 0;
+        const int phase = (kb - 1) & 31;
+        const long long klen = ((long long)phase + (nz - kb + 1) + 31) / 32 * 32;
+        if (ok) {   // every column starts at kb and the columns are regularly spaced in the aux arrays
+            asi = ncols > 1 ? aoff(a0 + 1, b0) - aoff(a0, b0) : klen;
+            asj = nrows_j > 1 ? aoff(a0, b0 + 1) - aoff(a0, b0) : asi * ncols;
+            for (int lj = b0; lj <= b1 && ok; lj++)
+                for (int li = a0; li <= a1; li++)
+                    if (kba(li, lj) != kb || aoff(li, lj) != aoff(a0, b0) + (long long)(li - a0) * asi + (long long)(lj - b0) * asj) { ok = false; break; }
+            if (asi < klen || asj < asi * ncols || asi % 4 || asj % 4) ok = false;
+        }
+        if (!ok) { pl->direct.push_back(whole); return; }
+        const int im = nmap[cls]++;
+        {   // aux tensor of the region: (k within the column allocation, column, plane, array)
+            const cuuint64_t dims[4] = {(cuuint64_t)klen, (cuuint64_t)ncols, (cuuint64_t)nrows_j, 18};
+            const cuuint64_t st[3] = {(cuuint64_t)asi * 4, (cuuint64_t)asj * 4, (cuuint64_t)h->naux * 4};
+            const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TI, 1, 9};
+            if (!make_map_generic(&pl->maps[cls].aux[im], h->aux + (aoff(a0, b0) - phase), 4, dims, st, box, bottom ? h->pml_promo_b : h->pml_promo)) {
+                nmap[cls]--;
+                pl->direct.push_back(whole);
+                return;
+            }
+        }
+        // items: k-tile fastest, then column tile, then plane chunk -- blocks that run side by side work on neighbouring tiles
+        const int nkt = bottom ? 1 : (nz + BK - 1) / BK;
+        for (int c = 0; c < nch; c++) {
+            const int j0 = b0 + (int)((long long)nrows_j * c / nch), j1 = b0 + (int)((long long)nrows_j * (c + 1) / nch) - 1;
+            for (int it = 0; it * TI < ncols; it++)
+                for (int kt = 0; kt < nkt; kt++) {
+                    PmlItem I{};
+                    if (bottom) { I.k0 = kb - shift; I.r0 = shift; I.r1 = shift + (nz - kb); I.ak = phase - shift; }
+                    else { I.k0 = 1 + kt * BK; I.r0 = 0; I.r1 = std::min(BK - 1, nz - I.k0); I.ak = I.k0 - 1; }
+                    I.li0 = a0 + it * TI; I.ncol = std::min(TI, a1 - I.li0 + 1);
+                    I.lj0 = j0; I.nsteps = j1 - j0 + 1;
+                    I.amap = im; I.ai = I.li0 - a0; I.aj = j0 - b0;
+                    I.asi = (int)asi; I.asj = asj;
+                    I.aux0 = aoff(a0, b0) + (I.k0 - kb) + (long long)I.ai * asi + (long long)I.aj * asj;
+                    items[cls].push_back(I);
+                }
+        }
+    };
+    if (ki1 < ki0 || kj1 < kj0) {   // a subdomain entirely inside the absorber
+        pl->direct.push_back(Box3{1, nz, rg.li0, rg.li1, rg.lj0, rg.lj1, 0, 0});
+    } else {
+        add_region(rg.li0, rg.li1, rg.lj0, kj0 - 1, 1, false, false);
+        add_region(rg.li0, rg.li1, kj1 + 1, rg.lj1, 1, false, false);
+        add_region(rg.li0, ki0 - 1, kj0, kj1, 1, false, h->flat_bottom != 0);
+        add_region(ki1 + 1, rg.li1, kj0, kj1, 1, false, h->flat_bottom != 0);
+        // interior columns that are not under `cols` (ragged tiles of the stress sweep): all their rows with sweep_direct
+        if (cols.li0 > ki0) pl->direct.push_back(Box3{1, nz, ki0, cols.li0 - 1, kj0, kj1, 0, h->flat_bottom});
+        if (cols.li1 < ki1) pl->direct.push_back(Box3{1, nz, cols.li1 + 1, ki1, kj0, kj1, 0, h->flat_bottom});
+        if (cols.lj0 > kj0) pl->direct.push_back(Box3{1, nz, cols.li0, cols.li1, kj0, cols.lj0 - 1, 0, 0});
+        if (cols.lj1 < kj1) pl->direct.push_back(Box3{1, nz, cols.li0, cols.li1, cols.lj1 + 1, kj1, 0, 0});
+        add_region(cols.li0, cols.li1, cols.lj0, cols.lj1, g.kend_k + 1, true, h->flat_bottom != 0);
+    }
+    CK(cudaMalloc(&pl->d_ticket, PML_NCLS * sizeof(unsigned int)));
+    CK(cudaMemset(pl->d_ticket, 0, PML_NCLS * sizeof(unsigned int)));
+    // field / medium maps of the kernel classes in use
+    for (int cls = 0; cls < PML_NCLS; cls++) {
+        if (items[cls].empty()) continue;
+        const int TI = PML_TI[cls], BK = PML_BK[cls], pr = cls == 1 ? h->pml_promo_b : h->pml_promo;
+        PmlMaps &M = pl->maps[cls];
+        const bool ok = make_map(h, &M.C, h->Fall, sizeof(F), 9, BK, TI, STRESS ? 6 : 3, pr) && make_map(h, &M.H, h->Fall, sizeof(F), 9, BK + 8, TI + 2, 3, pr) &&
+                        make_map(h, &M.M1, h->Mall, 4, 5, BK, TI, 1, pr) && make_map(h, &M.Mh, h->Mall, 4, 5, BK + 4, TI + 1, 1, pr);
+        const cudaError_t e = !ok ? cudaErrorUnknown : cls == 0 ? pml_set_smem<F, STRESS, 0>() : cls == 1 ? pml_set_smem<F, STRESS, 1>() : pml_set_smem<F, STRESS, 2>();
+        if (!ok || e != cudaSuccess) {
+            cudaGetLastError();
+            return fail("pml_tma: cannot encode the tensor maps / set the shared-memory size");
+        }
+        CK(cudaMalloc(&pl->d_items[cls], items[cls].size() * sizeof(PmlItem)));
+        CK(cudaMemcpy(pl->d_items[cls], items[cls].data(), items[cls].size() * sizeof(PmlItem), cudaMemcpyHostToDevice));
+        pl->n_items[cls] = (int)items[cls].size();
+    }
+    return 0;
+}
+
+template <typename F, bool STRESS, int CLS>
+static void pml_launch_class(const KParams<F> &p, PmlPlan *pl, const PmlGeom &gm, int grid, cudaStream_t st) {
+    using C = PmlCfg<F, STRESS, PmlClass<CLS>::TI, PmlClass<CLS>::BK>;
+    pml_tma<F, STRESS, PmlClass<CLS>::TI, PmlClass<CLS>::BK><<<grid, C::THREADS, C::SMEM, st>>>(p, pl->maps[CLS], pl->d_items[CLS], pl->d_ticket + CLS,
+                                                                                                    pl->base[CLS], gm);
+    pl->base[CLS] += (unsigned int)(gm.nitems + grid);   // every block takes one ticket past the end
+}
+
+// the absorber shell of region rg: pml_tma work lists + the boxes left to sweep_direct, all beside the interior kernel
+template <typename F, bool STRESS>
+static int launch_shell(swpc3d_handle *h, const KParams<F> &p, const Region &rg, const Box3 &cols) {
+    const Region w = whole_region(h);
+    const int ri = (rg.li0 == w.li0 && rg.li1 == w.li1 && rg.lj0 == w.lj0 && rg.lj1 == w.lj1) ? 0 : 1;
+    PmlPlan *&pl = h->pml[ri][STRESS ? 0 : 1];
+    auto same = [](const Box3 &a, const Box3 &b) { return a.li0 == b.li0 && a.li1 == b.li1 && a.lj0 == b.lj0 && a.lj1 == b.lj1; };
+    if (pl && !(pl->rg.li0 == rg.li0 && pl->rg.li1 == rg.li1 && pl->rg.lj0 == rg.lj0 && pl->rg.lj1 == rg.lj1 && same(pl->cols, cols) &&
+                pl->jl == h->pml_jl && pl->jlb == h->pml_jl_bottom)) {
+        CK(cudaDeviceSynchronize());
+        for (int c = 0; c < PML_NCLS; c++) cudaFree(pl->d_items[c]);
+        cudaFree(pl->d_ticket);
+        delete pl;
+        pl = nullptr;
+    }
+    if (!pl) {
+        pl = new PmlPlan();
+        if (pml_build<F, STRESS>(h, rg, cols, pl)) return 1;
+    }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev);
+    int qs = 0;   // side stream round robin
+    auto fork = [&](cudaStream_t &st) -> int {
+        st = h->st;
+        if (h->use_side) {
+            st = h->side[qs % 5];
+            if (qs < 5) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+        }
+        return 0;
+    };
+    auto join = [&](cudaStream_t st) -> int {
+        if (h->use_side) {
+            CK(cudaEventRecord(h->ev_join[qs % 5], st));
+            CK(cudaStreamWaitEvent(h->st, h->ev_join[qs % 5], 0));
+            qs++;
+        }
+        return 0;
+    };
+    PmlGeom gm{};
+    if (STRESS) { gm.c_first = 3; gm.h_first = 0; gm.sa_first = 0; gm.m1_index = 2; gm.mh_index = 1; gm.a_first = 0; }
+    else { gm.c_first = 0; gm.h_first = 6; gm.sa_first = 3; gm.m1_index = 2; gm.mh_index = 0; gm.a_first = 9; }
+    for (int cls = 0; cls < PML_NCLS; cls++) {
+        if (!pl->n_items[cls]) continue;
+        cudaStream_t st;
+        if (fork(st)) return 1;
+        gm.nitems = pl->n_items[cls];
+        const int grid = std::min(gm.nitems, nsm);
+        if (cls == 0) pml_launch_class<F, STRESS, 0>(p, pl, gm, grid, st);
+        else if (cls == 1) pml_launch_class<F, STRESS, 1>(p, pl, gm, grid, st);
+        else pml_launch_class<F, STRESS, 2>(p, pl, gm, grid, st);
+        h->launches++;
+        CK(cudaGetLastError());
+        if (join(st)) return 1;
+    }
+    for (const Box3 &b : pl->direct) {
+        if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
+        cudaStream_t st;
+        if (fork(st)) return 1;
+        if (launch_direct_box<F, STRESS>(h, p, b, st)) return 1;
+        if (join(st)) return 1;
+    }
+    return 0;
+}
+
+// Work items of stress_tma_p for the tile box t, in ticket order: k-tile fastest, then i-tile, then j-chunk of about tma_pl planes
+struct TmaPlan {
+    Box3 t{};
+    int shift = 0, pl = 0, grid = 0, nitems = 0;
+    TmaItem *d_items = nullptr;
+    unsigned int *d_ticket = nullptr;
+    unsigned int base = 0;     // tickets handed out by the launches so far (each launch takes nitems + grid)
+};
+static void tplan_drop(swpc3d_handle *h) {
+    for (TmaPlan *&tp : h->tplan) {
+        if (!tp) continue;
+        cudaSetDevice(h->dev);
+        cudaDeviceSynchronize();
+        cudaFree(tp->d_items);
+        cudaFree(tp->d_ticket);
+        delete tp;
+        tp = nullptr;
+    }
+}
+static int tplan_build(swpc3d_handle *h, const Box3 &t, int TK, int TI, int blocks_per_sm, TmaPlan *tp) {
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev);
+    nsm *= std::max(1, blocks_per_sm);
+    const int nkt = (t.k1 - t.k0 + 1) / TK, nit = (t.li1 - t.li0 + 1) / TI, P = t.lj1 - t.lj0 + 1;
+    const int k1_k = h->g.kend_k;
+    const int nch = std::max(1, (P + h->tma_pl / 2) / std::max(1, h->tma_pl));
+    std::vector<TmaItem> items;
+    for (int c = 0; c < nch; c++) {
+        const int j0 = t.lj0 + (int)((long long)P * c / nch), j1 = t.lj0 + (int)((long long)P * (c + 1) / nch) - 1;
+        for (int it = 0; it < nit; it++)
+            for (int kt = 0; kt < nkt; kt++) {
+                TmaItem I{};
+                const int k0t = 1 + kt * TK;
+                // a last tile that would reach below the interior box is shifted up to the first k = 1 mod 4 that still covers kend_k
+                I.k0 = (k0t + TK - 1 > k1_k && k1_k >= TK && h->tma_shift) ? ((k1_k - TK + 3) / 4) * 4 + 1 : k0t;
+                I.kown = k0t;
+                I.li0 = t.li0 + it * TI; I.lj0 = j0; I.nsteps = j1 - j0 + 1;
+                items.push_back(I);
+            }
+    }
+    tp->t = t; tp->shift = h->tma_shift; tp->pl = h->tma_pl; tp->nitems = (int)items.size();
+    tp->grid = std::min(nsm, tp->nitems);
+    tp->base = 0;
+    CK(cudaMalloc(&tp->d_items, items.size() * sizeof(TmaItem)));
+    CK(cudaMalloc(&tp->d_ticket, sizeof(unsigned int)));
+    CK(cudaMemcpy(tp->d_items, items.data(), items.size() * sizeof(TmaItem), cudaMemcpyHostToDevice));
+    CK(cudaMemset(tp->d_ticket, 0, sizeof(unsigned int)));
+    return 0;
+}
+
 template <typename F, int NM>
 static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg) {
     using C = TmaCfg<F, NM>;
@@ -801,31 +1117,35 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
     g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
     g.shift_last = h->tma_shift;
     dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + 1) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
-    const int kE = (h->g.kend_k / C::TK) * C::TK + 1;   // first k of the tile that contains kend_k + 1 (warp-aligned)
-    // complement of the TMA box inside the owned box: two j slabs, two i slabs, one k slab (absorber cells only: the TMA
-    // tiles already did every interior cell, also in the partial last k-tile).  All six launches touch disjoint cells and
-    // only read V, so the shell boxes run on side streams next to the interior kernel.
-    Box3 bottom{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1, 0};
-    if (h->flat_bottom) { bottom.k0 = h->g.kend_k + 1; bottom.skip_interior = 0; bottom.flat = 1; }
-    // (the two i slabs are 20-odd columns wide, not a multiple of the block's 8: flat numbering there too)
-    const Box3 boxes[5] = {Box3{1, h->g.nz, rg.li0, rg.li1, rg.lj0, t.lj0 - 1, 0}, Box3{1, h->g.nz, rg.li0, rg.li1, t.lj1 + 1, rg.lj1, 0},
-                           Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0, h->flat_bottom}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0, h->flat_bottom},
-                           bottom};
+    // complement of the TMA box inside the owned box: the absorber shell (four slabs of wall columns, the bottom rows under the
+    // interior columns) and, if the interior box is not a whole number of tiles wide, the ragged interior columns.  All launches
+    // touch disjoint cells and only read V, so they are issued on side streams next to the interior kernel.
     if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
-    stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
+    if (h->tma_persist) {
+        const Region w = whole_region(h);
+        const int ri = (rg.li0 == w.li0 && rg.li1 == w.li1 && rg.lj0 == w.lj0 && rg.lj1 == w.lj1) ? 0 : 1;
+        TmaPlan *&tp = h->tplan[ri];
+        auto same = [](const Box3 &a, const Box3 &b) { return a.k1 == b.k1 && a.li0 == b.li0 && a.li1 == b.li1 && a.lj0 == b.lj0 && a.lj1 == b.lj1; };
+        if (tp && !(same(tp->t, t) && tp->shift == h->tma_shift && tp->pl == h->tma_pl)) {
+            CK(cudaDeviceSynchronize());
+            cudaFree(tp->d_items); cudaFree(tp->d_ticket);
+            delete tp;
+            tp = nullptr;
+        }
+        if (!tp) {
+            tp = new TmaPlan();
+            int bps = 1;   // resident blocks per SM (2 for the elastic instantiation)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, stress_tma_p<F, NM>, C::THREADS, C::SMEM) != cudaSuccess) { cudaGetLastError(); bps = 1; }
+            if (tplan_build(h, t, C::TK, C::TI, bps, tp)) return 1;
+        }
+        stress_tma_p<F, NM><<<tp->grid, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, tp->d_items, tp->nitems, tp->d_ticket, tp->base, g);
+        tp->base += (unsigned int)(tp->nitems + tp->grid);
+    } else {
+        stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
+    }
     h->launches++;
     CK(cudaGetLastError());
-    for (int q = 0; q < 5; q++) {
-        const Box3 &b = boxes[q];
-        if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
-        if (h->use_side) {
-            CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
-            if (launch_direct_box<F, true>(h, p, b, h->side[q])) return 1;
-            CK(cudaEventRecord(h->ev_join[q], h->side[q]));
-            CK(cudaStreamWaitEvent(h->st, h->ev_join[q], 0));
-        } else if (launch_direct_box<F, true>(h, p, b)) return 1;
-    }
-    return 0;
+    return launch_shell<F, true>(h, p, rg, t);
 }
 
 template <typename F, int NM>
@@ -842,9 +1162,6 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         // the bottom k slab) with the direct kernel on side streams.  Every launch writes disjoint cells and only reads S.
         const swpc3d_grid &gg = h->g;
         const Box3 in{1, gg.kend_k, ki0, ki1, kj0, kj1, 0};
-        const Box3 sh[5] = {Box3{1, gg.nz, rg.li0, rg.li1, rg.lj0, in.lj0 - 1, 0}, Box3{1, gg.nz, rg.li0, rg.li1, in.lj1 + 1, rg.lj1, 0},
-                            Box3{1, gg.nz, rg.li0, in.li0 - 1, in.lj0, in.lj1, 0, h->flat_bottom}, Box3{1, gg.nz, in.li1 + 1, rg.li1, in.lj0, in.lj1, 0, h->flat_bottom},
-                            Box3{gg.kend_k + 1, gg.nz, in.li0, in.li1, in.lj0, in.lj1, 0, h->flat_bottom}};
         const int jlen = std::max(1, h->ring_jlen);
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
         dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
@@ -852,17 +1169,7 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         vel_ring<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
         h->launches++;
         CK(cudaGetLastError());
-        for (int q = 0; q < 5; q++) {
-            const Box3 &b = sh[q];
-            if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
-            if (h->use_side) {
-                CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
-                if (launch_direct_box<F, false>(h, p, b, h->side[q])) return 1;
-                CK(cudaEventRecord(h->ev_join[q], h->side[q]));
-                CK(cudaStreamWaitEvent(h->st, h->ev_join[q], 0));
-            } else if (launch_direct_box<F, false>(h, p, b)) return 1;
-        }
-        return 0;
+        return launch_shell<F, false>(h, p, rg, in);
     }
     if (t.k1 < t.k0 || !h->vtma_ok || h->use_tma < 2) return launch_direct_box<F, false>(h, p, all);
     TmaGeom g{};
@@ -1598,6 +1905,8 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "zero_outer_halo")) h->zero_outer = value != 0;
     else if (!strcmp(key, "tma")) h->use_tma = value;
     else if (!strcmp(key, "tma_shift")) h->tma_shift = value != 0;
+    else if (!strcmp(key, "tma_persist")) h->tma_persist = value != 0;
+    else if (!strcmp(key, "tma_pl")) { if (value < 1) return fail("tma_pl must be >= 1"); h->tma_pl = value; }
     else if (!strcmp(key, "vel_ring")) h->use_ring = value;
     else if (!strcmp(key, "flat_bottom")) h->flat_bottom = value != 0;
     else if (!strcmp(key, "overlap")) h->overlap = value != 0;
@@ -1606,6 +1915,13 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "ring_pf")) { if (value < 0 || value > 8) return fail("ring_pf must be 0..8"); h->ring_pf = value; }
     else if (!strcmp(key, "side_streams")) h->use_side = value;
     else if (!strcmp(key, "comm_timeout_s")) h->comm_timeout_s = value;
+    else if (!strcmp(key, "pml_tma")) { h->use_pml = value; pml_drop(h); }
+    else if (!strcmp(key, "l2promo")) { h->l2promo = value; h->tma_ready = false; }
+    else if (!strcmp(key, "l2promo_halo")) { h->l2promo_halo = value; h->tma_ready = false; }
+    else if (!strcmp(key, "pml_promo")) { h->pml_promo = value; pml_drop(h); }
+    else if (!strcmp(key, "pml_promo_bottom")) { h->pml_promo_b = value; pml_drop(h); }
+    else if (!strcmp(key, "pml_jl")) { if (value < 1) return fail("pml_jl must be >= 1"); h->pml_jl = value; }
+    else if (!strcmp(key, "pml_jl_bottom")) { if (value < 1) return fail("pml_jl_bottom must be >= 1"); h->pml_jl_bottom = value; }
     else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }
     else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; h->cev_used = 0; h->halo_bytes = 0.0; }
     else return fail(std::string("unknown option ") + key);
@@ -1621,6 +1937,14 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "naux")) *value = (double)h->naux;
     else if (!strcmp(key, "device")) *value = h->dev;
     else if (!strcmp(key, "tma_ok")) *value = h->tma_ok ? 1.0 : 0.0;
+    else if (!strncmp(key, "pml_", 4)) {   // the shell plan of the last whole-region (core-region: "_core" suffix) sweeps
+        const int ri = strstr(key, "_core") ? 1 : 0, w = strstr(key, "_vel") ? 1 : 0;
+        const PmlPlan *pl = h->pml[ri][w];
+        if (!strncmp(key, "pml_items_walls", 15)) *value = pl ? pl->n_items[0] + pl->n_items[2] : 0;
+        else if (!strncmp(key, "pml_items_bottom", 16)) *value = pl ? pl->n_items[1] : 0;
+        else if (!strncmp(key, "pml_direct_boxes", 16)) *value = pl ? (double)pl->direct.size() : 0;
+        else return fail(std::string("unknown info key ") + key);
+    }
     else if (!strcmp(key, "ms_stress") || !strcmp(key, "ms_vel") || !strcmp(key, "n_stress") || !strcmp(key, "n_vel")) {
         const int w = strstr(key, "stress") ? 0 : 1;
         if (key[0] == 'n') { *value = (double)h->kev_used[w]; return 0; }

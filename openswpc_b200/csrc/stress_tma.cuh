@@ -236,6 +236,132 @@ stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps
 }
 
 // ================================================================================================
+// stress_tma, persistent form: ONE block per SM takes work items -- a tile (k0, li0) marching `nsteps` planes from lj0 --
+// from a global ticket counter, in the order k-tile, i-tile, j-chunk (the order the hardware dispatches stress_tma's grid in,
+// so that the blocks that run side by side are neighbours and their halos meet in L2).  Dynamic tickets, not a static split:
+// the SMs do not stream at the same rate (a static split of this sweep measured 20 % slower than the plain grid).  What the
+// persistent form buys over one block per chunk: the next item's loads are issued while the last planes of the previous one
+// are still being computed, chunks can be long (the 4-plane V prologue is paid per item), and there is no block launch / exit
+// in between.  Before an item's first ring loads the producer drains the pipeline (the rings have no room for two items'
+// planes), so the V / mu rings are indexed by the block's running step count.  The producer tells the consumers which
+// (item, plane) a stage holds through a small mailbox written before the stage's barrier is armed; item -1 ends the block.
+struct TmaItem {
+    int k0;        // first k of the boxes (1-based; 1 mod 4)
+    int kown;      // first k this tile owns: rows k0 .. kown-1 of a shifted last tile belong to the tile above
+    int li0, lj0;  // first local column / plane
+    int nsteps;
+};
+
+template <typename F, int NM>
+__global__ void __maxnreg__((TmaCfg<F, NM>::MAXREG))
+stress_tma_p(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps tm, const TmaItem *__restrict__ items, int nitems,
+             unsigned int *ticket, unsigned int ticket_base, const TmaGeom g) {
+    using C = TmaCfg<F, NM>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::BAR_OFF);
+    uint64_t *empty = full + C::NS;
+    volatile int2 *meta = reinterpret_cast<volatile int2 *>(smem + C::BAR_OFF + 64);   // (item, plane) of each stage
+    static_assert(2 * C::NS * 8 <= 64 && C::NS * 8 <= 64, "barriers and mailbox share 128 bytes");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::NS; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], C::NCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == C::NCW) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            int gs = 0;
+            for (;;) {
+                const unsigned int it = atomicAdd(ticket, 1u) - ticket_base;
+                if (it >= (unsigned int)nitems) break;
+                const TmaItem I = items[it];
+                const int ck = I.k0 + KOFF - 1, ci = I.li0 + HALO, cj = I.lj0 + HALO;
+                for (int t = 0; t < I.nsteps; t++, gs++) {
+                    const int s = gs % C::NS;
+                    if (gs >= C::NS) mbar_wait(&empty[s], ((gs / C::NS) - 1) & 1);
+                    unsigned char *st = smem + s * C::STAGE;
+                    uint32_t tx = C::STEP_TX;
+                    if (t == 0) tx += 4 * C::V_BYTES + C::MU_BYTES;
+                    meta[s].x = (int)it; meta[s].y = t;
+                    mbar_expect_tx(&full[s], tx);
+                    tma_load_4d(st, &tm.S, &full[s], ck, ci, cj + t, 3);
+                    if (NM > 0) tma_load_4d(st + C::R_OFF, &tm.R, &full[s], ck, ci, cj + t, 0);
+                    tma_load_4d(st + C::M_OFF, &tm.M, &full[s], ck, ci, cj + t, g.m_first);
+                    if (t == 0) {
+                        // drain: every earlier step released, so the prologue may overwrite any ring slot
+                        for (int q = C::NS - 1; q >= 1; q--) {
+                            const int gp = gs - q;
+                            if (gp >= 0) mbar_wait(&empty[gp % C::NS], (gp / C::NS) & 1);
+                        }
+                        for (int q = 0; q < 4; q++)
+                            tma_load_4d(smem + C::V_OFF + ((gs + q) % C::NV) * C::V_STRIDE, &tm.V, &full[s], ck - C::VHK, ci - 2, cj - 2 + q, 0);
+                        tma_load_4d(smem + C::MU_OFF + (gs % C::NMU) * C::MU_STRIDE, &tm.Mu, &full[s], ck, ci, cj, g.mu_index);
+                    }
+                    tma_load_4d(smem + C::V_OFF + ((gs + 4) % C::NV) * C::V_STRIDE, &tm.V, &full[s], ck - C::VHK, ci - 2, cj + t + 2, 0);
+                    tma_load_4d(smem + C::MU_OFF + ((gs + 1) % C::NMU) * C::MU_STRIDE, &tm.Mu, &full[s], ck, ci, cj + t + 1, g.mu_index);
+                }
+            }
+            const int s = gs % C::NS;   // end of work: an empty stage that carries item -1
+            if (gs >= C::NS) mbar_wait(&empty[s], ((gs / C::NS) - 1) & 1);
+            meta[s].x = -1; meta[s].y = 0;
+            mbar_arrive(&full[s]);
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers (as stress_tma)
+    const bool shear = warp >= C::NHW;
+    const int wq = shear ? warp - C::NHW : warp;
+    const int tk = (wq % (C::TK / 32)) * 32 + lane, ti = wq / (C::TK / 32);
+    AccTma<F, NM> a(p);
+    const int voff = (ti + 2) * C::VK + (tk + C::VHK);
+    const int muoff = ti * C::MUK + tk;
+    const int coff = ti * C::TK + tk;
+    int k = 0, mi = 0, mj = 0;
+    bool active = false;
+    long long col = 0;
+    for (int gs = 0;; gs++) {
+        const int s = gs % C::NS;
+        mbar_wait(&full[s], (gs / C::NS) & 1);
+        const int it = meta[s].x, t = meta[s].y;
+        if (it < 0) break;
+        if (t == 0) {
+            const TmaItem I = items[it];
+            k = I.k0 + tk;
+            mi = I.li0 + ti + HALO;
+            mj = I.lj0 + HALO;
+            active = k <= p.k1_k && k >= I.kown;
+            col = (long long)mi + (long long)p.NXM * mj;
+            a.n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+        }
+        const int4 bnd = p.band[col];
+        const unsigned char *st = smem + s * C::STAGE;
+#pragma unroll
+        for (int q = 0; q < 5; q++) a.v[q] = reinterpret_cast<const F *>(smem + C::V_OFF + ((gs + q) % C::NV) * C::V_STRIDE) + voff;
+        a.mu0 = reinterpret_cast<const float *>(smem + C::MU_OFF + (gs % C::NMU) * C::MU_STRIDE) + muoff;
+        a.mu1 = reinterpret_cast<const float *>(smem + C::MU_OFF + ((gs + 1) % C::NMU) * C::MU_STRIDE) + muoff;
+        a.s = reinterpret_cast<const F *>(st) + coff;
+        a.r = reinterpret_cast<const float *>(st + C::R_OFF) + coff;
+        a.m = reinterpret_cast<const float *>(st + C::M_OFF) + coff;
+        if (active) {
+            if (shear) stress_interior_t<F, NM, AccTma<F, NM>, false, true>(p, a, k, mi, mj, bnd);
+            else stress_interior_t<F, NM, AccTma<F, NM>, true, false>(p, a, k, mi, mj, bnd);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        a.n += p.SJ;
+        col += p.NXM;
+        mj++;
+    }
+}
+
+// ================================================================================================
 // velocity sweep, same scheme.  Per step t (plane j = j0 + t), one full-barrier:
 //   V    box (TK, TI, 1, 3)        Vx Vy Vz (field slots 0..2), read-modify-write   -> stage t % NS
 //   SA   box (TK+8, TI+4, 1, 3)    Sxx Szz Sxz (slots 3..5): only plane j is needed -> stage t % NS

@@ -118,7 +118,7 @@ def test_step_entry_point_and_run(tmp_path):
     _compare(o, [d], exact=True)
 
 
-@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}, {"flat_bottom": 0},
+@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"pml_tma": 0}, {"tma_persist": 1}, {"tma_persist": 1, "tma_pl": 5}, {"pml_jl": 4, "pml_jl_bottom": 5}, {"side_streams": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}, {"flat_bottom": 0},
                                      {"tma_shift": 1}, {"tma_shift": 0}])
 @pytest.mark.parametrize("abc", ["pml", "cerjan"])
 def test_kernel_variants_bit_exact(tmp_path, variant, abc):
@@ -126,6 +126,39 @@ def test_kernel_variants_bit_exact(tmp_path, variant, abc):
     o, devs = _run_pair(tmp_path, 24, nranks=(2, 1), nx=70, ny=44, abc_type=abc, options=variant,
                         sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
     _compare(o, devs, exact=True)
+
+
+@pytest.mark.parametrize("case", [
+    dict(nx=48, ny=40, nz=44, na=6),                                   # bottom box starts 2 rows above the absorber (k = 39 is 3 mod 4)
+    dict(nx=52, ny=47, nz=70, na=9),                                   # three k-tiles of the walls, the last one partial; 9-column walls = 2 tiles
+    dict(nx=90, ny=60, nz=44, na=20),                                  # the bench's absorber: 20 columns = two 10-wide tiles, 20 rows from k = 25
+    dict(nx=90, ny=60, nz=45, na=20, no_bottom=True),                  # 20 rows from k = 26 do not fit the 20-row box (it would start at 25)
+    dict(nx=44, ny=40, nz=37, na=3),                                   # walls thinner than the pipeline is deep: those regions stay with sweep_direct
+    dict(nx=60, ny=52, nz=64, na=10, nranks=(2, 2)),                   # ranks with walls on two sides only
+    dict(nx=48, ny=40, nz=44, na=6, mp="sp"),                          # float32 fields
+    dict(nx=48, ny=40, nz=44, na=6, nm=0, vmodel="lhm_land"),          # elastic
+])
+def test_tma_staged_absorber_shell_bit_exact(tmp_path, case):
+    """pml_tma (persistent, TMA-staged PML cells) against the oracle and against sweep_direct's PML path, every region kind:
+    full / partial k-tiles and column tiles, bottom boxes that start above the absorber, regions too thin for the pipeline."""
+    case = dict(case)
+    nranks, mp, nm, no_bottom = case.pop("nranks", (1, 1)), case.pop("mp", "dp"), case.pop("nm", 3), case.pop("no_bottom", False)
+    src = ["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"]
+    o, devs = _run_pair(tmp_path / "a", 36, nranks=nranks, mp=mp, nm=nm, sources=src, **case)
+    _compare(o, devs, exact=True)
+    thin = case["na"] < 4
+    for d in devs:   # the staged kernels did run (or, for the thin walls, did not)
+        walls, bottom = d.info("pml_items_walls"), d.info("pml_items_bottom")
+        assert (bottom > 0) != no_bottom
+        assert walls > 0
+        assert d.info("pml_direct_boxes") >= (2 if thin else 0)   # j slabs of 3 planes are shorter than the pipeline: sweep_direct
+        assert d.info("pml_items_walls_vel") == walls
+    o2, devs2 = _run_pair(tmp_path / "b", 36, nranks=nranks, mp=mp, nm=nm, sources=src, options={"pml_tma": 0}, **case)
+    _compare(o2, devs2, exact=True)
+    assert all(d.info("pml_items_walls") == 0 and d.info("pml_items_bottom") == 0 for d in devs2)
+    # the absorber has been reached: the ADE variables are in use
+    r = o.rank(0)
+    assert np.abs(o.field(0, "Vz")[3:3 + r["nyp"], 3:3 + case["na"] + 1, 3:-3]).max() > 0 or nranks != (1, 1)
 
 
 @pytest.mark.parametrize("abc,bf", [("pml", False), ("cerjan", False), ("pml", True)])
