@@ -155,6 +155,13 @@ int swpc3d_snap_step(swpc3d_handle *h, int32_t it);
  * is attached); out is written on the root only.  _max: max-V/H/A arrays of the fs/ob v and u products (:2295-2348). */
 int swpc3d_snap_fetch(swpc3d_handle *h, int32_t product, int32_t root, float *out);
 int swpc3d_snap_fetch_max(swpc3d_handle *h, int32_t product, int32_t root, float *out);
+/* The same reduction without stopping the time loop -- the reference overlaps it with the sweeps: `mpi_ireduce` of the current
+ * record, `mpi_wait` before the next one (m_snap.f90:1057-1064).  _begin (stream-ordered, returns at once) sets the slice
+ * buffer aside and starts reduce + device-to-host copy into pinned buffer `slot` (0 or 1) on a stream of its own; _end waits
+ * for it and returns the host pointer (valid until the next _begin of that product and slot; NULL on non-root ranks).
+ * _end may be called from another host thread than the one that drives the time loop. */
+int swpc3d_snap_fetch_begin(swpc3d_handle *h, int32_t product, int32_t root, int32_t slot);
+int swpc3d_snap_fetch_end(swpc3d_handle *h, int32_t product, int32_t slot, const float **data);
 /* sum-reduce a host float buffer over all ranks to root (setup-time medium slices of the snapshot headers, :600-607) */
 int swpc3d_reduce_sum(swpc3d_handle *h, float *buf, int64_t n, int32_t root);
 

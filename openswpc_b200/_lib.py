@@ -70,7 +70,7 @@ SYMBOLS = [
     "swpc3d_set_stations", "swpc3d_update_stress", "swpc3d_stressglut", "swpc3d_comm_stress", "swpc3d_update_vel",
     "swpc3d_bodyforce", "swpc3d_comm_vel", "swpc3d_wav_store", "swpc3d_step", "swpc3d_run", "swpc3d_sync", "swpc3d_vmax",
     "swpc3d_get_wav", "swpc3d_vmax_global", "swpc3d_set_wav_products", "swpc3d_get_wav_product", "swpc3d_snap_setup", "swpc3d_snap_step", "swpc3d_snap_fetch",
-    "swpc3d_snap_fetch_max", "swpc3d_reduce_sum", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
+    "swpc3d_snap_fetch_max", "swpc3d_snap_fetch_begin", "swpc3d_snap_fetch_end", "swpc3d_reduce_sum", "swpc3d_nccl_unique_id", "swpc3d_comm_init", "swpc3d_comm_local", "swpc3d_set_option", "swpc3d_get_info", "swpc3d_timer_start", "swpc3d_timer_stop",
     "swpc3d_set_green", "swpc3d_green_store", "swpc3d_green_source", "swpc3d_get_green", "swpc3d_advance",
 ]
 
@@ -117,6 +117,8 @@ def load() -> C.CDLL:
     lib.swpc3d_nccl_unique_id.argtypes = [C.c_char_p]
     lib.swpc3d_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     lib.swpc3d_comm_local.argtypes = [C.POINTER(vp), i32, i32]
+    lib.swpc3d_snap_fetch_begin.argtypes = [vp, i32, i32, i32]
+    lib.swpc3d_snap_fetch_end.argtypes = [vp, i32, i32, C.POINTER(fp)]
     lib.swpc3d_set_green.argtypes = [vp, i32, ip, ip, ip, i32, i32, i32, i32, i32] + [C.c_float] * 4 + [cp, i32, i32, C.c_float]
     lib.swpc3d_green_store.argtypes = [vp, i32]
     lib.swpc3d_green_source.argtypes = [vp, i32]

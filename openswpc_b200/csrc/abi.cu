@@ -56,6 +56,7 @@ struct NcclApi {
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t *) = nullptr;
     ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;   // optional (NCCL >= 2.18)
 };
 static NcclApi g_nccl;
 static int nccl_load() {
@@ -82,6 +83,7 @@ static int nccl_load() {
     SYM(CommGetAsyncError, "ncclCommGetAsyncError");
     SYM(CommAbort, "ncclCommAbort");
 #undef SYM
+    *(void **)(&g_nccl.CommSplit) = dlsym(g_nccl.lib, "ncclCommSplit");
     return 0;
 }
 #define NK(call)                                                                                       \
@@ -156,6 +158,13 @@ struct swpc3d_handle {
     bool snap_on = false;
     float *snap_buf[15] = {}, *snap_max[15] = {}, *snap_tmp = nullptr;
     size_t snap_tmp_n = 0;
+    // asynchronous fetch (swpc3d_snap_fetch_begin / _end): device staging copy, reduce target, double-buffered pinned host memory
+    cudaStream_t ss = nullptr;
+    float *snap_stage[15] = {}, *snap_red[15] = {}, *snap_pin[15][2] = {};
+    cudaEvent_t snap_ev_staged[15] = {}, snap_ev_done[15][2] = {};
+    bool snap_inflight[15] = {};
+    int snap_last_slot[15] = {};
+    ncclComm_t comm_io = nullptr;          // a communicator of its own for the snapshot reductions (they run beside the halo exchange)
     // halo
     void *sbuf[4] = {}, *rbuf[4] = {};     // 0: +x (ip) 1: -x (im) 2: +y (jp) 3: -y (jm)
     int nbr[4] = {-1, -1, -1, -1};
@@ -179,6 +188,7 @@ struct swpc3d_handle {
     bool vtma_ok = false;
     int variant = 1;
     int use_ring = 1, ring_jlen = 32, ring_pf = 2;   // vel_ring: register-pipelined interior velocity sweep
+    int ring_pair = 1;                               // option "ring_pair": float32 fields use vel_ring2 (two cells per thread)
     int flat_bottom = 1;                             // flat thread numbering for the bottom absorber slab (Box3::flat)
     // boundary-first overlap of the halo exchange (swpc3d_step): the two outermost owned planes towards every neighbour are
     // swept first, then pack / NCCL / unpack run on `cs` while the core of the subdomain is swept on `st`
@@ -425,7 +435,17 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->dev);
     cudaDeviceSynchronize();
+    if (h->comm_io && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm_io);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (int q = 0; q < 15; q++) {
+        cudaFree(h->snap_stage[q]); cudaFree(h->snap_red[q]);
+        if (h->snap_ev_staged[q]) cudaEventDestroy(h->snap_ev_staged[q]);
+        for (int b = 0; b < 2; b++) {
+            if (h->snap_pin[q][b]) cudaFreeHost(h->snap_pin[q][b]);
+            if (h->snap_ev_done[q][b]) cudaEventDestroy(h->snap_ev_done[q][b]);
+        }
+    }
+    if (h->ss) cudaStreamDestroy(h->ss);
     cudaFree(h->Fall);
     cudaFree(h->R);
     cudaFree(h->Mall);
@@ -1166,7 +1186,15 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
         dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
         if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
-        vel_ring<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
+        bool pair = false;
+        if constexpr (sizeof(F) == 4) {   // float32 fields: two cells per thread, 64-bit loads
+            if (h->ring_pair) {
+                pair = true;
+                grd.x = (unsigned)((in.k1 + 2 * h->tk - 1) / (2 * h->tk));
+                vel_ring2<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
+            }
+        }
+        if (!pair) vel_ring<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
         h->launches++;
         CK(cudaGetLastError());
         return launch_shell<F, false>(h, p, rg, in);
@@ -1630,6 +1658,66 @@ extern "C" int swpc3d_snap_fetch_max(swpc3d_handle *h, int32_t product, int32_t 
     snap_dims(h->snap, product, n1, n2, nvar);
     return snap_fetch_impl(h, h->snap_max[product], (size_t)n1 * n2 * 3, root, out);
 }
+// The asynchronous pair (m_snap.f90:1057-1064: `mpi_wait` of the previous record / `mpi_ireduce` of the current one): _begin
+// copies the slice buffer aside on the launch stream (device to device, microseconds) and lets a third stream reduce it onto
+// the root and copy it into pinned host memory [slot]; _end waits for that copy and returns the host pointer.  The sweeps go on
+// meanwhile; a slot may be reused once its _end has returned.
+static int event_wait(swpc3d_handle *h, cudaEvent_t ev) {
+    if (!h->comm) { CK(cudaEventSynchronize(ev)); return 0; }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (long long spin = 0;; spin++) {
+        const cudaError_t e = cudaEventQuery(ev);
+        if (e == cudaSuccess) return 0;
+        if (e != cudaErrorNotReady) return fail(std::string("event_wait: ") + cudaGetErrorString(e));
+        if ((spin & 255) == 255) {
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (h->comm_timeout_s > 0 && waited > (double)h->comm_timeout_s) return fail("snapshot reduction timed out: a rank stopped taking part");
+            if (waited > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
+    }
+}
+extern "C" int swpc3d_snap_fetch_begin(swpc3d_handle *h, int32_t product, int32_t root, int32_t slot) {
+    if (!h || product < 0 || product >= 15 || slot < 0 || slot > 1) return fail("swpc3d_snap_fetch_begin: bad argument");
+    if (!h->snap_buf[product]) return fail("swpc3d_snap_fetch_begin: product not enabled");
+    CK(cudaSetDevice(h->dev));
+    const int q = product;
+    int n1, n2, nvar;
+    snap_dims(h->snap, q, n1, n2, nvar);
+    const size_t n = (size_t)n1 * n2 * nvar, bytes = n * sizeof(float);
+    const bool is_root = !h->comm || h->g.myid == root;
+    if (!h->ss) CK(cudaStreamCreateWithFlags(&h->ss, cudaStreamNonBlocking));
+    if (!h->snap_stage[q]) {
+        CK(cudaMalloc(&h->snap_stage[q], bytes));
+        CK(cudaEventCreateWithFlags(&h->snap_ev_staged[q], cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) CK(cudaEventCreateWithFlags(&h->snap_ev_done[q][b], cudaEventDisableTiming));
+    }
+    if (is_root && !h->snap_pin[q][slot]) CK(cudaMallocHost(&h->snap_pin[q][slot], bytes));
+    if (h->comm && is_root && !h->snap_red[q]) CK(cudaMalloc(&h->snap_red[q], bytes));
+    // the staging copy is read by the previous record's reduce / copy on `ss`: overwrite it only after those
+    if (h->snap_inflight[q]) CK(cudaStreamWaitEvent(h->st, h->snap_ev_done[q][h->snap_last_slot[q]], 0));
+    CK(cudaMemcpyAsync(h->snap_stage[q], h->snap_buf[q], bytes, cudaMemcpyDeviceToDevice, h->st));
+    CK(cudaEventRecord(h->snap_ev_staged[q], h->st));
+    CK(cudaStreamWaitEvent(h->ss, h->snap_ev_staged[q], 0));
+    const float *from = h->snap_stage[q];
+    if (h->comm) {
+        ncclComm_t c = h->comm_io ? h->comm_io : h->comm;
+        NK(g_nccl.Reduce(h->snap_stage[q], is_root ? h->snap_red[q] : h->snap_stage[q], n, ncclFloat, ncclSum, root, c, h->ss));
+        from = h->snap_red[q];
+    }
+    if (is_root) CK(cudaMemcpyAsync(h->snap_pin[q][slot], from, bytes, cudaMemcpyDeviceToHost, h->ss));
+    CK(cudaEventRecord(h->snap_ev_done[q][slot], h->ss));
+    h->snap_inflight[q] = true;
+    h->snap_last_slot[q] = slot;
+    return 0;
+}
+extern "C" int swpc3d_snap_fetch_end(swpc3d_handle *h, int32_t product, int32_t slot, const float **data) {
+    if (!h || product < 0 || product >= 15 || slot < 0 || slot > 1) return fail("swpc3d_snap_fetch_end: bad argument");
+    if (!h->snap_ev_done[product][slot]) return fail("swpc3d_snap_fetch_end: no fetch was begun for this product");
+    CK(cudaSetDevice(h->dev));
+    if (event_wait(h, h->snap_ev_done[product][slot])) return 1;
+    if (data) *data = h->snap_pin[product][slot];   // NULL on the ranks that are not the root of this product
+    return 0;
+}
 extern "C" int swpc3d_reduce_sum(swpc3d_handle *h, float *buf, int64_t n, int32_t root) {
     if (!h || !buf || n < 0) return fail("swpc3d_reduce_sum: bad argument");
     if (!h->comm || n == 0) return 0;
@@ -1790,6 +1878,8 @@ extern "C" int swpc3d_comm_init(swpc3d_handle *h, const char id[128], int32_t nr
     NK(g_nccl.CommInitRank(&h->comm, nranks, u, rank));
     h->comm_rank = rank;
     h->comm_size = nranks;
+    // snapshot reductions get a communicator of their own: they are issued on another stream, beside the halo exchange
+    if (g_nccl.CommSplit && g_nccl.CommSplit(h->comm, 0, rank, &h->comm_io, nullptr) != ncclSuccess) h->comm_io = nullptr;
     return 0;
 }
 
@@ -1909,6 +1999,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "tma_pl")) { if (value < 1) return fail("tma_pl must be >= 1"); h->tma_pl = value; }
     else if (!strcmp(key, "vel_ring")) h->use_ring = value;
     else if (!strcmp(key, "flat_bottom")) h->flat_bottom = value != 0;
+    else if (!strcmp(key, "ring_pair")) h->ring_pair = value != 0;
     else if (!strcmp(key, "overlap")) h->overlap = value != 0;
     else if (!strcmp(key, "split_test")) h->split_test = value != 0;
     else if (!strcmp(key, "ring_jlen")) { if (value < 1) return fail("ring_jlen must be >= 1"); h->ring_jlen = value; }

@@ -7,6 +7,11 @@
 #include "../../../include/swpc3d_host.h"
 
 #include "common.hpp"
+
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include "models.hpp"
 
 // ============================================================================================================
@@ -828,7 +833,23 @@ struct SnapHost {
     bool any = false, opened = false;
     std::vector<float> tmp;
     bool native = false;
-    ~SnapHost() { for (auto &q : p) { delete q.nc; if (q.snp) std::fclose(q.snp); } }
+    // asynchronous output (the reference's mpi_ireduce / mpi_wait overlap, m_snap.f90:1057-1064): the time loop only starts
+    // the device-side fetch of a record; a writer thread waits for it and writes the file while the sweeps go on
+    struct Job { int q, slot, rec, it; };
+    std::thread writer;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Job> jobs;
+    bool stop = false, busy = false;
+    int slot_busy[15][2] = {};
+    std::string werr;
+    void stop_writer() {
+        if (!writer.joinable()) return;
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        writer.join();
+    }
+    ~SnapHost() { stop_writer(); for (auto &q : p) { delete q.nc; if (q.snp) std::fclose(q.snp); } }
 };
 
 int swpc3d_host::setup_snap(const IniFile &ini) {   // m_snap.f90:95-322
@@ -1005,32 +1026,73 @@ int swpc3d_host::snap_open_files(const std::string &dir) {
     return 0;
 }
 
-// snap__write(it): device step, and at output steps reduce + record write (wbuf_nc :950-979; written at once instead of
-// one cycle later -- same record index it0/ntdec_s+1, same time it0*dt, same data)
+// one record of one product into its file (wbuf_nc :950-979 / write_reduce_array2d_r): runs on the writer thread
+static void snap_put_record(SnapHost &S, SnapProd &P, const float *data, int rec, float tval) {
+    const size_t np = (size_t)P.n1 * P.n2;
+    if (P.snp) { std::fwrite(data, 4, np * (size_t)P.nvar, P.snp); std::fflush(P.snp); return; }
+    if (!P.nc) return;
+    (void)S;
+    P.nc->put_record(P.nc->var_index("t"), rec, &tval, 1);
+    for (int v = 0; v < P.nvar; v++) {
+        const float *d = data + np * (size_t)v;
+        const int vi = P.nc->var_index(P.vname[(size_t)v]);
+        P.nc->put_record(vi, rec, d, np);
+        for (size_t n = 0; n < np; n++) { P.vmax[v] = std::max(P.vmax[v], d[n]); P.vmin[v] = std::min(P.vmin[v], d[n]); }
+        *P.nc->find_att(P.nc->vars[(size_t)vi], "actual_range") = att_floats("actual_range", {P.vmin[v], P.vmax[v]});
+    }
+    P.nc->flush_header();
+}
+
+// snap__write(it): device step, and at output steps the record of every product: the device-side fetch (reduce onto the I/O
+// rank + copy to pinned host memory, on a stream of its own) is only STARTED here; the writer thread waits for it and writes
+// the file (same record index it0/ntdec_s+1, same time it0*dt, same data as the reference's one-cycle-late wbuf_nc).  A
+// record's host buffer (two per product) is reused two records later: the loop waits for the writer only then.
 int swpc3d_host::snap_write(int it) {
     SnapHost &S = *snap;
     if (!S.any || !S.opened) return 0;
     if (swpc3d_snap_step(dev, it)) return hfail(std::string("device: ") + swpc3d_last_error());
     if (!(S.ntdec_s > 0 && (it - 1) % S.ntdec_s == 0)) return 0;
+    const int rec = it / S.ntdec_s;   // stt(3) = it0/ntdec_s + 1, zero-based here
+    if (!S.writer.joinable()) {
+        S.stop = false;
+        S.writer = std::thread([this, &S]() {
+            for (;;) {
+                SnapHost::Job j;
+                {
+                    std::unique_lock<std::mutex> lk(S.mu);
+                    S.cv.wait(lk, [&] { return S.stop || !S.jobs.empty(); });
+                    if (S.jobs.empty()) return;   // stop requested and nothing left
+                    j = S.jobs.front();
+                    S.jobs.pop_front();
+                    S.busy = true;
+                }
+                const float *data = nullptr;
+                std::string err;
+                if (swpc3d_snap_fetch_end(dev, j.q, j.slot, &data)) err = std::string("device: ") + swpc3d_last_error();
+                else if (data) snap_put_record(S, S.p[j.q], data, j.rec, j.it * dt);
+                {
+                    std::lock_guard<std::mutex> lk(S.mu);
+                    S.slot_busy[j.q][j.slot] = 0;
+                    S.busy = false;
+                    if (!err.empty() && S.werr.empty()) S.werr = err;
+                }
+                S.cv.notify_all();
+            }
+        });
+    }
     for (int q = 0; q < 15; q++) {
         SnapProd &P = S.p[q];
         if (!P.on) continue;
-        const size_t np = (size_t)P.n1 * P.n2;
-        S.tmp.assign(np * (size_t)P.nvar, 0.0f);
-        if (swpc3d_snap_fetch(dev, q, P.ionode, S.tmp.data())) return hfail(std::string("device: ") + swpc3d_last_error());
-        if (P.snp) { std::fwrite(S.tmp.data(), 4, np * (size_t)P.nvar, P.snp); std::fflush(P.snp); continue; }   // write_reduce_array2d_r per component
-        if (!P.nc) continue;
-        const int rec = it / S.ntdec_s;   // stt(3) = it0/ntdec_s + 1, zero-based here
-        const float tval = it * dt;
-        P.nc->put_record(P.nc->var_index("t"), rec, &tval, 1);
-        for (int v = 0; v < P.nvar; v++) {
-            const float *d = S.tmp.data() + np * (size_t)v;
-            const int vi = P.nc->var_index(P.vname[(size_t)v]);
-            P.nc->put_record(vi, rec, d, np);
-            for (size_t n = 0; n < np; n++) { P.vmax[v] = std::max(P.vmax[v], d[n]); P.vmin[v] = std::min(P.vmin[v], d[n]); }
-            *P.nc->find_att(P.nc->vars[(size_t)vi], "actual_range") = att_floats("actual_range", {P.vmin[v], P.vmax[v]});
+        const int slot = rec & 1;
+        {
+            std::unique_lock<std::mutex> lk(S.mu);
+            S.cv.wait(lk, [&] { return S.slot_busy[q][slot] == 0; });   // the reference's mpi_wait before reusing the buffer
+            if (!S.werr.empty()) return hfail("snapshot writer: " + S.werr);
+            S.slot_busy[q][slot] = 1;
         }
-        P.nc->flush_header();
+        if (swpc3d_snap_fetch_begin(dev, q, P.ionode, slot)) return hfail(std::string("device: ") + swpc3d_last_error());
+        { std::lock_guard<std::mutex> lk(S.mu); S.jobs.push_back(SnapHost::Job{q, slot, rec, it}); }
+        S.cv.notify_all();
     }
     return 0;
 }
@@ -1039,6 +1101,12 @@ int swpc3d_host::snap_write(int it) {
 int swpc3d_host::snap_close() {
     SnapHost &S = *snap;
     if (!S.any || !S.opened) return 0;
+    {   // every record that was started is on disk before the maxima are fetched and the files closed
+        std::unique_lock<std::mutex> lk(S.mu);
+        S.cv.wait(lk, [&] { return S.jobs.empty() && !S.busy; });
+        if (!S.werr.empty()) return hfail("snapshot writer: " + S.werr);
+    }
+    S.stop_writer();
     for (int q = 0; q < 15; q++) {
         SnapProd &P = S.p[q];
         if (!P.on) continue;

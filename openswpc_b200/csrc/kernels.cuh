@@ -645,6 +645,151 @@ __global__ void __launch_bounds__(SWPC_RING_THREADS, SWPC_RING_MINB) vel_ring(co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Velocity sweep over INTERIOR cells, version 3 ("ring, two cells per thread"): for float32 fields (the reference's MP = SP
+// build) vel_ring moves half the bytes of the float64 run with the same instruction count and ends up instruction / latency
+// bound (50 % of the HBM peak).  Here a thread owns the cells (k, k+1) of a column: every own-column stream and every in-plane
+// neighbour comes in as ONE 64-bit load for both cells -- 25 vector loads per cell pair where vel_ring issues 72 scalar ones --
+// and the k-neighbours that are the pair's own other cell come from registers.  Same arithmetic body (vel_interior_calc).
+template <typename F> struct Vec2;
+template <> struct Vec2<float> { using T = float2; };
+template <> struct Vec2<double> { using T = double2; };
+
+template <typename F>
+struct RingPair {
+    using F2 = typename Vec2<F>::T;
+    F2 sxx0, szz0, sxz0;               // own column, plane j
+    F2 syy[4];                         // j-1 .. j+2
+    F2 sxy[4], syz[4];                 // j-2 .. j+1
+    F2 v[3];
+    float2 rho0, rho_j1, rho_i1;
+    float rho_k2;
+    F2 sxx_i[3];                       // columns i-1, i+1, i+2
+    F2 sxy_i[3], sxz_i[3];             // columns i-2, i-1, i+1
+    F2 sxz_k[2], syz_k[2], szz_k[2];   // rows (k-2, k-1) and (k+2, k+3)
+};
+
+template <typename F, int E>
+struct AccVelPair {
+    using F2 = typename Vec2<F>::T;
+    const RingPair<F> &r;
+    __device__ __forceinline__ AccVelPair(const RingPair<F> &r_) : r(r_) {}
+    template <typename T2> static __device__ __forceinline__ auto el(const T2 &v) { return E == 0 ? v.x : v.y; }
+    // value at row k + E + dk of a column whose rows (k-2, k-1), (k, k+1), (k+2, k+3) are lo, mid, hi
+    template <int dk> static __device__ __forceinline__ F row(const F2 &lo, const F2 &mid, const F2 &hi) {
+        constexpr int q = E + dk;
+        static_assert(q >= -2 && q <= 3, "row out of the preloaded range");
+        return q == -2 ? lo.x : q == -1 ? lo.y : q == 0 ? mid.x : q == 1 ? mid.y : q == 2 ? hi.x : hi.y;
+    }
+    template <int c, int dk, int di, int dj> __device__ __forceinline__ F S() const {
+        if constexpr (c == 0) {
+            static_assert(dk == 0 && dj == 0, "Sxx: i neighbours only");
+            if constexpr (di == 0) return el(r.sxx0);
+            else return el(r.sxx_i[di == -1 ? 0 : di == 1 ? 1 : 2]);
+        } else if constexpr (c == 1) {
+            static_assert(dk == 0 && di == 0, "Syy: j neighbours only");
+            return el(r.syy[dj + 1]);
+        } else if constexpr (c == 2) {
+            static_assert(di == 0 && dj == 0, "Szz: k neighbours only");
+            return row<dk>(r.szz_k[0], r.szz0, r.szz_k[1]);
+        } else if constexpr (c == 3) {
+            static_assert(di == 0, "Syz: j and k neighbours only");
+            if constexpr (dk == 0) return el(r.syz[dj + 2]);
+            else return row<dk>(r.syz_k[0], r.syz[2], r.syz_k[1]);
+        } else if constexpr (c == 4) {
+            static_assert(dj == 0, "Sxz: i and k neighbours only");
+            if constexpr (di != 0) return el(r.sxz_i[di == -2 ? 0 : di == -1 ? 1 : 2]);
+            else return row<dk>(r.sxz_k[0], r.sxz0, r.sxz_k[1]);
+        } else {
+            static_assert(dk == 0, "Sxy: i and j neighbours only");
+            if constexpr (di != 0) return el(r.sxy_i[di == -2 ? 0 : di == -1 ? 1 : 2]);
+            else return el(r.sxy[dj + 2]);
+        }
+    }
+    template <int dk, int di, int dj> __device__ __forceinline__ float rho() const {
+        if constexpr (dk == 1) return E == 0 ? r.rho0.y : r.rho_k2;
+        else if constexpr (di == 1) return el(r.rho_i1);
+        else if constexpr (dj == 1) return el(r.rho_j1);
+        else return el(r.rho0);
+    }
+    __device__ __forceinline__ F V(int f) const { return el(r.v[f]); }
+};
+
+template <typename T2, typename T> __device__ __forceinline__ T2 ld2ro(const T *ptr) { return __ldg(reinterpret_cast<const T2 *>(ptr)); }
+template <typename T2, typename T> __device__ __forceinline__ T2 ld2cs(const T *ptr) { return __ldcs(reinterpret_cast<const T2 *>(ptr)); }
+
+template <typename F>
+__global__ void __launch_bounds__(SWPC_RING_THREADS, SWPC_RING_MINB) vel_ring2(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
+    using F2 = typename Vec2<F>::T;
+    const int k = b.k0 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // b.k0 is odd: index k + KOFF - 1 is even, 2-element loads are aligned
+    const int li = b.li0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (k > b.k1 || li > b.li1) return;
+    const bool two = k + 1 <= b.k1;
+    const int mi = li + HALO;
+    const int ljs = b.lj0 + blockIdx.z * jlen;
+    const int lje = min(ljs + jlen, b.lj1 + 1);
+    const long long sj = p.SJ, si = p.SI;
+    RingPair<F> r;
+    long long col = (long long)mi + (long long)p.NXM * (ljs + HALO);
+    long long n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
+    {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            r.syy[q] = ld2ro<F2>(p.Syy + n + (q - 1) * sj);
+            r.sxy[q] = ld2ro<F2>(p.Sxy + n + (q - 2) * sj);
+            r.syz[q] = ld2ro<F2>(p.Syz + n + (q - 2) * sj);
+        }
+        r.sxx0 = ld2ro<F2>(p.Sxx + n); r.szz0 = ld2ro<F2>(p.Szz + n); r.sxz0 = ld2ro<F2>(p.Sxz + n);
+        r.v[0] = ld2cs<F2>(p.Vx + n); r.v[1] = ld2cs<F2>(p.Vy + n); r.v[2] = ld2cs<F2>(p.Vz + n);
+        r.rho0 = ld2ro<float2>(p.rho + n); r.rho_j1 = ld2ro<float2>(p.rho + n + sj);
+    }
+    int4 bnd = p.band[col];
+    for (int lj = ljs; lj < lje; lj++) {
+        const bool more = (lj + 1 < lje);
+        F2 nsxx{}, nszz{}, nsxz{}, nsyy{}, nsxy{}, nsyz{}, nv0{}, nv1{}, nv2{};
+        float2 nrho{};
+        int4 nbnd = bnd;
+        if (more) {   // plane j+1, consumed next iteration
+            nsxx = ld2ro<F2>(p.Sxx + n + sj); nszz = ld2ro<F2>(p.Szz + n + sj); nsxz = ld2ro<F2>(p.Sxz + n + sj);
+            nsyy = ld2ro<F2>(p.Syy + n + 3 * sj); nsxy = ld2ro<F2>(p.Sxy + n + 2 * sj); nsyz = ld2ro<F2>(p.Syz + n + 2 * sj);
+            nv0 = ld2cs<F2>(p.Vx + n + sj); nv1 = ld2cs<F2>(p.Vy + n + sj); nv2 = ld2cs<F2>(p.Vz + n + sj);
+            nrho = ld2ro<float2>(p.rho + n + 2 * sj);
+            nbnd = p.band[col + p.NXM];
+            if (pf > 0 && lj + 1 + pf < lje) {
+                const long long q = n + sj * (1 + pf);
+                pf_l2(p.Sxx + q); pf_l2(p.Szz + q); pf_l2(p.Sxz + q); pf_l2(p.Vx + q); pf_l2(p.Vy + q); pf_l2(p.Vz + q);
+                pf_l2(p.Syy + q + 2 * sj); pf_l2(p.Sxy + q + sj); pf_l2(p.Syz + q + sj); pf_l2(p.rho + q + sj);
+            }
+        }
+        // in-plane neighbours of plane j: lines the neighbour threads pulled into L1 one or two iterations earlier
+        r.sxx_i[0] = ld2ro<F2>(p.Sxx + n - si); r.sxx_i[1] = ld2ro<F2>(p.Sxx + n + si); r.sxx_i[2] = ld2ro<F2>(p.Sxx + n + 2 * si);
+        r.sxy_i[0] = ld2ro<F2>(p.Sxy + n - 2 * si); r.sxy_i[1] = ld2ro<F2>(p.Sxy + n - si); r.sxy_i[2] = ld2ro<F2>(p.Sxy + n + si);
+        r.sxz_i[0] = ld2ro<F2>(p.Sxz + n - 2 * si); r.sxz_i[1] = ld2ro<F2>(p.Sxz + n - si); r.sxz_i[2] = ld2ro<F2>(p.Sxz + n + si);
+        r.sxz_k[0] = ld2ro<F2>(p.Sxz + n - 2); r.sxz_k[1] = ld2ro<F2>(p.Sxz + n + 2);
+        r.syz_k[0] = ld2ro<F2>(p.Syz + n - 2); r.syz_k[1] = ld2ro<F2>(p.Syz + n + 2);
+        r.szz_k[0] = ld2ro<F2>(p.Szz + n - 2); r.szz_k[1] = ld2ro<F2>(p.Szz + n + 2);
+        r.rho_i1 = ld2ro<float2>(p.rho + n + si);
+        r.rho_k2 = ldro(p.rho + n + 2);
+        F2 ox, oy, oz;
+        vel_interior_calc<F>(p, AccVelPair<F, 0>(r), k, mi, lj + HALO, bnd, ox.x, oy.x, oz.x);
+        vel_interior_calc<F>(p, AccVelPair<F, 1>(r), k + 1, mi, lj + HALO, bnd, ox.y, oy.y, oz.y);
+        if (two) {
+            __stcs(reinterpret_cast<F2 *>(p.Vx + n), ox); __stcs(reinterpret_cast<F2 *>(p.Vy + n), oy); __stcs(reinterpret_cast<F2 *>(p.Vz + n), oz);
+        } else {
+            sts_(p.Vx + n, ox.x); sts_(p.Vy + n, oy.x); sts_(p.Vz + n, oz.x);
+        }
+        r.syy[0] = r.syy[1]; r.syy[1] = r.syy[2]; r.syy[2] = r.syy[3]; r.syy[3] = nsyy;
+        r.sxy[0] = r.sxy[1]; r.sxy[1] = r.sxy[2]; r.sxy[2] = r.sxy[3]; r.sxy[3] = nsxy;
+        r.syz[0] = r.syz[1]; r.syz[1] = r.syz[2]; r.syz[2] = r.syz[3]; r.syz[3] = nsyz;
+        r.sxx0 = nsxx; r.szz0 = nszz; r.sxz0 = nsxz;
+        r.v[0] = nv0; r.v[1] = nv1; r.v[2] = nv2;
+        r.rho0 = r.rho_j1; r.rho_j1 = nrho;
+        bnd = nbnd;
+        n += sj;
+        col += p.NXM;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // source time functions, m_fdtool.f90:339-497 (PI is real(DP) there)
 __device__ __forceinline__ float momentrate_dev(float t, int stf, float ts, float tr) {
     const double PI = 3.14159265358979323846;

@@ -92,7 +92,12 @@ struct TmaCfg {
     // elastic runs (NM = 0) move 128 B per cell instead of 280: the consumer warps of ONE resident block cannot keep up with
     // HBM, so that instantiation takes a 2-stage ring (100 KB) and a 56-register cap (17 warps x 1792 registers): two blocks per SM
     // (stress sweep 4.31 -> 3.89 ms at 512^3; the same change for float32 fields with NM = 3 measured 1 % slower, not kept)
-    static constexpr int TK = SWPC_TMA_TK, TI = SWPC_TMA_TI, NS = (NM == 0 && sizeof(F) == 8 && SWPC_TMA_NM0_TWO) ? 2 : SWPC_TMA_NS;
+    // float32 fields: a stage is 27 KB instead of 45 KB -- a 4-stage ring fits (164 KB) and covers more latency
+#ifndef SWPC_TMA_NS_F32
+#define SWPC_TMA_NS_F32 4
+#endif
+    static constexpr int TK = SWPC_TMA_TK, TI = SWPC_TMA_TI,
+                         NS = (NM == 0 && sizeof(F) == 8 && SWPC_TMA_NM0_TWO) ? 2 : (sizeof(F) == 4 && NM > 0) ? SWPC_TMA_NS_F32 : SWPC_TMA_NS;
     static constexpr int MAXREG = (NM == 0 && sizeof(F) == 8 && SWPC_TMA_NM0_TWO) ? 56 : SWPC_TMA_MAXREG;
     static constexpr int NHW = (TK / 32) * TI;   // warps per half: one warp = 32 consecutive k of one column
     static constexpr int NCW = 2 * NHW;          // consumer warps: NHW for the normal, NHW for the shear components

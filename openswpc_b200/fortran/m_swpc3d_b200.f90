@@ -41,6 +41,7 @@ module m_swpc3d_b200
     public :: swpc3d_nccl_unique_id, swpc3d_comm_init, swpc3d_last_error
     public :: swpc3d_set_wav_products, swpc3d_get_wav_product, swpc3d_set_option
     public :: swpc3d_snap_cfg, swpc3d_snap_setup, swpc3d_snap_step, swpc3d_snap_fetch, swpc3d_snap_fetch_max, swpc3d_reduce_sum
+    public :: swpc3d_snap_fetch_begin, swpc3d_snap_fetch_end
     public :: swpc3d_set_green, swpc3d_green_store, swpc3d_green_source, swpc3d_get_green, swpc3d_advance
     public :: swpc3d_version, swpc3d_zero_state, swpc3d_run, swpc3d_timer_start, swpc3d_timer_stop, swpc3d_get_info, swpc3d_comm_local
     public :: swpc3d_check
@@ -233,6 +234,18 @@ module m_swpc3d_b200
             type(c_ptr), value :: h
             integer(c_int32_t), value :: product, root
             real(c_float), intent(out) :: rbuf(*)           !! (nxs, nys, 3): max-V, max-H, max-A
+        end function
+        !! the asynchronous pair: mpi_ireduce of the current record / mpi_wait before the next one (m_snap.f90:1057-1064)
+        integer(c_int) function swpc3d_snap_fetch_begin(h, product, root, slot) bind(c, name='swpc3d_snap_fetch_begin')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: product, root, slot    !! slot = 0 or 1: which pinned host buffer receives the record
+        end function
+        integer(c_int) function swpc3d_snap_fetch_end(h, product, slot, rbuf) bind(c, name='swpc3d_snap_fetch_end')
+            import :: c_int, c_int32_t, c_ptr
+            type(c_ptr), value :: h
+            integer(c_int32_t), value :: product, slot
+            type(c_ptr), intent(out) :: rbuf                    !! c_f_pointer(rbuf, buf, [n1, n2, nvar]) on the root; c_null_ptr elsewhere
         end function
         integer(c_int) function swpc3d_reduce_sum(h, buf, n, root) bind(c, name='swpc3d_reduce_sum')
             import :: c_int, c_int32_t, c_int64_t, c_float, c_ptr

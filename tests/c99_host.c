@@ -45,7 +45,8 @@ static anyfn entry_points[] = {
     (anyfn)swpc3d_green_store, (anyfn)swpc3d_green_source, (anyfn)swpc3d_get_green, (anyfn)swpc3d_update_stress, (anyfn)swpc3d_stressglut,
     (anyfn)swpc3d_comm_stress, (anyfn)swpc3d_update_vel, (anyfn)swpc3d_bodyforce, (anyfn)swpc3d_comm_vel, (anyfn)swpc3d_wav_store, (anyfn)swpc3d_step,
     (anyfn)swpc3d_advance, (anyfn)swpc3d_run, (anyfn)swpc3d_sync, (anyfn)swpc3d_vmax, (anyfn)swpc3d_vmax_global, (anyfn)swpc3d_get_wav,
-    (anyfn)swpc3d_snap_setup, (anyfn)swpc3d_snap_step, (anyfn)swpc3d_snap_fetch, (anyfn)swpc3d_snap_fetch_max, (anyfn)swpc3d_reduce_sum,
+    (anyfn)swpc3d_snap_setup, (anyfn)swpc3d_snap_step, (anyfn)swpc3d_snap_fetch, (anyfn)swpc3d_snap_fetch_max, (anyfn)swpc3d_snap_fetch_begin, (anyfn)swpc3d_snap_fetch_end,
+    (anyfn)swpc3d_reduce_sum,
     (anyfn)swpc3d_nccl_unique_id, (anyfn)swpc3d_comm_init, (anyfn)swpc3d_comm_local, (anyfn)swpc3d_timer_start, (anyfn)swpc3d_timer_stop,
     (anyfn)swpc3d_set_option, (anyfn)swpc3d_get_info,
     (anyfn)swpcpsv_last_error, (anyfn)swpcpsv_version, (anyfn)swpcpsv_create, (anyfn)swpcpsv_destroy, (anyfn)swpcpsv_step, (anyfn)swpcpsv_run,

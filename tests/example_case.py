@@ -45,8 +45,37 @@ def es92(x: float) -> str:
     return f"{m}E{int(e):+03d}"
 
 
-def write_example(d: Path, *, n=384, nz=384, nt=1000, nproc_x=2, nproc_y=2) -> Path:
-    """example/input.inf (keys that the in-scope path reads), optionally on a smaller box centred on the source."""
+# example/input.inf:55-83, verbatim values
+EXAMPLE_SNAP_BLOCK = """
+  snp_format       = 'netcdf'
+  xy_ps%sw         = .false.
+  xz_ps%sw         = .true.
+  yz_ps%sw         = .false.
+  fs_ps%sw         = .false.
+  ob_ps%sw         = .true.
+  xy_v%sw          = .false.
+  xz_v%sw          = .true.
+  yz_v%sw          = .false.
+  fs_v%sw          = .false.
+  ob_v%sw          = .true.
+  xy_u%sw          = .false.
+  xz_u%sw          = .true.
+  yz_u%sw          = .false.
+  fs_u%sw          = .false.
+  ob_u%sw          = .true.
+  z0_xy            =  7.0
+  x0_yz            =  0.0
+  y0_xz            =  0.0
+  ntdec_s          = 5
+  idec             = 2
+  jdec             = 2
+  kdec             = 2
+"""
+
+
+def write_example(d: Path, *, n=384, nz=384, nt=1000, nproc_x=2, nproc_y=2, snapshots=False) -> Path:
+    """example/input.inf (keys that the in-scope path reads), optionally on a smaller box centred on the source;
+    `snapshots`: with the snapshot block of example/input.inf:55-83 (six netCDF products every 5 steps)."""
     d = Path(d)
     d.mkdir(parents=True, exist_ok=True)
     (d / "lhm.dat").write_text(EXAMPLE_LHM)
@@ -95,5 +124,5 @@ def write_example(d: Path, *, n=384, nz=384, nt=1000, nproc_x=2, nproc_y=2) -> P
   munk_profile     = .true.
   earth_flattening = .false.
   fn_lhm           = 'lhm.dat'
-""")
+""" + (EXAMPLE_SNAP_BLOCK if snapshots else ""))
     return d / "input.inf"

@@ -108,6 +108,16 @@ def test_single_precision_fields(tmp_path):
     _compare(o, devs, exact=True)
 
 
+@pytest.mark.parametrize("variant", [{}, {"ring_pair": 0}, {"vel_ring": 0}, {"tma": 0}, {"pml_tma": 0}, {"ring_jlen": 7}])
+@pytest.mark.parametrize("nz,abc", [(44, "pml"), (45, "pml"), (41, "cerjan")])
+def test_single_precision_kernel_variants(tmp_path, variant, nz, abc):
+    # float32 fields: vel_ring2 (two cells per thread: odd and even row counts of the interior box, kend_k = 38 / 39 / 41) and
+    # every other kernel of the two sweeps against the MP=SP oracle
+    o, devs = _run_pair(tmp_path, 24, mp="sp", nz=nz, abc_type=abc, nranks=(2, 1), nx=70, ny=44, options=variant,
+                        sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
+    _compare(o, devs, exact=True)
+
+
 def test_step_entry_point_and_run(tmp_path):
     inf = write_case(tmp_path, nt=24, sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
     o = Oracle(inf, base_dir=tmp_path, nm=3)
