@@ -670,15 +670,27 @@ def main():
     ms_halo, n_halo, halo_bytes = run.info("ms_halo"), run.info("n_halo"), run.info("halo_bytes")
     run.set_option("kernel_timing", 0)
     # the halo phase on its own (nothing else on the GPU): 10 velocity exchanges, idempotent on an up-to-date halo
-    ms_halo_alone = 0.0
+    ms_halo_alone = ms_halo_alone_nccl = 0.0
+    p2p_on = 0.0
     if world > 1:
-        run.set_option("kernel_timing", 1)
-        barrier()
-        for _ in range(10):
-            run.device_call("swpc3d_comm_vel")
-        barrier()
-        ms_halo_alone = run.info("ms_halo")
-        run.set_option("kernel_timing", 0)
+        p2p_on = run.info("p2p_ok")
+
+        def exchange_alone():
+            run.set_option("kernel_timing", 1)
+            barrier()
+            for _ in range(10):
+                run.device_call("swpc3d_comm_vel")
+            barrier()
+            v = run.info("ms_halo")
+            run.set_option("kernel_timing", 0)
+            return v
+
+        ms_halo_alone = exchange_alone()
+        if p2p_on:   # the library path (pack + ncclSend/ncclRecv + unpack) beside it, for the record
+            run.set_option("p2p", 0)
+            exchange_alone()
+            ms_halo_alone_nccl = exchange_alone()
+            run.set_option("p2p", 1)
 
     # ---- timed region 2 (e2e): the call a user makes -- Swpc3d.run() + waveform read-back, host wall clock.
     # Every step the host evaluates the moment-rate values and copies them to the device; every ntdec_r steps the
@@ -702,7 +714,7 @@ def main():
     c_interior, c_pml = cell_counts(run, core_region(run, world)) if overlapped else (interior, pml)
     exposed_rank = ms / K - ms_stress - ms_vel   # this rank's step time outside its two sweep brackets (not clamped)
     stats = torch.tensor([ms, t_e2e * 1e3, launches, h2d, d2h, float(interior), float(pml), ms_stress, ms_vel, ms_halo,
-                          halo_bytes / max(n_halo, 1.0), ms_halo_alone, exposed_rank], dtype=torch.float64, device="cuda")
+                          halo_bytes / max(n_halo, 1.0), ms_halo_alone, exposed_rank, ms_halo_alone_nccl], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -759,14 +771,18 @@ def main():
                         "traces D2H + SAC write; fields stay device-resident as in the reference's `!$acc enter data` design",
                 "one_time_upload_s": t_upload, "host_setup_s": t_host},
         "halo": None if world == 1 else {
-            "what": "one exchange = pack kernels + ncclSend/ncclRecv with up to 4 neighbours + unpack kernels of one field family "
-                    "(2 exchanges per step), CUDA events on the exchange stream; it runs beside the core sweep (boundary-first overlap)",
+            "what": ("one exchange of one field family (2 per step) = push kernels that store the face planes straight into the neighbours' receive "
+                     "buffers over NVLink (CUDA IPC peer memory, release/acquire flags) + wait + pull kernels" if p2p_on else
+                     "one exchange of one field family (2 per step) = pack kernels + ncclSend/ncclRecv with up to 4 neighbours + unpack kernels") +
+                    "; CUDA events on the exchange stream; it runs beside the core sweep (boundary-first overlap)",
+            "transport": "peer-to-peer stores (halo_push / halo_wait / halo_pull)" if p2p_on else "NCCL send/recv",
+            "ms_per_exchange_alone_nccl_path_max": float(mx[13]) if p2p_on else None,
             "ms_per_exchange_overlapped_max": float(mx[9]), "ms_per_exchange_alone_max": float(mx[11]),
             "bytes_sent_per_exchange_max": float(mx[10]),
             "achieved_GBs_per_direction": float(mx[10]) / (float(mx[11]) / 1e3) / 1e9 if mx[11] > 0 else None,
             "nvlink_peak_GBs_per_direction": 900.0,
             "nvlink_frac": float(mx[10]) / (float(mx[11]) / 1e3) / 1e9 / 900.0 if mx[11] > 0 else None,
-            "nvlink_frac_note": "bytes sent by the busiest rank / time of the exchange run alone (pack + NCCL + unpack kernels included) / 900 GB/s",
+            "nvlink_frac_note": "bytes sent by the busiest rank / time of the exchange run alone (every kernel of the exchange included) / 900 GB/s",
             "outside_sweeps_ms_per_step_max": float(mx[12]),
             "outside_sweeps_note": "max over ranks of (step - core stress sweep - core velocity sweep) on that rank, not clamped: source, "
                                    "station and join overhead plus any exchange tail the core sweep did not cover; the exposed cost of "

@@ -172,6 +172,16 @@ struct swpc3d_handle {
     int comm_rank = -1, comm_size = 0;
     int comm_timeout_s = 1800;             // option "comm_timeout_s": a host-side wait on a stream that carries NCCL work gives up after this
     bool comm_dead = false;                // the communicator was aborted (peer failure / timeout): every later exchange fails at once
+    // peer-to-peer exchange (one node): a face's planes are stored straight into the neighbour's receive buffer (halo_push / halo_pull)
+    int use_p2p = 1;                       // option "p2p": 0 = pack + ncclSend/ncclRecv + unpack
+    bool p2p_ok = false;
+    char *p2p_base = nullptr;              // my block: receive buffers [family][parity][face], flag words [family][face], block counters
+    size_t p2p_off[2][2][4] = {};
+    size_t p2p_flag_off = 0, p2p_count_off = 0, p2p_bytes = 0;
+    void *p2p_peer[4] = {};                // the neighbours' blocks, opened through CUDA IPC
+    size_t p2p_peer_off[4][2][2] = {};     // [face][family][parity]: where my message lands in the neighbour's block
+    size_t p2p_peer_flag[4][2] = {};       // [face][family]: the neighbour's flag word for messages from me
+    unsigned int p2p_seq[2] = {0, 0};      // exchanges done per family
     // streams
     cudaStream_t st = nullptr;
     cudaStream_t side[5] = {};             // absorber-shell boxes run beside the TMA interior kernel
@@ -435,6 +445,9 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     if (!h) return 0;
     cudaSetDevice(h->dev);
     cudaDeviceSynchronize();
+    for (int f = 0; f < 4; f++)
+        if (h->p2p_peer[f]) cudaIpcCloseMemHandle(h->p2p_peer[f]);
+    cudaFree(h->p2p_base);
     if (h->comm_io && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm_io);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (int q = 0; q < 15; q++) {
@@ -1779,9 +1792,10 @@ static FaceLists face_lists(const swpc3d_handle *h, int which) {
 }
 
 template <typename F>
-static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack, cudaStream_t st_) {
+static int launch_halo(swpc3d_handle *h, const FaceLists &L, bool pack, cudaStream_t st_, bool outer_only = false) {
     const int nz = h->g.nz;
     for (int f = 0; f < 4; f++) {
+        if (outer_only && h->nbr[f] >= 0) continue;
         // A face without a neighbour: the reference still unpacks its (all-zero) receive buffer into the outer halo
         // planes (m_global.f90:458-488).  Those planes are zero anyway unless something else wrote them:
         // the plane-wave initial condition / edge extrapolation, or a source stencil at the model edge.
@@ -1815,6 +1829,132 @@ static bool has_neighbour(const swpc3d_handle *h) {
     return false;
 }
 
+// ---- peer-to-peer form of the exchange.  What the neighbours tell each other once, at swpc3d_comm_init (over NCCL, 200 bytes per
+// face): the CUDA IPC handle of their block and where in it the messages from this rank go.
+struct P2pInfo {
+    cudaIpcMemHandle_t handle;
+    unsigned long long off[2][2];   // [family][parity]: receive buffer for the messages that cross this face
+    unsigned long long flag[2];     // [family]
+    unsigned long long ok;
+};
+static int p2p_setup(swpc3d_handle *h) {
+    h->p2p_ok = false;
+    const bool any = has_neighbour(h);
+    int ok = 1;
+    // my block
+    size_t off = 0;
+    const size_t isz = (size_t)5 * h->nyp * h->g.nz * h->fb, jsz = (size_t)5 * h->nxp * h->g.nz * h->fb;
+    for (int fam = 0; fam < 2; fam++)
+        for (int par = 0; par < 2; par++)
+            for (int f = 0; f < 4; f++) {
+                h->p2p_off[fam][par][f] = off;
+                if (h->nbr[f] >= 0) off += ((f < 2 ? isz : jsz) + 255) / 256 * 256;
+            }
+    h->p2p_flag_off = off; off += 256;
+    h->p2p_count_off = off; off += 256;
+    h->p2p_bytes = off;
+    if (cudaMalloc(&h->p2p_base, off) != cudaSuccess) { cudaGetLastError(); h->p2p_base = nullptr; ok = 0; }
+    if (h->p2p_base) CK(cudaMemset(h->p2p_base, 0, off));
+    P2pInfo mine[4], theirs[4];
+    memset(mine, 0, sizeof(mine));
+    memset(theirs, 0, sizeof(theirs));
+    const int opp[4] = {1, 0, 3, 2};
+    cudaIpcMemHandle_t hd;
+    memset(&hd, 0, sizeof(hd));
+    if (ok && cudaIpcGetMemHandle(&hd, h->p2p_base) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    for (int f = 0; f < 4; f++) {   // what the neighbour across face f needs: my buffers / flags for the messages that arrive through face f
+        mine[f].handle = hd;
+        for (int fam = 0; fam < 2; fam++) {
+            for (int par = 0; par < 2; par++) mine[f].off[fam][par] = h->p2p_off[fam][par][f];
+            mine[f].flag[fam] = h->p2p_flag_off + (size_t)(fam * 4 + f) * sizeof(unsigned int);
+        }
+        mine[f].ok = (unsigned long long)ok;
+    }
+    (void)opp;
+    if (any) {
+        P2pInfo *d = nullptr;
+        CK(cudaMalloc(&d, 8 * sizeof(P2pInfo)));
+        CK(cudaMemcpy(d, mine, sizeof(mine), cudaMemcpyHostToDevice));
+        NK(g_nccl.GroupStart());
+        for (int f = 0; f < 4; f++) {
+            if (h->nbr[f] < 0) continue;
+            NK(g_nccl.Send(d + f, sizeof(P2pInfo), ncclChar, h->nbr[f], h->comm, h->st));
+            NK(g_nccl.Recv(d + 4 + f, sizeof(P2pInfo), ncclChar, h->nbr[f], h->comm, h->st));
+        }
+        NK(g_nccl.GroupEnd());
+        CK(cudaMemcpyAsync(theirs, d + 4, sizeof(theirs), cudaMemcpyDeviceToHost, h->st));
+        CK(cudaStreamSynchronize(h->st));
+        cudaFree(d);
+        for (int f = 0; f < 4 && ok; f++) {
+            if (h->nbr[f] < 0) continue;
+            if (!theirs[f].ok) { ok = 0; break; }
+            // (a neighbour on two faces would be the same process on both: open its block once)
+            void *ptr = nullptr;
+            for (int e = 0; e < f; e++)
+                if (h->nbr[e] == h->nbr[f]) ptr = h->p2p_peer[e];
+            if (!ptr && cudaIpcOpenMemHandle(&ptr, theirs[f].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            h->p2p_peer[f] = ptr;
+            for (int fam = 0; fam < 2; fam++) {
+                for (int par = 0; par < 2; par++) h->p2p_peer_off[f][fam][par] = (size_t)theirs[f].off[fam][par];
+                h->p2p_peer_flag[f][fam] = (size_t)theirs[f].flag[fam];
+            }
+        }
+    }
+    // every rank takes the same path: peer-to-peer only if it works everywhere
+    int *dok = nullptr;
+    CK(cudaMalloc(&dok, sizeof(int)));
+    CK(cudaMemcpy(dok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NK(g_nccl.AllReduce(dok, dok, 1, ncclInt, ncclMin, h->comm, h->st));
+    CK(cudaMemcpyAsync(&ok, dok, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    cudaFree(dok);
+    h->p2p_ok = ok != 0;
+    return 0;
+}
+
+// one exchange, peer to peer: ONE push launch for all faces, a one-warp wait, ONE pull launch
+template <typename F>
+static int p2p_exchange(swpc3d_handle *h, const FaceLists &L, int which, cudaStream_t st_) {
+    const int nz = h->g.nz, fam = which;
+    const unsigned int seq = ++h->p2p_seq[fam];
+    const int par = (int)(seq & 1u);
+    constexpr int VEC = 16 / (int)sizeof(F);
+    P2pFaces push{}, pull{};
+    int z = 0, maxline = 0;
+    const unsigned int *fl[4];
+    for (int f = 0; f < 4; f++) {
+        const bool on = h->nbr[f] >= 0;
+        const int nline = on ? (f < 2 ? h->nyp : h->nxp) : 0;
+        push.pl[f] = L.send[f]; pull.pl[f] = L.recv[f];
+        if (!on) { push.pl[f].n = 0; pull.pl[f].n = 0; }
+        push.nline[f] = pull.nline[f] = nline;
+        z += on ? L.send[f].n : 0;      // (send and receive lists of a face pair up: 4 planes one way, 5 the other -- see below)
+        push.zend[f] = z;
+        maxline = std::max(maxline, nline);
+        push.buf[f] = on ? (void *)((char *)h->p2p_peer[f] + h->p2p_peer_off[f][fam][par]) : nullptr;
+        push.flag[f] = on ? (unsigned int *)((char *)h->p2p_peer[f] + h->p2p_peer_flag[f][fam]) : nullptr;
+        push.count[f] = (unsigned int *)(h->p2p_base + h->p2p_count_off) + (fam * 4 + f);
+        pull.buf[f] = on ? (void *)(h->p2p_base + h->p2p_off[fam][par][f]) : nullptr;
+        fl[f] = on ? (const unsigned int *)(h->p2p_base + h->p2p_flag_off) + (fam * 4 + f) : nullptr;
+        if (on) h->halo_bytes += (double)(face_count(h, L.send[f], f) * (size_t)h->fb);
+    }
+    int zr = 0;
+    for (int f = 0; f < 4; f++) { zr += pull.pl[f].n; pull.zend[f] = zr; }
+    dim3 blk(128, 1, 1);
+    const unsigned gx = (unsigned)((nz + 128 * VEC - 1) / (128 * VEC));
+    halo_p2p<F, true><<<dim3(gx, (unsigned)maxline, (unsigned)z), blk, 0, st_>>>(nz, h->NZP, h->NXM, push, seq);
+    h->launches++;
+    CK(cudaGetLastError());
+    halo_wait<<<1, 32, 0, st_>>>(fl[0], fl[1], fl[2], fl[3], seq);
+    h->launches++;
+    CK(cudaGetLastError());
+    halo_p2p<F, false><<<dim3(gx, (unsigned)maxline, (unsigned)zr), blk, 0, st_>>>(nz, h->NZP, h->NXM, pull, seq);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (h->zero_outer && launch_halo<F>(h, L, false, st_, true)) return 1;   // faces without a neighbour: the reference unpacks its zero receive buffers there
+    return 0;
+}
+
 // pack -> ncclSend/ncclRecv with up to four neighbours -> unpack, all on `st_` (the launch stream, or the exchange
 // stream of the boundary-first overlap); with kernel_timing the exchange is bracketed by an event pair (halo phase)
 static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr) {
@@ -1836,6 +1976,14 @@ static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr
             h->cev[1].push_back(b);
         }
         CK(cudaEventRecord(h->cev[0][h->cev_used], st_));
+    }
+    if (h->p2p_ok && h->use_p2p) {
+        if (h->fb == 8 ? p2p_exchange<double>(h, L, which, st_) : p2p_exchange<float>(h, L, which, st_)) return 1;
+        if (timed) {
+            CK(cudaEventRecord(h->cev[1][h->cev_used], st_));
+            h->cev_used++;
+        }
+        return 0;
     }
     if (h->fb == 8 ? launch_halo<double>(h, L, true, st_) : launch_halo<float>(h, L, true, st_)) return 1;
     const ncclDataType_t ty = h->fb == 8 ? ncclDouble : ncclFloat;
@@ -1880,7 +2028,7 @@ extern "C" int swpc3d_comm_init(swpc3d_handle *h, const char id[128], int32_t nr
     h->comm_size = nranks;
     // snapshot reductions get a communicator of their own: they are issued on another stream, beside the halo exchange
     if (g_nccl.CommSplit && g_nccl.CommSplit(h->comm, 0, rank, &h->comm_io, nullptr) != ncclSuccess) h->comm_io = nullptr;
-    return 0;
+    return p2p_setup(h);
 }
 
 // single-process emulation: all handles on GPUs of this process, ordered by myid
@@ -2006,6 +2154,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "ring_pf")) { if (value < 0 || value > 8) return fail("ring_pf must be 0..8"); h->ring_pf = value; }
     else if (!strcmp(key, "side_streams")) h->use_side = value;
     else if (!strcmp(key, "comm_timeout_s")) h->comm_timeout_s = value;
+    else if (!strcmp(key, "p2p")) h->use_p2p = value != 0;
     else if (!strcmp(key, "pml_tma")) { h->use_pml = value; pml_drop(h); }
     else if (!strcmp(key, "l2promo")) { h->l2promo = value; h->tma_ready = false; }
     else if (!strcmp(key, "l2promo_halo")) { h->l2promo_halo = value; h->tma_ready = false; }
@@ -2028,6 +2177,7 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "naux")) *value = (double)h->naux;
     else if (!strcmp(key, "device")) *value = h->dev;
     else if (!strcmp(key, "tma_ok")) *value = h->tma_ok ? 1.0 : 0.0;
+    else if (!strcmp(key, "p2p_ok")) *value = (h->p2p_ok && h->use_p2p) ? 1.0 : 0.0;
     else if (!strncmp(key, "pml_", 4)) {   // the shell plan of the last whole-region (core-region: "_core" suffix) sweeps
         const int ri = strstr(key, "_core") ? 1 : 0, w = strstr(key, "_vel") ? 1 : 0;
         const PmlPlan *pl = h->pml[ri][w];

@@ -1114,6 +1114,79 @@ __global__ void halo_kernel(int nz, int nline, int NZP, int NXM, const PlaneList
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same exchange without a library in between (one node, NVLink / NVSwitch peer memory): the "pack" kernel of a face stores
+// its planes STRAIGHT into the neighbour's receive buffer -- one hop over NVLink, no send buffer, no copy kernel of a
+// communication library -- and, when its last block is done, publishes the exchange's sequence number in the neighbour's flag
+// word with a system-scope release store.  The neighbour's "unpack" kernel spins on that flag (acquire) before it reads.
+// Messages keep the reference's layout (plane lists of m_global.f90:416-443 ...), so both paths fill the halo identically.
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All faces of a rank in ONE launch (blockIdx.z runs over the (face, plane) pairs), 16 bytes per thread.
+struct P2pFaces {
+    PlaneList pl[4];          // push: the planes sent through face f; pull: the halo planes filled through face f
+    void *buf[4];             // push: the neighbour's receive buffer (peer memory); pull: this rank's receive buffer
+    unsigned int *flag[4];    // push: the neighbour's flag word (peer memory); pull: unused
+    unsigned int *count[4];   // push: block counter of face f (own memory)
+    int nline[4];             // owned j (x faces: f = 0, 1) or owned i (y faces: f = 2, 3) along the face; 0 = no neighbour
+    int zend[4];              // running sum of pl[f].n over the faces with a neighbour
+};
+
+template <typename F, bool PUSH>
+__global__ void halo_p2p(int nz, int NZP, int NXM, const __grid_constant__ P2pFaces q, unsigned int seq) {
+    constexpr int VEC = 16 / (int)sizeof(F);
+    int f = 0;
+    while (f < 3 && (int)blockIdx.z >= q.zend[f]) f++;
+    const int s = (int)blockIdx.z - (f > 0 ? q.zend[f - 1] : 0);
+    const int line = blockIdx.y;
+    const int nline = q.nline[f];
+    if (line >= nline) return;                                 // (uniform per block; such blocks are not counted)
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;   // 0-based
+    const PlaneList &pl = q.pl[f];
+    F *fld = (F *)pl.field[s];
+    long long col;
+    if (f < 2) col = (long long)pl.m[s] + (long long)NXM * (line + HALO);
+    else col = (long long)(line + HALO) + (long long)NXM * pl.m[s];
+    const long long n = (long long)(k + KOFF) + (long long)NZP * col;
+    const long long b = (long long)s * nline * nz + (long long)line * nz + k;
+    F *buf = (F *)q.buf[f];
+    const bool vec = (nz % VEC) == 0;                          // rows of the message stay 16-byte aligned
+    if (k < nz) {
+        if (vec) {
+            if (PUSH) *reinterpret_cast<int4 *>(buf + b) = *reinterpret_cast<const int4 *>(fld + n);
+            else *reinterpret_cast<int4 *>(fld + n) = __ldcg(reinterpret_cast<const int4 *>(buf + b));
+        } else {
+            for (int e = 0; e < VEC && k + e < nz; e++) {
+                if (PUSH) buf[b + e] = fld[n + e];
+                else fld[n + e] = __ldcg(buf + b + e);
+            }
+        }
+    }
+    if (!PUSH) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();                                  // this block's stores before the ticket
+        const unsigned int total = gridDim.x * (unsigned int)nline * (unsigned int)pl.n;
+        if (atomicAdd(q.count[f], 1u) == total - 1) {             // the last block of this face
+            *q.count[f] = 0;
+            __threadfence_system();
+            st_release_sys(q.flag[f], seq);
+        }
+    }
+}
+
+// one warp waits for the flags of up to four faces, so that the pull kernel behind it in the stream need not spin in every block
+static __global__ void halo_wait(const unsigned int *f0, const unsigned int *f1, const unsigned int *f2, const unsigned int *f3, unsigned int seq) {
+    const unsigned int *f = threadIdx.x == 0 ? f0 : threadIdx.x == 1 ? f1 : threadIdx.x == 2 ? f2 : threadIdx.x == 3 ? f3 : nullptr;
+    if (f)
+        while ((int)(ld_acquire_sys(f) - seq) < 0) __nanosleep(200);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Plane-wave mode: horizontal zero-derivative boundary (m_absorb_p.f90:137-243 / :332-424).  Linear extrapolation into
 // the first plane outside the model on the outer ranks, owned rows and k = 1..nz only.  blockIdx.z = edge
 // (0: i=0, 1: i=nx+1, 2: j=0, 3: j=ny+1); `dst/s1/s2[e]` are memory-box indices along the edge's normal, < 0 = edge off.

@@ -21,6 +21,7 @@ from oracle_lib import Oracle  # noqa: E402
 def main():
     work = Path(sys.argv[1])
     npx, npy, nt = int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    p2p = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     rank, world, local = init_process_group("nccl")
     d = work / f"r{rank}"
     inf = write_case(d, nt=nt, nproc_x=npx, nproc_y=npy, nx=56, ny=48, ntdec_r=5,
@@ -29,6 +30,8 @@ def main():
     allreduce_minmax(run)
     run.attach_device(local)
     attach_nccl(run)
+    run.set_option("p2p", p2p)                     # 1: halo planes pushed straight into the neighbour's buffer over NVLink; 0: NCCL send/recv
+    p2p_on = run.info("p2p_ok")
     run.snap_open(work / "snap")                   # every rank takes part; the I/O ranks of m_snap.f90:163-191 write
     vm = run.run(1, nt)
     run.snap_close()
@@ -52,7 +55,7 @@ def main():
     for q in range(rank, 15, world):                # snapshot files, shared directory, checks spread over the ranks
         sec, typ = divmod(q, 3)
         check_file(work / "snap" / f"mg.3d.{OL.SNAP_SECTIONS[sec]}.{OL.SNAP_TYPES[typ]}.nc", o, q, "mg", run["dt"], 4)
-    print(f"rank {rank}/{world} ok: nst={run['nst']} nsrc={run['nsrc']}", flush=True)
+    print(f"rank {rank}/{world} ok: nst={run['nst']} nsrc={run['nsrc']} p2p={int(p2p_on)}", flush=True)
 
 
 if __name__ == "__main__":

@@ -16,17 +16,20 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("p2p", [1, 0])
 @pytest.mark.parametrize("layout", [(2, 1), (1, 2), (2, 2)])
-def test_nccl_halo_exchange_matches_oracle(tmp_path, layout):
+def test_nccl_halo_exchange_matches_oracle(tmp_path, layout, p2p):
+    """p2p = 1: the peer-to-peer exchange (halo_push / halo_wait / halo_pull over CUDA IPC memory); 0: pack + ncclSend/Recv + unpack"""
     n = layout[0] * layout[1]
     if _ngpu() < n:
         pytest.skip(f"needs {n} GPUs")
     port = 29600 + os.getpid() % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(ROOT / "tests" / "mgpu_worker.py"), str(tmp_path), str(layout[0]), str(layout[1]), "30"]
+           "--master-port", str(port), str(ROOT / "tests" / "mgpu_worker.py"), str(tmp_path), str(layout[0]), str(layout[1]), "30", str(p2p)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count(" ok:") == n
+    assert p.stdout.count(f" p2p={p2p}") == n, p.stdout[-2000:]          # the path that was asked for is the one that ran
 
 
 @pytest.mark.parametrize("n", [2, 3])
