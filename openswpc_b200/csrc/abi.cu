@@ -114,7 +114,7 @@ struct swpc3d_handle {
     int *kbeg_a = nullptr, *kob = nullptr, *kfs = nullptr;
     std::vector<int> h_kbeg_a;
     std::vector<long long> h_aoff;         // host copy of aoff (per owned column)
-    struct PmlPlan *pml[2][2] = {};        // [whole | core region][stress | velocity]: TMA-staged absorber shell (pml_tma.cuh)
+    std::vector<struct PmlPlan *> pml[2];  // [stress | velocity]: TMA-staged absorber shell (pml_tma.cuh), one plan per region swept (whole box, core, boundary slabs)
     struct TmaPlan *tplan[2] = {};         // [whole | core region]: work lists of the persistent interior stress kernel (stress_tma_p)
     int tma_persist = 0;                   // option "tma_persist": 1 = stress_tma_p (persistent blocks, ticket counter) instead of one block per 16-plane chunk; measured slower
     int tma_pl = 64;                       // option "tma_pl": planes per work item of the persistent kernel
@@ -203,8 +203,11 @@ struct swpc3d_handle {
     // boundary-first overlap of the halo exchange (swpc3d_step): the two outermost owned planes towards every neighbour are
     // swept first, then pack / NCCL / unpack run on `cs` while the core of the subdomain is swept on `st`
     cudaStream_t cs = nullptr;
+    cudaStream_t cur = nullptr;   // set while the boundary slabs are launched: the sweeps' kernels go to this stream, no side streams
     cudaEvent_t ev_b = nullptr, ev_c = nullptr;
     int overlap = 1;       // 0: the reference's fully exposed order
+    int slab_x = 8;        // option "slab_x": columns of the x boundary slabs (>= 2; 8 = one tile column of stress_tma)
+    int slab_tiled = 1;    // option "slab_tiled": 0 = the slabs with sweep_direct
     int split_test = 0;    // testing aid: split the sweeps as if all four faces had neighbours, without any exchange
     int pw_mode = 0;   // plane-wave mode: edge extrapolation ahead of the PML sweeps
     int zero_outer = 0;   // re-zero the outer halo planes at every exchange (see launch_halo)
@@ -264,6 +267,8 @@ static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
 static void pml_drop(swpc3d_handle *h);
 static void tplan_drop(swpc3d_handle *h);
 
+static inline cudaStream_t main_stream(const swpc3d_handle *h) { return h->cur ? h->cur : h->st; }
+static inline bool side_streams(const swpc3d_handle *h) { return h->use_side && !h->cur; }
 static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
 
 template <typename F>
@@ -725,7 +730,7 @@ extern "C" int swpc3d_set_stations(swpc3d_handle *h, int32_t nst, const int32_t 
 // sweeps
 template <typename F, bool STRESS>
 static int launch_direct_box(swpc3d_handle *h, const KParams<F> &p, const Box3 &b, cudaStream_t st = nullptr) {
-    if (!st) st = h->st;
+    if (!st) st = main_stream(h);
     if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) return 0;
     dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
     const int jlen = std::max(1, h->jlen);
@@ -808,12 +813,19 @@ static int tma_prepare(swpc3d_handle *h) {
 struct Region { int li0, li1, lj0, lj1; };
 static Region whole_region(const swpc3d_handle *h) { return Region{0, h->nxp - 1, 0, h->nyp - 1}; }
 static bool face_split(const swpc3d_handle *h, int f) { return h->split_test || h->nbr[f] >= 0; }
+// Width of the boundary slab towards face f.  The exchange carries the two outermost planes; the x slabs are made one tile
+// column (8 columns) wide, so that the slab and what is left for the core are both swept by the tiled kernels at full
+// efficiency (a 2-column slab is 0.4 % of the cells but cost 1 ms per step with sweep_direct next to the core sweep).
+static int slab_width(const swpc3d_handle *h, int f) {
+    if (f >= 2) return 2;
+    return (h->slab_x >= 2 && h->nxp >= 4 * h->slab_x) ? h->slab_x : 2;
+}
 static Region core_region(const swpc3d_handle *h) {   // faces: 0 +x, 1 -x, 2 +y, 3 -y; planes sent: 2 per face (m_global.f90:416-443, 527-553)
     Region r = whole_region(h);
-    if (face_split(h, 1)) r.li0 += 2;
-    if (face_split(h, 0)) r.li1 -= 2;
-    if (face_split(h, 3)) r.lj0 += 2;
-    if (face_split(h, 2)) r.lj1 -= 2;
+    if (face_split(h, 1)) r.li0 += slab_width(h, 1);
+    if (face_split(h, 0)) r.li1 -= slab_width(h, 0);
+    if (face_split(h, 3)) r.lj0 += slab_width(h, 3);
+    if (face_split(h, 2)) r.lj1 -= slab_width(h, 2);
     return r;
 }
 // the boundary slabs: x slabs over every owned j, y slabs over the core's i range only (each cell exactly once)
@@ -838,10 +850,10 @@ static Box3 tma_box(const swpc3d_handle *h, const Region &rg) {
     const int nkt = (g.kend_k + C::TK - 1) / C::TK;                     // interior k is 1..kend_k; the last tile may be partial
     const int li0 = std::max(g.ibeg_k - g.ibeg, rg.li0), li1 = std::min(g.iend_k - g.ibeg, rg.li1);
     const int lj0 = std::max(g.jbeg_k - g.jbeg, rg.lj0), lj1 = std::min(g.jend_k - g.jbeg, rg.lj1);
-    const int nit = (li1 - li0 + 1) / C::TI;
-    if (nkt < 1 || nit < 1 || lj1 < lj0) return b;
-    // (the last tile may reach past the padded column: TMA zero-fills out-of-bounds elements, and those lanes are masked)
-    b.k0 = 1; b.k1 = nkt * C::TK; b.li0 = li0; b.li1 = li0 + nit * C::TI - 1; b.lj0 = lj0; b.lj1 = lj1;
+    if (nkt < 1 || li1 < li0 || lj1 < lj0) return b;
+    // (the last k-tile may reach past the padded column and the last i-tile past the box: TMA zero-fills what is out of bounds,
+    // and those lanes are masked)
+    b.k0 = 1; b.k1 = nkt * C::TK; b.li0 = li0; b.li1 = li1; b.lj0 = lj0; b.lj1 = lj1;
     return b;
 }
 
@@ -871,20 +883,17 @@ struct PmlPlan {
     int jl = 0, jlb = 0;
 };
 static void pml_drop(swpc3d_handle *h) {
-    bool any = false;
-    for (auto &per_region : h->pml)
-        for (PmlPlan *&pl : per_region) any = any || pl;
-    if (!any) return;
+    if (h->pml[0].empty() && h->pml[1].empty()) return;
     cudaSetDevice(h->dev);
     cudaDeviceSynchronize();
-    for (auto &per_region : h->pml)
-        for (PmlPlan *&pl : per_region) {
-            if (!pl) continue;
+    for (auto &list : h->pml) {
+        for (PmlPlan *pl : list) {
             for (int c = 0; c < PML_NCLS; c++) cudaFree(pl->d_items[c]);
             cudaFree(pl->d_ticket);
             delete pl;
-            pl = nullptr;
         }
+        list.clear();
+    }
 }
 
 static bool make_map_generic(CUtensorMap *m, void *base, int elem, const cuuint64_t dims[4], const cuuint64_t strides_bytes[3], const cuuint32_t box[4],
@@ -1028,35 +1037,38 @@ static void pml_launch_class(const KParams<F> &p, PmlPlan *pl, const PmlGeom &gm
 // the absorber shell of region rg: pml_tma work lists + the boxes left to sweep_direct, all beside the interior kernel
 template <typename F, bool STRESS>
 static int launch_shell(swpc3d_handle *h, const KParams<F> &p, const Region &rg, const Box3 &cols) {
-    const Region w = whole_region(h);
-    const int ri = (rg.li0 == w.li0 && rg.li1 == w.li1 && rg.lj0 == w.lj0 && rg.lj1 == w.lj1) ? 0 : 1;
-    PmlPlan *&pl = h->pml[ri][STRESS ? 0 : 1];
     auto same = [](const Box3 &a, const Box3 &b) { return a.li0 == b.li0 && a.li1 == b.li1 && a.lj0 == b.lj0 && a.lj1 == b.lj1; };
-    if (pl && !(pl->rg.li0 == rg.li0 && pl->rg.li1 == rg.li1 && pl->rg.lj0 == rg.lj0 && pl->rg.lj1 == rg.lj1 && same(pl->cols, cols) &&
-                pl->jl == h->pml_jl && pl->jlb == h->pml_jl_bottom)) {
-        CK(cudaDeviceSynchronize());
-        for (int c = 0; c < PML_NCLS; c++) cudaFree(pl->d_items[c]);
-        cudaFree(pl->d_ticket);
-        delete pl;
-        pl = nullptr;
+    std::vector<PmlPlan *> &list = h->pml[STRESS ? 0 : 1];
+    PmlPlan *pl = nullptr;
+    for (size_t q = 0; q < list.size(); q++) {
+        PmlPlan *c = list[q];
+        if (!(c->rg.li0 == rg.li0 && c->rg.li1 == rg.li1 && c->rg.lj0 == rg.lj0 && c->rg.lj1 == rg.lj1)) continue;
+        if (same(c->cols, cols) && c->jl == h->pml_jl && c->jlb == h->pml_jl_bottom) { pl = c; break; }
+        CK(cudaDeviceSynchronize());   // the same region with other tiling options: rebuild
+        for (int k = 0; k < PML_NCLS; k++) cudaFree(c->d_items[k]);
+        cudaFree(c->d_ticket);
+        delete c;
+        list.erase(list.begin() + (long)q);
+        break;
     }
     if (!pl) {
         pl = new PmlPlan();
-        if (pml_build<F, STRESS>(h, rg, cols, pl)) return 1;
+        if (pml_build<F, STRESS>(h, rg, cols, pl)) { delete pl; return 1; }
+        list.push_back(pl);
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev);
     int qs = 0;   // side stream round robin
     auto fork = [&](cudaStream_t &st) -> int {
-        st = h->st;
-        if (h->use_side) {
+        st = main_stream(h);
+        if (side_streams(h)) {
             st = h->side[qs % 5];
             if (qs < 5) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
         }
         return 0;
     };
     auto join = [&](cudaStream_t st) -> int {
-        if (h->use_side) {
+        if (side_streams(h)) {
             CK(cudaEventRecord(h->ev_join[qs % 5], st));
             CK(cudaStreamWaitEvent(h->st, h->ev_join[qs % 5], 0));
             qs++;
@@ -1112,7 +1124,7 @@ static int tplan_build(swpc3d_handle *h, const Box3 &t, int TK, int TI, int bloc
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev);
     nsm *= std::max(1, blocks_per_sm);
-    const int nkt = (t.k1 - t.k0 + 1) / TK, nit = (t.li1 - t.li0 + 1) / TI, P = t.lj1 - t.lj0 + 1;
+    const int nkt = (t.k1 - t.k0 + 1) / TK, nit = (t.li1 - t.li0 + TI) / TI, P = t.lj1 - t.lj0 + 1;
     const int k1_k = h->g.kend_k;
     const int nch = std::max(1, (P + h->tma_pl / 2) / std::max(1, h->tma_pl));
     std::vector<TmaItem> items;
@@ -1147,14 +1159,14 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
     const Box3 all{1, h->g.nz, rg.li0, rg.li1, rg.lj0, rg.lj1, 0};
     if (t.k1 < t.k0) return launch_direct_box<F, true>(h, p, all);
     TmaGeom g{};
-    g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
+    g.li0 = t.li0; g.li1 = t.li1; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
     g.shift_last = h->tma_shift;
-    dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + 1) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
+    dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + C::TI) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
     // complement of the TMA box inside the owned box: the absorber shell (four slabs of wall columns, the bottom rows under the
     // interior columns) and, if the interior box is not a whole number of tiles wide, the ragged interior columns.  All launches
     // touch disjoint cells and only read V, so they are issued on side streams next to the interior kernel.
-    if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
-    if (h->tma_persist) {
+    if (side_streams(h)) CK(cudaEventRecord(h->ev_fork, h->st));
+    if (h->tma_persist && !h->cur) {
         const Region w = whole_region(h);
         const int ri = (rg.li0 == w.li0 && rg.li1 == w.li1 && rg.lj0 == w.lj0 && rg.lj1 == w.lj1) ? 0 : 1;
         TmaPlan *&tp = h->tplan[ri];
@@ -1171,10 +1183,10 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, stress_tma_p<F, NM>, C::THREADS, C::SMEM) != cudaSuccess) { cudaGetLastError(); bps = 1; }
             if (tplan_build(h, t, C::TK, C::TI, bps, tp)) return 1;
         }
-        stress_tma_p<F, NM><<<tp->grid, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, tp->d_items, tp->nitems, tp->d_ticket, tp->base, g);
+        stress_tma_p<F, NM><<<tp->grid, C::THREADS, C::SMEM, main_stream(h)>>>(p, h->tmaps, tp->d_items, tp->nitems, tp->d_ticket, tp->base, g);
         tp->base += (unsigned int)(tp->nitems + tp->grid);
     } else {
-        stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, h->st>>>(p, h->tmaps, g);
+        stress_tma<F, NM><<<grd, C::THREADS, C::SMEM, main_stream(h)>>>(p, h->tmaps, g);
     }
     h->launches++;
     CK(cudaGetLastError());
@@ -1198,36 +1210,36 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         const int jlen = std::max(1, h->ring_jlen);
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
         dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
-        if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
+        if (side_streams(h)) CK(cudaEventRecord(h->ev_fork, h->st));
         bool pair = false;
         if constexpr (sizeof(F) == 4) {   // float32 fields: two cells per thread, 64-bit loads
             if (h->ring_pair) {
                 pair = true;
                 grd.x = (unsigned)((in.k1 + 2 * h->tk - 1) / (2 * h->tk));
-                vel_ring2<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
+                vel_ring2<F><<<grd, blk, 0, main_stream(h)>>>(p, in, jlen, h->ring_pf);
             }
         }
-        if (!pair) vel_ring<F><<<grd, blk, 0, h->st>>>(p, in, jlen, h->ring_pf);
+        if (!pair) vel_ring<F><<<grd, blk, 0, main_stream(h)>>>(p, in, jlen, h->ring_pf);
         h->launches++;
         CK(cudaGetLastError());
         return launch_shell<F, false>(h, p, rg, in);
     }
     if (t.k1 < t.k0 || !h->vtma_ok || h->use_tma < 2) return launch_direct_box<F, false>(h, p, all);
     TmaGeom g{};
-    g.li0 = t.li0; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl);
-    dim3 grd((unsigned)((t.k1 - t.k0 + 1) / CV::TK), (unsigned)((t.li1 - t.li0 + 1) / CV::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
+    g.li0 = t.li0; g.li1 = t.li1; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl);
+    dim3 grd((unsigned)((t.k1 - t.k0 + 1) / CV::TK), (unsigned)((t.li1 - t.li0 + CV::TI) / CV::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
     const int kE = (h->g.kend_k / C::TK) * C::TK + 1;
     const Box3 boxes[5] = {Box3{1, h->g.nz, rg.li0, rg.li1, rg.lj0, t.lj0 - 1, 0}, Box3{1, h->g.nz, rg.li0, rg.li1, t.lj1 + 1, rg.lj1, 0},
                            Box3{1, h->g.nz, rg.li0, t.li0 - 1, t.lj0, t.lj1, 0}, Box3{1, h->g.nz, t.li1 + 1, rg.li1, t.lj0, t.lj1, 0},
                            Box3{kE, h->g.nz, t.li0, t.li1, t.lj0, t.lj1, 1}};
-    if (h->use_side) CK(cudaEventRecord(h->ev_fork, h->st));
-    vel_tma<F><<<grd, CV::THREADS, CV::SMEM, h->st>>>(p, h->vmaps, g);
+    if (side_streams(h)) CK(cudaEventRecord(h->ev_fork, h->st));
+    vel_tma<F><<<grd, CV::THREADS, CV::SMEM, main_stream(h)>>>(p, h->vmaps, g);
     h->launches++;
     CK(cudaGetLastError());
     for (int q = 0; q < 5; q++) {
         const Box3 &b = boxes[q];
         if (b.k1 < b.k0 || b.li1 < b.li0 || b.lj1 < b.lj0) continue;
-        if (h->use_side) {
+        if (side_streams(h)) {
             CK(cudaStreamWaitEvent(h->side[q], h->ev_fork, 0));
             if (launch_direct_box<F, false>(h, p, b, h->side[q])) return 1;
             CK(cudaEventRecord(h->ev_join[q], h->side[q]));
@@ -1245,11 +1257,35 @@ static int launch_sweep(swpc3d_handle *h, int part = 0) {
     if (h->tk * h->ti > 256) return fail("tk*ti must be <= 256 (launch bounds)");
     const int w = STRESS ? 0 : 1;
     const bool timed = h->ktiming && h->kev_used[w] < 4096;
-    if (part == 1) {   // x slabs are 2 columns wide: a (128 k) x (2 i) block keeps every lane busy
+    if (part == 1) {
         Box3 bb[4];
         const int nb = boundary_boxes(h, bb);
-        const int tk0 = h->tk, ti0 = h->ti;
         int rc = 0;
+        if (h->slab_tiled) {   // every slab is a region of its own for the tiled kernels, on the exchange stream, one after the other
+            h->cur = h->cs;
+            for (int q = 0; q < nb && !rc; q++) {
+                const Region r{bb[q].li0, bb[q].li1, bb[q].lj0, bb[q].lj1};
+                if (STRESS) {
+                    switch (h->nm) {
+                    case 0: rc = launch_stress_nm<F, 0>(h, p, r); break;
+                    case 1: rc = launch_stress_nm<F, 1>(h, p, r); break;
+                    case 2: rc = launch_stress_nm<F, 2>(h, p, r); break;
+                    default: rc = launch_stress_nm<F, 3>(h, p, r); break;
+                    }
+                } else {
+                    switch (h->nm) {
+                    case 0: rc = launch_vel_nm<F, 0>(h, p, r); break;
+                    case 1: rc = launch_vel_nm<F, 1>(h, p, r); break;
+                    case 2: rc = launch_vel_nm<F, 2>(h, p, r); break;
+                    default: rc = launch_vel_nm<F, 3>(h, p, r); break;
+                    }
+                }
+            }
+            h->cur = nullptr;
+            return rc;
+        }
+        // sweep_direct: x slabs 2 columns wide get a (128 k) x (2 i) block so that every lane is busy
+        const int tk0 = h->tk, ti0 = h->ti;
         for (int q = 0; q < nb && !rc; q++) {
             if (bb[q].li1 - bb[q].li0 + 1 <= 2) { h->tk = 128; h->ti = 2; }
             rc = launch_direct_box<F, STRESS>(h, p, bb[q], h->cs);
@@ -2150,6 +2186,8 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "ring_pair")) h->ring_pair = value != 0;
     else if (!strcmp(key, "overlap")) h->overlap = value != 0;
     else if (!strcmp(key, "split_test")) h->split_test = value != 0;
+    else if (!strcmp(key, "slab_x")) { if (value < 2) return fail("slab_x must be >= 2"); h->slab_x = value; }
+    else if (!strcmp(key, "slab_tiled")) h->slab_tiled = value != 0;
     else if (!strcmp(key, "ring_jlen")) { if (value < 1) return fail("ring_jlen must be >= 1"); h->ring_jlen = value; }
     else if (!strcmp(key, "ring_pf")) { if (value < 0 || value > 8) return fail("ring_pf must be 0..8"); h->ring_pf = value; }
     else if (!strcmp(key, "side_streams")) h->use_side = value;
@@ -2179,8 +2217,14 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "tma_ok")) *value = h->tma_ok ? 1.0 : 0.0;
     else if (!strcmp(key, "p2p_ok")) *value = (h->p2p_ok && h->use_p2p) ? 1.0 : 0.0;
     else if (!strncmp(key, "pml_", 4)) {   // the shell plan of the last whole-region (core-region: "_core" suffix) sweeps
-        const int ri = strstr(key, "_core") ? 1 : 0, w = strstr(key, "_vel") ? 1 : 0;
-        const PmlPlan *pl = h->pml[ri][w];
+        const int w = strstr(key, "_vel") ? 1 : 0;
+        const bool core = strstr(key, "_core") != nullptr;
+        const Region wr = whole_region(h);
+        const PmlPlan *pl = nullptr;
+        for (const PmlPlan *c : h->pml[w]) {
+            const bool whole = c->rg.li0 == wr.li0 && c->rg.li1 == wr.li1 && c->rg.lj0 == wr.lj0 && c->rg.lj1 == wr.lj1;
+            if (whole != core) { pl = c; break; }
+        }
         if (!strncmp(key, "pml_items_walls", 15)) *value = pl ? pl->n_items[0] + pl->n_items[2] : 0;
         else if (!strncmp(key, "pml_items_bottom", 16)) *value = pl ? pl->n_items[1] : 0;
         else if (!strncmp(key, "pml_direct_boxes", 16)) *value = pl ? (double)pl->direct.size() : 0;

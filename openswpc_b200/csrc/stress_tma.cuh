@@ -64,6 +64,7 @@ struct TmaMaps {
 };
 struct TmaGeom {
     int li0, lj0, lj1;   // first interior column handled (local i), j range (local, inclusive)
+    int li1;             // last interior column handled: the last tile column may be partial (its idle columns are loaded and masked)
     int jl;              // planes per block
     int m_first;         // index of lam in the medium tensor's 4th dimension (lam, taup, taus are consecutive)
     int mu_index;        // index of mu in the medium tensor's 4th dimension
@@ -209,8 +210,9 @@ stress_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMaps
     const bool shear = warp >= C::NHW;
     const int wq = shear ? warp - C::NHW : warp;
     const int tk = (wq % (C::TK / 32)) * 32 + lane, ti = wq / (C::TK / 32);
-    const bool active = (k0 + tk) <= p.k1_k && (k0 + tk) >= k0t;   // last k-tile: absorber rows / rows of the tile above idle
     const int k = k0 + tk, li = li0 + ti, mi = li + HALO;
+    // last k-tile: absorber rows / rows of the tile above idle; last i-tile: columns past the box idle
+    const bool active = (k0 + tk) <= p.k1_k && (k0 + tk) >= k0t && li <= g.li1;
     AccTma<F, NM> a(p);
     const int voff = (ti + 2) * C::VK + (tk + C::VHK);
     const int muoff = ti * C::MUK + tk;
@@ -341,7 +343,7 @@ stress_tma_p(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMa
             k = I.k0 + tk;
             mi = I.li0 + ti + HALO;
             mj = I.lj0 + HALO;
-            active = k <= p.k1_k && k >= I.kown;
+            active = k <= p.k1_k && k >= I.kown && I.li0 + ti <= g.li1;
             col = (long long)mi + (long long)p.NXM * mj;
             a.n = (long long)(k + KOFF - 1) + (long long)p.NZP * col;
         }
@@ -465,8 +467,8 @@ vel_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ TmaMapsVel
     }
 
     const int tk = (warp % (C::TK / 32)) * 32 + lane, ti = warp / (C::TK / 32);
-    const bool active = (k0 + tk) <= p.k1_k;
     const int k = k0 + tk, li = li0 + ti, mi = li + HALO;
+    const bool active = (k0 + tk) <= p.k1_k && li <= g.li1;
     AccVelTma<F> a(p);
     const int soff = (ti + 2) * C::SK + (tk + C::HK);
     const int roff = ti * C::RK + tk;

@@ -171,8 +171,9 @@ def test_tma_staged_absorber_shell_bit_exact(tmp_path, case):
     assert np.abs(o.field(0, "Vz")[3:3 + r["nyp"], 3:3 + case["na"] + 1, 3:-3]).max() > 0 or nranks != (1, 1)
 
 
+@pytest.mark.parametrize("opts", [{}, {"slab_tiled": 0}, {"slab_x": 2}, {"slab_x": 5}])
 @pytest.mark.parametrize("abc,bf", [("pml", False), ("cerjan", False), ("pml", True)])
-def test_boundary_first_split_bit_exact(tmp_path, abc, bf):
+def test_boundary_first_split_bit_exact(tmp_path, abc, bf, opts):
     # swpc3d_step's boundary-first schedule (boundary slabs -> exchange stream | core sweep -> join) with the sweeps and
     # the source terms split as if all four faces had neighbours; sources sit on / next to the slab-core seam
     if bf:
@@ -184,6 +185,8 @@ def test_boundary_first_split_bit_exact(tmp_path, abc, bf):
     o = Oracle(inf, base_dir=tmp_path, nm=3)
     d = device_from_oracle(o, 0, device=0)
     d.set_option("split_test", 1)
+    for key, val in opts.items():   # x slabs one tile column wide swept by the tiled kernels (default), 2 / 5 columns, or sweep_direct
+        d.set_option(key, val)
     o.run(1, 24)
     d.run(1, 24)
     d.sync()
