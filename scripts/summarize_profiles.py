@@ -53,6 +53,45 @@ def launch_list(src: Path, dst: Path, header: str, key: str):
     print(json.dumps(res, indent=1))
 
 
+def launch_list_r02(src: Path, dst: Path, header: str, key: str):
+    """round 2: the fused stress sweep = stress_tma + pml_tma<., 1, ..>, the velocity sweep = vel_ring / vel_ring2 + pml_tma<., 0, ..>"""
+    rows = [r for r in csv.reader(open(src)) if len(r) > 5]
+    hdr = rows[0]
+    ik, im, iv, iid, iu = (hdr.index(x) for x in ("Kernel Name", "Metric Name", "Metric Value", "ID", "Metric Unit"))
+    L = collections.OrderedDict()
+    for r in rows[1:]:
+        d = L.setdefault(r[iid], {"k": r[ik]})
+        d[r[im]] = (float(r[iv].replace(",", "")), r[iu])
+    out = []
+    for i, d in L.items():
+        t, rd, wr = d["gpu__time_duration.sum"], d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
+        out.append((int(i), d["k"].split("(")[0].replace("void ", ""), t[0] * TF[t[1]], rd[0] * F[rd[1]], wr[0] * F[wr[1]]))
+    with open(dst, "w") as fo:
+        fo.write(header)
+        fo.write("id,kernel,ms,dram_read_GB,dram_write_GB\n")
+        for o in out:
+            fo.write(f"{o[0]},{o[1]},{o[2]:.4f},{o[3] / 1e9:.3f},{o[4] / 1e9:.3f}\n")
+    tma = [n for n, o in enumerate(out) if o[1].startswith("stress_tma")]
+    step = out[tma[-2]:tma[-1]] if len(tma) >= 2 else out
+    tot = sum(o[2] for o in step)
+    share = collections.OrderedDict()
+    for o in step:
+        share[o[1]] = share.get(o[1], 0.0) + o[2]
+    is_stress = lambda n: n.startswith("stress_tma") or (n.startswith("pml_tma") and ", 1, " in n) or ("sweep_direct" in n and ", 1>" in n)
+    is_vel = lambda n: n.startswith("vel_ring") or n.startswith("vel_tma") or (n.startswith("pml_tma") and ", 0, " in n) or ("sweep_direct" in n and ", 0>" in n)
+    stress = [o for o in step if is_stress(o[1])]
+    vel = [o for o in step if is_vel(o[1])]
+    res = {"stress_dram_bytes_per_launch": sum(o[3] + o[4] for o in stress), "vel_dram_bytes_per_launch": sum(o[3] + o[4] for o in vel),
+           "stress_ms_under_ncu": sum(o[2] for o in stress), "vel_ms_under_ncu": sum(o[2] for o in vel),
+           "step_share": {k: round(v / tot, 4) for k, v in share.items()}, "source": str(dst.relative_to(ROOT)),
+           "note": "the fused stress sweep = stress_tma (interior tiles) + pml_tma<F,1,..> launches (absorber shell); serialised under ncu"}
+    tj = OUT / "traffic.json"
+    cur = json.loads(tj.read_text()) if tj.exists() else {}
+    cur[key] = res
+    tj.write_text(json.dumps(cur, indent=1))
+    print(key, json.dumps(res, indent=1))
+
+
 def full_summary(rep: Path, dst: Path, header: str):
     raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
