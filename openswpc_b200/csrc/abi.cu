@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "stress_tma.cuh"
 #include "pml_tma.cuh"
+#include "bottom_tma.cuh"
 #include "snap.cuh"
 
 #include <cuda_runtime.h>
@@ -16,6 +17,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <thread>
 #include <string>
 #include <vector>
@@ -118,6 +120,10 @@ struct swpc3d_handle {
     struct TmaPlan *tplan[2] = {};         // [whole | core region]: work lists of the persistent interior stress kernel (stress_tma_p)
     int tma_persist = 0;                   // option "tma_persist": 1 = stress_tma_p (persistent blocks, ticket counter) instead of one block per 16-plane chunk; measured slower
     int tma_pl = 64;                       // option "tma_pl": planes per work item of the persistent kernel
+    std::vector<struct BotPlan *> bot[2];  // [stress | velocity]: whole-line bottom tiles (bottom_tma.cuh), one plan per region swept
+    // options "bottom_tma" / "bot_jl".  Off by default: built, bit-exact, and measured at 1024 x 1024 x 512 -- stress sweep 25.71 -> 25.60 ms,
+    // velocity sweep 10.62 -> 11.49 ms (the tile's 256 active cells per plane cannot hide the latency of a plane)
+    int use_bot = 0, bot_jl = 82;
     int use_pml = 1;                       // option "pml_tma": 0 = the whole shell with sweep_direct
     int pml_jl = 32, pml_jl_bottom = 41;   // planes per work item (targets; evened out over the region)
     int l2promo = 2, l2promo_halo = 2;     // options "l2promo" / "l2promo_halo": L2 promotion of stress_tma's centre / halo boxes (0 none, 1 64 B, 2 128 B, 3 256 B)
@@ -266,6 +272,7 @@ static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
 
 static void pml_drop(swpc3d_handle *h);
 static void tplan_drop(swpc3d_handle *h);
+static void bot_drop(swpc3d_handle *h);
 
 static inline cudaStream_t main_stream(const swpc3d_handle *h) { return h->cur ? h->cur : h->st; }
 static inline bool side_streams(const swpc3d_handle *h) { return h->use_side && !h->cur; }
@@ -469,6 +476,7 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaFree(h->Mall);
     pml_drop(h);
     tplan_drop(h);
+    bot_drop(h);
     cudaFree(h->band); cudaFree(h->kbeg_a); cudaFree(h->kob); cudaFree(h->kfs); cudaFree(h->snap_tmp);
     for (int q = 0; q < 15; q++) { cudaFree(h->snap_buf[q]); cudaFree(h->snap_max[q]); } cudaFree(h->aoff); cudaFree(h->aux);
     for (int a = 0; a < 6; a++) { cudaFree(h->g4[a]); cudaFree(h->cg[a]); }
@@ -620,6 +628,7 @@ extern "C" int swpc3d_setup_pml(swpc3d_handle *h, const float *gxc, const float 
     h->naux = off;
     h->h_aoff = aoff;
     pml_drop(h);
+    bot_drop(h);
     if (h->aoff) cudaFree(h->aoff);
     if (h->aux) cudaFree(h->aux);
     h->aoff = nullptr; h->aux = nullptr;
@@ -881,6 +890,7 @@ struct PmlPlan {
     PmlMaps maps[PML_NCLS]{};
     std::vector<Box3> direct;
     int jl = 0, jlb = 0;
+    bool skip_bottom = false;
 };
 static void pml_drop(swpc3d_handle *h) {
     if (h->pml[0].empty() && h->pml[1].empty()) return;
@@ -923,10 +933,10 @@ template <typename F, bool STRESS, int CLS>
 static int pml_ns() { return PmlCfg<F, STRESS, PmlClass<CLS>::TI, PmlClass<CLS>::BK>::NS; }
 
 template <typename F, bool STRESS>
-static int pml_build(swpc3d_handle *h, const Region &rg, const Box3 &cols, PmlPlan *pl) {
+static int pml_build(swpc3d_handle *h, const Region &rg, const Box3 &cols, bool skip_bottom, PmlPlan *pl) {
     const swpc3d_grid &g = h->g;
     const int nz = g.nz, nxp = h->nxp;
-    pl->rg = rg; pl->cols = cols; pl->jl = h->pml_jl; pl->jlb = h->pml_jl_bottom;
+    pl->rg = rg; pl->cols = cols; pl->jl = h->pml_jl; pl->jlb = h->pml_jl_bottom; pl->skip_bottom = skip_bottom;
     pl->direct.clear();
     for (int c = 0; c < PML_NCLS; c++) pl->n_items[c] = 0;
     const int ki0 = std::max(g.ibeg_k - g.ibeg, rg.li0), ki1 = std::min(g.iend_k - g.ibeg, rg.li1);
@@ -1003,7 +1013,7 @@ static int pml_build(swpc3d_handle *h, const Region &rg, const Box3 &cols, PmlPl
         if (cols.li1 < ki1) pl->direct.push_back(Box3{1, nz, cols.li1 + 1, ki1, kj0, kj1, 0, h->flat_bottom});
         if (cols.lj0 > kj0) pl->direct.push_back(Box3{1, nz, cols.li0, cols.li1, kj0, cols.lj0 - 1, 0, 0});
         if (cols.lj1 < kj1) pl->direct.push_back(Box3{1, nz, cols.li0, cols.li1, cols.lj1 + 1, kj1, 0, 0});
-        add_region(cols.li0, cols.li1, cols.lj0, cols.lj1, g.kend_k + 1, true, h->flat_bottom != 0);
+        if (!skip_bottom) add_region(cols.li0, cols.li1, cols.lj0, cols.lj1, g.kend_k + 1, true, h->flat_bottom != 0);
     }
     CK(cudaMalloc(&pl->d_ticket, PML_NCLS * sizeof(unsigned int)));
     CK(cudaMemset(pl->d_ticket, 0, PML_NCLS * sizeof(unsigned int)));
@@ -1036,14 +1046,15 @@ static void pml_launch_class(const KParams<F> &p, PmlPlan *pl, const PmlGeom &gm
 
 // the absorber shell of region rg: pml_tma work lists + the boxes left to sweep_direct, all beside the interior kernel
 template <typename F, bool STRESS>
-static int launch_shell(swpc3d_handle *h, const KParams<F> &p, const Region &rg, const Box3 &cols) {
+static int launch_shell(swpc3d_handle *h, const KParams<F> &p, const Region &rg, const Box3 &cols, bool skip_bottom = false,
+                        const std::function<int(cudaStream_t)> &extra = nullptr) {
     auto same = [](const Box3 &a, const Box3 &b) { return a.li0 == b.li0 && a.li1 == b.li1 && a.lj0 == b.lj0 && a.lj1 == b.lj1; };
     std::vector<PmlPlan *> &list = h->pml[STRESS ? 0 : 1];
     PmlPlan *pl = nullptr;
     for (size_t q = 0; q < list.size(); q++) {
         PmlPlan *c = list[q];
         if (!(c->rg.li0 == rg.li0 && c->rg.li1 == rg.li1 && c->rg.lj0 == rg.lj0 && c->rg.lj1 == rg.lj1)) continue;
-        if (same(c->cols, cols) && c->jl == h->pml_jl && c->jlb == h->pml_jl_bottom) { pl = c; break; }
+        if (same(c->cols, cols) && c->jl == h->pml_jl && c->jlb == h->pml_jl_bottom && c->skip_bottom == skip_bottom) { pl = c; break; }
         CK(cudaDeviceSynchronize());   // the same region with other tiling options: rebuild
         for (int k = 0; k < PML_NCLS; k++) cudaFree(c->d_items[k]);
         cudaFree(c->d_ticket);
@@ -1053,7 +1064,7 @@ static int launch_shell(swpc3d_handle *h, const KParams<F> &p, const Region &rg,
     }
     if (!pl) {
         pl = new PmlPlan();
-        if (pml_build<F, STRESS>(h, rg, cols, pl)) { delete pl; return 1; }
+        if (pml_build<F, STRESS>(h, rg, cols, skip_bottom, pl)) { delete pl; return 1; }
         list.push_back(pl);
     }
     int nsm = 148;
@@ -1078,6 +1089,12 @@ static int launch_shell(swpc3d_handle *h, const KParams<F> &p, const Region &rg,
     PmlGeom gm{};
     if (STRESS) { gm.c_first = 3; gm.h_first = 0; gm.sa_first = 0; gm.m1_index = 2; gm.mh_index = 1; gm.a_first = 0; }
     else { gm.c_first = 0; gm.h_first = 6; gm.sa_first = 3; gm.m1_index = 2; gm.mh_index = 0; gm.a_first = 9; }
+    if (extra) {   // the whole-line bottom tiles of this region (bottom_tma)
+        cudaStream_t st;
+        if (fork(st)) return 1;
+        if (extra(st)) return 1;
+        if (join(st)) return 1;
+    }
     for (int cls = 0; cls < PML_NCLS; cls++) {
         if (!pl->n_items[cls]) continue;
         cudaStream_t st;
@@ -1120,12 +1137,11 @@ static void tplan_drop(swpc3d_handle *h) {
         tp = nullptr;
     }
 }
-static int tplan_build(swpc3d_handle *h, const Box3 &t, int TK, int TI, int blocks_per_sm, TmaPlan *tp) {
+static int tplan_build(swpc3d_handle *h, const Box3 &t, int TK, int TI, int blocks_per_sm, int k1_k, TmaPlan *tp) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev);
     nsm *= std::max(1, blocks_per_sm);
     const int nkt = (t.k1 - t.k0 + 1) / TK, nit = (t.li1 - t.li0 + TI) / TI, P = t.lj1 - t.lj0 + 1;
-    const int k1_k = h->g.kend_k;
     const int nch = std::max(1, (P + h->tma_pl / 2) / std::max(1, h->tma_pl));
     std::vector<TmaItem> items;
     for (int c = 0; c < nch; c++) {
@@ -1151,20 +1167,154 @@ static int tplan_build(swpc3d_handle *h, const Box3 &t, int TK, int TI, int bloc
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// bottom_tma: the rows k = nz-31 .. nz under the interior columns `cols` of a region, as whole 32-row tiles
+struct BotPlan {
+    Box3 cols{};
+    int jl = 0, nitems = 0, grid = 0;
+    BotItem *d_items = nullptr;
+    unsigned int *d_ticket = nullptr;
+    unsigned int base = 0;
+    BotMaps maps{};
+    BotGeom g{};
+    bool ok = false;
+};
+static void bot_drop(swpc3d_handle *h) {
+    if (h->bot[0].empty() && h->bot[1].empty()) return;
+    cudaSetDevice(h->dev);
+    cudaDeviceSynchronize();
+    for (auto &list : h->bot) {
+        for (BotPlan *b : list) { cudaFree(b->d_items); cudaFree(b->d_ticket); delete b; }
+        list.clear();
+    }
+}
+// can the bottom rows of this run be swept as whole-line tiles at all?  (geometry only; the per-region checks are in bot_build)
+static bool bot_possible(const swpc3d_handle *h, bool stress) {
+    const swpc3d_grid &g = h->g;
+    if (!h->use_bot || !h->use_pml || g.abc_type != SWPC3D_ABC_PML || !get_encode() || h->h_aoff.empty()) return false;
+    if (!h->use_tma || !h->tma_ok || (!stress && !h->use_ring)) return false;
+    if (g.nz % 4 != 0 || g.nz < 64) return false;
+    const int k0 = g.nz - 31, RI = g.kend_k - k0 + 1;
+    if (RI < 1 || RI > 31 || g.kend_k != g.nz - g.na) return false;
+    const int nint32 = (RI * 8 + 31) / 32 * 32, npml = (32 - RI) * 8;
+    return (stress ? 2 : 1) * nint32 + npml <= 512;
+}
+template <typename F, int NM, bool STRESS>
+static int bot_build(swpc3d_handle *h, const Box3 &cols, BotPlan *bp) {
+    using C = BotCfg<F, NM, STRESS>;
+    const swpc3d_grid &g = h->g;
+    bp->cols = cols; bp->jl = h->bot_jl; bp->ok = false;
+    const int nz = g.nz, nxp = h->nxp, kb = g.kend_k + 1;
+    auto aoff = [&](int li, int lj) { return h->h_aoff[(size_t)li + (size_t)nxp * lj]; };
+    auto kba = [&](int li, int lj) { return h->h_kbeg_a[(size_t)(li + HALO) + (size_t)h->NXM * (lj + HALO)]; };
+    const int a0 = cols.li0, a1 = cols.li1, b0 = cols.lj0, b1 = cols.lj1;
+    if (a1 < a0 || b1 < b0 || C::SMEM > 227 * 1024) return 0;
+    const int ncols = a1 - a0 + 1, nrows_j = b1 - b0 + 1;
+    const int phase = (kb - 1) & 31;
+    const long long klen = ((long long)phase + (nz - kb + 1) + 31) / 32 * 32;
+    const long long asi = ncols > 1 ? aoff(a0 + 1, b0) - aoff(a0, b0) : klen;
+    const long long asj = nrows_j > 1 ? aoff(a0, b0 + 1) - aoff(a0, b0) : asi * ncols;
+    for (int lj = b0; lj <= b1; lj++)
+        for (int li = a0; li <= a1; li++)
+            if (kba(li, lj) != kb || aoff(li, lj) != aoff(a0, b0) + (long long)(li - a0) * asi + (long long)(lj - b0) * asj) return 0;
+    if (asi < klen || asj < asi * ncols || asi % 4 || asj % 4) return 0;
+    BotGeom &G = bp->g;
+    G = BotGeom{};
+    G.k0 = nz - 31; G.RI = g.kend_k - G.k0 + 1;
+    G.RIB = (G.RI + 3) / 4 * 4; G.RIA = G.RI / 4 * 4; G.NA = 32 - G.RIA;
+    G.ak = phase - (G.RI - G.RIA);
+    if (G.ak < 0) return 0;
+    G.asi = (int)asi; G.asj = asj;
+    if (STRESS) { G.c_first = 3; G.h_first = 0; G.sa_first = 0; G.m_first = 2; G.mh_index = 1; G.a_first = 0; }
+    else { G.c_first = 0; G.h_first = 6; G.sa_first = 3; G.m_first = 2; G.mh_index = 0; G.a_first = 9; }
+    G.nint = G.RI * 8; G.nint32 = (G.nint + 31) / 32 * 32;
+    // tensor maps
+    const int pr = h->pml_promo;
+    BotMaps &M = bp->maps;
+    bool ok = make_map(h, &M.C, h->Fall, sizeof(F), 9, 32, 8, STRESS ? 6 : 3, pr) && make_map(h, &M.H, h->Fall, sizeof(F), 9, 40, 12, 3, pr) &&
+              make_map(h, &M.Mh, h->Mall, 4, 5, 36, 9, 1, pr);
+    if (STRESS) ok = ok && make_map(h, &M.M, h->Mall, 4, 5, 32, 8, C::NMED, pr);
+    if (STRESS && NM > 0) ok = ok && make_map(h, &M.R, h->R, 4, 6 * NM, G.RIB, 8, 6 * NM, pr);
+    {
+        const cuuint64_t dims[4] = {(cuuint64_t)klen, (cuuint64_t)ncols, (cuuint64_t)nrows_j, 18};
+        const cuuint64_t st[3] = {(cuuint64_t)asi * 4, (cuuint64_t)asj * 4, (cuuint64_t)h->naux * 4};
+        const cuuint32_t box[4] = {(cuuint32_t)G.NA, 8, 1, 9};
+        ok = ok && make_map_generic(&M.aux, h->aux + (aoff(a0, b0) - phase), 4, dims, st, box, pr);
+    }
+    if (!ok || cudaFuncSetAttribute(bottom_tma<F, NM, STRESS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    // items: tile column fastest, then runs of about bot_jl planes
+    const int nch = std::max(1, (nrows_j + h->bot_jl / 2) / std::max(1, h->bot_jl));
+    std::vector<BotItem> items;
+    for (int c = 0; c < nch; c++) {
+        const int j0 = b0 + (int)((long long)nrows_j * c / nch), j1 = b0 + (int)((long long)nrows_j * (c + 1) / nch) - 1;
+        for (int it = 0; it * 8 < ncols; it++) {
+            BotItem I{};
+            I.li0 = a0 + it * 8; I.ncol = std::min(8, a1 - I.li0 + 1);
+            I.lj0 = j0; I.nsteps = j1 - j0 + 1;
+            I.ai = I.li0 - a0; I.aj = j0 - b0;
+            I.aux0 = aoff(a0, b0) + (G.RIA - G.RI) + (long long)I.ai * asi + (long long)I.aj * asj;
+            items.push_back(I);
+        }
+    }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->dev);
+    bp->nitems = (int)items.size();
+    G.nitems = bp->nitems;
+    bp->grid = std::min(nsm, bp->nitems);
+    CK(cudaMalloc(&bp->d_items, items.size() * sizeof(BotItem)));
+    CK(cudaMalloc(&bp->d_ticket, sizeof(unsigned int)));
+    CK(cudaMemcpy(bp->d_items, items.data(), items.size() * sizeof(BotItem), cudaMemcpyHostToDevice));
+    CK(cudaMemset(bp->d_ticket, 0, sizeof(unsigned int)));
+    bp->ok = true;
+    return 0;
+}
+// the plan of region columns `cols` (built on first use); nullptr when the bottom rows cannot be swept this way
+template <typename F, int NM, bool STRESS>
+static BotPlan *bot_plan(swpc3d_handle *h, const Box3 &cols) {
+    if (!bot_possible(h, STRESS)) return nullptr;
+    auto same = [](const Box3 &a, const Box3 &b) { return a.li0 == b.li0 && a.li1 == b.li1 && a.lj0 == b.lj0 && a.lj1 == b.lj1; };
+    std::vector<BotPlan *> &list = h->bot[STRESS ? 0 : 1];
+    for (BotPlan *b : list)
+        if (same(b->cols, cols) && b->jl == h->bot_jl) return b->ok ? b : nullptr;
+    BotPlan *bp = new BotPlan();
+    if (bot_build<F, NM, STRESS>(h, cols, bp)) { bp->ok = false; cudaGetLastError(); }
+    list.push_back(bp);
+    return bp->ok ? bp : nullptr;
+}
+template <typename F, int NM, bool STRESS>
+static int bot_launch(swpc3d_handle *h, const KParams<F> &p, BotPlan *bp, cudaStream_t st) {
+    using C = BotCfg<F, NM, STRESS>;
+    bottom_tma<F, NM, STRESS><<<bp->grid, C::THREADS, C::SMEM, st>>>(p, bp->maps, bp->d_items, bp->d_ticket, bp->base, bp->g);
+    bp->base += (unsigned int)(bp->nitems + bp->grid);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <typename F, int NM>
-static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg) {
+static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p0, const Region &rg) {
     using C = TmaCfg<F, NM>;
     if (!h->tma_ready) tma_prepare<F, NM>(h);
-    const Box3 t = tma_box<F, NM>(h, rg);
+    Box3 t = tma_box<F, NM>(h, rg);
     const Box3 all{1, h->g.nz, rg.li0, rg.li1, rg.lj0, rg.lj1, 0};
-    if (t.k1 < t.k0) return launch_direct_box<F, true>(h, p, all);
+    if (t.k1 < t.k0) return launch_direct_box<F, true>(h, p0, all);
+    // the bottom 32 rows of the interior columns as whole-line tiles (bottom_tma): the interior kernel then stops at k = nz - 32
+    KParams<F> p = p0;
+    BotPlan *bp = bot_plan<F, NM, true>(h, t);
+    if (bp) {
+        p.k1_k = h->g.nz - 32;
+        t.k1 = (p.k1_k + C::TK - 1) / C::TK * C::TK;
+    }
     TmaGeom g{};
     g.li0 = t.li0; g.li1 = t.li1; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
     g.shift_last = h->tma_shift;
     dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + C::TI) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
     // complement of the TMA box inside the owned box: the absorber shell (four slabs of wall columns, the bottom rows under the
-    // interior columns) and, if the interior box is not a whole number of tiles wide, the ragged interior columns.  All launches
-    // touch disjoint cells and only read V, so they are issued on side streams next to the interior kernel.
+    // interior columns).  All launches touch disjoint cells and only read V, so they are issued on side streams next to the
+    // interior kernel.
     if (side_streams(h)) CK(cudaEventRecord(h->ev_fork, h->st));
     if (h->tma_persist && !h->cur) {
         const Region w = whole_region(h);
@@ -1181,7 +1331,7 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
             tp = new TmaPlan();
             int bps = 1;   // resident blocks per SM (2 for the elastic instantiation)
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, stress_tma_p<F, NM>, C::THREADS, C::SMEM) != cudaSuccess) { cudaGetLastError(); bps = 1; }
-            if (tplan_build(h, t, C::TK, C::TI, bps, tp)) return 1;
+            if (tplan_build(h, t, C::TK, C::TI, bps, p.k1_k, tp)) return 1;
         }
         stress_tma_p<F, NM><<<tp->grid, C::THREADS, C::SMEM, main_stream(h)>>>(p, h->tmaps, tp->d_items, tp->nitems, tp->d_ticket, tp->base, g);
         tp->base += (unsigned int)(tp->nitems + tp->grid);
@@ -1190,9 +1340,9 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p, const Region 
     }
     h->launches++;
     CK(cudaGetLastError());
-    return launch_shell<F, true>(h, p, rg, t);
+    if (bp) return launch_shell<F, true>(h, p0, rg, t, true, [&](cudaStream_t st) { return bot_launch<F, NM, true>(h, p0, bp, st); });
+    return launch_shell<F, true>(h, p0, rg, t);
 }
-
 template <typename F, int NM>
 static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg) {
     using C = TmaCfg<F, NM>;
@@ -1206,7 +1356,10 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         // interior kernel box with the register-ring kernel; the absorber shell (all PML cells: two j slabs, two i slabs,
         // the bottom k slab) with the direct kernel on side streams.  Every launch writes disjoint cells and only reads S.
         const swpc3d_grid &gg = h->g;
-        const Box3 in{1, gg.kend_k, ki0, ki1, kj0, kj1, 0};
+        Box3 in{1, gg.kend_k, ki0, ki1, kj0, kj1, 0};
+        BotPlan *bp = bot_plan<F, NM, false>(h, in);   // the bottom 32 rows as whole-line tiles: the ring kernel stops at k = nz - 32
+        const Box3 cols = in;
+        if (bp) in.k1 = gg.nz - 32;
         const int jlen = std::max(1, h->ring_jlen);
         dim3 blk((unsigned)h->tk, (unsigned)h->ti, 1);
         dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
@@ -1222,7 +1375,8 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         if (!pair) vel_ring<F><<<grd, blk, 0, main_stream(h)>>>(p, in, jlen, h->ring_pf);
         h->launches++;
         CK(cudaGetLastError());
-        return launch_shell<F, false>(h, p, rg, in);
+        if (bp) return launch_shell<F, false>(h, p, rg, cols, true, [&](cudaStream_t st) { return bot_launch<F, NM, false>(h, p, bp, st); });
+        return launch_shell<F, false>(h, p, rg, cols);
     }
     if (t.k1 < t.k0 || !h->vtma_ok || h->use_tma < 2) return launch_direct_box<F, false>(h, p, all);
     TmaGeom g{};
@@ -2193,7 +2347,9 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "side_streams")) h->use_side = value;
     else if (!strcmp(key, "comm_timeout_s")) h->comm_timeout_s = value;
     else if (!strcmp(key, "p2p")) h->use_p2p = value != 0;
-    else if (!strcmp(key, "pml_tma")) { h->use_pml = value; pml_drop(h); }
+    else if (!strcmp(key, "pml_tma")) { h->use_pml = value; pml_drop(h); bot_drop(h); }
+    else if (!strcmp(key, "bottom_tma")) { h->use_bot = value != 0; pml_drop(h); bot_drop(h); }
+    else if (!strcmp(key, "bot_jl")) { if (value < 1) return fail("bot_jl must be >= 1"); h->bot_jl = value; bot_drop(h); }
     else if (!strcmp(key, "l2promo")) { h->l2promo = value; h->tma_ready = false; }
     else if (!strcmp(key, "l2promo_halo")) { h->l2promo_halo = value; h->tma_ready = false; }
     else if (!strcmp(key, "pml_promo")) { h->pml_promo = value; pml_drop(h); }
@@ -2216,6 +2372,11 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "device")) *value = h->dev;
     else if (!strcmp(key, "tma_ok")) *value = h->tma_ok ? 1.0 : 0.0;
     else if (!strcmp(key, "p2p_ok")) *value = (h->p2p_ok && h->use_p2p) ? 1.0 : 0.0;
+    else if (!strcmp(key, "bottom_items") || !strcmp(key, "bottom_items_vel")) {
+        double n = 0;
+        for (const BotPlan *b : h->bot[strstr(key, "_vel") ? 1 : 0]) n += b->ok ? b->nitems : 0;
+        *value = n;
+    }
     else if (!strncmp(key, "pml_", 4)) {   // the shell plan of the last whole-region (core-region: "_core" suffix) sweeps
         const int w = strstr(key, "_vel") ? 1 : 0;
         const bool core = strstr(key, "_core") != nullptr;

@@ -194,6 +194,10 @@ pml_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ PmlMaps tm
     float4 gxc = make_float4(0, 0, 0, 0), gxe = gxc, gzc = gxc, gze = gxc;
     for (int gs = 0;; gs++) {
         const int s = gs % C::NS;
+        // the y profile of this plane comes from global memory: fetched BEFORE the wait (lj already points at this step unless a new
+        // item starts), so that its L2 latency hides behind the barrier
+        float4 gyc = make_float4(0, 0, 0, 0), gye = gyc;
+        if (active) { const int q = min(lj, p.nyp - 1); gyc = ldro(p.gyc + q); gye = ldro(p.gye + q); }   // (lj = one past the item's last plane after its last step)
         mbar_wait(&full[s], (gs / C::NS) & 1);
         const int it = meta[s].x, t = meta[s].y;
         if (it < 0) break;
@@ -210,9 +214,8 @@ pml_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ PmlMaps tm
             a.an = I.aux0 + kr + (long long)ai * I.asi;
             asj = I.asj;
             lj = I.lj0;
+            if (active) { gyc = ldro(p.gyc + lj); gye = ldro(p.gye + lj); }
         }
-        float4 gyc = make_float4(0, 0, 0, 0), gye = gyc;
-        if (active) { gyc = ldro(p.gyc + lj); gye = ldro(p.gye + lj); }
         const int v0 = gs + 2 * m, q0 = gs + m;
         const unsigned char *st = smem + s * C::STAGE;
 #pragma unroll

@@ -128,7 +128,7 @@ def test_step_entry_point_and_run(tmp_path):
     _compare(o, [d], exact=True)
 
 
-@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"pml_tma": 0}, {"tma_persist": 1}, {"tma_persist": 1, "tma_pl": 5}, {"pml_jl": 4, "pml_jl_bottom": 5}, {"side_streams": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}, {"flat_bottom": 0},
+@pytest.mark.parametrize("variant", [{"tma": 0, "vel_ring": 0}, {"pml_tma": 0}, {"tma_persist": 1}, {"tma_persist": 1, "tma_pl": 5}, {"bottom_tma": 1}, {"pml_jl": 4, "pml_jl_bottom": 5}, {"side_streams": 0}, {"tma": 1, "vel_ring": 0}, {"tma": 2, "vel_ring": 0}, {"vel_ring": 1, "ring_jlen": 5, "ring_pf": 0}, {"vel_ring": 1, "ring_pf": 2}, {"flat_bottom": 0},
                                      {"tma_shift": 1}, {"tma_shift": 0}])
 @pytest.mark.parametrize("abc", ["pml", "cerjan"])
 def test_kernel_variants_bit_exact(tmp_path, variant, abc):
@@ -169,6 +169,34 @@ def test_tma_staged_absorber_shell_bit_exact(tmp_path, case):
     # the absorber has been reached: the ADE variables are in use
     r = o.rank(0)
     assert np.abs(o.field(0, "Vz")[3:3 + r["nyp"], 3:3 + case["na"] + 1, 3:-3]).max() > 0 or nranks != (1, 1)
+
+
+@pytest.mark.parametrize("case", [
+    dict(nx=48, ny=44, nz=64, na=20),                                  # the bench's shape: 12 interior rows + 20 PML rows per tile
+    dict(nx=52, ny=47, nz=96, na=10),                                  # 22 interior rows, partial tile columns
+    dict(nx=48, ny=40, nz=64, na=6),                                   # 26 interior rows: every consumer warp has a role
+    dict(nx=48, ny=44, nz=64, na=7),                                   # na not a multiple of 4: R / aux boxes start off the role boundary
+    dict(nx=64, ny=56, nz=64, na=10, nranks=(2, 2)),                   # decomposed: core and slab regions each get their plan
+    dict(nx=48, ny=44, nz=64, na=20, mp="sp"),                         # float32 fields (vel_ring2 above the tiles)
+    dict(nx=48, ny=44, nz=64, na=20, nm=0, vmodel="lhm_land"),         # elastic: no memory variables, no R box
+])
+def test_whole_line_bottom_tiles_bit_exact(tmp_path, case):
+    """bottom_tma (option, off by default: measured no faster): the rows k = nz-31 .. nz as whole 32-row tiles whose interior cells
+    and PML cells are updated by different warps of one block; stress_tma / vel_ring stop at k = nz-32.  Against the oracle, and
+    against the same run with the tiles off."""
+    case = dict(case)
+    nranks, mp, nm = case.pop("nranks", (1, 1)), case.pop("mp", "dp"), case.pop("nm", 3)
+    zdeep = -3.0 + (case["nz"] - case["na"] - 4) * 0.5      # the second source sits four cells above the absorber
+    src = ["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8", f"-2.1 1.7 {zdeep} 0.10 0.5 4e14 -0.2 0.9 0.1 -0.5 0.3 0.6"]
+    case.setdefault("zbeg", -3.0)
+    o, devs = _run_pair(tmp_path / "a", 40, nranks=nranks, mp=mp, nm=nm, sources=src, options={"bottom_tma": 1}, **case)
+    _compare(o, devs, exact=True)
+    for d in devs:
+        assert d.info("bottom_items") > 0 and d.info("bottom_items_vel") > 0 and d.info("pml_items_bottom") == 0
+    o2, devs2 = _run_pair(tmp_path / "b", 40, nranks=nranks, mp=mp, nm=nm, sources=src, **case)    # the default: tiles off
+    _compare(o2, devs2, exact=True)
+    assert all(d.info("bottom_items") == 0 for d in devs2)
+    assert np.abs(o.field(0, "Szz")[3:-3, 3:-3, -8:-3]).max() > 0 or nranks != (1, 1)   # the bottom rows have seen the wave
 
 
 @pytest.mark.parametrize("opts", [{}, {"slab_tiled": 0}, {"slab_x": 2}, {"slab_x": 5}])
