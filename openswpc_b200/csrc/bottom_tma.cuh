@@ -259,7 +259,10 @@ bottom_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ BotMaps
             else bnd = p.band[col];
         }
         mbar_wait(&full[s], (gs / C::NS) & 1);
-        const int it = meta[s].x, t = meta[s].y;
+        int it = 0, t = 0;
+        if (lane == 0) { it = meta[s].x; t = meta[s].y; }   // the lane that arrives on the empty-barrier is the one that reads the mailbox
+        it = __shfl_sync(0xffffffffu, it, 0);
+        t = __shfl_sync(0xffffffffu, t, 0);
         if (it < 0) break;
         if (t == 0) {
             const BotItem I = items[it];

@@ -199,7 +199,10 @@ pml_tma(const __grid_constant__ KParams<F> p, const __grid_constant__ PmlMaps tm
         float4 gyc = make_float4(0, 0, 0, 0), gye = gyc;
         if (active) { const int q = min(lj, p.nyp - 1); gyc = ldro(p.gyc + q); gye = ldro(p.gye + q); }   // (lj = one past the item's last plane after its last step)
         mbar_wait(&full[s], (gs / C::NS) & 1);
-        const int it = meta[s].x, t = meta[s].y;
+        int it = 0, t = 0;
+        if (lane == 0) { it = meta[s].x; t = meta[s].y; }   // the lane that arrives on the empty-barrier is the one that reads the mailbox
+        it = __shfl_sync(0xffffffffu, it, 0);
+        t = __shfl_sync(0xffffffffu, t, 0);
         if (it < 0) break;
         if (t == 0) {
             const PmlItem I = items[it];

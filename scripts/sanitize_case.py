@@ -4,6 +4,9 @@
   python scripts/sanitize_case.py green   Green's-function mode through the host driver (green_store / green_source kernels)
   python scripts/sanitize_case.py psv     swpc_psv: 2 emulated ranks, PML NM=3
   python scripts/sanitize_case.py elastic NM=0, one rank: the two-blocks-per-SM instantiation of stress_tma (2-stage ring)
+  python scripts/sanitize_case.py sp      float32 fields, one rank: vel_ring2, 4-stage stress_tma, pml_tma<float>
+  python scripts/sanitize_case.py bottom  nz = 64, na = 20, one rank, option bottom_tma = 1 (whole-line bottom tiles) + persistent stress_tma_p
+Round 2: the 2x2 / split / elastic cases now run pml_tma (ticket-scheduled shell) and, for split, the tiled boundary slabs.
 """
 import sys
 import tempfile
@@ -58,6 +61,34 @@ elif mode == "elastic":
     x.run(1, 6)
     x.sync()
     print('tma_ok', x.info('tma_ok'), 'bit-exact:', check(o, [x], 76))
+elif mode == "sp":
+    inf = write_case(d, nt=6, nx=96, ny=88, nz=76, na=8)
+    o = Oracle(inf, base_dir=d, nm=3, mp="sp")
+    x = device_from_oracle(o, 0, field_dtype=np.float32, device=0)
+    o.run(1, 6)
+    x.run(1, 6)
+    x.sync()
+    print('pml items', x.info('pml_items_walls'), x.info('pml_items_bottom'), 'bit-exact:', check(o, [x], 76))
+elif mode == "many":   # more work items than SMs: every persistent block walks several items (mailbox / ring reuse across items)
+    inf = write_case(d, nt=4, nx=232, ny=216, nz=76, na=8)
+    o = Oracle(inf, base_dir=d, nm=3)
+    x = device_from_oracle(o, 0, device=0)
+    if len(sys.argv) > 2:
+        x.set_option(sys.argv[2], int(sys.argv[3]))
+    o.run(1, 4)
+    x.run(1, 4)
+    x.sync()
+    print('pml items', x.info('pml_items_walls'), x.info('pml_items_bottom'), 'bit-exact:', check(o, [x], 76))
+elif mode == "bottom":
+    inf = write_case(d, nt=6, nx=96, ny=88, nz=64, na=20)
+    o = Oracle(inf, base_dir=d, nm=3)
+    x = device_from_oracle(o, 0, device=0)
+    x.set_option("bottom_tma", 1)
+    x.set_option("tma_persist", 1)
+    o.run(1, 6)
+    x.run(1, 6)
+    x.sync()
+    print('bottom items', x.info('bottom_items'), x.info('bottom_items_vel'), 'bit-exact:', check(o, [x], 64))
 elif mode == "split":
     inf = write_case(d, nt=6, nx=96, ny=88, nz=76, na=8, sources=["-23.3 -21.3 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8",
                                                                   "0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
