@@ -200,13 +200,14 @@ def cell_counts(run, region=None) -> tuple[int, int]:
 
 def core_region(run, world: int) -> tuple[int, int, int, int]:
     """Owned columns swept on the launch stream inside the timed brackets when the exchange is overlapped: everything but the
-    two outermost planes towards each neighbour (abi.cu core_region)."""
+    boundary slab towards each neighbour (abi.cu core_region)."""
     npx, npy, me = run["nproc_x"], run["nproc_y"], run["myid"]
     idx, idy = me % npx, me // npx
     li0, li1, lj0, lj1 = 0, run["nxp"] - 1, 0, run["nyp"] - 1
+    wx = 8 if run["nxp"] >= 32 else 2   # x slabs are one tile column wide (abi.cu slab_width), y slabs the two planes the messages carry
     if world > 1:
-        if idx > 0: li0 += 2
-        if idx < npx - 1: li1 -= 2
+        if idx > 0: li0 += wx
+        if idx < npx - 1: li1 -= wx
         if idy > 0: lj0 += 2
         if idy < npy - 1: lj1 -= 2
     return li0, li1, lj0, lj1

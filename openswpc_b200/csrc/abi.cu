@@ -2372,6 +2372,7 @@ extern "C" int swpc3d_get_info(swpc3d_handle *h, const char *key, double *value)
     else if (!strcmp(key, "device")) *value = h->dev;
     else if (!strcmp(key, "tma_ok")) *value = h->tma_ok ? 1.0 : 0.0;
     else if (!strcmp(key, "p2p_ok")) *value = (h->p2p_ok && h->use_p2p) ? 1.0 : 0.0;
+    else if (!strcmp(key, "overlapped")) *value = (h->overlap && has_neighbour(h) && h->comm) ? 1.0 : 0.0;
     else if (!strcmp(key, "bottom_items") || !strcmp(key, "bottom_items_vel")) {
         double n = 0;
         for (const BotPlan *b : h->bot[strstr(key, "_vel") ? 1 : 0]) n += b->ok ? b->nitems : 0;

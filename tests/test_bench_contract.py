@@ -49,3 +49,24 @@ def test_b200_arm_has_no_cpu_fallback():
     assert p.returncode != 0
     assert "no CUDA device" in (p.stderr + p.stdout)
     assert not [l for l in p.stdout.splitlines() if l.startswith("{")]
+
+
+def test_cell_counts_and_core_region_arithmetic():
+    """The algorithmic-byte bookkeeping of the roofline: interior / absorber cells of a rank (m_global.f90:334-376) and of the core
+    region the sweep stopwatches cover when the exchange is overlapped (every owned column but the slab towards each neighbour)."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    # rank 1 of a 2 x 1 decomposition of 1024 x 1024 x 1024, na = 20: columns 513..1024, interior kernel box 513..1004 x 21..1004 x 1..1004
+    run = {"nz": 1024, "nxp": 512, "nyp": 1024, "ibeg": 513, "jbeg": 1, "ibeg_k": 513, "iend_k": 1004, "jbeg_k": 21, "jend_k": 1004,
+           "kbeg_k": 1, "kend_k": 1004, "nproc_x": 2, "nproc_y": 1, "myid": 1}
+    interior, pml = bench.cell_counts(run)
+    assert interior == 492 * 984 * 1004 and interior + pml == 512 * 1024 * 1024
+    li0, li1, lj0, lj1 = bench.core_region(run, 2)
+    assert (li0, li1, lj0, lj1) == (8, 511, 0, 1023)                      # one tile column (8) towards the -x neighbour, nothing else
+    ci, cp = bench.cell_counts(run, (li0, li1, lj0, lj1))
+    assert ci == (492 - 8) * 984 * 1004 and ci + cp == 504 * 1024 * 1024
+    assert bench.core_region(run, 1) == (0, 511, 0, 1023)
+    b = bench.bytes_per_cell(3, 8)
+    assert (b["stress_interior"], b["stress_pml"], b["vel_interior"], b["vel_pml"]) == (280, 200, 100, 172)
+    assert bench.psv_bytes_per_cell(3, 8)["stress_interior"] == 152 and bench.bytes_per_cell(0, 8)["stress_interior"] == 128
