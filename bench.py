@@ -331,9 +331,9 @@ def cpu_port_throughput(nm: int, sample=(384, 384, 384), steps: int = 24, warmup
 
 # ---------------------------------------------------------------------------------------------------------------------
 # secondary lines (N = 1): each a separate run on the same GPU, CUDA events on the library's launch stream
-def time_3d_case(inf: Path, wdir: Path, *, nm: int, fdt, K: int, Wm: int, device: int, snap: bool = False) -> dict:
+def time_3d_case(inf: Path, wdir: Path, *, nm: int, fdt, K: int, Wm: int, device: int) -> dict:
     """W warm-up + K timed steps of one swpc_3d case (state resident in HBM), the per-sweep stopwatches, and the roofline
-    fractions on algorithmic bytes.  With `snap` the timed region is Swpc3d.run() with the snapshot files open (host clock)."""
+    fractions on algorithmic bytes."""
     from openswpc_b200.swpc3d import Swpc3d
 
     W = np.dtype(fdt).itemsize
@@ -342,20 +342,8 @@ def time_3d_case(inf: Path, wdir: Path, *, nm: int, fdt, K: int, Wm: int, device
         run.attach_device(device)
         out = {"grid": [run["nx"], run["ny"], run["nz"]], "nm": nm, "field_type": "f64" if W == 8 else "f32", "steps": K, "warmup": Wm}
         cells = run["nx"] * run["ny"] * run["nz"]
-        if snap:
-            run.snap_open(wdir / "snap")
         run.run(1, Wm)
         run.device_call("swpc3d_sync")
-        if snap:   # the public call with the reference example's product set (host wall clock: the files are part of it)
-            t0 = time.perf_counter()
-            run.run(Wm + 1, Wm + K)
-            run.device_call("swpc3d_sync")
-            ms = (time.perf_counter() - t0) * 1e3
-            t1 = time.perf_counter()
-            run.snap_close()
-            out["close_s"] = time.perf_counter() - t1
-            out.update({"ms_per_step": ms / K, "value": cells * K / (ms / 1e3), "unit": "cell-updates/s"})
-            return out
         run.set_option("kernel_timing", 1)
         l0 = run.info("launches")
         run.timer_start()
@@ -550,7 +538,7 @@ def main():
     ap.add_argument("--grid", default="", help="nx,ny,nz per GPU (development only; default = the BASELINE workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary / weak_base / e2e_snap runs (development, profiling)")
-    ap.add_argument("--secondary", default="", help="comma separated subset of psv,elastic,f32,weak_base,e2e_snap (development)")
+    ap.add_argument("--secondary", default="", help="comma separated subset of psv,elastic,f32,weak_base (development)")
     ap.add_argument("--hetero", type=int, default=-1, help="1: lhm_rmed model, 0: layered lhm (default: lhm at N=1, lhm_rmed at N>1)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--opts", default="", help="key=value,... library options (development only, e.g. overlap=0)")
@@ -615,7 +603,7 @@ def main():
     fdt = np.float64 if a.dtype == "f64" else np.float32
     W = np.dtype(fdt).itemsize
     K, Wm = a.steps, max(a.warmup, 3)
-    nt = Wm + 2 * K + 2
+    nt = Wm + 3 * K + 12
     td = tempfile.TemporaryDirectory()
 
     parity = None
@@ -628,7 +616,7 @@ def main():
             raise SystemExit(3)
 
     wdir = Path(td.name) / f"rank{rank}"
-    inf = write_workload(wdir, nx, ny, nz, nt, npx, npy, hetero=hetero)
+    inf = write_workload(wdir, nx, ny, nz, nt, npx, npy, hetero=hetero, extra=SNAP_BLOCK)   # (snapshot files only exist once snap_open is called)
     t_setup = time.perf_counter()
     run = Swpc3d(inf, base_dir=wdir, nm=nm, myid=rank, field_dtype=fdt)
     allreduce_minmax(run)
@@ -705,6 +693,23 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- timed region 3 (e2e_snap): the same public call with the snapshot files of the reference's example open (example/input.inf:55-83:
+    # xz / ob sections x ps / v / u, every 5 steps, decimation 2, netCDF): slice kernels every step, and at output steps the reduction onto
+    # the I/O ranks, the copies to the host and the file records -- all of it beside the sweeps (asynchronous snapshot path)
+    t_snap = None
+    if not a.no_secondary:
+        run.snap_open(Path(td.name) / "snap")      # the I/O ranks of m_snap.f90:163-191 write
+        run.run(Wm + 2 * K + 1, Wm + 2 * K + 10)   # warm-up: two output steps (first use of the snapshot communicator, pinned buffers, files)
+        barrier()
+        t0 = time.perf_counter()
+        run.run(Wm + 2 * K + 11, Wm + 3 * K + 10)
+        run.device_call("swpc3d_sync")
+        t_snap = time.perf_counter() - t0
+        barrier()
+        t1 = time.perf_counter()
+        run.snap_close()
+        t_snap_close = time.perf_counter() - t1
+
     nsrc, nst, ntw = run["nsrc"], run["nst"], run["ntw"]
     h2d = 4.0 * nsrc
     d2h = (12.0 * len(vm) + 4.0 * 3 * nst * ntw) / K
@@ -715,7 +720,8 @@ def main():
     c_interior, c_pml = cell_counts(run, core_region(run, world)) if overlapped else (interior, pml)
     exposed_rank = ms / K - ms_stress - ms_vel   # this rank's step time outside its two sweep brackets (not clamped)
     stats = torch.tensor([ms, t_e2e * 1e3, launches, h2d, d2h, float(interior), float(pml), ms_stress, ms_vel, ms_halo,
-                          halo_bytes / max(n_halo, 1.0), ms_halo_alone, exposed_rank, ms_halo_alone_nccl], dtype=torch.float64, device="cuda")
+                          halo_bytes / max(n_halo, 1.0), ms_halo_alone, exposed_rank, ms_halo_alone_nccl,
+                          (t_snap or 0.0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -792,26 +798,22 @@ def main():
         "gpu_launches": int(sm[2]),
         "progress_lines": [[float(x) for x in r] for r in vm[-2:]],
     }
+    if t_snap is not None:
+        line["e2e_snap"] = {"value": cells * K / (float(mx[14]) / 1e3), "unit": "cell-updates/s", "ms_per_step": float(mx[14]) / K, "close_s": t_snap_close,
+                            "what": "Swpc3d.run() with the snapshot files of example/input.inf:55-83 open (xz / ob sections x ps / v / u, ntdec_s = 5, decimation 2, "
+                                    "netCDF): slice kernels, reduction onto the I/O ranks, D2H and file records included, on the headline run's own state; "
+                                    "compare ms_per_step with e2e.ms_per_step"}
     if parity is not None:
         line["parity"] = parity
     line["clocks"] = clocks
     if world == 1 and not a.no_secondary and not a.grid:
-        which = set(filter(None, a.secondary.split(","))) or {"psv", "elastic", "f32", "weak_base", "e2e_snap"}
+        which = set(filter(None, a.secondary.split(","))) or {"psv", "elastic", "f32", "weak_base"}
         Ks, Ws = min(K, 20), 3
         sampler2 = ClockSampler(local)
         sampler2.start()
         line["secondary"] = secondary_lines(Path(td.name), Ks, Ws, local, which)
         if "weak_base" in which:
             line["weak_base"] = weak_base_line(Path(td.name), Ks, Ws, local)
-        if "e2e_snap" in which:
-            try:   # the public call with the reference example's snapshot product set (example/input.inf:55-83) on the headline grid
-                inf_s = write_workload(Path(td.name) / "snap", nx, ny, nz, Ws + Ks + 2, 1, 1, hetero=hetero, extra=SNAP_BLOCK)
-                r = time_3d_case(inf_s, Path(td.name) / "snap", nm=nm, fdt=fdt, K=Ks, Wm=Ws, device=local, snap=True)
-                r["what"] = ("Swpc3d.run() with the snapshot files of example/input.inf:55-83 open (xz/ob x ps/v/u, ntdec_s=5, decimation 2, netCDF): "
-                             "slice kernels, D2H and file records included; compare ms_per_step with e2e.ms_per_step")
-                line["e2e_snap"] = r
-            except Exception as e:
-                line["e2e_snap"] = {"error": f"{type(e).__name__}: {e}"[:400]}
         line["secondary"]["clocks"] = sampler2.stop()
     if world == 1 and not a.no_cpu_baseline:
         try:

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -2217,7 +2218,14 @@ extern "C" int swpc3d_comm_init(swpc3d_handle *h, const char id[128], int32_t nr
     h->comm_rank = rank;
     h->comm_size = nranks;
     // snapshot reductions get a communicator of their own: they are issued on another stream, beside the halo exchange
-    if (g_nccl.CommSplit && g_nccl.CommSplit(h->comm, 0, rank, &h->comm_io, nullptr) != ncclSuccess) h->comm_io = nullptr;
+    // and it is held to ONE channel (one CTA): a snapshot slice is a few MB, and every CTA of a collective kernel takes an SM away
+    // from the DRAM-bound sweeps while it waits for its peers (with NCCL's default channel count a reduction cost 1 ms of step time)
+    if (g_nccl.CommSplit) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = 1;
+        if (g_nccl.CommSplit(h->comm, 0, rank, &h->comm_io, &cfg) != ncclSuccess) h->comm_io = nullptr;
+    }
     return p2p_setup(h);
 }
 
