@@ -127,6 +127,7 @@ struct swpc3d_handle {
     int use_bot = 0, bot_jl = 82;
     int use_pml = 1;                       // option "pml_tma": 0 = the whole shell with sweep_direct
     int pml_jl = 32, pml_jl_bottom = 41;   // planes per work item (targets; evened out over the region)
+    int l2hint = 0;                        // option "l2hint": L2 eviction policy of stress_tma's TMA loads (1: centre boxes evict-first, 2: + halo boxes evict-last)
     int l2promo = 2, l2promo_halo = 2;     // options "l2promo" / "l2promo_halo": L2 promotion of stress_tma's centre / halo boxes (0 none, 1 64 B, 2 128 B, 3 256 B)
     int pml_promo = 1, pml_promo_b = 1;    // options "pml_promo" / "pml_promo_bottom": the same for pml_tma's wall / bottom items
     long long *aoff = nullptr;
@@ -145,6 +146,13 @@ struct swpc3d_handle {
     int *src_ijk = nullptr;
     double *src_mo = nullptr, *src_mij = nullptr;
     float *src_prm = nullptr, *src_stime = nullptr;
+    // host-evaluated source-time values of a step, 17..256 sources: pinned host ring -> device ring (a copy from pageable memory would
+    // synchronise the host with the launch stream at every step)
+    static constexpr int STIME_RING = 32;
+    float *stime_pin = nullptr;
+    cudaEvent_t stime_ev[STIME_RING] = {};
+    unsigned int stime_n = 0;
+    float *stime_cur = nullptr;
     std::vector<float> h_prm;
     double dt_dxyz = 0;
     // stations
@@ -160,6 +168,8 @@ struct swpc3d_handle {
     int *g_ijk = nullptr;
     float *g_acc = nullptr, *g_gf = nullptr;
     unsigned int *vmax_d = nullptr;
+    float *vmax_h = nullptr;               // pinned: a device-to-host copy into pageable memory blocks the host until the stream gets there,
+                                           // i.e. for ever behind an exchange whose peer is gone -- before any time-out could fire
     // snapshots
     swpc3d_snap_cfg snap{};
     bool snap_on = false;
@@ -177,6 +187,8 @@ struct swpc3d_handle {
     int nbr[4] = {-1, -1, -1, -1};
     ncclComm_t comm = nullptr;
     int comm_rank = -1, comm_size = 0;
+    cudaEvent_t nccl_ev[4] = {};           // the last four NCCL exchanges: the host never runs more than four exchanges ahead of the device,
+    unsigned int nccl_n = 0;               // so a peer that stopped is noticed here (a full NCCL work queue would block ncclGroupEnd for ever)
     int comm_timeout_s = 1800;             // option "comm_timeout_s": a host-side wait on a stream that carries NCCL work gives up after this
     bool comm_dead = false;                // the communicator was aborted (peer failure / timeout): every later exchange fails at once
     // peer-to-peer exchange (one node): a face's planes are stored straight into the neighbour's receive buffer (halo_push / halo_pull)
@@ -234,30 +246,43 @@ struct swpc3d_handle {
 // m_report.f90:144-151, say): poll the stream and ncclCommGetAsyncError instead, and turn an asynchronous NCCL error or a
 // timeout (option "comm_timeout_s") into the reference's clean abort -- ncclCommAbort, an error message, a non-zero return
 // -- where a blocking synchronise would hang for ever.
-static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
-    if (!h->comm || !g_nccl.CommGetAsyncError) {
-        CK(cudaStreamSynchronize(st));
+// the peer-to-peer exchange's own failure flag: halo_wait gave up on a neighbour that never pushed
+static int p2p_check(swpc3d_handle *h) {
+    if (!h->p2p_ok || !h->p2p_base) return 0;
+    unsigned int err = 0;
+    if (cudaMemcpy(&err, (unsigned int *)(h->p2p_base + h->p2p_count_off) + 16, sizeof(err), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
         return 0;
     }
+    if (!err) return 0;
+    char b[256];
+    snprintf(b, sizeof(b), "halo exchange aborted on rank %d: the neighbour across face %u sent nothing for %d s (it died or left the time loop)",
+             h->comm_rank, err - 1, h->comm_timeout_s);
+    h->comm_dead = true;
+    return fail(b);
+}
+template <typename Query>
+static int poll_wait(swpc3d_handle *h, Query query) {
     const auto t0 = std::chrono::steady_clock::now();
     for (long long spin = 0;; spin++) {
-        const cudaError_t e = cudaStreamQuery(st);
-        if (e == cudaSuccess) return 0;
+        const cudaError_t e = query();
+        if (e == cudaSuccess) return p2p_check(h);
         if (e != cudaErrorNotReady) {
             char b[256];
-            snprintf(b, sizeof(b), "stream_wait: %s", cudaGetErrorString(e));
+            snprintf(b, sizeof(b), "poll_wait: %s", cudaGetErrorString(e));
             return fail(b);
         }
         if ((spin & 255) == 255) {
             ncclResult_t ar = ncclSuccess;
-            const ncclResult_t qr = g_nccl.CommGetAsyncError(h->comm, &ar);
+            const ncclResult_t qr = (h->comm && g_nccl.CommGetAsyncError) ? g_nccl.CommGetAsyncError(h->comm, &ar) : ncclSuccess;
             const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             const bool timeout = h->comm_timeout_s > 0 && waited > (double)h->comm_timeout_s;
             if (qr != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress) || timeout) {
                 char b[384];
                 snprintf(b, sizeof(b), "halo exchange aborted on rank %d: %s (waited %.1f s); communicator destroyed with ncclCommAbort",
                          h->comm_rank, timeout ? "time-out, a neighbour rank stopped exchanging" : g_nccl.GetErrorString(qr != ncclSuccess ? qr : ar), waited);
-                g_nccl.CommAbort(h->comm);
+                if (h->comm_io && g_nccl.CommAbort) { g_nccl.CommAbort(h->comm_io); h->comm_io = nullptr; }
+                if (h->comm && g_nccl.CommAbort) g_nccl.CommAbort(h->comm);
                 h->comm = nullptr;
                 h->comm_dead = true;
                 return fail(b);
@@ -265,6 +290,20 @@ static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
             if (waited > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));
         }
     }
+}
+static int stream_wait(swpc3d_handle *h, cudaStream_t st) {
+    if (!h->comm) {
+        CK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    return poll_wait(h, [st]() { return cudaStreamQuery(st); });
+}
+static int event_wait(swpc3d_handle *h, cudaEvent_t ev) {
+    if (!h->comm) {
+        CK(cudaEventSynchronize(ev));
+        return 0;
+    }
+    return poll_wait(h, [ev]() { return cudaEventQuery(ev); });
 }
 #define WAIT(h_, st_)                        \
     do {                                     \
@@ -435,6 +474,7 @@ static int create_state(swpc3d_handle *h, const swpc3d_grid *g, const float *ts)
         }
     CK(cudaMemcpyAsync(h->kbeg_a, h->h_kbeg_a.data(), n2 * sizeof(int), cudaMemcpyHostToDevice, h->st));
     CK(cudaMalloc(&h->vmax_d, 3 * sizeof(unsigned int)));
+    CK(cudaMallocHost(&h->vmax_h, 3 * sizeof(float)));
     // halo buffers: 5 planes per face, m_global.f90:251-258
     const size_t isz = (size_t)5 * h->nyp * g->nz * h->fb, jsz = (size_t)5 * h->nxp * g->nz * h->fb;
     for (int f = 0; f < 4; f++) {
@@ -460,6 +500,8 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaDeviceSynchronize();
     for (int f = 0; f < 4; f++)
         if (h->p2p_peer[f]) cudaIpcCloseMemHandle(h->p2p_peer[f]);
+    for (cudaEvent_t e : h->nccl_ev)
+        if (e) cudaEventDestroy(e);
     cudaFree(h->p2p_base);
     if (h->comm_io && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm_io);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -484,6 +526,10 @@ extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     cudaFree(h->src_ijk); cudaFree(h->src_mo); cudaFree(h->src_mij); cudaFree(h->src_prm); cudaFree(h->src_stime);
     cudaFree(h->g_ijk); cudaFree(h->g_acc); cudaFree(h->g_gf);
     cudaFree(h->st_ijk); cudaFree(h->wav); cudaFree(h->wav_u); cudaFree(h->wav_s); cudaFree(h->wav_e); cudaFree(h->wav_acc); cudaFree(h->vmax_d);
+    if (h->vmax_h) cudaFreeHost(h->vmax_h);
+    if (h->stime_pin) cudaFreeHost(h->stime_pin);
+    for (cudaEvent_t e : h->stime_ev)
+        if (e) cudaEventDestroy(e);
     for (int f = 0; f < 4; f++) { cudaFree(h->sbuf[f]); cudaFree(h->rbuf[f]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -706,7 +752,8 @@ extern "C" int swpc3d_set_sources(swpc3d_handle *h, int32_t nsrc, const int32_t 
     CK(cudaMalloc(&h->src_mo, vmo.size() * sizeof(double)));
     CK(cudaMalloc(&h->src_mij, mij.size() * sizeof(double)));
     CK(cudaMalloc(&h->src_prm, h->h_prm.size() * sizeof(float)));
-    CK(cudaMalloc(&h->src_stime, (size_t)nsrc * sizeof(float)));
+    CK(cudaMalloc(&h->src_stime, (size_t)swpc3d_handle::STIME_RING * 256 * sizeof(float)));
+    if (!h->stime_pin) CK(cudaMallocHost(&h->stime_pin, (size_t)swpc3d_handle::STIME_RING * 256 * sizeof(float)));
     CK(cudaMemcpy(h->src_ijk, ijk.data(), ijk.size() * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->src_mo, vmo.data(), vmo.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->src_mij, mij.data(), mij.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -1312,6 +1359,7 @@ static int launch_stress_nm(swpc3d_handle *h, const KParams<F> &p0, const Region
     TmaGeom g{};
     g.li0 = t.li0; g.li1 = t.li1; g.lj0 = t.lj0; g.lj1 = t.lj1; g.jl = std::max(1, h->tma_jl); g.m_first = 2; g.mu_index = 1;
     g.shift_last = h->tma_shift;
+    g.l2hint = h->l2hint;
     dim3 grd((unsigned)((t.k1 - t.k0 + 1) / C::TK), (unsigned)((t.li1 - t.li0 + C::TI) / C::TI), (unsigned)((t.lj1 - t.lj0 + 1 + g.jl - 1) / g.jl));
     // complement of the TMA box inside the owned box: the absorber shell (four slabs of wall columns, the bottom rows under the
     // interior columns).  All launches touch disjoint cells and only read V, so they are issued on side streams next to the
@@ -1565,11 +1613,24 @@ static int launch_source(swpc3d_handle *h, int it, bool body, int phase = 0, cud
     const float dt = h->g.dt;
     s.t = body ? h->tbeg + it * dt : h->tbeg + ((float)it - 0.5f) * dt;   // m_source.f90:873 / :800
     s.stime = nullptr;
-    if (h->nsrc <= 256) {
-        float st[256];
-        for (int i = 0; i < h->nsrc; i++) st[i] = momentrate_host(s.t, h->stf, h->h_prm[2 * i], h->h_prm[2 * i + 1]);
-        if (phase == 0 || phase == 3) CK(cudaMemcpyAsync(h->src_stime, st, (size_t)h->nsrc * sizeof(float), cudaMemcpyHostToDevice, h->st));
-        s.stime = h->src_stime;
+    s.nstv = 0;
+    if (h->nsrc <= 16) {          // a handful of sources: the values ride in the kernel parameters
+        s.nstv = h->nsrc;
+        for (int i = 0; i < h->nsrc; i++) s.stv[i] = momentrate_host(s.t, h->stf, h->h_prm[2 * i], h->h_prm[2 * i + 1]);
+    } else if (h->nsrc <= 256) {  // pinned ring -> device ring, asynchronous; a slot is reused STIME_RING steps later, once its copy is done
+        if (phase == 0 || phase == 3) {
+            const unsigned int slot = h->stime_n % swpc3d_handle::STIME_RING;
+            cudaEvent_t &ev = h->stime_ev[slot];
+            if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            else if (event_wait(h, ev)) return 1;
+            float *st = h->stime_pin + (size_t)slot * 256;
+            for (int i = 0; i < h->nsrc; i++) st[i] = momentrate_host(s.t, h->stf, h->h_prm[2 * i], h->h_prm[2 * i + 1]);
+            h->stime_cur = h->src_stime + (size_t)slot * 256;
+            CK(cudaMemcpyAsync(h->stime_cur, st, (size_t)h->nsrc * sizeof(float), cudaMemcpyHostToDevice, h->st));
+            CK(cudaEventRecord(ev, h->st));
+            h->stime_n++;
+        }
+        s.stime = h->stime_cur;
     }
     if (phase == 3) return 0;
     const KParams<F> p = make_params<F>(h);
@@ -1729,27 +1790,28 @@ extern "C" int swpc3d_vmax(swpc3d_handle *h, float out[3]) {
     const int i0 = std::max(g.na + margin + 1, g.ibeg_k), i1 = std::min(g.nx - g.na - margin, g.iend_k);
     const int j0 = std::max(g.na + margin + 1, g.jbeg_k), j1 = std::min(g.ny - g.na - margin, g.jend_k);
     out[0] = out[1] = out[2] = 0.0f;
+    CK(cudaMemsetAsync(h->vmax_d, 0, 3 * sizeof(unsigned int), h->st));   // (also what swpc3d_vmax_global reduces for a rank without such cells)
     if (i1 < i0 || j1 < j0) return 0;
-    CK(cudaMemsetAsync(h->vmax_d, 0, 3 * sizeof(unsigned int), h->st));
     const long long n = (long long)(i1 - i0 + 1) * (j1 - j0 + 1);
     const int nb = (int)std::min<long long>((n + 255) / 256, 1184);
     if (h->fb == 8) vmax_kernel<double><<<nb, 256, 0, h->st>>>(make_params<double>(h), i0 - g.ibeg, i1 - g.ibeg, j0 - g.jbeg, j1 - g.jbeg, h->vmax_d);
     else vmax_kernel<float><<<nb, 256, 0, h->st>>>(make_params<float>(h), i0 - g.ibeg, i1 - g.ibeg, j0 - g.jbeg, j1 - g.jbeg, h->vmax_d);
     h->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->vmax_h, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     WAIT(h, h->st);
+    out[0] = h->vmax_h[0]; out[1] = h->vmax_h[1]; out[2] = h->vmax_h[2];
     return 0;
 }
 
 extern "C" int swpc3d_vmax_global(swpc3d_handle *h, float out[3]) {
     if (swpc3d_vmax(h, out)) return 1;
     if (!h->comm) return 0;
-    // non-negative floats: the max of the values is the max of their bit patterns, reduce as float
-    CK(cudaMemcpyAsync(h->vmax_d, out, 3 * sizeof(float), cudaMemcpyHostToDevice, h->st));
+    // non-negative floats: the max of the values is the max of their bit patterns, reduce as float (vmax_d still holds this rank's maxima)
     NK(g_nccl.AllReduce(h->vmax_d, h->vmax_d, 3, ncclFloat, ncclMax, h->comm, h->st));
-    CK(cudaMemcpyAsync(out, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
+    CK(cudaMemcpyAsync(h->vmax_h, h->vmax_d, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->st));
     WAIT(h, h->st);
+    out[0] = h->vmax_h[0]; out[1] = h->vmax_h[1]; out[2] = h->vmax_h[2];
     return 0;
 }
 
@@ -1866,20 +1928,6 @@ extern "C" int swpc3d_snap_fetch_max(swpc3d_handle *h, int32_t product, int32_t 
 // copies the slice buffer aside on the launch stream (device to device, microseconds) and lets a third stream reduce it onto
 // the root and copy it into pinned host memory [slot]; _end waits for that copy and returns the host pointer.  The sweeps go on
 // meanwhile; a slot may be reused once its _end has returned.
-static int event_wait(swpc3d_handle *h, cudaEvent_t ev) {
-    if (!h->comm) { CK(cudaEventSynchronize(ev)); return 0; }
-    const auto t0 = std::chrono::steady_clock::now();
-    for (long long spin = 0;; spin++) {
-        const cudaError_t e = cudaEventQuery(ev);
-        if (e == cudaSuccess) return 0;
-        if (e != cudaErrorNotReady) return fail(std::string("event_wait: ") + cudaGetErrorString(e));
-        if ((spin & 255) == 255) {
-            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            if (h->comm_timeout_s > 0 && waited > (double)h->comm_timeout_s) return fail("snapshot reduction timed out: a rank stopped taking part");
-            if (waited > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));
-        }
-    }
-}
 extern "C" int swpc3d_snap_fetch_begin(swpc3d_handle *h, int32_t product, int32_t root, int32_t slot) {
     if (!h || product < 0 || product >= 15 || slot < 0 || slot > 1) return fail("swpc3d_snap_fetch_begin: bad argument");
     if (!h->snap_buf[product]) return fail("swpc3d_snap_fetch_begin: product not enabled");
@@ -2136,7 +2184,9 @@ static int p2p_exchange(swpc3d_handle *h, const FaceLists &L, int which, cudaStr
     halo_p2p<F, true><<<dim3(gx, (unsigned)maxline, (unsigned)z), blk, 0, st_>>>(nz, h->NZP, h->NXM, push, seq);
     h->launches++;
     CK(cudaGetLastError());
-    halo_wait<<<1, 32, 0, st_>>>(fl[0], fl[1], fl[2], fl[3], seq);
+    unsigned int *err = (unsigned int *)(h->p2p_base + h->p2p_count_off) + 16;   // (behind the eight block counters)
+    const unsigned long long tmo = h->comm_timeout_s > 0 ? (unsigned long long)h->comm_timeout_s * 1000000000ull : 0ull;
+    halo_wait<<<1, 32, 0, st_>>>(fl[0], fl[1], fl[2], fl[3], seq, tmo, err);
     h->launches++;
     CK(cudaGetLastError());
     halo_p2p<F, false><<<dim3(gx, (unsigned)maxline, (unsigned)zr), blk, 0, st_>>>(nz, h->NZP, h->NXM, pull, seq);
@@ -2176,6 +2226,11 @@ static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr
         }
         return 0;
     }
+    {   // bound the host's run-ahead: exchange n is only issued once exchange n-4 has completed (polled with the failure checks)
+        cudaEvent_t &ev = h->nccl_ev[h->nccl_n & 3];
+        if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        else if (event_wait(h, ev)) return 1;
+    }
     if (h->fb == 8 ? launch_halo<double>(h, L, true, st_) : launch_halo<float>(h, L, true, st_)) return 1;
     const ncclDataType_t ty = h->fb == 8 ? ncclDouble : ncclFloat;
     NK(g_nccl.GroupStart());
@@ -2187,6 +2242,8 @@ static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr
     }
     NK(g_nccl.GroupEnd());
     if (h->fb == 8 ? launch_halo<double>(h, L, false, st_) : launch_halo<float>(h, L, false, st_)) return 1;
+    CK(cudaEventRecord(h->nccl_ev[h->nccl_n & 3], st_));
+    h->nccl_n++;
     if (timed) {
         CK(cudaEventRecord(h->cev[1][h->cev_used], st_));
         h->cev_used++;
@@ -2358,6 +2415,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "pml_tma")) { h->use_pml = value; pml_drop(h); bot_drop(h); }
     else if (!strcmp(key, "bottom_tma")) { h->use_bot = value != 0; pml_drop(h); bot_drop(h); }
     else if (!strcmp(key, "bot_jl")) { if (value < 1) return fail("bot_jl must be >= 1"); h->bot_jl = value; bot_drop(h); }
+    else if (!strcmp(key, "l2hint")) h->l2hint = value;
     else if (!strcmp(key, "l2promo")) { h->l2promo = value; h->tma_ready = false; }
     else if (!strcmp(key, "l2promo_halo")) { h->l2promo_halo = value; h->tma_ready = false; }
     else if (!strcmp(key, "pml_promo")) { h->pml_promo = value; pml_drop(h); }

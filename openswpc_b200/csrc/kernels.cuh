@@ -832,6 +832,8 @@ struct SrcParams {
     const double *mij;      // 6*nsrc: mxx myy mzz myz mxz mxy  (body force: fx fy fz in the first three)
     const float *prm;       // 2*nsrc
     const float *stime;     // optional host-evaluated moment rate for this step (nsrc), else nullptr
+    int nstv;               // > 0: the host-evaluated values travel in the kernel parameters themselves (up to 16 sources: no copy at all)
+    float stv[16];
     int stf;
     float t;                // evaluation time
     double dt_dxyz;
@@ -851,7 +853,7 @@ template <typename F>
 __global__ void stressglut_kernel(const __grid_constant__ KParams<F> p, const SrcParams s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.nsrc) return;
-    const float stime = s.stime ? s.stime[i] : momentrate_dev(s.t, s.stf, s.prm[2 * i], s.prm[2 * i + 1]);
+    const float stime = s.nstv > 0 ? s.stv[i] : s.stime ? s.stime[i] : momentrate_dev(s.t, s.stf, s.prm[2 * i], s.prm[2 * i + 1]);
     const F sdrop = (F)((F)s.mo[i] * stime * (F)s.dt_dxyz);
     const long long si = p.SI, sj = p.SJ;
     const long long n = (long long)(s.ijk[3 * i + 2] + KOFF - 1) + (long long)p.NZP * ((long long)s.ijk[3 * i] + (long long)p.NXM * s.ijk[3 * i + 1]);
@@ -876,7 +878,7 @@ template <typename F>
 __global__ void bodyforce_kernel(const __grid_constant__ KParams<F> p, const SrcParams s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.nsrc) return;
-    const float stime = s.stime ? s.stime[i] : momentrate_dev(s.t, s.stf, s.prm[2 * i], s.prm[2 * i + 1]);
+    const float stime = s.nstv > 0 ? s.stv[i] : s.stime ? s.stime[i] : momentrate_dev(s.t, s.stf, s.prm[2 * i], s.prm[2 * i + 1]);
     const long long si = p.SI, sj = p.SJ;
     const long long n = (long long)(s.ijk[3 * i + 2] + KOFF - 1) + (long long)p.NZP * ((long long)s.ijk[3 * i] + (long long)p.NXM * s.ijk[3 * i + 1]);
     const F fx = (F)s.mij[6 * i], fy = (F)s.mij[6 * i + 1], fz = (F)s.mij[6 * i + 2];
@@ -1179,11 +1181,26 @@ __global__ void halo_p2p(int nz, int NZP, int NXM, const __grid_constant__ P2pFa
     }
 }
 
-// one warp waits for the flags of up to four faces, so that the pull kernel behind it in the stream need not spin in every block
-static __global__ void halo_wait(const unsigned int *f0, const unsigned int *f1, const unsigned int *f2, const unsigned int *f3, unsigned int seq) {
+// one warp waits for the flags of up to four faces, so that the pull kernel behind it in the stream need not spin in every block.
+// A neighbour that never pushes (it died, or left the time loop) must not leave this kernel spinning for ever: after timeout_ns
+// (0 = none) the lane gives up and raises *err, which the host reads at its next wait (stream_wait) and turns into the abort.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+static __global__ void halo_wait(const unsigned int *f0, const unsigned int *f1, const unsigned int *f2, const unsigned int *f3, unsigned int seq,
+                                 unsigned long long timeout_ns, unsigned int *err) {
     const unsigned int *f = threadIdx.x == 0 ? f0 : threadIdx.x == 1 ? f1 : threadIdx.x == 2 ? f2 : threadIdx.x == 3 ? f3 : nullptr;
-    if (f)
-        while ((int)(ld_acquire_sys(f) - seq) < 0) __nanosleep(200);
+    if (!f || *(volatile unsigned int *)err) return;   // (an earlier exchange already gave up: do not wait again)
+    const unsigned long long t0 = globaltimer_ns();
+    while ((int)(ld_acquire_sys(f) - seq) < 0) {
+        __nanosleep(200);
+        if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) {
+            atomicExch(err, 1u + threadIdx.x);
+            return;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -118,6 +118,27 @@ def test_single_precision_kernel_variants(tmp_path, variant, nz, abc):
     _compare(o, devs, exact=True)
 
 
+def test_many_sources_asynchronous_upload(tmp_path):
+    # 40 sources in distinct cells: their host-evaluated moment rates reach the device through the pinned ring (17..256 sources;
+    # up to 16 ride in the kernel parameters), 70 steps through swpc3d_run so that the 32-slot ring wraps twice
+    rng = np.random.default_rng(7)
+    src, seen = [], set()
+    while len(src) < 40:
+        x, y, z = rng.uniform(-8, 8), rng.uniform(-6, 6), rng.uniform(2.5, 12.0)
+        key = (int(x / 0.5 + 100), int(y / 0.5 + 100), int(z / 0.5))
+        if any((key[0] + a, key[1] + b, key[2] + c) in seen for a in (-1, 0, 1) for b in (-1, 0, 1) for c in (-1, 0, 1)):
+            continue                                  # the 4-node shear stencils must not overlap (atomics: free summation order)
+        seen.add(key)
+        src.append(f"{x:.3f} {y:.3f} {z:.3f} {rng.uniform(0, 0.3):.3f} {rng.uniform(0.3, 0.8):.3f} 1e15 " + " ".join(f"{v:.3f}" for v in rng.uniform(-1, 1, 6)))
+    inf = write_case(tmp_path, nt=70, sources=src)
+    o = Oracle(inf, base_dir=tmp_path, nm=3)
+    d = device_from_oracle(o, 0, device=0)
+    o.run(1, 70)
+    d.run(1, 70)
+    d.sync()
+    _compare(o, [d], exact=True)
+
+
 def test_step_entry_point_and_run(tmp_path):
     inf = write_case(tmp_path, nt=24, sources=["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8"])
     o = Oracle(inf, base_dir=tmp_path, nm=3)

@@ -44,3 +44,18 @@ def test_psv_nccl(tmp_path, n):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count(" psv ok:") == n
+
+
+@pytest.mark.parametrize("p2p", [1, 0])
+def test_a_silent_neighbour_is_detected(tmp_path, p2p):
+    """Failure detection (the reference aborts cleanly, m_report.f90:144-151): rank 1 stops taking part after 12
+    steps; rank 0's time loop must return an error within the communication time-out (4 s here) -- through the bounded spin of
+    halo_wait (peer-to-peer transport) or the stream poll + ncclCommAbort (NCCL transport) -- instead of hanging."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29000 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "mgpu_fail_worker.py"), str(tmp_path), str(p2p)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert "rank 0 aborted cleanly" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+    assert "rank 1 left the loop" in p.stdout
