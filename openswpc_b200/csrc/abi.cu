@@ -14,9 +14,12 @@
 #include <nccl.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <chrono>
 #include <functional>
 #include <thread>
@@ -28,6 +31,10 @@ using namespace swpc;
 static thread_local std::string g_err;
 extern "C" const char *swpc3d_last_error(void) { return g_err.c_str(); }
 extern "C" const char *swpc3d_version(void) { return "swpc3d_b200 0.1 (reference: OpenSWPC 25.05.2 swpc_3d)"; }
+
+// development aid: SWPC3D_TRACE=1 prints where the host is (stderr), for diagnosing hangs
+static bool g_trace = getenv("SWPC3D_TRACE") != nullptr;
+#define TRACE(...) do { if (g_trace) { fprintf(stderr, "[swpc3d %d] ", (int)getpid()); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
 
 static int fail(const std::string &m) {
     g_err = m;
@@ -278,13 +285,30 @@ static int poll_wait(swpc3d_handle *h, Query query) {
             const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             const bool timeout = h->comm_timeout_s > 0 && waited > (double)h->comm_timeout_s;
             if (qr != ncclSuccess || (ar != ncclSuccess && ar != ncclInProgress) || timeout) {
+                TRACE("poll_wait: giving up after %.1f s (qr %d ar %d): aborting the communicators", waited, (int)qr, (int)ar);
                 char b[384];
                 snprintf(b, sizeof(b), "halo exchange aborted on rank %d: %s (waited %.1f s); communicator destroyed with ncclCommAbort",
                          h->comm_rank, timeout ? "time-out, a neighbour rank stopped exchanging" : g_nccl.GetErrorString(qr != ncclSuccess ? qr : ar), waited);
-                if (h->comm_io && g_nccl.CommAbort) { g_nccl.CommAbort(h->comm_io); h->comm_io = nullptr; }
-                if (h->comm && g_nccl.CommAbort) g_nccl.CommAbort(h->comm);
+                // ncclCommAbort can itself block while a kernel of the communicator sits on the device waiting for the lost peer:
+                // abort from a helper thread and give it a few seconds; the error is returned to the caller either way
+                {
+                    ncclComm_t c0 = h->comm, c1 = h->comm_io;
+                    auto abort_fn = g_nccl.CommAbort;
+                    auto done = std::make_shared<std::atomic<int>>(0);
+                    std::thread([c0, c1, abort_fn, done]() {
+                        if (abort_fn) {
+                            if (c0) abort_fn(c0);
+                            if (c1) abort_fn(c1);
+                        }
+                        done->store(1);
+                    }).detach();
+                    for (int q = 0; q < 100 && !done->load(); q++) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+                    TRACE("poll_wait: abort %s", done->load() ? "completed" : "still running in its helper thread");
+                }
                 h->comm = nullptr;
+                h->comm_io = nullptr;
                 h->comm_dead = true;
+                TRACE("poll_wait: communicators aborted");
                 return fail(b);
             }
             if (waited > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));
@@ -496,7 +520,12 @@ static int create_state(swpc3d_handle *h, const swpc3d_grid *g, const float *ts)
 
 extern "C" int swpc3d_destroy(swpc3d_handle *h) {
     if (!h) return 0;
+    TRACE("destroy");
     cudaSetDevice(h->dev);
+    if (h->comm_dead) {   // after a communication failure kernels may still sit on the device waiting for the lost peer: every
+        delete h;         // cudaFree would wait for them.  The caller is about to stop (m_report.f90:144-151); the context goes with the process.
+        return 0;
+    }
     cudaDeviceSynchronize();
     for (int f = 0; f < 4; f++)
         if (h->p2p_peer[f]) cudaIpcCloseMemHandle(h->p2p_peer[f]);
@@ -1785,6 +1814,7 @@ extern "C" int swpc3d_get_wav_product(swpc3d_handle *h, int32_t which, float *ou
 
 extern "C" int swpc3d_vmax(swpc3d_handle *h, float out[3]) {
     if (ready(h)) return 1;
+    TRACE("vmax");
     const swpc3d_grid &g = h->g;
     const int margin = 5;
     const int i0 = std::max(g.na + margin + 1, g.ibeg_k), i1 = std::min(g.nx - g.na - margin, g.iend_k);
@@ -2226,6 +2256,7 @@ static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr
         }
         return 0;
     }
+    TRACE("comm_exchange which=%d n=%u", which, h->nccl_n);
     {   // bound the host's run-ahead: exchange n is only issued once exchange n-4 has completed (polled with the failure checks)
         cudaEvent_t &ev = h->nccl_ev[h->nccl_n & 3];
         if (!ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -2241,6 +2272,7 @@ static int comm_exchange(swpc3d_handle *h, int which, cudaStream_t st_ = nullptr
         h->halo_bytes += (double)(face_count(h, L.send[f], f) * (size_t)h->fb);
     }
     NK(g_nccl.GroupEnd());
+    TRACE("comm_exchange group issued");
     if (h->fb == 8 ? launch_halo<double>(h, L, false, st_) : launch_halo<float>(h, L, false, st_)) return 1;
     CK(cudaEventRecord(h->nccl_ev[h->nccl_n & 3], st_));
     h->nccl_n++;

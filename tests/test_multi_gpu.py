@@ -56,6 +56,6 @@ def test_a_silent_neighbour_is_detected(tmp_path, p2p):
     port = 29000 + os.getpid() % 300
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(ROOT / "tests" / "mgpu_fail_worker.py"), str(tmp_path), str(p2p)]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=90)
     assert "rank 0 aborted cleanly" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
     assert "rank 1 left the loop" in p.stdout
