@@ -1443,12 +1443,10 @@ static int launch_vel_nm(swpc3d_handle *h, const KParams<F> &p, const Region &rg
         dim3 grd((unsigned)((in.k1 + h->tk - 1) / h->tk), (unsigned)((in.li1 - in.li0 + 1 + h->ti - 1) / h->ti), (unsigned)((in.lj1 - in.lj0 + 1 + jlen - 1) / jlen));
         if (side_streams(h)) CK(cudaEventRecord(h->ev_fork, h->st));
         bool pair = false;
-        if constexpr (sizeof(F) == 4) {   // float32 fields: two cells per thread, 64-bit loads
-            if (h->ring_pair) {
-                pair = true;
-                grd.x = (unsigned)((in.k1 + 2 * h->tk - 1) / (2 * h->tk));
-                vel_ring2<F><<<grd, blk, 0, main_stream(h)>>>(p, in, jlen, h->ring_pf);
-            }
+        if ((sizeof(F) == 4 && h->ring_pair) || (sizeof(F) == 8 && h->ring_pair >= 2)) {   // two cells per thread, 64 / 128-bit loads
+            pair = true;
+            grd.x = (unsigned)((in.k1 + 2 * h->tk - 1) / (2 * h->tk));
+            vel_ring2<F><<<grd, blk, 0, main_stream(h)>>>(p, in, jlen, h->ring_pf);
         }
         if (!pair) vel_ring<F><<<grd, blk, 0, main_stream(h)>>>(p, in, jlen, h->ring_pf);
         h->launches++;
@@ -2434,7 +2432,7 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "tma_pl")) { if (value < 1) return fail("tma_pl must be >= 1"); h->tma_pl = value; }
     else if (!strcmp(key, "vel_ring")) h->use_ring = value;
     else if (!strcmp(key, "flat_bottom")) h->flat_bottom = value != 0;
-    else if (!strcmp(key, "ring_pair")) h->ring_pair = value != 0;
+    else if (!strcmp(key, "ring_pair")) h->ring_pair = value;
     else if (!strcmp(key, "overlap")) h->overlap = value != 0;
     else if (!strcmp(key, "split_test")) h->split_test = value != 0;
     else if (!strcmp(key, "slab_x")) { if (value < 2) return fail("slab_x must be >= 2"); h->slab_x = value; }

@@ -717,8 +717,9 @@ struct AccVelPair {
 template <typename T2, typename T> __device__ __forceinline__ T2 ld2ro(const T *ptr) { return __ldg(reinterpret_cast<const T2 *>(ptr)); }
 template <typename T2, typename T> __device__ __forceinline__ T2 ld2cs(const T *ptr) { return __ldcs(reinterpret_cast<const T2 *>(ptr)); }
 
+// (float64 fields: the pair's neighbour registers need more than 128 registers -- one block of 256 threads per SM, option ring_pair = 2)
 template <typename F>
-__global__ void __launch_bounds__(SWPC_RING_THREADS, SWPC_RING_MINB) vel_ring2(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
+__global__ void __launch_bounds__(SWPC_RING_THREADS, (sizeof(F) == 8 ? 1 : SWPC_RING_MINB)) vel_ring2(const __grid_constant__ KParams<F> p, const Box3 b, int jlen, int pf) {
     using F2 = typename Vec2<F>::T;
     const int k = b.k0 + 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // b.k0 is odd: index k + KOFF - 1 is even, 2-element loads are aligned
     const int li = b.li0 + blockIdx.y * blockDim.y + threadIdx.y;
