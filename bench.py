@@ -731,6 +731,9 @@ def main():
         mx = sm = stats
     mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
     run.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
