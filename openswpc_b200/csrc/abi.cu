@@ -124,6 +124,10 @@ struct swpc3d_handle {
     int *kbeg_a = nullptr, *kob = nullptr, *kfs = nullptr;
     std::vector<int> h_kbeg_a;
     std::vector<long long> h_aoff;         // host copy of aoff (per owned column)
+    // ADE columns of the bottom rows (kbeg_a > 1) are PACKED: stride = their 20-odd elements rounded up to 4, not to 32 -- a tile's aux
+    // box is then one contiguous run of whole 64-byte pieces instead of 80 used bytes per 128-byte line.  (SWPC3D_AUX_PACK=0: the
+    // round-1 layout that keeps lane = (k-1) mod 32, for comparison.)
+    bool aux_pack = true;
     std::vector<struct PmlPlan *> pml[2];  // [stress | velocity]: TMA-staged absorber shell (pml_tma.cuh), one plan per region swept (whole box, core, boundary slabs)
     struct TmaPlan *tplan[2] = {};         // [whole | core region]: work lists of the persistent interior stress kernel (stress_tma_p)
     int tma_persist = 0;                   // option "tma_persist": 1 = stress_tma_p (persistent blocks, ticket counter) instead of one block per 16-plane chunk; measured slower
@@ -338,6 +342,12 @@ static void pml_drop(swpc3d_handle *h);
 static void tplan_drop(swpc3d_handle *h);
 static void bot_drop(swpc3d_handle *h);
 
+// the aux allocation of a column whose first element is k = kb: `lead` unused elements, then nz - kb + 1 values, `klen` elements in all
+static inline int aux_lead(const swpc3d_handle *h, int kb) { return (h->aux_pack && kb > 1) ? (kb - 1) % 4 : (kb - 1) & 31; }
+static inline long long aux_klen(const swpc3d_handle *h, int kb) {
+    const long long n = aux_lead(h, kb) + (h->g.nz - kb + 1);
+    return (h->aux_pack && kb > 1) ? (n + 3) / 4 * 4 : (n + 31) / 32 * 32;
+}
 static inline cudaStream_t main_stream(const swpc3d_handle *h) { return h->cur ? h->cur : h->st; }
 static inline bool side_streams(const swpc3d_handle *h) { return h->use_side && !h->cur; }
 static inline long long col_of(const swpc3d_handle *h, int mi, int mj) { return (long long)mi + (long long)h->NXM * mj; }
@@ -422,6 +432,7 @@ extern "C" int swpc3d_create(const swpc3d_grid *g, const float *ts, swpc3d_handl
     swpc3d_handle *h = new swpc3d_handle();
     h->g = *g;
     h->dev = g->device >= 0 ? g->device : (g->myid % ndev);   // m_global.f90:208-214
+    if (const char *e = getenv("SWPC3D_AUX_PACK")) h->aux_pack = atoi(e) != 0;
     const int rc = create_state(h, g, ts);
     if (rc) {   // e.g. out of device memory half way: give everything back, keep the message
         const std::string msg = swpc3d_last_error();
@@ -696,10 +707,11 @@ extern "C" int swpc3d_setup_pml(swpc3d_handle *h, const float *gxc, const float 
         for (int li = 0; li < h->nxp; li++) {
             const int kb = h->h_kbeg_a[(size_t)(li + HALO) + (size_t)h->NXM * (lj + HALO)];
             const int len_k = h->g.nz - kb + 1;
-            // keep the column's lane phase: element k sits at off + (k - kb) with off = 32*q + ((kb-1) & 31)
-            const int phase = (kb - 1) & 31;
-            aoff[(size_t)li + (size_t)h->nxp * lj] = off + phase;
-            off += ((phase + len_k) + 31) / 32 * 32;
+            // wall columns keep their lane phase: element k sits at off + (k - kb) with off = 32*q + ((kb-1) & 31); the short columns
+            // of the bottom rows are packed (aux_lead / aux_klen)
+            (void)len_k;
+            aoff[(size_t)li + (size_t)h->nxp * lj] = off + aux_lead(h, kb);
+            off += aux_klen(h, kb);
         }
     h->naux = off;
     h->h_aoff = aoff;
@@ -1038,8 +1050,8 @@ static int pml_build(swpc3d_handle *h, const Region &rg, const Box3 &cols, bool 
         const int shift = (kb - 1) % 4;                  // the boxes start at kb - shift (16-byte aligned for float arrays)
         if (ok && bottom && shift + (nz - kb + 1) > BK) ok = false;
         long long asi = 0, asj = 0;
-        const int phase = (kb - 1) & 31;
-        const long long klen = ((long long)phase + (nz - kb + 1) + 31) / 32 * 32;
+        const int phase = aux_lead(h, kb);
+        const long long klen = aux_klen(h, kb);
         if (ok) {   // every column starts at kb and the columns are regularly spaced in the aux arrays
             asi = ncols > 1 ? aoff(a0 + 1, b0) - aoff(a0, b0) : klen;
             asj = nrows_j > 1 ? aoff(a0, b0 + 1) - aoff(a0, b0) : asi * ncols;
@@ -1287,8 +1299,8 @@ static int bot_build(swpc3d_handle *h, const Box3 &cols, BotPlan *bp) {
     const int a0 = cols.li0, a1 = cols.li1, b0 = cols.lj0, b1 = cols.lj1;
     if (a1 < a0 || b1 < b0 || C::SMEM > 227 * 1024) return 0;
     const int ncols = a1 - a0 + 1, nrows_j = b1 - b0 + 1;
-    const int phase = (kb - 1) & 31;
-    const long long klen = ((long long)phase + (nz - kb + 1) + 31) / 32 * 32;
+    const int phase = aux_lead(h, kb);
+    const long long klen = aux_klen(h, kb);
     const long long asi = ncols > 1 ? aoff(a0 + 1, b0) - aoff(a0, b0) : klen;
     const long long asj = nrows_j > 1 ? aoff(a0, b0 + 1) - aoff(a0, b0) : asi * ncols;
     for (int lj = b0; lj <= b1; lj++)

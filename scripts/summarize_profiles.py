@@ -138,6 +138,9 @@ def launch_list_psv(src: Path, dst: Path, header: str):
 
 if __name__ == "__main__":
     go = ROOT / "gpurun_out"
+    if len(sys.argv) >= 5 and sys.argv[1] == "r02":   # r02 <raw ncu csv> <profiles/ name> <traffic.json key> [header line ...]
+        launch_list_r02(Path(sys.argv[2]), OUT / sys.argv[3], "".join(f"# {x}\n" for x in sys.argv[5:]), sys.argv[4])
+        sys.exit(0)
     if (go / "launches_psv_final.csv").exists():
         launch_list_psv(go / "launches_psv_final.csv", OUT / "r01_launches_psv_16384x8192.csv",
                         "# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 40 python scripts/psv_probe.py 16384,8192 3\n"

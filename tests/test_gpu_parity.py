@@ -220,6 +220,18 @@ def test_whole_line_bottom_tiles_bit_exact(tmp_path, case):
     assert np.abs(o.field(0, "Szz")[3:-3, 3:-3, -8:-3]).max() > 0 or nranks != (1, 1)   # the bottom rows have seen the wave
 
 
+@pytest.mark.parametrize("opts", [{}, {"bottom_tma": 1}, {"pml_tma": 0}])
+def test_unpacked_ade_columns_bit_exact(tmp_path, monkeypatch, opts):
+    """SWPC3D_AUX_PACK=0: the round-1 layout of the ADE arrays (every column of the bottom rows on its own 128-byte line) that the
+    packed default is measured against; na = 7 puts the columns off the 16-byte grid.  A source just above the absorber."""
+    monkeypatch.setenv("SWPC3D_AUX_PACK", "0")
+    case = dict(nx=48, ny=44, nz=64, na=7, zbeg=-3.0)
+    src = ["0.3 -0.2 4.1 0.05 0.6 1e15 0.7 -0.3 0.5 0.4 -0.6 0.8", f"-2.1 1.7 {-3.0 + (64 - 7 - 4) * 0.5} 0.10 0.5 4e14 -0.2 0.9 0.1 -0.5 0.3 0.6"]
+    o, devs = _run_pair(tmp_path / "a", 40, sources=src, options=opts, **case)
+    _compare(o, devs, exact=True)
+    assert np.abs(o.field(0, "Szz")[3:-3, 3:-3, -8:-3]).max() > 0
+
+
 @pytest.mark.parametrize("opts", [{}, {"slab_tiled": 0}, {"slab_x": 2}, {"slab_x": 5}])
 @pytest.mark.parametrize("abc,bf", [("pml", False), ("cerjan", False), ("pml", True)])
 def test_boundary_first_split_bit_exact(tmp_path, abc, bf, opts):
