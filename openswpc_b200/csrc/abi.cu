@@ -141,6 +141,7 @@ struct swpc3d_handle {
     int l2hint = 0;                        // option "l2hint": L2 eviction policy of stress_tma's TMA loads (1: centre boxes evict-first, 2: + halo boxes evict-last)
     int l2promo = 2, l2promo_halo = 2;     // options "l2promo" / "l2promo_halo": L2 promotion of stress_tma's centre / halo boxes (0 none, 1 64 B, 2 128 B, 3 256 B)
     int pml_promo = 1, pml_promo_b = 1;    // options "pml_promo" / "pml_promo_bottom": the same for pml_tma's wall / bottom items
+    int pml_promo_aux_b = -1;              // option "pml_promo_aux_bottom": the ADE map of the bottom items alone (-1: as pml_promo_bottom)
     long long *aoff = nullptr;
     float *aux = nullptr;
     long long naux = 0;
@@ -1066,7 +1067,8 @@ static int pml_build(swpc3d_handle *h, const Region &rg, const Box3 &cols, bool 
             const cuuint64_t dims[4] = {(cuuint64_t)klen, (cuuint64_t)ncols, (cuuint64_t)nrows_j, 18};
             const cuuint64_t st[3] = {(cuuint64_t)asi * 4, (cuuint64_t)asj * 4, (cuuint64_t)h->naux * 4};
             const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TI, 1, 9};
-            if (!make_map_generic(&pl->maps[cls].aux[im], h->aux + (aoff(a0, b0) - phase), 4, dims, st, box, bottom ? h->pml_promo_b : h->pml_promo)) {
+            if (!make_map_generic(&pl->maps[cls].aux[im], h->aux + (aoff(a0, b0) - phase), 4, dims, st, box,
+                                  bottom ? (h->pml_promo_aux_b >= 0 ? h->pml_promo_aux_b : h->pml_promo_b) : h->pml_promo)) {
                 nmap[cls]--;
                 pl->direct.push_back(whole);
                 return;
@@ -2462,8 +2464,9 @@ extern "C" int swpc3d_set_option(swpc3d_handle *h, const char *key, int32_t valu
     else if (!strcmp(key, "l2promo_halo")) { h->l2promo_halo = value; h->tma_ready = false; }
     else if (!strcmp(key, "pml_promo")) { h->pml_promo = value; pml_drop(h); }
     else if (!strcmp(key, "pml_promo_bottom")) { h->pml_promo_b = value; pml_drop(h); }
-    else if (!strcmp(key, "pml_jl")) { if (value < 1) return fail("pml_jl must be >= 1"); h->pml_jl = value; }
-    else if (!strcmp(key, "pml_jl_bottom")) { if (value < 1) return fail("pml_jl_bottom must be >= 1"); h->pml_jl_bottom = value; }
+    else if (!strcmp(key, "pml_promo_aux_bottom")) { h->pml_promo_aux_b = value; pml_drop(h); }
+    else if (!strcmp(key, "pml_jl")) { if (value < 1) return fail("pml_jl must be >= 1"); h->pml_jl = value; pml_drop(h); }
+    else if (!strcmp(key, "pml_jl_bottom")) { if (value < 1) return fail("pml_jl_bottom must be >= 1"); h->pml_jl_bottom = value; pml_drop(h); }
     else if (!strcmp(key, "tma_jl")) { if (value < 1) return fail("tma_jl must be >= 1"); h->tma_jl = value; }
     else if (!strcmp(key, "kernel_timing")) { h->ktiming = value != 0; h->kev_used[0] = h->kev_used[1] = 0; h->cev_used = 0; h->halo_bytes = 0.0; }
     else return fail(std::string("unknown option ") + key);
